@@ -1,0 +1,205 @@
+/* mrhyde_b200.h -- C ABI of the B200-native element residual/Jacobian assembly.
+ *
+ * This library replaces the body of MrHyDE's
+ *     AssemblyManager<Node>::assembleJacRes<EvalT>(set, ..., block)
+ *         src/managers/assembly/assemblyManager_jacres.hpp:119-630   (group loop :336-603,
+ *         gather gather.hpp:181-234, updateWorkset workset.hpp:963-1049, physics
+ *         volumeResidual/boundaryResidual physicsInterface_residual.hpp:13-216, fused scatter
+ *         scatter.hpp:162-278, dofConstraints constraints.hpp:241-270)
+ * and of assembleRes (jacres.hpp:668-875) with hand-written sm_100a kernels.  The reference host
+ * code (DOF managers, Tpetra graph/vectors, solvers, YAML) stays as it is; it hands this library
+ * the raw arrays those objects already hold.  INTEGRATION.md shows the call sites.
+ *
+ * Conventions
+ *   - every entry point returns an int status (MRHYDE_B200_OK == 0); no C++ exception crosses the
+ *     boundary; mrhyde_b200_last_error() returns the message of the last failure on this thread.
+ *   - "host" pointers are read during the call and never retained unless stated; "device" pointers
+ *     are CUDA device pointers on the plan's device.
+ *   - LO = int32_t (preferences.hpp:39-97), row_map = int64_t (KokkosSparse size_type), fp64 only.
+ *   - there is no CPU fallback: every assemble call launches the CUDA kernels or fails.
+ *   - a plan is not thread-safe (the reference is not re-entrant either: shared workset scratch,
+ *     assemblyManager_jacres.hpp:334).
+ */
+#ifndef MRHYDE_B200_H
+#define MRHYDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRHYDE_B200_OK 0
+#define MRHYDE_B200_ERR_INVALID 1     /* bad argument / inconsistent sizes                      */
+#define MRHYDE_B200_ERR_UNSUPPORTED 2 /* valid reference input this build has no kernel for       */
+#define MRHYDE_B200_ERR_PARSE 3       /* expression could not be decomposed (reference wording)   */
+#define MRHYDE_B200_ERR_CUDA 4        /* CUDA runtime / launch failure                             */
+#define MRHYDE_B200_ERR_STATE 5       /* call order violated (e.g. assemble before finalize)       */
+#define MRHYDE_B200_ERR_NCCL 6
+
+typedef struct mrhyde_b200_plan mrhyde_b200_plan; /* opaque, library-owned */
+
+/* Reference basis tabulated at the reference cubature points -- exactly what
+ * DiscretizationInterface::setReferenceBasisData stores (discretizationInterface_basis.hpp:12-133),
+ * so a MrHyDE host passes Intrepid2's own numbers.  Layouts are row-major. */
+typedef struct {
+  const char* type;      /* "HGRAD" | "HCURL" | "HDIV" | "HVOL"                                   */
+  int32_t order;
+  int32_t card;          /* basis cardinality                                                    */
+  const double* val;     /* [card][nqp][vdim]  vdim = 1 (HGRAD/HVOL) or dim (HCURL/HDIV)          */
+  const double* grad;    /* [card][nqp][dim]   HGRAD, else NULL                                  */
+  const double* curl;    /* [card][nqp][dim]   HCURL (3-D), else NULL                            */
+  const double* div;     /* [card][nqp]        HDIV, else NULL                                   */
+} mrhyde_b200_basis;
+
+/* One block of one physics set: what AssemblyManager/PhysicsInterface know after construction. */
+typedef struct {
+  const char* physics;          /* module name as in PhysicsImporter::import (physicsImporter.cpp:64-281):
+                                   "thermal" | "linearelasticity" | "navierstokes" | "maxwell"  */
+  int32_t dim;                  /* 2 | 3 ; cell topology is Quadrilateral_4 / Hexahedron_8       */
+  int32_t nvars;
+  const char* const* var_names; /* module variable order, e.g. {"ux","pr","uy","uz"}             */
+  const int32_t* var_basis;     /* [nvars] index into bases[]                                    */
+  int32_t nbases;
+  const mrhyde_b200_basis* bases;
+  int32_t ndof_elem;            /* LIDs per element                                              */
+  const int32_t* offsets;       /* [nvars][max_card], wkset->offsets (getGIDFieldOffsets), -1 padded */
+  int32_t max_card;
+  int32_t nqp;                  /* volume cubature (DefaultCubatureFactory, _construct.hpp:103-112) */
+  const double* qp_pts;         /* [nqp][dim] reference points                                   */
+  const double* qp_wts;         /* [nqp]                                                         */
+} mrhyde_b200_desc;
+
+/* Time-integration data of one assembleJacRes call (updateWorksetTime / computeSolnTransientSeeded,
+ * workset.cpp:600-834; Butcher and BDF tables solverManager_setup.hpp:181-480).  NULL = steady. */
+typedef struct {
+  double time;                  /* t_n; stage time is time + butcher_c[stage]*deltat             */
+  double deltat;
+  int32_t stage;
+  int32_t nstages;
+  const double* butcher_A;      /* host [nstages][nstages]                                       */
+  const double* butcher_b;      /* host [nstages]                                                */
+  const double* butcher_c;      /* host [nstages]                                                */
+  int32_t nbdf;                 /* number of BDF weights (order+1)                               */
+  const double* bdf_wts;        /* host [nbdf]                                                   */
+  const double* const* sol_prev;  /* host array of [nbdf-1] device vectors u_{n}, u_{n-1}, ...    */
+  const double* const* sol_stage; /* host array of [nstages] device vectors (stages < stage read) */
+} mrhyde_b200_time;
+
+/* Side data of one boundary group family (BoundaryGroup, assemblyManager_groups.hpp; reference
+ * side cubature + side-tabulated bases as produced by getPhysicalBoundaryIntegrationData,
+ * discretizationInterface_integration.hpp:592-774). */
+typedef struct {
+  int32_t sideset;              /* index into the side-name list given to set_sidesets           */
+  int32_t local_side;           /* Shards local side id of the cell                              */
+  int32_t n_elem;
+  const int32_t* elem_ids;      /* host [n_elem] element indices (as in set_mesh)                */
+  int32_t nqp_side;
+  const double* side_pts;       /* host [nqp_side][dim] side points in the CELL reference frame  */
+  const double* side_wts;       /* host [nqp_side]                                               */
+  const double* tangent_u;      /* host [3] reference side tangent(s) (getReferenceFaceTangents) */
+  const double* tangent_v;      /* host [3]                                                      */
+  const mrhyde_b200_basis* side_bases; /* [nbases] tables at side_pts (val/grad)                 */
+} mrhyde_b200_boundary_group;
+
+const char* mrhyde_b200_version(void);
+const char* mrhyde_b200_last_error(void);
+
+/* ---- plan construction (host side, once per block/set) -------------------------------------- */
+int mrhyde_b200_plan_create(mrhyde_b200_plan** plan, const mrhyde_b200_desc* desc, int device);
+void mrhyde_b200_plan_destroy(mrhyde_b200_plan* plan);
+
+/* `Functions:` sublist entry, reference grammar (functionManager_create.hpp:78-540, interpreter.cpp).
+ * Module defaults (e.g. thermal.cpp:47-65) are registered by the library; user entries override. */
+int mrhyde_b200_plan_set_function(mrhyde_b200_plan* plan, const char* name, const char* expression);
+
+/* Module / solver flags by their YAML key ("useSUPG", "usePSPG", "form_param", "include advection",
+ * "use strong DBCs", "assemble boundary terms", ...) plus library keys:
+ *   "ns3d_uz_rows" = "reference" | "corrected"   (navierstokes.cpp:688)
+ *   "accumulate"   = "true" (reference contract: sum into caller-zeroed res/J) | "false" (overwrite)
+ * Unknown keys are an error, never silently ignored. */
+int mrhyde_b200_plan_set_option(mrhyde_b200_plan* plan, const char* key, const char* value);
+
+/* Element data of the block: Group::nodes / Group::LIDs for every element, group order
+ * (assemblyManager_groups.hpp:413-426).  elem_nodes[n_elem][nverts][dim], lids[n_elem][ndof_elem],
+ * orient_sign[n_elem][ndof_elem] (+1/-1 per dof after Intrepid2 orientation; NULL = all +1). */
+int mrhyde_b200_plan_set_mesh(mrhyde_b200_plan* plan, int64_t n_elem, const double* elem_nodes,
+                              const int32_t* lids, const int8_t* orient_sign);
+/* Same, from a vertex table + connectivity (skips the coordinate de-duplication). */
+int mrhyde_b200_plan_set_mesh_indexed(mrhyde_b200_plan* plan, int64_t n_verts, const double* vert_coords /*[n_verts][dim]*/,
+                                      int64_t n_elem, const int32_t* conn /*[n_elem][nverts]*/,
+                                      const int32_t* lids, const int8_t* orient_sign);
+
+/* The overlapped CrsGraph of J (J->getLocalMatrixDevice().graph, jacres.hpp:145-151) and the
+ * isFixedDOF mask (assemblyManager_constraints.hpp:13-92).  n_owned <= n_rows: rows [n_owned,n_rows)
+ * are ghost rows (overlapped_map = owned then ghosted, discretizationInterface_dof.hpp:129-137). */
+int mrhyde_b200_plan_set_graph(mrhyde_b200_plan* plan, int64_t n_rows, int64_t n_owned, const int64_t* row_map,
+                               const int32_t* entries, const uint8_t* is_fixed_dof);
+
+/* Boundary conditions: side names, then per (variable, sideset) a type
+ * "none" | "Dirichlet" | "weak Dirichlet" | "Neumann" and the data expression. */
+int mrhyde_b200_plan_set_sidesets(mrhyde_b200_plan* plan, int32_t n_sides, const char* const* side_names);
+int mrhyde_b200_plan_set_bc(mrhyde_b200_plan* plan, const char* var, const char* side, const char* type, const char* expression);
+int mrhyde_b200_plan_add_boundary_group(mrhyde_b200_plan* plan, const mrhyde_b200_boundary_group* bg);
+
+/* Builds patches, scatter programs and compiled expressions and uploads them. */
+int mrhyde_b200_plan_finalize(mrhyde_b200_plan* plan);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* assembleJacRes (jacres.hpp:119-630): res += -F(u) on free rows, jac_values += dF/du on free rows,
+ * J(d,d) = 1 on strong-Dirichlet rows when compute_jacobian (dofConstraints).  With option
+ * accumulate=false the outputs are overwritten instead (caller need not zero them).
+ * sol/res: [n_rows]; jac_values: [nnz] in the order of `entries`.  `stream` is a cudaStream_t. */
+int mrhyde_b200_assemble_jacres(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t,
+                                int compute_jacobian, int compute_residual, double* res, double* jac_values,
+                                void* stream);
+/* assembleRes (jacres.hpp:668-875): residual only (the ScalarT workset path). */
+int mrhyde_b200_assemble_res(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, double* res,
+                             void* stream);
+/* Same as assemble_jacres but sol/res/jac_values (and t->sol_prev/sol_stage) are HOST buffers:
+ * copies in, assembles, copies out, synchronises. */
+int mrhyde_b200_assemble_jacres_host(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t,
+                                     int compute_jacobian, int compute_residual, double* res, double* jac_values);
+
+/* ---- multi-GPU: the Tpetra Export(overlapped -> owned, ADD) replacement ---------------------------
+ * (linearAlgebraInterface_matrix.hpp:233-237, _vector.hpp:56-66).  Ghost rows of this rank are summed
+ * into the owning rank's rows in fixed neighbour-rank order. */
+int mrhyde_b200_comm_unique_id(uint8_t* id128);                      /* ncclGetUniqueId, 128 bytes */
+int mrhyde_b200_plan_comm_init(mrhyde_b200_plan* plan, const uint8_t* id128, int rank, int nranks);
+/* Global ids of this rank's rows (owned then ghost); collective over the communicator. */
+int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* plan, const int64_t* row_gids /*host [n_rows]*/);
+int mrhyde_b200_halo_sum(mrhyde_b200_plan* plan, double* res, double* jac_values, void* stream);
+
+/* ---- introspection (tests, bench) ----------------------------------------------------------- */
+/* keys: "n_patches" "n_templates" "kernel_launches_per_assemble" "smem_bytes" "threads_per_block"
+ *       "n_elem" "n_elem_with_halo" "n_rows" "nnz" "plan_device_bytes" "n_affine"               */
+int mrhyde_b200_plan_stat(mrhyde_b200_plan* plan, const char* key, int64_t* value);
+/* Average device time (ms, CUDA events on the launch stream) of the volume kernel over the
+ * assemble calls since the last reset; used by bench.py for the roofline figure. */
+int mrhyde_b200_plan_kernel_time(mrhyde_b200_plan* plan, int reset, double* avg_ms, int64_t* n_launches);
+/* Evaluates a registered function at points (host), through the device expression kernel. */
+int mrhyde_b200_plan_eval_function(mrhyde_b200_plan* plan, const char* name, int64_t npts, const double* xyz /*host [npts][3]*/,
+                                   double time, double* out /*host [npts]*/);
+
+/* ---- host-side analysis hooks (no GPU needed; used by the CPU test-suite) ---------------------------
+ * A plan created with device = -1 is "host only": set-up and finalize run the full plan analysis
+ * (expression compilation, affine classification, patches, scatter programs) but nothing is
+ * uploaded and every assemble call fails with MRHYDE_B200_ERR_STATE. */
+/* Compiles `which` out of n (name, expression) pairs and writes the flattened program as text. */
+int mrhyde_b200_expr_disassemble(int32_t n, const char* const* names, const char* const* exprs, const char* which,
+                                 char* out, size_t out_cap);
+/* Runs the same flattened program on the host at vars = {x,y,z,t,n[x],n[y],n[z]} (checks of the
+ * compiler against the reference grammar; the kernels never call this). */
+int mrhyde_b200_expr_eval_host(int32_t n, const char* const* names, const char* const* exprs, const char* which,
+                               int64_t npts, const double* vars7, double* out);
+/* Applies the plan's scatter programs on the host to caller-supplied staged element vectors
+ * stage[n_elem][stage_len] (local Jacobian entries then residual entries), with the
+ * same ordering and fixed-row rules as the device pull-scatter.  Verifies plan logic only. */
+int mrhyde_b200_plan_debug_scatter_host(mrhyde_b200_plan* plan, const double* stage, int64_t stage_len, int accumulate,
+                                        double* res, double* jac_values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRHYDE_B200_H */

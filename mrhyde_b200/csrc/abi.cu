@@ -1,0 +1,868 @@
+// C ABI of the assembly library (include/mrhyde_b200.h): plan object, option/function registry,
+// upload of the plan to the device, kernel dispatch.  No CPU fallback exists: if no CUDA device or
+// no kernel matches the described block the call fails with an error code.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mrhyde_b200.h"
+#include "boundary.cuh"
+#include "expr.hpp"
+#include "expr_device.cuh"
+#include "halo.hpp"
+#include "plan.hpp"
+#include "thermal.cuh"
+
+using namespace mrhyde_b200;
+
+namespace {
+
+thread_local std::string g_error;
+
+struct AbiError {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const std::string& msg) { throw AbiError{code, msg}; }
+
+#define CUDA_OK(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess) fail(MRHYDE_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+#define ABI_BEGIN try {
+#define ABI_END                                                                  \
+  return MRHYDE_B200_OK;                                                         \
+  }                                                                              \
+  catch (const AbiError& e) { g_error = e.msg; return e.code; }                  \
+  catch (const ExprError& e) { g_error = e.what(); return e.code; }              \
+  catch (const std::exception& e) { g_error = e.what(); return MRHYDE_B200_ERR_INVALID; } \
+  catch (...) { g_error = "unknown failure"; return MRHYDE_B200_ERR_INVALID; }
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void upload(const std::vector<T>& h, size_t* total) {
+    if (p) { cudaFree(p); p = nullptr; }
+    n = h.size();
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CUDA_OK(cudaMalloc(&p, bytes));
+    if (n) CUDA_OK(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+    if (total) *total += bytes;
+  }
+  void resize(size_t count, size_t* total) {
+    if (count <= n && p) return;
+    if (p) { cudaFree(p); p = nullptr; }
+    n = count;
+    CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    if (total) *total += n * sizeof(T);
+  }
+};
+
+struct BasisCopy {
+  std::string type;
+  int order = 1, card = 0;
+  std::vector<double> val, grad, curl, div;
+};
+
+struct BCEntry {
+  std::string type = "none", expr = "0.0";
+};
+
+}  // namespace
+
+struct mrhyde_b200_plan {
+  int device = 0;
+  // description
+  std::string physics;
+  int dim = 3, nvars = 0, ndof_elem = 0, max_card = 0, nqp = 0;
+  std::vector<std::string> var_names;
+  std::vector<int> var_basis;
+  std::vector<BasisCopy> bases;
+  std::vector<int32_t> offsets;
+  std::vector<double> qp_pts, qp_wts;
+  // registry
+  std::map<std::string, std::string> functions, options;
+  std::vector<std::string> side_names;
+  std::map<std::pair<std::string, std::string>, BCEntry> bcs;  // (var, side)
+  std::vector<BoundaryGroupHost> bgroups;
+  // mesh / graph
+  MeshGraph mesh;
+  bool have_mesh = false, have_graph = false, finalized = false;
+  PatchPlan pp;
+  // device copies
+  size_t dev_bytes = 0;
+  DevBuf<double> d_vx, d_vy, d_vz;
+  DevBuf<int32_t> d_conn, d_lids, d_colind, d_patch_elem_ptr, d_patch_elems, d_patch_row_ptr, d_patch_rows, d_patch_tmpl, d_orphans, d_fixed_rows;
+  DevBuf<int64_t> d_rowptr, d_fixed_diag;
+  DevBuf<uint8_t> d_fixed, d_affine;
+  DevBuf<TemplateHeader> d_tmpl;
+  DevBuf<uint16_t> d_slot_row, d_slot_k, d_csrc;
+  DevBuf<uint32_t> d_cptr;
+  // host-buffer entry point scratch
+  DevBuf<double> h_sol, h_res, h_jac;
+  std::vector<DevBuf<double>> h_prev, h_stage;
+  // kernels
+  ThermalParams<2> th2;
+  ThermalParams<3> th3;
+  BoundaryPlan boundary;
+  int threads = 256;
+  size_t smem = 0;
+  int64_t n_affine = 0;
+  int launches_per_assemble = 0;
+  bool accumulate = true;
+  int stage_len = 0;
+  std::vector<uint16_t> kmap, rmap;
+  // timing of the volume kernel
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t ev_next = 0, ev_used = 0;
+  double ev_ms = 0.0;
+  int64_t ev_count = 0;
+  // halo
+  std::unique_ptr<HaloExchange> halo;
+
+  ~mrhyde_b200_plan() {
+    for (auto& p : ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  }
+};
+
+namespace {
+
+const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "patch elements", "threads", "use leap frog", nullptr};
+
+std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
+  auto it = P->options.find(key);
+  return it == P->options.end() ? def : it->second;
+}
+bool opt_bool(const mrhyde_b200_plan* P, const std::string& key, bool def) {
+  const std::string v = opt(P, key, def ? "true" : "false");
+  return v == "true" || v == "True" || v == "1";
+}
+
+// Hex8 / Quad4 nodal shape functions in Shards vertex order (CellTools::setJacobian uses the cell's
+// HGRAD C1 basis; discretizationInterface_basis.hpp:244-252, 407-413)
+void geom_shape(int dim, const double* xi, double* N, double* dN) {
+  static const double sg[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+  const int nv = 1 << dim;
+  for (int n = 0; n < nv; ++n) {
+    double f[3] = {1, 1, 1}, df[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d) { f[d] = 0.5 * (1.0 + sg[n][d] * xi[d]); df[d] = 0.5 * sg[n][d]; }
+    N[n] = f[0] * f[1] * (dim == 3 ? f[2] : 1.0);
+    for (int d = 0; d < dim; ++d) {
+      double g = df[d];
+      for (int o = 0; o < dim; ++o) if (o != d) g *= f[o];
+      dN[n * dim + d] = g;
+    }
+  }
+}
+
+template <int DIM>
+void fill_thermal_tables(const mrhyde_b200_plan* P, ThermalTables<DIM>& T) {
+  typedef Q1Shape<DIM> S;
+  const BasisCopy& B = P->bases[P->var_basis[0]];
+  std::memset(&T, 0, sizeof(T));
+  for (int q = 0; q < S::NQ; ++q) {
+    double N[8], dN[24];
+    geom_shape(DIM, &P->qp_pts[(size_t)q * DIM], N, dN);
+    T.qw[q] = P->qp_wts[q];
+    for (int d = 0; d < DIM; ++d) T.qpt[q][d] = P->qp_pts[(size_t)q * DIM + d];
+    for (int n = 0; n < S::NV; ++n) {
+      T.gN[q][n] = N[n];
+      T.phi[q][n] = B.val[(size_t)n * S::NQ + q];
+      for (int d = 0; d < DIM; ++d) {
+        T.gdN[q][n][d] = dN[n * DIM + d];
+        T.dphi[q][n][d] = B.grad[((size_t)n * S::NQ + q) * DIM + d];
+      }
+    }
+  }
+  int pa[S::NG], pb[S::NG], g = 0;
+  for (int a = 0; a < DIM; ++a) { pa[g] = a; pb[g] = a; ++g; }
+  for (int a = 0; a < DIM; ++a) for (int b = a + 1; b < DIM; ++b) { pa[g] = a; pb[g] = b; ++g; }
+  for (int i = 0; i < S::NV; ++i)
+    for (int j = i; j < S::NV; ++j) {
+      const int t = i * S::NV - (i * (i - 1)) / 2 + (j - i);
+      double m = 0.0;
+      for (int q = 0; q < S::NQ; ++q) m += T.qw[q] * T.phi[q][i] * T.phi[q][j];
+      T.Mtab[t] = m;
+      for (int k = 0; k < S::NG; ++k) {
+        double s = 0.0;
+        for (int q = 0; q < S::NQ; ++q) {
+          if (pa[k] == pb[k]) s += T.qw[q] * T.dphi[q][i][pa[k]] * T.dphi[q][j][pa[k]];
+          else s += T.qw[q] * (T.dphi[q][i][pa[k]] * T.dphi[q][j][pb[k]] + T.dphi[q][i][pb[k]] * T.dphi[q][j][pa[k]]);
+        }
+        T.Stab[k][t] = s;
+      }
+    }
+}
+
+FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side) {
+  FunctionSet fs;
+  // module defaults (thermal::defineFunctions, thermal.cpp:47-65), then user overrides
+  if (P->physics == "thermal") {
+    fs.set("thermal source", "0.0");
+    fs.set("thermal diffusion", "1.0");
+    fs.set("specific heat", "1.0");
+    fs.set("density", "1.0");
+    fs.set("advection x", "0.0"); fs.set("advection y", "0.0"); fs.set("advection z", "0.0");
+    fs.set("robin alpha", "0.0");
+  }
+  for (auto& kv : P->functions) fs.set(kv.first, kv.second);
+  std::vector<std::string> sol;
+  static const char* comps[3] = {"[x]", "[y]", "[z]"};
+  for (auto& v : P->var_names) {
+    sol.push_back(v); sol.push_back(v + "_t");
+    for (int d = 0; d < 3; ++d) {
+      sol.push_back("grad(" + v + ")" + comps[d]);
+      sol.push_back(v + comps[d]); sol.push_back(v + "_t" + comps[d]);
+      sol.push_back("curl(" + v + ")" + comps[d]);
+    }
+    sol.push_back("div(" + v + ")");
+  }
+  fs.set_solution_fields(sol);
+  if (side) fs.set_scalar_fields({"x", "y", "z", "", "n[x]", "n[y]", "n[z]"});
+  else fs.set_scalar_fields({"x", "y", "z"});
+  // boundary data functions at side ip: "Dirichlet <var> <side>" / "Neumann <var> <side>"
+  if (side)
+    for (auto& kv : P->bcs) {
+      const BCEntry& b = kv.second;
+      if (b.type == "weak Dirichlet" || b.type == "Dirichlet") fs.set("Dirichlet " + kv.first.first + " " + kv.first.second, b.expr);
+      else if (b.type == "Neumann") fs.set("Neumann " + kv.first.first + " " + kv.first.second, b.expr);
+    }
+  return fs;
+}
+
+__global__ void eval_points_kernel(const __grid_constant__ ExprProgram prog, const double* __restrict__ xyz, double time, int64_t n, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ExprVars in;
+  in.v[0] = xyz[3 * i]; in.v[1] = xyz[3 * i + 1]; in.v[2] = xyz[3 * i + 2]; in.v[3] = time; in.v[4] = in.v[5] = in.v[6] = 0.0;
+  out[i] = expr_eval(prog, in);
+}
+
+__global__ void orphan_rows_kernel(const int32_t* __restrict__ rows, int n, GraphDev G, OutDev O) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t r = rows[i];
+  if (O.res) O.res[r] = 0.0;
+  if (O.jac)
+    for (int64_t p = G.rowptr[r]; p < G.rowptr[r + 1]; ++p) O.jac[p] = (G.fixed[r] && G.colind[p] == r) ? 1.0 : 0.0;
+}
+
+// dofConstraints -> setJacobianConstraints: J(d,d) = 1 on strong-Dirichlet dofs (replaceLocalValues)
+__global__ void fixed_diag_kernel(const int64_t* __restrict__ diag, int n, double* __restrict__ jac) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && diag[i] >= 0) jac[diag[i]] = 1.0;
+}
+
+void fill_time(const mrhyde_b200_time* t, TimeDev& td, bool device_ptrs_ok) {
+  std::memset(&td, 0, sizeof(td));
+  td.alpha_u = 1.0;
+  if (!t) return;
+  td.time = t->time;
+  if (t->nstages <= 0) return;  // steady evaluation at a given time
+  if (t->stage < 0 || t->stage >= t->nstages || t->nstages > MAX_STAGE) fail(MRHYDE_B200_ERR_INVALID, "time: stage index / stage count out of range");
+  if (t->nbdf < 2 || t->nbdf - 1 > MAX_PREV) fail(MRHYDE_B200_ERR_INVALID, "time: unsupported number of BDF weights");
+  if (!t->butcher_A || !t->butcher_b || !t->butcher_c || !t->bdf_wts || !t->sol_prev) fail(MRHYDE_B200_ERR_INVALID, "time: missing tables");
+  const int s = t->stage, ns = t->nstages;
+  td.transient = 1;
+  td.alpha_u = t->butcher_A[s * ns + s] / t->butcher_b[s];
+  td.one_minus_alpha_u = 1.0 - td.alpha_u;
+  td.timewt = 1.0 / t->deltat / t->butcher_b[s];
+  td.alpha_t = t->bdf_wts[0] * td.timewt;
+  td.nprev = t->nbdf - 1;
+  for (int k = 1; k < t->nbdf; ++k) td.bdf[k] = t->bdf_wts[k];
+  td.nstage_lo = s;
+  for (int k = 0; k < s; ++k) td.stage_w[k] = t->butcher_A[s * ns + k] / t->butcher_b[k];
+  td.time = t->time + t->butcher_c[s] * t->deltat;
+  if (device_ptrs_ok) {
+    for (int k = 0; k < td.nprev; ++k) { td.prev[k] = t->sol_prev[k]; if (!td.prev[k]) fail(MRHYDE_B200_ERR_INVALID, "time: null sol_prev vector"); }
+    if (s > 0 && !t->sol_stage) fail(MRHYDE_B200_ERR_INVALID, "time: missing sol_stage");
+    for (int k = 0; k < s; ++k) { td.stg[k] = t->sol_stage[k]; if (!td.stg[k]) fail(MRHYDE_B200_ERR_INVALID, "time: null sol_stage vector"); }
+  }
+}
+
+constexpr size_t EV_RING = 64;
+void fold_oldest(mrhyde_b200_plan* P) {
+  auto& pr = P->ev[P->ev_next];
+  CUDA_OK(cudaEventSynchronize(pr.second));
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+  P->ev_ms += ms; ++P->ev_count;
+  P->ev_next = (P->ev_next + 1) % EV_RING; --P->ev_used;
+}
+void record_begin(mrhyde_b200_plan* P, cudaStream_t st, size_t& slot) {
+  if (P->ev.empty())
+    for (size_t i = 0; i < EV_RING; ++i) {
+      cudaEvent_t a, b;
+      CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b));
+      P->ev.push_back({a, b});
+    }
+  if (P->ev_used == EV_RING) fold_oldest(P);
+  slot = (P->ev_next + P->ev_used) % EV_RING;  // ev_next = oldest pending pair
+  CUDA_OK(cudaEventRecord(P->ev[slot].first, st));
+}
+void record_end(mrhyde_b200_plan* P, cudaStream_t st, size_t slot) {
+  CUDA_OK(cudaEventRecord(P->ev[slot].second, st));
+  ++P->ev_used;
+}
+
+void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool want_jac, bool want_res, double* res, double* jac, cudaStream_t st) {
+  if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "assemble called before mrhyde_b200_plan_finalize");
+  if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "host-only analysis plan (device = -1) cannot assemble: there is no CPU path");
+  if (!sol) fail(MRHYDE_B200_ERR_INVALID, "sol is null");
+  if (want_res && !res) fail(MRHYDE_B200_ERR_INVALID, "res is null");
+  if (want_jac && !jac) fail(MRHYDE_B200_ERR_INVALID, "jac_values is null");
+  CUDA_OK(cudaSetDevice(P->device));
+  OutDev out;
+  out.res = want_res ? res : nullptr;
+  out.jac = want_jac ? jac : nullptr;
+  out.accumulate = P->accumulate ? 1 : 0;
+  GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
+  const bool volume = opt_bool(P, "assemble volume terms", true);
+  if (volume) {
+    size_t slot = 0;
+    record_begin(P, st, slot);
+    if (P->dim == 3) {
+      P->th3.sol = sol; P->th3.td = td; P->th3.out = out;
+      launch_thermal_q1_3d(P->th3, P->pp.n_patches, P->threads, P->smem, st);
+    } else {
+      P->th2.sol = sol; P->th2.td = td; P->th2.out = out;
+      launch_thermal_q1_2d(P->th2, P->pp.n_patches, P->threads, P->smem, st);
+    }
+    record_end(P, st, slot);
+    CUDA_OK(cudaGetLastError());
+    if (!P->accumulate && !P->pp.orphan_rows.empty()) {
+      const int n = (int)P->pp.orphan_rows.size();
+      orphan_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(P->d_orphans.p, n, G, out);
+    }
+  } else if (!P->accumulate) {
+    fail(MRHYDE_B200_ERR_UNSUPPORTED, "accumulate=false needs the volume pass (it defines every entry)");
+  }
+  if (!P->boundary.groups.empty() && opt_bool(P, "assemble boundary terms", true)) {
+    OutDev bout = out;
+    bout.accumulate = 1;  // boundary groups always add on top of the volume result
+    launch_boundary(P->boundary, sol, td, G, bout, st);
+    CUDA_OK(cudaGetLastError());
+  }
+  if (want_jac && P->accumulate && P->d_fixed_diag.n > 0 && opt_bool(P, "use strong DBCs", true)) {
+    const int n = (int)P->d_fixed_diag.n;
+    fixed_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(P->d_fixed_diag.p, n, jac);
+    CUDA_OK(cudaGetLastError());
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mrhyde_b200_version(void) { return "mrhyde_b200 0.1 (sm_100a)"; }
+const char* mrhyde_b200_last_error(void) { return g_error.c_str(); }
+
+int mrhyde_b200_plan_create(mrhyde_b200_plan** plan, const mrhyde_b200_desc* d, int device) {
+  ABI_BEGIN
+  if (!plan || !d) fail(MRHYDE_B200_ERR_INVALID, "plan_create: null argument");
+  *plan = nullptr;
+  if (!d->physics || !d->var_names || !d->var_basis || !d->bases || !d->offsets || !d->qp_pts || !d->qp_wts) fail(MRHYDE_B200_ERR_INVALID, "plan_create: null field in descriptor");
+  if (d->dim != 2 && d->dim != 3) fail(MRHYDE_B200_ERR_UNSUPPORTED, "plan_create: only Quadrilateral_4 (dim 2) and Hexahedron_8 (dim 3) cells");
+  if (d->nvars < 1 || d->nbases < 1 || d->nqp < 1 || d->ndof_elem < 1 || d->max_card < 1) fail(MRHYDE_B200_ERR_INVALID, "plan_create: non-positive size");
+  if (device != -1) {  // -1: host-only analysis plan (cannot assemble)
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0)
+      fail(MRHYDE_B200_ERR_CUDA, "plan_create: CUDA device " + std::to_string(device) + " not available (this library has no CPU path)");
+  }
+  std::unique_ptr<mrhyde_b200_plan> P(new mrhyde_b200_plan());
+  P->device = device;
+  P->physics = d->physics;
+  P->dim = d->dim; P->nvars = d->nvars; P->ndof_elem = d->ndof_elem; P->max_card = d->max_card; P->nqp = d->nqp;
+  for (int v = 0; v < d->nvars; ++v) {
+    P->var_names.push_back(d->var_names[v]);
+    if (d->var_basis[v] < 0 || d->var_basis[v] >= d->nbases) fail(MRHYDE_B200_ERR_INVALID, "plan_create: var_basis out of range");
+    P->var_basis.push_back(d->var_basis[v]);
+  }
+  P->offsets.assign(d->offsets, d->offsets + (size_t)d->nvars * d->max_card);
+  P->qp_pts.assign(d->qp_pts, d->qp_pts + (size_t)d->nqp * d->dim);
+  P->qp_wts.assign(d->qp_wts, d->qp_wts + d->nqp);
+  for (int b = 0; b < d->nbases; ++b) {
+    const mrhyde_b200_basis& in = d->bases[b];
+    if (!in.type || !in.val || in.card < 1) fail(MRHYDE_B200_ERR_INVALID, "plan_create: incomplete basis table");
+    BasisCopy B;
+    B.type = in.type; B.order = in.order; B.card = in.card;
+    const int vdim = (B.type == "HCURL" || B.type == "HDIV") ? d->dim : 1;
+    B.val.assign(in.val, in.val + (size_t)in.card * d->nqp * vdim);
+    if (in.grad) B.grad.assign(in.grad, in.grad + (size_t)in.card * d->nqp * d->dim);
+    if (in.curl) B.curl.assign(in.curl, in.curl + (size_t)in.card * d->nqp * d->dim);
+    if (in.div) B.div.assign(in.div, in.div + (size_t)in.card * d->nqp);
+    P->bases.push_back(std::move(B));
+  }
+  P->mesh.dim = d->dim; P->mesh.nverts = 1 << d->dim; P->mesh.ndof = d->ndof_elem;
+  *plan = P.release();
+  ABI_END
+}
+
+void mrhyde_b200_plan_destroy(mrhyde_b200_plan* plan) { delete plan; }
+
+int mrhyde_b200_plan_set_function(mrhyde_b200_plan* P, const char* name, const char* expression) {
+  ABI_BEGIN
+  if (!P || !name || !expression) fail(MRHYDE_B200_ERR_INVALID, "set_function: null argument");
+  if (P->finalized) fail(MRHYDE_B200_ERR_STATE, "set_function after finalize");
+  P->functions[name] = expression;
+  ABI_END
+}
+
+int mrhyde_b200_plan_set_option(mrhyde_b200_plan* P, const char* key, const char* value) {
+  ABI_BEGIN
+  if (!P || !key || !value) fail(MRHYDE_B200_ERR_INVALID, "set_option: null argument");
+  bool known = false;
+  for (const char** k = kKnownOptions; *k; ++k) if (std::string(*k) == key) known = true;
+  if (!known) fail(MRHYDE_B200_ERR_INVALID, std::string("set_option: unknown key '") + key + "'");
+  const std::string k(key), v(value);
+  if (P->finalized && k != "accumulate" && k != "assemble boundary terms" && k != "assemble volume terms") fail(MRHYDE_B200_ERR_STATE, "set_option: '" + k + "' must be set before finalize");
+  if (k == "accumulate") {
+    if (v != "true" && v != "false") fail(MRHYDE_B200_ERR_INVALID, "set_option: accumulate must be true|false");
+    P->accumulate = (v == "true");
+  }
+  if (k == "ns3d_uz_rows" && v != "reference" && v != "corrected") fail(MRHYDE_B200_ERR_INVALID, "set_option: ns3d_uz_rows must be reference|corrected");
+  P->options[k] = v;
+  ABI_END
+}
+
+int mrhyde_b200_plan_set_mesh(mrhyde_b200_plan* P, int64_t n_elem, const double* elem_nodes, const int32_t* lids, const int8_t* orient_sign) {
+  ABI_BEGIN
+  if (!P || !elem_nodes || !lids) fail(MRHYDE_B200_ERR_INVALID, "set_mesh: null argument");
+  if (n_elem < 1 || n_elem > 0x7fffffff) fail(MRHYDE_B200_ERR_INVALID, "set_mesh: element count out of range");
+  if (P->finalized) fail(MRHYDE_B200_ERR_STATE, "set_mesh after finalize");
+  P->mesh.set_elem_nodes(n_elem, elem_nodes);
+  P->mesh.lids.assign(lids, lids + (size_t)n_elem * P->ndof_elem);
+  if (orient_sign) P->mesh.orient.assign(orient_sign, orient_sign + (size_t)n_elem * P->ndof_elem); else P->mesh.orient.clear();
+  P->have_mesh = true;
+  ABI_END
+}
+
+int mrhyde_b200_plan_set_mesh_indexed(mrhyde_b200_plan* P, int64_t n_verts, const double* vc, int64_t n_elem, const int32_t* conn,
+                                      const int32_t* lids, const int8_t* orient_sign) {
+  ABI_BEGIN
+  if (!P || !vc || !conn || !lids) fail(MRHYDE_B200_ERR_INVALID, "set_mesh_indexed: null argument");
+  if (n_elem < 1 || n_elem > 0x7fffffff || n_verts < 1 || n_verts > 0x7fffffff) fail(MRHYDE_B200_ERR_INVALID, "set_mesh_indexed: count out of range");
+  if (P->finalized) fail(MRHYDE_B200_ERR_STATE, "set_mesh after finalize");
+  MeshGraph& M = P->mesh;
+  M.nelem = n_elem; M.nvert = n_verts;
+  for (int d = 0; d < 3; ++d) M.vcoord[d].assign((size_t)n_verts, 0.0);
+  for (int64_t v = 0; v < n_verts; ++v) for (int d = 0; d < P->dim; ++d) M.vcoord[d][(size_t)v] = vc[v * P->dim + d];
+  M.conn.assign(conn, conn + (size_t)n_elem * M.nverts);
+  for (int32_t c : M.conn) if (c < 0 || c >= n_verts) fail(MRHYDE_B200_ERR_INVALID, "set_mesh_indexed: connectivity out of range");
+  M.lids.assign(lids, lids + (size_t)n_elem * P->ndof_elem);
+  if (orient_sign) M.orient.assign(orient_sign, orient_sign + (size_t)n_elem * P->ndof_elem); else M.orient.clear();
+  P->have_mesh = true;
+  ABI_END
+}
+
+int mrhyde_b200_plan_set_graph(mrhyde_b200_plan* P, int64_t n_rows, int64_t n_owned, const int64_t* row_map, const int32_t* entries, const uint8_t* is_fixed) {
+  ABI_BEGIN
+  if (!P || !row_map || !entries) fail(MRHYDE_B200_ERR_INVALID, "set_graph: null argument");
+  if (n_rows < 1 || n_rows > 0x7fffffff || n_owned < 0 || n_owned > n_rows) fail(MRHYDE_B200_ERR_INVALID, "set_graph: row counts out of range");
+  if (P->finalized) fail(MRHYDE_B200_ERR_STATE, "set_graph after finalize");
+  MeshGraph& M = P->mesh;
+  M.nrows = n_rows; M.nowned = n_owned;
+  M.rowptr.assign(row_map, row_map + n_rows + 1);
+  if (M.rowptr[0] != 0) fail(MRHYDE_B200_ERR_INVALID, "set_graph: row_map[0] != 0");
+  for (int64_t r = 0; r < n_rows; ++r) if (M.rowptr[(size_t)r + 1] < M.rowptr[(size_t)r]) fail(MRHYDE_B200_ERR_INVALID, "set_graph: row_map not monotone");
+  M.nnz = M.rowptr[(size_t)n_rows];
+  M.colind.assign(entries, entries + M.nnz);
+  for (int64_t r = 0; r < n_rows; ++r)
+    for (int64_t p = M.rowptr[(size_t)r] + 1; p < M.rowptr[(size_t)r + 1]; ++p)
+      if (M.colind[(size_t)p] <= M.colind[(size_t)p - 1]) fail(MRHYDE_B200_ERR_INVALID, "set_graph: column indices must be strictly ascending within a row (fillComplete'd graph)");
+  if (is_fixed) M.fixed.assign(is_fixed, is_fixed + n_rows); else M.fixed.assign((size_t)n_rows, 0);
+  P->have_graph = true;
+  ABI_END
+}
+
+int mrhyde_b200_plan_set_sidesets(mrhyde_b200_plan* P, int32_t n_sides, const char* const* side_names) {
+  ABI_BEGIN
+  if (!P || (n_sides > 0 && !side_names)) fail(MRHYDE_B200_ERR_INVALID, "set_sidesets: null argument");
+  P->side_names.clear();
+  for (int s = 0; s < n_sides; ++s) P->side_names.push_back(side_names[s]);
+  ABI_END
+}
+
+int mrhyde_b200_plan_set_bc(mrhyde_b200_plan* P, const char* var, const char* side, const char* type, const char* expression) {
+  ABI_BEGIN
+  if (!P || !var || !side || !type) fail(MRHYDE_B200_ERR_INVALID, "set_bc: null argument");
+  const std::string t(type);
+  if (t != "none" && t != "Dirichlet" && t != "weak Dirichlet" && t != "Neumann") fail(MRHYDE_B200_ERR_INVALID, "set_bc: unknown type '" + t + "'");
+  bool okv = false, oks = false;
+  for (auto& v : P->var_names) okv = okv || v == var;
+  for (auto& s : P->side_names) oks = oks || s == side;
+  if (!okv) fail(MRHYDE_B200_ERR_INVALID, std::string("set_bc: unknown variable '") + var + "'");
+  if (!oks) fail(MRHYDE_B200_ERR_INVALID, std::string("set_bc: unknown sideset '") + side + "' (call set_sidesets first)");
+  BCEntry b; b.type = t; b.expr = expression ? expression : "0.0";
+  P->bcs[{var, side}] = b;
+  ABI_END
+}
+
+int mrhyde_b200_plan_add_boundary_group(mrhyde_b200_plan* P, const mrhyde_b200_boundary_group* bg) {
+  ABI_BEGIN
+  if (!P || !bg) fail(MRHYDE_B200_ERR_INVALID, "add_boundary_group: null argument");
+  if (P->finalized) fail(MRHYDE_B200_ERR_STATE, "add_boundary_group after finalize");
+  if (bg->sideset < 0 || bg->sideset >= (int)P->side_names.size()) fail(MRHYDE_B200_ERR_INVALID, "add_boundary_group: sideset out of range");
+  if (bg->n_elem < 0 || (bg->n_elem > 0 && !bg->elem_ids) || bg->nqp_side < 1 || !bg->side_pts || !bg->side_wts || !bg->tangent_u || !bg->side_bases)
+    fail(MRHYDE_B200_ERR_INVALID, "add_boundary_group: incomplete group");
+  BoundaryGroupHost H;
+  H.sideset = bg->sideset; H.local_side = bg->local_side; H.nqp = bg->nqp_side;
+  H.elem_ids.assign(bg->elem_ids, bg->elem_ids + bg->n_elem);
+  H.pts.assign(bg->side_pts, bg->side_pts + (size_t)bg->nqp_side * P->dim);
+  H.wts.assign(bg->side_wts, bg->side_wts + bg->nqp_side);
+  for (int d = 0; d < 3; ++d) { H.tu[d] = bg->tangent_u[d]; H.tv[d] = bg->tangent_v ? bg->tangent_v[d] : 0.0; }
+  const mrhyde_b200_basis& sb = bg->side_bases[P->var_basis[0]];
+  if (!sb.val) fail(MRHYDE_B200_ERR_INVALID, "add_boundary_group: missing side basis values");
+  H.val.assign(sb.val, sb.val + (size_t)sb.card * bg->nqp_side);
+  if (sb.grad) H.grad.assign(sb.grad, sb.grad + (size_t)sb.card * bg->nqp_side * P->dim);
+  P->bgroups.push_back(std::move(H));
+  ABI_END
+}
+
+int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "finalize: null plan");
+  if (P->finalized) fail(MRHYDE_B200_ERR_STATE, "finalize called twice");
+  if (!P->have_mesh || !P->have_graph) fail(MRHYDE_B200_ERR_STATE, "finalize: set_mesh and set_graph must be called first");
+  const bool host_only = (P->device == -1);
+  if (!host_only) CUDA_OK(cudaSetDevice(P->device));
+  MeshGraph& M = P->mesh;
+  for (int32_t l : M.lids) if (l < 0 || l >= M.nrows) fail(MRHYDE_B200_ERR_INVALID, "finalize: LID outside the graph's rows");
+
+  if (P->physics != "thermal") fail(MRHYDE_B200_ERR_UNSUPPORTED, "physics module '" + P->physics + "' has no device kernel in this build");
+  // ---- thermal, HGRAD Q1
+  const int NV = 1 << P->dim;
+  const BasisCopy& B = P->bases[P->var_basis[0]];
+  if (P->nvars != 1 || B.type != "HGRAD" || B.order != 1 || B.card != NV || P->ndof_elem != NV || P->nqp != NV || B.grad.empty())
+    fail(MRHYDE_B200_ERR_UNSUPPORTED, "thermal: this build has the HGRAD order-1 kernel with the 2-point Gauss rule only");
+  for (int i = 0; i < NV; ++i) if (P->offsets[i] != i) fail(MRHYDE_B200_ERR_UNSUPPORTED, "thermal: offsets must be the identity for a single variable");
+  if (opt_bool(P, "include advection", false)) fail(MRHYDE_B200_ERR_UNSUPPORTED, "thermal: 'include advection' has no device kernel in this build");
+
+  FunctionSet fs = make_function_set(P, false);
+  ExprProgram src = fs.compile("thermal source"), dif = fs.compile("thermal diffusion"), cp = fs.compile("specific heat"), rho = fs.compile("density");
+
+  M.classify_affine();
+  P->n_affine = 0;
+  for (uint8_t a : M.affine) P->n_affine += a;
+
+  // staged vector per element: upper triangle of the local Jacobian, then the residual
+  const int NT = NV * (NV + 1) / 2, STAGE = NT + NV;
+  std::vector<uint16_t> kmap((size_t)NV * NV), rmap((size_t)NV);
+  for (int i = 0; i < NV; ++i) {
+    rmap[(size_t)i] = (uint16_t)(NT + i);
+    for (int j = 0; j < NV; ++j) { const int a = std::min(i, j), b = std::max(i, j); kmap[(size_t)i * NV + j] = (uint16_t)(a * NV - (a * (a - 1)) / 2 + (b - a)); }
+  }
+  const int chunk = std::stoi(opt(P, "patch elements", P->dim == 3 ? "256" : "256"));
+  P->threads = std::stoi(opt(P, "threads", "256"));
+  if (P->threads < 32 || P->threads > 256 || P->threads % 32) fail(MRHYDE_B200_ERR_INVALID, "option threads must be a multiple of 32 in [32,256]");
+  build_patch_plan(M, kmap, rmap, STAGE, chunk, (size_t)thermal_q1_max_smem(), P->pp);
+  P->smem = (size_t)P->pp.max_pe * STAGE * sizeof(double);
+
+  P->stage_len = STAGE;
+  P->kmap = kmap; P->rmap = rmap;
+  if (host_only) {
+    // boundary groups still get their expressions compiled so that set-up errors surface
+    if (!P->bgroups.empty()) {
+      FunctionSet fss = make_function_set(P, true);
+      for (auto& g : P->bgroups) {
+        const std::string& sname = P->side_names[(size_t)g.sideset];
+        auto it = P->bcs.find({P->var_names[0], sname});
+        g.bctype = (it == P->bcs.end()) ? "none" : it->second.type;
+        if (g.bctype == "weak Dirichlet") g.data = fss.compile("Dirichlet " + P->var_names[0] + " " + sname);
+        else if (g.bctype == "Neumann") g.data = fss.compile("Neumann " + P->var_names[0] + " " + sname);
+      }
+    }
+    P->launches_per_assemble = 1;
+    P->finalized = true;
+    return MRHYDE_B200_OK;
+  }
+  // ---- upload
+  size_t* tot = &P->dev_bytes;
+  P->d_vx.upload(M.vcoord[0], tot); P->d_vy.upload(M.vcoord[1], tot); P->d_vz.upload(M.vcoord[2], tot);
+  P->d_conn.upload(M.conn, tot); P->d_lids.upload(M.lids, tot);
+  P->d_rowptr.upload(M.rowptr, tot); P->d_colind.upload(M.colind, tot); P->d_fixed.upload(M.fixed, tot); P->d_affine.upload(M.affine, tot);
+  P->d_patch_elem_ptr.upload(P->pp.patch_elem_ptr, tot); P->d_patch_elems.upload(P->pp.patch_elems, tot);
+  P->d_patch_row_ptr.upload(P->pp.patch_row_ptr, tot); P->d_patch_rows.upload(P->pp.patch_rows, tot);
+  P->d_patch_tmpl.upload(P->pp.patch_tmpl, tot); P->d_tmpl.upload(P->pp.tmpl, tot);
+  P->d_slot_row.upload(P->pp.slot_row, tot); P->d_slot_k.upload(P->pp.slot_k, tot);
+  P->d_cptr.upload(P->pp.cptr, tot); P->d_csrc.upload(P->pp.csrc, tot);
+  P->d_orphans.upload(P->pp.orphan_rows, tot);
+  {
+    std::vector<int64_t> diag;
+    for (int64_t r = 0; r < M.nrows; ++r) {
+      if (!M.fixed[(size_t)r]) continue;
+      int64_t pos = -1;
+      for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) if (M.colind[(size_t)p] == r) pos = p;
+      diag.push_back(pos);
+    }
+    P->d_fixed_diag.upload(diag, tot);
+    if (diag.empty()) P->d_fixed_diag.n = 0;
+  }
+  PatchDev D{P->d_patch_elem_ptr.p, P->d_patch_elems.p, P->d_patch_row_ptr.p, P->d_patch_rows.p, P->d_patch_tmpl.p, P->d_tmpl.p,
+             P->d_slot_row.p, P->d_slot_k.p, P->d_cptr.p, P->d_csrc.p};
+  GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
+  auto fill_common = [&](auto& th) {
+    th.source = src; th.diffusion = dif; th.specific_heat = cp; th.density = rho;
+    th.all_const = (dif.is_const && cp.is_const && rho.is_const) ? 1 : 0;
+    th.vx = P->d_vx.p; th.vy = P->d_vy.p; th.vz = P->d_vz.p;
+    th.conn = P->d_conn.p; th.lids = P->d_lids.p; th.affine = P->d_affine.p;
+    th.patches = D; th.graph = G;
+  };
+  if (P->dim == 3) { fill_thermal_tables<3>(P, P->th3.tab); fill_common(P->th3); }
+  else { fill_thermal_tables<2>(P, P->th2.tab); fill_common(P->th2); }
+  P->launches_per_assemble = 1;
+
+  // ---- boundary groups (Neumann / weak Dirichlet); strong-Dirichlet and "none" sides add nothing
+  if (!P->bgroups.empty()) {
+    FunctionSet fss = make_function_set(P, true);
+    BoundarySetup bs;
+    bs.dim = P->dim; bs.nv = NV;
+    bs.formparam = std::stod(opt(P, "form_param", "1.0"));
+    for (auto& g : P->bgroups) {
+      const std::string& sname = P->side_names[(size_t)g.sideset];
+      auto it = P->bcs.find({P->var_names[0], sname});
+      g.bctype = (it == P->bcs.end()) ? "none" : it->second.type;
+      if (g.bctype == "weak Dirichlet") g.data = fss.compile("Dirichlet " + P->var_names[0] + " " + sname);
+      else if (g.bctype == "Neumann") g.data = fss.compile("Neumann " + P->var_names[0] + " " + sname);
+    }
+    bs.diffusion = fss.compile("thermal diffusion");
+    build_boundary_plan(bs, P->bgroups, M, P->boundary, tot);
+    P->boundary.vx = P->d_vx.p; P->boundary.vy = P->d_vy.p; P->boundary.vz = P->d_vz.p;
+    P->boundary.conn = P->d_conn.p; P->boundary.lids = P->d_lids.p;
+    P->launches_per_assemble += (int)P->boundary.groups.size();
+  }
+  if (P->d_fixed_diag.n > 0) P->launches_per_assemble += 1;
+  P->finalized = true;
+  ABI_END
+}
+
+int mrhyde_b200_assemble_jacres(mrhyde_b200_plan* P, const double* sol, const mrhyde_b200_time* t, int compute_jacobian, int compute_residual,
+                                double* res, double* jac_values, void* stream) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "assemble_jacres: null plan");
+  if (!compute_jacobian && !compute_residual) fail(MRHYDE_B200_ERR_INVALID, "assemble_jacres: nothing requested");
+  TimeDev td;
+  fill_time(t, td, true);
+  do_assemble(P, sol, td, compute_jacobian != 0, compute_residual != 0, res, jac_values, (cudaStream_t)stream);
+  ABI_END
+}
+
+int mrhyde_b200_assemble_res(mrhyde_b200_plan* P, const double* sol, const mrhyde_b200_time* t, double* res, void* stream) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "assemble_res: null plan");
+  TimeDev td;
+  fill_time(t, td, true);
+  do_assemble(P, sol, td, false, true, res, nullptr, (cudaStream_t)stream);
+  ABI_END
+}
+
+int mrhyde_b200_assemble_jacres_host(mrhyde_b200_plan* P, const double* sol, const mrhyde_b200_time* t, int compute_jacobian, int compute_residual,
+                                     double* res, double* jac_values) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "assemble_jacres_host: null plan");
+  if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "assemble called before mrhyde_b200_plan_finalize");
+  if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "host-only analysis plan (device = -1) cannot assemble: there is no CPU path");
+  if (!sol || (compute_residual && !res) || (compute_jacobian && !jac_values)) fail(MRHYDE_B200_ERR_INVALID, "assemble_jacres_host: null buffer");
+  CUDA_OK(cudaSetDevice(P->device));
+  const size_t nr = (size_t)P->mesh.nrows, nnz = (size_t)P->mesh.nnz;
+  cudaStream_t st = 0;
+  P->h_sol.resize(nr, nullptr);
+  CUDA_OK(cudaMemcpyAsync(P->h_sol.p, sol, nr * sizeof(double), cudaMemcpyHostToDevice, st));
+  TimeDev td;
+  fill_time(t, td, false);
+  if (td.transient) {
+    if ((int)P->h_prev.size() < td.nprev) P->h_prev.resize((size_t)td.nprev);
+    if ((int)P->h_stage.size() < td.nstage_lo) P->h_stage.resize((size_t)td.nstage_lo);
+    for (int k = 0; k < td.nprev; ++k) {
+      P->h_prev[(size_t)k].resize(nr, nullptr);
+      CUDA_OK(cudaMemcpyAsync(P->h_prev[(size_t)k].p, t->sol_prev[k], nr * sizeof(double), cudaMemcpyHostToDevice, st));
+      td.prev[k] = P->h_prev[(size_t)k].p;
+    }
+    for (int k = 0; k < td.nstage_lo; ++k) {
+      P->h_stage[(size_t)k].resize(nr, nullptr);
+      CUDA_OK(cudaMemcpyAsync(P->h_stage[(size_t)k].p, t->sol_stage[k], nr * sizeof(double), cudaMemcpyHostToDevice, st));
+      td.stg[k] = P->h_stage[(size_t)k].p;
+    }
+  }
+  if (compute_residual) {
+    P->h_res.resize(nr, nullptr);
+    if (P->accumulate) CUDA_OK(cudaMemcpyAsync(P->h_res.p, res, nr * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  if (compute_jacobian) {
+    P->h_jac.resize(nnz, nullptr);
+    if (P->accumulate) CUDA_OK(cudaMemcpyAsync(P->h_jac.p, jac_values, nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  do_assemble(P, P->h_sol.p, td, compute_jacobian != 0, compute_residual != 0, P->h_res.p, P->h_jac.p, st);
+  if (compute_residual) CUDA_OK(cudaMemcpyAsync(res, P->h_res.p, nr * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (compute_jacobian) CUDA_OK(cudaMemcpyAsync(jac_values, P->h_jac.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  ABI_END
+}
+
+int mrhyde_b200_comm_unique_id(uint8_t* id128) {
+  ABI_BEGIN
+  if (!id128) fail(MRHYDE_B200_ERR_INVALID, "comm_unique_id: null argument");
+  std::string err;
+  if (!halo_unique_id(id128, err)) fail(MRHYDE_B200_ERR_NCCL, err);
+  ABI_END
+}
+
+int mrhyde_b200_plan_comm_init(mrhyde_b200_plan* P, const uint8_t* id128, int rank, int nranks) {
+  ABI_BEGIN
+  if (!P || !id128) fail(MRHYDE_B200_ERR_INVALID, "comm_init: null argument");
+  CUDA_OK(cudaSetDevice(P->device));
+  std::string err;
+  P->halo.reset(new HaloExchange());
+  if (!P->halo->init(id128, rank, nranks, err)) { P->halo.reset(); fail(MRHYDE_B200_ERR_NCCL, err); }
+  ABI_END
+}
+
+int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* P, const int64_t* row_gids) {
+  ABI_BEGIN
+  if (!P || !row_gids) fail(MRHYDE_B200_ERR_INVALID, "set_halo: null argument");
+  if (!P->halo) fail(MRHYDE_B200_ERR_STATE, "set_halo: call plan_comm_init first");
+  if (!P->have_graph) fail(MRHYDE_B200_ERR_STATE, "set_halo: call set_graph first");
+  CUDA_OK(cudaSetDevice(P->device));
+  std::string err;
+  if (!P->halo->setup(P->mesh.nrows, P->mesh.nowned, row_gids, P->mesh.rowptr.data(), P->mesh.colind.data(), err)) fail(MRHYDE_B200_ERR_NCCL, err);
+  ABI_END
+}
+
+int mrhyde_b200_halo_sum(mrhyde_b200_plan* P, double* res, double* jac_values, void* stream) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "halo_sum: null plan");
+  if (!P->halo || !P->halo->ready()) fail(MRHYDE_B200_ERR_STATE, "halo_sum: call plan_comm_init and plan_set_halo first");
+  CUDA_OK(cudaSetDevice(P->device));
+  std::string err;
+  if (!P->halo->sum(res, jac_values, (cudaStream_t)stream, err)) fail(MRHYDE_B200_ERR_NCCL, err);
+  ABI_END
+}
+
+int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) {
+  ABI_BEGIN
+  if (!P || !key || !value) fail(MRHYDE_B200_ERR_INVALID, "plan_stat: null argument");
+  const std::string k(key);
+  if (k == "n_patches") *value = P->pp.n_patches;
+  else if (k == "n_templates") *value = (int64_t)P->pp.tmpl.size();
+  else if (k == "kernel_launches_per_assemble") *value = P->launches_per_assemble;
+  else if (k == "smem_bytes") *value = (int64_t)P->smem;
+  else if (k == "threads_per_block") *value = P->threads;
+  else if (k == "n_elem") *value = P->mesh.nelem;
+  else if (k == "n_elem_with_halo") *value = P->pp.n_elem_with_halo;
+  else if (k == "n_rows") *value = P->mesh.nrows;
+  else if (k == "nnz") *value = P->mesh.nnz;
+  else if (k == "n_verts") *value = P->mesh.nvert;
+  else if (k == "plan_device_bytes") *value = (int64_t)P->dev_bytes;
+  else if (k == "n_affine") *value = P->n_affine;
+  else if (k == "patch_elements") *value = P->pp.chunk;
+  else if (k == "max_patch_elements") *value = P->pp.max_pe;
+  else if (k == "n_orphan_rows") *value = (int64_t)P->pp.orphan_rows.size();
+  else fail(MRHYDE_B200_ERR_INVALID, "plan_stat: unknown key '" + k + "'");
+  ABI_END
+}
+
+int mrhyde_b200_plan_kernel_time(mrhyde_b200_plan* P, int reset, double* avg_ms, int64_t* n_launches) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "kernel_time: null plan");
+  while (P->ev_used > 0) fold_oldest(P);
+  if (avg_ms) *avg_ms = P->ev_count ? P->ev_ms / (double)P->ev_count : 0.0;
+  if (n_launches) *n_launches = P->ev_count;
+  if (reset) { P->ev_ms = 0.0; P->ev_count = 0; }
+  ABI_END
+}
+
+int mrhyde_b200_plan_eval_function(mrhyde_b200_plan* P, const char* name, int64_t npts, const double* xyz, double time, double* out) {
+  ABI_BEGIN
+  if (!P || !name || !xyz || !out || npts < 0) fail(MRHYDE_B200_ERR_INVALID, "eval_function: bad argument");
+  if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "eval_function needs a device plan (use mrhyde_b200_expr_eval_host for host checks)");
+  CUDA_OK(cudaSetDevice(P->device));
+  FunctionSet fs = make_function_set(P, false);
+  if (!fs.has(name)) fail(MRHYDE_B200_ERR_INVALID, std::string("eval_function: function not registered: ") + name);
+  const ExprProgram prog = fs.compile(name);
+  if (npts == 0) return MRHYDE_B200_OK;
+  DevBuf<double> dx, dout;
+  dx.resize((size_t)npts * 3, nullptr); dout.resize((size_t)npts, nullptr);
+  CUDA_OK(cudaMemcpy(dx.p, xyz, (size_t)npts * 3 * sizeof(double), cudaMemcpyHostToDevice));
+  eval_points_kernel<<<(unsigned)((npts + 127) / 128), 128>>>(prog, dx.p, time, npts, dout.p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(out, dout.p, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost));
+  ABI_END
+}
+
+static FunctionSet adhoc_set(int32_t n, const char* const* names, const char* const* exprs) {
+  FunctionSet fs;
+  for (int i = 0; i < n; ++i) {
+    if (!names[i] || !exprs[i]) fail(MRHYDE_B200_ERR_INVALID, "null function name / expression");
+    fs.set(names[i], exprs[i]);
+  }
+  fs.set_scalar_fields({"x", "y", "z", "", "n[x]", "n[y]", "n[z]"});
+  return fs;
+}
+
+int mrhyde_b200_expr_disassemble(int32_t n, const char* const* names, const char* const* exprs, const char* which, char* out, size_t out_cap) {
+  ABI_BEGIN
+  if (n < 0 || (n > 0 && (!names || !exprs)) || !which || !out || out_cap == 0) fail(MRHYDE_B200_ERR_INVALID, "expr_disassemble: bad argument");
+  FunctionSet fs = adhoc_set(n, names, exprs);
+  const std::string text = FunctionSet::disassemble(fs.compile(which));
+  if (text.size() + 1 > out_cap) fail(MRHYDE_B200_ERR_INVALID, "expr_disassemble: output buffer too small");
+  std::memcpy(out, text.c_str(), text.size() + 1);
+  ABI_END
+}
+
+int mrhyde_b200_expr_eval_host(int32_t n, const char* const* names, const char* const* exprs, const char* which, int64_t npts, const double* vars7, double* out) {
+  ABI_BEGIN
+  if (n < 0 || (n > 0 && (!names || !exprs)) || !which || npts < 0 || (npts > 0 && (!vars7 || !out))) fail(MRHYDE_B200_ERR_INVALID, "expr_eval_host: bad argument");
+  FunctionSet fs = adhoc_set(n, names, exprs);
+  const ExprProgram p = fs.compile(which);
+  for (int64_t i = 0; i < npts; ++i) out[i] = p.is_const ? p.cval : FunctionSet::eval_host(p, vars7 + 7 * i);
+  ABI_END
+}
+
+int mrhyde_b200_plan_debug_scatter_host(mrhyde_b200_plan* P, const double* stage, int64_t stage_len, int accumulate, double* res, double* jac) {
+  ABI_BEGIN
+  if (!P || !stage) fail(MRHYDE_B200_ERR_INVALID, "debug_scatter_host: null argument");
+  if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "debug_scatter_host before finalize");
+  if (stage_len != P->stage_len) fail(MRHYDE_B200_ERR_INVALID, "debug_scatter_host: stage_len must be " + std::to_string(P->stage_len));
+  const PatchPlan& pp = P->pp;
+  const MeshGraph& M = P->mesh;
+  for (int32_t p = 0; p < pp.n_patches; ++p) {
+    const TemplateHeader& T = pp.tmpl[(size_t)pp.patch_tmpl[(size_t)p]];
+    const int32_t e0 = pp.patch_elem_ptr[(size_t)p], n_pe = pp.patch_elem_ptr[(size_t)p + 1] - e0;
+    const int32_t r0 = pp.patch_row_ptr[(size_t)p];
+    if (n_pe != T.n_pe) fail(MRHYDE_B200_ERR_STATE, "debug_scatter_host: template / patch size mismatch");
+    for (int32_t s = 0; s < T.n_slots; ++s) {
+      const uint16_t k = pp.slot_k[(size_t)T.off_slot + s];
+      const int32_t row = pp.patch_rows[(size_t)r0 + pp.slot_row[(size_t)T.off_slot + s]];
+      double acc = 0.0;
+      for (uint32_t c = pp.cptr[(size_t)T.off_cptr + s]; c < pp.cptr[(size_t)T.off_cptr + s + 1]; ++c) {
+        const uint32_t src = pp.csrc[(size_t)T.off_csrc + c];
+        const uint32_t entry = src / (uint32_t)n_pe, le = src % (uint32_t)n_pe;
+        acc += stage[(size_t)pp.patch_elems[(size_t)e0 + le] * stage_len + entry];
+      }
+      const bool fixed = M.fixed[(size_t)row] != 0;
+      if (k == SLOT_RES) {
+        if (!res) continue;
+        if (!fixed) { if (accumulate) res[row] += -acc; else res[row] = -acc; }
+        else if (!accumulate) res[row] = 0.0;
+      } else {
+        if (!jac) continue;
+        const int64_t pos = M.rowptr[(size_t)row] + k;
+        if (!fixed) { if (accumulate) jac[pos] += acc; else jac[pos] = acc; }
+        else if (!accumulate) jac[pos] = (M.colind[(size_t)pos] == row) ? 1.0 : 0.0;
+      }
+    }
+  }
+  ABI_END
+}
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+// Host side of the expression compiler (see expr.hpp for the reference map).
+#include "expr.hpp"
+
+#include <cctype>
+#include <cmath>
+#include <sstream>
+
+#include "../../include/mrhyde_b200.h"
+
+namespace mrhyde_b200 {
+
+namespace {
+
+const double kPi = 3.141592653589793238463;  // src/preferences.hpp:70
+
+// Interpreter::isScalar (interpreter.cpp:17-57): digits, one '.', one 'e'/'E', sign first or after the exponent
+bool looks_scalar(const std::string& s) {
+  bool isnum = true;
+  int ndots = 0, nexp = 0;
+  for (size_t k = 0; k < s.size(); ++k) {
+    const char ch = s[k];
+    if (std::isdigit((unsigned char)ch)) continue;
+    if (ch == '.') { if (ndots++ > 0) isnum = false; }
+    else if (ch == 'e' || ch == 'E') { if (nexp++ > 0) isnum = false; }
+    else if (ch == '+' || ch == '-') { if (k > 0 && !(s[k - 1] == 'e' || s[k - 1] == 'E')) isnum = false; }
+    else isnum = false;
+  }
+  return isnum;
+}
+
+const char* const kOps[] = {"sin", "cos", "exp", "log", "tan", "abs", "max", "min", "mean", "emax", "emin", "emean", "sqrt", "sinh", "cosh"};
+
+// op(arg) recognition, interpreter.cpp:360-446
+bool match_operator(const std::string& s, std::string& oper, std::string& arg) {
+  for (const char* opname : kOps) {
+    const std::string op(opname);
+    const size_t L = op.size();
+    if (s.size() < L || s.compare(0, L, op) != 0) continue;
+    if (s.size() <= L + 1 || s[L] != '(' || s.back() != ')') continue;
+    bool inner_close = false;
+    for (size_t j = L + 1; j + 1 < s.size(); ++j) if (s[j] == ')') inner_close = true;
+    if (inner_close) continue;
+    oper = op;
+    arg = s.substr(L + 1, s.size() - L - 2);
+    return true;
+  }
+  return false;
+}
+
+typedef std::vector<std::pair<std::string, std::string>> Pieces;  // (op, sub-expression)
+
+// Interpreter::split (interpreter.cpp:63-352)
+Pieces split_expression(std::string s) {
+  Pieces out;
+  if (!s.empty() && s[0] == '-') s = "0.0" + s;
+  if (s.empty()) return out;
+  if (s.size() == 1) { out.push_back({"", s}); return out; }
+  size_t num_pm = 0, num_mdp = 0, num_pow = 0;
+  int paren = 0;
+  for (char ch : s) {
+    if (ch == '(') ++paren;
+    else if (ch == ')') --paren;
+    else if (paren == 0) {
+      if (ch == '+' || ch == '-') ++num_pm;
+      if (ch == '*' || ch == '/' || ch == '<' || ch == '>') ++num_mdp;
+      if (ch == '^') ++num_pow;
+    }
+  }
+  if (paren > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE found an unclosed parenthesis in: " + s);
+  if (paren < 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE found an extra parenthesis in: " + s);
+  std::string cur, curop;
+  if (num_pm > 0) {
+    for (size_t i = 0; i < s.size(); ++i) {
+      const char ch = s[i];
+      if (ch == ' ' || ch == '=') {}
+      else if (ch == '(') { ++paren; cur += ch; }
+      else if (ch == ')') { --paren; cur += ch; }
+      else if (paren == 0 && (ch == '+' || ch == '-') && !cur.empty()) {
+        out.push_back({curop, cur});
+        cur.clear();
+        curop = (ch == '+') ? "plus" : "minus";
+      } else cur += ch;
+    }
+    if (!cur.empty()) out.push_back({curop, cur});
+  } else if (num_mdp > 0) {
+    for (size_t i = 0; i < s.size(); ++i) {
+      const char ch = s[i];
+      if (ch == ' ') {}
+      else if (ch == '(') { ++paren; cur += ch; }
+      else if (ch == ')') { --paren; cur += ch; }
+      else if (paren == 0 && (ch == '*' || ch == '/' || ch == '<' || ch == '>')) {
+        out.push_back({curop, cur});
+        cur.clear();
+        if (ch == '*') curop = "times";
+        else if (ch == '/') curop = "divide";
+        else {
+          const bool eq = (i + 1 < s.size() && s[i + 1] == '=');
+          curop = (ch == '<') ? (eq ? "lte" : "lt") : (eq ? "gte" : "gt");
+          if (eq) ++i;
+        }
+      } else cur += ch;
+    }
+    out.push_back({curop, cur});
+  } else if (num_pow > 0) {
+    for (size_t i = 0; i < s.size(); ++i) {
+      const char ch = s[i];
+      if (ch == '(') { ++paren; cur += ch; }
+      else if (ch == ')') { --paren; cur += ch; }
+      else if (paren == 0 && ch == '^') { out.push_back({curop, cur}); cur.clear(); curop = "power"; }
+      else cur += ch;
+    }
+    out.push_back({curop, cur});
+  } else if (s.front() == '(' && s.back() == ')') {
+    out.push_back({"", s.substr(1, s.size() - 2)});
+  } else {
+    // name(args) with an unknown name: the reference turns the name into the op string; no kernel knows it
+    size_t pindex = std::string::npos;
+    for (size_t k = 1; k + 1 < s.size(); ++k) if (s[k] == '(') { pindex = k; break; }
+    if (pindex != std::string::npos && s.back() == ')')
+      throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE was not able to decompose or find: " + s);
+  }
+  return out;
+}
+
+double apply_binary(const std::string& op, double a, double b) {  // functionManager_evaluate.hpp:237-560
+  if (op == "plus") return a + b;
+  if (op == "minus") return a + (-b);
+  if (op == "times") return a * b;
+  if (op == "divide") return a / b;
+  if (op == "power") return std::pow(a, b);
+  if (op == "lt") return a < b ? 1.0 : 0.0;
+  if (op == "lte") return a <= b ? 1.0 : 0.0;
+  if (op == "gt") return a > b ? 1.0 : 0.0;
+  if (op == "gte") return a >= b ? 1.0 : 0.0;
+  if (op == "max") return b > a ? b : a;
+  if (op == "min") return b < a ? b : a;
+  if (op == "mean") return 0.5 * a + 0.5 * b;
+  throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression operator not supported on the device path: " + op);
+}
+double apply_unary(const std::string& op, double a) {
+  if (op == "sin") return std::sin(a);
+  if (op == "cos") return std::cos(a);
+  if (op == "tan") return std::tan(a);
+  if (op == "exp") return std::exp(a);
+  if (op == "log") return std::log(a);
+  if (op == "abs") return a < 0.0 ? -a : a;
+  if (op == "sqrt") return a <= 0.0 ? 0.0 : std::sqrt(a);
+  if (op == "sinh") return std::sinh(a);
+  if (op == "cosh") return std::cosh(a);
+  throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression operator not supported on the device path: " + op);
+}
+bool is_unary(const std::string& op) {
+  return op == "sin" || op == "cos" || op == "tan" || op == "exp" || op == "log" || op == "abs" || op == "sqrt" || op == "sinh" || op == "cosh";
+}
+uint8_t binary_code(const std::string& op) {
+  if (op == "plus") return OP_ADD;
+  if (op == "minus") return OP_SUB;
+  if (op == "times") return OP_MUL;
+  if (op == "divide") return OP_DIV;
+  if (op == "power") return OP_POW;
+  if (op == "lt") return OP_LT;
+  if (op == "lte") return OP_LTE;
+  if (op == "gt") return OP_GT;
+  if (op == "gte") return OP_GTE;
+  if (op == "max") return OP_MAX;
+  if (op == "min") return OP_MIN;
+  if (op == "mean") return OP_MEAN;
+  throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression operator not supported on the device path: " + op);
+}
+uint8_t unary_code(const std::string& op) {
+  if (op == "sin") return OP_SIN;
+  if (op == "cos") return OP_COS;
+  if (op == "tan") return OP_TAN;
+  if (op == "exp") return OP_EXP;
+  if (op == "log") return OP_LOG;
+  if (op == "abs") return OP_ABS;
+  if (op == "sqrt") return OP_SQRT;
+  if (op == "sinh") return OP_SINH;
+  return OP_COSH;
+}
+
+}  // namespace
+
+int FunctionSet::build(const std::string& expr, std::vector<Node>& nodes, std::set<std::string>& active) const {
+  const int me = (int)nodes.size();
+  nodes.emplace_back();
+  // 1. solution fields of the workset (AD data): a coefficient that depends on the state
+  for (auto& f : soln_fields_)
+    if (expr == f) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "solution-dependent coefficient '" + expr + "' has no device kernel in this build");
+  // 2. scalar fields of the workset (x, y, z; n[x].. on sides)
+  for (size_t j = 0; j < scalar_fields_.size(); ++j)
+    if (!scalar_fields_[j].empty() && expr == scalar_fields_[j]) { nodes[me].kind = Node::VAR; nodes[me].var = (int)j; return me; }
+  // 3. another function of the forest
+  auto it = funcs_.find(expr);
+  if (it != funcs_.end()) {
+    if (active.count(expr)) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE detected a cyclic graph in: " + expr);
+    active.insert(expr);
+    const int sub = build(it->second, nodes, active);
+    active.erase(expr);
+    nodes[me].kind = Node::CHAIN;
+    nodes[me].deps.push_back({"", sub});
+    return me;
+  }
+  // 4. plain number
+  if (!expr.empty() && looks_scalar(expr)) {
+    try { nodes[me].value = std::stod(expr); } catch (...) { throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE was not able to decompose or find: " + expr); }
+    nodes[me].kind = Node::CONST;
+    return me;
+  }
+  // 5. known variables
+  if (expr == "t") { nodes[me].kind = Node::VAR; nodes[me].var = 3; return me; }
+  if (expr == "pi") { nodes[me].kind = Node::CONST; nodes[me].value = kPi; return me; }
+  // 6. op(arg) / op(arg1,arg2)
+  std::string oper, arg;
+  if (match_operator(expr, oper, arg)) {
+    if (arg.empty()) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE was not able to decompose or find: " + expr);
+    size_t comma = std::string::npos;
+    for (size_t i = 0; i + 1 < arg.size(); ++i) if (arg[i] == ',') comma = i;
+    nodes[me].kind = Node::CHAIN;
+    if (comma != std::string::npos) {
+      const int a = build(arg.substr(0, comma), nodes, active);
+      const int b = build(arg.substr(comma + 1), nodes, active);
+      nodes[me].deps.push_back({"", a});
+      nodes[me].deps.push_back({oper, b});
+    } else {
+      const int a = build(arg, nodes, active);
+      nodes[me].deps.push_back({oper, a});
+    }
+    return me;
+  }
+  // 7. split
+  Pieces pieces = split_expression(expr);
+  if (pieces.empty()) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE was not able to decompose or find: " + expr);
+  if (pieces.size() == 1 && pieces[0].first.empty() && pieces[0].second == expr)
+    throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE was not able to decompose or find: " + expr);
+  nodes[me].kind = Node::CHAIN;
+  for (auto& pc : pieces) {
+    const int sub = build(pc.second, nodes, active);
+    nodes[me].deps.push_back({pc.first, sub});
+  }
+  return me;
+}
+
+// Folds branches whose dependencies are all constant (reference: evaluated once at set-up).
+bool FunctionSet::fold(std::vector<Node>& nodes, int idx) {
+  Node& n = nodes[idx];
+  if (n.kind == Node::CONST) return true;
+  if (n.kind == Node::VAR) return false;
+  bool all = true;
+  for (auto& d : n.deps) all = fold(nodes, d.second) && all;
+  if (!all) return false;
+  double acc = 0.0;
+  for (size_t k = 0; k < n.deps.size(); ++k) {
+    const double v = nodes[n.deps[k].second].value;
+    const std::string& op = n.deps[k].first;
+    if (op.empty()) acc = v;
+    else if (is_unary(op)) acc = apply_unary(op, v);
+    else acc = apply_binary(op, acc, v);
+  }
+  n.kind = Node::CONST;
+  n.value = acc;
+  n.deps.clear();
+  return true;
+}
+
+void FunctionSet::emit(const std::vector<Node>& nodes, int idx, ExprProgram& p, int& depth, int& maxdepth) {
+  auto push_op = [&](uint8_t op, double c) {
+    if (p.n >= EXPR_MAXOPS - 1) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression too long for the device evaluator");
+    p.op[p.n] = op; p.c[p.n] = c; ++p.n;
+  };
+  const Node& n = nodes[idx];
+  if (n.kind == Node::CONST) { push_op(OP_PUSHC, n.value); maxdepth = std::max(maxdepth, ++depth); return; }
+  if (n.kind == Node::VAR) { push_op(OP_PUSHV, (double)n.var); maxdepth = std::max(maxdepth, ++depth); return; }
+  for (size_t k = 0; k < n.deps.size(); ++k) {
+    const std::string& op = n.deps[k].first;
+    const Node& d = nodes[n.deps[k].second];
+    if (op.empty()) {
+      // "data = dep": the splitter only produces this for the first dependency
+      if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: assignment in a chained position");
+      emit(nodes, n.deps[k].second, p, depth, maxdepth);
+    } else if (is_unary(op)) {
+      emit(nodes, n.deps[k].second, p, depth, maxdepth);
+      if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: unary operator in a chained position");
+      push_op(unary_code(op), 0.0);
+    } else {
+      if (k == 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: binary operator without a left operand");
+      const uint8_t code = binary_code(op);
+      if (d.kind == Node::CONST && code >= OP_ADD && code <= OP_POW) push_op((uint8_t)(OP_ADDC + (code - OP_ADD)), d.value);
+      else if (d.kind == Node::VAR && code >= OP_ADD && code <= OP_DIV) push_op((uint8_t)(OP_ADDV + (code - OP_ADD)), (double)d.var);
+      else {
+        emit(nodes, n.deps[k].second, p, depth, maxdepth);
+        push_op(code, 0.0);
+        --depth;
+      }
+    }
+  }
+}
+
+ExprProgram FunctionSet::compile(const std::string& name) const {
+  auto it = funcs_.find(name);
+  if (it == funcs_.end()) throw ExprError(MRHYDE_B200_ERR_INVALID, "function not registered: " + name);
+  std::vector<Node> nodes;
+  std::set<std::string> active;
+  active.insert(name);
+  const int root = build(it->second, nodes, active);
+  ExprProgram p;
+  if (fold(nodes, root)) {
+    p.is_const = 1;
+    p.cval = nodes[root].value;
+    p.n = 1;
+    p.op[0] = OP_PUSHC; p.c[0] = p.cval; p.op[1] = OP_END;
+    return p;
+  }
+  p.is_const = 0;
+  int depth = 0, maxdepth = 0;
+  emit(nodes, root, p, depth, maxdepth);
+  p.op[p.n] = OP_END;
+  if (maxdepth > EXPR_MAXSTACK) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression nests too deeply for the device evaluator: " + name);
+  return p;
+}
+
+double FunctionSet::eval_host(const ExprProgram& p, const double* vars) {
+  double st[EXPR_MAXSTACK + 1];
+  int sp = -1;
+  for (int i = 0; i < p.n; ++i) {
+    const double c = p.c[i];
+    switch (p.op[i]) {
+      case OP_PUSHC: st[++sp] = c; break;
+      case OP_PUSHV: st[++sp] = vars[(int)c]; break;
+      case OP_ADD: st[sp - 1] = st[sp - 1] + st[sp]; --sp; break;
+      case OP_SUB: st[sp - 1] = st[sp - 1] + (-st[sp]); --sp; break;
+      case OP_MUL: st[sp - 1] = st[sp - 1] * st[sp]; --sp; break;
+      case OP_DIV: st[sp - 1] = st[sp - 1] / st[sp]; --sp; break;
+      case OP_POW: st[sp - 1] = std::pow(st[sp - 1], st[sp]); --sp; break;
+      case OP_LT: st[sp - 1] = st[sp - 1] < st[sp] ? 1.0 : 0.0; --sp; break;
+      case OP_LTE: st[sp - 1] = st[sp - 1] <= st[sp] ? 1.0 : 0.0; --sp; break;
+      case OP_GT: st[sp - 1] = st[sp - 1] > st[sp] ? 1.0 : 0.0; --sp; break;
+      case OP_GTE: st[sp - 1] = st[sp - 1] >= st[sp] ? 1.0 : 0.0; --sp; break;
+      case OP_MAX: st[sp - 1] = st[sp] > st[sp - 1] ? st[sp] : st[sp - 1]; --sp; break;
+      case OP_MIN: st[sp - 1] = st[sp] < st[sp - 1] ? st[sp] : st[sp - 1]; --sp; break;
+      case OP_MEAN: st[sp - 1] = 0.5 * st[sp - 1] + 0.5 * st[sp]; --sp; break;
+      case OP_ADDC: st[sp] = st[sp] + c; break;
+      case OP_SUBC: st[sp] = st[sp] + (-c); break;
+      case OP_MULC: st[sp] = st[sp] * c; break;
+      case OP_DIVC: st[sp] = st[sp] / c; break;
+      case OP_POWC: st[sp] = std::pow(st[sp], c); break;
+      case OP_ADDV: st[sp] = st[sp] + vars[(int)c]; break;
+      case OP_SUBV: st[sp] = st[sp] + (-vars[(int)c]); break;
+      case OP_MULV: st[sp] = st[sp] * vars[(int)c]; break;
+      case OP_DIVV: st[sp] = st[sp] / vars[(int)c]; break;
+      case OP_SIN: st[sp] = std::sin(st[sp]); break;
+      case OP_COS: st[sp] = std::cos(st[sp]); break;
+      case OP_TAN: st[sp] = std::tan(st[sp]); break;
+      case OP_EXP: st[sp] = std::exp(st[sp]); break;
+      case OP_LOG: st[sp] = std::log(st[sp]); break;
+      case OP_ABS: st[sp] = st[sp] < 0.0 ? -st[sp] : st[sp]; break;
+      case OP_SQRT: st[sp] = st[sp] <= 0.0 ? 0.0 : std::sqrt(st[sp]); break;
+      case OP_SINH: st[sp] = std::sinh(st[sp]); break;
+      case OP_COSH: st[sp] = std::cosh(st[sp]); break;
+      default: break;
+    }
+  }
+  return sp >= 0 ? st[sp] : 0.0;
+}
+
+std::string FunctionSet::disassemble(const ExprProgram& p) {
+  static const char* names[] = {"end", "pushc", "pushv", "add", "sub", "mul", "div", "pow", "lt", "lte", "gt", "gte", "max", "min", "mean",
+                                "addc", "subc", "mulc", "divc", "powc", "addv", "subv", "mulv", "divv",
+                                "sin", "cos", "tan", "exp", "log", "abs", "sqrt", "sinh", "cosh"};
+  std::ostringstream os;
+  os.precision(17);
+  if (p.is_const) { os << "const " << p.cval; return os.str(); }
+  for (int i = 0; i < p.n; ++i) {
+    os << names[p.op[i]];
+    const uint8_t o = p.op[i];
+    if (o == OP_PUSHC || (o >= OP_ADDC && o <= OP_POWC)) os << " " << p.c[i];
+    if (o == OP_PUSHV || (o >= OP_ADDV && o <= OP_DIVV)) os << " v" << (int)p.c[i];
+    os << "; ";
+  }
+  return os.str();
+}
+
+}  // namespace mrhyde_b200

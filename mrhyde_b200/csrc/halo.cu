@@ -1,0 +1,248 @@
+// NCCL halo sum (see halo.hpp).  NCCL is loaded with dlopen("libnccl.so.2"): inside a
+// torch.distributed process this resolves to the library torch already loaded.
+#include "halo.hpp"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+
+namespace mrhyde_b200 {
+
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+NcclApi& api() {
+  static NcclApi A;
+  if (A.handle || !A.why.empty()) return A;
+  A.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!A.handle) { A.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return A; }
+  auto sym = [&](const char* n) { void* p = dlsym(A.handle, n); if (!p && A.why.empty()) A.why = std::string("libnccl.so.2 lacks ") + n; return p; };
+  A.GetUniqueId = (decltype(A.GetUniqueId))sym("ncclGetUniqueId");
+  A.CommInitRank = (decltype(A.CommInitRank))sym("ncclCommInitRank");
+  A.CommDestroy = (decltype(A.CommDestroy))sym("ncclCommDestroy");
+  A.Send = (decltype(A.Send))sym("ncclSend");
+  A.Recv = (decltype(A.Recv))sym("ncclRecv");
+  A.AllGather = (decltype(A.AllGather))sym("ncclAllGather");
+  A.GroupStart = (decltype(A.GroupStart))sym("ncclGroupStart");
+  A.GroupEnd = (decltype(A.GroupEnd))sym("ncclGroupEnd");
+  A.GetErrorString = (decltype(A.GetErrorString))sym("ncclGetErrorString");
+  A.ok = A.why.empty();
+  return A;
+}
+
+#define NCCL_TRY(call)                                                                        \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess) { err = std::string(#call) + ": " + api().GetErrorString(r_); return false; } \
+  } while (0)
+#define CU_TRY(call)                                                                          \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } \
+  } while (0)
+
+__global__ void pack_kernel(const double* __restrict__ src, const int64_t* __restrict__ pos, int64_t n, double* __restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[pos[i]];
+}
+__global__ void unpack_add_kernel(const double* __restrict__ src, const int64_t* __restrict__ pos, int64_t n, double* __restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && pos[i] >= 0) dst[pos[i]] += src[i];
+}
+
+template <class T>
+bool to_device(T** d, const std::vector<T>& h, std::string& err) {
+  CU_TRY(cudaMalloc((void**)d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) CU_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return true;
+}
+
+}  // namespace
+
+bool halo_unique_id(uint8_t* id128, std::string& err) {
+  NcclApi& A = api();
+  if (!A.ok) { err = A.why; return false; }
+  ncclUniqueId id;
+  NCCL_TRY(A.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(id128, &id, 128);
+  return true;
+}
+
+HaloExchange::~HaloExchange() {
+  for (auto& p : peers_) {
+    cudaFree(p.d_send_res); cudaFree(p.d_send_jac); cudaFree(p.d_recv_res); cudaFree(p.d_recv_jac);
+    cudaFree(p.d_sendbuf); cudaFree(p.d_recvbuf);
+  }
+  if (comm_ && api().ok) api().CommDestroy((ncclComm_t)comm_);
+}
+
+bool HaloExchange::init(const uint8_t* id128, int rank, int nranks, std::string& err) {
+  NcclApi& A = api();
+  if (!A.ok) { err = A.why; return false; }
+  if (rank < 0 || rank >= nranks) { err = "halo: rank out of range"; return false; }
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclComm_t c;
+  NCCL_TRY(A.CommInitRank(&c, nranks, id, rank));
+  comm_ = c; rank_ = rank; nranks_ = nranks;
+  return true;
+}
+
+// Variable-size all-to-all of int64 payloads through grouped send/recv (host vectors in, host vectors out).
+static bool exchange_lists(NcclApi& A, ncclComm_t comm, int rank, int nranks, const std::vector<std::vector<int64_t>>& out_lists,
+                           std::vector<std::vector<int64_t>>& in_lists, std::string& err) {
+  // counts
+  std::vector<int64_t> cnt((size_t)nranks), allcnt((size_t)nranks * nranks);
+  for (int p = 0; p < nranks; ++p) cnt[(size_t)p] = (int64_t)out_lists[(size_t)p].size();
+  int64_t *d_cnt = nullptr, *d_all = nullptr;
+  CU_TRY(cudaMalloc(&d_cnt, nranks * sizeof(int64_t)));
+  CU_TRY(cudaMalloc(&d_all, (size_t)nranks * nranks * sizeof(int64_t)));
+  CU_TRY(cudaMemcpy(d_cnt, cnt.data(), nranks * sizeof(int64_t), cudaMemcpyHostToDevice));
+  NCCL_TRY(A.AllGather(d_cnt, d_all, (size_t)nranks, ncclInt64, comm, 0));
+  CU_TRY(cudaStreamSynchronize(0));
+  CU_TRY(cudaMemcpy(allcnt.data(), d_all, allcnt.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  cudaFree(d_cnt); cudaFree(d_all);
+  in_lists.assign((size_t)nranks, {});
+  std::vector<int64_t*> dsend((size_t)nranks, nullptr), drecv((size_t)nranks, nullptr);
+  for (int p = 0; p < nranks; ++p) {
+    if (p == rank) continue;
+    const int64_t ns = cnt[(size_t)p], nr = allcnt[(size_t)p * nranks + rank];
+    in_lists[(size_t)p].resize((size_t)nr);
+    if (ns) { CU_TRY(cudaMalloc(&dsend[(size_t)p], ns * sizeof(int64_t))); CU_TRY(cudaMemcpy(dsend[(size_t)p], out_lists[(size_t)p].data(), ns * sizeof(int64_t), cudaMemcpyHostToDevice)); }
+    if (nr) CU_TRY(cudaMalloc(&drecv[(size_t)p], nr * sizeof(int64_t)));
+  }
+  NCCL_TRY(A.GroupStart());
+  for (int p = 0; p < nranks; ++p) {
+    if (p == rank) continue;
+    if (!out_lists[(size_t)p].empty()) NCCL_TRY(A.Send(dsend[(size_t)p], out_lists[(size_t)p].size(), ncclInt64, p, comm, 0));
+    if (!in_lists[(size_t)p].empty()) NCCL_TRY(A.Recv(drecv[(size_t)p], in_lists[(size_t)p].size(), ncclInt64, p, comm, 0));
+  }
+  NCCL_TRY(A.GroupEnd());
+  CU_TRY(cudaStreamSynchronize(0));
+  for (int p = 0; p < nranks; ++p) {
+    if (!in_lists[(size_t)p].empty()) CU_TRY(cudaMemcpy(in_lists[(size_t)p].data(), drecv[(size_t)p], in_lists[(size_t)p].size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    cudaFree(dsend[(size_t)p]); cudaFree(drecv[(size_t)p]);
+  }
+  return true;
+}
+
+bool HaloExchange::setup(int64_t n_rows, int64_t n_owned, const int64_t* row_gids, const int64_t* rowptr, const int32_t* colind, std::string& err) {
+  NcclApi& A = api();
+  ncclComm_t comm = (ncclComm_t)comm_;
+  ready_ = false;
+  // 1. every rank learns who owns which global row: all-to-all of the owned gid lists
+  std::vector<std::vector<int64_t>> out((size_t)nranks_), in;
+  for (int p = 0; p < nranks_; ++p) if (p != rank_) out[(size_t)p].assign(row_gids, row_gids + n_owned);
+  if (!exchange_lists(A, comm, rank_, nranks_, out, in, err)) return false;
+  std::unordered_map<int64_t, int> owner;
+  owner.reserve((size_t)n_rows * 2);
+  for (int p = 0; p < nranks_; ++p) for (int64_t g : in[(size_t)p]) owner[g] = p;
+  // 2. for each peer: my ghost rows it owns -> message [row gid, ncols, col gids...]; value order = same walk
+  std::vector<std::vector<int64_t>> desc((size_t)nranks_);
+  std::vector<std::vector<int64_t>> send_res((size_t)nranks_), send_jac((size_t)nranks_);
+  for (int64_t r = n_owned; r < n_rows; ++r) {
+    auto it = owner.find(row_gids[r]);
+    if (it == owner.end()) { err = "halo: ghost row " + std::to_string(row_gids[r]) + " is owned by no rank"; return false; }
+    const int p = it->second;
+    desc[(size_t)p].push_back(row_gids[r]);
+    desc[(size_t)p].push_back(rowptr[r + 1] - rowptr[r]);
+    send_res[(size_t)p].push_back(r);
+    for (int64_t q = rowptr[r]; q < rowptr[r + 1]; ++q) { desc[(size_t)p].push_back(row_gids[colind[q]]); send_jac[(size_t)p].push_back(q); }
+  }
+  std::vector<std::vector<int64_t>> rdesc;
+  if (!exchange_lists(A, comm, rank_, nranks_, desc, rdesc, err)) return false;
+  // 3. destination positions on the owner
+  std::unordered_map<int64_t, int64_t> my_row;  // gid -> local row (owned and ghost: columns may be ghosts)
+  my_row.reserve((size_t)n_rows * 2);
+  for (int64_t r = 0; r < n_rows; ++r) my_row[row_gids[r]] = r;
+  peers_.assign((size_t)nranks_, Peer());
+  for (int p = 0; p < nranks_; ++p) {
+    if (p == rank_) continue;
+    std::vector<int64_t> recv_res, recv_jac;
+    const auto& d = rdesc[(size_t)p];
+    size_t k = 0;
+    while (k < d.size()) {
+      const int64_t gid = d[k++], nc = d[k++];
+      auto it = my_row.find(gid);
+      if (it == my_row.end() || it->second >= n_owned) { err = "halo: received a row this rank does not own"; return false; }
+      const int64_t r = it->second;
+      recv_res.push_back(r);
+      for (int64_t c = 0; c < nc; ++c) {
+        const int64_t cg = d[k++];
+        int64_t pos = -1;
+        auto ic = my_row.find(cg);
+        if (ic != my_row.end()) {
+          const int32_t lc = (int32_t)ic->second;
+          const int32_t* b = colind + rowptr[r];
+          const int32_t* e = colind + rowptr[r + 1];
+          const int32_t* f = std::lower_bound(b, e, lc);
+          if (f != e && *f == lc) pos = rowptr[r] + (f - b);
+        }
+        if (pos < 0) { err = "halo: owner row lacks a column present in the ghost copy (graphs are inconsistent)"; return false; }
+        recv_jac.push_back(pos);
+      }
+    }
+    Peer& P = peers_[(size_t)p];
+    P.n_send_res = (int64_t)send_res[(size_t)p].size(); P.n_send_jac = (int64_t)send_jac[(size_t)p].size();
+    P.n_recv_res = (int64_t)recv_res.size(); P.n_recv_jac = (int64_t)recv_jac.size();
+    if (!to_device(&P.d_send_res, send_res[(size_t)p], err) || !to_device(&P.d_send_jac, send_jac[(size_t)p], err) ||
+        !to_device(&P.d_recv_res, recv_res, err) || !to_device(&P.d_recv_jac, recv_jac, err)) return false;
+    CU_TRY(cudaMalloc(&P.d_sendbuf, std::max<int64_t>(1, P.n_send_res + P.n_send_jac) * sizeof(double)));
+    CU_TRY(cudaMalloc(&P.d_recvbuf, std::max<int64_t>(1, P.n_recv_res + P.n_recv_jac) * sizeof(double)));
+  }
+  ready_ = true;
+  return true;
+}
+
+bool HaloExchange::sum(double* res, double* jac, cudaStream_t st, std::string& err) {
+  NcclApi& A = api();
+  ncclComm_t comm = (ncclComm_t)comm_;
+  auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
+  for (int p = 0; p < nranks_; ++p) {
+    Peer& P = peers_[(size_t)p];
+    if (p == rank_) continue;
+    if (res && P.n_send_res) pack_kernel<<<blocks(P.n_send_res), 256, 0, st>>>(res, P.d_send_res, P.n_send_res, P.d_sendbuf);
+    if (jac && P.n_send_jac) pack_kernel<<<blocks(P.n_send_jac), 256, 0, st>>>(jac, P.d_send_jac, P.n_send_jac, P.d_sendbuf + P.n_send_res);
+  }
+  NCCL_TRY(A.GroupStart());
+  for (int p = 0; p < nranks_; ++p) {
+    Peer& P = peers_[(size_t)p];
+    if (p == rank_) continue;
+    const int64_t ns = (res ? P.n_send_res : 0) + (jac ? P.n_send_jac : 0);
+    const int64_t nr = (res ? P.n_recv_res : 0) + (jac ? P.n_recv_jac : 0);
+    // layout in the buffers is [res | jac]; when only one of them is exchanged send just that slice
+    double* sb = P.d_sendbuf + (res ? 0 : P.n_send_res);
+    double* rb = P.d_recvbuf + (res ? 0 : P.n_recv_res);
+    if (ns) NCCL_TRY(A.Send(sb, (size_t)ns, ncclFloat64, p, comm, st));
+    if (nr) NCCL_TRY(A.Recv(rb, (size_t)nr, ncclFloat64, p, comm, st));
+  }
+  NCCL_TRY(A.GroupEnd());
+  for (int p = 0; p < nranks_; ++p) {  // ascending source rank: fixed summation order
+    Peer& P = peers_[(size_t)p];
+    if (p == rank_) continue;
+    if (res && P.n_recv_res) unpack_add_kernel<<<blocks(P.n_recv_res), 256, 0, st>>>(P.d_recvbuf, P.d_recv_res, P.n_recv_res, res);
+    if (jac && P.n_recv_jac) unpack_add_kernel<<<blocks(P.n_recv_jac), 256, 0, st>>>(P.d_recvbuf + P.n_recv_res, P.d_recv_jac, P.n_recv_jac, jac);
+  }
+  CU_TRY(cudaGetLastError());
+  return true;
+}
+
+}  // namespace mrhyde_b200

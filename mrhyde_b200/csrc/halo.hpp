@@ -1,0 +1,45 @@
+// Multi-GPU halo sum: the replacement of Tpetra's Export(overlapped -> owned, ADD) for the residual
+// vector and the Jacobian values (linearAlgebraInterface_matrix.hpp:233-237, _vector.hpp:56-66;
+// maps built at linearAlgebraInterface_construct.hpp:159-207).
+//
+// Each rank assembles its own elements into its overlapped rows (owned rows first, then ghost rows).
+// halo sum: the values of every ghost row are packed, sent to the owning rank with NCCL send/recv
+// over NVLink, and added into the owner's row at positions matched through global column ids at
+// set-up.  Contributions are added source rank by source rank in ascending order, so the result is
+// reproducible.  NCCL is resolved with dlopen at run time (the library loads without it).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mrhyde_b200 {
+
+bool halo_unique_id(uint8_t* id128, std::string& err);
+
+class HaloExchange {
+ public:
+  HaloExchange() {}
+  ~HaloExchange();
+  bool init(const uint8_t* id128, int rank, int nranks, std::string& err);
+  // collective: builds send/receive maps from the global row ids of every rank
+  bool setup(int64_t n_rows, int64_t n_owned, const int64_t* row_gids, const int64_t* rowptr, const int32_t* colind, std::string& err);
+  bool sum(double* res, double* jac, cudaStream_t st, std::string& err);
+  bool ready() const { return ready_; }
+
+ private:
+  void* comm_ = nullptr;
+  int rank_ = 0, nranks_ = 1;
+  bool ready_ = false;
+  // per peer: what I send (positions in my res / jac arrays) and where received values are added
+  struct Peer {
+    int64_t n_send_res = 0, n_send_jac = 0, n_recv_res = 0, n_recv_jac = 0;
+    int64_t* d_send_res = nullptr; int64_t* d_send_jac = nullptr;   // source positions
+    int64_t* d_recv_res = nullptr; int64_t* d_recv_jac = nullptr;   // destination positions (-1: column absent on the owner)
+    double* d_sendbuf = nullptr; double* d_recvbuf = nullptr;
+  };
+  std::vector<Peer> peers_;
+};
+
+}  // namespace mrhyde_b200

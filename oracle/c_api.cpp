@@ -3,6 +3,7 @@
 // ctypes-facing C entry points of the CPU restatement.  Only tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference legs may load this library.
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -135,6 +136,26 @@ int oracle_get_bcs(void* hv, int32_t* codes) {
       codes[v * ns + s] = t == "Dirichlet" ? 1 : t == "weak Dirichlet" ? 2 : t == "Neumann" ? 3 : 0;
     }
   return 0;
+}
+
+// string-valued metadata: "modules", "var_names", "basis_types", "basis_orders" (comma separated),
+// "bc_expr <var> <side>" (the boundary data expression)
+const char* oracle_get_string(void* hv, const char* key) {
+  auto* h = (OracleHandle*)hv;
+  auto& am = *h->am;
+  const std::string k(key);
+  std::string out;
+  auto join = [&](const std::vector<std::string>& v) { std::string s; for (size_t i = 0; i < v.size(); ++i) { if (i) s += ","; s += v[i]; } return s; };
+  if (k == "modules") out = join(am.modules);
+  else if (k == "var_names") { std::vector<std::string> v; for (auto& x : am.dofs.vars) v.push_back(x.name); out = join(v); }
+  else if (k == "basis_types") { std::vector<std::string> v; for (auto& b : am.dofs.bases) v.push_back(b.type); out = join(v); }
+  else if (k == "basis_orders") { std::vector<std::string> v; for (auto& b : am.dofs.bases) v.push_back(std::to_string(b.order)); out = join(v); }
+  else if (k.compare(0, 8, "bc_expr ") == 0) {
+    int v = 0, s = 0;
+    if (std::sscanf(key + 8, "%d %d", &v, &s) == 2 && v >= 0 && v < (int)am.bcs.size() && s >= 0 && s < (int)am.bcs[v].size()) out = am.bcs[v][s].expr;
+  }
+  h->scratch = out;
+  return h->scratch.c_str();
 }
 
 int oracle_set_time(void* hv, int isTransient, double time, double deltat, int stage, int nstages, const double* A, const double* b,

@@ -36,6 +36,8 @@ def lib():
         L.oracle_print_tree.restype = C.c_char_p
         L.oracle_print_tree.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_get_string.restype = C.c_char_p
+        L.oracle_get_string.argtypes = [C.c_void_p, C.c_char_p]
         _LIB = L
     return _LIB
 
@@ -104,6 +106,25 @@ class OracleProblem:
     def _chk(self, rc):
         if rc != 0:
             raise RuntimeError(self.L.oracle_last_error().decode())
+
+    # ---- metadata -----------------------------------------------------------------------
+    def _s(self, key):
+        return self.L.oracle_get_string(self.h, key.encode()).decode()
+
+    def modules(self):
+        return self._s("modules")
+
+    def var_names(self):
+        return self._s("var_names").split(",")
+
+    def basis_type(self, b):
+        return self._s("basis_types").split(",")[b]
+
+    def basis_order(self, b):
+        return int(self._s("basis_orders").split(",")[b])
+
+    def bc_exprs(self):
+        return [[self._s("bc_expr %d %d" % (v, s)) for s in range(self.nsides)] for v in range(self.nvars)]
 
     # ---- reference tables -------------------------------------------------------------
     def ref_basis(self, b):

@@ -1,0 +1,186 @@
+"""GPU parity tests of the thermal path: CUDA kernels through the C ABI vs the CPU oracle on the
+same seeded inputs.  Tolerance (north_star): 1e-12 relative on residual entries (to the vector
+max-norm) and on matrix values (to the row max-norm); identical CSR pattern by construction (the
+graph is an input)."""
+import numpy as np
+import pytest
+
+import configs
+import helpers
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _device_arrays(op, u):
+    import torch
+    dev = torch.device("cuda:0")
+    return (torch.from_numpy(np.ascontiguousarray(u)).to(dev), torch.zeros(op.num_dofs, dtype=torch.float64, device=dev),
+            torch.zeros(op.nnz, dtype=torch.float64, device=dev))
+
+
+def _check(op, plan, u, time=None, oracle_kw=None, tol=TOL):
+    import torch
+    d_u, d_res, d_jac = _device_arrays(op, u)
+    res_ref, jac_ref = op.assemble_jacres(u, **(oracle_kw or {}))
+    plan.assemble_jacres(d_u, d_res, d_jac, time=time)
+    torch.cuda.synchronize()
+    e_res = helpers.rel_err_vec(d_res.cpu().numpy(), res_ref)
+    e_jac = helpers.rel_err_rows(d_jac.cpu().numpy(), jac_ref, op.rowptr)
+    assert e_res < tol, "residual rel err %.3e" % e_res
+    assert e_jac < tol, "Jacobian rel err %.3e" % e_jac
+    return d_res.cpu().numpy(), d_jac.cpu().numpy(), res_ref, jac_ref
+
+
+@pytest.mark.parametrize("name,cfg", [("2d", configs.THERMAL_2D), ("3d", configs.THERMAL_3D)])
+def test_regression_decks_match_oracle(oracle_lib, product_lib, name, cfg):
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    _check(op, plan, np.zeros(op.num_dofs))            # the state the reference's first Newton step sees
+    _check(op, plan, helpers.manufactured_state(op))   # non-trivial state
+
+
+def test_gold_l2_error_through_cuda_path(oracle_lib, product_lib):
+    """Solve the 2-D regression problem with the CUDA-assembled system and reproduce mrhyde.gold."""
+    import scipy.sparse.linalg as spla
+    import torch
+    cfg = configs.THERMAL_2D
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    d_u, d_res, d_jac = _device_arrays(op, np.zeros(op.num_dofs))
+    plan.assemble_jacres(d_u, d_res, d_jac)
+    torch.cuda.synchronize()
+    u = spla.spsolve(op.csr(d_jac.cpu().numpy()).tocsc(), d_res.cpu().numpy())
+    assert abs(op.l2_error(["T"], u) - configs.THERMAL_2D_GOLD["T"]) < 5e-9
+    assert abs(op.l2_error(["grad(T)[x]", "grad(T)[y]"], u) - configs.THERMAL_2D_GOLD["grad(T)"]) < 5e-7
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_perturbed_mesh_variable_coefficients(oracle_lib, product_lib, dim):
+    """Non-affine cells + x-dependent diffusion/source exercise the general per-point path."""
+    base = configs.THERMAL_2D if dim == 2 else configs.THERMAL_3D
+    upd = {"Mesh/perturb": 0.02, "Functions/thermal diffusion": "1.0+0.5*x*x+exp(-y)", "Mesh/NX": 9, "Mesh/NY": 7}
+    if dim == 3:
+        upd["Mesh/NZ"] = 5
+    cfg = configs.variant(base, **upd)
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    assert plan.stat("n_affine") < op.num_elems
+    _check(op, plan, helpers.manufactured_state(op))
+
+
+def test_affine_sheared_mesh_constant_coefficients(oracle_lib, product_lib):
+    """Stretched (non-cubic) brick keeps the table path honest about the metric tensor."""
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/xmax": 2.0, "Mesh/ymax": 0.5, "Mesh/zmin": -1.0, "Mesh/NX": 7, "Mesh/NY": 5, "Mesh/NZ": 6,
+                                                  "Functions/thermal diffusion": "2.5"})
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    assert plan.stat("n_affine") == op.num_elems
+    _check(op, plan, helpers.manufactured_state(op))
+
+
+def test_overwrite_mode_equals_accumulate_on_zeroed(oracle_lib, product_lib):
+    import torch
+    cfg = configs.THERMAL_3D
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    u = helpers.manufactured_state(op)
+    r1, j1, _, _ = _check(op, plan, u)
+    plan.set_option("accumulate", "false")
+    d_u, d_res, d_jac = _device_arrays(op, u)
+    d_res.fill_(7.0)
+    d_jac.fill_(-3.0)   # garbage the overwrite mode must replace
+    plan.assemble_jacres(d_u, d_res, d_jac)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_res.cpu().numpy(), r1)
+    assert np.array_equal(d_jac.cpu().numpy(), j1)
+
+
+def test_residual_only_and_jacobian_only(oracle_lib, product_lib):
+    import torch
+    cfg = configs.THERMAL_3D
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    u = helpers.manufactured_state(op)
+    r1, j1, _, _ = _check(op, plan, u)
+    d_u, d_res, d_jac = _device_arrays(op, u)
+    plan.assemble_res(d_u, d_res)
+    torch.cuda.synchronize()
+    res_scalar = op.assemble_res(u)                        # the ScalarT workset path of the oracle
+    assert helpers.rel_err_vec(d_res.cpu().numpy(), res_scalar) < TOL
+    assert np.array_equal(d_res.cpu().numpy(), r1)
+    d_res.zero_()
+    plan.assemble_jacres(d_u, None, d_jac, compute_residual=False)   # autotune flow, SURVEY 3.2
+    torch.cuda.synchronize()
+    assert np.array_equal(d_jac.cpu().numpy(), j1)
+
+
+def test_run_to_run_reproducible(oracle_lib, product_lib):
+    import torch
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 16, "Mesh/NY": 16, "Mesh/NZ": 16})
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    u = helpers.manufactured_state(op)
+    outs = []
+    for _ in range(3):
+        d_u, d_res, d_jac = _device_arrays(op, u)
+        plan.assemble_jacres(d_u, d_res, d_jac)
+        torch.cuda.synchronize()
+        outs.append((d_res.cpu().numpy(), d_jac.cpu().numpy()))
+    for r, j in outs[1:]:
+        assert np.array_equal(r, outs[0][0]) and np.array_equal(j, outs[0][1])
+
+
+def test_transient_bdf1_and_dirk(oracle_lib, product_lib):
+    """Mass term + stage/BDF combination (computeSolnTransientSeeded)."""
+    import torch
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Functions/density": "2.0", "Functions/specific heat": "1.5",
+                                                  "Functions/thermal source": "sin(t)*x+y*z"})
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    rng = np.random.default_rng(3)
+    u, up = rng.standard_normal(op.num_dofs), rng.standard_normal(op.num_dofs)
+    dev = torch.device("cuda:0")
+    d_up = torch.from_numpy(up).to(dev)
+    for (A, b, c) in (([[1.0]], [1.0], [1.0]), ([[0.5]], [1.0], [0.5])):   # BWE, DIRK-1,2 (solverManager_setup.hpp:181-250)
+        op.set_time(True, time=0.3, dt=0.01, stage=0, A=A, b=b, c=c, bdf=(1.0, -1.0))
+        ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=0, A=A, b=b, c=c, bdf=(1.0, -1.0), sol_prev=[d_up], sol_stage=[d_up])
+        _check(op, plan, u, time=ts, oracle_kw=dict(sol_prev=[up], sol_stage=[u]))
+    op.set_time(False)
+
+
+def test_weak_dirichlet_and_neumann_boundaries(oracle_lib, product_lib):
+    for dim, base in ((2, configs.THERMAL_2D), (3, configs.THERMAL_3D)):
+        upd = {"Solver/use strong DBCs": False, "Physics/assemble boundary terms": True, "Mesh/NX": 6, "Mesh/NY": 5, "Mesh/perturb": 0.01,
+               "Physics/Dirichlet conditions/T": {"left": "1.0+y", "top": "x*x"}, "Physics/Neumann conditions/T": {"right": "2.0*y-0.3"}}
+        if dim == 3:
+            upd["Mesh/NZ"] = 4
+        cfg = configs.variant(base, **upd)
+        op = oracle_lib.OracleProblem(cfg)
+        plan = helpers.plan_from_oracle(op, cfg)
+        _check(op, plan, helpers.manufactured_state(op))
+
+
+def test_host_buffer_entry_point(oracle_lib, product_lib):
+    cfg = configs.THERMAL_3D
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, indexed=True)
+    u = helpers.manufactured_state(op)
+    res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+    plan.assemble_jacres_host(u, res, jac)
+    res_ref, jac_ref = op.assemble_jacres(u)
+    assert helpers.rel_err_vec(res, res_ref) < TOL and helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL
+
+
+def test_device_expression_evaluator(oracle_lib, product_lib):
+    cfg = configs.variant(configs.THERMAL_3D, **{"Functions/f1": "exp(-x*x)*cos(3*y)+z^2/(1.0+x)", "Functions/f2": "max(x,y)*(x<0.5)+sqrt(z)-abs(y-0.5)+f1*2",
+                                                  "Mesh/NX": 4, "Mesh/NY": 4, "Mesh/NZ": 4})
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    for name in ("f1", "f2", "thermal source"):
+        for grp in range(op.num_groups):
+            wts, ip = op.group_info(grp)
+            ref = op.eval_function(name, grp)
+            xyz = np.stack([ip[0].ravel(), ip[1].ravel(), ip[2].ravel()], axis=1)
+            got = plan.eval_function(name, xyz).reshape(ref.shape)
+            assert np.max(np.abs(got - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref)))
