@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- fp64 residual+Jacobian assembly throughput of the thermal hex-Q1 path.
+
+Workload (BASELINE.json configs[1]): 3-D steady thermal, hex Q1, 128^3 inline brick, residual +
+Jacobian, source 12 pi^2 sin sin sin, all-boundary strong Dirichlet.  One step = one
+assembleJacRes(compute_jacobian, compute_residual) over every element of the rank's mesh, written
+into the CSR values / residual vector (overwrite mode, i.e. the caller's zeroing is not needed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference ...                          CPU restatement of the reference path
+                                                                (oracle/, all host cores as processes)
+N > 1 is launched by torch.distributed.run; the mesh is N bricks stacked along z (weak scaling),
+every rank assembles its slab and the shared-row contributions are summed with the NCCL halo sum.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fp64 residual+Jacobian elements/sec"
+UNIT = "elements/s"
+
+
+def workload_name(n, world):
+    return "thermal hex-Q1 %dx%dx%d inline brick, steady, residual+Jacobian%s" % (n, n, n * world, "" if world == 1 else " (%d z-slabs of %d^3)" % (world, n))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.path = "/tmp/bench_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]          # the loaded half of the samples
+            out["sm_mhz"] = float(np.median(top))
+            out["sm_max_mhz"] = mx
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY places that touch oracle/)
+# --------------------------------------------------------------------------------------------------
+def _oracle_cfg(n, nz):
+    return {"Mesh": {"dimension": 3, "element type": "hex", "xmin": 0.0, "xmax": 1.0, "ymin": 0.0, "ymax": 1.0, "zmin": 0.0, "zmax": float(nz) / n,
+                     "NX": n, "NY": n, "NZ": nz},
+            "Physics": {"modules": "thermal", "Dirichlet conditions": {"T": {"all boundaries": "0.0"}}},
+            "Discretization": {"order": {"T": 1}, "quadrature": 2},
+            "Functions": {"thermal source": "12*(pi*pi)*sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)"},
+            "Solver": {"solver": "steady-state", "workset size": 100}}
+
+
+_W = {}
+
+
+def _worker_init(n, nz):
+    from oracle import pyoracle
+    op = pyoracle.OracleProblem(_oracle_cfg(n, nz))
+    rng = np.random.default_rng(20261017)
+    _W["op"] = op
+    _W["u"] = rng.uniform(-1.0, 1.0, op.num_dofs)
+    _W["res"] = np.zeros(op.num_dofs)
+    _W["jac"] = np.zeros(op.nnz)
+
+
+def _worker_step(_):
+    op = _W["op"]
+    _W["res"][:] = 0.0
+    _W["jac"][:] = 0.0
+    t0 = time.perf_counter()
+    op.assemble_jacres(_W["u"], res=_W["res"], jac=_W["jac"])
+    return time.perf_counter() - t0, op.num_elems
+
+
+def cpu_baseline_serial(n, budget_s=15.0):
+    """Oracle (scalar C++ restatement, 1 thread == Kokkos::Serial) on a z-slab of the same mesh."""
+    from oracle import pyoracle
+    pyoracle.build()
+    nz = max(2, min(n, 16))
+    _worker_init(n, nz)
+    _worker_step(0)
+    t_total, elems, reps = 0.0, 0, 0
+    while t_total < budget_s and reps < 50:
+        dt, ne = _worker_step(0)
+        t_total += dt
+        elems += ne
+        reps += 1
+    return {"value": elems / t_total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle assembleJacRes on a %dx%dx%d z-slab of the workload, %d passes, %.1f s" % (n, n, nz, reps, t_total)}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference cannot be built here (Trilinos + MPI are absent), so this times
+    the oracle port, one process per host core like `mpiexec -n <cores>` of the serial build, each on
+    its own z-slab of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import pyoracle
+    pyoracle.build()
+    n = args.n
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    nz = 4
+    ctx = mp.get_context("fork")
+    pools = [ctx.Pool(1, initializer=_worker_init, initargs=(n, nz)) for _ in range(cores)]
+    try:
+        def step():
+            t0 = time.perf_counter()
+            rs = [p.apply_async(_worker_step, (0,)) for p in pools]
+            out = [r.get() for r in rs]
+            return time.perf_counter() - t0, sum(o[1] for o in out)
+        for _ in range(args.warmup):
+            step()
+        t_total, elems = 0.0, 0
+        for _ in range(args.steps):
+            dt, ne = step()
+            t_total += dt
+            elems += ne
+    finally:
+        for p in pools:
+            p.terminate()
+    value = elems / t_total
+    sample = "%d processes x (%dx%dx%d z-slab of the workload) per step" % (cores, n, n, nz)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(n, 1), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mrhyde_b200.problems import ThermalBrick
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the assembly path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    prob = ThermalBrick(3, [n, n, n], device=local, rank=rank, nranks=world, options={"accumulate": "false"})
+    plan = prob.plan
+    if world > 1:
+        uid = torch.from_numpy(plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
+        dist.broadcast(uid, 0)
+        plan.comm_init(uid.cpu().numpy(), rank, world)
+        plan.set_halo(prob.row_gids)
+    d_u = torch.from_numpy(prob.state()).to(dev)
+    d_res = torch.empty(prob.n_rows, dtype=torch.float64, device=dev)
+    d_jac = torch.empty(prob.nnz, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        plan.assemble_jacres(d_u, d_res, d_jac, stream=stream)
+        if world > 1:
+            plan.halo_sum(d_res, d_jac, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    plan.kernel_time(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier()
+    kern_ms, kern_n = plan.kernel_time(reset=True)
+    launches_per_step = plan.stat("kernel_launches_per_assemble") + (plan.stat("halo_launches_per_sum") if world > 1 else 0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    total_elems = prob.n_elem * world
+    value = total_elems * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call: pinned host sol in, res + J values out, every step
+    h_u = torch.from_numpy(prob.state()).pin_memory()
+    h_res = torch.empty(prob.n_rows, dtype=torch.float64).pin_memory()
+    h_jac = torch.empty(prob.nnz, dtype=torch.float64).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    plan.assemble_jacres_host(h_u.numpy(), h_res.numpy(), h_jac.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.assemble_jacres_host(h_u.numpy(), h_res.numpy(), h_jac.numpy())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = total_elems * e2e_steps / e2e_s
+    # the same load for ~1 s more so the clock sampler sees the kernel under load
+    t_end = time.perf_counter() + 1.0
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    assert bool(torch.isfinite(d_res).all()) and bool(torch.isfinite(d_jac[:: 97]).all())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = prob.algorithmic_bytes()
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "thermal_q1_volume_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(n, world), "elements_per_gpu": prob.n_elem, "rows_per_gpu": prob.n_rows, "nnz_per_gpu": prob.nnz,
+                           "l2": "inputs+outputs %.2f GB per GPU exceed the 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
+                           "output_mode": "overwrite (accumulate=false)", "patches": plan.stat("n_patches"), "patch_elements": plan.stat("patch_elements"),
+                           "elements_incl_halo": plan.stat("n_elem_with_halo"), "parallelism": "z-slabs x%d + NCCL halo sum" % world if world > 1 else "1 GPU"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                             "kernel": "thermal_q1_volume_kernel<3>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * prob.n_rows * world, "d2h_bytes_per_step": 8 * (prob.n_rows + prob.nnz) * world,
+                        "steps": e2e_steps, "api": "mrhyde_b200_assemble_jacres_host (pinned host buffers)"},
+                "gpu_launches": int(args.steps * launches_per_step), "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_serial(n)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="elements per brick edge (per GPU)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -117,7 +117,7 @@ struct mrhyde_b200_plan {
   int threads = 256;
   size_t smem = 0;
   int64_t n_affine = 0;
-  int launches_per_assemble = 0;
+  int launches_per_assemble = 0;   // kernels launched by the last assemble call
   bool accumulate = true;
   int stage_len = 0;
   std::vector<uint16_t> kmap, rmap;
@@ -328,6 +328,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
   out.accumulate = P->accumulate ? 1 : 0;
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
   const bool volume = opt_bool(P, "assemble volume terms", true);
+  int launched = 0;
   if (volume) {
     size_t slot = 0;
     record_begin(P, st, slot);
@@ -339,10 +340,12 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
       launch_thermal_q1_2d(P->th2, P->pp.n_patches, P->threads, P->smem, st);
     }
     record_end(P, st, slot);
+    ++launched;
     CUDA_OK(cudaGetLastError());
     if (!P->accumulate && !P->pp.orphan_rows.empty()) {
       const int n = (int)P->pp.orphan_rows.size();
       orphan_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(P->d_orphans.p, n, G, out);
+      ++launched;
     }
   } else if (!P->accumulate) {
     fail(MRHYDE_B200_ERR_UNSUPPORTED, "accumulate=false needs the volume pass (it defines every entry)");
@@ -351,13 +354,16 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     OutDev bout = out;
     bout.accumulate = 1;  // boundary groups always add on top of the volume result
     launch_boundary(P->boundary, sol, td, G, bout, st);
+    launched += (int)P->boundary.groups.size();
     CUDA_OK(cudaGetLastError());
   }
   if (want_jac && P->accumulate && P->d_fixed_diag.n > 0 && opt_bool(P, "use strong DBCs", true)) {
     const int n = (int)P->d_fixed_diag.n;
     fixed_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(P->d_fixed_diag.p, n, jac);
+    ++launched;
     CUDA_OK(cudaGetLastError());
   }
+  P->launches_per_assemble = launched;
 }
 
 }  // namespace
@@ -755,6 +761,7 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   if (k == "n_patches") *value = P->pp.n_patches;
   else if (k == "n_templates") *value = (int64_t)P->pp.tmpl.size();
   else if (k == "kernel_launches_per_assemble") *value = P->launches_per_assemble;
+  else if (k == "halo_launches_per_sum") *value = P->halo ? P->halo->launches_per_sum() : 0;
   else if (k == "smem_bytes") *value = (int64_t)P->smem;
   else if (k == "threads_per_block") *value = P->threads;
   else if (k == "n_elem") *value = P->mesh.nelem;

@@ -216,11 +216,12 @@ bool HaloExchange::sum(double* res, double* jac, cudaStream_t st, std::string& e
   NcclApi& A = api();
   ncclComm_t comm = (ncclComm_t)comm_;
   auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
+  int launched = 0;
   for (int p = 0; p < nranks_; ++p) {
     Peer& P = peers_[(size_t)p];
     if (p == rank_) continue;
-    if (res && P.n_send_res) pack_kernel<<<blocks(P.n_send_res), 256, 0, st>>>(res, P.d_send_res, P.n_send_res, P.d_sendbuf);
-    if (jac && P.n_send_jac) pack_kernel<<<blocks(P.n_send_jac), 256, 0, st>>>(jac, P.d_send_jac, P.n_send_jac, P.d_sendbuf + P.n_send_res);
+    if (res && P.n_send_res) pack_kernel<<<blocks(P.n_send_res), 256, 0, st>>>(res, P.d_send_res, P.n_send_res, P.d_sendbuf), ++launched;
+    if (jac && P.n_send_jac) pack_kernel<<<blocks(P.n_send_jac), 256, 0, st>>>(jac, P.d_send_jac, P.n_send_jac, P.d_sendbuf + P.n_send_res), ++launched;
   }
   NCCL_TRY(A.GroupStart());
   for (int p = 0; p < nranks_; ++p) {
@@ -238,9 +239,10 @@ bool HaloExchange::sum(double* res, double* jac, cudaStream_t st, std::string& e
   for (int p = 0; p < nranks_; ++p) {  // ascending source rank: fixed summation order
     Peer& P = peers_[(size_t)p];
     if (p == rank_) continue;
-    if (res && P.n_recv_res) unpack_add_kernel<<<blocks(P.n_recv_res), 256, 0, st>>>(P.d_recvbuf, P.d_recv_res, P.n_recv_res, res);
-    if (jac && P.n_recv_jac) unpack_add_kernel<<<blocks(P.n_recv_jac), 256, 0, st>>>(P.d_recvbuf + P.n_recv_res, P.d_recv_jac, P.n_recv_jac, jac);
+    if (res && P.n_recv_res) unpack_add_kernel<<<blocks(P.n_recv_res), 256, 0, st>>>(P.d_recvbuf, P.d_recv_res, P.n_recv_res, res), ++launched;
+    if (jac && P.n_recv_jac) unpack_add_kernel<<<blocks(P.n_recv_jac), 256, 0, st>>>(P.d_recvbuf + P.n_recv_res, P.d_recv_jac, P.n_recv_jac, jac), ++launched;
   }
+  launches_ = launched;
   CU_TRY(cudaGetLastError());
   return true;
 }

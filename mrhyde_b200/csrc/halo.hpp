@@ -27,11 +27,13 @@ class HaloExchange {
   bool setup(int64_t n_rows, int64_t n_owned, const int64_t* row_gids, const int64_t* rowptr, const int32_t* colind, std::string& err);
   bool sum(double* res, double* jac, cudaStream_t st, std::string& err);
   bool ready() const { return ready_; }
+  int launches_per_sum() const { return launches_; }
 
  private:
   void* comm_ = nullptr;
   int rank_ = 0, nranks_ = 1;
   bool ready_ = false;
+  int launches_ = 0;
   // per peer: what I send (positions in my res / jac arrays) and where received values are added
   struct Peer {
     int64_t n_send_res = 0, n_send_jac = 0, n_recv_res = 0, n_recv_jac = 0;

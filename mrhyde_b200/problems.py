@@ -1,0 +1,79 @@
+"""Set-up helpers that play the role of the reference host for synthetic inline meshes: they build
+the arrays of mrhyde_b200.inline_mesh and feed them through the C ABI exactly as INTEGRATION.md
+describes for a MrHyDE host (mesh -> set_mesh, DOF manager -> lids, CrsGraph -> set_graph,
+Functions/Physics sublists -> set_function/set_option)."""
+import numpy as np
+
+from . import inline_mesh as im
+from .capi import AssemblyPlan
+
+# regression/thermal/3D_verification/input.yaml and 2D_verification/input.yaml source terms
+THERMAL_SOURCE = {2: "8*(pi*pi)*sin(2*pi*x)*sin(2*pi*y)", 3: "12*(pi*pi)*sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)"}
+
+
+class ThermalBrick:
+    """Steady thermal, HGRAD Q1, all-boundary strong Dirichlet on an inline brick; with nranks > 1 the
+    global mesh is `nranks` bricks stacked along the last axis (weak scaling, Zprocs = nranks) and this
+    object holds rank `rank`'s slab: owned rows first, the ghost plane (owned by rank+1) last."""
+
+    def __init__(self, dim, n, device=0, rank=0, nranks=1, functions=None, options=None):
+        self.dim, self.n, self.rank, self.nranks = dim, [int(v) for v in n[:dim]], rank, nranks
+        n = self.n
+        lo = [0.0] * 3
+        hi = [1.0] * 3
+        lo[dim - 1] = float(rank)
+        hi[dim - 1] = float(rank + 1)
+        nodes, conn = im.brick(dim, n, lo, hi)
+        # keep the global problem on the unit cube so the source term matches the regression deck
+        nodes[:, dim - 1] /= float(nranks)
+        self.nodes, self.conn = nodes, conn
+        self.lids = conn  # Q1 scalar field: local dof id == local node id (owned planes first by construction)
+        self.rowptr, self.colind = im.q1_graph(dim, n)
+        nn = [v + 1 for v in n]
+        plane = int(np.prod(nn[:-1]))
+        self.n_rows = int(np.prod(nn))
+        self.n_owned = self.n_rows if rank == nranks - 1 else self.n_rows - plane
+        self.row_gids = np.arange(self.n_rows, dtype=np.int64) + rank * n[-1] * plane
+        # strong Dirichlet on the GLOBAL boundary only (partition planes are interior)
+        idx = np.arange(self.n_rows)
+        fixed = np.zeros(self.n_rows, dtype=bool)
+        stride = 1
+        for d in range(dim):
+            c = (idx // stride) % nn[d]
+            if d < dim - 1:
+                fixed |= (c == 0) | (c == nn[d] - 1)
+            else:
+                fixed |= ((c == 0) & (rank == 0)) | ((c == nn[d] - 1) & (rank == nranks - 1))
+            stride *= nn[d]
+        fixed = fixed.astype(np.uint8)
+        self.is_fixed = fixed
+        self.n_elem = conn.shape[0]
+        self.nnz = int(self.rowptr[-1])
+        pts, wts, val, grad = im.q1_reference(dim)
+        nv = 2 ** dim
+        self.plan = AssemblyPlan("thermal", dim, ["T"], [0], [dict(type="HGRAD", order=1, card=nv, val=val, grad=grad)], nv,
+                                 np.arange(nv, dtype=np.int32).reshape(1, nv), pts, wts, device=device)
+        fn = {"thermal source": THERMAL_SOURCE[dim]}
+        fn.update(functions or {})
+        for k, v in fn.items():
+            self.plan.set_function(k, v)
+        for k, v in (options or {}).items():
+            self.plan.set_option(k, v)
+        self.plan.set_mesh_indexed(nodes, conn, self.lids)
+        self.plan.set_graph(self.rowptr, self.colind, self.is_fixed, n_owned=self.n_owned)
+        self.plan.finalize()
+
+    def state(self, seed=20261017):
+        """u = manufactured solution + 1e-3 U(-1,1), same values on shared rows of every rank."""
+        x = self.nodes
+        u = np.prod(np.sin(2.0 * np.pi * x), axis=1)
+        if self.nranks == 1:
+            noise = np.random.default_rng(seed).uniform(-1.0, 1.0, size=self.n_rows)
+        else:  # a function of the global id, so the replicas of a shared row agree across ranks
+            noise = np.modf(np.sin(self.row_gids * 12.9898) * 43758.5453)[0]
+        return u + 1e-3 * noise
+
+    # algorithmic bytes per element, SURVEY 8(d): LIDs + unique vertices + state + residual + J values
+    def algorithmic_bytes(self):
+        nv = 2 ** self.dim
+        return 4.0 * nv * self.n_elem + 8.0 * self.dim * self.nodes.shape[0] + 8.0 * self.n_rows + 8.0 * self.n_rows + 8.0 * self.nnz
