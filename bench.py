@@ -203,7 +203,7 @@ def run_ours(args):
         uid = torch.from_numpy(plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
         dist.broadcast(uid, 0)
         plan.comm_init(uid.cpu().numpy(), rank, world)
-        plan.set_halo(prob.row_gids)
+        plan.set_halo(prob.col_gids)
     d_u = torch.from_numpy(prob.state()).to(dev)
     d_res = torch.empty(prob.n_rows, dtype=torch.float64, device=dev)
     d_jac = torch.empty(prob.nnz, dtype=torch.float64, device=dev)

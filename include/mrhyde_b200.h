@@ -167,8 +167,11 @@ int mrhyde_b200_assemble_jacres_host(mrhyde_b200_plan* plan, const double* sol, 
  * into the owning rank's rows in fixed neighbour-rank order. */
 int mrhyde_b200_comm_unique_id(uint8_t* id128);                      /* ncclGetUniqueId, 128 bytes */
 int mrhyde_b200_plan_comm_init(mrhyde_b200_plan* plan, const uint8_t* id128, int rank, int nranks);
-/* Global ids of this rank's rows (owned then ghost); collective over the communicator. */
-int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* plan, const int64_t* row_gids /*host [n_rows]*/);
+/* Global ids of this rank's local column indices: entries [0,n_rows) are the rows (owned then ghost, the
+ * overlapped map), entries [n_rows,n_cols) are column-only ghosts -- remote columns that owned interface rows
+ * need so that the summed row is complete (the column map of the owned Tpetra matrix J that
+ * exportMatrixFromOverlapped fills).  n_cols >= n_rows.  Collective over the communicator. */
+int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* plan, int64_t n_cols, const int64_t* col_gids /*host [n_cols]*/);
 int mrhyde_b200_halo_sum(mrhyde_b200_plan* plan, double* res, double* jac_values, void* stream);
 
 /* ---- introspection (tests, bench) ----------------------------------------------------------- */

@@ -88,7 +88,7 @@ def lib():
         L.mrhyde_b200_assemble_jacres_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(TimeData), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_comm_unique_id.argtypes = [C.c_void_p]
         L.mrhyde_b200_plan_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-        L.mrhyde_b200_plan_set_halo.argtypes = [C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_plan_set_halo.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.mrhyde_b200_halo_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_stat.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
         L.mrhyde_b200_plan_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -319,9 +319,10 @@ class AssemblyPlan:
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
         self._chk(self.L.mrhyde_b200_plan_comm_init(self.h, _ptr(uid), rank, nranks))
 
-    def set_halo(self, row_gids):
-        g = np.ascontiguousarray(row_gids, dtype=np.int64)
-        self._chk(self.L.mrhyde_b200_plan_set_halo(self.h, _ptr(g)))
+    def set_halo(self, col_gids):
+        """col_gids: global ids of the local column ids (rows first, then column-only ghosts)."""
+        g = np.ascontiguousarray(col_gids, dtype=np.int64)
+        self._chk(self.L.mrhyde_b200_plan_set_halo(self.h, len(g), _ptr(g)))
 
     def halo_sum(self, res, jac, stream=None):
         self._chk(self.L.mrhyde_b200_halo_sum(self.h, _ptr(res), _ptr(jac), C.c_void_p(stream) if stream else None))

@@ -733,14 +733,16 @@ int mrhyde_b200_plan_comm_init(mrhyde_b200_plan* P, const uint8_t* id128, int ra
   ABI_END
 }
 
-int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* P, const int64_t* row_gids) {
+int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* P, int64_t n_cols, const int64_t* col_gids) {
   ABI_BEGIN
-  if (!P || !row_gids) fail(MRHYDE_B200_ERR_INVALID, "set_halo: null argument");
+  if (!P || !col_gids) fail(MRHYDE_B200_ERR_INVALID, "set_halo: null argument");
   if (!P->halo) fail(MRHYDE_B200_ERR_STATE, "set_halo: call plan_comm_init first");
   if (!P->have_graph) fail(MRHYDE_B200_ERR_STATE, "set_halo: call set_graph first");
+  if (n_cols < P->mesh.nrows) fail(MRHYDE_B200_ERR_INVALID, "set_halo: n_cols must be >= n_rows");
+  for (int32_t c : P->mesh.colind) if (c < 0 || c >= n_cols) fail(MRHYDE_B200_ERR_INVALID, "set_halo: a column index of the graph is outside [0, n_cols)");
   CUDA_OK(cudaSetDevice(P->device));
   std::string err;
-  if (!P->halo->setup(P->mesh.nrows, P->mesh.nowned, row_gids, P->mesh.rowptr.data(), P->mesh.colind.data(), err)) fail(MRHYDE_B200_ERR_NCCL, err);
+  if (!P->halo->setup(P->mesh.nrows, P->mesh.nowned, n_cols, col_gids, P->mesh.rowptr.data(), P->mesh.colind.data(), err)) fail(MRHYDE_B200_ERR_NCCL, err);
   ABI_END
 }
 

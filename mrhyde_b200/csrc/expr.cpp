@@ -113,11 +113,18 @@ Pieces split_expression(std::string s) {
   } else if (s.front() == '(' && s.back() == ')') {
     out.push_back({"", s.substr(1, s.size() - 2)});
   } else {
-    // name(args) with an unknown name: the reference turns the name into the op string; no kernel knows it
+    // name(args) where isOperator refused the string because args contain parentheses (interpreter.cpp:316-341):
+    // the reference makes `name` the op of a single dependency, e.g. exp(-(a+b)^2) -> exp applied to -(a+b)^2
     size_t pindex = std::string::npos;
     for (size_t k = 1; k + 1 < s.size(); ++k) if (s[k] == '(') { pindex = k; break; }
-    if (pindex != std::string::npos && s.back() == ')')
-      throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE was not able to decompose or find: " + s);
+    if (pindex != std::string::npos && s.back() == ')') {
+      const std::string name = s.substr(0, pindex);
+      static const char* const unary[] = {"sin", "cos", "tan", "exp", "log", "abs", "sqrt", "sinh", "cosh"};
+      bool known = false;
+      for (const char* u : unary) known = known || name == u;
+      if (!known) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: MrHyDE was not able to decompose or find: " + s);
+      out.push_back({name, s.substr(pindex + 1, s.size() - pindex - 2)});
+    }
   }
   return out;
 }

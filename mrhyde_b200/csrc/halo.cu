@@ -144,7 +144,8 @@ static bool exchange_lists(NcclApi& A, ncclComm_t comm, int rank, int nranks, co
   return true;
 }
 
-bool HaloExchange::setup(int64_t n_rows, int64_t n_owned, const int64_t* row_gids, const int64_t* rowptr, const int32_t* colind, std::string& err) {
+bool HaloExchange::setup(int64_t n_rows, int64_t n_owned, int64_t n_cols, const int64_t* row_gids, const int64_t* rowptr, const int32_t* colind, std::string& err) {
+  // row_gids doubles as the column gid table: [0,n_rows) rows, [n_rows,n_cols) column-only ghosts
   NcclApi& A = api();
   ncclComm_t comm = (ncclComm_t)comm_;
   ready_ = false;
@@ -170,9 +171,9 @@ bool HaloExchange::setup(int64_t n_rows, int64_t n_owned, const int64_t* row_gid
   std::vector<std::vector<int64_t>> rdesc;
   if (!exchange_lists(A, comm, rank_, nranks_, desc, rdesc, err)) return false;
   // 3. destination positions on the owner
-  std::unordered_map<int64_t, int64_t> my_row;  // gid -> local row (owned and ghost: columns may be ghosts)
-  my_row.reserve((size_t)n_rows * 2);
-  for (int64_t r = 0; r < n_rows; ++r) my_row[row_gids[r]] = r;
+  std::unordered_map<int64_t, int64_t> my_row;  // gid -> local column id (rows, then column-only ghosts)
+  my_row.reserve((size_t)n_cols * 2);
+  for (int64_t r = 0; r < n_cols; ++r) my_row[row_gids[r]] = r;
   peers_.assign((size_t)nranks_, Peer());
   for (int p = 0; p < nranks_; ++p) {
     if (p == rank_) continue;

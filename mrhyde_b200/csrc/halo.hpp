@@ -24,7 +24,7 @@ class HaloExchange {
   ~HaloExchange();
   bool init(const uint8_t* id128, int rank, int nranks, std::string& err);
   // collective: builds send/receive maps from the global row ids of every rank
-  bool setup(int64_t n_rows, int64_t n_owned, const int64_t* row_gids, const int64_t* rowptr, const int32_t* colind, std::string& err);
+  bool setup(int64_t n_rows, int64_t n_owned, int64_t n_cols, const int64_t* col_gids, const int64_t* rowptr, const int32_t* colind, std::string& err);
   bool sum(double* res, double* jac, cudaStream_t st, std::string& err);
   bool ready() const { return ready_; }
   int launches_per_sum() const { return launches_; }

@@ -28,12 +28,28 @@ class ThermalBrick:
         nodes[:, dim - 1] /= float(nranks)
         self.nodes, self.conn = nodes, conn
         self.lids = conn  # Q1 scalar field: local dof id == local node id (owned planes first by construction)
-        self.rowptr, self.colind = im.q1_graph(dim, n)
         nn = [v + 1 for v in n]
         plane = int(np.prod(nn[:-1]))
         self.n_rows = int(np.prod(nn))
         self.n_owned = self.n_rows if rank == nranks - 1 else self.n_rows - plane
         self.row_gids = np.arange(self.n_rows, dtype=np.int64) + rank * n[-1] * plane
+        if rank == 0:
+            self.rowptr, self.colind = im.q1_graph(dim, n)
+            self.col_gids = self.row_gids
+        else:
+            # The bottom plane is owned here but shared with rank-1's elements: its rows also couple to the plane
+            # below, which no local element touches.  Those nodes become column-only ghosts (local column ids
+            # >= n_rows), i.e. the column map of the owned matrix that Tpetra's export fills.
+            n_ext = list(n)
+            n_ext[-1] += 1
+            rp, ci = im.q1_graph(dim, n_ext)           # box extended by one plane below; ext id = local id + plane
+            rp = rp[plane:] - rp[plane]
+            ci = ci[int(im.q1_graph(dim, n_ext)[0][plane]):].astype(np.int64) - plane
+            ci = np.where(ci < 0, self.n_rows + (ci + plane), ci)   # plane -1 -> column-only ghost ids
+            rows = np.repeat(np.arange(self.n_rows), np.diff(rp))
+            order = np.lexsort((ci, rows))             # ascending local column ids within each row
+            self.rowptr, self.colind = rp.astype(np.int64), ci[order].astype(np.int32)
+            self.col_gids = np.concatenate([self.row_gids, np.arange(plane, dtype=np.int64) + (rank * n[-1] - 1) * plane])
         # strong Dirichlet on the GLOBAL boundary only (partition planes are interior)
         idx = np.arange(self.n_rows)
         fixed = np.zeros(self.n_rows, dtype=bool)

@@ -286,6 +286,8 @@ struct Engine : EngineBase {
     const bool side = (loc == "side ip");
     const Group& g = side ? am.boundary_groups[grp] : am.groups[grp];
     wkset.isOnSide = side;
+    // postprocess evaluates true solutions at the current (post-step) time: am.td.time when steady, else stage time
+    wkset.time = am.td.isTransient && !am.td.butcher_c.empty() ? am.td.time + am.td.butcher_c[am.td.stage] * am.td.deltat : am.td.time;
     pointAtGroup(am, g, side);
     wkset.reset();
     Vista<EvalT> v = fm.evaluate(name, loc);

@@ -75,3 +75,60 @@ def manufactured_state(op, seed=20261017):
     must treat them like any other column."""
     rng = np.random.default_rng(seed)
     return 0.3 * np.sin(1.0 + 0.7 * np.arange(op.num_dofs) / max(1, op.num_dofs)) + 1e-3 * rng.uniform(-1.0, 1.0, op.num_dofs)
+
+
+# ---- a minimal stand-in for the reference's solver loop (solverManager_solvers.hpp:13-31, 40-282, 290-640) ------
+# so that assembled systems can be checked against the L2 errors the reference's mrhyde.gold files print.
+def dirichlet_values(op, cfg, time=0.0):
+    """Strong-Dirichlet data at the fixed dofs (HGRAD Q1: dof == node), evaluated like setDirichlet does."""
+    import math
+    vals = np.zeros(op.num_dofs)
+    dc = cfg.get("Physics", {}).get("Dirichlet conditions", {})
+    sides = SIDE_NAMES_2D if op.dim == 2 else SIDE_NAMES_3D
+    x = op.nodes
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    on = {"left": np.isclose(x[:, 0], lo[0]), "right": np.isclose(x[:, 0], hi[0]), "bottom": np.isclose(x[:, 1], lo[1]), "top": np.isclose(x[:, 1], hi[1])}
+    if op.dim == 3:
+        on["back"] = np.isclose(x[:, 2], lo[2])
+        on["front"] = np.isclose(x[:, 2], hi[2])
+    env = {"sin": np.sin, "cos": np.cos, "exp": np.exp, "pi": math.pi, "x": x[:, 0], "y": x[:, 1], "z": x[:, 2] if op.dim == 3 else 0.0, "t": time}
+    for var, spec in dc.items():
+        if not isinstance(spec, dict):
+            continue
+        for side, expr in spec.items():
+            names = sides if side == "all boundaries" else [side]
+            v = eval(str(expr).replace("^", "**"), {"__builtins__": {}}, env) * np.ones(op.num_dofs)
+            for s in names:
+                vals[on[s]] = v[on[s]]
+    return vals
+
+
+def newton_steady(op, cfg, assemble, iters=2):
+    """assemble(u) -> (res = -F(u), J values); u <- u + J^-1 res, strong-Dirichlet rows carry res = 0, J(d,d) = 1."""
+    import scipy.sparse.linalg as spla
+    u = np.zeros(op.num_dofs)
+    fixed = op.is_fixed.astype(bool)
+    u[fixed] = dirichlet_values(op, cfg)[fixed]
+    for _ in range(iters):
+        res, jac = assemble(u)
+        u = u + spla.spsolve(op.csr(jac).tocsc(), res)
+    return u
+
+
+def gold_errors(case):
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regression_gold.json")))
+    return g[case]["deck"], g[case]["errors"]
+
+
+def deck_to_cfg(deck):
+    """mrhyde input deck (golden fixture) -> the flat-block form the oracle reads (block sublists dropped)."""
+    import copy
+    cfg = copy.deepcopy(deck)
+    for sec in ("Physics", "Discretization"):
+        blk = cfg.get(sec, {})
+        keys = [k for k in blk if k.startswith("eblock")]
+        for k in keys:
+            blk.update(blk.pop(k))
+    return cfg

@@ -1,0 +1,177 @@
+"""CPU-side checks of the C-ABI library (no GPU, no compute calls on a device): the shared object loads,
+exports every symbol include/mrhyde_b200.h declares, validates its inputs like the header says, and its
+host-side plan analysis (expression compiler, patches, scatter programs) is consistent."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import configs
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "mrhyde_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mrhyde_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    L = product_lib.lib()
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for s in declared:
+        assert hasattr(L, s), "libmrhyde_b200.so does not export %s" % s
+    assert sorted(product_lib.SYMBOLS) == declared, "capi.SYMBOLS and the header disagree"
+    assert b"sm_100a" in L.mrhyde_b200_version()
+
+
+def test_no_cpu_fallback_without_a_device(product_lib):
+    """On a box without CUDA plan_create(device >= 0) must fail loudly; with CUDA this is covered by the gpu tests."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from mrhyde_b200 import inline_mesh as im
+    pts, wts, val, grad = im.q1_reference(3)
+    with pytest.raises(product_lib.MrhydeB200Error) as ei:
+        product_lib.AssemblyPlan("thermal", 3, ["T"], [0], [dict(type="HGRAD", order=1, card=8, val=val, grad=grad)], 8,
+                                 np.arange(8, dtype=np.int32).reshape(1, 8), pts, wts, device=0)
+    assert ei.value.code == product_lib.ERR_CUDA and "no CPU path" in ei.value.message
+
+
+def _host_plan(oracle_lib, cfg, **kw):
+    op = oracle_lib.OracleProblem(cfg)
+    return op, helpers.plan_from_oracle(op, cfg, device=-1, **kw)
+
+
+def test_host_only_plan_refuses_to_assemble(oracle_lib, product_lib):
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3})
+    op, plan = _host_plan(oracle_lib, cfg)
+    assert plan.stat("n_elem") == op.num_elems and plan.stat("nnz") == op.nnz and plan.stat("n_affine") == op.num_elems
+    u, r, j = np.zeros(op.num_dofs), np.zeros(op.num_dofs), np.zeros(op.nnz)
+    with pytest.raises(product_lib.MrhydeB200Error) as ei:
+        plan.assemble_jacres_host(u, r, j)
+    assert ei.value.code == product_lib.ERR_STATE
+
+
+def test_argument_validation(oracle_lib, product_lib):
+    cfg = configs.variant(configs.THERMAL_2D, **{"Mesh/NX": 4, "Mesh/NY": 4})
+    op = oracle_lib.OracleProblem(cfg)
+    rb = op.ref_basis(0)
+    mk = lambda: product_lib.AssemblyPlan("thermal", 2, ["T"], [0], [dict(type="HGRAD", order=1, card=4, val=rb["val"], grad=rb["grad"])], 4,
+                                          op.offsets, op.qpts, op.qwts, device=-1)
+    p = mk()
+    with pytest.raises(product_lib.MrhydeB200Error):
+        p.set_option("no such option", "1")                      # unknown keys are an error, never ignored
+    with pytest.raises(product_lib.MrhydeB200Error):
+        p.finalize()                                             # before set_mesh / set_graph
+    p.set_mesh(op.elem_nodes, op.lids)
+    bad = op.colind.copy()
+    bad[[0, 1]] = bad[[1, 0]]
+    with pytest.raises(product_lib.MrhydeB200Error):
+        p.set_graph(op.rowptr, bad, op.is_fixed)                 # columns must ascend (fillComplete'd graph)
+    p.set_function("thermal source", "sin(x")                    # reference: unclosed parenthesis
+    p.set_graph(op.rowptr, op.colind, op.is_fixed)
+    with pytest.raises(product_lib.MrhydeB200Error) as ei:
+        p.finalize()
+    assert ei.value.code == product_lib.ERR_PARSE
+    q = mk()
+    q.set_mesh(op.elem_nodes, op.lids)
+    short = op.rowptr[:-3].copy()                                # graph with fewer rows than the LIDs reference
+    q.set_graph(short, op.colind[: short[-1]], op.is_fixed[: len(short) - 1])
+    with pytest.raises(product_lib.MrhydeB200Error):
+        q.finalize()
+    with pytest.raises(product_lib.MrhydeB200Error) as ei:
+        product_lib.AssemblyPlan("maxwell", 3, ["E"], [0], [dict(type="HGRAD", order=1, card=4, val=rb["val"], grad=rb["grad"])], 4,
+                                 op.offsets, op.qpts, op.qwts, device=-1).finalize()
+    assert ei.value.code in (product_lib.ERR_STATE, product_lib.ERR_UNSUPPORTED)
+
+
+EXPRS = {
+    "a": "1.0", "b": "2.0", "Ha": "1.0", "gtst": "a+b",
+    "f0": "sin(x+y+t)", "f1": "x+exp(y)", "f2": "8*(pi^2)*sin(2*pi*x+1)*sin(2*pi*y+1)", "f3": "-exp(x)", "f4": "(a-sin(x))^(2+b)",
+    "f5": "(a+2.0)*(b-pi)", "f6": "(a+b) + ((x+y)*a - 2.0)", "f7": "exp(-(a+b)^2)", "f8": "sin(gtst)", "f9": "8*pi^2", "f10": "min(a,b)",
+    "f11": "a <= b", "f13": "(1+exp(-2.0*Ha))/(2.0*exp(-1.0*Ha))",
+    "g0": "12*(pi*pi)*sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)", "g1": "1.0+0.5*x*x+exp(-y)", "g2": "max(x,y)-min(y,z)+abs(x-0.5)",
+    "g3": "sqrt(x*x+y*y)/(1.0+z)", "g4": "(x<0.5)*2.0+(x>=0.5)*3.0", "g5": "cosh(x)-sinh(y)+tan(0.3*z)+log(1.0+x)", "g6": "n[x]*x+n[y]*y-n[z]",
+    "g7": "2.0^x^2", "g8": "x-y-z", "g9": "x/y/2.0",
+}
+
+
+def _py_eval(expr, fn, v):
+    """Independent evaluation with Python semantics arranged to match the reference's left-to-right rules."""
+    x, y, z, t, nx, ny, nz = v
+    env = {"sin": math.sin, "cos": math.cos, "exp": math.exp, "log": math.log, "tan": math.tan, "abs": abs, "max": max, "min": min,
+           "sqrt": math.sqrt, "sinh": math.sinh, "cosh": math.cosh, "pi": math.pi, "x": x, "y": y, "z": z, "t": t, "nx": nx, "ny": ny, "nz": nz}
+    for k in ("a", "b", "Ha"):
+        env[k] = float(fn[k])
+    env["gtst"] = env["a"] + env["b"]
+    e = expr.replace("n[x]", "nx").replace("n[y]", "ny").replace("n[z]", "nz")
+    if expr == "2.0^x^2":
+        return (2.0 ** x) ** 2                                   # the reference applies ^ left to right
+    return float(eval(e.replace("^", "**"), {"__builtins__": {}}, env))
+
+
+def test_expression_compiler_matches_reference_semantics(product_lib):
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(0.05, 0.95, size=(40, 7))
+    for name, expr in EXPRS.items():
+        got = product_lib.expr_eval_host(EXPRS, name, pts)
+        want = np.array([_py_eval(expr, EXPRS, v) for v in pts])
+        assert np.allclose(got, want, rtol=1e-14, atol=1e-14), (name, expr, np.max(np.abs(got - want)))
+    # constant trees are folded at set-up like the reference does (functionManager_create.hpp:519-534)
+    assert "const" in product_lib.expr_disassemble(EXPRS, "f13").lower()
+    for bad in ("sin(x", "x)+1", "foo(x)", "1.0+undefined_name"):
+        with pytest.raises(product_lib.MrhydeB200Error):
+            product_lib.expr_eval_host({"bad": bad}, "bad", pts)
+
+
+@pytest.mark.parametrize("dim,perturb", [(2, 0.0), (3, 0.0), (3, 0.03)])
+def test_scatter_programs_equal_serial_element_loop(oracle_lib, product_lib, dim, perturb):
+    """The plan's pull-scatter programs (owner-computes patches + templates) must reproduce the reference's serial
+    element loop (scatter.hpp:162-278) for arbitrary staged element matrices, including the fixed-row rules."""
+    base = configs.THERMAL_2D if dim == 2 else configs.THERMAL_3D
+    upd = {"Mesh/NX": 11, "Mesh/NY": 9, "Mesh/perturb": perturb}
+    if dim == 3:
+        upd["Mesh/NZ"] = 7
+    cfg = configs.variant(base, **upd)
+    op, plan = _host_plan(oracle_lib, cfg, options={"patch elements": 64})
+    nd = op.ndof_elem
+    nt = nd * (nd + 1) // 2
+    rng = np.random.default_rng(3)
+    stage = rng.standard_normal((op.num_elems, nt + nd))
+    # reference loop
+    res_ref = np.zeros(op.num_dofs)
+    jac_ref = np.zeros(op.nnz)
+    fixed = op.is_fixed.astype(bool)
+    tri = {}
+    k = 0
+    for i in range(nd):
+        for j in range(i, nd):
+            tri[(i, j)] = tri[(j, i)] = k
+            k += 1
+    for e in range(op.num_elems):
+        l = op.lids[e]
+        for i in range(nd):
+            r = l[i]
+            if fixed[r]:
+                continue
+            res_ref[r] -= stage[e, nt + i]
+            cols = op.colind[op.rowptr[r]:op.rowptr[r + 1]]
+            for j in range(nd):
+                jac_ref[op.rowptr[r] + np.searchsorted(cols, l[j])] += stage[e, tri[(i, j)]]
+    for accumulate in (1, 0):
+        res = np.full(op.num_dofs, 0.0 if accumulate else 7.0)
+        jac = np.full(op.nnz, 0.0 if accumulate else 7.0)
+        plan.debug_scatter_host(stage, accumulate, res, jac)
+        rr, jr = res_ref.copy(), jac_ref.copy()
+        if not accumulate:   # overwrite mode also applies dofConstraints: identity rows, zero residual
+            for r in np.nonzero(fixed)[0]:
+                jr[op.rowptr[r]:op.rowptr[r + 1]] = (op.colind[op.rowptr[r]:op.rowptr[r + 1]] == r)
+        assert np.allclose(res, rr, rtol=0, atol=1e-13)
+        assert np.allclose(jac, jr, rtol=0, atol=1e-13)
+    assert plan.stat("n_patches") > 1 and plan.stat("n_templates") <= plan.stat("n_patches")

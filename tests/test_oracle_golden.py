@@ -1,0 +1,107 @@
+"""Pins the CPU oracle (oracle/, the checker) to the reference's own regression answers: the input
+decks and the L2-error lines of mrhyde.gold committed under tests/golden/ (generated from
+/root/reference by tests/golden/make_golden.py).  The reference prints 6 significant digits."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _tol(v):
+    return 0.5e-5 * abs(v) + 1e-12   # half a unit of the 6th significant digit
+
+
+def _errs(case):
+    deck, errs = helpers.gold_errors(case)
+    return helpers.deck_to_cfg(deck), errs
+
+
+@pytest.mark.parametrize("case", ["thermal/2D_verification", "thermal/2D_verification_mpi", "thermal/3D_verification", "thermal/2D_mixed_bcs"])
+def test_steady_thermal_gold(oracle_lib, case):
+    cfg, errs = _errs(case)
+    op = oracle_lib.OracleProblem(cfg)
+    u = helpers.newton_steady(op, cfg, lambda v: op.assemble_jacres(v))
+    checked = 0
+    for e in errs:
+        if e["norm"] != "L2 norm":
+            continue   # L2-face norms need the face-term machinery, which is off the hot path
+        labels = ["T"] if e["field"] == "T" else ["grad(T)[x]", "grad(T)[y]"]
+        got = op.l2_error(labels, u)
+        assert abs(got - e["value"]) <= _tol(e["value"]), (case, e, got)
+        checked += 1
+    assert checked >= 1
+
+
+def test_transient_thermal_gold(oracle_lib):
+    """regression/thermal/2D_verification_transient: BWE + BDF1, 20 steps (computeSolnTransientSeeded path)."""
+    import scipy.sparse.linalg as spla
+    cfg, errs = _errs("thermal/2D_verification_transient")
+    op = oracle_lib.OracleProblem(cfg)
+    nsteps = int(cfg["Solver"]["number of steps"])
+    dt = float(cfg["Solver"]["final time"]) / nsteps
+    u = np.zeros(op.num_dofs)
+    gold = {round(e["time"], 6): e["value"] for e in errs}
+    for n in range(nsteps):
+        t = n * dt
+        op.set_time(True, time=t, dt=dt, stage=0, A=((1.0,),), b=(1.0,), c=(1.0,), bdf=(1.0, -1.0))
+        us = u.copy()
+        for _ in range(2):
+            res, jac = op.assemble_jacres(us, sol_prev=[u], sol_stage=[us])
+            us = us + spla.spsolve(op.csr(jac).tocsc(), res)
+        u = us
+        got = op.l2_error(["T"], u)
+        want = gold[round(t + dt, 6)]
+        assert abs(got - want) <= _tol(want), (n, got, want)
+
+
+def test_function_forest_matches_functions_valid_gold(oracle_lib):
+    """regression/functions/Valid prints the decomposition forest; the oracle's Interpreter::split restatement
+    must produce the same branches in the same order (pins the parse / evaluation order)."""
+    fv = json.load(open(os.path.join(HERE, "golden", "functions_valid.json")))
+    import configs
+    cfg = configs.variant(configs.THERMAL_2D, **{"Mesh/NX": 2, "Mesh/NY": 2})
+    # trees that only use fields the thermal block has (T); the others need HDIV/HCURL/HVOL extra variables
+    skip = {"f14", "f15", "f16", "f17"}
+    cfg["Functions"] = {k: str(v) for k, v in fv["functions"].items() if k not in skip}
+    op = oracle_lib.OracleProblem(cfg)
+    n = 0
+    for name, branches in fv["forests"]["ip"].items():
+        if name in skip or name not in cfg["Functions"]:
+            continue
+        got = [line.split(":", 1)[1].rsplit("|", 1)[0] for line in op.print_tree(name).strip().splitlines()]
+        assert got == branches, (name, got, branches)
+        n += 1
+    assert n == 18
+
+
+def test_q1_laplace_stencil_and_symmetry(oracle_lib):
+    """Analytic check: the interior row of the hex-Q1 Laplace matrix on a uniform grid of size h is
+    8h/3 (diagonal), 0 (face neighbours), -h/6 (edge neighbours), -h/12 (corner neighbours)."""
+    import configs
+    n = 4
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": n, "Mesh/NY": n, "Mesh/NZ": n})
+    op = oracle_lib.OracleProblem(cfg)
+    res, jac = op.assemble_jacres(np.zeros(op.num_dofs))
+    A = op.csr(jac).toarray()
+    h = 1.0 / n
+    nn = n + 1
+    c = 2 + 2 * nn + 2 * nn * nn
+    for dk in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            for di in (-1, 0, 1):
+                m = abs(di) + abs(dj) + abs(dk)
+                want = {0: 8 * h / 3, 1: 0.0, 2: -h / 6, 3: -h / 12}[m]
+                assert abs(A[c, c + di + dj * nn + dk * nn * nn] - want) < 1e-14
+    free = ~op.is_fixed.astype(bool)
+    Aff = A[np.ix_(free, free)]
+    assert np.max(np.abs(Aff - Aff.T)) < 1e-14
+    # constant state: K * 1 = 0, so the residual is only the source load (and zero with no source)
+    cfg0 = configs.variant(cfg, **{"Functions/thermal source": "0.0"})
+    op0 = oracle_lib.OracleProblem(cfg0)
+    r0, _ = op0.assemble_jacres(np.ones(op0.num_dofs))
+    assert np.max(np.abs(r0)) < 1e-14
