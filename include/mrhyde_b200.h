@@ -118,6 +118,8 @@ int mrhyde_b200_plan_set_function(mrhyde_b200_plan* plan, const char* name, cons
  * "use strong DBCs", "assemble boundary terms", ...) plus library keys:
  *   "ns3d_uz_rows" = "reference" | "corrected"   (navierstokes.cpp:688)
  *   "accumulate"   = "true" (reference contract: sum into caller-zeroed res/J) | "false" (overwrite)
+ *   "jit"          = "auto" (default: specialise the kernel with NVRTC when available) | "true" | "false"
+ *   "column elements", "min chains", "min segment levels", "sweep axis", "threads"   sweep-plan tuning
  * Unknown keys are an error, never silently ignored. */
 int mrhyde_b200_plan_set_option(mrhyde_b200_plan* plan, const char* key, const char* value);
 
@@ -175,8 +177,10 @@ int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* plan, int64_t n_cols, const int6
 int mrhyde_b200_halo_sum(mrhyde_b200_plan* plan, double* res, double* jac_values, void* stream);
 
 /* ---- introspection (tests, bench) ----------------------------------------------------------- */
-/* keys: "n_patches" "n_templates" "kernel_launches_per_assemble" "smem_bytes" "threads_per_block"
- *       "n_elem" "n_elem_with_halo" "n_rows" "nnz" "plan_device_bytes" "n_affine"               */
+/* keys: "n_chains" "n_columns" "n_segments" "n_levels" "n_steps" "n_patterns" "n_pattern_items" "ring_capacity"
+ *       "max_rows_per_step" "kernel_launches_per_assemble" "halo_launches_per_sum" "smem_bytes" "threads_per_block"
+ *       "n_elem" "n_elem_with_halo" "n_rows" "nnz" "n_verts" "plan_device_bytes" "n_affine" "n_box"
+ *       "n_orphan_rows" "jit" (1 = plan-specialised NVRTC kernel in use) "jit_registers"                        */
 int mrhyde_b200_plan_stat(mrhyde_b200_plan* plan, const char* key, int64_t* value);
 /* Average device time (ms, CUDA events on the launch stream) of the volume kernel over the
  * assemble calls since the last reset; used by bench.py for the roofline figure. */
@@ -196,6 +200,10 @@ int mrhyde_b200_expr_disassemble(int32_t n, const char* const* names, const char
  * compiler against the reference grammar; the kernels never call this). */
 int mrhyde_b200_expr_eval_host(int32_t n, const char* const* names, const char* const* exprs, const char* which,
                                int64_t npts, const double* vars7, double* out);
+/* Generates the translation unit NVRTC compiles for this plan (the volume kernel with the plan's expressions,
+ * tables and block size as constants), compiles it for sm_100a -- no device needed -- and optionally writes
+ * the source / cubin to files (inspection with cuobjdump -sass).  log receives the compiler output. */
+int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* plan, const char* source_path, const char* cubin_path, char* log, size_t log_cap);
 /* Applies the plan's scatter programs on the host to caller-supplied staged element vectors
  * stage[n_elem][stage_len] (local Jacobian entries then residual entries), with the
  * same ordering and fixed-row rules as the device pull-scatter.  Verifies plan logic only. */

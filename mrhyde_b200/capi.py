@@ -25,7 +25,7 @@ SYMBOLS = [
     "mrhyde_b200_assemble_jacres", "mrhyde_b200_assemble_res", "mrhyde_b200_assemble_jacres_host",
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
-    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host",
+    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
         L.mrhyde_b200_expr_disassemble.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_char_p, C.c_size_t]
         L.mrhyde_b200_expr_eval_host.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_scatter_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_plan_debug_jit.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         _LIB = L
     return _LIB
 
@@ -342,6 +343,13 @@ class AssemblyPlan:
     def debug_scatter_host(self, stage, accumulate, res, jac):
         st = np.ascontiguousarray(stage, dtype=np.float64)
         self._chk(self.L.mrhyde_b200_plan_debug_scatter_host(self.h, _ptr(st), st.shape[1], int(accumulate), _ptr(res), _ptr(jac)))
+
+    def debug_jit(self, source_path=None, cubin_path=None):
+        """Generates + NVRTC-compiles the plan-specialised kernel (no device needed); returns the compiler log."""
+        buf = C.create_string_buffer(1 << 16)
+        self._chk(self.L.mrhyde_b200_plan_debug_jit(self.h, source_path.encode() if source_path else None,
+                                                  cubin_path.encode() if cubin_path else None, buf, len(buf)))
+        return buf.value.decode()
 
     def eval_function(self, name, xyz, time=0.0):
         p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)

@@ -11,12 +11,16 @@
 #include <vector>
 
 #include "../../include/mrhyde_b200.h"
+#include <cstdio>
+#include <cstdlib>
+
 #include "boundary.cuh"
 #include "expr.hpp"
-#include "expr_device.cuh"
 #include "halo.hpp"
 #include "plan.hpp"
-#include "thermal.cuh"
+#include "volume_kernel.cuh"
+#include "volume_launch.hpp"
+#include "build/jit_sources.h"
 
 using namespace mrhyde_b200;
 
@@ -97,16 +101,22 @@ struct mrhyde_b200_plan {
   // mesh / graph
   MeshGraph mesh;
   bool have_mesh = false, have_graph = false, finalized = false;
-  PatchPlan pp;
+  ChainPlan cp;
   // device copies
   size_t dev_bytes = 0;
   DevBuf<double> d_vx, d_vy, d_vz;
-  DevBuf<int32_t> d_conn, d_lids, d_colind, d_patch_elem_ptr, d_patch_elems, d_patch_row_ptr, d_patch_rows, d_patch_tmpl, d_orphans, d_fixed_rows;
+  DevBuf<int32_t> d_conn, d_lids, d_colind, d_chain_step_ptr, d_step_elems, d_orphans;
   DevBuf<int64_t> d_rowptr, d_fixed_diag;
-  DevBuf<uint8_t> d_fixed, d_affine;
-  DevBuf<TemplateHeader> d_tmpl;
-  DevBuf<uint16_t> d_slot_row, d_slot_k, d_csrc;
-  DevBuf<uint32_t> d_cptr;
+  DevBuf<uint8_t> d_fixed, d_eclass;
+  DevBuf<StepRec> d_steps;
+  DevBuf<RowRec> d_rows;
+  DevBuf<PatternRec> d_patterns;
+  DevBuf<uint32_t> d_item_src0, d_item_src1, d_item_meta;
+  // plan-specialised (NVRTC) volume kernel; falls back to the ahead-of-time kernel when absent
+  JitKernel jit;
+  bool use_jit = false;
+  std::string jit_note;   // why the plan is not specialised (empty when it is)
+  std::string jit_source; // translation unit handed to NVRTC
   // host-buffer entry point scratch
   DevBuf<double> h_sol, h_res, h_jac;
   std::vector<DevBuf<double>> h_prev, h_stage;
@@ -116,7 +126,7 @@ struct mrhyde_b200_plan {
   BoundaryPlan boundary;
   int threads = 256;
   size_t smem = 0;
-  int64_t n_affine = 0;
+  int64_t n_affine = 0, n_box = 0;
   int launches_per_assemble = 0;   // kernels launched by the last assemble call
   bool accumulate = true;
   int stage_len = 0;
@@ -137,7 +147,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "patch elements", "threads", "use leap frog", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "column elements", "min chains", "min segment levels", "sweep axis", "threads", "jit", "use leap frog", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -192,6 +202,7 @@ void fill_thermal_tables(const mrhyde_b200_plan* P, ThermalTables<DIM>& T) {
       const int t = i * S::NV - (i * (i - 1)) / 2 + (j - i);
       double m = 0.0;
       for (int q = 0; q < S::NQ; ++q) m += T.qw[q] * T.phi[q][i] * T.phi[q][j];
+      if (j == i) { double l = 0.0; for (int q = 0; q < S::NQ; ++q) l += T.qw[q] * T.phi[q][i]; T.Ltab[i] = l; }
       T.Mtab[t] = m;
       for (int k = 0; k < S::NG; ++k) {
         double s = 0.0;
@@ -202,6 +213,65 @@ void fill_thermal_tables(const mrhyde_b200_plan* P, ThermalTables<DIM>& T) {
         T.Stab[k][t] = s;
       }
     }
+}
+
+// ---- source of the plan-specialised kernel: prelude (constants + generated coefficient functions) + embedded headers
+std::string hexd(double v) {
+  char b[64];
+  std::snprintf(b, sizeof(b), "%a", v);
+  return b;
+}
+void emit_values(std::string& o, const double* v, size_t n) {
+  for (size_t i = 0; i < n; ++i) { o += hexd(v[i]); o += (i + 1 < n) ? "," : ""; }
+}
+template <int DIM>
+std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const) {
+  typedef Q1Shape<DIM> S;
+  std::string o;
+  o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
+  o += "#define MRH_JIT_DIM " + std::to_string(DIM) + "\n";
+  o += "#define MRH_JIT_ALL_CONST " + std::to_string(all_const) + "\n";
+  o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
+  o += kKernelAbiSrc;
+  o += "\nnamespace mrhyde_b200 {\n";
+  o += "__device__ __forceinline__ double mrh_abs(double a) { return a < 0.0 ? -a : a; }\n";
+  o += "__device__ __forceinline__ double mrh_sqrt(double a) { return a <= 0.0 ? 0.0 : sqrt(a); }\n";
+  o += "__device__ __forceinline__ double mrh_max(double a, double b) { return b > a ? b : a; }\n";
+  o += "__device__ __forceinline__ double mrh_min(double a, double b) { return b < a ? b : a; }\n";
+  const char* fn[4][2] = {{"mrh_fn_source", "thermal source"}, {"mrh_fn_diffusion", "thermal diffusion"}, {"mrh_fn_specific_heat", "specific heat"}, {"mrh_fn_density", "density"}};
+  for (auto& f : fn)
+    o += std::string("__device__ __forceinline__ double ") + f[0] + "(double x, double y, double z, double t) { return " + fs.codegen(f[1]) + "; }\n";
+  // distinct cubature coordinates per axis: sub-expressions of one coordinate are evaluated once per distinct value
+  int nqa[3] = {1, 1, 1}, qidx[S::NQ * 3];
+  double qax[3][S::NQ];
+  for (int d = 0; d < 3; ++d) for (int q = 0; q < S::NQ; ++q) { qax[d][q] = 0.0; qidx[q * 3 + d] = 0; }
+  for (int d = 0; d < DIM; ++d) {
+    nqa[d] = 0;
+    for (int q = 0; q < S::NQ; ++q) {
+      int f = -1;
+      for (int i = 0; i < nqa[d]; ++i) if (qax[d][i] == T.qpt[q][d]) f = i;
+      if (f < 0) { f = nqa[d]++; qax[d][f] = T.qpt[q][d]; }
+      qidx[q * 3 + d] = f;
+    }
+  }
+  o += fs.codegen_tensor("thermal source", "mrh_fn_source_box", S::NQ, nqa, qidx);
+  o += "#define MRH_NQA0 " + std::to_string(nqa[0]) + "\n#define MRH_NQA1 " + std::to_string(nqa[1]) + "\n#define MRH_NQA2 " + std::to_string(nqa[2]) + "\n";
+  o += "namespace jit_tab {\n";
+  auto arr = [&](const char* decl, const double* v, size_t n) { o += std::string("constexpr double ") + decl + " = {"; emit_values(o, v, n); o += "};\n"; };
+  const std::string nq = std::to_string(S::NQ), nv = std::to_string(S::NV), dm = std::to_string(DIM), nt = std::to_string(S::NT), ng = std::to_string(S::NG);
+  arr(("gN[" + nq + "][" + nv + "]").c_str(), &T.gN[0][0], S::NQ * S::NV);
+  arr(("gdN[" + nq + "][" + nv + "][" + dm + "]").c_str(), &T.gdN[0][0][0], S::NQ * S::NV * DIM);
+  arr(("phi[" + nq + "][" + nv + "]").c_str(), &T.phi[0][0], S::NQ * S::NV);
+  arr(("dphi[" + nq + "][" + nv + "][" + dm + "]").c_str(), &T.dphi[0][0][0], S::NQ * S::NV * DIM);
+  arr(("qw[" + nq + "]").c_str(), &T.qw[0], S::NQ);
+  arr(("qpt[" + nq + "][" + dm + "]").c_str(), &T.qpt[0][0], S::NQ * DIM);
+  arr(("Stab[" + ng + "][" + nt + "]").c_str(), &T.Stab[0][0], S::NG * S::NT);
+  arr(("Mtab[" + nt + "]").c_str(), &T.Mtab[0], S::NT);
+  arr(("Ltab[" + nv + "]").c_str(), &T.Ltab[0], S::NV);
+  arr(("qax[3][" + nq + "]").c_str(), &qax[0][0], 3 * S::NQ);
+  o += "}  // namespace jit_tab\n}  // namespace mrhyde_b200\n";
+  o += kVolumeKernelSrc;
+  return o;
 }
 
 FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side) {
@@ -332,18 +402,17 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
   if (volume) {
     size_t slot = 0;
     record_begin(P, st, slot);
-    if (P->dim == 3) {
-      P->th3.sol = sol; P->th3.td = td; P->th3.out = out;
-      launch_thermal_q1_3d(P->th3, P->pp.n_patches, P->threads, P->smem, st);
-    } else {
-      P->th2.sol = sol; P->th2.td = td; P->th2.out = out;
-      launch_thermal_q1_2d(P->th2, P->pp.n_patches, P->threads, P->smem, st);
-    }
+    const void* params;
+    if (P->dim == 3) { P->th3.sol = sol; P->th3.td = td; P->th3.out = out; params = &P->th3; }
+    else { P->th2.sol = sol; P->th2.td = td; P->th2.out = out; params = &P->th2; }
+    const char* lerr = P->use_jit ? P->jit.launch(params, P->cp.n_chains, P->threads, P->smem, st)
+                                  : launch_thermal_q1_aot(P->dim, params, P->cp.n_chains, P->threads, P->smem, st);
+    if (lerr) fail(MRHYDE_B200_ERR_CUDA, std::string("volume kernel launch: ") + lerr);
     record_end(P, st, slot);
     ++launched;
     CUDA_OK(cudaGetLastError());
-    if (!P->accumulate && !P->pp.orphan_rows.empty()) {
-      const int n = (int)P->pp.orphan_rows.size();
+    if (!P->accumulate && !P->cp.orphan_rows.empty()) {
+      const int n = (int)P->cp.orphan_rows.size();
       orphan_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(P->d_orphans.p, n, G, out);
       ++launched;
     }
@@ -557,9 +626,9 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   FunctionSet fs = make_function_set(P, false);
   ExprProgram src = fs.compile("thermal source"), dif = fs.compile("thermal diffusion"), cp = fs.compile("specific heat"), rho = fs.compile("density");
 
-  M.classify_affine();
-  P->n_affine = 0;
-  for (uint8_t a : M.affine) P->n_affine += a;
+  M.classify_cells();
+  P->n_affine = 0; P->n_box = 0;
+  for (uint8_t a : M.eclass) { P->n_affine += (a != 0); P->n_box += (a == 2); }
 
   // staged vector per element: upper triangle of the local Jacobian, then the residual
   const int NT = NV * (NV + 1) / 2, STAGE = NT + NV;
@@ -568,14 +637,31 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     rmap[(size_t)i] = (uint16_t)(NT + i);
     for (int j = 0; j < NV; ++j) { const int a = std::min(i, j), b = std::max(i, j); kmap[(size_t)i * NV + j] = (uint16_t)(a * NV - (a * (a - 1)) / 2 + (b - a)); }
   }
-  const int chunk = std::stoi(opt(P, "patch elements", P->dim == 3 ? "256" : "256"));
-  P->threads = std::stoi(opt(P, "threads", "256"));
-  if (P->threads < 32 || P->threads > 256 || P->threads % 32) fail(MRHYDE_B200_ERR_INVALID, "option threads must be a multiple of 32 in [32,256]");
-  build_patch_plan(M, kmap, rmap, STAGE, chunk, (size_t)thermal_q1_max_smem(), P->pp);
-  P->smem = (size_t)P->pp.max_pe * STAGE * sizeof(double);
+  ChainOptions co;
+  co.column_elems = std::stoi(opt(P, "column elements", "128"));
+  co.min_chains = std::stoi(opt(P, "min chains", "592"));
+  co.sweep_axis = std::stoi(opt(P, "sweep axis", "-1"));
+  co.min_segment_levels = std::max(1, std::stoi(opt(P, "min segment levels", "8")));
+  if (co.column_elems < 1 || co.min_chains < 1) fail(MRHYDE_B200_ERR_INVALID, "options 'column elements' and 'min chains' must be positive");
+  build_chain_plan(M, kmap, rmap, STAGE, co, P->cp);
+  P->smem = (size_t)(2 * P->cp.slot_bytes());
+  {
+    const int want = std::stoi(opt(P, "threads", "0"));
+    int th = want > 0 ? want : std::max(128, ((P->cp.cap + 31) / 32) * 32);
+    if (th < 32 || th > 256 || th % 32) fail(MRHYDE_B200_ERR_INVALID, "option threads must be a multiple of 32 in [32,256]");
+    P->threads = th;
+  }
 
   P->stage_len = STAGE;
   P->kmap = kmap; P->rmap = rmap;
+  auto fill_host = [&](auto& th) {
+    th.source = src; th.diffusion = dif; th.specific_heat = cp; th.density = rho;
+    th.all_const = (dif.is_const && cp.is_const && rho.is_const) ? 1 : 0;
+  };
+  if (P->dim == 3) { fill_thermal_tables<3>(P, P->th3.tab); fill_host(P->th3); }
+  else { fill_thermal_tables<2>(P, P->th2.tab); fill_host(P->th2); }
+  P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const)
+                              : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const);
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
     if (!P->bgroups.empty()) {
@@ -594,15 +680,14 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   }
   // ---- upload
   size_t* tot = &P->dev_bytes;
+  const ChainPlan& CP = P->cp;
   P->d_vx.upload(M.vcoord[0], tot); P->d_vy.upload(M.vcoord[1], tot); P->d_vz.upload(M.vcoord[2], tot);
   P->d_conn.upload(M.conn, tot); P->d_lids.upload(M.lids, tot);
-  P->d_rowptr.upload(M.rowptr, tot); P->d_colind.upload(M.colind, tot); P->d_fixed.upload(M.fixed, tot); P->d_affine.upload(M.affine, tot);
-  P->d_patch_elem_ptr.upload(P->pp.patch_elem_ptr, tot); P->d_patch_elems.upload(P->pp.patch_elems, tot);
-  P->d_patch_row_ptr.upload(P->pp.patch_row_ptr, tot); P->d_patch_rows.upload(P->pp.patch_rows, tot);
-  P->d_patch_tmpl.upload(P->pp.patch_tmpl, tot); P->d_tmpl.upload(P->pp.tmpl, tot);
-  P->d_slot_row.upload(P->pp.slot_row, tot); P->d_slot_k.upload(P->pp.slot_k, tot);
-  P->d_cptr.upload(P->pp.cptr, tot); P->d_csrc.upload(P->pp.csrc, tot);
-  P->d_orphans.upload(P->pp.orphan_rows, tot);
+  P->d_rowptr.upload(M.rowptr, tot); P->d_colind.upload(M.colind, tot); P->d_fixed.upload(M.fixed, tot); P->d_eclass.upload(M.eclass, tot);
+  P->d_chain_step_ptr.upload(CP.chain_step_ptr, tot); P->d_steps.upload(CP.steps, tot); P->d_step_elems.upload(CP.step_elems, tot);
+  P->d_rows.upload(CP.rows, tot); P->d_patterns.upload(CP.patterns, tot);
+  P->d_item_src0.upload(CP.item_src[0], tot); P->d_item_src1.upload(CP.item_src[1], tot); P->d_item_meta.upload(CP.item_meta, tot);
+  P->d_orphans.upload(CP.orphan_rows, tot);
   {
     std::vector<int64_t> diag;
     for (int64_t r = 0; r < M.nrows; ++r) {
@@ -614,19 +699,36 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     P->d_fixed_diag.upload(diag, tot);
     if (diag.empty()) P->d_fixed_diag.n = 0;
   }
-  PatchDev D{P->d_patch_elem_ptr.p, P->d_patch_elems.p, P->d_patch_row_ptr.p, P->d_patch_rows.p, P->d_patch_tmpl.p, P->d_tmpl.p,
-             P->d_slot_row.p, P->d_slot_k.p, P->d_cptr.p, P->d_csrc.p};
+  ChainDev D;
+  D.chain_step_ptr = P->d_chain_step_ptr.p; D.steps = P->d_steps.p; D.step_elems = P->d_step_elems.p; D.rows = P->d_rows.p;
+  D.patterns = P->d_patterns.p;
+  D.item_src0 = reinterpret_cast<const SrcQuad*>(P->d_item_src0.p); D.item_src1 = reinterpret_cast<const SrcQuad*>(P->d_item_src1.p);
+  D.item_meta = P->d_item_meta.p; D.cap = CP.cap; D.need_add2 = 0;
+  for (uint32_t mt : CP.item_meta) if (mt & ITEM_ADD2) D.need_add2 = 1;
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
   auto fill_common = [&](auto& th) {
-    th.source = src; th.diffusion = dif; th.specific_heat = cp; th.density = rho;
-    th.all_const = (dif.is_const && cp.is_const && rho.is_const) ? 1 : 0;
     th.vx = P->d_vx.p; th.vy = P->d_vy.p; th.vz = P->d_vz.p;
-    th.conn = P->d_conn.p; th.lids = P->d_lids.p; th.affine = P->d_affine.p;
-    th.patches = D; th.graph = G;
+    th.conn = P->d_conn.p; th.lids = P->d_lids.p; th.eclass = P->d_eclass.p;
+    th.chains = D; th.graph = G;
   };
-  if (P->dim == 3) { fill_thermal_tables<3>(P, P->th3.tab); fill_common(P->th3); }
-  else { fill_thermal_tables<2>(P, P->th2.tab); fill_common(P->th2); }
+  if (P->dim == 3) fill_common(P->th3); else fill_common(P->th2);
   P->launches_per_assemble = 1;
+
+  // ---- plan-specialised kernel (NVRTC): expressions, tables and block size become compile-time constants
+  {
+    const std::string want = opt(P, "jit", "auto");
+    if (want != "auto" && want != "true" && want != "false") fail(MRHYDE_B200_ERR_INVALID, "option jit must be auto|true|false");
+    P->use_jit = false;
+    if (want == "false") P->jit_note = "disabled by option";
+    else {
+      const std::string& src_text = P->jit_source;
+      std::string log;
+      const int min_blocks = std::max(1, std::min(8, (int)((227 * 1024) / (P->smem + 1024))));
+      if (P->jit.build(src_text, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, std::min(min_blocks, 2048 / P->threads), P->smem, log)) P->use_jit = true;
+      else if (want == "true") fail(MRHYDE_B200_ERR_CUDA, "jit=true but the plan could not be specialised: " + log);
+      else P->jit_note = log;
+    }
+  }
 
   // ---- boundary groups (Neumann / weak Dirichlet); strong-Dirichlet and "none" sides add nothing
   if (!P->bgroups.empty()) {
@@ -760,22 +862,30 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   ABI_BEGIN
   if (!P || !key || !value) fail(MRHYDE_B200_ERR_INVALID, "plan_stat: null argument");
   const std::string k(key);
-  if (k == "n_patches") *value = P->pp.n_patches;
-  else if (k == "n_templates") *value = (int64_t)P->pp.tmpl.size();
+  if (k == "n_chains") *value = P->cp.n_chains;
+  else if (k == "n_columns") *value = P->cp.n_columns;
+  else if (k == "n_segments") *value = P->cp.n_segments;
+  else if (k == "n_levels") *value = P->cp.n_levels;
+  else if (k == "n_steps") *value = (int64_t)P->cp.steps.size();
+  else if (k == "n_patterns") *value = (int64_t)P->cp.patterns.size();
+  else if (k == "n_pattern_items") *value = (int64_t)P->cp.item_meta.size();
+  else if (k == "ring_capacity") *value = P->cp.cap;
+  else if (k == "max_rows_per_step") *value = P->cp.max_rows_step;
   else if (k == "kernel_launches_per_assemble") *value = P->launches_per_assemble;
   else if (k == "halo_launches_per_sum") *value = P->halo ? P->halo->launches_per_sum() : 0;
   else if (k == "smem_bytes") *value = (int64_t)P->smem;
   else if (k == "threads_per_block") *value = P->threads;
   else if (k == "n_elem") *value = P->mesh.nelem;
-  else if (k == "n_elem_with_halo") *value = P->pp.n_elem_with_halo;
+  else if (k == "n_elem_with_halo") *value = P->cp.n_elem_with_halo;
   else if (k == "n_rows") *value = P->mesh.nrows;
   else if (k == "nnz") *value = P->mesh.nnz;
   else if (k == "n_verts") *value = P->mesh.nvert;
   else if (k == "plan_device_bytes") *value = (int64_t)P->dev_bytes;
   else if (k == "n_affine") *value = P->n_affine;
-  else if (k == "patch_elements") *value = P->pp.chunk;
-  else if (k == "max_patch_elements") *value = P->pp.max_pe;
-  else if (k == "n_orphan_rows") *value = (int64_t)P->pp.orphan_rows.size();
+  else if (k == "n_box") *value = P->n_box;
+  else if (k == "n_orphan_rows") *value = (int64_t)P->cp.orphan_rows.size();
+  else if (k == "jit") *value = P->use_jit ? 1 : 0;
+  else if (k == "jit_registers") *value = P->use_jit ? P->jit.regs() : 0;
   else fail(MRHYDE_B200_ERR_INVALID, "plan_stat: unknown key '" + k + "'");
   ABI_END
 }
@@ -837,40 +947,36 @@ int mrhyde_b200_expr_eval_host(int32_t n, const char* const* names, const char* 
   ABI_END
 }
 
+int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* P, const char* source_path, const char* cubin_path, char* log, size_t log_cap) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "debug_jit: null plan");
+  if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "debug_jit before finalize");
+  if (source_path) {
+    FILE* f = std::fopen(source_path, "wb");
+    if (!f) fail(MRHYDE_B200_ERR_INVALID, "debug_jit: cannot write the source file");
+    std::fwrite(P->jit_source.data(), 1, P->jit_source.size(), f);
+    std::fclose(f);
+  }
+  std::string cubin, text;
+  const int min_blocks = std::max(1, std::min(8, (int)((227 * 1024) / (P->smem + 1024))));
+  const bool ok = nvrtc_compile(P->jit_source, P->threads, std::min(min_blocks, 2048 / P->threads), cubin, text);
+  if (log && log_cap) { std::snprintf(log, log_cap, "%s", text.c_str()); }
+  if (!ok) fail(MRHYDE_B200_ERR_CUDA, "debug_jit: " + text);
+  if (cubin_path) {
+    FILE* f = std::fopen(cubin_path, "wb");
+    if (!f) fail(MRHYDE_B200_ERR_INVALID, "debug_jit: cannot write the cubin file");
+    std::fwrite(cubin.data(), 1, cubin.size(), f);
+    std::fclose(f);
+  }
+  ABI_END
+}
+
 int mrhyde_b200_plan_debug_scatter_host(mrhyde_b200_plan* P, const double* stage, int64_t stage_len, int accumulate, double* res, double* jac) {
   ABI_BEGIN
   if (!P || !stage) fail(MRHYDE_B200_ERR_INVALID, "debug_scatter_host: null argument");
   if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "debug_scatter_host before finalize");
   if (stage_len != P->stage_len) fail(MRHYDE_B200_ERR_INVALID, "debug_scatter_host: stage_len must be " + std::to_string(P->stage_len));
-  const PatchPlan& pp = P->pp;
-  const MeshGraph& M = P->mesh;
-  for (int32_t p = 0; p < pp.n_patches; ++p) {
-    const TemplateHeader& T = pp.tmpl[(size_t)pp.patch_tmpl[(size_t)p]];
-    const int32_t e0 = pp.patch_elem_ptr[(size_t)p], n_pe = pp.patch_elem_ptr[(size_t)p + 1] - e0;
-    const int32_t r0 = pp.patch_row_ptr[(size_t)p];
-    if (n_pe != T.n_pe) fail(MRHYDE_B200_ERR_STATE, "debug_scatter_host: template / patch size mismatch");
-    for (int32_t s = 0; s < T.n_slots; ++s) {
-      const uint16_t k = pp.slot_k[(size_t)T.off_slot + s];
-      const int32_t row = pp.patch_rows[(size_t)r0 + pp.slot_row[(size_t)T.off_slot + s]];
-      double acc = 0.0;
-      for (uint32_t c = pp.cptr[(size_t)T.off_cptr + s]; c < pp.cptr[(size_t)T.off_cptr + s + 1]; ++c) {
-        const uint32_t src = pp.csrc[(size_t)T.off_csrc + c];
-        const uint32_t entry = src / (uint32_t)n_pe, le = src % (uint32_t)n_pe;
-        acc += stage[(size_t)pp.patch_elems[(size_t)e0 + le] * stage_len + entry];
-      }
-      const bool fixed = M.fixed[(size_t)row] != 0;
-      if (k == SLOT_RES) {
-        if (!res) continue;
-        if (!fixed) { if (accumulate) res[row] += -acc; else res[row] = -acc; }
-        else if (!accumulate) res[row] = 0.0;
-      } else {
-        if (!jac) continue;
-        const int64_t pos = M.rowptr[(size_t)row] + k;
-        if (!fixed) { if (accumulate) jac[pos] += acc; else jac[pos] = acc; }
-        else if (!accumulate) jac[pos] = (M.colind[(size_t)pos] == row) ? 1.0 : 0.0;
-      }
-    }
-  }
+  host_apply_chain_plan(P->mesh, P->cp, stage, accumulate != 0, res, jac);
   ABI_END
 }
 

@@ -9,9 +9,7 @@
 #include <stdexcept>
 
 #include "boundary.cuh"
-#include "expr_device.cuh"
-#include "geometry.cuh"
-#include "state_gather.cuh"
+#include "volume_kernel.cuh"
 
 namespace mrhyde_b200 {
 

@@ -7,9 +7,9 @@
 #include <string>
 #include <vector>
 
-#include "device_plan.cuh"
+#include "plan.hpp"
 #include "expr.hpp"
-#include "thermal.cuh"
+#include "kernel_abi.h"
 
 namespace mrhyde_b200 {
 

@@ -3,6 +3,8 @@
 
 #include <cctype>
 #include <cmath>
+#include <cstdio>
+#include <functional>
 #include <sstream>
 
 #include "../../include/mrhyde_b200.h"
@@ -324,6 +326,136 @@ ExprProgram FunctionSet::compile(const std::string& name) const {
   p.op[p.n] = OP_END;
   if (maxdepth > EXPR_MAXSTACK) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression nests too deeply for the device evaluator: " + name);
   return p;
+}
+
+
+// ---- C++ code generation (plan-specialised kernels) ---------------------------------------------------------
+namespace {
+std::string hexfloat(double v) {
+  char buf[64];
+  if (v != v) return "(0.0/0.0)";
+  if (v == HUGE_VAL) return "(1.0/0.0)";
+  if (v == -HUGE_VAL) return "(-1.0/0.0)";
+  std::snprintf(buf, sizeof(buf), "%a", v);
+  return std::string("(") + buf + ")";
+}
+}  // namespace
+
+// Combines the generated code of a CHAIN node's dependencies in the reference's left-to-right order.
+std::string FunctionSet::gen_chain(const Node& n, const std::function<std::string(int)>& child) {
+  std::string acc;
+  for (size_t k = 0; k < n.deps.size(); ++k) {
+    const std::string& op = n.deps[k].first;
+    const std::string d = child(n.deps[k].second);
+    if (op.empty()) {
+      if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: assignment in a chained position");
+      acc = d;
+    } else if (is_unary(op)) {
+      if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: unary operator in a chained position");
+      if (op == "abs") acc = "mrh_abs(" + d + ")";
+      else if (op == "sqrt") acc = "mrh_sqrt(" + d + ")";
+      else acc = op + "(" + d + ")";
+    } else {
+      if (k == 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: binary operator without a left operand");
+      if (op == "plus") acc = "(" + acc + " + " + d + ")";
+      else if (op == "minus") acc = "(" + acc + " + (-" + d + "))";
+      else if (op == "times") acc = "(" + acc + " * " + d + ")";
+      else if (op == "divide") acc = "(" + acc + " / " + d + ")";
+      else if (op == "power") acc = "pow(" + acc + ", " + d + ")";
+      else if (op == "lt") acc = "((" + acc + " < " + d + ") ? 1.0 : 0.0)";
+      else if (op == "lte") acc = "((" + acc + " <= " + d + ") ? 1.0 : 0.0)";
+      else if (op == "gt") acc = "((" + acc + " > " + d + ") ? 1.0 : 0.0)";
+      else if (op == "gte") acc = "((" + acc + " >= " + d + ") ? 1.0 : 0.0)";
+      else if (op == "max") acc = "mrh_max(" + acc + ", " + d + ")";
+      else if (op == "min") acc = "mrh_min(" + acc + ", " + d + ")";
+      else if (op == "mean") acc = "(0.5 * " + acc + " + 0.5 * " + d + ")";
+      else throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression operator not supported on the device path: " + op);
+    }
+  }
+  return acc;
+}
+
+std::string FunctionSet::gen(const std::vector<Node>& nodes, int idx) {
+  static const char* vars[] = {"x", "y", "z", "t", "nx", "ny", "nz"};
+  const Node& n = nodes[idx];
+  if (n.kind == Node::CONST) return hexfloat(n.value);
+  if (n.kind == Node::VAR) {
+    if (n.var < 0 || n.var > 6) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression variable has no generated-code name");
+    return vars[n.var];
+  }
+  return gen_chain(n, [&](int c) { return gen(nodes, c); });
+}
+
+std::string FunctionSet::codegen(const std::string& name) const {
+  auto it = funcs_.find(name);
+  if (it == funcs_.end()) throw ExprError(MRHYDE_B200_ERR_INVALID, "function not registered: " + name);
+  std::vector<Node> nodes;
+  std::set<std::string> active;
+  active.insert(name);
+  const int root = build(it->second, nodes, active);
+  fold(nodes, root);
+  return gen(nodes, root);
+}
+
+std::string FunctionSet::codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx) const {
+  auto it = funcs_.find(name);
+  if (it == funcs_.end()) throw ExprError(MRHYDE_B200_ERR_INVALID, "function not registered: " + name);
+  std::vector<Node> nodes;
+  std::set<std::string> active;
+  active.insert(name);
+  const int root = build(it->second, nodes, active);
+  fold(nodes, root);
+  std::function<int(int)> mask = [&](int idx) -> int {
+    const Node& n = nodes[idx];
+    if (n.kind == Node::CONST) return 0;
+    if (n.kind == Node::VAR) return n.var >= 0 && n.var <= 3 ? (1 << n.var) : 16;
+    int m = 0;
+    for (auto& d : n.deps) m |= mask(d.second);
+    return m;
+  };
+  std::string decls;
+  int ntemp = 0;
+  static const char* axis_arr[3] = {"xs", "ys", "zs"};
+  static const char* axis_var[3] = {"x", "y", "z"};
+  static const char* axis_tok[3] = {"@x", "@y", "@z"};
+  std::function<std::string(int)> gen_t = [&](int idx) -> std::string {
+    const Node& n = nodes[idx];
+    if (n.kind == Node::CONST) return hexfloat(n.value);
+    const int m = mask(idx);
+    if (m & 16) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "volume coefficient depends on a side-only field");
+    if (n.kind == Node::VAR) {
+      if (n.var == 3) return "t";
+      return std::string(axis_arr[n.var]) + "[" + axis_tok[n.var] + "]";
+    }
+    for (int a = 0; a < 3; ++a)
+      if (m == (1 << a)) {  // depends on one coordinate only: evaluate once per distinct coordinate value
+        const std::string h = "h" + std::to_string(ntemp++);
+        decls += "  double " + h + "[" + std::to_string(std::max(1, nqa[a])) + "];\n";
+        decls += "  _Pragma(\"unroll\") for (int i = 0; i < " + std::to_string(nqa[a]) + "; ++i) { const double " + axis_var[a] + " = " + axis_arr[a] + "[i]; " + h +
+                 "[i] = " + gen(nodes, idx) + "; }\n";
+        return h + "[" + axis_tok[a] + "]";
+      }
+    if (m == 8) {
+      const std::string h = "h" + std::to_string(ntemp++);
+      decls += "  const double " + h + " = " + gen(nodes, idx) + ";\n";
+      return h;
+    }
+    return gen_chain(n, gen_t);
+  };
+  const std::string body = gen_t(root);
+  std::string o = "__device__ __forceinline__ void " + fname + "(const double* xs, const double* ys, const double* zs, double t, double* out) {\n";
+  o += decls;
+  for (int q = 0; q < nq; ++q) {
+    std::string e = body;
+    for (int a = 0; a < 3; ++a) {
+      const std::string tok = axis_tok[a], rep = std::to_string(qidx[q * 3 + a]);
+      size_t p = 0;
+      while ((p = e.find(tok, p)) != std::string::npos) { e.replace(p, tok.size(), rep); p += rep.size(); }
+    }
+    o += "  out[" + std::to_string(q) + "] = " + e + ";\n";
+  }
+  o += "}\n";
+  return o;
 }
 
 double FunctionSet::eval_host(const ExprProgram& p, const double* vars) {

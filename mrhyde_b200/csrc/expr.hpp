@@ -14,35 +14,16 @@
 // small stack program that each thread runs in registers.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
+#include "kernel_abi.h"
+
 namespace mrhyde_b200 {
-
-enum ExprOp : uint8_t {
-  OP_END = 0,
-  OP_PUSHC,   // push constant
-  OP_PUSHV,   // push variable (index in c: 0 x, 1 y, 2 z, 3 t, 4.. extra inputs)
-  OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_LT, OP_LTE, OP_GT, OP_GTE, OP_MAX, OP_MIN, OP_MEAN,   // binary: a = a op b
-  OP_ADDC, OP_SUBC, OP_MULC, OP_DIVC, OP_POWC,        // binary with constant right operand
-  OP_ADDV, OP_SUBV, OP_MULV, OP_DIVV,                 // binary with variable right operand
-  OP_SIN, OP_COS, OP_TAN, OP_EXP, OP_LOG, OP_ABS, OP_SQRT, OP_SINH, OP_COSH,  // unary on top of stack
-};
-
-constexpr int EXPR_MAXOPS = 56;
-constexpr int EXPR_MAXSTACK = 8;
-constexpr int EXPR_NVARS = 10;  // x y z t n[x] n[y] n[z] + spare
-
-struct ExprProgram {  // POD, copied into kernel parameters
-  int32_t n = 0;
-  int32_t is_const = 1;
-  double cval = 0.0;
-  uint8_t op[EXPR_MAXOPS] = {0};
-  double c[EXPR_MAXOPS] = {0};
-};
 
 struct ExprError : std::runtime_error {
   int code;
@@ -58,6 +39,14 @@ class FunctionSet {
   void set_solution_fields(const std::vector<std::string>& f) { soln_fields_.assign(f.begin(), f.end()); }
   void set_scalar_fields(const std::vector<std::string>& f) { scalar_fields_ = f; }  // index = variable slot
   ExprProgram compile(const std::string& name) const;
+  // The same tree as a C++ expression in x, y, z, t (and nx, ny, nz on sides) for the plan-specialised (NVRTC)
+  // kernels: every reference op is applied in the reference's left-to-right order; constants are hex floats.
+  std::string codegen(const std::string& name) const;
+  // Definition of `void fname(const double* xs, const double* ys, const double* zs, double t, double* out)` that evaluates
+  // the function at the nq points (xs[qidx[q][0]], ys[qidx[q][1]], zs[qidx[q][2]]) of a tensor-product point set with
+  // nqa[a] distinct coordinates per axis: sub-trees that depend on one coordinate only are evaluated once per distinct
+  // value (they are loop invariants of the reference's point loop); every value equals the pointwise evaluation bit for bit.
+  std::string codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx) const;
   // human-readable flattened program (tests)
   static std::string disassemble(const ExprProgram& p);
   // reference-style host evaluation of a program (used for constant folding checks in tests)
@@ -73,6 +62,8 @@ class FunctionSet {
   int build(const std::string& expr, std::vector<Node>& nodes, std::set<std::string>& active) const;
   static bool fold(std::vector<Node>& nodes, int idx);
   static void emit(const std::vector<Node>& nodes, int idx, ExprProgram& p, int& depth, int& maxdepth);
+  static std::string gen(const std::vector<Node>& nodes, int idx);
+  static std::string gen_chain(const Node& n, const std::function<std::string(int)>& child);
   std::map<std::string, std::string> funcs_;
   std::vector<std::string> soln_fields_;
   std::vector<std::string> scalar_fields_ = {"x", "y", "z"};

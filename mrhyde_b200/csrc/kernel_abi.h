@@ -1,0 +1,156 @@
+// Plain structs shared by the host plan code and the device kernels.  This header is compiled three ways:
+// by g++ (plan.cpp, expr.cpp), by nvcc (the ahead-of-time kernels) and by NVRTC (the plan-specialised
+// kernels, jit.cpp), so it uses nothing but fixed-width integers.
+#pragma once
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
+#include <cstddef>
+#include <cstdint>
+#endif
+
+namespace mrhyde_b200 {
+
+// ---- sweep plan records (plan.hpp explains the scheme) ------------------------------------------------
+struct StepRec {      // one level of one chain
+  int32_t elem_begin, n_elem;   // into step_elems (global element ids, ascending); n_elem <= cap
+  int32_t row_begin, n_rows;    // into rows: the rows that are complete after this step
+};
+struct RowRec {       // 16 bytes
+  int32_t row;        // local row id (LID)
+  int32_t pattern;
+  uint16_t anchor;    // ring-slot element index the pattern offsets are relative to
+  uint16_t diag_k;    // position of the diagonal entry inside the CSR row (0xFFFF if absent)
+  uint32_t flags;     // bit 0: strong-Dirichlet row (isFixedDOF)
+};
+struct PatternRec {
+  int32_t item_begin, n_items;  // lane items; n_items is padded so no CSR slot straddles a 32-lane chunk
+};
+// A lane item sums up to 4 staged doubles.  item_src[parity][item] holds 4 byte offsets into the ring
+// (0xFFFFFFFF = unused) valid when the current step writes ring slot `parity`; item_meta packs
+//   bits 0-15  k: CSR position in the row (residual item: unused)
+//   bit 16 HEAD  this lane stores the sum        bit 17 ADD1  add lane+1's partial before storing
+//   bit 18 ADD2  then add lane+2's partial       bit 19 RES   the residual entry of the row
+constexpr uint32_t ITEM_HEAD = 1u << 16, ITEM_ADD1 = 1u << 17, ITEM_ADD2 = 1u << 18, ITEM_RES = 1u << 19;
+constexpr uint32_t SRC_NONE = 0xFFFFFFFFu;
+constexpr uint32_t ROW_FIXED = 1u;
+
+struct SrcQuad { uint32_t x, y, z, w; };  // layout of one item_src entry (read as uint4 on the device)
+
+struct ChainDev {
+  const int32_t* chain_step_ptr;   // [n_chains+1]
+  const StepRec* steps;
+  const int32_t* step_elems;
+  const RowRec* rows;
+  const PatternRec* patterns;
+  const SrcQuad* item_src0;        // parity 0 / 1 tables
+  const SrcQuad* item_src1;
+  const uint32_t* item_meta;
+  int32_t cap;                     // ring slot capacity (elements)
+  int32_t need_add2;               // some CSR entry has more than 8 contributions
+};
+
+struct GraphDev {
+  const int64_t* rowptr;
+  const int32_t* colind;
+  const uint8_t* fixed;
+};
+
+struct OutDev {
+  double* res;       // may be null (compute_residual = 0)
+  double* jac;       // may be null (compute_jacobian = 0)
+  int accumulate;    // 1: += into caller-zeroed arrays (reference contract); 0: overwrite
+};
+
+// ---- flattened expression programs (expr.hpp) -------------------------------------------------------------
+enum ExprOp : uint8_t {
+  OP_END = 0,
+  OP_PUSHC,   // push constant
+  OP_PUSHV,   // push variable (index in c: 0 x, 1 y, 2 z, 3 t, 4.. extra inputs)
+  OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_LT, OP_LTE, OP_GT, OP_GTE, OP_MAX, OP_MIN, OP_MEAN,   // binary: a = a op b
+  OP_ADDC, OP_SUBC, OP_MULC, OP_DIVC, OP_POWC,        // binary with constant right operand
+  OP_ADDV, OP_SUBV, OP_MULV, OP_DIVV,                 // binary with variable right operand
+  OP_SIN, OP_COS, OP_TAN, OP_EXP, OP_LOG, OP_ABS, OP_SQRT, OP_SINH, OP_COSH,  // unary on top of stack
+};
+
+constexpr int EXPR_MAXOPS = 56;
+constexpr int EXPR_MAXSTACK = 8;
+constexpr int EXPR_NVARS = 10;  // x y z t n[x] n[y] n[z] + spare
+
+struct ExprProgram {  // POD, copied into kernel parameters
+  int32_t n = 0;
+  int32_t is_const = 1;
+  double cval = 0.0;
+  uint8_t op[EXPR_MAXOPS] = {0};
+  double c[EXPR_MAXOPS] = {0};
+};
+
+// ---- time integration coefficients (computeSolnTransientSeeded, workset.cpp:600-834) ------------------
+constexpr int MAX_PREV = 4;   // BDF order <= 4 previous steps
+constexpr int MAX_STAGE = 4;  // Butcher stages
+
+struct TimeDev {
+  int transient;
+  int nprev, nstage_lo;          // previous steps used, stages below the current one
+  double alpha_u, alpha_t;       // du/d(dof), du_t/d(dof)
+  double one_minus_alpha_u;
+  double timewt;                 // 1 / (dt b_s)
+  double bdf[MAX_PREV + 1];      // BDF weights 1..nprev (index 0 unused)
+  double stage_w[MAX_STAGE];     // A(s,s') / b(s')
+  double time;                   // stage time
+  const double* prev[MAX_PREV];
+  const double* stg[MAX_STAGE];
+};
+
+// ---- thermal, HGRAD Q1 ----------------------------------------------------------------------------------
+template <int DIM>
+struct Q1Shape {
+  static constexpr int NV = 1 << DIM;            // vertices == HGRAD C1 dofs
+  static constexpr int NQ = 1 << DIM;            // 2-point Gauss per direction
+  static constexpr int NT = NV * (NV + 1) / 2;   // upper triangle of the local matrix
+  static constexpr int NG = DIM * (DIM + 1) / 2; // symmetric metric tensor entries
+  static constexpr int STAGE = NT + NV;          // staged doubles per element: J upper triangle, then residual
+};
+
+template <int DIM>
+struct ThermalTables {
+  typedef Q1Shape<DIM> S;
+  double gN[S::NQ][S::NV];          // geometry (Hex8/Quad4) shape values at the cubature points
+  double gdN[S::NQ][S::NV][DIM];    // and reference gradients
+  double phi[S::NQ][S::NV];         // HGRAD basis values  (setReferenceBasisData)
+  double dphi[S::NQ][S::NV][DIM];   // HGRAD reference gradients
+  double qw[S::NQ];
+  double qpt[S::NQ][DIM];
+  // constant-coefficient tables on parallelepipeds:
+  //   K_ij = kappa |det| sum_{a<=b} G_ab Stab[ab][ij],  G = J^-1 J^-T   (ab order: 00 11 22 01 02 12)
+  //   M_ij = rho cp |det| Mtab[ij],   load_i = f |det| Ltab[i] for a constant source
+  double Stab[S::NG][S::NT];
+  double Mtab[S::NT];
+  double Ltab[S::NV];
+};
+
+template <int DIM>
+struct ThermalParams {
+  ThermalTables<DIM> tab;
+  ExprProgram source, diffusion, specific_heat, density;
+  TimeDev td;
+  int all_const;          // diffusion, specific heat, density are constants
+  // mesh
+  const double* vx; const double* vy; const double* vz;
+  const int32_t* conn;    // [nelem][NV]
+  const int32_t* lids;    // [nelem][NV]
+  const uint8_t* eclass;  // [nelem] 0 general, 1 parallelepiped, 2 axis-aligned box
+  const double* sol;
+  ChainDev chains;
+  GraphDev graph;
+  OutDev out;
+};
+
+}  // namespace mrhyde_b200

@@ -20,33 +20,40 @@ inline uint64_t mix64(uint64_t x) {
 }
 inline uint64_t bits_of(double d) { if (d == 0.0) d = 0.0; uint64_t u; std::memcpy(&u, &d, 8); return u; }
 
-inline uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
-  v &= 0x3ff;
-  v = (v | (v << 16)) & 0x030000FF;
-  v = (v | (v << 8)) & 0x0300F00F;
-  v = (v | (v << 4)) & 0x030C30C3;
-  v = (v | (v << 2)) & 0x09249249;
-  return v;
+int host_threads() {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > 16) nt = 16;
+  return nt;
 }
 
 template <class F>
 void parallel_for(int64_t n, F&& f) {
-  int nt = (int)std::thread::hardware_concurrency();
-  if (nt < 1) nt = 1;
-  if (nt > 16) nt = 16;
+  int nt = host_threads();
   if (n < 4 * nt) nt = 1;
   std::atomic<int64_t> next(0);
+  std::atomic<bool> failed(false);
+  std::string what;
+  std::mutex mu;
   auto worker = [&](int tid) {
-    for (;;) {
-      const int64_t i = next.fetch_add(1);
-      if (i >= n) break;
-      f(i, tid);
+    try {
+      for (;;) {
+        const int64_t i = next.fetch_add(1);
+        if (i >= n || failed.load()) break;
+        f(i, tid);
+      }
+    } catch (const std::exception& e) {
+      std::lock_guard<std::mutex> lock(mu);
+      if (!failed.exchange(true)) what = e.what();
     }
   };
-  if (nt == 1) { worker(0); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < nt; ++t) th.emplace_back(worker, t);
-  for (auto& t : th) t.join();
+  if (nt == 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(worker, t);
+    for (auto& t : th) t.join();
+  }
+  if (failed.load()) throw std::runtime_error(what);
 }
 
 }  // namespace
@@ -80,8 +87,8 @@ void MeshGraph::set_elem_nodes(int64_t n_elem, const double* elem_nodes) {
   nvert = (int64_t)vcoord[0].size();
 }
 
-void MeshGraph::classify_affine() {
-  affine.assign((size_t)nelem, 0);
+void MeshGraph::classify_cells() {
+  eclass.assign((size_t)nelem, 0);
   const double tol = 2e-14;
   for (int64_t e = 0; e < nelem; ++e) {
     const int32_t* c = &conn[(size_t)e * nverts];
@@ -104,36 +111,34 @@ void MeshGraph::classify_affine() {
         worst = std::max(worst, std::fabs(X[6][d] - (X[1][d] + X[3][d] + X[4][d] - 2.0 * X[0][d])));
       }
     }
-    affine[(size_t)e] = (worst <= tol * emin) ? 1 : 0;
+    if (!(worst <= tol * emin)) continue;
+    // edge vectors from vertex 0 along xi, eta, zeta (Shards order: 1, 3, 4); "diagonal" must be exact so that the
+    // box path drops only terms that are exactly zero
+    static const int nb[3] = {1, 3, 4};
+    bool diag = true;
+    for (int a = 0; a < dim; ++a)
+      for (int d = 0; d < dim; ++d)
+        if (d != a && X[nb[a]][d] - X[0][d] != 0.0) diag = false;
+    eclass[(size_t)e] = diag ? 2 : 1;
   }
 }
 
-void build_patch_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, const std::vector<uint16_t>& rmap,
-                      int stage_len, int chunk_target, size_t smem_budget_bytes, PatchPlan& out) {
-  const int64_t ne = m.nelem, nr = m.nrows;
-  const int nd = m.ndof, nv = m.nverts;
-  if (ne <= 0 || nr <= 0) throw std::runtime_error("plan: empty mesh or graph");
+namespace {
 
-  // ---- Morton order of element centroids
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-  for (int d = 0; d < m.dim; ++d)
-    for (int64_t v = 0; v < m.nvert; ++v) { lo[d] = std::min(lo[d], m.vcoord[d][v]); hi[d] = std::max(hi[d], m.vcoord[d][v]); }
-  std::vector<uint64_t> keyed((size_t)ne);
-  for (int64_t e = 0; e < ne; ++e) {
-    uint32_t key = 0;
-    for (int d = 0; d < m.dim; ++d) {
-      double c = 0.0;
-      for (int n = 0; n < nv; ++n) c += m.vcoord[d][m.conn[(size_t)e * nv + n]];
-      c /= nv;
-      const double t = (hi[d] > lo[d]) ? (c - lo[d]) / (hi[d] - lo[d]) : 0.0;
-      uint32_t q = (uint32_t)std::min(1023.0, std::max(0.0, t * 1024.0));
-      key |= spread10(q) << d;
-    }
-    keyed[(size_t)e] = ((uint64_t)key << 32) | (uint64_t)e;
-  }
-  std::sort(keyed.begin(), keyed.end());
-  std::vector<int32_t> pos((size_t)ne);
-  for (int64_t k = 0; k < ne; ++k) pos[(size_t)(keyed[(size_t)k] & 0xffffffffu)] = (int32_t)k;
+struct ChainWork {  // per-chain scratch produced in parallel, concatenated afterwards
+  std::vector<StepRec> steps;       // elem_begin / row_begin local to this chain
+  std::vector<int32_t> elems;
+  std::vector<RowRec> rows;
+};
+
+}  // namespace
+
+void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, const std::vector<uint16_t>& rmap,
+                      int stage_len, const ChainOptions& opt, ChainPlan& out) {
+  const int64_t ne = m.nelem, nr = m.nrows;
+  const int nd = m.ndof, nv = m.nverts, dim = m.dim;
+  if (ne <= 0 || nr <= 0) throw std::runtime_error("plan: empty mesh or graph");
+  const int axis = (opt.sweep_axis >= 0 && opt.sweep_axis < dim) ? opt.sweep_axis : dim - 1;
 
   // ---- row -> (element, local dof) adjacency, elements ascending
   std::vector<int64_t> r2e_ptr((size_t)nr + 1, 0);
@@ -156,154 +161,390 @@ void build_patch_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       }
   }
 
-  int chunk = std::max(1, chunk_target);
-  for (;;) {  // shrink the chunk until every patch fits the shared-memory budget and 16-bit staging indices
-    out = PatchPlan();
-    out.chunk = chunk;
-    const int32_t npatch = (int32_t)((ne + chunk - 1) / chunk);
-    // owner patch of each row = largest chunk among its elements
-    std::vector<int32_t> owner((size_t)nr, -1);
-    for (int64_t r = 0; r < nr; ++r)
-      for (int64_t p = r2e_ptr[(size_t)r]; p < r2e_ptr[(size_t)r + 1]; ++p)
-        owner[(size_t)r] = std::max(owner[(size_t)r], pos[(size_t)r2e_elem[(size_t)p]] / chunk);
-    out.patch_row_ptr.assign((size_t)npatch + 1, 0);
-    for (int64_t r = 0; r < nr; ++r) {
-      if (owner[(size_t)r] >= 0) ++out.patch_row_ptr[(size_t)owner[(size_t)r] + 1];
-      else out.orphan_rows.push_back((int32_t)r);
+  // ---- element centroids and lowest coordinate along the sweep axis
+  std::vector<double> cen[3], elo((size_t)ne);
+  for (int d = 0; d < 3; ++d) cen[d].assign((size_t)ne, 0.0);
+  double amin = 1e300, amax = -1e300;
+  for (int64_t e = 0; e < ne; ++e) {
+    double lo = 1e300;
+    for (int n = 0; n < nv; ++n) {
+      const int32_t v = m.conn[(size_t)e * nv + n];
+      for (int d = 0; d < dim; ++d) cen[d][(size_t)e] += m.vcoord[d][(size_t)v];
+      lo = std::min(lo, m.vcoord[axis][(size_t)v]);
+      amax = std::max(amax, m.vcoord[axis][(size_t)v]);
     }
-    for (int32_t p = 0; p < npatch; ++p) out.patch_row_ptr[(size_t)p + 1] += out.patch_row_ptr[(size_t)p];
-    out.patch_rows.assign((size_t)out.patch_row_ptr[(size_t)npatch], 0);
+    for (int d = 0; d < dim; ++d) cen[d][(size_t)e] /= nv;
+    elo[(size_t)e] = lo;
+    amin = std::min(amin, lo);
+  }
+  const double atol = 1e-9 * std::max(amax - amin, 1e-300);
+
+  // ---- levels: breadth-first sweep over "shares a dof" adjacency, seeded at the low face of the sweep axis
+  std::vector<int32_t> level((size_t)ne, -1);
+  {
+    std::vector<uint8_t> row_done((size_t)nr, 0);
+    std::vector<int32_t> frontier, next;
+    int64_t visited = 0;
+    double seed_lo = amin;
+    while (visited < ne) {
+      frontier.clear();
+      for (int64_t e = 0; e < ne; ++e)
+        if (level[(size_t)e] < 0 && elo[(size_t)e] <= seed_lo + atol) { level[(size_t)e] = 0; frontier.push_back((int32_t)e); }
+      visited += (int64_t)frontier.size();
+      int32_t lv = 0;
+      while (!frontier.empty()) {
+        next.clear();
+        for (int32_t e : frontier)
+          for (int i = 0; i < nd; ++i) {
+            const int32_t r = m.lids[(size_t)e * nd + i];
+            if (row_done[(size_t)r]) continue;
+            row_done[(size_t)r] = 1;
+            for (int64_t p = r2e_ptr[(size_t)r]; p < r2e_ptr[(size_t)r + 1]; ++p) {
+              const int32_t f = r2e_elem[(size_t)p];
+              if (level[(size_t)f] < 0) { level[(size_t)f] = lv + 1; next.push_back(f); }
+            }
+          }
+        visited += (int64_t)next.size();
+        frontier.swap(next);
+        ++lv;
+      }
+      if (visited < ne) {  // disconnected remainder: restart from its own low face
+        seed_lo = 1e300;
+        for (int64_t e = 0; e < ne; ++e) if (level[(size_t)e] < 0) seed_lo = std::min(seed_lo, elo[(size_t)e]);
+      }
+    }
+  }
+  int32_t nlevels = 0;
+  for (int64_t e = 0; e < ne; ++e) nlevels = std::max(nlevels, level[(size_t)e] + 1);
+
+  const int cap_limit = (int)std::min<size_t>(opt.smem_budget / 2 / ((size_t)stage_len * 8), 1024);
+  if (cap_limit < 1) throw std::runtime_error("plan: a single element does not fit the shared-memory ring");
+  int column_elems = std::max(1, std::min(opt.column_elems, cap_limit));
+
+  for (int attempt = 0;; ++attempt) {
+    out = ChainPlan();
+    out.stage_len = stage_len;
+    out.n_levels = nlevels;
+    // ---- columns: recursive coordinate bisection of the projected centroids, cuts only between distinct coordinates
+    std::vector<int32_t> col((size_t)ne, 0);
+    int32_t ncol = 0;
     {
-      std::vector<int32_t> fill(out.patch_row_ptr.begin(), out.patch_row_ptr.end() - 1);
-      for (int64_t r = 0; r < nr; ++r) if (owner[(size_t)r] >= 0) out.patch_rows[(size_t)fill[(size_t)owner[(size_t)r]]++] = (int32_t)r;
+      std::vector<int32_t> idx((size_t)ne);
+      for (int64_t e = 0; e < ne; ++e) idx[(size_t)e] = (int32_t)e;
+      struct Range { int64_t b, e; };
+      std::vector<Range> stack{{0, ne}};
+      const int64_t target = (int64_t)column_elems * nlevels;
+      while (!stack.empty()) {
+        const Range rg = stack.back();
+        stack.pop_back();
+        const int64_t n = rg.e - rg.b;
+        bool split = false;
+        if (n > target && dim > 1) {
+          // candidate axes ordered by centroid spread
+          int axes[2], na = 0;
+          double spread[2];
+          for (int d = 0; d < dim; ++d) {
+            if (d == axis) continue;
+            double lo = 1e300, hi = -1e300;
+            for (int64_t k = rg.b; k < rg.e; ++k) { const double c = cen[d][(size_t)idx[(size_t)k]]; lo = std::min(lo, c); hi = std::max(hi, c); }
+            axes[na] = d; spread[na] = hi - lo; ++na;
+          }
+          if (na == 2 && spread[1] > spread[0] * (1.0 + 1e-9)) { std::swap(axes[0], axes[1]); std::swap(spread[0], spread[1]); }
+          for (int a = 0; a < na && !split; ++a) {
+            const int d = axes[a];
+            if (!(spread[a] > 0.0)) continue;
+            std::sort(idx.begin() + rg.b, idx.begin() + rg.e, [&](int32_t x, int32_t y) {
+              const double cx = cen[d][(size_t)x], cy = cen[d][(size_t)y];
+              return cx < cy || (cx == cy && x < y);
+            });
+            const double tol = 1e-9 * spread[a];
+            const int64_t mid = rg.b + n / 2;
+            int64_t cut = -1;
+            for (int64_t off = 0; off < n; ++off) {  // nearest position to the median where the coordinate changes
+              const int64_t c1 = mid + off, c2 = mid - off;
+              if (c1 > rg.b && c1 < rg.e && cen[d][(size_t)idx[(size_t)c1]] - cen[d][(size_t)idx[(size_t)c1 - 1]] > tol) { cut = c1; break; }
+              if (c2 > rg.b && c2 < rg.e && cen[d][(size_t)idx[(size_t)c2]] - cen[d][(size_t)idx[(size_t)c2 - 1]] > tol) { cut = c2; break; }
+            }
+            if (cut > rg.b && cut < rg.e) { stack.push_back({cut, rg.e}); stack.push_back({rg.b, cut}); split = true; }
+          }
+        }
+        if (!split) {
+          for (int64_t k = rg.b; k < rg.e; ++k) col[(size_t)idx[(size_t)k]] = ncol;
+          ++ncol;
+        }
+      }
+    }
+    out.n_columns = ncol;
+    int32_t nseg = (int32_t)((opt.min_chains + ncol - 1) / ncol);
+    nseg = std::max(1, std::min(nseg, std::max(1, nlevels / std::max(1, opt.min_segment_levels))));
+    out.n_segments = nseg;
+    auto seg_of = [&](int32_t lv) { return (int32_t)(((int64_t)lv * nseg) / nlevels); };
+    const int32_t nchains = ncol * nseg;
+    out.n_chains = nchains;
+
+    // ---- row owner: the chain of the adjacent element with the largest (level, column); row completes at that level
+    std::vector<int32_t> row_chain((size_t)nr, -1), row_level((size_t)nr, -1);
+    std::vector<int32_t> chain_row_ptr((size_t)nchains + 1, 0);
+    for (int64_t r = 0; r < nr; ++r) {
+      int32_t bl = -1, bc = -1;
+      for (int64_t p = r2e_ptr[(size_t)r]; p < r2e_ptr[(size_t)r + 1]; ++p) {
+        const int32_t e = r2e_elem[(size_t)p];
+        const int32_t l = level[(size_t)e], c = col[(size_t)e];
+        if (l > bl || (l == bl && c > bc)) { bl = l; bc = c; }
+      }
+      if (bl < 0) { out.orphan_rows.push_back((int32_t)r); continue; }
+      row_chain[(size_t)r] = bc * nseg + seg_of(bl);
+      row_level[(size_t)r] = bl;
+      ++chain_row_ptr[(size_t)row_chain[(size_t)r] + 1];
+    }
+    for (int32_t c = 0; c < nchains; ++c) chain_row_ptr[(size_t)c + 1] += chain_row_ptr[(size_t)c];
+    std::vector<int32_t> chain_rows((size_t)chain_row_ptr[(size_t)nchains]);
+    {
+      std::vector<int32_t> fill(chain_row_ptr.begin(), chain_row_ptr.end() - 1);
+      for (int64_t r = 0; r < nr; ++r) if (row_chain[(size_t)r] >= 0) chain_rows[(size_t)fill[(size_t)row_chain[(size_t)r]]++] = (int32_t)r;
     }
 
-    // per-patch element lists (halo included), ordered by Morton position
-    std::vector<std::vector<int32_t>> pelems((size_t)npatch);
-    int nthreads = (int)std::thread::hardware_concurrency();
-    if (nthreads < 1) nthreads = 1;
-    if (nthreads > 16) nthreads = 16;
+    // ---- pass 1: per-chain element lists by level (own column + halo ring), ring capacity
+    const int nthreads = host_threads();
+    std::vector<ChainWork> work((size_t)nchains);
     std::vector<std::vector<int32_t>> stamp((size_t)nthreads);
-    std::atomic<int> too_big(0);
-    parallel_for(npatch, [&](int64_t p, int tid) {
+    std::atomic<int32_t> max_step_elems(0);
+    parallel_for(nchains, [&](int64_t c, int tid) {
       auto& st = stamp[(size_t)tid];
       if (st.empty()) st.assign((size_t)ne, -1);
-      auto& list = pelems[(size_t)p];
-      for (int32_t k = out.patch_row_ptr[(size_t)p]; k < out.patch_row_ptr[(size_t)p + 1]; ++k) {
-        const int32_t r = out.patch_rows[(size_t)k];
+      ChainWork& W = work[(size_t)c];
+      std::vector<int32_t> need;
+      for (int32_t k = chain_row_ptr[(size_t)c]; k < chain_row_ptr[(size_t)c + 1]; ++k) {
+        const int32_t r = chain_rows[(size_t)k];
         for (int64_t q = r2e_ptr[(size_t)r]; q < r2e_ptr[(size_t)r + 1]; ++q) {
           const int32_t e = r2e_elem[(size_t)q];
-          if (st[(size_t)e] != (int32_t)p) { st[(size_t)e] = (int32_t)p; list.push_back(e); }
+          if (st[(size_t)e] != (int32_t)c) { st[(size_t)e] = (int32_t)c; need.push_back(e); }
         }
       }
-      std::sort(list.begin(), list.end(), [&](int32_t a, int32_t b) { return pos[(size_t)a] < pos[(size_t)b]; });
-      if ((size_t)list.size() * stage_len * sizeof(double) > smem_budget_bytes || (size_t)list.size() * stage_len > 65535u) too_big = 1;
+      std::sort(need.begin(), need.end(), [&](int32_t a, int32_t b) {
+        return level[(size_t)a] < level[(size_t)b] || (level[(size_t)a] == level[(size_t)b] && a < b);
+      });
+      W.elems = need;
+      size_t k = 0;
+      while (k < need.size()) {
+        size_t k2 = k;
+        while (k2 < need.size() && level[(size_t)need[k2]] == level[(size_t)need[k]]) ++k2;
+        StepRec S;
+        S.elem_begin = (int32_t)k; S.n_elem = (int32_t)(k2 - k); S.row_begin = 0; S.n_rows = 0;
+        W.steps.push_back(S);
+        int32_t cur = max_step_elems.load();
+        while (S.n_elem > cur && !max_step_elems.compare_exchange_weak(cur, S.n_elem)) {}
+        k = k2;
+      }
     });
-    if (too_big.load()) {
-      if (chunk == 1) throw std::runtime_error("plan: a single element patch exceeds the shared-memory budget");
-      chunk = std::max(1, chunk / 2);
+    if (max_step_elems.load() > cap_limit) {
+      if (column_elems == 1 || attempt > 40) throw std::runtime_error("plan: cannot fit one sweep step into the shared-memory ring");
+      column_elems = std::max(1, (column_elems * 3) / 4);
       continue;
     }
-    out.n_patches = npatch;
-    out.patch_elem_ptr.assign((size_t)npatch + 1, 0);
-    for (int32_t p = 0; p < npatch; ++p) out.patch_elem_ptr[(size_t)p + 1] = out.patch_elem_ptr[(size_t)p] + (int32_t)pelems[(size_t)p].size();
-    out.patch_elems.resize((size_t)out.patch_elem_ptr[(size_t)npatch]);
-    for (int32_t p = 0; p < npatch; ++p) {
-      std::copy(pelems[(size_t)p].begin(), pelems[(size_t)p].end(), out.patch_elems.begin() + out.patch_elem_ptr[(size_t)p]);
-      out.max_pe = std::max(out.max_pe, (int32_t)pelems[(size_t)p].size());
-      out.max_rows = std::max(out.max_rows, out.patch_row_ptr[(size_t)p + 1] - out.patch_row_ptr[(size_t)p]);
-    }
-    out.n_elem_with_halo = out.patch_elem_ptr[(size_t)npatch];
+    out.cap = std::max(1, max_step_elems.load());
+    const uint32_t cap = (uint32_t)out.cap;
+    const uint32_t slot_bytes = (uint32_t)out.slot_bytes();
 
-    // ---- scatter programs, de-duplicated into templates
-    out.patch_tmpl.assign((size_t)npatch, -1);
-    std::unordered_map<uint64_t, std::vector<int32_t>> by_hash;
+    // ---- pass 2: rows of every step and their gather patterns
+    std::unordered_map<std::string, int32_t> pattern_ids;
     std::mutex mu;
     struct Scratch {
-      std::vector<int32_t> local;      // global element -> local index (stamped)
-      std::vector<int32_t> local_tag;
-      std::vector<uint16_t> slot_row, slot_k, csrc;
-      std::vector<uint32_t> cptr;
-      std::vector<uint32_t> ckey;      // per-row scratch: (slot << 16) | src
+      std::vector<int32_t> pos_cur, pos_prev;           // global element -> index in the step's list (stamped by tag)
+      std::vector<int32_t> tag_cur, tag_prev;
+      std::unordered_map<std::string, int32_t> cache;   // thread-local view of pattern_ids
+      std::vector<std::vector<uint32_t>> slot_src;      // per CSR slot (+ residual): packed (slot_rel, le, t)
+      std::string key;
     };
     std::vector<Scratch> scratch((size_t)nthreads);
-    parallel_for(npatch, [&](int64_t p, int tid) {
+    std::atomic<int32_t> max_rows_step(0);
+    int64_t tagbase = 0;
+    std::vector<int64_t> chain_tag((size_t)nchains);
+    for (int32_t c = 0; c < nchains; ++c) { chain_tag[(size_t)c] = tagbase; tagbase += (int64_t)work[(size_t)c].steps.size() + 2; }
+    if (tagbase > 0x7fffffff) throw std::runtime_error("plan: too many sweep steps");
+    parallel_for(nchains, [&](int64_t c, int tid) {
       Scratch& S = scratch[(size_t)tid];
-      if (S.local.empty()) { S.local.assign((size_t)ne, 0); S.local_tag.assign((size_t)ne, -1); }
-      const auto& list = pelems[(size_t)p];
-      const int32_t n_pe = (int32_t)list.size();
-      for (int32_t l = 0; l < n_pe; ++l) { S.local[(size_t)list[(size_t)l]] = l; S.local_tag[(size_t)list[(size_t)l]] = (int32_t)p; }
-      S.slot_row.clear(); S.slot_k.clear(); S.csrc.clear(); S.cptr.clear();
-      const int32_t r0 = out.patch_row_ptr[(size_t)p], r1 = out.patch_row_ptr[(size_t)p + 1];
-      for (int32_t lr = 0; lr < r1 - r0; ++lr) {
-        const int32_t r = out.patch_rows[(size_t)(r0 + lr)];
-        const int64_t rs = m.rowptr[(size_t)r], re = m.rowptr[(size_t)r + 1];
-        const int32_t len = (int32_t)(re - rs);
-        const int32_t* cols = &m.colind[(size_t)rs];
-        // contributions of this row, keyed by slot; adjacency is element-ascending so a stable sort keeps that order
-        S.ckey.clear();
-        for (int64_t q = r2e_ptr[(size_t)r]; q < r2e_ptr[(size_t)r + 1]; ++q) {
-          const int32_t e = r2e_elem[(size_t)q];
-          const int i = r2e_dof[(size_t)q];
-          const int32_t le = S.local[(size_t)e];
-          for (int j = 0; j < nd; ++j) {
-            const int32_t c = m.lids[(size_t)e * nd + j];
-            const int32_t* it = std::lower_bound(cols, cols + len, c);
-            if (it == cols + len || *it != c) throw std::runtime_error("plan: graph is missing an element coupling (row " + std::to_string(r) + ", col " + std::to_string(c) + ")");
-            const uint32_t k = (uint32_t)(it - cols);
-            S.ckey.push_back((k << 16) | (uint32_t)((uint32_t)kmap[(size_t)i * nd + j] * n_pe + le));
+      if (S.pos_cur.empty()) { S.pos_cur.assign((size_t)ne, 0); S.pos_prev.assign((size_t)ne, 0); S.tag_cur.assign((size_t)ne, -1); S.tag_prev.assign((size_t)ne, -1); }
+      ChainWork& W = work[(size_t)c];
+      // rows of this chain bucketed by completion level
+      std::vector<int32_t> rows_sorted(chain_rows.begin() + chain_row_ptr[(size_t)c], chain_rows.begin() + chain_row_ptr[(size_t)c + 1]);
+      std::sort(rows_sorted.begin(), rows_sorted.end(), [&](int32_t a, int32_t b) {
+        return row_level[(size_t)a] < row_level[(size_t)b] || (row_level[(size_t)a] == row_level[(size_t)b] && a < b);
+      });
+      size_t rk = 0;
+      for (size_t s = 0; s < W.steps.size(); ++s) {
+        StepRec& ST = W.steps[s];
+        const int32_t lv = level[(size_t)W.elems[(size_t)ST.elem_begin]];
+        const int32_t tag = (int32_t)(chain_tag[(size_t)c] + (int64_t)s);
+        // previous step's map becomes pos_prev (swap roles), current step is stamped fresh
+        S.pos_cur.swap(S.pos_prev); S.tag_cur.swap(S.tag_prev);
+        for (int32_t l = 0; l < ST.n_elem; ++l) { const int32_t e = W.elems[(size_t)(ST.elem_begin + l)]; S.pos_cur[(size_t)e] = l; S.tag_cur[(size_t)e] = tag; }
+        ST.row_begin = (int32_t)W.rows.size();
+        while (rk < rows_sorted.size() && row_level[(size_t)rows_sorted[rk]] < lv) ++rk;  // cannot happen; defensive
+        for (; rk < rows_sorted.size() && row_level[(size_t)rows_sorted[rk]] == lv; ++rk) {
+          const int32_t r = rows_sorted[rk];
+          const int64_t rs = m.rowptr[(size_t)r], re = m.rowptr[(size_t)r + 1];
+          const int32_t len = (int32_t)(re - rs);
+          if (len > 0xFFFE) throw std::runtime_error("plan: CSR row longer than 65534 entries");
+          const int32_t* cols = &m.colind[(size_t)rs];
+          if (S.slot_src.size() < (size_t)len + 1) S.slot_src.resize((size_t)len + 1);
+          for (int32_t k = 0; k <= len; ++k) S.slot_src[(size_t)k].clear();
+          uint32_t anchor = 0xFFFFFFFFu;
+          for (int64_t q = r2e_ptr[(size_t)r]; q < r2e_ptr[(size_t)r + 1]; ++q) {
+            const int32_t e = r2e_elem[(size_t)q];
+            const int i = r2e_dof[(size_t)q];
+            uint32_t rel, le;
+            if (S.tag_cur[(size_t)e] == tag) { rel = 0; le = (uint32_t)S.pos_cur[(size_t)e]; }
+            else if (s > 0 && S.tag_prev[(size_t)e] == tag - 1) { rel = 1; le = (uint32_t)S.pos_prev[(size_t)e]; }
+            else throw std::runtime_error("plan: an element of row " + std::to_string(r) + " is outside the two-step window (internal error)");
+            anchor = std::min(anchor, le);
+            for (int j = 0; j < nd; ++j) {
+              const int32_t cj = m.lids[(size_t)e * nd + j];
+              const int32_t* it = std::lower_bound(cols, cols + len, cj);
+              if (it == cols + len || *it != cj) throw std::runtime_error("plan: graph is missing an element coupling (row " + std::to_string(r) + ", col " + std::to_string(cj) + ")");
+              S.slot_src[(size_t)(it - cols)].push_back((rel << 31) | (le << 12) | (uint32_t)kmap[(size_t)i * nd + j]);
+            }
+            S.slot_src[(size_t)len].push_back((rel << 31) | (le << 12) | (uint32_t)rmap[(size_t)i]);
           }
-          S.ckey.push_back(((uint32_t)len << 16) | (uint32_t)((uint32_t)rmap[(size_t)i] * n_pe + le));
+          // lane items
+          std::string& key = S.key;
+          key.clear();
+          int32_t n_items = 0;
+          auto put = [&](uint32_t v) { key.append((const char*)&v, 4); };
+          for (int32_t k = 0; k <= len; ++k) {
+            const auto& src = S.slot_src[(size_t)k];
+            const int nch = std::max(1, (int)((src.size() + 3) / 4));
+            if (nch > 4) throw std::runtime_error("plan: more than 16 elements contribute to one matrix entry");
+            while ((n_items & 31) + nch > 32) { put(0u); for (int z = 0; z < 4; ++z) put(SRC_NONE); ++n_items; }  // pad: keep the slot in one 32-lane chunk
+            for (int ch = 0; ch < nch; ++ch) {
+              uint32_t meta = (uint32_t)(k == len ? 0 : k);
+              if (ch == 0) meta |= ITEM_HEAD;
+              if ((ch & 1) == 0 && ch + 1 < nch) meta |= ITEM_ADD1;
+              if (ch == 0 && nch > 2) meta |= ITEM_ADD2;
+              if (k == len) meta |= ITEM_RES;
+              put(meta);
+              for (int z = 0; z < 4; ++z) {
+                const size_t ci = (size_t)ch * 4 + z;
+                if (ci < src.size()) {
+                  const uint32_t rel = src[ci] >> 31, le = (src[ci] >> 12) & 0x7FFFFu, t = src[ci] & 0xFFFu;
+                  put(rel * slot_bytes + (t * cap + (le - anchor)) * 8u);   // parity-0 offset; parity 1 flips the slot
+                } else put(SRC_NONE);
+              }
+              ++n_items;
+            }
+          }
+          int32_t pid;
+          auto itc = S.cache.find(key);
+          if (itc != S.cache.end()) pid = itc->second;
+          else {
+            std::lock_guard<std::mutex> lock(mu);
+            auto itg = pattern_ids.find(key);
+            if (itg != pattern_ids.end()) pid = itg->second;
+            else {
+              pid = (int32_t)out.patterns.size();
+              PatternRec PR;
+              PR.item_begin = (int32_t)out.item_meta.size(); PR.n_items = n_items;
+              out.patterns.push_back(PR);
+              const uint32_t* w = (const uint32_t*)key.data();
+              for (int32_t it = 0; it < n_items; ++it) {
+                out.item_meta.push_back(w[(size_t)it * 5]);
+                for (int z = 0; z < 4; ++z) {
+                  const uint32_t s0 = w[(size_t)it * 5 + 1 + z];
+                  uint32_t s1 = s0;
+                  if (s0 != SRC_NONE) s1 = (s0 >= slot_bytes) ? s0 - slot_bytes : s0 + slot_bytes;
+                  out.item_src[0].push_back(s0);
+                  out.item_src[1].push_back(s1);
+                }
+              }
+              pattern_ids.emplace(key, pid);
+            }
+            S.cache.emplace(key, pid);
+          }
+          RowRec RR;
+          RR.row = r; RR.pattern = pid; RR.anchor = (uint16_t)anchor;
+          const int32_t* dg = std::lower_bound(cols, cols + len, r);
+          RR.diag_k = (dg != cols + len && *dg == r) ? (uint16_t)(dg - cols) : (uint16_t)0xFFFF;
+          RR.flags = m.fixed[(size_t)r] ? ROW_FIXED : 0u;
+          W.rows.push_back(RR);
         }
-        std::stable_sort(S.ckey.begin(), S.ckey.end(), [](uint32_t a, uint32_t b) { return (a >> 16) < (b >> 16); });
-        size_t c = 0;
-        for (int32_t k = 0; k <= len; ++k) {
-          S.slot_row.push_back((uint16_t)lr);
-          S.slot_k.push_back(k == len ? SLOT_RES : (uint16_t)k);
-          S.cptr.push_back((uint32_t)S.csrc.size());
-          while (c < S.ckey.size() && (int32_t)(S.ckey[c] >> 16) == k) { S.csrc.push_back((uint16_t)(S.ckey[c] & 0xffff)); ++c; }
-        }
+        ST.n_rows = (int32_t)W.rows.size() - ST.row_begin;
+        int32_t cur = max_rows_step.load();
+        while (ST.n_rows > cur && !max_rows_step.compare_exchange_weak(cur, ST.n_rows)) {}
       }
-      S.cptr.push_back((uint32_t)S.csrc.size());
-      // hash + de-duplicate
-      uint64_t h = mix64((uint64_t)n_pe * 1315423911u + (uint64_t)(r1 - r0));
-      auto feed = [&](const void* d, size_t nbytes) {
-        const uint8_t* b = (const uint8_t*)d;
-        size_t i = 0;
-        for (; i + 8 <= nbytes; i += 8) { uint64_t w; std::memcpy(&w, b + i, 8); h = mix64(h ^ w) + 0x9e3779b97f4a7c15ULL; }
-        uint64_t w = 0; if (i < nbytes) { std::memcpy(&w, b + i, nbytes - i); h = mix64(h ^ w) + 0x51ed270b; }
-      };
-      feed(S.slot_row.data(), S.slot_row.size() * 2); feed(S.slot_k.data(), S.slot_k.size() * 2);
-      feed(S.cptr.data(), S.cptr.size() * 4); feed(S.csrc.data(), S.csrc.size() * 2);
-      std::lock_guard<std::mutex> lock(mu);
-      int32_t found = -1;
-      for (int32_t t : by_hash[h]) {
-        const TemplateHeader& T = out.tmpl[(size_t)t];
-        if (T.n_pe != n_pe || T.n_rows != r1 - r0 || T.n_slots != (int32_t)S.slot_row.size()) continue;
-        const uint32_t nc = out.cptr[(size_t)T.off_cptr + T.n_slots];
-        if (nc != S.csrc.size()) continue;
-        if (std::memcmp(&out.slot_row[(size_t)T.off_slot], S.slot_row.data(), S.slot_row.size() * 2)) continue;
-        if (std::memcmp(&out.slot_k[(size_t)T.off_slot], S.slot_k.data(), S.slot_k.size() * 2)) continue;
-        if (std::memcmp(&out.cptr[(size_t)T.off_cptr], S.cptr.data(), S.cptr.size() * 4)) continue;
-        if (std::memcmp(&out.csrc[(size_t)T.off_csrc], S.csrc.data(), S.csrc.size() * 2)) continue;
-        found = t; break;
-      }
-      if (found < 0) {
-        TemplateHeader T;
-        T.n_pe = n_pe; T.n_rows = r1 - r0; T.n_slots = (int32_t)S.slot_row.size(); T.pad = 0;
-        T.off_slot = (int64_t)out.slot_row.size(); T.off_cptr = (int64_t)out.cptr.size(); T.off_csrc = (int64_t)out.csrc.size();
-        out.slot_row.insert(out.slot_row.end(), S.slot_row.begin(), S.slot_row.end());
-        out.slot_k.insert(out.slot_k.end(), S.slot_k.begin(), S.slot_k.end());
-        out.cptr.insert(out.cptr.end(), S.cptr.begin(), S.cptr.end());
-        out.csrc.insert(out.csrc.end(), S.csrc.begin(), S.csrc.end());
-        found = (int32_t)out.tmpl.size();
-        out.tmpl.push_back(T);
-        by_hash[h].push_back(found);
-      }
-      out.patch_tmpl[(size_t)p] = found;
-      out.max_slots = std::max(out.max_slots, (int32_t)S.slot_row.size());
+      if (rk != rows_sorted.size()) throw std::runtime_error("plan: a row was not assigned to a sweep step (internal error)");
     });
+    out.max_rows_step = max_rows_step.load();
+
+    // ---- concatenate
+    out.chain_step_ptr.assign((size_t)nchains + 1, 0);
+    for (int32_t c = 0; c < nchains; ++c) {
+      ChainWork& W = work[(size_t)c];
+      const int32_t eb = (int32_t)out.step_elems.size(), rb = (int32_t)out.rows.size();
+      for (StepRec S : W.steps) { S.elem_begin += eb; S.row_begin += rb; out.steps.push_back(S); }
+      out.step_elems.insert(out.step_elems.end(), W.elems.begin(), W.elems.end());
+      out.rows.insert(out.rows.end(), W.rows.begin(), W.rows.end());
+      out.chain_step_ptr[(size_t)c + 1] = (int32_t)out.steps.size();
+      W = ChainWork();
+    }
+    out.n_elem_with_halo = (int64_t)out.step_elems.size();
     break;
+  }
+}
+
+void host_apply_chain_plan(const MeshGraph& m, const ChainPlan& cp, const double* stage, bool accumulate, double* res, double* jac) {
+  const int SL = cp.stage_len;
+  const int64_t slot_doubles = (int64_t)cp.cap * SL;
+  std::vector<double> ring((size_t)(2 * slot_doubles), 0.0);
+  for (int32_t c = 0; c < cp.n_chains; ++c) {
+    for (int32_t s = cp.chain_step_ptr[(size_t)c]; s < cp.chain_step_ptr[(size_t)c + 1]; ++s) {
+      const StepRec& ST = cp.steps[(size_t)s];
+      const int parity = (s - cp.chain_step_ptr[(size_t)c]) & 1;
+      for (int32_t l = 0; l < ST.n_elem; ++l) {
+        const int32_t e = cp.step_elems[(size_t)(ST.elem_begin + l)];
+        for (int t = 0; t < SL; ++t) ring[(size_t)(parity * slot_doubles + (int64_t)t * cp.cap + l)] = stage[(size_t)e * SL + t];
+      }
+      for (int32_t lr = 0; lr < ST.n_rows; ++lr) {
+        const RowRec& R = cp.rows[(size_t)(ST.row_begin + lr)];
+        const int64_t base = m.rowptr[(size_t)R.row];
+        const int32_t len = (int32_t)(m.rowptr[(size_t)R.row + 1] - base);
+        if (R.flags & ROW_FIXED) {
+          if (!accumulate) {
+            if (jac) for (int32_t k = 0; k < len; ++k) jac[base + k] = (k == (int32_t)R.diag_k) ? 1.0 : 0.0;
+            if (res) res[R.row] = 0.0;
+          }
+          continue;
+        }
+        const PatternRec& PT = cp.patterns[(size_t)R.pattern];
+        for (int32_t it0 = 0; it0 < PT.n_items; it0 += 32) {
+          double acc[32];
+          uint32_t meta[32];
+          const int32_t nl = std::min(32, PT.n_items - it0);
+          for (int32_t l = 0; l < 32; ++l) { acc[l] = 0.0; meta[l] = 0; }
+          for (int32_t l = 0; l < nl; ++l) {
+            const size_t it = (size_t)(PT.item_begin + it0 + l);
+            meta[l] = cp.item_meta[it];
+            for (int z = 0; z < 4; ++z) {
+              const uint32_t src = cp.item_src[parity][it * 4 + z];
+              if (src != SRC_NONE) acc[l] += ring[(size_t)(src / 8 + R.anchor)];
+            }
+          }
+          double nxt[32];
+          for (int32_t l = 0; l < 32; ++l) nxt[l] = (l + 1 < 32) ? acc[l + 1] : 0.0;
+          for (int32_t l = 0; l < 32; ++l) if (meta[l] & ITEM_ADD1) acc[l] += nxt[l];
+          for (int32_t l = 0; l < 32; ++l) nxt[l] = (l + 2 < 32) ? acc[l + 2] : 0.0;
+          for (int32_t l = 0; l < 32; ++l) if (meta[l] & ITEM_ADD2) acc[l] += nxt[l];
+          for (int32_t l = 0; l < nl; ++l) {
+            if (!(meta[l] & ITEM_HEAD)) continue;
+            if (meta[l] & ITEM_RES) {
+              if (res) { if (accumulate) res[R.row] += -acc[l]; else res[R.row] = -acc[l]; }
+            } else if (jac) {
+              const int64_t p = base + (meta[l] & 0xFFFFu);
+              if (accumulate) jac[p] += acc[l]; else jac[p] = acc[l];
+            }
+          }
+        }
+      }
+    }
   }
 }
 

@@ -1,19 +1,24 @@
-// Plan-time (host) analysis for the owner-computes assembly kernels.
+// Plan-time (host) analysis for the owner-computes, sweep-ordered assembly kernels.
 //
 // The reference scatters each element's local matrix into the CSR matrix with a per-entry linear
-// search and atomics (assemblyManager_scatter.hpp:162-278).  Here the scatter is turned around at
-// plan time: rows are grouped into spatially compact PATCHES; one CTA computes every element
-// that touches its rows (elements on patch borders are recomputed by the neighbouring patches),
-// stages the local matrices in shared memory, and then each CSR slot of an owned row sums its
-// contributions in ascending element order -- the serial reference's order -- and is
-// written exactly once with a plain store.  No atomics, no colour passes, run-to-run reproducible.
-//
-// The per-slot contribution lists ("scatter program") are identical for all interior patches of a
-// structured mesh, so programs are de-duplicated into TEMPLATES that stay L2-resident.
+// search and atomics (assemblyManager_scatter.hpp:162-278), one small group of elements at a time.
+// Here the scatter is turned around at plan time:
+//   * elements are layered by a breadth-first sweep (two elements that share a dof are at most one
+//     LEVEL apart) and cut into COLUMNS across the sweep; a CHAIN is one column over a range of levels;
+//   * one CTA walks a chain level by level (a STEP): it computes the local matrices of the step's
+//     elements -- its own column plus the one-element halo ring around it -- into a two-slot ring
+//     buffer in shared memory, then every CSR slot (and residual entry) of the rows that became
+//     complete sums its contributions, which by construction sit in the current or the previous
+//     ring slot, in ascending element order -- the serial reference's order -- and
+//     is written exactly once with a plain store.  No atomics, no colour passes, reproducible.
+//   * the per-row gather lists are stored as PATTERNS relative to a per-row anchor, so a structured
+//     mesh needs a handful of patterns that stay cache resident.
 #pragma once
 #include <cstdint>
 #include <string>
 #include <vector>
+
+#include "kernel_abi.h"
 
 namespace mrhyde_b200 {
 
@@ -27,42 +32,45 @@ struct MeshGraph {  // host inputs of one block
   std::vector<int64_t> rowptr;     // [nrows+1]
   std::vector<int32_t> colind;     // [nnz]
   std::vector<uint8_t> fixed;      // [nrows]
-  std::vector<uint8_t> affine;     // [nelem] 1 = constant Jacobian (parallelepiped) within 2e-14
-  void classify_affine();
+  std::vector<uint8_t> eclass;     // [nelem] 0 = general cell, 1 = parallelepiped (constant Jacobian within 2e-14),
+                                   //         2 = parallelepiped whose Jacobian is diagonal (axis-aligned box)
+  void classify_cells();
   // de-duplicates per-element coordinates into the vertex table + connectivity
   void set_elem_nodes(int64_t n_elem, const double* elem_nodes);
 };
 
-constexpr uint16_t SLOT_RES = 0xFFFF;  // slot_k value of the residual slot of a row
-
-struct TemplateHeader {  // one scatter program
-  int32_t n_pe;        // elements of the patch, halo included
-  int32_t n_rows;      // owned rows
-  int32_t n_slots;     // sum(rowlen + 1) over owned rows
-  int32_t pad;
-  int64_t off_slot;    // offset into slot_row / slot_k / cptr (cptr has n_slots + 1 entries per template)
-  int64_t off_cptr;
-  int64_t off_csrc;    // offset into csrc
+struct ChainPlan {
+  int32_t n_chains = 0, n_levels = 0, n_columns = 0, n_segments = 0;
+  int32_t cap = 0;             // ring slot capacity in elements (max elements of any step)
+  int32_t stage_len = 0;       // staged doubles per element
+  int32_t max_rows_step = 0;
+  int64_t n_elem_with_halo = 0;
+  std::vector<int32_t> chain_step_ptr;   // [n_chains+1]
+  std::vector<StepRec> steps;
+  std::vector<int32_t> step_elems;
+  std::vector<RowRec> rows;
+  std::vector<PatternRec> patterns;
+  std::vector<uint32_t> item_src[2];     // 4 per item
+  std::vector<uint32_t> item_meta;
+  std::vector<int32_t> orphan_rows;      // rows no element touches
+  int64_t slot_bytes() const { return (int64_t)cap * stage_len * 8; }
 };
 
-struct PatchPlan {
-  int32_t n_patches = 0;
-  int32_t chunk = 0;                 // target elements per patch before the halo
-  int32_t max_pe = 0, max_slots = 0, max_rows = 0;
-  int64_t n_elem_with_halo = 0;
-  std::vector<int32_t> patch_elem_ptr, patch_elems;  // [n_patches+1], global element ids
-  std::vector<int32_t> patch_row_ptr, patch_rows;    // [n_patches+1], owned rows (ascending)
-  std::vector<int32_t> patch_tmpl;                   // [n_patches]
-  std::vector<TemplateHeader> tmpl;
-  std::vector<uint16_t> slot_row, slot_k;
-  std::vector<uint32_t> cptr;
-  std::vector<uint16_t> csrc;                        // staged index = entry * n_pe + local element
-  std::vector<int32_t> orphan_rows;                  // rows no element touches
+struct ChainOptions {
+  int sweep_axis = -1;          // -1: last axis
+  int column_elems = 128;       // target owned elements per level and column
+  int min_chains = 592;         // aim for at least this many chains (4 per SM) by cutting the sweep into segments
+  int min_segment_levels = 8;
+  size_t smem_budget = 113 * 1024;  // ring (2 slots) must fit here
 };
 
 // kmap[i*ndof + j] = index of local-matrix entry (i,j) in the staged per-element vector,
 // rmap[i] = index of residual entry i; stage_len = staged doubles per element.
-void build_patch_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, const std::vector<uint16_t>& rmap,
-                      int stage_len, int chunk_target, size_t smem_budget_bytes, PatchPlan& out);
+void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, const std::vector<uint16_t>& rmap,
+                      int stage_len, const ChainOptions& opt, ChainPlan& out);
+
+// Applies the plan on the host to caller-supplied staged element vectors stage[nelem][stage_len], walking
+// chains, ring slots, patterns and lane items exactly like the device pull phase (plan verification).
+void host_apply_chain_plan(const MeshGraph& m, const ChainPlan& cp, const double* stage, bool accumulate, double* res, double* jac);
 
 }  // namespace mrhyde_b200

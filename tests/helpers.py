@@ -8,6 +8,7 @@ from mrhyde_b200.capi import AssemblyPlan, TimeSpec
 SIDE_NAMES_2D = ["left", "right", "bottom", "top"]
 SIDE_NAMES_3D = SIDE_NAMES_2D + ["back", "front"]
 BC_NAMES = {0: "none", 1: "Dirichlet", 2: "weak Dirichlet", 3: "Neumann"}
+DEFAULT_OPTIONS = {}   # plan options every plan_from_oracle call applies first (the gpu tests switch "jit" through it)
 
 
 def plan_from_oracle(op, cfg, device=0, options=None, indexed=False):
@@ -27,7 +28,7 @@ def plan_from_oracle(op, cfg, device=0, options=None, indexed=False):
             plan.set_option(key, phys[key])
     if "use strong DBCs" in solver:
         plan.set_option("use strong DBCs", solver["use strong DBCs"])
-    for k, v in (options or {}).items():
+    for k, v in list(DEFAULT_OPTIONS.items()) + list((options or {}).items()):
         plan.set_option(k, v)
     if indexed:
         plan.set_mesh_indexed(op.nodes, op.conn, op.lids)

@@ -139,7 +139,7 @@ def test_scatter_programs_equal_serial_element_loop(oracle_lib, product_lib, dim
     if dim == 3:
         upd["Mesh/NZ"] = 7
     cfg = configs.variant(base, **upd)
-    op, plan = _host_plan(oracle_lib, cfg, options={"patch elements": 64})
+    op, plan = _host_plan(oracle_lib, cfg, options={"column elements": 4, "min segment levels": 2})
     nd = op.ndof_elem
     nt = nd * (nd + 1) // 2
     rng = np.random.default_rng(3)
@@ -174,4 +174,4 @@ def test_scatter_programs_equal_serial_element_loop(oracle_lib, product_lib, dim
                 jr[op.rowptr[r]:op.rowptr[r + 1]] = (op.colind[op.rowptr[r]:op.rowptr[r + 1]] == r)
         assert np.allclose(res, rr, rtol=0, atol=1e-13)
         assert np.allclose(jac, jr, rtol=0, atol=1e-13)
-    assert plan.stat("n_patches") > 1 and plan.stat("n_templates") <= plan.stat("n_patches")
+    assert plan.stat("n_chains") > 1 and plan.stat("n_patterns") < plan.stat("n_rows")

@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        prob = ThermalBrick(3, N, device=-1, rank=rank, nranks=world, options={"patch elements": 32})
+        prob = ThermalBrick(3, N, device=-1, rank=rank, nranks=world, options={"column elements": 4, "min segment levels": 2})
         ne = prob.n_elem
         stage = _stage(np.arange(ne) + rank * ne, 44)
         res = np.zeros(prob.n_rows)
@@ -77,7 +77,7 @@ def test_two_rank_partition_and_halo_sum_equal_single_rank(product_lib):
         p.join(timeout=60)
         assert p.exitcode == 0
     # single-rank reference: the same global mesh (N[0] x N[1] x 2 N[2]) as ONE slab
-    glob = ThermalBrick(3, (N[0], N[1], world * N[2]), device=-1, rank=0, nranks=1, options={"patch elements": 32})
+    glob = ThermalBrick(3, (N[0], N[1], world * N[2]), device=-1, rank=0, nranks=1, options={"column elements": 4, "min segment levels": 2})
     stage = _stage(np.arange(glob.n_elem), 44)
     res = np.zeros(glob.n_rows)
     jac = np.zeros(glob.nnz)
