@@ -197,7 +197,11 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
-    prob = ThermalBrick(3, [n, n, n], device=local, rank=rank, nranks=world, options={"accumulate": "false"})
+    options = {"accumulate": "false"}
+    for kv in args.opt:
+        k, v = kv.split("=", 1)
+        options[k] = v
+    prob = ThermalBrick(3, [n, n, n], device=local, rank=rank, nranks=world, options=options)
     plan = prob.plan
     if world > 1:
         uid = torch.from_numpy(plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -285,10 +289,12 @@ def run_ours(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(n, world), "elements_per_gpu": prob.n_elem, "rows_per_gpu": prob.n_rows, "nnz_per_gpu": prob.nnz,
                            "l2": "inputs+outputs %.2f GB per GPU exceed the 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
-                           "output_mode": "overwrite (accumulate=false)", "patches": plan.stat("n_patches"), "patch_elements": plan.stat("patch_elements"),
-                           "elements_incl_halo": plan.stat("n_elem_with_halo"), "parallelism": "z-slabs x%d + NCCL halo sum" % world if world > 1 else "1 GPU"},
+                           "output_mode": "overwrite (accumulate=false)", "chains": plan.stat("n_chains"), "columns": plan.stat("n_columns"),
+                           "segments": plan.stat("n_segments"), "ring_capacity": plan.stat("ring_capacity"), "threads_per_block": plan.stat("threads_per_block"),
+                           "smem_bytes": plan.stat("smem_bytes"), "row_patterns": plan.stat("n_patterns"), "kernel_build": "nvrtc plan-specialised" if plan.stat("jit") else "ahead-of-time",
+                           "elements_incl_halo": plan.stat("n_elem_with_halo"), "plan_options": {k: v for k, v in options.items() if k != "accumulate"}, "parallelism": "z-slabs x%d + NCCL halo sum" % world if world > 1 else "1 GPU"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                             "kernel": "thermal_q1_volume_kernel<3>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                             "kernel": "mrh_thermal_q1_3d", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * prob.n_rows * world, "d2h_bytes_per_step": 8 * (prob.n_rows + prob.nnz) * world,
                         "steps": e2e_steps, "api": "mrhyde_b200_assemble_jacres_host (pinned host buffers)"},
@@ -309,6 +315,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="elements per brick edge (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="plan option key=value (tuning experiments), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

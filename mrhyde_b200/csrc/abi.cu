@@ -110,10 +110,9 @@ struct mrhyde_b200_plan {
   DevBuf<uint8_t> d_fixed, d_eclass;
   DevBuf<StepRec> d_steps;
   DevBuf<RowRec> d_rows;
-  DevBuf<PatternRec> d_patterns;
   DevBuf<uint32_t> d_item_src0, d_item_src1, d_item_meta;
   // plan-specialised (NVRTC) volume kernel; falls back to the ahead-of-time kernel when absent
-  JitKernel jit;
+  JitKernel jit, jit_transient;   // steady build at finalize; the transient build on the first transient call
   bool use_jit = false;
   std::string jit_note;   // why the plan is not specialised (empty when it is)
   std::string jit_source; // translation unit handed to NVRTC
@@ -125,6 +124,8 @@ struct mrhyde_b200_plan {
   ThermalParams<3> th3;
   BoundaryPlan boundary;
   int threads = 256;
+  int row_tab = 0;
+  int jit_min_blocks = 1;
   size_t smem = 0;
   int64_t n_affine = 0, n_box = 0;
   int launches_per_assemble = 0;   // kernels launched by the last assemble call
@@ -147,7 +148,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "column elements", "min chains", "min segment levels", "sweep axis", "threads", "jit", "use leap frog", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -230,6 +231,7 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
   o += "#define MRH_JIT_DIM " + std::to_string(DIM) + "\n";
+  o += "#define MRH_JIT_TRANSIENT 0  /*@transient@*/\n";
   o += "#define MRH_JIT_ALL_CONST " + std::to_string(all_const) + "\n";
   o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
   o += kKernelAbiSrc;
@@ -405,7 +407,17 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     const void* params;
     if (P->dim == 3) { P->th3.sol = sol; P->th3.td = td; P->th3.out = out; params = &P->th3; }
     else { P->th2.sol = sol; P->th2.td = td; P->th2.out = out; params = &P->th2; }
-    const char* lerr = P->use_jit ? P->jit.launch(params, P->cp.n_chains, P->threads, P->smem, st)
+    if (P->use_jit && td.transient && !P->jit_transient.ready()) {
+      std::string tsrc = P->jit_source, log;
+      const std::string mark = "#define MRH_JIT_TRANSIENT 0  /*@transient@*/";
+      const size_t at = tsrc.find(mark);
+      if (at == std::string::npos) fail(MRHYDE_B200_ERR_STATE, "jit: transient marker missing from the generated source");
+      tsrc.replace(at, mark.size(), "#define MRH_JIT_TRANSIENT 1");
+      if (!P->jit_transient.build(tsrc, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, P->jit_min_blocks, P->smem, log))
+        fail(MRHYDE_B200_ERR_CUDA, "jit: transient kernel build failed: " + log);
+    }
+    const JitKernel& jk = td.transient ? P->jit_transient : P->jit;
+    const char* lerr = P->use_jit ? jk.launch(params, P->cp.n_chains, P->threads, P->smem, st)
                                   : launch_thermal_q1_aot(P->dim, params, P->cp.n_chains, P->threads, P->smem, st);
     if (lerr) fail(MRHYDE_B200_ERR_CUDA, std::string("volume kernel launch: ") + lerr);
     record_end(P, st, slot);
@@ -641,13 +653,15 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   co.column_elems = std::stoi(opt(P, "column elements", "128"));
   co.min_chains = std::stoi(opt(P, "min chains", "592"));
   co.sweep_axis = std::stoi(opt(P, "sweep axis", "-1"));
+  co.cta_slots = std::max(1, std::stoi(opt(P, "cta slots", "296")));
   co.min_segment_levels = std::max(1, std::stoi(opt(P, "min segment levels", "8")));
   if (co.column_elems < 1 || co.min_chains < 1) fail(MRHYDE_B200_ERR_INVALID, "options 'column elements' and 'min chains' must be positive");
   build_chain_plan(M, kmap, rmap, STAGE, co, P->cp);
-  P->smem = (size_t)(2 * P->cp.slot_bytes());
+  P->row_tab = std::max(32, std::min(P->cp.max_rows_step, 1024));
+  P->smem = (size_t)(2 * P->cp.slot_bytes()) + (size_t)P->row_tab * 24;
   {
     const int want = std::stoi(opt(P, "threads", "0"));
-    int th = want > 0 ? want : std::max(128, ((P->cp.cap + 31) / 32) * 32);
+    int th = want > 0 ? want : 256;
     if (th < 32 || th > 256 || th % 32) fail(MRHYDE_B200_ERR_INVALID, "option threads must be a multiple of 32 in [32,256]");
     P->threads = th;
   }
@@ -685,7 +699,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   P->d_conn.upload(M.conn, tot); P->d_lids.upload(M.lids, tot);
   P->d_rowptr.upload(M.rowptr, tot); P->d_colind.upload(M.colind, tot); P->d_fixed.upload(M.fixed, tot); P->d_eclass.upload(M.eclass, tot);
   P->d_chain_step_ptr.upload(CP.chain_step_ptr, tot); P->d_steps.upload(CP.steps, tot); P->d_step_elems.upload(CP.step_elems, tot);
-  P->d_rows.upload(CP.rows, tot); P->d_patterns.upload(CP.patterns, tot);
+  P->d_rows.upload(CP.rows, tot);
   P->d_item_src0.upload(CP.item_src[0], tot); P->d_item_src1.upload(CP.item_src[1], tot); P->d_item_meta.upload(CP.item_meta, tot);
   P->d_orphans.upload(CP.orphan_rows, tot);
   {
@@ -701,9 +715,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   }
   ChainDev D;
   D.chain_step_ptr = P->d_chain_step_ptr.p; D.steps = P->d_steps.p; D.step_elems = P->d_step_elems.p; D.rows = P->d_rows.p;
-  D.patterns = P->d_patterns.p;
   D.item_src0 = reinterpret_cast<const SrcQuad*>(P->d_item_src0.p); D.item_src1 = reinterpret_cast<const SrcQuad*>(P->d_item_src1.p);
-  D.item_meta = P->d_item_meta.p; D.cap = CP.cap; D.need_add2 = 0;
+  D.item_meta = P->d_item_meta.p; D.cap = CP.cap; D.need_add2 = 0; D.row_tab = P->row_tab;
   for (uint32_t mt : CP.item_meta) if (mt & ITEM_ADD2) D.need_add2 = 1;
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
   auto fill_common = [&](auto& th) {
@@ -714,6 +727,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   if (P->dim == 3) fill_common(P->th3); else fill_common(P->th2);
   P->launches_per_assemble = 1;
 
+  P->jit_min_blocks = std::max(1, std::min(std::min(8, 2048 / P->threads), (int)((228 * 1024) / (P->smem + 1024))));
   // ---- plan-specialised kernel (NVRTC): expressions, tables and block size become compile-time constants
   {
     const std::string want = opt(P, "jit", "auto");
@@ -723,8 +737,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     else {
       const std::string& src_text = P->jit_source;
       std::string log;
-      const int min_blocks = std::max(1, std::min(8, (int)((227 * 1024) / (P->smem + 1024))));
-      if (P->jit.build(src_text, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, std::min(min_blocks, 2048 / P->threads), P->smem, log)) P->use_jit = true;
+      if (P->jit.build(src_text, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, P->jit_min_blocks, P->smem, log)) P->use_jit = true;
       else if (want == "true") fail(MRHYDE_B200_ERR_CUDA, "jit=true but the plan could not be specialised: " + log);
       else P->jit_note = log;
     }
@@ -958,8 +971,8 @@ int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* P, const char* source_path, con
     std::fclose(f);
   }
   std::string cubin, text;
-  const int min_blocks = std::max(1, std::min(8, (int)((227 * 1024) / (P->smem + 1024))));
-  const bool ok = nvrtc_compile(P->jit_source, P->threads, std::min(min_blocks, 2048 / P->threads), cubin, text);
+  const int min_blocks = std::max(1, std::min(std::min(8, 2048 / P->threads), (int)((228 * 1024) / (P->smem + 1024))));
+  const bool ok = nvrtc_compile(P->jit_source, P->threads, min_blocks, cubin, text);
   if (log && log_cap) { std::snprintf(log, log_cap, "%s", text.c_str()); }
   if (!ok) fail(MRHYDE_B200_ERR_CUDA, "debug_jit: " + text);
   if (cubin_path) {

@@ -23,15 +23,16 @@ struct StepRec {      // one level of one chain
   int32_t elem_begin, n_elem;   // into step_elems (global element ids, ascending); n_elem <= cap
   int32_t row_begin, n_rows;    // into rows: the rows that are complete after this step
 };
-struct RowRec {       // 16 bytes
+struct RowRec {       // 16 bytes, read as one int4
   int32_t row;        // local row id (LID)
-  int32_t pattern;
+  int32_t item_begin; // first lane item of the row's pattern
   uint16_t anchor;    // ring-slot element index the pattern offsets are relative to
   uint16_t diag_k;    // position of the diagonal entry inside the CSR row (0xFFFF if absent)
-  uint32_t flags;     // bit 0: strong-Dirichlet row (isFixedDOF)
+  uint16_t n_items;   // lane items of the pattern (padded so no CSR slot straddles a 32-lane chunk)
+  uint16_t flags;     // bit 0: strong-Dirichlet row (isFixedDOF)
 };
-struct PatternRec {
-  int32_t item_begin, n_items;  // lane items; n_items is padded so no CSR slot straddles a 32-lane chunk
+struct PatternRec {   // host-side bookkeeping of the de-duplicated patterns
+  int32_t item_begin, n_items;
 };
 // A lane item sums up to 4 staged doubles.  item_src[parity][item] holds 4 byte offsets into the ring
 // (0xFFFFFFFF = unused) valid when the current step writes ring slot `parity`; item_meta packs
@@ -49,12 +50,12 @@ struct ChainDev {
   const StepRec* steps;
   const int32_t* step_elems;
   const RowRec* rows;
-  const PatternRec* patterns;
   const SrcQuad* item_src0;        // parity 0 / 1 tables
   const SrcQuad* item_src1;
   const uint32_t* item_meta;
   int32_t cap;                     // ring slot capacity (elements)
   int32_t need_add2;               // some CSR entry has more than 8 contributions
+  int32_t row_tab;                 // capacity of the shared-memory row table (rows staged per pass of the pull phase)
 };
 
 struct GraphDev {

@@ -275,8 +275,21 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       }
     }
     out.n_columns = ncol;
-    int32_t nseg = (int32_t)((opt.min_chains + ncol - 1) / ncol);
-    nseg = std::max(1, std::min(nseg, std::max(1, nlevels / std::max(1, opt.min_segment_levels))));
+    // segments along the sweep: enough chains to fill the device, preferring counts that make whole waves of
+    // resident CTAs; every extra segment costs one recomputed level per column
+    int32_t nseg = 1;
+    {
+      const int32_t smax = std::max(1, nlevels / std::max(1, opt.min_segment_levels));
+      const int32_t smin = std::max(1, std::min(smax, (int32_t)((opt.min_chains + ncol - 1) / ncol)));
+      double best = -1.0;
+      for (int32_t sg = smin; sg <= std::min(smax, 4 * smin + 4); ++sg) {
+        const double waves = (double)ncol * sg / std::max(1, opt.cta_slots);
+        const double fill = waves / std::ceil(waves);
+        const double work = (double)nlevels / (double)(nlevels + sg - 1);
+        const double score = fill * work;
+        if (score > best + 1e-12) { best = score; nseg = sg; }
+      }
+    }
     out.n_segments = nseg;
     auto seg_of = [&](int32_t lv) { return (int32_t)(((int64_t)lv * nseg) / nlevels); };
     const int32_t nchains = ncol * nseg;
@@ -461,10 +474,16 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
             S.cache.emplace(key, pid);
           }
           RowRec RR;
-          RR.row = r; RR.pattern = pid; RR.anchor = (uint16_t)anchor;
+          RR.row = r; RR.anchor = (uint16_t)anchor;
+          {
+            std::lock_guard<std::mutex> lock(mu);   // patterns may be reallocated by other threads
+            RR.item_begin = out.patterns[(size_t)pid].item_begin;
+          }
+          if (n_items > 0xFFFF) throw std::runtime_error("plan: a row pattern has more than 65535 lane items");
+          RR.n_items = (uint16_t)n_items;
           const int32_t* dg = std::lower_bound(cols, cols + len, r);
           RR.diag_k = (dg != cols + len && *dg == r) ? (uint16_t)(dg - cols) : (uint16_t)0xFFFF;
-          RR.flags = m.fixed[(size_t)r] ? ROW_FIXED : 0u;
+          RR.flags = m.fixed[(size_t)r] ? (uint16_t)ROW_FIXED : (uint16_t)0;
           W.rows.push_back(RR);
         }
         ST.n_rows = (int32_t)W.rows.size() - ST.row_begin;
@@ -514,7 +533,8 @@ void host_apply_chain_plan(const MeshGraph& m, const ChainPlan& cp, const double
           }
           continue;
         }
-        const PatternRec& PT = cp.patterns[(size_t)R.pattern];
+        PatternRec PT;
+        PT.item_begin = R.item_begin; PT.n_items = R.n_items;
         for (int32_t it0 = 0; it0 < PT.n_items; it0 += 32) {
           double acc[32];
           uint32_t meta[32];

@@ -61,7 +61,8 @@ struct ChainOptions {
   int column_elems = 128;       // target owned elements per level and column
   int min_chains = 592;         // aim for at least this many chains (4 per SM) by cutting the sweep into segments
   int min_segment_levels = 8;
-  size_t smem_budget = 113 * 1024;  // ring (2 slots) must fit here
+  int cta_slots = 296;          // CTAs resident on the device at once (SMs x CTAs per SM): the chain count is tuned to fill whole waves
+  size_t smem_budget = 108 * 1024;  // ring (2 slots) must fit here; the row table (24 B per row of a step) sits behind it
 };
 
 // kmap[i*ndof + j] = index of local-matrix entry (i,j) in the staged per-element vector,

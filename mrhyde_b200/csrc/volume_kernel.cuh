@@ -30,9 +30,11 @@
 namespace mrhyde_b200 {
 
 #ifdef MRH_JIT
+#define MRH_TRANSIENT(td) (MRH_JIT_TRANSIENT != 0)
 #define MRH_TAB(f) jit_tab::f
 #define MRH_UNROLL_Q _Pragma("unroll")
 #else
+#define MRH_TRANSIENT(td) ((td).transient != 0)
 #define MRH_TAB(f) P.tab.f
 #define MRH_UNROLL_Q _Pragma("unroll 1")
 #endif
@@ -173,7 +175,7 @@ __device__ __forceinline__ double thermal_fn(const ThermalParams<DIM>& P, const 
 __device__ __forceinline__ void gather_dof(const double* __restrict__ sol, const TimeDev& td, int lid, double& u, double& ut) {
   const double s = __ldg(sol + lid);
   u = s; ut = 0.0;
-  if (td.transient) {
+  if (MRH_TRANSIENT(td)) {
     const double p0 = __ldg(td.prev[0] + lid);
     double bu = td.one_minus_alpha_u * p0;
     for (int k = 0; k < td.nstage_lo; ++k) bu += td.stage_w[k] * (__ldg(td.stg[k] + lid) - p0);
@@ -254,7 +256,7 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
       }
   }
   double md = 0.0;
-  if (td.transient) md = thermal_fn<DIM, FN_DENSITY>(P, xzero, td.time) * thermal_fn<DIM, FN_SPECIFIC_HEAT>(P, xzero, td.time) * adet;
+  if (MRH_TRANSIENT(td)) md = thermal_fn<DIM, FN_DENSITY>(P, xzero, td.time) * thermal_fn<DIM, FN_SPECIFIC_HEAT>(P, xzero, td.time) * adet;
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
@@ -265,7 +267,7 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
       for (int g = 0; g < NGU; ++g) k += G[g] * MRH_TAB(Stab)[g][t];
       r[i] += k * u[j];
       if (j != i) r[j] += k * u[i];
-      if (td.transient) {
+      if (MRH_TRANSIENT(td)) {
         const double mm = md * MRH_TAB(Mtab)[t];
         r[i] += mm * ut[j];
         if (j != i) r[j] += mm * ut[i];
@@ -406,7 +408,7 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
         gT[d] = s * kap * wd;
       }
       double lin = -f * wd, mw = 0.0;
-      if (td.transient) {
+      if (MRH_TRANSIENT(td)) {
         const double rc = thermal_fn<DIM, FN_DENSITY>(P, x, td.time) * thermal_fn<DIM, FN_SPECIFIC_HEAT>(P, x, td.time);
         double Tt = 0.0;
 #pragma unroll
@@ -444,58 +446,119 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 // ---------------------------------------------------------------------------------------------------------
 // Phase 2: rows completed by this step.  One warp per row; each lane owns one lane item of the row's pattern
 // (up to 4 staged values of one CSR entry), partial sums of an entry are combined with shuffles, and the
-// first lane of each entry stores it.
+// first lane of each entry stores it.  Row records and CSR row offsets of the step are staged in shared memory
+// during phase 1; the lane items of the next row are fetched while the current row is summed.
 //   res(row) (+)= -sum r_e[i]           (assemblyManager_scatter.hpp:227, sign convention -F)
 //   J(row, col) (+)= sum dF_i/du_j      (:261-271)
 //   fixed rows are skipped (:208, :253); in overwrite mode they receive the dofConstraints result
 //   directly: J(d,d) = 1, rest of the row 0, res(d) = 0 (assemblyManager_constraints.hpp:125-138).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pull_rows(const ChainDev& C, const GraphDev& G, const OutDev& O, const StepRec& ST, const int parity,
-                                          const char* __restrict__ ring) {
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+struct RowItems {  // one lane's item of a row chunk
+  unsigned meta;
+  uint4 src;
+};
+
+__device__ __forceinline__ RowItems load_items(const ChainDev& C, const uint4* __restrict__ isrc, const int4& rr, const int it0, const int lane) {
+  RowItems R;
+  R.meta = 0u;
+  R.src = make_uint4(SRC_NONE, SRC_NONE, SRC_NONE, SRC_NONE);
+  const int it = it0 + lane;
+  if (it < (int)((unsigned)rr.w & 0xFFFFu) && !(((unsigned)rr.w >> 16) & ROW_FIXED)) {
+    R.meta = __ldg(C.item_meta + rr.y + it);
+    R.src = __ldg(isrc + rr.y + it);
+  }
+  return R;
+}
+
+template <bool HAS_RES, bool HAS_JAC, bool ACC>
+__device__ __forceinline__ void pull_rows(const ChainDev& C, const OutDev& O, const int n_rows, const int parity, const unsigned ring_s,
+                                          const int4* __restrict__ tab_rec, const int64_t* __restrict__ tab_base) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const uint4* __restrict__ isrc = reinterpret_cast<const uint4*>(parity ? C.item_src1 : C.item_src0);
-  for (int lr = warp; lr < ST.n_rows; lr += nwarps) {
-    const int4 rr = __ldg(reinterpret_cast<const int4*>(C.rows + ST.row_begin + lr));
-    const int row = rr.x, pattern = rr.y;
-    const unsigned anchor = (unsigned)rr.z & 0xFFFFu, diag_k = (unsigned)rr.z >> 16;
-    const int64_t base = __ldg(G.rowptr + row);
-    if ((unsigned)rr.w & ROW_FIXED) {
-      if (!O.accumulate) {
-        const int len = (int)(__ldg(G.rowptr + row + 1) - base);
-        if (O.jac) for (int k = lane; k < len; k += 32) O.jac[base + k] = ((unsigned)k == diag_k) ? 1.0 : 0.0;
-        if (O.res && lane == 0) O.res[row] = 0.0;
-      }
-      continue;
+  int lr = warp;
+  if (lr >= n_rows) return;
+  int4 rr = tab_rec[lr];
+  int64_t base = tab_base[lr];
+  RowItems cur = load_items(C, isrc, rr, 0, lane);
+  for (;;) {
+    const int lr_next = lr + nwarps;
+    const bool has_next = lr_next < n_rows;
+    int4 rr_n = rr;
+    int64_t base_n = base;
+    RowItems nxt = cur;
+    if (has_next) {
+      rr_n = tab_rec[lr_next];
+      base_n = tab_base[lr_next];
+      nxt = load_items(C, isrc, rr_n, 0, lane);
     }
-    const int2 pt = __ldg(reinterpret_cast<const int2*>(C.patterns + pattern));
-    const char* rbase = ring + (size_t)anchor * 8u;
-    for (int it0 = 0; it0 < pt.y; it0 += 32) {
-      const int it = it0 + lane;
-      unsigned meta = 0u;
-      double acc = 0.0;
-      if (it < pt.y) {
-        meta = __ldg(C.item_meta + pt.x + it);
-        const uint4 s = __ldg(isrc + pt.x + it);
-        if (s.x != SRC_NONE) acc = *reinterpret_cast<const double*>(rbase + s.x);
-        if (s.y != SRC_NONE) acc += *reinterpret_cast<const double*>(rbase + s.y);
-        if (s.z != SRC_NONE) acc += *reinterpret_cast<const double*>(rbase + s.z);
-        if (s.w != SRC_NONE) acc += *reinterpret_cast<const double*>(rbase + s.w);
+    // ---- current row
+    const int row = rr.x;
+    const unsigned n_items = (unsigned)rr.w & 0xFFFFu;
+    if (((unsigned)rr.w >> 16) & ROW_FIXED) {
+      if (!ACC) {
+        const unsigned diag_k = (unsigned)rr.z >> 16;
+        const int len = (int)n_items;  // fixed rows carry their CSR length here
+        if (HAS_JAC) for (int k = lane; k < len; k += 32) O.jac[base + k] = ((unsigned)k == diag_k) ? 1.0 : 0.0;
+        if (HAS_RES && lane == 0) O.res[row] = 0.0;
       }
-      double v = __shfl_down_sync(0xffffffffu, acc, 1);
-      if (meta & ITEM_ADD1) acc += v;
-      if (C.need_add2) {
-        v = __shfl_down_sync(0xffffffffu, acc, 2);
-        if (meta & ITEM_ADD2) acc += v;
-      }
-      if (meta & ITEM_HEAD) {
-        if (meta & ITEM_RES) {
-          if (O.res) { if (O.accumulate) O.res[row] += -acc; else O.res[row] = -acc; }
-        } else if (O.jac) {
-          double* p = O.jac + base + (meta & 0xFFFFu);
-          if (O.accumulate) *p += acc; else *p = acc;
+    } else {
+      const unsigned rbase = ring_s + ((unsigned)rr.z & 0xFFFFu) * 8u;
+      for (unsigned it0 = 0;;) {
+        double acc = 0.0;
+        if (cur.src.x != SRC_NONE) acc = lds_f64(rbase + cur.src.x);
+        if (cur.src.y != SRC_NONE) acc += lds_f64(rbase + cur.src.y);
+        if (cur.src.z != SRC_NONE) acc += lds_f64(rbase + cur.src.z);
+        if (cur.src.w != SRC_NONE) acc += lds_f64(rbase + cur.src.w);
+        double v = __shfl_down_sync(0xffffffffu, acc, 1);
+        if (cur.meta & ITEM_ADD1) acc += v;
+        if (C.need_add2) {
+          v = __shfl_down_sync(0xffffffffu, acc, 2);
+          if (cur.meta & ITEM_ADD2) acc += v;
         }
+        const bool is_res = (cur.meta & ITEM_RES) != 0u;
+        if ((cur.meta & ITEM_HEAD) && (is_res ? HAS_RES : HAS_JAC)) {
+          double* p = is_res ? (O.res + row) : (O.jac + base + (cur.meta & 0xFFFFu));
+          double val = is_res ? -acc : acc;
+          if (ACC) val += *p;
+          *p = val;
+        }
+        it0 += 32u;
+        if (it0 >= n_items) break;
+        cur = load_items(C, isrc, rr, (int)it0, lane);
       }
     }
+    if (!has_next) break;
+    lr = lr_next; rr = rr_n; base = base_n; cur = nxt;
+  }
+}
+
+__device__ __forceinline__ void pull_dispatch(const ChainDev& C, const OutDev& O, const int n_rows, const int parity, const unsigned ring_s,
+                                              const int4* tab_rec, const int64_t* tab_base) {
+  const int mode = (O.res ? 1 : 0) | (O.jac ? 2 : 0) | (O.accumulate ? 4 : 0);
+  switch (mode) {
+    case 1: pull_rows<true, false, false>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
+    case 2: pull_rows<false, true, false>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
+    case 3: pull_rows<true, true, false>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
+    case 5: pull_rows<true, false, true>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
+    case 6: pull_rows<false, true, true>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
+    case 7: pull_rows<true, true, true>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
+    default: break;
+  }
+}
+
+// Row record of a step -> shared-memory row table entry.  Fixed rows get their CSR length in place of n_items.
+__device__ __forceinline__ void fetch_row(const ChainDev& C, const GraphDev& G, const int idx, int4& rec, int64_t& base) {
+  rec = __ldg(reinterpret_cast<const int4*>(C.rows + idx));
+  base = __ldg(G.rowptr + rec.x);
+  if (((unsigned)rec.w >> 16) & ROW_FIXED) {
+    const int len = (int)(__ldg(G.rowptr + rec.x + 1) - base);
+    rec.w = (int)(((unsigned)rec.w & 0xFFFF0000u) | (unsigned)len);
   }
 }
 
@@ -507,17 +570,35 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   const int s0 = __ldg(C.chain_step_ptr + blockIdx.x), s1 = __ldg(C.chain_step_ptr + blockIdx.x + 1);
   const int cap = C.cap;
   const int slot_doubles = cap * S::STAGE;
+  const int row_tab = C.row_tab;
+  int64_t* tab_base = reinterpret_cast<int64_t*>(ring + 2 * slot_doubles);
+  int4* tab_rec = reinterpret_cast<int4*>(tab_base + row_tab);
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+  const int tid = threadIdx.x, nth = blockDim.x;
   for (int s = s0; s < s1; ++s) {
     const int4 sr = __ldg(reinterpret_cast<const int4*>(C.steps + s));
-    StepRec ST;
-    ST.elem_begin = sr.x; ST.n_elem = sr.y; ST.row_begin = sr.z; ST.n_rows = sr.w;
+    const int elem_begin = sr.x, n_elem = sr.y, row_begin = sr.z, n_rows = sr.w;
     const int parity = (s - s0) & 1;
     double* slot = ring + parity * slot_doubles;
-    for (int le = threadIdx.x; le < ST.n_elem; le += blockDim.x)
-      thermal_element<DIM>(P, __ldg(C.step_elems + ST.elem_begin + le), cap, slot + le);
+    // row-table prefetch (first pass): issued before the element work so its latency is hidden
+    const int pass0 = n_rows < row_tab ? n_rows : row_tab;
+    int4 rec0 = make_int4(0, 0, 0, 0);
+    int64_t base0 = 0;
+    if (tid < pass0) fetch_row(C, P.graph, row_begin + tid, rec0, base0);
+    for (int le = tid; le < n_elem; le += nth)
+      thermal_element<DIM>(P, __ldg(C.step_elems + elem_begin + le), cap, slot + le);
+    if (tid < pass0) { tab_rec[tid] = rec0; tab_base[tid] = base0; }
+    for (int i = tid + nth; i < pass0; i += nth) { int4 r; int64_t b; fetch_row(C, P.graph, row_begin + i, r, b); tab_rec[i] = r; tab_base[i] = b; }
     __syncthreads();
-    pull_rows(C, P.graph, P.out, ST, parity, reinterpret_cast<const char*>(ring));
-    __syncthreads();  // the next step overwrites the slot this pull read as "previous"
+    pull_dispatch(C, P.out, pass0, parity, ring_s, tab_rec, tab_base);
+    for (int done = pass0; done < n_rows; done += row_tab) {  // steps with more rows than the table holds
+      __syncthreads();
+      const int n = (n_rows - done) < row_tab ? (n_rows - done) : row_tab;
+      for (int i = tid; i < n; i += nth) { int4 r; int64_t b; fetch_row(C, P.graph, row_begin + done + i, r, b); tab_rec[i] = r; tab_base[i] = b; }
+      __syncthreads();
+      pull_dispatch(C, P.out, n, parity, ring_s, tab_rec, tab_base);
+    }
+    __syncthreads();  // the next step overwrites the slot this pull read as "previous", and the row table
   }
 }
 
