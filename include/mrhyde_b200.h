@@ -177,7 +177,7 @@ int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* plan, int64_t n_cols, const int6
 int mrhyde_b200_halo_sum(mrhyde_b200_plan* plan, double* res, double* jac_values, void* stream);
 
 /* ---- introspection (tests, bench) ----------------------------------------------------------- */
-/* keys: "n_chains" "n_columns" "n_segments" "n_levels" "n_steps" "n_patterns" "n_pattern_items" "ring_capacity"
+/* keys: "n_chains" "n_columns" "n_segments" "n_levels" "n_steps" "n_patterns" "n_pattern_slots" "n_batches" "max_batches_per_step" "ring_capacity"
  *       "max_rows_per_step" "kernel_launches_per_assemble" "halo_launches_per_sum" "smem_bytes" "threads_per_block"
  *       "n_elem" "n_elem_with_halo" "n_rows" "nnz" "n_verts" "plan_device_bytes" "n_affine" "n_box"
  *       "n_orphan_rows" "jit" (1 = plan-specialised NVRTC kernel in use) "jit_registers"                        */

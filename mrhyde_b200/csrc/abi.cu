@@ -109,8 +109,9 @@ struct mrhyde_b200_plan {
   DevBuf<int64_t> d_rowptr, d_fixed_diag;
   DevBuf<uint8_t> d_fixed, d_eclass;
   DevBuf<StepRec> d_steps;
+  DevBuf<BatchRec> d_batches;
   DevBuf<RowRec> d_rows;
-  DevBuf<uint32_t> d_item_src0, d_item_src1, d_item_meta;
+  DevBuf<uint32_t> d_desc0, d_desc1;
   // plan-specialised (NVRTC) volume kernel; falls back to the ahead-of-time kernel when absent
   JitKernel jit, jit_transient;   // steady build at finalize; the transient build on the first transient call
   bool use_jit = false;
@@ -226,7 +227,7 @@ void emit_values(std::string& o, const double* v, size_t n) {
   for (size_t i = 0; i < n; ++i) { o += hexd(v[i]); o += (i + 1 < n) ? "," : ""; }
 }
 template <int DIM>
-std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const) {
+std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -240,6 +241,39 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   o += "__device__ __forceinline__ double mrh_sqrt(double a) { return a <= 0.0 ? 0.0 : sqrt(a); }\n";
   o += "__device__ __forceinline__ double mrh_max(double a, double b) { return b > a ? b : a; }\n";
   o += "__device__ __forceinline__ double mrh_min(double a, double b) { return b < a ? b : a; }\n";
+  // sin / cos without the math library's coefficient table in global memory: Cody-Waite reduction by pi/2 (three FMA
+  // terms, exact for |x| < 1e5) and the fdlibm k_sin / k_cos minimax polynomials on [-pi/4, pi/4] (< 1 ulp); larger or
+  // non-finite arguments take the library routine
+  o += R"MRH(
+__device__ __forceinline__ double mrh_sincos(double x, int shift) {
+  if (!(fabs(x) < 1.0e5)) return shift ? cos(x) : sin(x);
+  const double q = rint(x * 0x1.45f306dc9c883p-1);
+  double r = fma(-q, 0x1.921fb54442d18p+0, x);
+  r = fma(-q, 0x1.1a62633145c07p-54, r);
+  r = fma(-q, -0x1.f1976b7ed8fbcp-110, r);
+  const int n = (int)q + shift;
+  const double z = r * r;
+  double v;
+  if (n & 1) {
+    double p = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    p = fma(z, p, -2.75573143513906633035e-07);
+    p = fma(z, p, 2.48015872894767294178e-05);
+    p = fma(z, p, -1.38888888888741095749e-03);
+    p = fma(z, p, 4.16666666666666019037e-02);
+    v = 1.0 - (0.5 * z - z * (z * p));
+  } else {
+    double p = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    p = fma(z, p, 2.75573137070700676789e-06);
+    p = fma(z, p, -1.98412698298579493134e-04);
+    p = fma(z, p, 8.33333333332248946124e-03);
+    p = fma(z, p, -1.66666666666666324348e-01);
+    v = fma(z * r, p, r);
+  }
+  return (n & 2) ? -v : v;
+}
+__device__ __forceinline__ double mrh_sin(double x) { return mrh_sincos(x, 0); }
+__device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
+)MRH";
   const char* fn[4][2] = {{"mrh_fn_source", "thermal source"}, {"mrh_fn_diffusion", "thermal diffusion"}, {"mrh_fn_specific_heat", "specific heat"}, {"mrh_fn_density", "density"}};
   for (auto& f : fn)
     o += std::string("__device__ __forceinline__ double ") + f[0] + "(double x, double y, double z, double t) { return " + fs.codegen(f[1]) + "; }\n";
@@ -271,7 +305,22 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   arr(("Mtab[" + nt + "]").c_str(), &T.Mtab[0], S::NT);
   arr(("Ltab[" + nv + "]").c_str(), &T.Ltab[0], S::NV);
   arr(("qax[3][" + nq + "]").c_str(), &qax[0][0], 3 * S::NQ);
-  o += "}  // namespace jit_tab\n}  // namespace mrhyde_b200\n";
+  o += "}  // namespace jit_tab\n";
+  // gather patterns of the plan as constant data (warp-uniform reads in the pull phase hit the constant cache)
+  const size_t desc_words = cp.desc[0].size();
+  if (desc_words > 0 && desc_words * 4 * 2 <= 40 * 1024) {
+    o += "#define MRH_JIT_CONST_DESC 1\n";
+    for (int par = 0; par < 2; ++par) {
+      o += "__constant__ uint4 mrh_desc" + std::to_string(par) + "[" + std::to_string(desc_words / 4) + "] = {";
+      char b[64];
+      for (size_t q = 0; q < desc_words / 4; ++q) {
+        std::snprintf(b, sizeof(b), "{%uu,%uu,%uu,%uu}%s", cp.desc[par][4 * q], cp.desc[par][4 * q + 1], cp.desc[par][4 * q + 2], cp.desc[par][4 * q + 3], q + 1 < desc_words / 4 ? "," : "");
+        o += b;
+      }
+      o += "};\n";
+    }
+  }
+  o += "}  // namespace mrhyde_b200\n";
   o += kVolumeKernelSrc;
   return o;
 }
@@ -657,14 +706,16 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   co.min_segment_levels = std::max(1, std::stoi(opt(P, "min segment levels", "8")));
   if (co.column_elems < 1 || co.min_chains < 1) fail(MRHYDE_B200_ERR_INVALID, "options 'column elements' and 'min chains' must be positive");
   build_chain_plan(M, kmap, rmap, STAGE, co, P->cp);
-  P->row_tab = std::max(32, std::min(P->cp.max_rows_step, 1024));
-  P->smem = (size_t)(2 * P->cp.slot_bytes()) + (size_t)P->row_tab * 24;
   {
     const int want = std::stoi(opt(P, "threads", "0"));
-    int th = want > 0 ? want : 256;
+    int th = want > 0 ? want : std::max(128, std::min(256, ((P->cp.cap + 31) / 32) * 32));
     if (th < 32 || th > 256 || th % 32) fail(MRHYDE_B200_ERR_INVALID, "option threads must be a multiple of 32 in [32,256]");
+    if (th < P->cp.cap) th = ((P->cp.cap + 31) / 32) * 32;   // one thread per element of a sweep step
+    if (th > 256) fail(MRHYDE_B200_ERR_UNSUPPORTED, "sweep steps larger than 256 elements are not supported (lower 'column elements')");
     P->threads = th;
   }
+  // ring (2 slots) + one transpose buffer per warp
+  P->smem = (size_t)(2 * P->cp.slot_bytes()) + (size_t)(P->threads / 32) * PULL_WARP_DOUBLES * sizeof(double);
 
   P->stage_len = STAGE;
   P->kmap = kmap; P->rmap = rmap;
@@ -674,8 +725,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   };
   if (P->dim == 3) { fill_thermal_tables<3>(P, P->th3.tab); fill_host(P->th3); }
   else { fill_thermal_tables<2>(P, P->th2.tab); fill_host(P->th2); }
-  P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const)
-                              : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const);
+  P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp)
+                              : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp);
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
     if (!P->bgroups.empty()) {
@@ -699,8 +750,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   P->d_conn.upload(M.conn, tot); P->d_lids.upload(M.lids, tot);
   P->d_rowptr.upload(M.rowptr, tot); P->d_colind.upload(M.colind, tot); P->d_fixed.upload(M.fixed, tot); P->d_eclass.upload(M.eclass, tot);
   P->d_chain_step_ptr.upload(CP.chain_step_ptr, tot); P->d_steps.upload(CP.steps, tot); P->d_step_elems.upload(CP.step_elems, tot);
-  P->d_rows.upload(CP.rows, tot);
-  P->d_item_src0.upload(CP.item_src[0], tot); P->d_item_src1.upload(CP.item_src[1], tot); P->d_item_meta.upload(CP.item_meta, tot);
+  P->d_batches.upload(CP.batches, tot); P->d_rows.upload(CP.rows, tot);
+  P->d_desc0.upload(CP.desc[0], tot); P->d_desc1.upload(CP.desc[1], tot);
   P->d_orphans.upload(CP.orphan_rows, tot);
   {
     std::vector<int64_t> diag;
@@ -714,10 +765,10 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     if (diag.empty()) P->d_fixed_diag.n = 0;
   }
   ChainDev D;
-  D.chain_step_ptr = P->d_chain_step_ptr.p; D.steps = P->d_steps.p; D.step_elems = P->d_step_elems.p; D.rows = P->d_rows.p;
-  D.item_src0 = reinterpret_cast<const SrcQuad*>(P->d_item_src0.p); D.item_src1 = reinterpret_cast<const SrcQuad*>(P->d_item_src1.p);
-  D.item_meta = P->d_item_meta.p; D.cap = CP.cap; D.need_add2 = 0; D.row_tab = P->row_tab;
-  for (uint32_t mt : CP.item_meta) if (mt & ITEM_ADD2) D.need_add2 = 1;
+  D.chain_step_ptr = P->d_chain_step_ptr.p; D.steps = P->d_steps.p; D.step_elems = P->d_step_elems.p;
+  D.batches = P->d_batches.p; D.rows = P->d_rows.p;
+  D.desc0 = reinterpret_cast<const SrcQuad*>(P->d_desc0.p); D.desc1 = reinterpret_cast<const SrcQuad*>(P->d_desc1.p);
+  D.cap = CP.cap;
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
   auto fill_common = [&](auto& th) {
     th.vx = P->d_vx.p; th.vy = P->d_vy.p; th.vz = P->d_vz.p;
@@ -881,7 +932,9 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "n_levels") *value = P->cp.n_levels;
   else if (k == "n_steps") *value = (int64_t)P->cp.steps.size();
   else if (k == "n_patterns") *value = (int64_t)P->cp.patterns.size();
-  else if (k == "n_pattern_items") *value = (int64_t)P->cp.item_meta.size();
+  else if (k == "n_pattern_slots") *value = (int64_t)(P->cp.desc[0].size() / SLOT_SRCS);
+  else if (k == "n_batches") *value = (int64_t)P->cp.batches.size();
+  else if (k == "max_batches_per_step") *value = P->cp.max_batches_step;
   else if (k == "ring_capacity") *value = P->cp.cap;
   else if (k == "max_rows_per_step") *value = P->cp.max_rows_step;
   else if (k == "kernel_launches_per_assemble") *value = P->launches_per_assemble;

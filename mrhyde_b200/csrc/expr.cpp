@@ -354,6 +354,7 @@ std::string FunctionSet::gen_chain(const Node& n, const std::function<std::strin
       if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: unary operator in a chained position");
       if (op == "abs") acc = "mrh_abs(" + d + ")";
       else if (op == "sqrt") acc = "mrh_sqrt(" + d + ")";
+      else if (op == "sin" || op == "cos") acc = "mrh_" + op + "(" + d + ")";   // table-free kernels (jit prelude)
       else acc = op + "(" + d + ")";
     } else {
       if (k == 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: binary operator without a left operand");

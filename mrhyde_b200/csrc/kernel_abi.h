@@ -20,42 +20,43 @@ namespace mrhyde_b200 {
 
 // ---- sweep plan records (plan.hpp explains the scheme) ------------------------------------------------
 struct StepRec {      // one level of one chain
-  int32_t elem_begin, n_elem;   // into step_elems (global element ids, ascending); n_elem <= cap
-  int32_t row_begin, n_rows;    // into rows: the rows that are complete after this step
+  int32_t elem_begin, n_elem;     // into step_elems (global element ids, ascending); n_elem <= cap
+  int32_t batch_begin, n_batches; // into batches: the rows that are complete after this step
 };
-struct RowRec {       // 16 bytes, read as one int4
+// Rows of a step are grouped into BATCHES of up to 32 rows that share one gather pattern; a warp takes a batch with one
+// row per lane, so every lane walks the same descriptor list and differs only in its ring anchor and output offset.
+struct BatchRec {     // 16 bytes, read as one int4
+  int32_t row_begin;  // into rows
+  int32_t desc_begin; // first slot descriptor of the pattern
+  uint16_t n_rows;    // 1..32
+  uint16_t n_slots;   // CSR entries of a row + 1: the last slot is the residual entry
+  uint32_t flags;     // bit 0: strong-Dirichlet rows (isFixedDOF): no pattern, rows may differ in length
+};
+struct RowRec {       // 8 bytes
   int32_t row;        // local row id (LID)
-  int32_t item_begin; // first lane item of the row's pattern
   uint16_t anchor;    // ring-slot element index the pattern offsets are relative to
-  uint16_t diag_k;    // position of the diagonal entry inside the CSR row (0xFFFF if absent)
-  uint16_t n_items;   // lane items of the pattern (padded so no CSR slot straddles a 32-lane chunk)
-  uint16_t flags;     // bit 0: strong-Dirichlet row (isFixedDOF)
+  uint16_t aux;       // fixed rows: position of the diagonal entry inside the CSR row (0xFFFF if absent)
 };
 struct PatternRec {   // host-side bookkeeping of the de-duplicated patterns
-  int32_t item_begin, n_items;
+  int32_t desc_begin, n_slots;
 };
-// A lane item sums up to 4 staged doubles.  item_src[parity][item] holds 4 byte offsets into the ring
-// (0xFFFFFFFF = unused) valid when the current step writes ring slot `parity`; item_meta packs
-//   bits 0-15  k: CSR position in the row (residual item: unused)
-//   bit 16 HEAD  this lane stores the sum        bit 17 ADD1  add lane+1's partial before storing
-//   bit 18 ADD2  then add lane+2's partial       bit 19 RES   the residual entry of the row
-constexpr uint32_t ITEM_HEAD = 1u << 16, ITEM_ADD1 = 1u << 17, ITEM_ADD2 = 1u << 18, ITEM_RES = 1u << 19;
+// A slot descriptor lists up to 8 staged doubles (byte offsets into the ring relative to the row's anchor,
+// 0xFFFFFFFF = unused, ascending element order); desc[parity] is valid when the current step writes ring slot `parity`.
 constexpr uint32_t SRC_NONE = 0xFFFFFFFFu;
-constexpr uint32_t ROW_FIXED = 1u;
+constexpr uint32_t BATCH_FIXED = 1u;
+constexpr int SLOT_SRCS = 8;
 
-struct SrcQuad { uint32_t x, y, z, w; };  // layout of one item_src entry (read as uint4 on the device)
+struct SrcQuad { uint32_t x, y, z, w; };  // half a slot descriptor (read as uint4 on the device)
 
 struct ChainDev {
   const int32_t* chain_step_ptr;   // [n_chains+1]
   const StepRec* steps;
   const int32_t* step_elems;
+  const BatchRec* batches;
   const RowRec* rows;
-  const SrcQuad* item_src0;        // parity 0 / 1 tables
-  const SrcQuad* item_src1;
-  const uint32_t* item_meta;
+  const SrcQuad* desc0;            // parity 0 / 1 descriptor tables, 2 SrcQuad per slot
+  const SrcQuad* desc1;
   int32_t cap;                     // ring slot capacity (elements)
-  int32_t need_add2;               // some CSR entry has more than 8 contributions
-  int32_t row_tab;                 // capacity of the shared-memory row table (rows staged per pass of the pull phase)
 };
 
 struct GraphDev {

@@ -126,8 +126,9 @@ void MeshGraph::classify_cells() {
 namespace {
 
 struct ChainWork {  // per-chain scratch produced in parallel, concatenated afterwards
-  std::vector<StepRec> steps;       // elem_begin / row_begin local to this chain
+  std::vector<StepRec> steps;       // elem_begin / batch_begin local to this chain
   std::vector<int32_t> elems;
+  std::vector<BatchRec> batches;    // row_begin local to this chain
   std::vector<RowRec> rows;
 };
 
@@ -217,7 +218,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
   int32_t nlevels = 0;
   for (int64_t e = 0; e < ne; ++e) nlevels = std::max(nlevels, level[(size_t)e] + 1);
 
-  const int cap_limit = (int)std::min<size_t>(opt.smem_budget / 2 / ((size_t)stage_len * 8), 1024);
+  const int cap_limit = (int)std::min<size_t>(opt.smem_budget / 2 / ((size_t)stage_len * 8), 256);   // one thread per element, <= 256 threads
   if (cap_limit < 1) throw std::runtime_error("plan: a single element does not fit the shared-memory ring");
   int column_elems = std::max(1, std::min(opt.column_elems, cap_limit));
 
@@ -343,7 +344,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
         size_t k2 = k;
         while (k2 < need.size() && level[(size_t)need[k2]] == level[(size_t)need[k]]) ++k2;
         StepRec S;
-        S.elem_begin = (int32_t)k; S.n_elem = (int32_t)(k2 - k); S.row_begin = 0; S.n_rows = 0;
+        S.elem_begin = (int32_t)k; S.n_elem = (int32_t)(k2 - k); S.batch_begin = 0; S.n_batches = 0;
         W.steps.push_back(S);
         int32_t cur = max_step_elems.load();
         while (S.n_elem > cur && !max_step_elems.compare_exchange_weak(cur, S.n_elem)) {}
@@ -370,11 +371,12 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       std::string key;
     };
     std::vector<Scratch> scratch((size_t)nthreads);
-    std::atomic<int32_t> max_rows_step(0);
+    std::atomic<int32_t> max_rows_step(0), max_batches_step(0);
     int64_t tagbase = 0;
     std::vector<int64_t> chain_tag((size_t)nchains);
     for (int32_t c = 0; c < nchains; ++c) { chain_tag[(size_t)c] = tagbase; tagbase += (int64_t)work[(size_t)c].steps.size() + 2; }
     if (tagbase > 0x7fffffff) throw std::runtime_error("plan: too many sweep steps");
+    struct StepRow { int32_t pid; RowRec rec; };
     parallel_for(nchains, [&](int64_t c, int tid) {
       Scratch& S = scratch[(size_t)tid];
       if (S.pos_cur.empty()) { S.pos_cur.assign((size_t)ne, 0); S.pos_prev.assign((size_t)ne, 0); S.tag_cur.assign((size_t)ne, -1); S.tag_prev.assign((size_t)ne, -1); }
@@ -384,6 +386,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       std::sort(rows_sorted.begin(), rows_sorted.end(), [&](int32_t a, int32_t b) {
         return row_level[(size_t)a] < row_level[(size_t)b] || (row_level[(size_t)a] == row_level[(size_t)b] && a < b);
       });
+      std::vector<StepRow> step_rows;
       size_t rk = 0;
       for (size_t s = 0; s < W.steps.size(); ++s) {
         StepRec& ST = W.steps[s];
@@ -392,14 +395,23 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
         // previous step's map becomes pos_prev (swap roles), current step is stamped fresh
         S.pos_cur.swap(S.pos_prev); S.tag_cur.swap(S.tag_prev);
         for (int32_t l = 0; l < ST.n_elem; ++l) { const int32_t e = W.elems[(size_t)(ST.elem_begin + l)]; S.pos_cur[(size_t)e] = l; S.tag_cur[(size_t)e] = tag; }
-        ST.row_begin = (int32_t)W.rows.size();
-        while (rk < rows_sorted.size() && row_level[(size_t)rows_sorted[rk]] < lv) ++rk;  // cannot happen; defensive
+        step_rows.clear();
+        if (rk < rows_sorted.size() && row_level[(size_t)rows_sorted[rk]] < lv) throw std::runtime_error("plan: a row precedes its sweep step (internal error)");
         for (; rk < rows_sorted.size() && row_level[(size_t)rows_sorted[rk]] == lv; ++rk) {
           const int32_t r = rows_sorted[rk];
           const int64_t rs = m.rowptr[(size_t)r], re = m.rowptr[(size_t)r + 1];
           const int32_t len = (int32_t)(re - rs);
           if (len > 0xFFFE) throw std::runtime_error("plan: CSR row longer than 65534 entries");
           const int32_t* cols = &m.colind[(size_t)rs];
+          StepRow SR;
+          SR.rec.row = r; SR.rec.anchor = 0; SR.rec.aux = 0xFFFF;
+          if (m.fixed[(size_t)r]) {  // strong-Dirichlet row: nothing is gathered (scatter.hpp:208, 253)
+            const int32_t* dg = std::lower_bound(cols, cols + len, r);
+            SR.rec.aux = (dg != cols + len && *dg == r) ? (uint16_t)(dg - cols) : (uint16_t)0xFFFF;
+            SR.pid = -1;
+            step_rows.push_back(SR);
+            continue;
+          }
           if (S.slot_src.size() < (size_t)len + 1) S.slot_src.resize((size_t)len + 1);
           for (int32_t k = 0; k <= len; ++k) S.slot_src[(size_t)k].clear();
           uint32_t anchor = 0xFFFFFFFFu;
@@ -419,31 +431,18 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
             }
             S.slot_src[(size_t)len].push_back((rel << 31) | (le << 12) | (uint32_t)rmap[(size_t)i]);
           }
-          // lane items
+          // slot descriptors (parity 0), keyed for de-duplication
           std::string& key = S.key;
           key.clear();
-          int32_t n_items = 0;
           auto put = [&](uint32_t v) { key.append((const char*)&v, 4); };
           for (int32_t k = 0; k <= len; ++k) {
             const auto& src = S.slot_src[(size_t)k];
-            const int nch = std::max(1, (int)((src.size() + 3) / 4));
-            if (nch > 4) throw std::runtime_error("plan: more than 16 elements contribute to one matrix entry");
-            while ((n_items & 31) + nch > 32) { put(0u); for (int z = 0; z < 4; ++z) put(SRC_NONE); ++n_items; }  // pad: keep the slot in one 32-lane chunk
-            for (int ch = 0; ch < nch; ++ch) {
-              uint32_t meta = (uint32_t)(k == len ? 0 : k);
-              if (ch == 0) meta |= ITEM_HEAD;
-              if ((ch & 1) == 0 && ch + 1 < nch) meta |= ITEM_ADD1;
-              if (ch == 0 && nch > 2) meta |= ITEM_ADD2;
-              if (k == len) meta |= ITEM_RES;
-              put(meta);
-              for (int z = 0; z < 4; ++z) {
-                const size_t ci = (size_t)ch * 4 + z;
-                if (ci < src.size()) {
-                  const uint32_t rel = src[ci] >> 31, le = (src[ci] >> 12) & 0x7FFFFu, t = src[ci] & 0xFFFu;
-                  put(rel * slot_bytes + (t * cap + (le - anchor)) * 8u);   // parity-0 offset; parity 1 flips the slot
-                } else put(SRC_NONE);
-              }
-              ++n_items;
+            if (src.size() > (size_t)SLOT_SRCS) throw std::runtime_error("plan: more than 8 elements contribute to one matrix entry");
+            for (int z = 0; z < SLOT_SRCS; ++z) {
+              if ((size_t)z < src.size()) {
+                const uint32_t rel = src[(size_t)z] >> 31, le = (src[(size_t)z] >> 12) & 0x7FFFFu, t = src[(size_t)z] & 0xFFFu;
+                put(rel * slot_bytes + (t * cap + (le - anchor)) * 8u);   // parity-0 offset; parity 1 flips the slot
+              } else put(SRC_NONE);
             }
           }
           int32_t pid;
@@ -456,50 +455,61 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
             else {
               pid = (int32_t)out.patterns.size();
               PatternRec PR;
-              PR.item_begin = (int32_t)out.item_meta.size(); PR.n_items = n_items;
+              PR.desc_begin = (int32_t)(out.desc[0].size() / SLOT_SRCS); PR.n_slots = len + 1;
               out.patterns.push_back(PR);
               const uint32_t* w = (const uint32_t*)key.data();
-              for (int32_t it = 0; it < n_items; ++it) {
-                out.item_meta.push_back(w[(size_t)it * 5]);
-                for (int z = 0; z < 4; ++z) {
-                  const uint32_t s0 = w[(size_t)it * 5 + 1 + z];
-                  uint32_t s1 = s0;
-                  if (s0 != SRC_NONE) s1 = (s0 >= slot_bytes) ? s0 - slot_bytes : s0 + slot_bytes;
-                  out.item_src[0].push_back(s0);
-                  out.item_src[1].push_back(s1);
-                }
+              for (size_t z = 0; z < key.size() / 4; ++z) {
+                const uint32_t s0 = w[z];
+                uint32_t s1 = s0;
+                if (s0 != SRC_NONE) s1 = (s0 >= slot_bytes) ? s0 - slot_bytes : s0 + slot_bytes;
+                out.desc[0].push_back(s0);
+                out.desc[1].push_back(s1);
               }
               pattern_ids.emplace(key, pid);
             }
             S.cache.emplace(key, pid);
           }
-          RowRec RR;
-          RR.row = r; RR.anchor = (uint16_t)anchor;
-          {
-            std::lock_guard<std::mutex> lock(mu);   // patterns may be reallocated by other threads
-            RR.item_begin = out.patterns[(size_t)pid].item_begin;
-          }
-          if (n_items > 0xFFFF) throw std::runtime_error("plan: a row pattern has more than 65535 lane items");
-          RR.n_items = (uint16_t)n_items;
-          const int32_t* dg = std::lower_bound(cols, cols + len, r);
-          RR.diag_k = (dg != cols + len && *dg == r) ? (uint16_t)(dg - cols) : (uint16_t)0xFFFF;
-          RR.flags = m.fixed[(size_t)r] ? (uint16_t)ROW_FIXED : (uint16_t)0;
-          W.rows.push_back(RR);
+          SR.pid = pid; SR.rec.anchor = (uint16_t)anchor;
+          step_rows.push_back(SR);
         }
-        ST.n_rows = (int32_t)W.rows.size() - ST.row_begin;
+        // batches: up to 32 rows of one pattern (fixed rows together), rows ascending inside a batch
+        std::stable_sort(step_rows.begin(), step_rows.end(), [](const StepRow& a, const StepRow& b) { return a.pid < b.pid; });
+        ST.batch_begin = (int32_t)W.batches.size();
+        size_t k = 0;
+        while (k < step_rows.size()) {
+          size_t k2 = k;
+          while (k2 < step_rows.size() && step_rows[k2].pid == step_rows[k].pid && k2 - k < 32) ++k2;
+          BatchRec B;
+          B.row_begin = (int32_t)W.rows.size(); B.n_rows = (uint16_t)(k2 - k);
+          if (step_rows[k].pid < 0) { B.desc_begin = 0; B.n_slots = 0; B.flags = BATCH_FIXED; }
+          else {
+            std::lock_guard<std::mutex> lock(mu);   // patterns may be reallocated by other threads
+            const PatternRec& PR = out.patterns[(size_t)step_rows[k].pid];
+            B.desc_begin = PR.desc_begin; B.n_slots = (uint16_t)PR.n_slots; B.flags = 0;
+          }
+          for (size_t q = k; q < k2; ++q) W.rows.push_back(step_rows[q].rec);
+          W.batches.push_back(B);
+          k = k2;
+        }
+        ST.n_batches = (int32_t)W.batches.size() - ST.batch_begin;
+        const int32_t nrows_step = (int32_t)step_rows.size();
         int32_t cur = max_rows_step.load();
-        while (ST.n_rows > cur && !max_rows_step.compare_exchange_weak(cur, ST.n_rows)) {}
+        while (nrows_step > cur && !max_rows_step.compare_exchange_weak(cur, nrows_step)) {}
+        cur = max_batches_step.load();
+        while (ST.n_batches > cur && !max_batches_step.compare_exchange_weak(cur, ST.n_batches)) {}
       }
       if (rk != rows_sorted.size()) throw std::runtime_error("plan: a row was not assigned to a sweep step (internal error)");
     });
     out.max_rows_step = max_rows_step.load();
+    out.max_batches_step = max_batches_step.load();
 
     // ---- concatenate
     out.chain_step_ptr.assign((size_t)nchains + 1, 0);
     for (int32_t c = 0; c < nchains; ++c) {
       ChainWork& W = work[(size_t)c];
-      const int32_t eb = (int32_t)out.step_elems.size(), rb = (int32_t)out.rows.size();
-      for (StepRec S : W.steps) { S.elem_begin += eb; S.row_begin += rb; out.steps.push_back(S); }
+      const int32_t eb = (int32_t)out.step_elems.size(), bb = (int32_t)out.batches.size(), rb = (int32_t)out.rows.size();
+      for (StepRec S : W.steps) { S.elem_begin += eb; S.batch_begin += bb; out.steps.push_back(S); }
+      for (BatchRec B : W.batches) { B.row_begin += rb; out.batches.push_back(B); }
       out.step_elems.insert(out.step_elems.end(), W.elems.begin(), W.elems.end());
       out.rows.insert(out.rows.end(), W.rows.begin(), W.rows.end());
       out.chain_step_ptr[(size_t)c + 1] = (int32_t)out.steps.size();
@@ -522,45 +532,28 @@ void host_apply_chain_plan(const MeshGraph& m, const ChainPlan& cp, const double
         const int32_t e = cp.step_elems[(size_t)(ST.elem_begin + l)];
         for (int t = 0; t < SL; ++t) ring[(size_t)(parity * slot_doubles + (int64_t)t * cp.cap + l)] = stage[(size_t)e * SL + t];
       }
-      for (int32_t lr = 0; lr < ST.n_rows; ++lr) {
-        const RowRec& R = cp.rows[(size_t)(ST.row_begin + lr)];
-        const int64_t base = m.rowptr[(size_t)R.row];
-        const int32_t len = (int32_t)(m.rowptr[(size_t)R.row + 1] - base);
-        if (R.flags & ROW_FIXED) {
-          if (!accumulate) {
-            if (jac) for (int32_t k = 0; k < len; ++k) jac[base + k] = (k == (int32_t)R.diag_k) ? 1.0 : 0.0;
-            if (res) res[R.row] = 0.0;
-          }
-          continue;
-        }
-        PatternRec PT;
-        PT.item_begin = R.item_begin; PT.n_items = R.n_items;
-        for (int32_t it0 = 0; it0 < PT.n_items; it0 += 32) {
-          double acc[32];
-          uint32_t meta[32];
-          const int32_t nl = std::min(32, PT.n_items - it0);
-          for (int32_t l = 0; l < 32; ++l) { acc[l] = 0.0; meta[l] = 0; }
-          for (int32_t l = 0; l < nl; ++l) {
-            const size_t it = (size_t)(PT.item_begin + it0 + l);
-            meta[l] = cp.item_meta[it];
-            for (int z = 0; z < 4; ++z) {
-              const uint32_t src = cp.item_src[parity][it * 4 + z];
-              if (src != SRC_NONE) acc[l] += ring[(size_t)(src / 8 + R.anchor)];
+      for (int32_t b = 0; b < ST.n_batches; ++b) {
+        const BatchRec& B = cp.batches[(size_t)(ST.batch_begin + b)];
+        for (int32_t lane = 0; lane < (int32_t)B.n_rows; ++lane) {
+          const RowRec& R = cp.rows[(size_t)(B.row_begin + lane)];
+          const int64_t base = m.rowptr[(size_t)R.row];
+          const int32_t len = (int32_t)(m.rowptr[(size_t)R.row + 1] - base);
+          if (B.flags & BATCH_FIXED) {
+            if (!accumulate) {
+              if (jac) for (int32_t k = 0; k < len; ++k) jac[base + k] = (k == (int32_t)R.aux) ? 1.0 : 0.0;
+              if (res) res[R.row] = 0.0;
             }
+            continue;
           }
-          double nxt[32];
-          for (int32_t l = 0; l < 32; ++l) nxt[l] = (l + 1 < 32) ? acc[l + 1] : 0.0;
-          for (int32_t l = 0; l < 32; ++l) if (meta[l] & ITEM_ADD1) acc[l] += nxt[l];
-          for (int32_t l = 0; l < 32; ++l) nxt[l] = (l + 2 < 32) ? acc[l + 2] : 0.0;
-          for (int32_t l = 0; l < 32; ++l) if (meta[l] & ITEM_ADD2) acc[l] += nxt[l];
-          for (int32_t l = 0; l < nl; ++l) {
-            if (!(meta[l] & ITEM_HEAD)) continue;
-            if (meta[l] & ITEM_RES) {
-              if (res) { if (accumulate) res[R.row] += -acc[l]; else res[R.row] = -acc[l]; }
-            } else if (jac) {
-              const int64_t p = base + (meta[l] & 0xFFFFu);
-              if (accumulate) jac[p] += acc[l]; else jac[p] = acc[l];
+          if ((int32_t)B.n_slots != len + 1) throw std::runtime_error("plan: batch pattern does not match the row length (internal error)");
+          for (int32_t k = 0; k <= len; ++k) {
+            double acc = 0.0;
+            for (int z = 0; z < SLOT_SRCS; ++z) {
+              const uint32_t src = cp.desc[parity][((size_t)B.desc_begin + (size_t)k) * SLOT_SRCS + (size_t)z];
+              if (src != SRC_NONE) acc += ring[(size_t)(src / 8 + R.anchor)];
             }
+            if (k == len) { if (res) { if (accumulate) res[R.row] += -acc; else res[R.row] = -acc; } }
+            else if (jac) { if (accumulate) jac[base + k] += acc; else jac[base + k] = acc; }
           }
         }
       }

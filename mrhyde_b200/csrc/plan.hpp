@@ -43,15 +43,15 @@ struct ChainPlan {
   int32_t n_chains = 0, n_levels = 0, n_columns = 0, n_segments = 0;
   int32_t cap = 0;             // ring slot capacity in elements (max elements of any step)
   int32_t stage_len = 0;       // staged doubles per element
-  int32_t max_rows_step = 0;
+  int32_t max_rows_step = 0, max_batches_step = 0;
   int64_t n_elem_with_halo = 0;
   std::vector<int32_t> chain_step_ptr;   // [n_chains+1]
   std::vector<StepRec> steps;
   std::vector<int32_t> step_elems;
+  std::vector<BatchRec> batches;
   std::vector<RowRec> rows;
   std::vector<PatternRec> patterns;
-  std::vector<uint32_t> item_src[2];     // 4 per item
-  std::vector<uint32_t> item_meta;
+  std::vector<uint32_t> desc[2];         // SLOT_SRCS per slot
   std::vector<int32_t> orphan_rows;      // rows no element touches
   int64_t slot_bytes() const { return (int64_t)cap * stage_len * 8; }
 };

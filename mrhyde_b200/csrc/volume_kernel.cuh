@@ -192,25 +192,35 @@ __device__ __forceinline__ void gather_dof(const double* __restrict__ sol, const
 // tables, K = kappa |det| sum_ab G_ab Stab_ab with G = J^-1 J^-T (BOX: J diagonal, only the G_aa terms exist).
 // Each entry is staged as soon as it is final so that only r, u and G stay live in registers.
 // ---------------------------------------------------------------------------------------------------------
+// Inputs of one element, fetched one sweep step ahead (stage 1: connectivity and LIDs, stage 2: state and the
+// vertices that span a parallelepiped) so that the global-memory latency is hidden behind the previous step's work.
+template <int DIM>
+struct ElemPre {
+  int ecls;                       // 0 general cell, 1 parallelepiped, 2 axis-aligned box
+  int cn[1 << DIM], ld[1 << DIM];
+  double u[1 << DIM], ut[1 << DIM];
+  double xv[DIM + 1][DIM];        // vertex 0 and its +xi, +eta, +zeta neighbours (Shards vertices 1, 3, 4)
+};
+
 template <int DIM, bool BOX>
-__device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, const int (&cn)[1 << DIM], const double (&u)[1 << DIM],
-                                               const double (&ut)[1 << DIM], double (&r)[1 << DIM], const int cap, double* __restrict__ st) {
+__device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double (&r)[1 << DIM], const int cap,
+                                               double* __restrict__ st) {
+  const double (&u)[1 << DIM] = E.u;
+  const double (&ut)[1 << DIM] = E.ut;
   typedef Q1Shape<DIM> S;
   constexpr int NV = S::NV, NQ = S::NQ, NG = S::NG;
   constexpr int NGU = BOX ? DIM : NG;
   const TimeDev& td = P.td;
-  constexpr int nb[3] = {1, 3, 4};  // +xi, +eta, +zeta neighbours of vertex 0 (Shards order)
-  const double* vc[3] = {P.vx, P.vy, P.vz};
   double X0[DIM], J[DIM][DIM], G[NG];
   double adet;
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) X0[d] = __ldg(vc[d] + cn[0]);
+  for (int d = 0; d < DIM; ++d) X0[d] = E.xv[0][d];
   const double xzero[3] = {0.0, 0.0, 0.0};
   const double kap = thermal_fn<DIM, FN_DIFFUSION>(P, xzero, td.time);
   if constexpr (BOX) {
     double h[DIM];
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) h[d] = 0.5 * (__ldg(vc[d] + cn[nb[d]]) - X0[d]);
+    for (int d = 0; d < DIM; ++d) h[d] = 0.5 * (E.xv[d + 1][d] - X0[d]);
     double det = h[0];
 #pragma unroll
     for (int d = 1; d < DIM; ++d) det *= h[d];
@@ -233,7 +243,7 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
 #pragma unroll
-      for (int a = 0; a < DIM; ++a) J[d][a] = 0.5 * (__ldg(vc[d] + cn[nb[a]]) - X0[d]);
+      for (int a = 0; a < DIM; ++a) J[d][a] = 0.5 * (E.xv[a + 1][d] - X0[d]);
     const double det = det_inverse<DIM>(J, Ji);
     adet = fabs(det);
     const double kd = kap * adet;
@@ -327,37 +337,50 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
 //   st points at this element's column of the ring slot; entry t lives at st[t * cap]
 // ---------------------------------------------------------------------------------------------------------
 template <int DIM>
-__device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, const int e, const int cap, double* __restrict__ st) {
+__device__ __forceinline__ void elem_stage1(const ThermalParams<DIM>& P, const int e, ElemPre<DIM>& E) {
+  constexpr int NV = 1 << DIM;
+  const int4* c4 = reinterpret_cast<const int4*>(P.conn + (size_t)e * NV);
+  const int4* l4 = reinterpret_cast<const int4*>(P.lids + (size_t)e * NV);
+#pragma unroll
+  for (int k = 0; k < NV / 4; ++k) {
+    const int4 a = __ldg(c4 + k), b = __ldg(l4 + k);
+    E.cn[4 * k] = a.x; E.cn[4 * k + 1] = a.y; E.cn[4 * k + 2] = a.z; E.cn[4 * k + 3] = a.w;
+    E.ld[4 * k] = b.x; E.ld[4 * k + 1] = b.y; E.ld[4 * k + 2] = b.z; E.ld[4 * k + 3] = b.w;
+  }
+  E.ecls = P.eclass[e];
+}
+
+template <int DIM>
+__device__ __forceinline__ void elem_stage2(const ThermalParams<DIM>& P, ElemPre<DIM>& E) {
+  constexpr int NV = 1 << DIM;
+  constexpr int nb[4] = {0, 1, 3, 4};  // vertex 0 and its +xi, +eta, +zeta neighbours (Shards order)
+  const double* vc[3] = {P.vx, P.vy, P.vz};
+#pragma unroll
+  for (int i = 0; i < NV; ++i) gather_dof(P.sol, P.td, E.ld[i], E.u[i], E.ut[i]);
+#pragma unroll
+  for (int v = 0; v <= DIM; ++v)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) E.xv[v][d] = __ldg(vc[d] + E.cn[nb[v]]);
+}
+
+template <int DIM>
+__device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, const int cap, double* __restrict__ st) {
   typedef Q1Shape<DIM> S;
   constexpr int NV = S::NV, NQ = S::NQ, NT = S::NT;
   const TimeDev& td = P.td;
   const double* vc[3] = {P.vx, P.vy, P.vz};
-
-  int cn[NV], ld[NV];
-  {
-    const int4* c4 = reinterpret_cast<const int4*>(P.conn + (size_t)e * NV);
-    const int4* l4 = reinterpret_cast<const int4*>(P.lids + (size_t)e * NV);
-#pragma unroll
-    for (int k = 0; k < NV / 4; ++k) {
-      const int4 a = __ldg(c4 + k), b = __ldg(l4 + k);
-      cn[4 * k] = a.x; cn[4 * k + 1] = a.y; cn[4 * k + 2] = a.z; cn[4 * k + 3] = a.w;
-      ld[4 * k] = b.x; ld[4 * k + 1] = b.y; ld[4 * k + 2] = b.z; ld[4 * k + 3] = b.w;
-    }
-  }
-  const int ecls = P.eclass[e];
-
-  // ---- gather + transient combination (u, u_t per dof)
-  double u[NV], ut[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) gather_dof(P.sol, td, ld[i], u[i], ut[i]);
+  const int (&cn)[NV] = E.cn;
+  const double (&u)[NV] = E.u;
+  const double (&ut)[NV] = E.ut;
+  const int ecls = E.ecls;
 
   double r[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) r[i] = 0.0;
 
   if (ecls != 0 && MRH_ALL_CONST) {
-    if (ecls == 2) thermal_affine<DIM, true>(P, cn, u, ut, r, cap, st);
-    else thermal_affine<DIM, false>(P, cn, u, ut, r, cap, st);
+    if (ecls == 2) thermal_affine<DIM, true>(P, E, r, cap, st);
+    else thermal_affine<DIM, false>(P, E, r, cap, st);
   } else {
     // ================= general path: per-point Jacobian and coefficients =================
     double K[NT];
@@ -367,7 +390,14 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 #pragma unroll
     for (int n = 0; n < NV; ++n)
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) X[n][d] = __ldg(vc[d] + cn[n]);
+      for (int d = 0; d < DIM; ++d) {
+        // vertices 0, 1, 3, 4 came with the prefetch
+        if (n == 0) X[n][d] = E.xv[0][d];
+        else if (n == 1) X[n][d] = E.xv[1][d];
+        else if (n == 3) X[n][d] = E.xv[2][d];
+        else if (n == 4 && DIM == 3) X[n][d] = E.xv[DIM][d];
+        else X[n][d] = __ldg(vc[d] + cn[n]);
+      }
     MRH_UNROLL_Q
     for (int q = 0; q < NQ; ++q) {
       double J[DIM][DIM], Ji[DIM][DIM];
@@ -444,121 +474,136 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Phase 2: rows completed by this step.  One warp per row; each lane owns one lane item of the row's pattern
-// (up to 4 staged values of one CSR entry), partial sums of an entry are combined with shuffles, and the
-// first lane of each entry stores it.  Row records and CSR row offsets of the step are staged in shared memory
-// during phase 1; the lane items of the next row are fetched while the current row is summed.
+// Phase 2: rows completed by this step.  A warp takes a BATCH of up to 32 rows that share one gather pattern,
+// one row per lane: all lanes walk the same slot descriptors (warp-uniform loads and branches) and differ only
+// in their ring anchor, so the shared-memory reads of a warp are consecutive.  Each CSR entry is the sum of its
+// staged contributions in ascending element order.  Results go through a small per-warp transpose buffer so
+// that the global stores cover 32 contiguous bytes per row.
 //   res(row) (+)= -sum r_e[i]           (assemblyManager_scatter.hpp:227, sign convention -F)
 //   J(row, col) (+)= sum dF_i/du_j      (:261-271)
 //   fixed rows are skipped (:208, :253); in overwrite mode they receive the dofConstraints result
 //   directly: J(d,d) = 1, rest of the row 0, res(d) = 0 (assemblyManager_constraints.hpp:125-138).
 // ---------------------------------------------------------------------------------------------------------
+#ifdef MRH_JIT_CONST_DESC
+#define MRH_DESC_LOAD(p) (*(p))
+#else
+#define MRH_DESC_LOAD(p) __ldg(p)
+#endif
+constexpr int PULL_CHUNK = 4;                       // CSR entries per transpose round
+constexpr int PULL_PITCH = PULL_CHUNK + 1;          // doubles per lane in the transpose buffer (padding: no bank conflicts)
+constexpr int PULL_WARP_DOUBLES = 32 * PULL_PITCH + 32;  // + 32 row offsets
+
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
 }
 
-struct RowItems {  // one lane's item of a row chunk
-  unsigned meta;
-  uint4 src;
+// sum of one slot for this lane's row
+__device__ __forceinline__ double slot_sum(const uint4* __restrict__ desc, const int k, const unsigned rbase) {
+  const uint4 a = MRH_DESC_LOAD(desc + 2 * k);
+  double acc = 0.0;
+  if (a.x != SRC_NONE) acc = lds_f64(rbase + a.x);
+  if (a.y != SRC_NONE) acc += lds_f64(rbase + a.y);
+  if (a.z != SRC_NONE) acc += lds_f64(rbase + a.z);
+  if (a.w != SRC_NONE) {
+    acc += lds_f64(rbase + a.w);
+    const uint4 b = MRH_DESC_LOAD(desc + 2 * k + 1);
+    if (b.x != SRC_NONE) acc += lds_f64(rbase + b.x);
+    if (b.y != SRC_NONE) acc += lds_f64(rbase + b.y);
+    if (b.z != SRC_NONE) acc += lds_f64(rbase + b.z);
+    if (b.w != SRC_NONE) acc += lds_f64(rbase + b.w);
+  }
+  return acc;
+}
+
+struct BatchRegs {  // what a lane holds of its batch: header (uniform), its row record and CSR offset
+  int4 hdr;         // row_begin, desc_begin, n_rows | n_slots << 16, flags
+  int2 rec;         // row, anchor | aux << 16
+  int64_t base;
 };
 
-__device__ __forceinline__ RowItems load_items(const ChainDev& C, const uint4* __restrict__ isrc, const int4& rr, const int it0, const int lane) {
-  RowItems R;
-  R.meta = 0u;
-  R.src = make_uint4(SRC_NONE, SRC_NONE, SRC_NONE, SRC_NONE);
-  const int it = it0 + lane;
-  if (it < (int)((unsigned)rr.w & 0xFFFFu) && !(((unsigned)rr.w >> 16) & ROW_FIXED)) {
-    R.meta = __ldg(C.item_meta + rr.y + it);
-    R.src = __ldg(isrc + rr.y + it);
-  }
+__device__ __forceinline__ BatchRegs fetch_batch(const ChainDev& C, const GraphDev& G, const int batch, const int lane) {
+  BatchRegs R;
+  R.hdr = __ldg(reinterpret_cast<const int4*>(C.batches + batch));
+  const int n_rows = R.hdr.z & 0xFFFF;
+  const int l = lane < n_rows ? lane : 0;   // idle lanes shadow row 0 (they never store)
+  R.rec = __ldg(reinterpret_cast<const int2*>(C.rows + R.hdr.x + l));
+  R.base = __ldg(G.rowptr + R.rec.x);
   return R;
 }
 
 template <bool HAS_RES, bool HAS_JAC, bool ACC>
-__device__ __forceinline__ void pull_rows(const ChainDev& C, const OutDev& O, const int n_rows, const int parity, const unsigned ring_s,
-                                          const int4* __restrict__ tab_rec, const int64_t* __restrict__ tab_base) {
+__device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C, const GraphDev& G, const OutDev& O, const int parity,
+                                           const unsigned ring_s, double* __restrict__ wbuf, const int lane) {
+  const int n_rows = R.hdr.z & 0xFFFF, n_slots = (int)((unsigned)R.hdr.z >> 16);
+  const bool active = lane < n_rows;
+  const int row = R.rec.x;
+  if ((unsigned)R.hdr.w & BATCH_FIXED) {
+    if (!ACC && active) {
+      const int len = (int)(__ldg(G.rowptr + row + 1) - R.base);
+      const int diag_k = (int)((unsigned)R.rec.y >> 16);
+      if (HAS_JAC) for (int k = 0; k < len; ++k) O.jac[R.base + k] = (k == diag_k) ? 1.0 : 0.0;
+      if (HAS_RES) O.res[row] = 0.0;
+    }
+    return;
+  }
+#ifdef MRH_JIT_CONST_DESC
+  const uint4* __restrict__ desc = (parity ? mrh_desc1 : mrh_desc0) + 2 * R.hdr.y;
+#else
+  const uint4* __restrict__ desc = reinterpret_cast<const uint4*>(parity ? C.desc1 : C.desc0) + 2 * (size_t)R.hdr.y;
+#endif
+  const unsigned rbase = ring_s + ((unsigned)R.rec.y & 0xFFFFu) * 8u;
+  const int n_jac = n_slots - 1;
+  if (HAS_JAC) {
+    int64_t* wbase = reinterpret_cast<int64_t*>(wbuf + 32 * PULL_PITCH);
+    wbase[lane] = R.base;
+    __syncwarp();
+    // store side of the transpose: this lane writes entry (k0 + kk) of rows rsub + 8 j
+    const int rsub = lane >> 2, kk_st = lane & 3;
+    int64_t sb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sb[j] = wbase[rsub + 8 * j];
+    for (int k0 = 0; k0 < n_jac; k0 += PULL_CHUNK) {
+#pragma unroll
+      for (int kk = 0; kk < PULL_CHUNK; ++kk)
+        if (k0 + kk < n_jac) wbuf[lane * PULL_PITCH + kk] = slot_sum(desc, k0 + kk, rbase);
+      __syncwarp();
+      if (k0 + kk_st < n_jac) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = rsub + 8 * j;
+          if (r < n_rows) {
+            double* p = O.jac + sb[j] + (k0 + kk_st);
+            double v = wbuf[r * PULL_PITCH + kk_st];
+            if (ACC) v += *p;
+            *p = v;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (HAS_RES) {
+    const double acc = slot_sum(desc, n_jac, rbase);
+    if (active) {
+      double v = -acc;
+      if (ACC) v += O.res[row];
+      O.res[row] = v;
+    }
+  }
+}
+
+template <bool HAS_RES, bool HAS_JAC, bool ACC>
+__device__ __forceinline__ void pull_step(BatchRegs R, const ChainDev& C, const GraphDev& G, const OutDev& O, const int batch_begin, const int n_batches,
+                                          const int parity, const unsigned ring_s, double* __restrict__ wbuf) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const uint4* __restrict__ isrc = reinterpret_cast<const uint4*>(parity ? C.item_src1 : C.item_src0);
-  int lr = warp;
-  if (lr >= n_rows) return;
-  int4 rr = tab_rec[lr];
-  int64_t base = tab_base[lr];
-  RowItems cur = load_items(C, isrc, rr, 0, lane);
-  for (;;) {
-    const int lr_next = lr + nwarps;
-    const bool has_next = lr_next < n_rows;
-    int4 rr_n = rr;
-    int64_t base_n = base;
-    RowItems nxt = cur;
-    if (has_next) {
-      rr_n = tab_rec[lr_next];
-      base_n = tab_base[lr_next];
-      nxt = load_items(C, isrc, rr_n, 0, lane);
-    }
-    // ---- current row
-    const int row = rr.x;
-    const unsigned n_items = (unsigned)rr.w & 0xFFFFu;
-    if (((unsigned)rr.w >> 16) & ROW_FIXED) {
-      if (!ACC) {
-        const unsigned diag_k = (unsigned)rr.z >> 16;
-        const int len = (int)n_items;  // fixed rows carry their CSR length here
-        if (HAS_JAC) for (int k = lane; k < len; k += 32) O.jac[base + k] = ((unsigned)k == diag_k) ? 1.0 : 0.0;
-        if (HAS_RES && lane == 0) O.res[row] = 0.0;
-      }
-    } else {
-      const unsigned rbase = ring_s + ((unsigned)rr.z & 0xFFFFu) * 8u;
-      for (unsigned it0 = 0;;) {
-        double acc = 0.0;
-        if (cur.src.x != SRC_NONE) acc = lds_f64(rbase + cur.src.x);
-        if (cur.src.y != SRC_NONE) acc += lds_f64(rbase + cur.src.y);
-        if (cur.src.z != SRC_NONE) acc += lds_f64(rbase + cur.src.z);
-        if (cur.src.w != SRC_NONE) acc += lds_f64(rbase + cur.src.w);
-        double v = __shfl_down_sync(0xffffffffu, acc, 1);
-        if (cur.meta & ITEM_ADD1) acc += v;
-        if (C.need_add2) {
-          v = __shfl_down_sync(0xffffffffu, acc, 2);
-          if (cur.meta & ITEM_ADD2) acc += v;
-        }
-        const bool is_res = (cur.meta & ITEM_RES) != 0u;
-        if ((cur.meta & ITEM_HEAD) && (is_res ? HAS_RES : HAS_JAC)) {
-          double* p = is_res ? (O.res + row) : (O.jac + base + (cur.meta & 0xFFFFu));
-          double val = is_res ? -acc : acc;
-          if (ACC) val += *p;
-          *p = val;
-        }
-        it0 += 32u;
-        if (it0 >= n_items) break;
-        cur = load_items(C, isrc, rr, (int)it0, lane);
-      }
-    }
-    if (!has_next) break;
-    lr = lr_next; rr = rr_n; base = base_n; cur = nxt;
-  }
-}
-
-__device__ __forceinline__ void pull_dispatch(const ChainDev& C, const OutDev& O, const int n_rows, const int parity, const unsigned ring_s,
-                                              const int4* tab_rec, const int64_t* tab_base) {
-  const int mode = (O.res ? 1 : 0) | (O.jac ? 2 : 0) | (O.accumulate ? 4 : 0);
-  switch (mode) {
-    case 1: pull_rows<true, false, false>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
-    case 2: pull_rows<false, true, false>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
-    case 3: pull_rows<true, true, false>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
-    case 5: pull_rows<true, false, true>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
-    case 6: pull_rows<false, true, true>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
-    case 7: pull_rows<true, true, true>(C, O, n_rows, parity, ring_s, tab_rec, tab_base); break;
-    default: break;
-  }
-}
-
-// Row record of a step -> shared-memory row table entry.  Fixed rows get their CSR length in place of n_items.
-__device__ __forceinline__ void fetch_row(const ChainDev& C, const GraphDev& G, const int idx, int4& rec, int64_t& base) {
-  rec = __ldg(reinterpret_cast<const int4*>(C.rows + idx));
-  base = __ldg(G.rowptr + rec.x);
-  if (((unsigned)rec.w >> 16) & ROW_FIXED) {
-    const int len = (int)(__ldg(G.rowptr + rec.x + 1) - base);
-    rec.w = (int)(((unsigned)rec.w & 0xFFFF0000u) | (unsigned)len);
+  for (int b = warp; b < n_batches; b += nwarps) {
+    const int bn = b + nwarps;
+    BatchRegs N = R;
+    if (bn < n_batches) N = fetch_batch(C, G, batch_begin + bn, lane);   // next batch of this warp: in flight while this one is summed
+    pull_batch<HAS_RES, HAS_JAC, ACC>(R, C, G, O, parity, ring_s, wbuf, lane);
+    R = N;
   }
 }
 
@@ -570,35 +615,41 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   const int s0 = __ldg(C.chain_step_ptr + blockIdx.x), s1 = __ldg(C.chain_step_ptr + blockIdx.x + 1);
   const int cap = C.cap;
   const int slot_doubles = cap * S::STAGE;
-  const int row_tab = C.row_tab;
-  int64_t* tab_base = reinterpret_cast<int64_t*>(ring + 2 * slot_doubles);
-  int4* tab_rec = reinterpret_cast<int4*>(tab_base + row_tab);
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-  const int tid = threadIdx.x, nth = blockDim.x;
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  double* wbuf = ring + 2 * slot_doubles + warp * PULL_WARP_DOUBLES;
+  const int mode = (P.out.res ? 1 : 0) | (P.out.jac ? 2 : 0) | (P.out.accumulate ? 4 : 0);
+  // software pipeline over the steps: element inputs of step s+1 are requested while step s is summed
+  int4 sr = __ldg(reinterpret_cast<const int4*>(C.steps + s0));
+  ElemPre<DIM> E;
+  if (tid < sr.y) { elem_stage1<DIM>(P, __ldg(C.step_elems + sr.x + tid), E); elem_stage2<DIM>(P, E); }
   for (int s = s0; s < s1; ++s) {
-    const int4 sr = __ldg(reinterpret_cast<const int4*>(C.steps + s));
-    const int elem_begin = sr.x, n_elem = sr.y, row_begin = sr.z, n_rows = sr.w;
+    const int elem_begin = sr.x, n_elem = sr.y, batch_begin = sr.z, n_batches = sr.w;
+    (void)elem_begin;
     const int parity = (s - s0) & 1;
     double* slot = ring + parity * slot_doubles;
-    // row-table prefetch (first pass): issued before the element work so its latency is hidden
-    const int pass0 = n_rows < row_tab ? n_rows : row_tab;
-    int4 rec0 = make_int4(0, 0, 0, 0);
-    int64_t base0 = 0;
-    if (tid < pass0) fetch_row(C, P.graph, row_begin + tid, rec0, base0);
-    for (int le = tid; le < n_elem; le += nth)
-      thermal_element<DIM>(P, __ldg(C.step_elems + elem_begin + le), cap, slot + le);
-    if (tid < pass0) { tab_rec[tid] = rec0; tab_base[tid] = base0; }
-    for (int i = tid + nth; i < pass0; i += nth) { int4 r; int64_t b; fetch_row(C, P.graph, row_begin + i, r, b); tab_rec[i] = r; tab_base[i] = b; }
+    int4 sr_next = sr;
+    if (s + 1 < s1) sr_next = __ldg(reinterpret_cast<const int4*>(C.steps + s + 1));
+    // this warp's first batch: requested before the element work so that the loads are hidden behind it
+    BatchRegs R;
+    R.hdr = make_int4(0, 0, 0, 0); R.rec = make_int2(0, 0); R.base = 0;
+    if (warp < n_batches) R = fetch_batch(C, P.graph, batch_begin + warp, lane);
+    if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);
+    const bool more = (s + 1 < s1) && (tid < sr_next.y);
+    if (more) elem_stage1<DIM>(P, __ldg(C.step_elems + sr_next.x + tid), E);
     __syncthreads();
-    pull_dispatch(C, P.out, pass0, parity, ring_s, tab_rec, tab_base);
-    for (int done = pass0; done < n_rows; done += row_tab) {  // steps with more rows than the table holds
-      __syncthreads();
-      const int n = (n_rows - done) < row_tab ? (n_rows - done) : row_tab;
-      for (int i = tid; i < n; i += nth) { int4 r; int64_t b; fetch_row(C, P.graph, row_begin + done + i, r, b); tab_rec[i] = r; tab_base[i] = b; }
-      __syncthreads();
-      pull_dispatch(C, P.out, n, parity, ring_s, tab_rec, tab_base);
+    switch (mode) {
+      case 1: pull_step<true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
+      case 2: pull_step<false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
+      case 3: pull_step<true, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
+      case 5: pull_step<true, false, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
+      case 6: pull_step<false, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
+      case 7: pull_step<true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
+      default: break;
     }
-    __syncthreads();  // the next step overwrites the slot this pull read as "previous", and the row table
+    if (more) elem_stage2<DIM>(P, E);
+    sr = sr_next;
+    __syncthreads();  // the next step overwrites the slot this pull read as "previous"
   }
 }
 
