@@ -3,6 +3,7 @@
 // no kernel matches the described block the call fails with an error code.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -226,6 +227,7 @@ std::string hexd(double v) {
 void emit_values(std::string& o, const double* v, size_t n) {
   for (size_t i = 0; i < n; ++i) { o += hexd(v[i]); o += (i + 1 < n) ? "," : ""; }
 }
+std::string pull_codegen(const ChainPlan& cp, int max_patterns);
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp) {
   typedef Q1Shape<DIM> S;
@@ -305,7 +307,14 @@ __device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
   arr(("Mtab[" + nt + "]").c_str(), &T.Mtab[0], S::NT);
   arr(("Ltab[" + nv + "]").c_str(), &T.Ltab[0], S::NV);
   arr(("qax[3][" + nq + "]").c_str(), &qax[0][0], 3 * S::NQ);
-  o += "}  // namespace jit_tab\n";
+  o += "}  // namespace jit_tab\nnamespace jit_ctab {\n";
+  auto carr = [&](const char* decl, const double* v, size_t n) { o += std::string("__constant__ double ") + decl + " = {"; emit_values(o, v, n); o += "};\n"; };
+  carr(("phi[" + nq + "][" + nv + "]").c_str(), &T.phi[0][0], S::NQ * S::NV);
+  carr(("qw[" + nq + "]").c_str(), &T.qw[0], S::NQ);
+  carr(("Stab[" + ng + "][" + nt + "]").c_str(), &T.Stab[0][0], S::NG * S::NT);
+  carr(("Mtab[" + nt + "]").c_str(), &T.Mtab[0], S::NT);
+  carr(("Ltab[" + nv + "]").c_str(), &T.Ltab[0], S::NV);
+  o += "}  // namespace jit_ctab\n";
   // gather patterns of the plan as constant data (warp-uniform reads in the pull phase hit the constant cache)
   const size_t desc_words = cp.desc[0].size();
   if (desc_words > 0 && desc_words * 4 * 2 <= 40 * 1024) {
@@ -320,8 +329,64 @@ __device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
       o += "};\n";
     }
   }
+  o += pull_codegen(cp, 3);
   o += "}  // namespace mrhyde_b200\n";
   o += kVolumeKernelSrc;
+  return o;
+}
+
+// ---- straight-line pull code for the plan's most frequent gather patterns (jit only) ------------------------------
+// For a pattern the slot descriptors are plan constants, so the generated code has no descriptor loads, no "unused"
+// tests and no address arithmetic: every staged value is one LDS with an immediate offset from the row's ring anchor.
+// Sums keep the ascending element order of the generic loop (slot_sum), so both paths give identical bits.
+std::string pull_codegen(const ChainPlan& cp, int max_patterns) {
+  std::map<int32_t, int64_t> freq;   // desc_begin -> rows
+  for (const BatchRec& B : cp.batches) if (!(B.flags & BATCH_FIXED)) freq[B.desc_begin] += B.n_rows;
+  std::vector<std::pair<int64_t, int32_t>> order;
+  for (auto& kv : freq) order.push_back({kv.second, kv.first});
+  std::sort(order.rbegin(), order.rend());
+  std::string o;
+  o += "#define MRH_JIT_PULL 1\n";
+  o += "__device__ __forceinline__ double mrh_lds_at(unsigned a) { double v; asm volatile(\"ld.shared.f64 %0, [%1];\" : \"=d\"(v) : \"r\"(a)); return v; }\n";
+  o += "#define MRH_L(off) mrh_lds_at(rbase + (off##u))\n";
+  o += "#define MRH_ST(K0, LIM) { __syncwarp(); if ((LIM) >= 4 || kk_st < (LIM)) { _Pragma(\"unroll\") for (int j = 0; j < 4; ++j) if (rv[j]) { double* p = pj[j] + (K0); "
+       "double v = wbuf[(rsub + 8 * j) * 5 + kk_st]; if (ACC) v += *p; *p = v; } } __syncwarp(); }\n";
+  o += "template <bool HAS_RES, bool HAS_JAC, bool ACC>\n__device__ __forceinline__ bool mrh_pull_special(const int desc_begin, const int parity, const unsigned rbase, "
+       "double* __restrict__ wbuf, const int lane, const int rsub, const int kk_st, double* const (&pj)[4], const bool (&rv)[4], double* pres, const bool active) {\n";
+  o += "  switch (desc_begin * 2 + parity) {\n";
+  int emitted = 0;
+  for (auto& pr : order) {
+    if (emitted >= max_patterns) break;
+    const int32_t db = pr.second;
+    int n_slots = 0;
+    for (const PatternRec& PR : cp.patterns) if (PR.desc_begin == db) n_slots = PR.n_slots;
+    if (n_slots < 2 || n_slots > 96) continue;
+    const int n_jac = n_slots - 1;
+    for (int par = 0; par < 2; ++par) {
+      auto sum_expr = [&](int k) {
+        std::string e;
+        int cnt = 0;
+        for (int z = 0; z < SLOT_SRCS; ++z) {
+          const uint32_t src = cp.desc[par][((size_t)db + (size_t)k) * SLOT_SRCS + (size_t)z];
+          if (src == SRC_NONE) continue;
+          const std::string t = "MRH_L(" + std::to_string(src) + ")";
+          e = cnt == 0 ? t : "(" + e + " + " + t + ")";
+          ++cnt;
+        }
+        return cnt ? e : std::string("0.0");
+      };
+      o += "    case " + std::to_string(db * 2 + par) + ": {\n      if (HAS_JAC) {\n";
+      for (int k0 = 0; k0 < n_jac; k0 += 4) {
+        for (int kk = 0; kk < 4 && k0 + kk < n_jac; ++kk)
+          o += "        wbuf[lane * 5 + " + std::to_string(kk) + "] = " + sum_expr(k0 + kk) + ";\n";
+        o += "        MRH_ST(" + std::to_string(k0) + ", " + std::to_string(n_jac - k0) + ")\n";
+      }
+      o += "      }\n      if (HAS_RES) { const double acc = " + sum_expr(n_jac) + "; if (active) { double v = -acc; if (ACC) v += *pres; *pres = v; } }\n";
+      o += "      return true;\n    }\n";
+    }
+    ++emitted;
+  }
+  o += "    default: return false;\n  }\n}\n";
   return o;
 }
 

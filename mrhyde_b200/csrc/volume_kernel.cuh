@@ -31,11 +31,13 @@ namespace mrhyde_b200 {
 
 #ifdef MRH_JIT
 #define MRH_TRANSIENT(td) (MRH_JIT_TRANSIENT != 0)
-#define MRH_TAB(f) jit_tab::f
+#define MRH_TAB(f) jit_tab::f      /* constexpr copy: folds into immediates / index arithmetic */
+#define MRH_CTAB(f) jit_ctab::f    /* __constant__ copy: the value is a constant-bank operand of the FMA */
 #define MRH_UNROLL_Q _Pragma("unroll")
 #else
 #define MRH_TRANSIENT(td) ((td).transient != 0)
 #define MRH_TAB(f) P.tab.f
+#define MRH_CTAB(f) P.tab.f
 #define MRH_UNROLL_Q _Pragma("unroll 1")
 #endif
 
@@ -274,11 +276,11 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
       const int t = tri<NV>(i, j);
       double k = 0.0;
 #pragma unroll
-      for (int g = 0; g < NGU; ++g) k += G[g] * MRH_TAB(Stab)[g][t];
+      for (int g = 0; g < NGU; ++g) k += G[g] * MRH_CTAB(Stab)[g][t];
       r[i] += k * u[j];
       if (j != i) r[j] += k * u[i];
       if (MRH_TRANSIENT(td)) {
-        const double mm = md * MRH_TAB(Mtab)[t];
+        const double mm = md * MRH_CTAB(Mtab)[t];
         r[i] += mm * ut[j];
         if (j != i) r[j] += mm * ut[i];
         k = td.alpha_u * k + td.alpha_t * mm;
@@ -289,7 +291,7 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
   if (MRH_SOURCE_CONST) {
     const double f = thermal_fn<DIM, FN_SOURCE>(P, xzero, td.time) * adet;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) r[i] -= f * MRH_TAB(Ltab)[i];
+    for (int i = 0; i < NV; ++i) r[i] -= f * MRH_CTAB(Ltab)[i];
   }
 #ifdef MRH_JIT
   else if constexpr (BOX) {
@@ -305,9 +307,9 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
     mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const double fw = f[q] * MRH_TAB(qw)[q] * adet;
+      const double fw = f[q] * MRH_CTAB(qw)[q] * adet;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) r[i] -= fw * MRH_TAB(phi)[q][i];
+      for (int i = 0; i < NV; ++i) r[i] -= fw * MRH_CTAB(phi)[q][i];
     }
   }
 #endif
@@ -325,9 +327,9 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
           x[d] = s;
         }
       }
-      const double fw = thermal_fn<DIM, FN_SOURCE>(P, x, td.time) * MRH_TAB(qw)[q] * adet;
+      const double fw = thermal_fn<DIM, FN_SOURCE>(P, x, td.time) * MRH_CTAB(qw)[q] * adet;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) r[i] -= fw * MRH_TAB(phi)[q][i];
+      for (int i = 0; i < NV; ++i) r[i] -= fw * MRH_CTAB(phi)[q][i];
     }
   }
 }
@@ -416,7 +418,7 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
         x[d] = xs;
       }
       const double det = det_inverse<DIM>(J, Ji);
-      const double wd = fabs(det) * MRH_TAB(qw)[q];
+      const double wd = fabs(det) * MRH_CTAB(qw)[q];
       double g[NV][DIM];
 #pragma unroll
       for (int i = 0; i < NV; ++i)
@@ -442,24 +444,24 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
         const double rc = thermal_fn<DIM, FN_DENSITY>(P, x, td.time) * thermal_fn<DIM, FN_SPECIFIC_HEAT>(P, x, td.time);
         double Tt = 0.0;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) Tt += ut[j] * MRH_TAB(phi)[q][j];
+        for (int j = 0; j < NV; ++j) Tt += ut[j] * MRH_CTAB(phi)[q][j];
         lin += rc * Tt * wd;
         mw = td.alpha_t * rc * wd;
       }
       const double kw = td.alpha_u * kap * wd;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        double s = lin * MRH_TAB(phi)[q][i];
+        double s = lin * MRH_CTAB(phi)[q][i];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) s += gT[d] * g[i][d];
         r[i] += s;
         double gi[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) gi[d] = kw * g[i][d];
-        const double mi = mw * MRH_TAB(phi)[q][i];
+        const double mi = mw * MRH_CTAB(phi)[q][i];
 #pragma unroll
         for (int j = i; j < NV; ++j) {
-          double k = mi * MRH_TAB(phi)[q][j];
+          double k = mi * MRH_CTAB(phi)[q][j];
 #pragma unroll
           for (int d = 0; d < DIM; ++d) k += gi[d] * g[j][d];
           K[tri<NV>(i, j)] += k;
@@ -492,6 +494,9 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 constexpr int PULL_CHUNK = 4;                       // CSR entries per transpose round
 constexpr int PULL_PITCH = PULL_CHUNK + 1;          // doubles per lane in the transpose buffer (padding: no bank conflicts)
 constexpr int PULL_WARP_DOUBLES = 32 * PULL_PITCH + 32;  // + 32 row offsets
+#ifdef MRH_JIT_PULL
+static_assert(PULL_CHUNK == 4 && PULL_PITCH == 5, "generated pull code assumes 4-entry chunks with pitch 5");
+#endif
 
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
@@ -555,15 +560,23 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
 #endif
   const unsigned rbase = ring_s + ((unsigned)R.rec.y & 0xFFFFu) * 8u;
   const int n_jac = n_slots - 1;
+  // store side of the transpose: this lane writes entry (k0 + kk_st) of rows rsub + 8 j
+  const int rsub = lane >> 2, kk_st = lane & 3;
+  double* pj[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool rv[4] = {false, false, false, false};
   if (HAS_JAC) {
     int64_t* wbase = reinterpret_cast<int64_t*>(wbuf + 32 * PULL_PITCH);
     wbase[lane] = R.base;
     __syncwarp();
-    // store side of the transpose: this lane writes entry (k0 + kk) of rows rsub + 8 j
-    const int rsub = lane >> 2, kk_st = lane & 3;
-    int64_t sb[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sb[j] = wbase[rsub + 8 * j];
+    for (int j = 0; j < 4; ++j) { pj[j] = O.jac + wbase[rsub + 8 * j] + kk_st; rv[j] = (rsub + 8 * j) < n_rows; }
+  }
+  double* pres = HAS_RES ? (O.res + row) : nullptr;
+#ifdef MRH_JIT_PULL
+  // straight-line code generated for the plan's most frequent patterns: ring offsets are immediates of the loads
+  if (mrh_pull_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, rsub, kk_st, pj, rv, pres, active)) return;
+#endif
+  if (HAS_JAC) {
     for (int k0 = 0; k0 < n_jac; k0 += PULL_CHUNK) {
 #pragma unroll
       for (int kk = 0; kk < PULL_CHUNK; ++kk)
@@ -571,15 +584,13 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
       __syncwarp();
       if (k0 + kk_st < n_jac) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = rsub + 8 * j;
-          if (r < n_rows) {
-            double* p = O.jac + sb[j] + (k0 + kk_st);
-            double v = wbuf[r * PULL_PITCH + kk_st];
+        for (int j = 0; j < 4; ++j)
+          if (rv[j]) {
+            double* p = pj[j] + k0;
+            double v = wbuf[(rsub + 8 * j) * PULL_PITCH + kk_st];
             if (ACC) v += *p;
             *p = v;
           }
-        }
       }
       __syncwarp();
     }
@@ -588,8 +599,8 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
     const double acc = slot_sum(desc, n_jac, rbase);
     if (active) {
       double v = -acc;
-      if (ACC) v += O.res[row];
-      O.res[row] = v;
+      if (ACC) v += *pres;
+      *pres = v;
     }
   }
 }
