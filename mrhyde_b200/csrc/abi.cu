@@ -106,9 +106,9 @@ struct mrhyde_b200_plan {
   // device copies
   size_t dev_bytes = 0;
   DevBuf<double> d_vx, d_vy, d_vz;
-  DevBuf<int32_t> d_conn, d_lids, d_colind, d_chain_step_ptr, d_step_elems, d_orphans;
+  DevBuf<int32_t> d_conn, d_lids, d_colind, d_chain_step_ptr, d_step_elems, d_step_conn, d_step_lids, d_orphans;
   DevBuf<int64_t> d_rowptr, d_fixed_diag;
-  DevBuf<uint8_t> d_fixed, d_eclass;
+  DevBuf<uint8_t> d_fixed, d_eclass, d_step_eclass;
   DevBuf<StepRec> d_steps;
   DevBuf<BatchRec> d_batches;
   DevBuf<RowRec> d_rows;
@@ -247,28 +247,34 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   // terms, exact for |x| < 1e5) and the fdlibm k_sin / k_cos minimax polynomials on [-pi/4, pi/4] (< 1 ulp); larger or
   // non-finite arguments take the library routine
   o += R"MRH(
+// coefficients live in the constant bank so that each one is a direct operand of its FMA
+__constant__ double mrh_sck[16] = {0x1.45f306dc9c883p-1, 0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54, -0x1.f1976b7ed8fbcp-110,
+  -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+  -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+  1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+  8.33333333332248946124e-03, -1.66666666666666324348e-01};
 __device__ __forceinline__ double mrh_sincos(double x, int shift) {
   if (!(fabs(x) < 1.0e5)) return shift ? cos(x) : sin(x);
-  const double q = rint(x * 0x1.45f306dc9c883p-1);
-  double r = fma(-q, 0x1.921fb54442d18p+0, x);
-  r = fma(-q, 0x1.1a62633145c07p-54, r);
-  r = fma(-q, -0x1.f1976b7ed8fbcp-110, r);
+  const double q = rint(x * mrh_sck[0]);
+  double r = fma(-q, mrh_sck[1], x);
+  r = fma(-q, mrh_sck[2], r);
+  r = fma(-q, mrh_sck[3], r);
   const int n = (int)q + shift;
   const double z = r * r;
   double v;
   if (n & 1) {
-    double p = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    p = fma(z, p, -2.75573143513906633035e-07);
-    p = fma(z, p, 2.48015872894767294178e-05);
-    p = fma(z, p, -1.38888888888741095749e-03);
-    p = fma(z, p, 4.16666666666666019037e-02);
+    double p = fma(z, mrh_sck[4], mrh_sck[5]);
+    p = fma(z, p, mrh_sck[6]);
+    p = fma(z, p, mrh_sck[7]);
+    p = fma(z, p, mrh_sck[8]);
+    p = fma(z, p, mrh_sck[9]);
     v = 1.0 - (0.5 * z - z * (z * p));
   } else {
-    double p = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    p = fma(z, p, 2.75573137070700676789e-06);
-    p = fma(z, p, -1.98412698298579493134e-04);
-    p = fma(z, p, 8.33333333332248946124e-03);
-    p = fma(z, p, -1.66666666666666324348e-01);
+    double p = fma(z, mrh_sck[10], mrh_sck[11]);
+    p = fma(z, p, mrh_sck[12]);
+    p = fma(z, p, mrh_sck[13]);
+    p = fma(z, p, mrh_sck[14]);
+    p = fma(z, p, mrh_sck[15]);
     v = fma(z * r, p, r);
   }
   return (n & 2) ? -v : v;
@@ -376,9 +382,11 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns) {
         return cnt ? e : std::string("0.0");
       };
       o += "    case " + std::to_string(db * 2 + par) + ": {\n      if (HAS_JAC) {\n";
+      // all sums first (the loads are independent and can be in flight together), then the transpose rounds
+      for (int k = 0; k < n_jac; ++k) o += "        const double a" + std::to_string(k) + " = " + sum_expr(k) + ";\n";
       for (int k0 = 0; k0 < n_jac; k0 += 4) {
         for (int kk = 0; kk < 4 && k0 + kk < n_jac; ++kk)
-          o += "        wbuf[lane * 5 + " + std::to_string(kk) + "] = " + sum_expr(k0 + kk) + ";\n";
+          o += "        wbuf[lane * 5 + " + std::to_string(kk) + "] = a" + std::to_string(k0 + kk) + ";\n";
         o += "        MRH_ST(" + std::to_string(k0) + ", " + std::to_string(n_jac - k0) + ")\n";
       }
       o += "      }\n      if (HAS_RES) { const double acc = " + sum_expr(n_jac) + "; if (active) { double v = -acc; if (ACC) v += *pres; *pres = v; } }\n";
@@ -816,6 +824,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   P->d_rowptr.upload(M.rowptr, tot); P->d_colind.upload(M.colind, tot); P->d_fixed.upload(M.fixed, tot); P->d_eclass.upload(M.eclass, tot);
   P->d_chain_step_ptr.upload(CP.chain_step_ptr, tot); P->d_steps.upload(CP.steps, tot); P->d_step_elems.upload(CP.step_elems, tot);
   P->d_batches.upload(CP.batches, tot); P->d_rows.upload(CP.rows, tot);
+  P->d_step_conn.upload(CP.step_conn, tot); P->d_step_lids.upload(CP.step_lids, tot); P->d_step_eclass.upload(CP.step_eclass, tot);
   P->d_desc0.upload(CP.desc[0], tot); P->d_desc1.upload(CP.desc[1], tot);
   P->d_orphans.upload(CP.orphan_rows, tot);
   {
@@ -832,6 +841,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   ChainDev D;
   D.chain_step_ptr = P->d_chain_step_ptr.p; D.steps = P->d_steps.p; D.step_elems = P->d_step_elems.p;
   D.batches = P->d_batches.p; D.rows = P->d_rows.p;
+  D.step_conn = P->d_step_conn.p; D.step_lids = P->d_step_lids.p; D.step_eclass = P->d_step_eclass.p;
   D.desc0 = reinterpret_cast<const SrcQuad*>(P->d_desc0.p); D.desc1 = reinterpret_cast<const SrcQuad*>(P->d_desc1.p);
   D.cap = CP.cap;
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};

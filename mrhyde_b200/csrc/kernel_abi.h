@@ -25,17 +25,18 @@ struct StepRec {      // one level of one chain
 };
 // Rows of a step are grouped into BATCHES of up to 32 rows that share one gather pattern; a warp takes a batch with one
 // row per lane, so every lane walks the same descriptor list and differs only in its ring anchor and output offset.
-struct BatchRec {     // 16 bytes, read as one int4
-  int32_t row_begin;  // into rows
+struct BatchRec {     // 16 bytes, read as one int4; batch b owns rows[32 b .. 32 b + n_rows)
+  int32_t row_begin;  // = 32 * (index of this batch)
   int32_t desc_begin; // first slot descriptor of the pattern
   uint16_t n_rows;    // 1..32
   uint16_t n_slots;   // CSR entries of a row + 1: the last slot is the residual entry
   uint32_t flags;     // bit 0: strong-Dirichlet rows (isFixedDOF): no pattern, rows may differ in length
 };
-struct RowRec {       // 8 bytes
+struct RowRec {       // 16 bytes, read as one int4; stored 32 per batch so that its address needs no batch header
   int32_t row;        // local row id (LID)
   uint16_t anchor;    // ring-slot element index the pattern offsets are relative to
   uint16_t aux;       // fixed rows: position of the diagonal entry inside the CSR row (0xFFFF if absent)
+  int64_t base;       // row_map[row]: offset of the row in the CSR value array (copied from the graph at plan time)
 };
 struct PatternRec {   // host-side bookkeeping of the de-duplicated patterns
   int32_t desc_begin, n_slots;
@@ -51,7 +52,10 @@ struct SrcQuad { uint32_t x, y, z, w; };  // half a slot descriptor (read as uin
 struct ChainDev {
   const int32_t* chain_step_ptr;   // [n_chains+1]
   const StepRec* steps;
-  const int32_t* step_elems;
+  const int32_t* step_elems;       // global element id of every step element (diagnostics)
+  const int32_t* step_conn;        // [n_elem_with_halo][nverts]  connectivity in step order: the kernel reads element inputs
+  const int32_t* step_lids;        // [n_elem_with_halo][ndof]    with one coalesced load level instead of id -> conn -> data
+  const uint8_t* step_eclass;      // [n_elem_with_halo]
   const BatchRec* batches;
   const RowRec* rows;
   const SrcQuad* desc0;            // parity 0 / 1 descriptor tables, 2 SrcQuad per slot

@@ -404,7 +404,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
           if (len > 0xFFFE) throw std::runtime_error("plan: CSR row longer than 65534 entries");
           const int32_t* cols = &m.colind[(size_t)rs];
           StepRow SR;
-          SR.rec.row = r; SR.rec.anchor = 0; SR.rec.aux = 0xFFFF;
+          SR.rec.row = r; SR.rec.anchor = 0; SR.rec.aux = 0xFFFF; SR.rec.base = 0;
           if (m.fixed[(size_t)r]) {  // strong-Dirichlet row: nothing is gathered (scatter.hpp:208, 253)
             const int32_t* dg = std::lower_bound(cols, cols + len, r);
             SR.rec.aux = (dg != cols + len && *dg == r) ? (uint16_t)(dg - cols) : (uint16_t)0xFFFF;
@@ -516,6 +516,31 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       W = ChainWork();
     }
     out.n_elem_with_halo = (int64_t)out.step_elems.size();
+    // rows: 32 per batch (padded), with the CSR offset of the row copied in, so the device needs one load level
+    {
+      std::vector<RowRec> padded((size_t)out.batches.size() * 32);
+      RowRec zero; zero.row = 0; zero.anchor = 0; zero.aux = 0; zero.base = 0;
+      for (size_t b = 0; b < out.batches.size(); ++b) {
+        BatchRec& B = out.batches[b];
+        for (int l = 0; l < 32; ++l) {
+          RowRec R = zero;
+          if (l < (int)B.n_rows) { R = out.rows[(size_t)B.row_begin + (size_t)l]; R.base = m.rowptr[(size_t)R.row]; }
+          padded[b * 32 + (size_t)l] = R;
+        }
+        B.row_begin = (int32_t)(b * 32);
+      }
+      out.rows.swap(padded);
+    }
+    // element inputs in step order
+    out.step_conn.resize((size_t)out.n_elem_with_halo * nv);
+    out.step_lids.resize((size_t)out.n_elem_with_halo * nd);
+    out.step_eclass.resize((size_t)out.n_elem_with_halo);
+    for (int64_t k = 0; k < out.n_elem_with_halo; ++k) {
+      const int32_t e = out.step_elems[(size_t)k];
+      std::memcpy(&out.step_conn[(size_t)k * nv], &m.conn[(size_t)e * nv], sizeof(int32_t) * (size_t)nv);
+      std::memcpy(&out.step_lids[(size_t)k * nd], &m.lids[(size_t)e * nd], sizeof(int32_t) * (size_t)nd);
+      out.step_eclass[(size_t)k] = m.eclass.empty() ? 0 : m.eclass[(size_t)e];
+    }
     break;
   }
 }
@@ -535,8 +560,9 @@ void host_apply_chain_plan(const MeshGraph& m, const ChainPlan& cp, const double
       for (int32_t b = 0; b < ST.n_batches; ++b) {
         const BatchRec& B = cp.batches[(size_t)(ST.batch_begin + b)];
         for (int32_t lane = 0; lane < (int32_t)B.n_rows; ++lane) {
-          const RowRec& R = cp.rows[(size_t)(B.row_begin + lane)];
-          const int64_t base = m.rowptr[(size_t)R.row];
+          const RowRec& R = cp.rows[(size_t)(ST.batch_begin + b) * 32 + (size_t)lane];
+          const int64_t base = R.base;
+          if (base != m.rowptr[(size_t)R.row]) throw std::runtime_error("plan: stale CSR offset in a row record (internal error)");
           const int32_t len = (int32_t)(m.rowptr[(size_t)R.row + 1] - base);
           if (B.flags & BATCH_FIXED) {
             if (!accumulate) {

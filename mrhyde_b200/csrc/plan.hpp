@@ -48,6 +48,8 @@ struct ChainPlan {
   std::vector<int32_t> chain_step_ptr;   // [n_chains+1]
   std::vector<StepRec> steps;
   std::vector<int32_t> step_elems;
+  std::vector<int32_t> step_conn, step_lids;   // element inputs in step order
+  std::vector<uint8_t> step_eclass;
   std::vector<BatchRec> batches;
   std::vector<RowRec> rows;
   std::vector<PatternRec> patterns;

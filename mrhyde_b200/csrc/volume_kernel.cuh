@@ -338,18 +338,19 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
 // Phase 1: one element -> staged upper triangle of dF/du and residual F
 //   st points at this element's column of the ring slot; entry t lives at st[t * cap]
 // ---------------------------------------------------------------------------------------------------------
+// k: position of the element in the plan's step order
 template <int DIM>
-__device__ __forceinline__ void elem_stage1(const ThermalParams<DIM>& P, const int e, ElemPre<DIM>& E) {
+__device__ __forceinline__ void elem_stage1(const ThermalParams<DIM>& P, const int k, ElemPre<DIM>& E) {
   constexpr int NV = 1 << DIM;
-  const int4* c4 = reinterpret_cast<const int4*>(P.conn + (size_t)e * NV);
-  const int4* l4 = reinterpret_cast<const int4*>(P.lids + (size_t)e * NV);
+  const int4* c4 = reinterpret_cast<const int4*>(P.chains.step_conn + (size_t)k * NV);
+  const int4* l4 = reinterpret_cast<const int4*>(P.chains.step_lids + (size_t)k * NV);
 #pragma unroll
   for (int k = 0; k < NV / 4; ++k) {
     const int4 a = __ldg(c4 + k), b = __ldg(l4 + k);
     E.cn[4 * k] = a.x; E.cn[4 * k + 1] = a.y; E.cn[4 * k + 2] = a.z; E.cn[4 * k + 3] = a.w;
     E.ld[4 * k] = b.x; E.ld[4 * k + 1] = b.y; E.ld[4 * k + 2] = b.z; E.ld[4 * k + 3] = b.w;
   }
-  E.ecls = P.eclass[e];
+  E.ecls = P.chains.step_eclass[k];
 }
 
 template <int DIM>
@@ -528,13 +529,13 @@ struct BatchRegs {  // what a lane holds of its batch: header (uniform), its row
   int64_t base;
 };
 
+// two independent loads (the row table is addressed by batch index, not through the header)
 __device__ __forceinline__ BatchRegs fetch_batch(const ChainDev& C, const GraphDev& G, const int batch, const int lane) {
   BatchRegs R;
   R.hdr = __ldg(reinterpret_cast<const int4*>(C.batches + batch));
-  const int n_rows = R.hdr.z & 0xFFFF;
-  const int l = lane < n_rows ? lane : 0;   // idle lanes shadow row 0 (they never store)
-  R.rec = __ldg(reinterpret_cast<const int2*>(C.rows + R.hdr.x + l));
-  R.base = __ldg(G.rowptr + R.rec.x);
+  const int4 rw = __ldg(reinterpret_cast<const int4*>(C.rows + (size_t)batch * 32 + lane));   // idle lanes read zero padding (they never store)
+  R.rec = make_int2(rw.x, rw.y);
+  R.base = (int64_t)(((uint64_t)(uint32_t)rw.w << 32) | (uint64_t)(uint32_t)rw.z);
   return R;
 }
 
@@ -630,24 +631,30 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
   double* wbuf = ring + 2 * slot_doubles + warp * PULL_WARP_DOUBLES;
   const int mode = (P.out.res ? 1 : 0) | (P.out.jac ? 2 : 0) | (P.out.accumulate ? 4 : 0);
-  // software pipeline over the steps: element inputs of step s+1 are requested while step s is summed
+  // software pipeline over the steps.  While step s is computed and summed the inputs of step s+1 are in flight:
+  //   top of step s   : step record of s+2, connectivity / LIDs of s+1 (addresses depend on the step record only)
+  //   after compute s : state and vertices of s+1 (need the LIDs / connectivity requested above)
+  // so no load is issued right behind the load that produces its address.
   int4 sr = __ldg(reinterpret_cast<const int4*>(C.steps + s0));
+  int4 sr_next = sr;
+  if (s0 + 1 < s1) sr_next = __ldg(reinterpret_cast<const int4*>(C.steps + s0 + 1));
   ElemPre<DIM> E;
-  if (tid < sr.y) { elem_stage1<DIM>(P, __ldg(C.step_elems + sr.x + tid), E); elem_stage2<DIM>(P, E); }
+  if (tid < sr.y) { elem_stage1<DIM>(P, sr.x + tid, E); elem_stage2<DIM>(P, E); }
   for (int s = s0; s < s1; ++s) {
-    const int elem_begin = sr.x, n_elem = sr.y, batch_begin = sr.z, n_batches = sr.w;
-    (void)elem_begin;
+    const int n_elem = sr.y, batch_begin = sr.z, n_batches = sr.w;
     const int parity = (s - s0) & 1;
     double* slot = ring + parity * slot_doubles;
-    int4 sr_next = sr;
-    if (s + 1 < s1) sr_next = __ldg(reinterpret_cast<const int4*>(C.steps + s + 1));
-    // this warp's first batch: requested before the element work so that the loads are hidden behind it
+    int4 sr_next2 = sr_next;
+    if (s + 2 < s1) sr_next2 = __ldg(reinterpret_cast<const int4*>(C.steps + s + 2));
+    // this warp's first batch of the step
     BatchRegs R;
     R.hdr = make_int4(0, 0, 0, 0); R.rec = make_int2(0, 0); R.base = 0;
     if (warp < n_batches) R = fetch_batch(C, P.graph, batch_begin + warp, lane);
-    if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);
     const bool more = (s + 1 < s1) && (tid < sr_next.y);
-    if (more) elem_stage1<DIM>(P, __ldg(C.step_elems + sr_next.x + tid), E);
+    ElemPre<DIM> En;
+    if (more) elem_stage1<DIM>(P, sr_next.x + tid, En);
+    if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);
+    if (more) { elem_stage2<DIM>(P, En); E = En; }
     __syncthreads();
     switch (mode) {
       case 1: pull_step<true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
@@ -658,8 +665,7 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
       case 7: pull_step<true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
       default: break;
     }
-    if (more) elem_stage2<DIM>(P, E);
-    sr = sr_next;
+    sr = sr_next; sr_next = sr_next2;
     __syncthreads();  // the next step overwrites the slot this pull read as "previous"
   }
 }
