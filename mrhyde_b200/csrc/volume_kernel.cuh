@@ -386,9 +386,8 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
     else thermal_affine<DIM, false>(P, E, r, cap, st);
   } else {
     // ================= general path: per-point Jacobian and coefficients =================
-    double K[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) K[t] = 0.0;
+    // the local matrix is accumulated in this element's own ring column, point by point, rather than in 36
+    // registers: the general path must not set the register footprint of the whole kernel
     double X[NV][DIM];
 #pragma unroll
     for (int n = 0; n < NV; ++n)
@@ -465,12 +464,11 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
           double k = mi * MRH_CTAB(phi)[q][j];
 #pragma unroll
           for (int d = 0; d < DIM; ++d) k += gi[d] * g[j][d];
-          K[tri<NV>(i, j)] += k;
+          double* kp = st + tri<NV>(i, j) * cap;
+          if (q == 0) *kp = k; else *kp += k;
         }
       }
     }
-#pragma unroll
-    for (int t = 0; t < NT; ++t) st[t * cap] = K[t];
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) st[(NT + i) * cap] = r[i];
@@ -523,6 +521,14 @@ __device__ __forceinline__ double slot_sum(const uint4* __restrict__ desc, const
   return acc;
 }
 
+// Loads of the software pipeline are issued through volatile asm so that the compiler keeps them where they are
+// written (early), instead of sinking them next to their first use.
+__device__ __forceinline__ int4 ldg_pinned_v4(const void* p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 struct BatchRegs {  // what a lane holds of its batch: header (uniform), its row record and CSR offset
   int4 hdr;         // row_begin, desc_begin, n_rows | n_slots << 16, flags
   int2 rec;         // row, anchor | aux << 16
@@ -532,8 +538,8 @@ struct BatchRegs {  // what a lane holds of its batch: header (uniform), its row
 // two independent loads (the row table is addressed by batch index, not through the header)
 __device__ __forceinline__ BatchRegs fetch_batch(const ChainDev& C, const GraphDev& G, const int batch, const int lane) {
   BatchRegs R;
-  R.hdr = __ldg(reinterpret_cast<const int4*>(C.batches + batch));
-  const int4 rw = __ldg(reinterpret_cast<const int4*>(C.rows + (size_t)batch * 32 + lane));   // idle lanes read zero padding (they never store)
+  R.hdr = ldg_pinned_v4(C.batches + batch);
+  const int4 rw = ldg_pinned_v4(C.rows + (size_t)batch * 32 + lane);   // idle lanes read zero padding (they never store)
   R.rec = make_int2(rw.x, rw.y);
   R.base = (int64_t)(((uint64_t)(uint32_t)rw.w << 32) | (uint64_t)(uint32_t)rw.z);
   return R;
@@ -632,8 +638,9 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   double* wbuf = ring + 2 * slot_doubles + warp * PULL_WARP_DOUBLES;
   const int mode = (P.out.res ? 1 : 0) | (P.out.jac ? 2 : 0) | (P.out.accumulate ? 4 : 0);
   // software pipeline over the steps.  While step s is computed and summed the inputs of step s+1 are in flight:
-  //   top of step s   : step record of s+2, connectivity / LIDs of s+1 (addresses depend on the step record only)
-  //   after compute s : state and vertices of s+1 (need the LIDs / connectivity requested above)
+  //   top of step s   : step record of s+2 and this warp's batch of step s (addresses depend on step records only)
+  //   after compute s : connectivity / LIDs of s+1 (step order: no element-id indirection)
+  //   after pull s    : state and vertices of s+1 (need the LIDs / connectivity requested before the pull)
   // so no load is issued right behind the load that produces its address.
   int4 sr = __ldg(reinterpret_cast<const int4*>(C.steps + s0));
   int4 sr_next = sr;
@@ -645,16 +652,14 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     const int parity = (s - s0) & 1;
     double* slot = ring + parity * slot_doubles;
     int4 sr_next2 = sr_next;
-    if (s + 2 < s1) sr_next2 = __ldg(reinterpret_cast<const int4*>(C.steps + s + 2));
+    if (s + 2 < s1) sr_next2 = ldg_pinned_v4(C.steps + s + 2);
     // this warp's first batch of the step
     BatchRegs R;
     R.hdr = make_int4(0, 0, 0, 0); R.rec = make_int2(0, 0); R.base = 0;
     if (warp < n_batches) R = fetch_batch(C, P.graph, batch_begin + warp, lane);
-    const bool more = (s + 1 < s1) && (tid < sr_next.y);
-    ElemPre<DIM> En;
-    if (more) elem_stage1<DIM>(P, sr_next.x + tid, En);
     if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);
-    if (more) { elem_stage2<DIM>(P, En); E = En; }
+    const bool more = (s + 1 < s1) && (tid < sr_next.y);
+    if (more) elem_stage1<DIM>(P, sr_next.x + tid, E);
     __syncthreads();
     switch (mode) {
       case 1: pull_step<true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
@@ -665,6 +670,7 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
       case 7: pull_step<true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
       default: break;
     }
+    if (more) elem_stage2<DIM>(P, E);
     sr = sr_next; sr_next = sr_next2;
     __syncthreads();  // the next step overwrites the slot this pull read as "previous"
   }
