@@ -1,0 +1,83 @@
+"""Two-GPU check of the NCCL halo sum (the Tpetra Export(overlapped -> owned, ADD) replacement): two ranks assemble
+their z-slabs on their own GPUs, exchange ghost rows, and the owned rows must equal the single-GPU assembly of the whole
+mesh to 1e-12.  Skipped on boxes with one GPU (the driver's gpu tier); run with `gpurun --gpus 2`."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N = (12, 10, 8)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from mrhyde_b200.problems import ThermalBrick
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        prob = ThermalBrick(3, N, device=rank, rank=rank, nranks=world, options={"column elements": 16, "min segment levels": 2})
+        uid = torch.from_numpy(prob.plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
+        dist.broadcast(uid, 0)
+        prob.plan.comm_init(uid.cpu().numpy(), rank, world)
+        prob.plan.set_halo(prob.col_gids)
+        u = torch.from_numpy(prob.state()).to(dev)
+        res = torch.zeros(prob.n_rows, dtype=torch.float64, device=dev)
+        jac = torch.zeros(prob.nnz, dtype=torch.float64, device=dev)
+        prob.plan.assemble_jacres(u, res, jac)
+        prob.plan.halo_sum(res, jac)
+        torch.cuda.synchronize()
+        no = prob.n_owned
+        q.put((rank, prob.col_gids.copy(), res[:no].cpu().numpy(), prob.rowptr[: no + 1].copy(), prob.colind[: prob.rowptr[no]].copy(),
+               jac[: prob.rowptr[no]].cpu().numpy(), prob.state()[:no].copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_halo_sum_equals_single_gpu(product_lib):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from mrhyde_b200.problems import ThermalBrick
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    glob = ThermalBrick(3, (N[0], N[1], world * N[2]), device=0)
+    dev = torch.device("cuda:0")
+    # the same state on the global mesh: value of every global row from the rank that owns it
+    ug = np.zeros(glob.n_rows)
+    for rank, gids, res, rp, ci, jac, st in outs:
+        ug[gids[: len(st)]] = st
+    d_u = torch.from_numpy(ug).to(dev)
+    d_res = torch.zeros(glob.n_rows, dtype=torch.float64, device=dev)
+    d_jac = torch.zeros(glob.nnz, dtype=torch.float64, device=dev)
+    glob.plan.assemble_jacres(d_u, d_res, d_jac)
+    torch.cuda.synchronize()
+    res_g, jac_g = d_res.cpu().numpy(), d_jac.cpu().numpy()
+    scale_r, scale_j = np.abs(res_g).max(), np.abs(jac_g).max()
+    for rank, gids, res, rp, ci, jac, st in outs:
+        own = gids[: len(st)]
+        assert np.max(np.abs(res - res_g[own])) <= 1e-12 * scale_r
+        for i, g in enumerate(own):
+            a, b = glob.rowptr[g], glob.rowptr[g + 1]
+            cg = gids[ci[rp[i]:rp[i + 1]]]
+            o = np.argsort(cg)
+            assert np.array_equal(cg[o], glob.colind[a:b])
+            assert np.max(np.abs(jac[rp[i]:rp[i + 1]][o] - jac_g[a:b])) <= 1e-12 * scale_j
