@@ -114,7 +114,7 @@ struct mrhyde_b200_plan {
   DevBuf<RowRec> d_rows;
   DevBuf<uint32_t> d_desc0, d_desc1;
   // plan-specialised (NVRTC) volume kernel; falls back to the ahead-of-time kernel when absent
-  JitKernel jit, jit_transient;   // steady build at finalize; the transient build on the first transient call
+  std::map<int, std::unique_ptr<JitKernel>> jit;   // specialised builds keyed by transient * 8 + output mode, built on first use
   bool use_jit = false;
   std::string jit_note;   // why the plan is not specialised (empty when it is)
   std::string jit_source; // translation unit handed to NVRTC
@@ -229,12 +229,18 @@ void emit_values(std::string& o, const double* v, size_t n) {
 }
 std::string pull_codegen(const ChainPlan& cp, int max_patterns);
 template <int DIM>
-std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp) {
+std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
+                               const int64_t (&n_class)[3]) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
   o += "#define MRH_JIT_DIM " + std::to_string(DIM) + "\n";
   o += "#define MRH_JIT_TRANSIENT 0  /*@transient@*/\n";
+  o += "#define MRH_JIT_MODE 7  /*@mode@*/\n";
+  // cell classes of this mesh; when coefficients are not all constant every cell takes the general path
+  o += "#define MRH_JIT_HAS_GENERAL " + std::to_string((n_class[0] > 0 || !all_const) ? 1 : 0) + "\n";
+  o += "#define MRH_JIT_HAS_AFFINE " + std::to_string((n_class[1] > 0 && all_const) ? 1 : 0) + "\n";
+  o += "#define MRH_JIT_HAS_BOX " + std::to_string((n_class[2] > 0 && all_const) ? 1 : 0) + "\n";
   o += "#define MRH_JIT_ALL_CONST " + std::to_string(all_const) + "\n";
   o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
   o += kKernelAbiSrc;
@@ -509,6 +515,30 @@ void record_end(mrhyde_b200_plan* P, cudaStream_t st, size_t slot) {
   ++P->ev_used;
 }
 
+// Specialised kernel for (steady | transient, output mode); compiled by NVRTC on first use.
+const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std::string& log) {
+  const int key = (transient ? 8 : 0) + mode;
+  auto it = P->jit.find(key);
+  if (it != P->jit.end()) return it->second.get();
+  std::string src = P->jit_source;
+  auto swap_define = [&](const std::string& mark, const std::string& with) {
+    const size_t at = src.find(mark);
+    if (at == std::string::npos) return false;
+    src.replace(at, mark.size(), with);
+    return true;
+  };
+  if (!swap_define("#define MRH_JIT_TRANSIENT 0  /*@transient@*/", std::string("#define MRH_JIT_TRANSIENT ") + (transient ? "1" : "0")) ||
+      !swap_define("#define MRH_JIT_MODE 7  /*@mode@*/", "#define MRH_JIT_MODE " + std::to_string(mode))) {
+    log = "specialisation markers missing from the generated source";
+    return nullptr;
+  }
+  std::unique_ptr<JitKernel> k(new JitKernel());
+  if (!k->build(src, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, P->jit_min_blocks, P->smem, log)) return nullptr;
+  const JitKernel* raw = k.get();
+  P->jit[key] = std::move(k);
+  return raw;
+}
+
 void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool want_jac, bool want_res, double* res, double* jac, cudaStream_t st) {
   if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "assemble called before mrhyde_b200_plan_finalize");
   if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "host-only analysis plan (device = -1) cannot assemble: there is no CPU path");
@@ -529,17 +559,14 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     const void* params;
     if (P->dim == 3) { P->th3.sol = sol; P->th3.td = td; P->th3.out = out; params = &P->th3; }
     else { P->th2.sol = sol; P->th2.td = td; P->th2.out = out; params = &P->th2; }
-    if (P->use_jit && td.transient && !P->jit_transient.ready()) {
-      std::string tsrc = P->jit_source, log;
-      const std::string mark = "#define MRH_JIT_TRANSIENT 0  /*@transient@*/";
-      const size_t at = tsrc.find(mark);
-      if (at == std::string::npos) fail(MRHYDE_B200_ERR_STATE, "jit: transient marker missing from the generated source");
-      tsrc.replace(at, mark.size(), "#define MRH_JIT_TRANSIENT 1");
-      if (!P->jit_transient.build(tsrc, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, P->jit_min_blocks, P->smem, log))
-        fail(MRHYDE_B200_ERR_CUDA, "jit: transient kernel build failed: " + log);
+    const JitKernel* jk = nullptr;
+    if (P->use_jit) {
+      const int mode = (out.res ? 1 : 0) | (out.jac ? 2 : 0) | (out.accumulate ? 4 : 0);
+      std::string log;
+      jk = jit_variant(P, td.transient != 0, mode, log);
+      if (!jk) fail(MRHYDE_B200_ERR_CUDA, "jit: kernel build failed: " + log);
     }
-    const JitKernel& jk = td.transient ? P->jit_transient : P->jit;
-    const char* lerr = P->use_jit ? jk.launch(params, P->cp.n_chains, P->threads, P->smem, st)
+    const char* lerr = P->use_jit ? jk->launch(params, P->cp.n_chains, P->threads, P->smem, st)
                                   : launch_thermal_q1_aot(P->dim, params, P->cp.n_chains, P->threads, P->smem, st);
     if (lerr) fail(MRHYDE_B200_ERR_CUDA, std::string("volume kernel launch: ") + lerr);
     record_end(P, st, slot);
@@ -798,8 +825,11 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   };
   if (P->dim == 3) { fill_thermal_tables<3>(P, P->th3.tab); fill_host(P->th3); }
   else { fill_thermal_tables<2>(P, P->th2.tab); fill_host(P->th2); }
-  P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp)
-                              : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp);
+  {
+    const int64_t n_class[3] = {M.nelem - P->n_affine, P->n_affine - P->n_box, P->n_box};
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class)
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class);
+  }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
     if (!P->bgroups.empty()) {
@@ -830,7 +860,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   {
     std::vector<int64_t> diag;
     for (int64_t r = 0; r < M.nrows; ++r) {
-      if (!M.fixed[(size_t)r]) continue;
+      if (!M.fixed[(size_t)r] || r >= M.nowned) continue;   // ghost copies of fixed rows stay zero (see plan.cpp)
       int64_t pos = -1;
       for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) if (M.colind[(size_t)p] == r) pos = p;
       diag.push_back(pos);
@@ -861,9 +891,9 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     P->use_jit = false;
     if (want == "false") P->jit_note = "disabled by option";
     else {
-      const std::string& src_text = P->jit_source;
       std::string log;
-      if (P->jit.build(src_text, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, P->jit_min_blocks, P->smem, log)) P->use_jit = true;
+      // build the variant the first assemble call will most likely use (steady, residual + Jacobian, current accumulate mode)
+      if (jit_variant(P, false, 3 | (P->accumulate ? 4 : 0), log)) P->use_jit = true;
       else if (want == "true") fail(MRHYDE_B200_ERR_CUDA, "jit=true but the plan could not be specialised: " + log);
       else P->jit_note = log;
     }
@@ -1026,7 +1056,8 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "n_box") *value = P->n_box;
   else if (k == "n_orphan_rows") *value = (int64_t)P->cp.orphan_rows.size();
   else if (k == "jit") *value = P->use_jit ? 1 : 0;
-  else if (k == "jit_registers") *value = P->use_jit ? P->jit.regs() : 0;
+  else if (k == "jit_registers") { *value = 0; for (auto& kv : P->jit) *value = std::max<int64_t>(*value, kv.second->regs()); }
+  else if (k == "jit_variants") *value = (int64_t)P->jit.size();
   else fail(MRHYDE_B200_ERR_INVALID, "plan_stat: unknown key '" + k + "'");
   ABI_END
 }

@@ -408,6 +408,9 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
           if (m.fixed[(size_t)r]) {  // strong-Dirichlet row: nothing is gathered (scatter.hpp:208, 253)
             const int32_t* dg = std::lower_bound(cols, cols + len, r);
             SR.rec.aux = (dg != cols + len && *dg == r) ? (uint16_t)(dg - cols) : (uint16_t)0xFFFF;
+            // a ghost copy of a fixed row contributes nothing: only the owner writes J(d,d) = 1, so the halo-summed
+            // matrix equals the serial reference's (the MPI reference would add one per sharing rank)
+            if (m.nowned > 0 && r >= m.nowned) SR.rec.aux = 0xFFFF;
             SR.pid = -1;
             step_rows.push_back(SR);
             continue;

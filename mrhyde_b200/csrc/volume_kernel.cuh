@@ -159,9 +159,15 @@ __device__ __forceinline__ double thermal_fn(const ThermalParams<DIM>& P, const 
 }
 
 #ifdef MRH_JIT
+#define MRH_HAS_BOX (MRH_JIT_HAS_BOX != 0)
+#define MRH_HAS_AFFINE (MRH_JIT_HAS_AFFINE != 0)
+#define MRH_HAS_GENERAL (MRH_JIT_HAS_GENERAL != 0)
 #define MRH_ALL_CONST (MRH_JIT_ALL_CONST != 0)
 #define MRH_SOURCE_CONST (MRH_JIT_SOURCE_CONST != 0)
 #else
+#define MRH_HAS_BOX true
+#define MRH_HAS_AFFINE true
+#define MRH_HAS_GENERAL true
 #define MRH_ALL_CONST (P.all_const != 0)
 #define MRH_SOURCE_CONST (P.source.is_const != 0)
 #endif
@@ -381,10 +387,11 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 #pragma unroll
   for (int i = 0; i < NV; ++i) r[i] = 0.0;
 
-  if (ecls != 0 && MRH_ALL_CONST) {
-    if (ecls == 2) thermal_affine<DIM, true>(P, E, r, cap, st);
-    else thermal_affine<DIM, false>(P, E, r, cap, st);
-  } else {
+  // MRH_HAS_*: cell classes present in the plan's mesh (the specialised build drops the paths it cannot take)
+  if (ecls != 0 && MRH_ALL_CONST && (MRH_HAS_BOX || MRH_HAS_AFFINE)) {
+    if (MRH_HAS_BOX && (ecls == 2 || !MRH_HAS_AFFINE)) thermal_affine<DIM, true>(P, E, r, cap, st);
+    else if (MRH_HAS_AFFINE) thermal_affine<DIM, false>(P, E, r, cap, st);
+  } else if (MRH_HAS_GENERAL) {
     // ================= general path: per-point Jacobian and coefficients =================
     // the local matrix is accumulated in this element's own ring column, point by point, rather than in 36
     // registers: the general path must not set the register footprint of the whole kernel
@@ -492,7 +499,7 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 #endif
 constexpr int PULL_CHUNK = 4;                       // CSR entries per transpose round
 constexpr int PULL_PITCH = PULL_CHUNK + 1;          // doubles per lane in the transpose buffer (padding: no bank conflicts)
-constexpr int PULL_WARP_DOUBLES = 32 * PULL_PITCH + 32;  // + 32 row offsets
+constexpr int PULL_WARP_DOUBLES = 32 * PULL_PITCH;
 #ifdef MRH_JIT_PULL
 static_assert(PULL_CHUNK == 4 && PULL_PITCH == 5, "generated pull code assumes 4-entry chunks with pitch 5");
 #endif
@@ -572,11 +579,12 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
   double* pj[4] = {nullptr, nullptr, nullptr, nullptr};
   bool rv[4] = {false, false, false, false};
   if (HAS_JAC) {
-    int64_t* wbase = reinterpret_cast<int64_t*>(wbuf + 32 * PULL_PITCH);
+    int64_t* wbase = reinterpret_cast<int64_t*>(wbuf);   // the row offsets are exchanged through the transpose buffer itself
     wbase[lane] = R.base;
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) { pj[j] = O.jac + wbase[rsub + 8 * j] + kk_st; rv[j] = (rsub + 8 * j) < n_rows; }
+    __syncwarp();
   }
   double* pres = HAS_RES ? (O.res + row) : nullptr;
 #ifdef MRH_JIT_PULL
@@ -636,7 +644,11 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
   double* wbuf = ring + 2 * slot_doubles + warp * PULL_WARP_DOUBLES;
+#ifdef MRH_JIT_MODE
+  constexpr int mode = MRH_JIT_MODE;   // output mode of this build: 1 res | 2 jac | 4 accumulate (the host picks the build)
+#else
   const int mode = (P.out.res ? 1 : 0) | (P.out.jac ? 2 : 0) | (P.out.accumulate ? 4 : 0);
+#endif
   // software pipeline over the steps.  While step s is computed and summed the inputs of step s+1 are in flight:
   //   top of step s   : step record of s+2 and this warp's batch of step s (addresses depend on step records only)
   //   after compute s : connectivity / LIDs of s+1 (step order: no element-id indirection)
