@@ -119,6 +119,10 @@ int mrhyde_b200_plan_set_function(mrhyde_b200_plan* plan, const char* name, cons
  *   "ns3d_uz_rows" = "reference" | "corrected"   (navierstokes.cpp:688)
  *   "accumulate"   = "true" (reference contract: sum into caller-zeroed res/J) | "false" (overwrite)
  *   "jit"          = "auto" (default: specialise the kernel with NVRTC when available) | "true" | "false"
+ *   "kernel"       = "auto" (default: the sweep kernel where it applies -- thermal, HGRAD order 1 -- else the general
+ *                    element kernel + pull) | "general" | "sweep"
+ *   "batch elems"  = elements per launch of the general path (0: sized so one batch of element matrices stays L2-resident)
+ *   "penalty", "incplanestress"   linearelasticity module keys
  *   "column elements", "min chains", "min segment levels", "sweep axis", "threads"   sweep-plan tuning
  * Unknown keys are an error, never silently ignored. */
 int mrhyde_b200_plan_set_option(mrhyde_b200_plan* plan, const char* key, const char* value);
@@ -204,6 +208,12 @@ int mrhyde_b200_expr_eval_host(int32_t n, const char* const* names, const char* 
  * tables and block size as constants), compiles it for sm_100a -- no device needed -- and optionally writes
  * the source / cubin to files (inspection with cuobjdump -sass).  log receives the compiler output. */
 int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* plan, const char* source_path, const char* cubin_path, char* log, size_t log_cap);
+/* Replays the general path's kernel stage functions (general_kernel.cuh, compiled by the host compiler) and the pull on
+ * the host for a host-only plan (device = -1) built with option kernel=general: a debugging aid that lets the kernel
+ * logic be checked against the oracle on machines without a GPU.  Fails with ERR_STATE on device plans; the assemble
+ * entry points never use it.  sol / res / jac_values (and t's vectors) are host buffers. */
+int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, int compute_jacobian,
+                                   int compute_residual, double* res, double* jac_values);
 /* Applies the plan's scatter programs on the host to caller-supplied staged element vectors
  * stage[n_elem][stage_len] (local Jacobian entries then residual entries), with the
  * same ordering and fixed-row rules as the device pull-scatter.  Verifies plan logic only. */

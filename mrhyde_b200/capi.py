@@ -26,6 +26,7 @@ SYMBOLS = [
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
     "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit",
+    "mrhyde_b200_plan_debug_emulate",
 ]
 
 
@@ -97,6 +98,7 @@ def lib():
         L.mrhyde_b200_expr_eval_host.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_scatter_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_jit.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.mrhyde_b200_plan_debug_emulate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(TimeData), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -343,6 +345,12 @@ class AssemblyPlan:
     def debug_scatter_host(self, stage, accumulate, res, jac):
         st = np.ascontiguousarray(stage, dtype=np.float64)
         self._chk(self.L.mrhyde_b200_plan_debug_scatter_host(self.h, _ptr(st), st.shape[1], int(accumulate), _ptr(res), _ptr(jac)))
+
+    def debug_emulate(self, sol, res, jac, time=None, compute_jacobian=True, compute_residual=True):
+        """Host replay of the general path's kernel stages (host-only plans, option kernel=general): a debugging aid,
+        never an assembly path (mrhyde_b200_plan_debug_emulate)."""
+        self._chk(self.L.mrhyde_b200_plan_debug_emulate(self.h, _ptr(sol), time.ref() if time is not None else None,
+                                                      int(compute_jacobian), int(compute_residual), _ptr(res), _ptr(jac)))
 
     def debug_jit(self, source_path=None, cubin_path=None):
         """Generates + NVRTC-compiles the plan-specialised kernel (no device needed); returns the compiler log."""

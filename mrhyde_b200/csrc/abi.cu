@@ -17,6 +17,7 @@
 
 #include "boundary.cuh"
 #include "expr.hpp"
+#include "general.hpp"
 #include "halo.hpp"
 #include "plan.hpp"
 #include "volume_kernel.cuh"
@@ -141,8 +142,15 @@ struct mrhyde_b200_plan {
   int64_t ev_count = 0;
   // halo
   std::unique_ptr<HaloExchange> halo;
+  // general path (any module / basis): element kernel + deterministic pull (general.hpp)
+  bool use_general = false;
+  GeneralPlanHost gen;
+  GeneralPlanDev* gen_dev = nullptr;
+  const GenDeviceKernels* gen_kernels = nullptr;
+  const GenHostKernels* gen_host = nullptr;
 
   ~mrhyde_b200_plan() {
+    if (gen_dev) gen_free(gen_dev);
     for (auto& p : ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   }
 };
@@ -150,7 +158,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -404,6 +412,39 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns) {
   return o;
 }
 
+
+// ---- module tables of the general path ----------------------------------------------------------------------------
+// YAML key and default of every coefficient function a module registers in defineFunctions, in the index order the
+// device physics reads them (general_physics.cuh): thermal.cpp:47-65, linearelasticity.cpp:64-86,
+// navierstokes.cpp:64-76, maxwell.cpp:63-78 (there the YAML keys permeability / permittivity / conductivity feed the
+// functions mu / epsilon / sigma).
+struct ModuleFn { const char* key; const char* def; };
+std::string canonical_physics(const std::string& name) {
+  if (name == "linear elasticity") return "linearelasticity";
+  if (name == "Navier Stokes" || name == "navierstokes") return "navier stokes";
+  return name;
+}
+const ModuleFn* module_functions(const std::string& phys) {
+  static const ModuleFn thermal[] = {{"thermal source", "0.0"}, {"thermal diffusion", "1.0"}, {"specific heat", "1.0"}, {"density", "1.0"},
+                                     {"advection x", "0.0"}, {"advection y", "0.0"}, {"advection z", "0.0"}, {"robin alpha", "0.0"}, {nullptr, nullptr}};
+  static const ModuleFn le[] = {{"lambda", "1.0"}, {"mu", "0.5"}, {"source dx", "0.0"}, {"source dy", "0.0"}, {"source dz", "0.0"}, {nullptr, nullptr}};
+  static const ModuleFn ns[] = {{"source ux", "0.0"}, {"source pr", "0.0"}, {"source uy", "0.0"}, {"source uz", "0.0"}, {"density", "1.0"}, {"viscosity", "1.0"}, {nullptr, nullptr}};
+  static const ModuleFn mx[] = {{"current x", "0.0"}, {"current y", "0.0"}, {"current z", "0.0"}, {"permeability", "1.0"}, {"refractive index", "1.0"},
+                                {"permittivity", "1.0"}, {"conductivity", "0.0"}, {nullptr, nullptr}};
+  if (phys == "thermal") return thermal;
+  if (phys == "linearelasticity") return le;
+  if (phys == "navier stokes") return ns;
+  if (phys == "maxwell") return mx;
+  return nullptr;
+}
+std::vector<std::string> module_variables(const std::string& phys, int dim) {
+  if (phys == "thermal") return {"T"};
+  if (phys == "linearelasticity") return dim == 2 ? std::vector<std::string>{"dx", "dy"} : std::vector<std::string>{"dx", "dy", "dz"};
+  if (phys == "navier stokes") return dim == 2 ? std::vector<std::string>{"ux", "pr", "uy"} : std::vector<std::string>{"ux", "pr", "uy", "uz"};
+  if (phys == "maxwell") return {"E", "B"};
+  return {};
+}
+
 FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side) {
   FunctionSet fs;
   // module defaults (thermal::defineFunctions, thermal.cpp:47-65), then user overrides
@@ -415,6 +456,7 @@ FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side) {
     fs.set("advection x", "0.0"); fs.set("advection y", "0.0"); fs.set("advection z", "0.0");
     fs.set("robin alpha", "0.0");
   }
+  for (const ModuleFn* f = module_functions(canonical_physics(P->physics)); f && f->key; ++f) if (P->physics != "thermal") fs.set(f->key, f->def);
   for (auto& kv : P->functions) fs.set(kv.first, kv.second);
   std::vector<std::string> sol;
   static const char* comps[3] = {"[x]", "[y]", "[z]"};
@@ -466,6 +508,7 @@ __global__ void fixed_diag_kernel(const int64_t* __restrict__ diag, int n, doubl
 void fill_time(const mrhyde_b200_time* t, TimeDev& td, bool device_ptrs_ok) {
   std::memset(&td, 0, sizeof(td));
   td.alpha_u = 1.0;
+  td.deltat = 1.0;
   if (!t) return;
   td.time = t->time;
   if (t->nstages <= 0) return;  // steady evaluation at a given time
@@ -474,6 +517,7 @@ void fill_time(const mrhyde_b200_time* t, TimeDev& td, bool device_ptrs_ok) {
   if (!t->butcher_A || !t->butcher_b || !t->butcher_c || !t->bdf_wts || !t->sol_prev) fail(MRHYDE_B200_ERR_INVALID, "time: missing tables");
   const int s = t->stage, ns = t->nstages;
   td.transient = 1;
+  td.deltat = t->deltat;
   td.alpha_u = t->butcher_A[s * ns + s] / t->butcher_b[s];
   td.one_minus_alpha_u = 1.0 - td.alpha_u;
   td.timewt = 1.0 / t->deltat / t->butcher_b[s];
@@ -553,6 +597,25 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
   const bool volume = opt_bool(P, "assemble volume terms", true);
   int launched = 0;
+  if (P->use_general) {
+    const bool bnd = opt_bool(P, "assemble boundary terms", true);
+    if (!P->accumulate && !volume) fail(MRHYDE_B200_ERR_UNSUPPORTED, "accumulate=false needs the volume pass (it defines every entry)");
+    size_t slot = 0;
+    record_begin(P, st, slot);
+    GenLaunchStats stats;
+    const char* err = gen_assemble(P->gen_dev, P->gen, P->gen_kernels, P->d_vx.p, P->d_vy.p, P->d_vz.p, P->d_conn.p, P->d_lids.p, G, out, sol, td, volume, bnd, st, &stats);
+    if (err) fail(MRHYDE_B200_ERR_CUDA, std::string("general assembly launch: ") + err);
+    record_end(P, st, slot);
+    launched = stats.launches;
+    if (want_jac && P->accumulate && P->d_fixed_diag.n > 0 && opt_bool(P, "use strong DBCs", true)) {
+      const int n = (int)P->d_fixed_diag.n;
+      fixed_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(P->d_fixed_diag.p, n, jac);
+      ++launched;
+      CUDA_OK(cudaGetLastError());
+    }
+    P->launches_per_assemble = launched;
+    return;
+  }
   if (volume) {
     size_t slot = 0;
     record_begin(P, st, slot);
@@ -594,6 +657,205 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     CUDA_OK(cudaGetLastError());
   }
   P->launches_per_assemble = launched;
+}
+
+
+// ---- general path set-up --------------------------------------------------------------------------------------
+int bc_code(const std::string& t) {
+  if (t == "Dirichlet") return BC_DIRICHLET;
+  if (t == "weak Dirichlet") return BC_WEAK_DIRICHLET;
+  if (t == "Neumann") return BC_NEUMANN;
+  return BC_NONE;
+}
+
+// reference tables of kernel basis kb in the uniform layout [card][nq][ncb] (general_physics.cuh)
+void append_ref_tab(const BasisCopy& B, const std::vector<double>& val, const std::vector<double>& grad, const std::vector<double>& curl,
+                    const std::vector<double>& div, int dim, int nq, int ncb, std::vector<double>& out) {
+  for (int i = 0; i < B.card; ++i)
+    for (int q = 0; q < nq; ++q) {
+      double e[6] = {0, 0, 0, 0, 0, 0};
+      if (B.type == "HGRAD") {
+        e[0] = val[(size_t)i * nq + q];
+        for (int d = 0; d < dim; ++d) e[1 + d] = grad.empty() ? 0.0 : grad[((size_t)i * nq + q) * dim + d];
+      } else if (B.type == "HCURL") {
+        for (int d = 0; d < dim; ++d) { e[d] = val[((size_t)i * nq + q) * dim + d]; e[3 + d] = curl.empty() ? 0.0 : curl[((size_t)i * nq + q) * dim + d]; }
+      } else {  // HDIV
+        for (int d = 0; d < dim; ++d) e[d] = val[((size_t)i * nq + q) * dim + d];
+        e[3] = div.empty() ? 0.0 : div[(size_t)i * nq + q];
+      }
+      for (int k = 0; k < ncb; ++k) out.push_back(e[k]);
+    }
+}
+
+void compile_functions(const FunctionSet& fs, const std::vector<std::string>& names, GenFnRec* rec, std::vector<uint8_t>& ops, std::vector<double>& cs) {
+  for (size_t f = 0; f < names.size(); ++f) {
+    GenFnRec r;
+    r.begin = 0; r.n = 0; r.is_const = 1; r.pad = 0; r.cval = 0.0;
+    if (!names[f].empty()) {
+      const LongProgram lp = fs.compile_long(names[f]);
+      r.is_const = lp.is_const ? 1 : 0; r.cval = lp.cval;
+      if (!lp.is_const) {
+        r.begin = (int32_t)ops.size(); r.n = (int32_t)lp.op.size();
+        ops.insert(ops.end(), lp.op.begin(), lp.op.end());
+        cs.insert(cs.end(), lp.c.begin(), lp.c.end());
+      }
+    }
+    rec[f] = r;
+  }
+}
+
+void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
+  const bool host_only = (P->device == -1);
+  MeshGraph& M = P->mesh;
+  GeneralPlanHost& H = P->gen;
+  const int dim = P->dim;
+  const int order = P->bases[(size_t)P->var_basis[0]].order;
+  const int nqs = P->bgroups.empty() ? 0 : P->bgroups[0].nqp;
+  P->gen_host = gen_find_host(phys, dim, order, P->nqp, nqs);
+  if (!P->gen_host)
+    fail(MRHYDE_B200_ERR_UNSUPPORTED, "no kernel for physics '" + P->physics + "' dim " + std::to_string(dim) + " order " + std::to_string(order) + " with " +
+                                          std::to_string(P->nqp) + " volume / " + std::to_string(nqs) + " side points; built: " + gen_supported_list());
+  if (!host_only) {
+    P->gen_kernels = gen_find_device(phys, dim, order, P->nqp, nqs);
+    if (!P->gen_kernels) fail(MRHYDE_B200_ERR_UNSUPPORTED, "general path: device kernel table lacks the configuration the host table has");
+  }
+  const GenKernelInfo& I = P->gen_host->info;
+  H.info = I;
+  // ---- the block must be the module's own variable / basis layout
+  const std::vector<std::string> want = module_variables(phys, dim);
+  if ((int)want.size() != P->nvars || I.nvars != P->nvars) fail(MRHYDE_B200_ERR_UNSUPPORTED, "general path: the block's variables are not the module's (" + phys + ")");
+  for (int v = 0; v < P->nvars; ++v) if (P->var_names[(size_t)v] != want[(size_t)v]) fail(MRHYDE_B200_ERR_UNSUPPORTED, "general path: variable order must be the module's: expected '" + want[(size_t)v] + "', got '" + P->var_names[(size_t)v] + "'");
+  if (P->ndof_elem != I.N) fail(MRHYDE_B200_ERR_INVALID, "general path: ndof_elem does not match the module's basis cardinalities");
+  static const char* tname[4] = {"HGRAD", "HCURL", "HDIV", "HVOL"};
+  std::vector<int> kb_desc((size_t)I.nbasis, -1);   // kernel basis -> descriptor basis
+  for (int v = 0; v < P->nvars; ++v) {
+    const int kb = I.var_basis[v];
+    const BasisCopy& B = P->bases[(size_t)P->var_basis[(size_t)v]];
+    const int bt = phys == "maxwell" ? (kb == 0 ? BT_HCURL : BT_HDIV) : BT_HGRAD;
+    if (B.type != tname[bt] || B.card != I.card[kb] || B.order != order) fail(MRHYDE_B200_ERR_UNSUPPORTED, "general path: variable '" + P->var_names[(size_t)v] + "' is not on the basis the module expects");
+    if (kb_desc[(size_t)kb] < 0) kb_desc[(size_t)kb] = P->var_basis[(size_t)v];
+    else if (kb_desc[(size_t)kb] != P->var_basis[(size_t)v]) fail(MRHYDE_B200_ERR_UNSUPPORTED, "general path: variables of one basis type must share one basis table");
+  }
+  std::memset(H.off, 0, sizeof(H.off));
+  {
+    std::vector<int> seen((size_t)I.N, 0);
+    for (int v = 0; v < P->nvars; ++v)
+      for (int i = 0; i < I.card[I.var_basis[v]]; ++i) {
+        const int32_t o = P->offsets[(size_t)v * P->max_card + i];
+        if (o < 0 || o >= I.N || seen[(size_t)o]++) fail(MRHYDE_B200_ERR_INVALID, "general path: offsets are not a permutation of the element dofs");
+        H.off[v][i] = (int16_t)o;
+      }
+  }
+  // ---- tables at the volume points
+  auto geo_tables = [&](const std::vector<double>& pts, int nq, std::vector<double>& gN, std::vector<double>& gdN) {
+    const int nv = 1 << dim;
+    gN.assign((size_t)nq * nv, 0.0); gdN.assign((size_t)nq * nv * dim, 0.0);
+    for (int q = 0; q < nq; ++q) geom_shape(dim, &pts[(size_t)q * dim], &gN[(size_t)q * nv], &gdN[(size_t)q * nv * dim]);
+  };
+  geo_tables(P->qp_pts, P->nqp, H.geo_N, H.geo_dN);
+  H.qwts = P->qp_wts;
+  H.ref_tab.clear();
+  for (int kb = 0; kb < I.nbasis; ++kb) {
+    const BasisCopy& B = P->bases[(size_t)kb_desc[(size_t)kb]];
+    if (B.type == "HGRAD" && B.grad.empty()) fail(MRHYDE_B200_ERR_INVALID, "general path: HGRAD basis without reference gradients");
+    if (B.type == "HCURL" && B.curl.empty()) fail(MRHYDE_B200_ERR_INVALID, "general path: HCURL basis without reference curls");
+    if (B.type == "HDIV" && B.div.empty()) fail(MRHYDE_B200_ERR_INVALID, "general path: HDIV basis without reference divergences");
+    append_ref_tab(B, B.val, B.grad, B.curl, B.div, dim, P->nqp, I.ncb[kb], H.ref_tab);
+  }
+  // ---- options
+  std::memset(&H.opt, 0, sizeof(H.opt));
+  H.opt.form_param = std::stod(opt(P, "form_param", "1.0"));
+  H.opt.penalty = std::stod(opt(P, "penalty", "10.0"));
+  H.opt.have_advection = opt_bool(P, "include advection", false) ? 1 : 0;
+  H.opt.useSUPG = opt_bool(P, "useSUPG", false) ? 1 : 0;
+  H.opt.usePSPG = opt_bool(P, "usePSPG", false) ? 1 : 0;
+  H.opt.uz_reference = opt(P, "ns3d_uz_rows", "reference") == "corrected" ? 0 : 1;
+  H.opt.incplanestress = opt_bool(P, "incplanestress", false) ? 1 : 0;
+  H.opt.leapfrog = opt_bool(P, "use leap frog", false) ? 1 : 0;
+  // ---- coefficient functions at the volume points
+  std::vector<std::string> fnames;
+  for (const ModuleFn* f = module_functions(phys); f->key; ++f) fnames.push_back(f->key);
+  if ((int)fnames.size() != I.nfn) fail(MRHYDE_B200_ERR_INVALID, "general path: module function table out of step with the kernel");
+  H.fn_op.clear(); H.fn_c.clear();
+  {
+    FunctionSet fs = make_function_set(P, false);
+    std::vector<std::string> names = fnames;
+    names.resize(GEN_MAXFN);
+    compile_functions(fs, names, H.fn, H.fn_op, H.fn_c);
+  }
+  // ---- boundary families
+  H.sides.clear();
+  int64_t inst = M.nelem;
+  if (!P->bgroups.empty()) {
+    FunctionSet fss = make_function_set(P, true);
+    for (auto& g : P->bgroups) {
+      GenSideFamily S;
+      S.sideset = g.sideset; S.local_side = g.local_side; S.nqs = g.nqp;
+      if (g.nqp != I.nqs) fail(MRHYDE_B200_ERR_UNSUPPORTED, "general path: boundary groups must all use the side rule the kernel was built for");
+      S.items = g.elem_ids;
+      for (int32_t e : S.items) if (e < 0 || e >= M.nelem) fail(MRHYDE_B200_ERR_INVALID, "boundary group: element id out of range");
+      for (int d = 0; d < 3; ++d) { S.tan_u[d] = g.tu[d]; S.tan_v[d] = g.tv[d]; }
+      const std::string& sname = P->side_names[(size_t)g.sideset];
+      std::vector<std::string> names = fnames;
+      names.resize(GEN_MAXFN);
+      for (int v = 0; v < P->nvars; ++v) {
+        auto it = P->bcs.find({P->var_names[(size_t)v], sname});
+        const std::string t = it == P->bcs.end() ? "none" : it->second.type;
+        S.bc_type[v] = bc_code(t);
+        if (S.bc_type[v] == BC_WEAK_DIRICHLET) { names[(size_t)I.nfn + v] = "Dirichlet " + P->var_names[(size_t)v] + " " + sname; S.bc_fn[v] = I.nfn + v; S.active = true; }
+        else if (S.bc_type[v] == BC_NEUMANN) { names[(size_t)I.nfn + v] = "Neumann " + P->var_names[(size_t)v] + " " + sname; S.bc_fn[v] = I.nfn + v; S.active = true; }
+      }
+      compile_functions(fss, names, S.fn, H.fn_op, H.fn_c);
+      geo_tables(g.pts, g.nqp, S.geo_N, S.geo_dN);
+      S.qwts = g.wts;
+      for (int kb = 0; kb < I.nbasis; ++kb) {
+        const size_t db = (size_t)kb_desc[(size_t)kb];
+        const BasisCopy& B = P->bases[db];
+        if (db >= g.bval.size()) fail(MRHYDE_B200_ERR_INVALID, "boundary group: side basis tables missing");
+        static const std::vector<double> none;
+        append_ref_tab(B, g.bval[db], g.bgrad[db], none, none, dim, g.nqp, I.ncb[kb], S.ref_tab);
+      }
+      if (S.active) { S.inst_base = inst; inst += (int64_t)S.items.size(); }
+      H.sides.push_back(std::move(S));
+    }
+  }
+  // ---- pull schedule
+  int64_t batch_elems = std::stoll(opt(P, "batch elems", "0"));
+  if (batch_elems == 0) {
+    // keep one batch of element matrices near the L2 capacity so that the pull reads them back from cache
+    const int64_t bytes_per_elem = (int64_t)I.N * I.N * 8;
+    batch_elems = std::max<int64_t>(4096, (48ll << 20) / bytes_per_elem);
+  }
+  try {
+    gen_build_pull(M, I.N, H.sides, batch_elems, H);
+  } catch (const std::exception& e) {
+    fail(MRHYDE_B200_ERR_INVALID, e.what());
+  }
+  P->use_general = true;
+  P->launches_per_assemble = 2 * (int)H.batches.size();
+  for (auto& S : H.sides) if (S.active && !S.items.empty()) ++P->launches_per_assemble;
+  if (host_only) { P->finalized = true; return; }
+  // ---- upload
+  size_t* tot = &P->dev_bytes;
+  P->d_vx.upload(M.vcoord[0], tot); P->d_vy.upload(M.vcoord[1], tot); P->d_vz.upload(M.vcoord[2], tot);
+  P->d_conn.upload(M.conn, tot); P->d_lids.upload(M.lids, tot);
+  P->d_rowptr.upload(M.rowptr, tot); P->d_colind.upload(M.colind, tot); P->d_fixed.upload(M.fixed, tot);
+  {
+    std::vector<int64_t> diag;
+    for (int64_t r = 0; r < M.nrows; ++r) {
+      if (!M.fixed[(size_t)r] || r >= M.nowned) continue;
+      int64_t pos = -1;
+      for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) if (M.colind[(size_t)p] == r) pos = p;
+      diag.push_back(pos);
+    }
+    P->d_fixed_diag.upload(diag, tot);
+    if (diag.empty()) P->d_fixed_diag.n = 0;
+  }
+  std::string err;
+  P->gen_dev = gen_upload(H, M, tot, err);
+  if (!P->gen_dev) fail(MRHYDE_B200_ERR_CUDA, err);
+  if (P->d_fixed_diag.n > 0) P->launches_per_assemble += 1;
+  P->finalized = true;
 }
 
 }  // namespace
@@ -761,6 +1023,14 @@ int mrhyde_b200_plan_add_boundary_group(mrhyde_b200_plan* P, const mrhyde_b200_b
   if (!sb.val) fail(MRHYDE_B200_ERR_INVALID, "add_boundary_group: missing side basis values");
   H.val.assign(sb.val, sb.val + (size_t)sb.card * bg->nqp_side);
   if (sb.grad) H.grad.assign(sb.grad, sb.grad + (size_t)sb.card * bg->nqp_side * P->dim);
+  for (size_t b = 0; b < P->bases.size(); ++b) {   // every basis at the side points (general path)
+    const mrhyde_b200_basis& in = bg->side_bases[b];
+    const BasisCopy& B = P->bases[b];
+    if (!in.val || in.card != B.card) fail(MRHYDE_B200_ERR_INVALID, "add_boundary_group: side basis table missing or of the wrong cardinality");
+    const int vdim = (B.type == "HCURL" || B.type == "HDIV") ? P->dim : 1;
+    H.bval.emplace_back(in.val, in.val + (size_t)in.card * bg->nqp_side * vdim);
+    if (in.grad) H.bgrad.emplace_back(in.grad, in.grad + (size_t)in.card * bg->nqp_side * P->dim); else H.bgrad.emplace_back();
+  }
   P->bgroups.push_back(std::move(H));
   ABI_END
 }
@@ -775,14 +1045,21 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   MeshGraph& M = P->mesh;
   for (int32_t l : M.lids) if (l < 0 || l >= M.nrows) fail(MRHYDE_B200_ERR_INVALID, "finalize: LID outside the graph's rows");
 
-  if (P->physics != "thermal") fail(MRHYDE_B200_ERR_UNSUPPORTED, "physics module '" + P->physics + "' has no device kernel in this build");
-  // ---- thermal, HGRAD Q1
+  const std::string phys = canonical_physics(P->physics);
+  if (!module_functions(phys)) fail(MRHYDE_B200_ERR_UNSUPPORTED, "physics module '" + P->physics + "' has no device kernel in this build");
+  // Kernel choice: the sweep kernel (volume_kernel.cuh) covers thermal on HGRAD order 1 with the 2-point Gauss rule and no
+  // advection; everything else -- and option kernel=general -- takes the general element kernel + pull (general.hpp).
   const int NV = 1 << P->dim;
   const BasisCopy& B = P->bases[P->var_basis[0]];
-  if (P->nvars != 1 || B.type != "HGRAD" || B.order != 1 || B.card != NV || P->ndof_elem != NV || P->nqp != NV || B.grad.empty())
-    fail(MRHYDE_B200_ERR_UNSUPPORTED, "thermal: this build has the HGRAD order-1 kernel with the 2-point Gauss rule only");
-  for (int i = 0; i < NV; ++i) if (P->offsets[i] != i) fail(MRHYDE_B200_ERR_UNSUPPORTED, "thermal: offsets must be the identity for a single variable");
-  if (opt_bool(P, "include advection", false)) fail(MRHYDE_B200_ERR_UNSUPPORTED, "thermal: 'include advection' has no device kernel in this build");
+  {
+    const std::string want = opt(P, "kernel", "auto");
+    if (want != "auto" && want != "general" && want != "sweep") fail(MRHYDE_B200_ERR_INVALID, "option kernel must be auto|general|sweep");
+    bool sweep_ok = phys == "thermal" && P->nvars == 1 && B.type == "HGRAD" && B.order == 1 && B.card == NV && P->ndof_elem == NV && P->nqp == NV && !B.grad.empty() &&
+                    !opt_bool(P, "include advection", false);
+    for (int i = 0; sweep_ok && i < NV; ++i) if (P->offsets[i] != i) sweep_ok = false;
+    if (want == "sweep" && !sweep_ok) fail(MRHYDE_B200_ERR_UNSUPPORTED, "kernel=sweep: the sweep kernel covers thermal, HGRAD order 1, 2-point Gauss rule, no advection only");
+    if (want == "general" || !sweep_ok) { finalize_general(P, phys); return MRHYDE_B200_OK; }
+  }
 
   FunctionSet fs = make_function_set(P, false);
   ExprProgram src = fs.compile("thermal source"), dif = fs.compile("thermal diffusion"), cp = fs.compile("specific heat"), rho = fs.compile("density");
@@ -1058,6 +1335,10 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "jit") *value = P->use_jit ? 1 : 0;
   else if (k == "jit_registers") { *value = 0; for (auto& kv : P->jit) *value = std::max<int64_t>(*value, kv.second->regs()); }
   else if (k == "jit_variants") *value = (int64_t)P->jit.size();
+  else if (k == "general") *value = P->use_general ? 1 : 0;
+  else if (k == "general_batches") *value = (int64_t)P->gen.batches.size();
+  else if (k == "general_instances") *value = P->gen.n_inst;
+  else if (k == "general_scratch_bytes") *value = P->gen.n_inst * (int64_t)P->gen.info.N * (P->gen.info.N + 1) * 8;
   else fail(MRHYDE_B200_ERR_INVALID, "plan_stat: unknown key '" + k + "'");
   ABI_END
 }
@@ -1140,6 +1421,56 @@ int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* P, const char* source_path, con
     std::fwrite(cubin.data(), 1, cubin.size(), f);
     std::fclose(f);
   }
+  ABI_END
+}
+
+int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const mrhyde_b200_time* t, int compute_jacobian, int compute_residual,
+                                   double* res, double* jac) {
+  ABI_BEGIN
+  if (!P || !sol) fail(MRHYDE_B200_ERR_INVALID, "debug_emulate: null argument");
+  if (!P->finalized || !P->use_general) fail(MRHYDE_B200_ERR_STATE, "debug_emulate: needs a finalized plan on the general path (option kernel=general)");
+  if (P->device != -1) fail(MRHYDE_B200_ERR_STATE, "debug_emulate: only host-only analysis plans (device = -1) replay the kernel stages on the host; device plans assemble on the GPU");
+  TimeDev td;
+  fill_time(t, td, true);   // host pointers: the replay reads them on the host
+  const GeneralPlanHost& H = P->gen;
+  const GenKernelInfo& I = H.info;
+  const MeshGraph& M = P->mesh;
+  const size_t N = (size_t)I.N;
+  std::vector<double> ej(compute_jacobian ? (size_t)H.n_inst * N * N : 0, 0.0), er(compute_residual ? (size_t)H.n_inst * N : 0, 0.0);
+  GenParams Q;
+  std::memset(&Q, 0, sizeof(Q));
+  Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
+  Q.orient = M.orient.empty() ? nullptr : M.orient.data();
+  Q.sol = sol; Q.td = td;
+  std::memcpy(Q.off, H.off, sizeof(Q.off));
+  Q.fn_op = H.fn_op.data(); Q.fn_c = H.fn_c.data(); Q.opt = H.opt;
+  Q.elem_jac = compute_jacobian ? ej.data() : nullptr;
+  Q.elem_res = compute_residual ? er.data() : nullptr;
+  if (opt_bool(P, "assemble volume terms", true)) {
+    Q.epb = 3;   // deliberately not a divisor of most meshes: exercises the padding elements
+    Q.items = nullptr; Q.item_begin = 0; Q.item_end = M.nelem; Q.inst_base = 0;
+    Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
+    std::memcpy(Q.fn, H.fn, sizeof(Q.fn));
+    for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = 0; Q.bc_fn[v] = -1; }
+    P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
+  }
+  if (opt_bool(P, "assemble boundary terms", true))
+    for (auto& S : H.sides) {
+      if (!S.active || S.items.empty()) continue;
+      Q.epb = 2;
+      Q.items = S.items.data(); Q.item_begin = 0; Q.item_end = (int64_t)S.items.size(); Q.inst_base = S.inst_base;
+      Q.geo_N = S.geo_N.data(); Q.geo_dN = S.geo_dN.data(); Q.ref_tab = S.ref_tab.data(); Q.qwts = S.qwts.data();
+      for (int d = 0; d < 3; ++d) { Q.tan_u[d] = S.tan_u[d]; Q.tan_v[d] = S.tan_v[d]; }
+      for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = S.bc_type[v]; Q.bc_fn[v] = S.bc_fn[v]; }
+      std::memcpy(Q.fn, S.fn, sizeof(Q.fn));
+      P->gen_host->emulate(true, Q, (int)((Q.item_end + Q.epb - 1) / Q.epb));
+    }
+  gen_pull_host(H, M, compute_jacobian ? ej.data() : nullptr, compute_residual ? er.data() : nullptr, P->accumulate, compute_residual ? res : nullptr,
+                compute_jacobian ? jac : nullptr);
+  if (compute_jacobian && jac && P->accumulate && opt_bool(P, "use strong DBCs", true))
+    for (int64_t r = 0; r < M.nowned; ++r)
+      if (M.fixed[(size_t)r])
+        for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) if (M.colind[(size_t)p] == r) jac[p] = 1.0;
   ABI_END
 }
 

@@ -20,6 +20,7 @@ struct BoundaryGroupHost {
   int sideset = 0, local_side = 0, nqp = 0;
   std::vector<int32_t> elem_ids;
   std::vector<double> pts, wts, val, grad;
+  std::vector<std::vector<double>> bval, bgrad;   // per basis: values [card][nqp][vdim], gradients [card][nqp][dim] (HGRAD)
   double tu[3] = {0, 0, 0}, tv[3] = {0, 0, 0};
   std::string bctype = "none";
   ExprProgram data;

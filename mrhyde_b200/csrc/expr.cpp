@@ -272,11 +272,7 @@ bool FunctionSet::fold(std::vector<Node>& nodes, int idx) {
   return true;
 }
 
-void FunctionSet::emit(const std::vector<Node>& nodes, int idx, ExprProgram& p, int& depth, int& maxdepth) {
-  auto push_op = [&](uint8_t op, double c) {
-    if (p.n >= EXPR_MAXOPS - 1) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression too long for the device evaluator");
-    p.op[p.n] = op; p.c[p.n] = c; ++p.n;
-  };
+void FunctionSet::emit(const std::vector<Node>& nodes, int idx, const std::function<void(uint8_t, double)>& push_op, int& depth, int& maxdepth) {
   const Node& n = nodes[idx];
   if (n.kind == Node::CONST) { push_op(OP_PUSHC, n.value); maxdepth = std::max(maxdepth, ++depth); return; }
   if (n.kind == Node::VAR) { push_op(OP_PUSHV, (double)n.var); maxdepth = std::max(maxdepth, ++depth); return; }
@@ -286,9 +282,9 @@ void FunctionSet::emit(const std::vector<Node>& nodes, int idx, ExprProgram& p, 
     if (op.empty()) {
       // "data = dep": the splitter only produces this for the first dependency
       if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: assignment in a chained position");
-      emit(nodes, n.deps[k].second, p, depth, maxdepth);
+      emit(nodes, n.deps[k].second, push_op, depth, maxdepth);
     } else if (is_unary(op)) {
-      emit(nodes, n.deps[k].second, p, depth, maxdepth);
+      emit(nodes, n.deps[k].second, push_op, depth, maxdepth);
       if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: unary operator in a chained position");
       push_op(unary_code(op), 0.0);
     } else {
@@ -297,7 +293,7 @@ void FunctionSet::emit(const std::vector<Node>& nodes, int idx, ExprProgram& p, 
       if (d.kind == Node::CONST && code >= OP_ADD && code <= OP_POW) push_op((uint8_t)(OP_ADDC + (code - OP_ADD)), d.value);
       else if (d.kind == Node::VAR && code >= OP_ADD && code <= OP_DIV) push_op((uint8_t)(OP_ADDV + (code - OP_ADD)), (double)d.var);
       else {
-        emit(nodes, n.deps[k].second, p, depth, maxdepth);
+        emit(nodes, n.deps[k].second, push_op, depth, maxdepth);
         push_op(code, 0.0);
         --depth;
       }
@@ -322,7 +318,11 @@ ExprProgram FunctionSet::compile(const std::string& name) const {
   }
   p.is_const = 0;
   int depth = 0, maxdepth = 0;
-  emit(nodes, root, p, depth, maxdepth);
+  auto push_op = [&](uint8_t op, double c) {
+    if (p.n >= EXPR_MAXOPS - 1) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression too long for the device evaluator");
+    p.op[p.n] = op; p.c[p.n] = c; ++p.n;
+  };
+  emit(nodes, root, push_op, depth, maxdepth);
   p.op[p.n] = OP_END;
   if (maxdepth > EXPR_MAXSTACK) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression nests too deeply for the device evaluator: " + name);
   return p;
@@ -457,6 +457,26 @@ std::string FunctionSet::codegen_tensor(const std::string& name, const std::stri
   }
   o += "}\n";
   return o;
+}
+
+LongProgram FunctionSet::compile_long(const std::string& name) const {
+  auto it = funcs_.find(name);
+  if (it == funcs_.end()) throw ExprError(MRHYDE_B200_ERR_INVALID, "function not registered: " + name);
+  std::vector<Node> nodes;
+  std::set<std::string> active;
+  active.insert(name);
+  const int root = build(it->second, nodes, active);
+  LongProgram p;
+  if (fold(nodes, root)) {
+    p.is_const = true;
+    p.cval = nodes[root].value;
+    return p;
+  }
+  int depth = 0, maxdepth = 0;
+  auto push_op = [&](uint8_t op, double c) { p.op.push_back(op); p.c.push_back(c); };
+  emit(nodes, root, push_op, depth, maxdepth);
+  if (maxdepth > 16) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression nests too deeply for the device evaluator: " + name);
+  return p;
 }
 
 double FunctionSet::eval_host(const ExprProgram& p, const double* vars) {

@@ -30,6 +30,14 @@ struct ExprError : std::runtime_error {
   ExprError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
+// Variable-length program for the general kernels (bytecode kept in global memory): same ops, no length limit, stack <= 16.
+struct LongProgram {
+  bool is_const = false;
+  double cval = 0.0;
+  std::vector<uint8_t> op;
+  std::vector<double> c;
+};
+
 // A named set of functions at one location ("ip" / "side ip"), i.e. one reference Forest.
 class FunctionSet {
  public:
@@ -39,6 +47,7 @@ class FunctionSet {
   void set_solution_fields(const std::vector<std::string>& f) { soln_fields_.assign(f.begin(), f.end()); }
   void set_scalar_fields(const std::vector<std::string>& f) { scalar_fields_ = f; }  // index = variable slot
   ExprProgram compile(const std::string& name) const;
+  LongProgram compile_long(const std::string& name) const;
   // The same tree as a C++ expression in x, y, z, t (and nx, ny, nz on sides) for the plan-specialised (NVRTC)
   // kernels: every reference op is applied in the reference's left-to-right order; constants are hex floats.
   std::string codegen(const std::string& name) const;
@@ -61,7 +70,7 @@ class FunctionSet {
   };
   int build(const std::string& expr, std::vector<Node>& nodes, std::set<std::string>& active) const;
   static bool fold(std::vector<Node>& nodes, int idx);
-  static void emit(const std::vector<Node>& nodes, int idx, ExprProgram& p, int& depth, int& maxdepth);
+  static void emit(const std::vector<Node>& nodes, int idx, const std::function<void(uint8_t, double)>& push_op, int& depth, int& maxdepth);
   static std::string gen(const std::vector<Node>& nodes, int idx);
   static std::string gen_chain(const Node& n, const std::function<std::string(int)>& child);
   std::map<std::string, std::string> funcs_;

@@ -1,0 +1,264 @@
+// Device side of the general assembly path: kernel instantiation table, the pull (row-sum) kernel and the launch
+// sequence of one assemble call (see general.hpp / general_kernel.cuh).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "general.hpp"
+#include "general_dispatch.hpp"
+
+namespace mrhyde_b200 {
+
+namespace {
+
+template <class Phys, int NQ, int NQS, int K>
+const char* launch_entry(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream) {
+  static size_t attr[2] = {0, 0};
+  const void* fn = side ? (const void*)gen_element_kernel<Phys, NQS, K, true> : (const void*)gen_element_kernel<Phys, NQ, K, false>;
+  if (smem > 48 * 1024 && smem > attr[side ? 1 : 0]) {
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr[side ? 1 : 0] = smem;
+  }
+  if (side) gen_element_kernel<Phys, NQS, K, true><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
+  else gen_element_kernel<Phys, NQ, K, false><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+std::vector<GenDeviceKernels>& device_table() {
+  static std::vector<GenDeviceKernels> T;
+  if (T.empty()) {
+#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS) T.push_back(GenDeviceKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER), &launch_entry<PHYS, NQ, NQS, K>});
+    MRH_GEN_LIST(X)
+#undef X
+  }
+  return T;
+}
+
+// ---- pull: one group of G lanes per CSR row ---------------------------------------------------------------------
+struct PullParams {
+  const int32_t* row_order;
+  const int64_t* contrib_ptr;
+  const int32_t* contrib;
+  const uint16_t* pos;
+  const double* elem_jac;
+  const double* elem_res;
+  GraphDev G;
+  OutDev O;
+  int64_t row_begin, row_end, n_owned;
+  int32_t N, max_row_len;
+};
+
+template <int G>
+__global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ PullParams Q) {
+  extern __shared__ __align__(16) double pull_smem[];
+  const int tid = threadIdx.x, lane = tid % G, grp = tid / G;
+  const int64_t k = Q.row_begin + (int64_t)blockIdx.x * (blockDim.x / G) + grp;
+  const unsigned mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((tid % 32) / G * G));
+  if (k >= Q.row_end) return;
+  double* buf = pull_smem + (size_t)grp * Q.max_row_len;
+  const int32_t r = __ldg(Q.row_order + k);
+  const int64_t rs = __ldg(Q.G.rowptr + r);
+  const int len = (int)(__ldg(Q.G.rowptr + r + 1) - rs);
+  if (__ldg(Q.G.fixed + r)) {   // strong-Dirichlet row: skipped by the scatter (scatter.hpp:208, 253); identity row when overwriting
+    if (!Q.O.accumulate) {
+      if (Q.O.res && lane == 0) Q.O.res[r] = 0.0;
+      if (Q.O.jac)
+        for (int t = lane; t < len; t += G) Q.O.jac[rs + t] = (__ldg(Q.G.colind + rs + t) == r && r < Q.n_owned) ? 1.0 : 0.0;
+    }
+    return;
+  }
+  const int N = Q.N;
+  const int64_t c0 = __ldg(Q.contrib_ptr + k), c1 = __ldg(Q.contrib_ptr + k + 1);
+  if (Q.O.jac) {
+    for (int t = lane; t < len; t += G) buf[t] = 0.0;
+    __syncwarp(mask);
+    for (int64_t p = c0; p < c1; ++p) {
+      const int64_t ci = (int64_t)__ldg(Q.contrib + p) * N;
+      for (int c = lane; c < N; c += G) buf[__ldg(Q.pos + ci + c)] += __ldcs(Q.elem_jac + ci + c);
+      __syncwarp(mask);
+    }
+    if (Q.O.accumulate) for (int t = lane; t < len; t += G) Q.O.jac[rs + t] += buf[t];
+    else for (int t = lane; t < len; t += G) __stcs(Q.O.jac + rs + t, buf[t]);
+  }
+  if (Q.O.res && lane == 0) {
+    double s = 0.0;
+    for (int64_t p = c0; p < c1; ++p) s += __ldcs(Q.elem_res + __ldg(Q.contrib + p));
+    Q.O.res[r] = (Q.O.accumulate ? Q.O.res[r] : 0.0) + (-s);
+  }
+}
+
+template <class T>
+struct Buf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~Buf() { if (p) cudaFree(p); }
+  bool upload(const std::vector<T>& h, size_t* tot, std::string& err) {
+    n = h.size();
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess && n) e = cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { err = std::string("general plan upload: ") + cudaGetErrorString(e); return false; }
+    if (tot) *tot += bytes;
+    return true;
+  }
+  bool alloc(size_t count, size_t* tot, std::string& err) {
+    n = count;
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    const cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { err = std::string("general plan scratch: ") + cudaGetErrorString(e); return false; }
+    if (tot) *tot += bytes;
+    return true;
+  }
+};
+
+struct SideDev {
+  Buf<int32_t> items;
+  Buf<double> geo_N, geo_dN, ref_tab, qwts;
+};
+
+}  // namespace
+
+struct GeneralPlanDev {
+  Buf<int32_t> row_order, contrib;
+  Buf<int64_t> contrib_ptr;
+  Buf<uint16_t> pos;
+  Buf<double> geo_N, geo_dN, ref_tab, qwts, fn_c, elem_jac, elem_res;
+  Buf<uint8_t> fn_op;
+  Buf<int8_t> orient;
+  std::vector<std::unique_ptr<SideDev>> sides;
+};
+
+const GenDeviceKernels* gen_find_device(const std::string& physics, int dim, int order, int nq, int nqs) {
+  for (auto& k : device_table())
+    if (physics == k.info.physics && dim == k.info.dim && order == k.info.order && nq == k.info.nq && (nqs == 0 || nqs == k.info.nqs)) return &k;
+  return nullptr;
+}
+
+void gen_free(GeneralPlanDev* D) { delete D; }
+
+GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t* tot, std::string& err) {
+  std::unique_ptr<GeneralPlanDev> D(new GeneralPlanDev());
+  const size_t N = (size_t)H.info.N;
+  bool ok = D->row_order.upload(H.row_order, tot, err) && D->contrib.upload(H.contrib, tot, err) && D->contrib_ptr.upload(H.contrib_ptr, tot, err) &&
+            D->pos.upload(H.pos, tot, err) && D->geo_N.upload(H.geo_N, tot, err) && D->geo_dN.upload(H.geo_dN, tot, err) &&
+            D->ref_tab.upload(H.ref_tab, tot, err) && D->qwts.upload(H.qwts, tot, err) && D->fn_c.upload(H.fn_c, tot, err) &&
+            D->fn_op.upload(H.fn_op, tot, err) && D->elem_jac.alloc((size_t)H.n_inst * N * N, tot, err) && D->elem_res.alloc((size_t)H.n_inst * N, tot, err);
+  if (ok && !m.orient.empty()) ok = D->orient.upload(m.orient, tot, err);
+  for (auto& s : H.sides) {
+    if (!ok) break;
+    std::unique_ptr<SideDev> sd(new SideDev());
+    ok = sd->items.upload(s.items, tot, err) && sd->geo_N.upload(s.geo_N, tot, err) && sd->geo_dN.upload(s.geo_dN, tot, err) &&
+         sd->ref_tab.upload(s.ref_tab, tot, err) && sd->qwts.upload(s.qwts, tot, err);
+    D->sides.push_back(std::move(sd));
+  }
+  if (!ok) return nullptr;
+  return D.release();
+}
+
+static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items) {
+  // threads per element in the derivative stage; aim for 128..256 threads and <= ~100 KB of shared memory per CTA
+  const int tpe = I.N / I.K;
+  const int sd = side ? I.smem_doubles_side : I.smem_doubles_volume;
+  int epb = std::max(1, 256 / tpe);
+  while (epb > 1 && (size_t)epb * sd * 8 > 100 * 1024) --epb;
+  if (n_items < epb) epb = (int)std::max<int64_t>(1, n_items);
+  return epb;
+}
+
+const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                         const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
+                         bool volume, bool boundary, void* stream, GenLaunchStats* stats) {
+  const GenKernelInfo& I = H.info;
+  GenParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.vx = vx; P.vy = vy; P.vz = vz; P.conn = conn; P.lids = lids; P.orient = D->orient.n ? D->orient.p : nullptr;
+  P.sol = sol; P.td = td;
+  std::memcpy(P.off, H.off, sizeof(P.off));
+  std::memcpy(P.fn, H.fn, sizeof(P.fn));
+  P.fn_op = D->fn_op.p; P.fn_c = D->fn_c.p; P.opt = H.opt;
+  for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
+  P.elem_jac = O.jac ? D->elem_jac.p : nullptr;
+  P.elem_res = O.res ? D->elem_res.p : nullptr;
+  int launches = 0;
+  auto run_elements = [&](bool side, int64_t n_items) -> const char* {
+    if (n_items <= 0) return nullptr;
+    const int epb = pick_epb(I, side, n_items);
+    P.epb = epb;
+    const int tpe = I.N / I.K;
+    int threads = ((epb * tpe + 31) / 32) * 32;
+    threads = std::max(64, std::min(256, threads));
+    const size_t smem = (size_t)epb * (side ? I.smem_doubles_side : I.smem_doubles_volume) * sizeof(double);
+    const int64_t nblocks = (n_items + epb - 1) / epb;
+    ++launches;
+    return kd->launch(side, P, (int)nblocks, threads, smem, stream);
+  };
+  auto run_pull = [&](int64_t row_begin, int64_t row_end) -> const char* {
+    if (row_end <= row_begin) return nullptr;
+    PullParams Q;
+    Q.row_order = D->row_order.p; Q.contrib_ptr = D->contrib_ptr.p; Q.contrib = D->contrib.p; Q.pos = D->pos.p;
+    Q.elem_jac = D->elem_jac.p; Q.elem_res = D->elem_res.p; Q.G = G; Q.O = O;
+    Q.row_begin = row_begin; Q.row_end = row_end; Q.n_owned = H.n_owned; Q.N = I.N; Q.max_row_len = std::max(1, H.max_row_len);
+    const int Gs = I.N <= 8 ? 8 : (I.N <= 16 ? 16 : 32);
+    const int threads = 256, rows_per_block = threads / Gs;
+    const size_t smem = (size_t)rows_per_block * Q.max_row_len * sizeof(double);
+    const int64_t nblocks = (row_end - row_begin + rows_per_block - 1) / rows_per_block;
+    ++launches;
+    if (smem > 48 * 1024) {
+      static size_t attr[3] = {0, 0, 0};
+      const int ai = Gs == 8 ? 0 : (Gs == 16 ? 1 : 2);
+      if (smem > attr[ai]) {
+        const void* fn = Gs == 8 ? (const void*)gen_pull_kernel<8> : (Gs == 16 ? (const void*)gen_pull_kernel<16> : (const void*)gen_pull_kernel<32>);
+        const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        attr[ai] = smem;
+      }
+    }
+    if (Gs == 8) gen_pull_kernel<8><<<(int)nblocks, threads, smem, (cudaStream_t)stream>>>(Q);
+    else if (Gs == 16) gen_pull_kernel<16><<<(int)nblocks, threads, smem, (cudaStream_t)stream>>>(Q);
+    else gen_pull_kernel<32><<<(int)nblocks, threads, smem, (cudaStream_t)stream>>>(Q);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+  };
+  const bool any_side = boundary && std::any_of(H.sides.begin(), H.sides.end(), [](const GenSideFamily& s) { return s.active && !s.items.empty(); });
+  // instances that are not computed in this call must read as zero: clear the scratch ranges that are skipped
+  if (!volume) {
+    if (P.elem_jac) cudaMemsetAsync(D->elem_jac.p, 0, (size_t)H.n_elem * I.N * I.N * sizeof(double), (cudaStream_t)stream);
+    if (P.elem_res) cudaMemsetAsync(D->elem_res.p, 0, (size_t)H.n_elem * I.N * sizeof(double), (cudaStream_t)stream);
+  }
+  if (!any_side && H.n_inst > H.n_elem) {
+    if (P.elem_jac) cudaMemsetAsync(D->elem_jac.p + (size_t)H.n_elem * I.N * I.N, 0, (size_t)(H.n_inst - H.n_elem) * I.N * I.N * sizeof(double), (cudaStream_t)stream);
+    if (P.elem_res) cudaMemsetAsync(D->elem_res.p + (size_t)H.n_elem * I.N, 0, (size_t)(H.n_inst - H.n_elem) * I.N * sizeof(double), (cudaStream_t)stream);
+  }
+  const int nb = (int)H.batches.size();
+  for (int b = 0; b < nb; ++b) {
+    const GenBatch& B = H.batches[(size_t)b];
+    if (volume) {
+      P.items = nullptr; P.item_begin = B.elem_begin; P.item_end = B.elem_end; P.inst_base = B.elem_begin;
+      std::memcpy(P.fn, H.fn, sizeof(P.fn));
+      for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
+      P.geo_N = D->geo_N.p; P.geo_dN = D->geo_dN.p; P.ref_tab = D->ref_tab.p; P.qwts = D->qwts.p;
+      if (const char* e = run_elements(false, B.elem_end - B.elem_begin)) return e;
+    }
+    if (b == nb - 1 && any_side) {
+      for (size_t s = 0; s < H.sides.size(); ++s) {
+        const GenSideFamily& S = H.sides[s];
+        if (!S.active || S.items.empty()) continue;
+        const SideDev& sd = *D->sides[s];
+        P.items = sd.items.p; P.item_begin = 0; P.item_end = (int64_t)S.items.size(); P.inst_base = S.inst_base;
+        P.geo_N = sd.geo_N.p; P.geo_dN = sd.geo_dN.p; P.ref_tab = sd.ref_tab.p; P.qwts = sd.qwts.p;
+        for (int d = 0; d < 3; ++d) { P.tan_u[d] = S.tan_u[d]; P.tan_v[d] = S.tan_v[d]; }
+        for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = S.bc_type[v]; P.bc_fn[v] = S.bc_fn[v]; }
+        std::memcpy(P.fn, S.fn, sizeof(P.fn));
+        if (const char* e = run_elements(true, (int64_t)S.items.size())) return e;
+      }
+    }
+    if (const char* e = run_pull(B.row_begin, B.row_end)) return e;
+  }
+  if (stats) stats->launches = launches;
+  return nullptr;
+}
+
+}  // namespace mrhyde_b200

@@ -1,0 +1,96 @@
+// Host side of the general assembly path (any restated module, any supported basis): plan-time analysis for the
+// deterministic pull (the fused scatter of assemblyManager_scatter.hpp:162-278 turned around), the table of compiled
+// kernel instantiations, and the per-call launch sequence.
+//
+//   element kernel   general_kernel.cuh   -> scratch element matrices / vectors (one instance per element, then one per
+//                                            boundary (element, side) in boundary-group order: the reference's order of
+//                                            contributions, assemblyManager_jacres.hpp:336-603)
+//   pull kernel      general.cu           -> every CSR row sums its instances in ascending order and is written once
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "general_kernel.cuh"
+#include "plan.hpp"
+
+namespace mrhyde_b200 {
+
+// One compiled instantiation <Phys, NQ, NQS, K>.
+struct GenKernelInfo {
+  const char* physics;
+  int dim, order, nq, nqs;
+  int N, nvars, nbasis, nfn, K;
+  int smem_doubles_volume, smem_doubles_side;   // per element
+  int card[2], ncb[2];                          // per basis
+  int var_basis[GEN_MAXVARS];
+};
+struct GenDeviceKernels {
+  GenKernelInfo info;
+  // returns nullptr on success, else a static error string
+  const char* (*launch)(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream);
+};
+struct GenHostKernels {
+  GenKernelInfo info;
+  void (*emulate)(bool side, const GenParams& P, int nblocks);
+};
+const GenDeviceKernels* gen_find_device(const std::string& physics, int dim, int order, int nq, int nqs);
+const GenHostKernels* gen_find_host(const std::string& physics, int dim, int order, int nq, int nqs);
+std::string gen_supported_list();
+
+struct GenSideFamily {      // one boundary group: (sideset, local side) with its side cubature and tables
+  int sideset = 0, local_side = 0, nqs = 0;
+  std::vector<int32_t> items;          // element ids
+  int64_t inst_base = 0;               // scratch instance of items[0]
+  std::vector<double> geo_N, geo_dN, ref_tab, qwts;
+  double tan_u[3] = {0, 0, 0}, tan_v[3] = {0, 0, 0};
+  int32_t bc_type[GEN_MAXVARS] = {0, 0, 0, 0};
+  int32_t bc_fn[GEN_MAXVARS] = {-1, -1, -1, -1};
+  GenFnRec fn[GEN_MAXFN];              // module functions at side ip, then the boundary data of each variable
+  bool active = false;                 // some variable has a Neumann / weak Dirichlet condition here
+};
+
+struct GenBatch {
+  int64_t elem_begin = 0, elem_end = 0;   // element kernel range
+  int64_t row_begin = 0, row_end = 0;     // rows (in row_order) that are complete after this batch
+};
+
+struct GeneralPlanHost {
+  GenKernelInfo info;
+  int64_t n_elem = 0, n_inst = 0, n_rows = 0, n_owned = 0;
+  int32_t max_row_len = 0;
+  // pull schedule
+  std::vector<int32_t> row_order;        // rows sorted by completion batch
+  std::vector<int64_t> contrib_ptr;      // [n_rows+1] in row_order order
+  std::vector<int32_t> contrib;          // inst * N + local row, ascending instance
+  std::vector<uint16_t> pos;             // [n_inst][N][N]: position of column LID(c) inside row LID(i)
+  std::vector<GenBatch> batches;         // volume batches; rows completed by side instances sit in the last batch
+  // launch tables (volume)
+  std::vector<double> geo_N, geo_dN, ref_tab, qwts;
+  std::vector<uint8_t> fn_op;
+  std::vector<double> fn_c;
+  GenFnRec fn[GEN_MAXFN];
+  int16_t off[GEN_MAXVARS][GEN_MAXDOF];
+  GenOpts opt;
+  std::vector<GenSideFamily> sides;
+};
+
+// builds contrib / pos / row_order / batches from the mesh graph and the side families' items
+void gen_build_pull(const MeshGraph& m, int N, const std::vector<GenSideFamily>& sides, int64_t batch_elems, GeneralPlanHost& out);
+
+// host replay of the pull (plan verification and the emulation hook)
+void gen_pull_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, const double* elem_res, bool accumulate,
+                   double* res, double* jac);
+
+// ---- device side (general.cu) ---------------------------------------------------------------------------------
+struct GeneralPlanDev;   // device buffers
+struct GenLaunchStats { int launches = 0; };
+GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t* dev_bytes, std::string& err);
+void gen_free(GeneralPlanDev* D);
+// the whole assemble call: element kernels + pull per batch.  Returns nullptr or an error string.
+const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                         const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
+                         bool volume, bool boundary, void* stream, GenLaunchStats* stats);
+
+}  // namespace mrhyde_b200

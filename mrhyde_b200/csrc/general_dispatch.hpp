@@ -1,0 +1,45 @@
+// The compiled instantiations of the general element kernel: (module, dimension, basis order, volume points, side points).
+// Included by general.cu (device launchers) and general_emulate.cpp (host replay of the same stage functions).
+#pragma once
+#include "general_physics.cuh"
+
+namespace mrhyde_b200 {
+typedef ThermalPhys<2, 1> GenTh21;
+typedef ThermalPhys<3, 1> GenTh31;
+typedef ThermalPhys<2, 2> GenTh22;
+typedef ThermalPhys<3, 2> GenTh32;
+typedef ElasticityPhys<2, 1> GenLe21;
+typedef ElasticityPhys<3, 1> GenLe31;
+typedef ElasticityPhys<2, 2> GenLe22;
+typedef ElasticityPhys<3, 2> GenLe32;
+typedef NavierStokesPhys<2, 1> GenNs21;
+typedef NavierStokesPhys<3, 1> GenNs31;
+}  // namespace mrhyde_b200
+
+// X(physics name, dim, order, NQ, NQS, K, Phys)
+#define MRH_GEN_LIST(X)                                   \
+  X("thermal", 2, 1, 4, 2, 1, GenTh21)                    \
+  X("thermal", 3, 1, 8, 4, 1, GenTh31)                    \
+  X("thermal", 2, 2, 9, 3, 1, GenTh22)                    \
+  X("thermal", 3, 2, 27, 9, 1, GenTh32)                   \
+  X("linearelasticity", 2, 1, 4, 2, 1, GenLe21)           \
+  X("linearelasticity", 3, 1, 8, 4, 1, GenLe31)           \
+  X("linearelasticity", 2, 2, 9, 3, 1, GenLe22)           \
+  X("linearelasticity", 3, 2, 27, 9, 1, GenLe32)          \
+  X("navier stokes", 2, 1, 4, 2, 1, GenNs21)              \
+  X("navier stokes", 3, 1, 8, 4, 1, GenNs31)              \
+  X("maxwell", 3, 1, 8, 4, 1, MaxwellPhys)
+
+namespace mrhyde_b200 {
+template <class Phys, int NQ, int NQS, int K>
+inline GenKernelInfo gen_make_info(const char* physics, int dim, int order) {
+  GenKernelInfo I;
+  I.physics = physics; I.dim = dim; I.order = order; I.nq = NQ; I.nqs = NQS;
+  I.N = Phys::N; I.nvars = Phys::NVAR; I.nbasis = Phys::NBASIS; I.nfn = Phys::NFN; I.K = K;
+  I.smem_doubles_volume = GenLayout<Phys, NQ>::SIZE;
+  I.smem_doubles_side = GenLayout<Phys, NQS>::SIZE;
+  for (int b = 0; b < 2; ++b) { I.card[b] = b < Phys::NBASIS ? Phys::card(b) : 0; I.ncb[b] = b < Phys::NBASIS ? Phys::ncb(b) : 0; }
+  for (int v = 0; v < GEN_MAXVARS; ++v) I.var_basis[v] = v < Phys::NVAR ? Phys::var_basis(v) : 0;
+  return I;
+}
+}  // namespace mrhyde_b200

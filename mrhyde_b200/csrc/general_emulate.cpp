@@ -1,0 +1,69 @@
+// Host replay of the general element kernel's stage functions (general_kernel.cuh compiled by the host compiler).
+// A debugging aid for machines without a GPU: reachable only through mrhyde_b200_plan_debug_emulate on host-only
+// plans (device = -1); mrhyde_b200_assemble_* never calls it -- there is no CPU fallback.
+#include <cstring>
+#include <vector>
+
+#include "general.hpp"
+#include "general_dispatch.hpp"
+
+namespace mrhyde_b200 {
+
+namespace {
+
+template <class Phys, int NQ, int K, bool SIDE>
+void emulate_blocks(const GenParams& P, int nblocks) {
+  typedef GenBlock<Phys, NQ, K, SIDE> Bk;
+  typedef GenLayout<Phys, NQ> L;
+  std::vector<double> sm((size_t)P.epb * L::SIZE);
+  for (int blk = 0; blk < nblocks; ++blk) {
+    std::fill(sm.begin(), sm.end(), 0.0);
+    const int n0 = P.epb * (L::N > L::NV ? L::N : L::NV);
+    for (int i = 0; i < n0; ++i) Bk::s0(P, sm.data(), blk, i);
+    for (int i = 0; i < P.epb * NQ; ++i) Bk::s1(P, sm.data(), blk, i);
+    for (int i = 0; i < P.epb; ++i) Bk::s1b(P, sm.data(), blk, i);
+    for (int i = 0; i < P.epb * Phys::max_card() * NQ; ++i) Bk::s2(P, sm.data(), blk, i);
+    for (int i = 0; i < P.epb * NQ; ++i) Bk::s3(P, sm.data(), blk, i);
+    for (int i = 0; i < P.epb * NQ; ++i) Bk::s4a(P, sm.data(), blk, i);
+    if (P.elem_jac)
+      for (int i = 0; i < P.epb * Bk::TPE; ++i) Bk::s4b(P, sm.data(), blk, i);
+    for (int i = 0; i < P.epb * L::N; ++i) Bk::s5(P, sm.data(), blk, i);
+  }
+}
+
+template <class Phys, int NQ, int NQS, int K>
+void emulate_entry(bool side, const GenParams& P, int nblocks) {
+  if (side) emulate_blocks<Phys, NQS, K, true>(P, nblocks);
+  else emulate_blocks<Phys, NQ, K, false>(P, nblocks);
+}
+
+struct HostEntry { GenHostKernels k; };
+
+std::vector<GenHostKernels>& host_table() {
+  static std::vector<GenHostKernels> T;
+  if (T.empty()) {
+#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS) T.push_back(GenHostKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER), &emulate_entry<PHYS, NQ, NQS, K>});
+    MRH_GEN_LIST(X)
+#undef X
+  }
+  return T;
+}
+
+}  // namespace
+
+const GenHostKernels* gen_find_host(const std::string& physics, int dim, int order, int nq, int nqs) {
+  for (auto& k : host_table())
+    if (physics == k.info.physics && dim == k.info.dim && order == k.info.order && nq == k.info.nq && (nqs == 0 || nqs == k.info.nqs)) return &k;
+  return nullptr;
+}
+
+std::string gen_supported_list() {
+  std::string s;
+  for (auto& k : host_table()) {
+    if (!s.empty()) s += "; ";
+    s += std::string(k.info.physics) + " dim " + std::to_string(k.info.dim) + " order " + std::to_string(k.info.order) + " nqp " + std::to_string(k.info.nq);
+  }
+  return s;
+}
+
+}  // namespace mrhyde_b200

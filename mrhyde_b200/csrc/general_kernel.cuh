@@ -1,0 +1,571 @@
+// General element kernel: residual + Jacobian of one batch of elements (or boundary sides) for any of the restated
+// physics modules, with forward-mode AD derivative components across the threads of an element.
+//
+// Reference path replaced (one launch instead of ~20 per group of 100 elements):
+//   performGather                       assemblyManager_gather.hpp:181-234
+//   computeSoln{Steady,Transient}Seeded workset.cpp:864-901, 600-834
+//   getPhysicalVolumetricBasis          discretizationInterface_basis.hpp:382-611   (push-forward, recomputed here)
+//   getPhysicalIntegrationData          discretizationInterface_integration.hpp:218-262, side data :592-774
+//   evaluateSolutionField               workset.cpp:978-1111
+//   FunctionManager::evaluate           functionManager_evaluate.hpp:14-229
+//   <module>::volumeResidual / boundaryResidual   (general_physics.cuh cites each)
+// The fused scatter (assemblyManager_scatter.hpp:162-278) becomes `pull_rows_kernel` in general.cu.
+//
+// Mapping.  A CTA owns EPB elements; thread (e, g) owns K derivative components (columns) of element e.  Stages,
+// separated by __syncthreads, all operands in shared memory:
+//   S0 gather dofs (+ transient combination) and vertex coordinates
+//   S1 cell Jacobian, inverse, determinant, weights, physical points (side: normals and side weights) per (e, q)
+//   S2 push-forward of the reference basis tables: PB[b][i][q][k]   k = (val, grad xyz) | (val xyz, curl xyz) | (val xyz, div)
+//   S3 solution fields F[v][k] = sum_i u_i PB, time-derivative fields, coefficient functions (bytecode) per (e, q)
+//   S4 weak-form coefficients Cf[v][k] of the module at each point: values (double) by thread (e, q); derivative
+//      components (dual numbers seeded with PB of the thread's columns) by thread (e, g), followed by the test-function
+//      loop  dF_{(v,i)}/du_col += sum_k dCf[v][k] PB[b(v)][i][q][k]  with the N accumulators in registers
+//   S5 residual rows F_{(v,i)} = sum_q sum_k Cf[v][k] PB
+// Output: element matrices / vectors in a scratch array (row-major per element); the pull kernel sums them into the CSR
+// values in ascending element order (the serial reference's order) without atomics.
+//
+// This header also compiles with a host compiler (MRH_HOST_EMULATION): the stage functions are plain functions of
+// (block, thread) and general_emulate.cpp runs them in loops -- a debugging aid for the kernel logic on machines
+// without a GPU, reachable only through mrhyde_b200_plan_debug_emulate on host-only plans; assemble_* never uses it.
+#pragma once
+#include "kernel_abi.h"
+
+#if defined(__CUDACC__)
+#define MRH_HD __device__ __forceinline__
+#define MRH_CE __host__ __device__ constexpr
+#define MRH_LDG(p) __ldg(p)
+#else
+#define MRH_HD inline
+#define MRH_CE constexpr
+#define MRH_LDG(p) (*(p))
+#include <cmath>
+#endif
+
+namespace mrhyde_b200 {
+
+// ---- dual number with K derivative components -----------------------------------------------------------
+template <int K>
+struct Dual {
+  double v;
+  double d[K];
+  MRH_HD Dual() {}
+  MRH_HD Dual(double x) : v(x) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) d[k] = 0.0;
+  }
+};
+#define MRH_DUAL_LOOP _Pragma("unroll") for (int k = 0; k < K; ++k)
+template <int K> MRH_HD Dual<K> operator-(const Dual<K>& a) { Dual<K> r; r.v = -a.v; MRH_DUAL_LOOP r.d[k] = -a.d[k]; return r; }
+template <int K> MRH_HD Dual<K> operator+(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v + b.v; MRH_DUAL_LOOP r.d[k] = a.d[k] + b.d[k]; return r; }
+template <int K> MRH_HD Dual<K> operator-(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v - b.v; MRH_DUAL_LOOP r.d[k] = a.d[k] - b.d[k]; return r; }
+template <int K> MRH_HD Dual<K> operator*(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v * b.v; MRH_DUAL_LOOP r.d[k] = a.d[k] * b.v + a.v * b.d[k]; return r; }
+template <int K> MRH_HD Dual<K> operator/(const Dual<K>& a, const Dual<K>& b) {
+  Dual<K> r; const double ib = 1.0 / b.v; r.v = a.v * ib; MRH_DUAL_LOOP r.d[k] = (a.d[k] - r.v * b.d[k]) * ib; return r;
+}
+template <int K> MRH_HD Dual<K> operator+(const Dual<K>& a, double b) { Dual<K> r = a; r.v += b; return r; }
+template <int K> MRH_HD Dual<K> operator+(double a, const Dual<K>& b) { Dual<K> r = b; r.v += a; return r; }
+template <int K> MRH_HD Dual<K> operator-(const Dual<K>& a, double b) { Dual<K> r = a; r.v -= b; return r; }
+template <int K> MRH_HD Dual<K> operator-(double a, const Dual<K>& b) { Dual<K> r; r.v = a - b.v; MRH_DUAL_LOOP r.d[k] = -b.d[k]; return r; }
+template <int K> MRH_HD Dual<K> operator*(const Dual<K>& a, double b) { Dual<K> r; r.v = a.v * b; MRH_DUAL_LOOP r.d[k] = a.d[k] * b; return r; }
+template <int K> MRH_HD Dual<K> operator*(double a, const Dual<K>& b) { Dual<K> r; r.v = a * b.v; MRH_DUAL_LOOP r.d[k] = a * b.d[k]; return r; }
+template <int K> MRH_HD Dual<K> operator/(const Dual<K>& a, double b) { const double ib = 1.0 / b; Dual<K> r; r.v = a.v * ib; MRH_DUAL_LOOP r.d[k] = a.d[k] * ib; return r; }
+template <int K> MRH_HD Dual<K> operator/(double a, const Dual<K>& b) { Dual<K> r; const double ib = 1.0 / b.v; r.v = a * ib; MRH_DUAL_LOOP r.d[k] = -r.v * b.d[k] * ib; return r; }
+template <int K> MRH_HD Dual<K> mrh_sqrt(const Dual<K>& a) { Dual<K> r; r.v = sqrt(a.v); const double g = 0.5 / r.v; MRH_DUAL_LOOP r.d[k] = g * a.d[k]; return r; }
+MRH_HD double mrh_sqrt(double a) { return sqrt(a); }
+template <int K> MRH_HD double mrh_val(const Dual<K>& a) { return a.v; }
+MRH_HD double mrh_val(double a) { return a; }
+
+// ---- launch parameters --------------------------------------------------------------------------------------
+constexpr int GEN_MAXVARS = 4;
+constexpr int GEN_MAXFN = 16;
+constexpr int GEN_MAXDOF = 96;
+enum GenBasisType : int32_t { BT_HGRAD = 0, BT_HCURL = 1, BT_HDIV = 2, BT_HVOL = 3 };
+enum GenBcType : int32_t { BC_NONE = 0, BC_DIRICHLET = 1, BC_WEAK_DIRICHLET = 2, BC_NEUMANN = 3 };
+
+struct GenFnRec {   // one coefficient function: constant or a bytecode range in GenParams::fn_op / fn_c
+  int32_t begin, n, is_const, pad;
+  double cval;
+};
+
+struct GenOpts {    // module flags by their YAML key
+  double form_param;     // "form_param"
+  double penalty;        // linearelasticity "penalty"
+  int32_t have_advection;  // thermal "include advection"
+  int32_t useSUPG, usePSPG;
+  int32_t uz_reference;    // navierstokes.cpp:688 defect reproduced (1) or corrected (0)
+  int32_t incplanestress;
+  int32_t leapfrog;
+};
+
+struct GenParams {
+  // mesh (global memory)
+  const double* vx; const double* vy; const double* vz;
+  const int32_t* conn;      // [n_elem][nverts]
+  const int32_t* lids;      // [n_elem][N]
+  const int8_t* orient;     // [n_elem][N] or null
+  const double* sol;
+  TimeDev td;
+  // work items: volume -> elements [item_begin, item_end); side -> items[item_begin .. item_end) hold element ids
+  const int32_t* items;     // null for the volume launch
+  int64_t item_begin, item_end;
+  int64_t inst_base;        // scratch instance index of item 0 (volume: 0; side groups: n_elem + offset)
+  // tables (global memory): geometry shape functions and reference bases at this launch's points
+  const double* geo_N;      // [nq][nverts]
+  const double* geo_dN;     // [nq][nverts][dim]
+  const double* ref_tab;    // per basis [card][nq][ncb], concatenated in basis order
+  const double* qwts;       // [nq] reference weights
+  double tan_u[3], tan_v[3];  // side launches: reference side tangents
+  // dof bookkeeping: element-local dof of (var, basis function)
+  int16_t off[GEN_MAXVARS][GEN_MAXDOF];
+  // functions
+  GenFnRec fn[GEN_MAXFN];
+  const uint8_t* fn_op;
+  const double* fn_c;
+  GenOpts opt;
+  // side launches: boundary condition of each variable on this sideset and the index of its data function
+  int32_t bc_type[GEN_MAXVARS];
+  int32_t bc_fn[GEN_MAXVARS];
+  // outputs (scratch)
+  double* elem_jac;         // [n_inst][N][N]   may be null
+  double* elem_res;         // [n_inst][N]      may be null
+  int32_t epb;              // elements per CTA
+};
+
+// what the physics sees at one point
+struct QpCtx {
+  double x, y, z, t, w, h, dt;
+  double n[3];
+  const double* fn;         // function values at this point
+  int32_t transient, stage;
+  const int32_t* bc_type;
+};
+
+// ---- bytecode evaluation (same op set and order as volume_kernel.cuh / expr.cpp) ----------------------------
+MRH_HD double gen_expr_eval(const GenFnRec& f, const uint8_t* __restrict__ ops, const double* __restrict__ cs, const double (&var)[7]) {
+  if (f.is_const) return f.cval;
+  double st[16];
+  int sp = 0;
+  double a = 0.0;
+  for (int i = f.begin; i < f.begin + f.n; ++i) {
+    const double c = MRH_LDG(cs + i);
+    switch (MRH_LDG(ops + i)) {
+      case OP_PUSHC: st[sp & 15] = a; ++sp; a = c; break;
+      case OP_PUSHV: st[sp & 15] = a; ++sp; a = var[(int)c]; break;
+      case OP_ADD: --sp; a = st[sp & 15] + a; break;
+      case OP_SUB: --sp; a = st[sp & 15] + (-a); break;
+      case OP_MUL: --sp; a = st[sp & 15] * a; break;
+      case OP_DIV: --sp; a = st[sp & 15] / a; break;
+      case OP_POW: --sp; a = pow(st[sp & 15], a); break;
+      case OP_LT: --sp; a = st[sp & 15] < a ? 1.0 : 0.0; break;
+      case OP_LTE: --sp; a = st[sp & 15] <= a ? 1.0 : 0.0; break;
+      case OP_GT: --sp; a = st[sp & 15] > a ? 1.0 : 0.0; break;
+      case OP_GTE: --sp; a = st[sp & 15] >= a ? 1.0 : 0.0; break;
+      case OP_MAX: { --sp; const double l = st[sp & 15]; a = a > l ? a : l; } break;
+      case OP_MIN: { --sp; const double l = st[sp & 15]; a = a < l ? a : l; } break;
+      case OP_MEAN: --sp; a = 0.5 * st[sp & 15] + 0.5 * a; break;
+      case OP_ADDC: a = a + c; break;
+      case OP_SUBC: a = a + (-c); break;
+      case OP_MULC: a = a * c; break;
+      case OP_DIVC: a = a / c; break;
+      case OP_POWC: a = pow(a, c); break;
+      case OP_ADDV: a = a + var[(int)c]; break;
+      case OP_SUBV: a = a + (-var[(int)c]); break;
+      case OP_MULV: a = a * var[(int)c]; break;
+      case OP_DIVV: a = a / var[(int)c]; break;
+      case OP_SIN: a = sin(a); break;
+      case OP_COS: a = cos(a); break;
+      case OP_TAN: a = tan(a); break;
+      case OP_EXP: a = exp(a); break;
+      case OP_LOG: a = log(a); break;
+      case OP_ABS: a = a < 0.0 ? -a : a; break;
+      case OP_SQRT: a = a <= 0.0 ? 0.0 : sqrt(a); break;
+      case OP_SINH: a = sinh(a); break;
+      case OP_COSH: a = cosh(a); break;
+      default: break;
+    }
+  }
+  return a;
+}
+
+// computeSolnTransientSeeded folded into the gather (same formulas as volume_kernel.cuh: gather_dof)
+MRH_HD void gen_gather_dof(const double* __restrict__ sol, const TimeDev& td, int lid, double& u, double& ut) {
+  const double s = MRH_LDG(sol + lid);
+  u = s; ut = 0.0;
+  if (td.transient) {
+    const double p0 = MRH_LDG(td.prev[0] + lid);
+    double bu = td.one_minus_alpha_u * p0;
+    for (int k = 0; k < td.nstage_lo; ++k) bu += td.stage_w[k] * (MRH_LDG(td.stg[k] + lid) - p0);
+    u = td.alpha_u * s + bu;
+    double bt = td.bdf[1] * p0;
+    for (int k = 2; k <= td.nprev; ++k) bt += td.bdf[k] * MRH_LDG(td.prev[k - 1] + lid);
+    bt *= td.timewt;
+    ut = td.alpha_t * s + bt;
+  }
+}
+
+// ---- shared-memory layout of one element (offsets in doubles; every block is a multiple of 2 doubles) ---------
+template <class Phys, int NQ>
+struct GenLayout {
+  static constexpr int DIM = Phys::DIM, NV = 1 << DIM, NVAR = Phys::NVAR, NC = Phys::NC, NFN = Phys::NFN + GEN_MAXVARS;
+  static constexpr int N = Phys::N;
+  static constexpr int GEO = 28;   // w, x y z, Jinv[9], J[9], det, pad, n[3], pad
+  static MRH_CE int even(int x) { return (x + 1) & ~1; }
+  static MRH_CE int pb_size() { int s = 0; for (int b = 0; b < Phys::NBASIS; ++b) s += Phys::card(b) * NQ * Phys::ncb(b); return s; }
+  static MRH_CE int pb_off(int b) { int s = 0; for (int c = 0; c < b; ++c) s += Phys::card(c) * NQ * Phys::ncb(c); return s; }
+  static constexpr int U = 0;
+  static constexpr int UT = U + even(N);
+  static constexpr int VX = UT + even(N);
+  static constexpr int G = VX + even(NV * 3);
+  static constexpr int H = G + NQ * GEO;
+  static constexpr int PB = H + 2;
+  static constexpr int FV = PB + even(pb_size());
+  static constexpr int FT = FV + NQ * NVAR * NC;
+  static constexpr int FN = FT + NQ * NVAR * NC;
+  static constexpr int CV = FN + even(NQ * NFN);
+  static constexpr int SIZE = CV + NQ * NVAR * NC;
+};
+
+// ---- the stages ----------------------------------------------------------------------------------------------
+template <class Phys, int NQ, int K, bool SIDE>
+struct GenBlock {
+  typedef GenLayout<Phys, NQ> L;
+  static constexpr int DIM = Phys::DIM, NV = L::NV, N = L::N, NVAR = L::NVAR, NC = L::NC;
+  static constexpr int TPE = N / K;   // threads per element in the derivative stage
+  static_assert(N % K == 0, "K must divide the element dof count");
+
+  MRH_HD static int64_t item_of(const GenParams& P, int blk, int el) { return P.item_begin + (int64_t)blk * P.epb + el; }
+  MRH_HD static int32_t elem_of(const GenParams& P, int64_t item) { return SIDE ? MRH_LDG(P.items + item) : (int32_t)item; }
+
+  // S0: gather
+  MRH_HD static void s0(const GenParams& P, double* sm, int blk, int idx) {
+    if (idx < P.epb * N) {
+      const int el = idx / N, c = idx % N;
+      const int64_t item = item_of(P, blk, el);
+      double u = 0.0, ut = 0.0;
+      if (item < P.item_end) gen_gather_dof(P.sol, P.td, MRH_LDG(P.lids + (int64_t)elem_of(P, item) * N + c), u, ut);
+      sm[el * L::SIZE + L::U + c] = u;
+      sm[el * L::SIZE + L::UT + c] = ut;
+    }
+    if (idx < P.epb * NV) {
+      const int el = idx / NV, n = idx % NV;
+      const int64_t item = item_of(P, blk, el);
+      double x = 0.0, y = 0.0, z = 0.0;
+      if (item < P.item_end) {
+        const int32_t v = MRH_LDG(P.conn + (int64_t)elem_of(P, item) * NV + n);
+        x = MRH_LDG(P.vx + v); y = MRH_LDG(P.vy + v);
+        if (DIM == 3) z = MRH_LDG(P.vz + v);
+      } else {   // padding element: unit reference cell keeps every stage finite
+        x = (n & 1) ^ ((n >> 1) & 1) ? 1.0 : 0.0; y = (n >> 1) & 1 ? 1.0 : 0.0; z = (n >> 2) & 1 ? 1.0 : 0.0;
+      }
+      double* vxs = sm + el * L::SIZE + L::VX;
+      vxs[n * 3] = x; vxs[n * 3 + 1] = y; vxs[n * 3 + 2] = z;
+    }
+  }
+
+  // S1: geometry at (element, point)
+  MRH_HD static void s1(const GenParams& P, double* sm, int /*blk*/, int idx) {
+    if (idx >= P.epb * NQ) return;
+    const int el = idx / NQ, q = idx % NQ;
+    const double* vxs = sm + el * L::SIZE + L::VX;
+    double* g = sm + el * L::SIZE + L::G + q * L::GEO;
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, x[3] = {0, 0, 0};
+    for (int n = 0; n < NV; ++n) {
+      const double Nn = MRH_LDG(P.geo_N + q * NV + n);
+      for (int i = 0; i < DIM; ++i) {
+        x[i] += vxs[n * 3 + i] * Nn;
+        for (int j = 0; j < DIM; ++j) J[i][j] += vxs[n * 3 + i] * MRH_LDG(P.geo_dN + (q * NV + n) * DIM + j);
+      }
+    }
+    double Ji[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, det;
+    if (DIM == 2) {
+      det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
+    } else {
+      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+      Ji[0][0] = c00 / det; Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det; Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+      Ji[1][0] = c01 / det; Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+      Ji[2][0] = c02 / det; Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det; Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+    }
+    double w, nrm[3] = {0, 0, 0};
+    const double wr = MRH_LDG(P.qwts + q);
+    if (!SIDE) {
+      w = (det < 0.0 ? -det : det) * wr;
+    } else if (DIM == 2) {   // getPhysicalBoundaryIntegrationData: tangent -> rotated normal, measure = |tangent|
+      double t[2] = {0, 0};
+      for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i] += J[i][j] * P.tan_u[j];
+      nrm[0] = t[1]; nrm[1] = -t[0];
+      const double len = sqrt(t[0] * t[0] + t[1] * t[1]);
+      w = len * wr;
+      nrm[0] /= len; nrm[1] /= len;
+    } else {
+      double tu[3] = {0, 0, 0}, tv[3] = {0, 0, 0};
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { tu[i] += J[i][j] * P.tan_u[j]; tv[i] += J[i][j] * P.tan_v[j]; }
+      nrm[0] = tu[1] * tv[2] - tu[2] * tv[1];
+      nrm[1] = tu[2] * tv[0] - tu[0] * tv[2];
+      nrm[2] = tu[0] * tv[1] - tu[1] * tv[0];
+      const double len = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+      w = len * wr;
+      nrm[0] /= len; nrm[1] /= len; nrm[2] /= len;
+    }
+    g[0] = w; g[1] = x[0]; g[2] = x[1]; g[3] = x[2];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { g[4 + i * 3 + j] = Ji[i][j]; g[13 + i * 3 + j] = J[i][j]; }
+    g[22] = det; g[24] = nrm[0]; g[25] = nrm[1]; g[26] = nrm[2];
+  }
+
+  // S1b: element size h = (sum_q w)^(1/dim) (getElementSize, workset.cpp:2699-2712; side: ^(1/(dim-1)), :2718-2733)
+  MRH_HD static void s1b(const GenParams& P, double* sm, int /*blk*/, int idx) {
+    if (idx >= P.epb) return;
+    double vol = 0.0;
+    for (int q = 0; q < NQ; ++q) vol += sm[idx * L::SIZE + L::G + q * L::GEO];
+    sm[idx * L::SIZE + L::H] = pow(vol, 1.0 / (SIDE ? (double)DIM - 1.0 : (double)DIM));
+  }
+
+  // S2: push-forward of basis b, function i, at point q
+  template <int B>
+  MRH_HD static void s2_basis(const GenParams& P, double* sm, int blk, int idx) {
+    constexpr int CARD = Phys::card(B), NCB = Phys::ncb(B), BT = Phys::btype(B);
+    if (idx >= P.epb * CARD * NQ) return;
+    const int el = idx / (CARD * NQ), r = idx % (CARD * NQ), i = r / NQ, q = r % NQ;
+    const double* g = sm + el * L::SIZE + L::G + q * L::GEO;
+    const double* rt = P.ref_tab + L::pb_off(B) + (i * NQ + q) * NCB;
+    double* out = sm + el * L::SIZE + L::PB + L::pb_off(B) + (i * NQ + q) * NCB;
+    if (BT == BT_HGRAD) {
+      out[0] = MRH_LDG(rt);
+      for (int d = 0; d < 3; ++d) {
+        double s = 0.0;
+        for (int k = 0; k < DIM; ++k) s += g[4 + k * 3 + d] * MRH_LDG(rt + 1 + k);   // Jinv^T grad_ref
+        out[1 + d] = (d < DIM) ? s : 0.0;
+      }
+    } else {
+      double sg = 1.0;
+      if (P.orient) {
+        const int64_t item = item_of(P, blk, el);
+        if (item < P.item_end) sg = (double)MRH_LDG(P.orient + (int64_t)elem_of(P, item) * N + P.off[Phys::first_var(B)][i]);
+      }
+      const double det = g[22];
+      if (BT == BT_HCURL) {
+        for (int d = 0; d < 3; ++d) {
+          double s = 0.0, c = 0.0;
+          for (int k = 0; k < 3; ++k) { s += g[4 + k * 3 + d] * MRH_LDG(rt + k); c += g[13 + d * 3 + k] * MRH_LDG(rt + 3 + k); }
+          out[d] = sg * s; out[3 + d] = sg * c / det;
+        }
+      } else {  // HDIV
+        for (int d = 0; d < 3; ++d) {
+          double s = 0.0;
+          for (int k = 0; k < 3; ++k) s += g[13 + d * 3 + k] * MRH_LDG(rt + k);
+          out[d] = sg * s / det;
+        }
+        out[3] = sg * MRH_LDG(rt + 3) / det;
+      }
+    }
+  }
+  MRH_HD static void s2(const GenParams& P, double* sm, int blk, int idx) {
+    s2_basis<0>(P, sm, blk, idx);
+    if (Phys::NBASIS > 1) s2_basis<(Phys::NBASIS > 1 ? 1 : 0)>(P, sm, blk, idx);
+  }
+
+  // S3: fields and functions at (element, point)
+  template <int V>
+  MRH_HD static void s3_var(const GenParams& P, double* sme, int q) {
+    constexpr int B = Phys::var_basis(V), CARD = Phys::card(B), NCB = Phys::ncb(B), NVAL = Phys::nval(B);
+    double f[NC], ft[NC];
+    for (int k = 0; k < NC; ++k) { f[k] = 0.0; ft[k] = 0.0; }
+    const double* pb = sme + L::PB + L::pb_off(B) + q * NCB;
+    for (int i = 0; i < CARD; ++i) {
+      const int c = P.off[V][i];
+      const double u = sme[L::U + c], ut = sme[L::UT + c];
+      for (int k = 0; k < NCB; ++k) f[k] += u * pb[i * NQ * NCB + k];
+      for (int k = 0; k < NVAL; ++k) ft[k] += ut * pb[i * NQ * NCB + k];
+    }
+    for (int k = 0; k < NC; ++k) { sme[L::FV + (q * NVAR + V) * NC + k] = f[k]; sme[L::FT + (q * NVAR + V) * NC + k] = ft[k]; }
+  }
+  MRH_HD static void s3(const GenParams& P, double* sm, int /*blk*/, int idx) {
+    if (idx >= P.epb * NQ) return;
+    const int el = idx / NQ, q = idx % NQ;
+    double* sme = sm + el * L::SIZE;
+    s3_var<0>(P, sme, q);
+    if (NVAR > 1) s3_var<(NVAR > 1 ? 1 : 0)>(P, sme, q);
+    if (NVAR > 2) s3_var<(NVAR > 2 ? 2 : 0)>(P, sme, q);
+    if (NVAR > 3) s3_var<(NVAR > 3 ? 3 : 0)>(P, sme, q);
+    const double* g = sme + L::G + q * L::GEO;
+    const double var[7] = {g[1], g[2], g[3], P.td.time, g[24], g[25], g[26]};
+    for (int f = 0; f < Phys::NFN; ++f) sme[L::FN + q * L::NFN + f] = gen_expr_eval(P.fn[f], P.fn_op, P.fn_c, var);
+    for (int v = 0; v < NVAR; ++v) {   // boundary data of each variable on this sideset
+      double val = 0.0;
+      if (SIDE && P.bc_fn[v] >= 0) val = gen_expr_eval(P.fn[P.bc_fn[v]], P.fn_op, P.fn_c, var);
+      sme[L::FN + q * L::NFN + Phys::NFN + v] = val;
+    }
+  }
+
+  MRH_HD static void make_ctx(const GenParams& P, const double* sme, int q, QpCtx& c) {
+    const double* g = sme + L::G + q * L::GEO;
+    c.w = g[0]; c.x = g[1]; c.y = g[2]; c.z = g[3]; c.t = P.td.time; c.h = sme[L::H];
+    c.dt = P.td.deltat;
+    c.n[0] = g[24]; c.n[1] = g[25]; c.n[2] = g[26];
+    c.fn = sme + L::FN + q * L::NFN;
+    c.transient = P.td.transient; c.stage = P.td.nstage_lo;
+    c.bc_type = P.bc_type;
+  }
+
+  // S4a: coefficient values
+  MRH_HD static void s4a(const GenParams& P, double* sm, int /*blk*/, int idx) {
+    if (idx >= P.epb * NQ) return;
+    const int el = idx / NQ, q = idx % NQ;
+    double* sme = sm + el * L::SIZE;
+    QpCtx c;
+    make_ctx(P, sme, q, c);
+    double F[NVAR][NC], Ft[NVAR][NC], Cf[NVAR][NC];
+    for (int v = 0; v < NVAR; ++v)
+      for (int k = 0; k < NC; ++k) { F[v][k] = sme[L::FV + (q * NVAR + v) * NC + k]; Ft[v][k] = sme[L::FT + (q * NVAR + v) * NC + k]; Cf[v][k] = 0.0; }
+    if (SIDE) Phys::template boundary<double>(c, P.opt, F, Ft, Cf);
+    else Phys::template volume<double>(c, P.opt, F, Ft, Cf);
+    for (int v = 0; v < NVAR; ++v)
+      for (int k = 0; k < NC; ++k) sme[L::CV + (q * NVAR + v) * NC + k] = Cf[v][k];
+  }
+
+  // S4b: derivative components.  Thread (el, g) owns columns (WV, i0 .. i0+K-1), WV = variable of the group.
+  template <int WV>
+  MRH_HD static void s4b_var(const GenParams& P, double* sm, int blk, int el, int i0) {
+    constexpr int B = Phys::var_basis(WV), NCB = Phys::ncb(B), NVAL = Phys::nval(B);
+    const int64_t item = item_of(P, blk, el);
+    const double* sme = sm + el * L::SIZE;
+    double acc[N][K];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) acc[r][kk] = 0.0;
+    const double au = P.td.transient ? P.td.alpha_u : 1.0, at = P.td.transient ? P.td.alpha_t : 0.0;
+    for (int q = 0; q < NQ; ++q) {
+      QpCtx c;
+      make_ctx(P, sme, q, c);
+      Dual<K> F[NVAR][NC], Ft[NVAR][NC], Cf[NVAR][NC];
+#pragma unroll
+      for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          F[v][k] = Dual<K>(sme[L::FV + (q * NVAR + v) * NC + k]);
+          Ft[v][k] = Dual<K>(sme[L::FT + (q * NVAR + v) * NC + k]);
+          Cf[v][k] = Dual<K>(0.0);
+        }
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        const double* pb = sme + L::PB + L::pb_off(B) + ((i0 + kk) * NQ + q) * NCB;
+#pragma unroll
+        for (int k = 0; k < NCB; ++k) F[WV][k].d[kk] = au * pb[k];
+#pragma unroll
+        for (int k = 0; k < NVAL; ++k) Ft[WV][k].d[kk] = at * pb[k];
+      }
+      if (SIDE) Phys::template boundary<Dual<K>>(c, P.opt, F, Ft, Cf);
+      else Phys::template volume<Dual<K>>(c, P.opt, F, Ft, Cf);
+      // test-function loop: rows in (variable, basis function) order
+      s4b_rows_all(sme + L::PB, q, Cf, acc);
+    }
+    if (item < P.item_end && P.elem_jac) {
+      double* out = P.elem_jac + (P.inst_base + (item - P.item_begin)) * (int64_t)(N * N);
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        const int col = P.off[WV][i0 + kk];
+        store_rows(P, out, col, acc, kk);
+      }
+    }
+  }
+  template <int V>
+  MRH_HD static void store_var(const GenParams& P, double* out, int col, const double (&acc)[N][K], int kk) {
+    constexpr int CARD = Phys::card(Phys::var_basis(V)), R0 = Phys::row0(V);
+#pragma unroll
+    for (int i = 0; i < CARD; ++i) out[(int)P.off[V][i] * N + col] = acc[R0 + i][kk];
+  }
+  MRH_HD static void store_rows(const GenParams& P, double* out, int col, const double (&acc)[N][K], int kk) {
+    store_var<0>(P, out, col, acc, kk);
+    if (NVAR > 1) store_var<(NVAR > 1 ? 1 : 0)>(P, out, col, acc, kk);
+    if (NVAR > 2) store_var<(NVAR > 2 ? 2 : 0)>(P, out, col, acc, kk);
+    if (NVAR > 3) store_var<(NVAR > 3 ? 3 : 0)>(P, out, col, acc, kk);
+  }
+  template <int V>
+  MRH_HD static void rows_var(const double* __restrict__ pbase, int q, const Dual<K> (&Cf)[NVAR][NC], double (&acc)[N][K]) {
+    constexpr int B = Phys::var_basis(V), CARD = Phys::card(B), NCB = Phys::ncb(B), R0 = Phys::row0(V);
+    const double* pbq = pbase + L::pb_off(B) + q * NCB;
+#pragma unroll
+    for (int i = 0; i < CARD; ++i) {
+#pragma unroll
+      for (int k = 0; k < NCB; ++k) {
+        const double b = pbq[i * NQ * NCB + k];
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) acc[R0 + i][kk] += Cf[V][k].d[kk] * b;
+      }
+    }
+  }
+  MRH_HD static void s4b_rows_all(const double* __restrict__ pbase, int q, const Dual<K> (&Cf)[NVAR][NC], double (&acc)[N][K]) {
+    rows_var<0>(pbase, q, Cf, acc);
+    if (NVAR > 1) rows_var<(NVAR > 1 ? 1 : 0)>(pbase, q, Cf, acc);
+    if (NVAR > 2) rows_var<(NVAR > 2 ? 2 : 0)>(pbase, q, Cf, acc);
+    if (NVAR > 3) rows_var<(NVAR > 3 ? 3 : 0)>(pbase, q, Cf, acc);
+  }
+  MRH_HD static void s4b(const GenParams& P, double* sm, int blk, int idx) {
+    if (idx >= P.epb * TPE) return;
+    const int el = idx / TPE, g = idx % TPE;
+    // groups are numbered variable-major: variable v owns card(v)/K consecutive groups
+    int v = 0, g0 = 0;
+    for (; v < NVAR - 1; ++v) {
+      const int ng = Phys::card_of_var(v) / K;
+      if (g < g0 + ng) break;
+      g0 += ng;
+    }
+    const int i0 = (g - g0) * K;
+    switch (v) {
+      case 0: s4b_var<0>(P, sm, blk, el, i0); break;
+      case 1: s4b_var<(NVAR > 1 ? 1 : 0)>(P, sm, blk, el, i0); break;
+      case 2: s4b_var<(NVAR > 2 ? 2 : 0)>(P, sm, blk, el, i0); break;
+      default: s4b_var<(NVAR > 3 ? 3 : 0)>(P, sm, blk, el, i0); break;
+    }
+  }
+
+  // S5: residual rows
+  MRH_HD static void s5(const GenParams& P, double* sm, int blk, int idx) {
+    if (idx >= P.epb * N || !P.elem_res) return;
+    const int el = idx / N, r = idx % N;
+    const int64_t item = item_of(P, blk, el);
+    if (item >= P.item_end) return;
+    // r is numbered variable-major (v, i); the element-local dof is off[v][i]
+    int v = 0, r0 = 0;
+    for (; v < NVAR - 1; ++v) {
+      if (r < r0 + Phys::card_of_var(v)) break;
+      r0 += Phys::card_of_var(v);
+    }
+    const int i = r - r0;
+    const int b = Phys::var_basis_rt(v), ncb = Phys::ncb_rt(b);
+    const double* sme = sm + el * L::SIZE;
+    const double* pb = sme + L::PB + L::pb_off(b) + i * NQ * ncb;
+    double s = 0.0;
+    for (int q = 0; q < NQ; ++q)
+      for (int k = 0; k < ncb; ++k) s += sme[L::CV + (q * NVAR + v) * NC + k] * pb[q * ncb + k];
+    P.elem_res[(P.inst_base + (item - P.item_begin)) * (int64_t)N + P.off[v][i]] = s;
+  }
+};
+
+#if defined(__CUDACC__)
+template <class Phys, int NQ, int K, bool SIDE>
+__global__ void __launch_bounds__(256) gen_element_kernel(const __grid_constant__ GenParams P) {
+  extern __shared__ __align__(16) double gen_smem[];
+  typedef GenBlock<Phys, NQ, K, SIDE> Bk;
+  const int blk = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
+  typedef GenLayout<Phys, NQ> L;
+  for (int i = tid; i < P.epb * (L::N > L::NV ? L::N : L::NV); i += T) Bk::s0(P, gen_smem, blk, i);
+  __syncthreads();
+  for (int i = tid; i < P.epb * NQ; i += T) Bk::s1(P, gen_smem, blk, i);
+  __syncthreads();
+  for (int i = tid; i < P.epb; i += T) Bk::s1b(P, gen_smem, blk, i);
+  for (int i = tid; i < P.epb * Phys::max_card() * NQ; i += T) Bk::s2(P, gen_smem, blk, i);
+  __syncthreads();
+  for (int i = tid; i < P.epb * NQ; i += T) Bk::s3(P, gen_smem, blk, i);
+  __syncthreads();
+  for (int i = tid; i < P.epb * NQ; i += T) Bk::s4a(P, gen_smem, blk, i);
+  if (P.elem_jac)
+    for (int i = tid; i < P.epb * Bk::TPE; i += T) Bk::s4b(P, gen_smem, blk, i);
+  __syncthreads();
+  for (int i = tid; i < P.epb * L::N; i += T) Bk::s5(P, gen_smem, blk, i);
+}
+#endif
+
+}  // namespace mrhyde_b200

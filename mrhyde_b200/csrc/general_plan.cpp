@@ -1,0 +1,144 @@
+// Plan-time analysis of the general path's deterministic pull (see general.hpp).
+//
+// The reference adds element matrices into the CSR matrix entry by entry with a linear search per entry and
+// atomics when threaded (assemblyManager_scatter.hpp:191-278).  Here every (instance, local row) pair is listed
+// under its global row in ascending instance order -- volume elements in element order, then boundary sides in
+// boundary-group order, which is the order the serial reference adds them (assemblyManager_jacres.hpp:336-603) --
+// and the position of every local column inside that CSR row is tabulated once (uint16).
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+
+#include "general.hpp"
+
+namespace mrhyde_b200 {
+
+void gen_build_pull(const MeshGraph& m, int N, const std::vector<GenSideFamily>& sides, int64_t batch_elems, GeneralPlanHost& out) {
+  const int64_t ne = m.nelem;
+  int64_t n_inst = ne;
+  for (auto& s : sides) if (s.active) n_inst += (int64_t)s.items.size();
+  if (n_inst * N > 0x7fffffffLL) throw std::runtime_error("general plan: element instances x dofs exceed the 32-bit contribution index");
+  out.n_elem = ne; out.n_inst = n_inst; out.n_rows = m.nrows; out.n_owned = m.nowned;
+  // instance -> element
+  std::vector<int32_t> inst_elem((size_t)n_inst);
+  for (int64_t e = 0; e < ne; ++e) inst_elem[(size_t)e] = (int32_t)e;
+  for (auto& s : sides) {
+    if (!s.active) continue;
+    for (size_t k = 0; k < s.items.size(); ++k) inst_elem[(size_t)(s.inst_base + (int64_t)k)] = s.items[k];
+  }
+  // rows -> (instance, local row) lists, ascending instance; completion instance of every row
+  std::vector<int64_t> cnt((size_t)m.nrows + 1, 0);
+  for (int64_t t = 0; t < n_inst; ++t) {
+    const int32_t* l = &m.lids[(size_t)inst_elem[(size_t)t] * N];
+    for (int i = 0; i < N; ++i) ++cnt[(size_t)l[i] + 1];
+  }
+  for (int64_t r = 0; r < m.nrows; ++r) cnt[(size_t)r + 1] += cnt[(size_t)r];
+  std::vector<int32_t> contrib_by_row((size_t)cnt[(size_t)m.nrows]);
+  std::vector<int64_t> fill(cnt.begin(), cnt.end() - 1);
+  std::vector<int64_t> last_inst((size_t)m.nrows, -1);
+  for (int64_t t = 0; t < n_inst; ++t) {
+    const int32_t* l = &m.lids[(size_t)inst_elem[(size_t)t] * N];
+    for (int i = 0; i < N; ++i) {
+      for (int j = 0; j < i; ++j)
+        if (l[j] == l[i]) throw std::runtime_error("general plan: an element lists the same dof twice (degenerate periodic mesh?)");
+      contrib_by_row[(size_t)fill[(size_t)l[i]]++] = (int32_t)(t * N + i);
+      last_inst[(size_t)l[i]] = t;
+    }
+  }
+  // volume batches over elements
+  out.batches.clear();
+  if (batch_elems <= 0 || batch_elems > ne) batch_elems = std::max<int64_t>(ne, 1);
+  for (int64_t e0 = 0; e0 < ne; e0 += batch_elems) {
+    GenBatch b;
+    b.elem_begin = e0; b.elem_end = std::min(ne, e0 + batch_elems);
+    out.batches.push_back(b);
+  }
+  if (out.batches.empty()) out.batches.push_back(GenBatch());
+  const int nb = (int)out.batches.size();
+  auto batch_of = [&](int64_t inst) -> int {
+    if (inst < 0) return 0;
+    if (inst >= ne) return nb - 1;
+    return (int)std::min<int64_t>(inst / batch_elems, nb - 1);
+  };
+  // rows sorted by completion batch (stable: ascending row inside a batch)
+  std::vector<int64_t> bcount((size_t)nb + 1, 0);
+  for (int64_t r = 0; r < m.nrows; ++r) ++bcount[(size_t)batch_of(last_inst[(size_t)r]) + 1];
+  for (int b = 0; b < nb; ++b) bcount[(size_t)b + 1] += bcount[(size_t)b];
+  for (int b = 0; b < nb; ++b) { out.batches[(size_t)b].row_begin = bcount[(size_t)b]; out.batches[(size_t)b].row_end = bcount[(size_t)b + 1]; }
+  out.row_order.assign((size_t)m.nrows, 0);
+  {
+    std::vector<int64_t> bf(bcount.begin(), bcount.end() - 1);
+    for (int64_t r = 0; r < m.nrows; ++r) out.row_order[(size_t)bf[(size_t)batch_of(last_inst[(size_t)r])]++] = (int32_t)r;
+  }
+  out.contrib_ptr.assign((size_t)m.nrows + 1, 0);
+  out.contrib.resize(contrib_by_row.size());
+  int64_t w = 0;
+  int32_t maxlen = 0;
+  for (int64_t k = 0; k < m.nrows; ++k) {
+    const int32_t r = out.row_order[(size_t)k];
+    out.contrib_ptr[(size_t)k] = w;
+    for (int64_t p = cnt[(size_t)r]; p < cnt[(size_t)r + 1]; ++p) out.contrib[(size_t)w++] = contrib_by_row[(size_t)p];
+    maxlen = std::max<int32_t>(maxlen, (int32_t)(m.rowptr[(size_t)r + 1] - m.rowptr[(size_t)r]));
+  }
+  out.contrib_ptr[(size_t)m.nrows] = w;
+  out.max_row_len = maxlen;
+  if (maxlen > 0xffff) throw std::runtime_error("general plan: CSR rows longer than 65535 entries");
+  // column positions
+  out.pos.assign((size_t)n_inst * N * N, 0);
+  std::string err;
+  auto work = [&](int64_t t0, int64_t t1) {
+    for (int64_t t = t0; t < t1; ++t) {
+      const int32_t* l = &m.lids[(size_t)inst_elem[(size_t)t] * N];
+      for (int i = 0; i < N; ++i) {
+        const int64_t rs = m.rowptr[(size_t)l[i]], re = m.rowptr[(size_t)l[i] + 1];
+        const int32_t* cb = &m.colind[(size_t)rs];
+        const int32_t* ce = cb + (re - rs);
+        const bool sorted = std::is_sorted(cb, ce);
+        for (int c = 0; c < N; ++c) {
+          const int32_t* f = sorted ? std::lower_bound(cb, ce, l[c]) : std::find(cb, ce, l[c]);
+          if (f == ce || *f != l[c]) { err = "general plan: the CSR graph lacks an entry for a column of one of the row's elements"; return; }
+          out.pos[((size_t)t * N + i) * N + c] = (uint16_t)(f - cb);
+        }
+      }
+    }
+  };
+  const unsigned nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n_inst * (int64_t)N * N < (1 << 22) || nth == 1) work(0, n_inst);
+  else {
+    std::vector<std::thread> th;
+    const int64_t chunk = (n_inst + nth - 1) / nth;
+    for (unsigned k = 0; k < nth; ++k) th.emplace_back(work, std::min<int64_t>(n_inst, k * chunk), std::min<int64_t>(n_inst, (k + 1) * chunk));
+    for (auto& t : th) t.join();
+  }
+  if (!err.empty()) throw std::runtime_error(err);
+}
+
+void gen_pull_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, const double* elem_res, bool accumulate,
+                   double* res, double* jac) {
+  const int N = H.info.N;
+  std::vector<double> buf((size_t)std::max(1, H.max_row_len));
+  for (int64_t k = 0; k < H.n_rows; ++k) {
+    const int32_t r = H.row_order[(size_t)k];
+    const int64_t rs = m.rowptr[(size_t)r];
+    const int len = (int)(m.rowptr[(size_t)r + 1] - rs);
+    if (m.fixed[(size_t)r]) {
+      if (!accumulate) {
+        if (res) res[r] = 0.0;
+        if (jac) for (int t = 0; t < len; ++t) jac[rs + t] = (m.colind[(size_t)(rs + t)] == r && r < m.nowned) ? 1.0 : 0.0;
+      }
+      continue;
+    }
+    for (int t = 0; t < len; ++t) buf[(size_t)t] = 0.0;
+    double rsum = 0.0;
+    for (int64_t p = H.contrib_ptr[(size_t)k]; p < H.contrib_ptr[(size_t)k + 1]; ++p) {
+      const int64_t ci = H.contrib[(size_t)p];
+      if (elem_jac && jac) for (int c = 0; c < N; ++c) buf[H.pos[(size_t)(ci * N + c)]] += elem_jac[ci * N + c];
+      if (elem_res) rsum += elem_res[ci];
+    }
+    if (jac) for (int t = 0; t < len; ++t) jac[rs + t] = (accumulate ? jac[rs + t] : 0.0) + buf[(size_t)t];
+    if (res) res[r] = (accumulate ? res[r] : 0.0) + (-rsum);
+  }
+}
+
+}  // namespace mrhyde_b200

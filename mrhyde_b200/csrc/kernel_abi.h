@@ -113,6 +113,7 @@ struct TimeDev {
   double time;                   // stage time
   const double* prev[MAX_PREV];
   const double* stg[MAX_STAGE];
+  double deltat;                 // time step (1 when steady)
 };
 
 // ---- thermal, HGRAD Q1 ----------------------------------------------------------------------------------

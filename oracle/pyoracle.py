@@ -147,8 +147,8 @@ class OracleProblem:
         self.L.oracle_get_side_rule(self.h, side, _p(pts, C.c_double), _p(wts, C.c_double), _p(tu, C.c_double), _p(tv, C.c_double))
         return pts, wts, tu, tv
 
-    def ref_basis_side(self, side, b, card, has_grad=True):
-        val = np.zeros((card, self.nqp_side, 1))
+    def ref_basis_side(self, side, b, card, has_grad=True, vdim=1):
+        val = np.zeros((card, self.nqp_side, vdim))
         grad = np.zeros((card, self.nqp_side, self.dim)) if has_grad else None
         self.L.oracle_get_ref_basis_side(self.h, side, b, _p(val, C.c_double), _p(grad, C.c_double))
         return val, grad

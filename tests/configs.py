@@ -41,3 +41,89 @@ def variant(base, **updates):
         else:
             node[parts[-1]] = val
     return cfg
+
+
+# ---- decks for the other modules on the path (synthetic; coefficient choices exercise every term) ------------------
+LE_3D = {
+    "Mesh": {"dimension": 3, "NX": 4, "NY": 3, "NZ": 3, "perturb": 0.03},
+    "Physics": {"modules": "linearelasticity",
+                "Dirichlet conditions": {"dx": {"all boundaries": "0.0"}, "dy": {"all boundaries": "0.0"}, "dz": {"all boundaries": "0.0"}}},
+    "Functions": {"lambda": "1.0+0.3*x", "mu": "1.0", "A": "1.0", "source dx": "sin(A*pi*x)*y", "source dy": "lambda*z", "source dz": "1.0-x*y"},
+    "Discretization": {"order": {"dx": 1, "dy": 1, "dz": 1}, "quadrature": 2},
+    "Solver": {"solver": "steady-state"},
+}
+LE_2D = {
+    "Mesh": {"dimension": 2, "NX": 6, "NY": 5, "perturb": 0.03},
+    "Physics": {"modules": "linearelasticity", "Dirichlet conditions": {"dx": {"all boundaries": "0.0"}, "dy": {"all boundaries": "0.0"}}},
+    "Functions": {"lambda": "2.0", "mu": "0.7", "source dx": "x*y", "source dy": "1.0"},
+    "Discretization": {"order": {"dx": 1, "dy": 1}, "quadrature": 2},
+    "Solver": {"solver": "steady-state"},
+}
+LE_3D_WEAK = {"Solver/use strong DBCs": False,
+              "Physics/Dirichlet conditions": {"dx": {"left": "0.1*y", "top": "0.0"}, "dy": {"left": "0.0", "top": "x"}, "dz": {"left": "0.0", "top": "0.2"}},
+              "Physics/Neumann conditions": {"dx": {"right": "1.0"}, "dy": {"right": "y"}, "dz": {"right": "0.0"}}}
+LE_2D_WEAK = {"Solver/use strong DBCs": False,
+              "Physics/Dirichlet conditions": {"dx": {"left": "0.1*y", "top": "0.0"}, "dy": {"left": "0.0", "top": "x"}},
+              "Physics/Neumann conditions": {"dx": {"right": "1.0"}, "dy": {"right": "y"}}}
+NS_2D = {
+    "Mesh": {"dimension": 2, "NX": 6, "NY": 5, "perturb": 0.02},
+    "Physics": {"modules": "navier stokes", "useSUPG": True, "usePSPG": True,
+                "Dirichlet conditions": {"ux": {"left": "1.0", "top": "0.0", "bottom": "0.0"}, "uy": {"left": "0.0", "top": "0.0", "bottom": "0.0"},
+                                         "pr": {"right": "0.0"}}},
+    "Functions": {"source ux": "1.0", "viscosity": "0.5", "density": "1.3"},
+    "Discretization": {"order": {"ux": 1, "pr": 1, "uy": 1}, "quadrature": 2},
+    "Solver": {"solver": "steady-state"},
+}
+NS_3D = {
+    "Mesh": {"dimension": 3, "NX": 4, "NY": 3, "NZ": 3, "perturb": 0.02},
+    "Physics": {"modules": "navier stokes", "useSUPG": True, "usePSPG": True,
+                "Dirichlet conditions": {"ux": {"all boundaries": "0.0"}, "uy": {"all boundaries": "0.0"}, "uz": {"all boundaries": "0.0"}}},
+    "Functions": {"source ux": "1.0", "source uz": "x"},
+    "Discretization": {"order": {"ux": 1, "pr": 1, "uy": 1, "uz": 1}, "quadrature": 2},
+    "Solver": {"solver": "steady-state"},
+}
+NS_3D_NEUMANN = {"Physics/Dirichlet conditions": {"ux": {"left": "1.0"}, "uy": {"left": "0.0"}, "uz": {"left": "0.0"}},
+                 "Physics/Neumann conditions": {"ux": {"right": "0.3"}, "uy": {"right": "y"}, "uz": {"top": "1.0"}}}
+MAXWELL_3D = {
+    "Mesh": {"dimension": 3, "NX": 3, "NY": 3, "NZ": 4, "perturb": 0.02},
+    "Physics": {"modules": "maxwell", "Dirichlet conditions": {"E": {"all boundaries": "0.0"}}},
+    "Functions": {"current x": "sin(t)*y", "permittivity": "1.5", "permeability": "0.8", "conductivity": "0.2", "refractive index": "1.1"},
+    "Discretization": {"order": {"E": 1, "B": 1}, "quadrature": 2},
+    "Solver": {"solver": "transient"},
+}
+MAXWELL_ABC = {"Physics/Dirichlet conditions": {"E": {"left": "0.0"}}, "Physics/Neumann conditions": {"B": {"right": "0.0", "top": "0.0", "front": "0.0"}}}
+THERMAL_WEAK = {"Solver/use strong DBCs": False, "Physics/assemble boundary terms": True, "Mesh/NX": 6, "Mesh/NY": 5, "Mesh/perturb": 0.01,
+                "Physics/Dirichlet conditions/T": {"left": "1.0+y", "top": "x*x"}, "Physics/Neumann conditions/T": {"right": "2.0*y-0.3"}}
+BWE = ([[1.0]], [1.0], [1.0], 0)
+DIRK12 = ([[0.5]], [1.0], [0.5], 0)
+
+
+def general_cases():
+    """(name, deck, plan options, transient tableau or None, zero state?) for the general path's parity tests."""
+    t3 = variant(THERMAL_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3, "Mesh/perturb": 0.03})
+    return [
+        ("thermal3d", t3, {}, None, False),
+        ("thermal3d-dirk", t3, {}, DIRK12, False),
+        ("thermal2d-weak-neumann", variant(THERMAL_2D, **THERMAL_WEAK), {}, None, False),
+        ("thermal3d-weak-neumann", variant(THERMAL_3D, **dict(THERMAL_WEAK, **{"Mesh/NZ": 4})), {}, None, False),
+        ("thermal3d-advection", variant(t3, **{"Physics/include advection": True, "Functions/advection x": "1.0+y", "Functions/advection y": "x",
+                                               "Functions/advection z": "0.5"}), {}, None, False),
+        ("thermal3d-q2", variant(t3, **{"Discretization/order/T": 2, "Discretization/quadrature": 4}), {}, None, False),
+        ("le3d", LE_3D, {}, None, False),
+        ("le2d", LE_2D, {}, None, False),
+        ("le2d-planestress", variant(LE_2D, **{"Physics/incplanestress": True}), {}, None, False),
+        ("le3d-q2", variant(LE_3D, **{"Discretization/order": {"dx": 2, "dy": 2, "dz": 2}, "Discretization/quadrature": 4, "Mesh/NX": 2, "Mesh/NY": 2, "Mesh/NZ": 2}), {}, None, False),
+        ("le3d-weak-neumann", variant(LE_3D, **LE_3D_WEAK), {}, None, False),
+        ("le2d-weak-neumann", variant(LE_2D, **LE_2D_WEAK), {}, None, False),
+        ("ns2d-supg-pspg", NS_2D, {}, None, False),
+        ("ns2d-galerkin", variant(NS_2D, **{"Physics/useSUPG": False, "Physics/usePSPG": False}), {}, None, False),
+        ("ns2d-bwe", NS_2D, {}, BWE, False),
+        ("ns3d-reference-uz-rows", NS_3D, {}, None, False),
+        ("ns3d-corrected-uz-rows", variant(NS_3D, **{"Physics/ns3d_uz_rows": "corrected"}), {}, None, False),
+        ("ns3d-stagnation-tau-branch", NS_3D, {}, None, True),
+        ("ns3d-neumann", variant(NS_3D, **NS_3D_NEUMANN), {}, None, False),
+        ("maxwell-steady", MAXWELL_3D, {}, None, False),
+        ("maxwell-dirk", MAXWELL_3D, {}, DIRK12, False),
+        ("maxwell-abc-bwe", variant(MAXWELL_3D, **MAXWELL_ABC), {}, BWE, False),
+        ("le3d-batched", variant(LE_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 4}), {"batch elems": 16}, None, False),
+    ]

@@ -14,8 +14,10 @@ DEFAULT_OPTIONS = {}   # plan options every plan_from_oracle call applies first 
 def plan_from_oracle(op, cfg, device=0, options=None, indexed=False):
     """AssemblyPlan for the block the OracleProblem `op` describes (cfg = its input deck)."""
     bases = []
+    rb_vdim = []
     for b in range(op.nbases):
         rb = op.ref_basis(b)
+        rb_vdim.append(rb["vdim"])
         bases.append(dict(type=op.basis_type(b), order=op.basis_order(b), card=rb["card"], val=rb["val"], grad=rb["grad"], curl=rb["curl"], div=rb["div"]))
     names = op.var_names()
     plan = AssemblyPlan(op.modules(), op.dim, names, op.usebasis, bases, op.ndof_elem, op.offsets, op.qpts, op.qwts, device=device)
@@ -23,7 +25,8 @@ def plan_from_oracle(op, cfg, device=0, options=None, indexed=False):
         plan.set_function(k, v)
     phys = cfg.get("Physics", {})
     solver = cfg.get("Solver", {})
-    for key in ("form_param", "include advection", "useSUPG", "usePSPG", "assemble boundary terms", "assemble volume terms"):
+    for key in ("form_param", "include advection", "useSUPG", "usePSPG", "assemble boundary terms", "assemble volume terms", "penalty",
+                "incplanestress", "ns3d_uz_rows", "use leap frog"):
         if key in phys:
             plan.set_option(key, phys[key])
     if "use strong DBCs" in solver:
@@ -49,7 +52,7 @@ def plan_from_oracle(op, cfg, device=0, options=None, indexed=False):
         side_bases = []
         for b in range(op.nbases):
             card = bases[b]["card"]
-            val, grad = op.ref_basis_side(bg["local_side"], b, card, has_grad=bases[b]["grad"] is not None)
+            val, grad = op.ref_basis_side(bg["local_side"], b, card, has_grad=bases[b]["grad"] is not None, vdim=rb_vdim[b])
             side_bases.append(dict(type=bases[b]["type"], order=bases[b]["order"], card=card, val=val, grad=grad))
         plan.add_boundary_group(bg["sideset"], bg["local_side"], bg["elem_ids"], pts, wts, tu, tv, side_bases)
     plan.finalize()

@@ -1,0 +1,74 @@
+"""CPU checks of the general path's kernel logic: mrhyde_b200_plan_debug_emulate replays the stage functions of
+general_kernel.cuh (the source the CUDA build compiles) and the pull on a host-only plan, and the result is compared
+with the oracle to the north_star tolerance.  This is a debugging aid for machines without a GPU -- the assemble entry
+points refuse host-only plans (asserted below); the parity tests proper are tests/test_gpu_general.py."""
+import numpy as np
+import pytest
+
+import configs
+import helpers
+
+TOL = 1e-12
+
+
+def _setup_time(op, tableau):
+    if tableau is None:
+        return None, {}
+    A, b, c, stage = tableau
+    rng = np.random.default_rng(5)
+    up, us = 0.1 * rng.standard_normal(op.num_dofs), 0.1 * rng.standard_normal(op.num_dofs)
+    op.set_time(True, time=0.3, dt=0.01, stage=stage, A=A, b=b, c=c, bdf=(1.0, -1.0))
+    ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=stage, A=A, b=b, c=c, bdf=(1.0, -1.0), sol_prev=[up], sol_stage=[us] * len(b))
+    return ts, dict(sol_prev=[up], sol_stage=[us] * len(b))
+
+
+@pytest.mark.parametrize("name,cfg,opts,tableau,zero", configs.general_cases(), ids=[c[0] for c in configs.general_cases()])
+def test_kernel_stages_match_oracle(oracle_lib, product_lib, name, cfg, opts, tableau, zero):
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options=dict({"kernel": "general"}, **opts))
+    assert plan.stat("general") == 1
+    u = np.zeros(op.num_dofs) if zero else helpers.manufactured_state(op)
+    ts, kw = _setup_time(op, tableau)
+    res_ref, jac_ref = op.assemble_jacres(u, **kw)
+    res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+    plan.debug_emulate(u, res, jac, time=ts)
+    op.set_time(False)
+    assert helpers.rel_err_vec(res, res_ref) < TOL
+    assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL
+    if "batched" in name:
+        assert plan.stat("general_batches") > 1
+
+
+def test_host_only_plan_cannot_assemble(oracle_lib, product_lib):
+    from mrhyde_b200.capi import MrhydeB200Error
+    op = oracle_lib.OracleProblem(configs.LE_2D)
+    plan = helpers.plan_from_oracle(op, configs.LE_2D, device=-1)
+    res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+    with pytest.raises(MrhydeB200Error):
+        plan.assemble_jacres_host(np.zeros(op.num_dofs), res, jac)
+
+
+def test_residual_only_and_overwrite_modes(oracle_lib, product_lib):
+    cfg = configs.NS_2D
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options={"kernel": "general"})
+    u = helpers.manufactured_state(op)
+    res_ref = op.assemble_res(u)                      # the ScalarT workset path
+    res = np.zeros(op.num_dofs)
+    plan.debug_emulate(u, res, None, compute_jacobian=False)
+    assert helpers.rel_err_vec(res, res_ref) < TOL
+    r1, j1 = np.zeros(op.num_dofs), np.zeros(op.nnz)
+    plan.debug_emulate(u, r1, j1)
+    plan.set_option("accumulate", "false")
+    r2, j2 = np.full(op.num_dofs, 7.0), np.full(op.nnz, -3.0)
+    plan.debug_emulate(u, r2, j2)
+    assert np.array_equal(r1, r2) and np.array_equal(j1, j2)
+
+
+def test_unsupported_configuration_is_an_error(oracle_lib, product_lib):
+    from mrhyde_b200.capi import MrhydeB200Error
+    cfg = configs.variant(configs.LE_2D, **{"Discretization/quadrature": 6})   # 4x4 Gauss points: no kernel built
+    op = oracle_lib.OracleProblem(cfg)
+    with pytest.raises(MrhydeB200Error) as e:
+        helpers.plan_from_oracle(op, cfg, device=-1)
+    assert "no kernel" in str(e.value)

@@ -1,0 +1,128 @@
+"""GPU parity tests of the general path (element kernel + pull, general_kernel.cuh / general.cu) through the C ABI:
+thermal (incl. advection, Q2), linear elasticity (Q1/Q2, plane stress, Nitsche + traction sides), Navier-Stokes
+(SUPG/PSPG, the navierstokes.cpp:688 uz-row behaviour in both modes, the computeTau stagnation branch, Neumann sides)
+and Maxwell (HCURL/HDIV, DIRK stage, ABC sides) against the CPU oracle on the same seeded inputs.
+Tolerance (north_star): 1e-12 relative on residual entries (vector max-norm) and matrix values (row max-norm);
+the CSR pattern is an input, hence identical."""
+import numpy as np
+import pytest
+
+import configs
+import helpers
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.device("cuda:0"))
+
+
+def _time(op, tableau):
+    if tableau is None:
+        return None, {}
+    A, b, c, stage = tableau
+    rng = np.random.default_rng(5)
+    up, us = 0.1 * rng.standard_normal(op.num_dofs), 0.1 * rng.standard_normal(op.num_dofs)
+    op.set_time(True, time=0.3, dt=0.01, stage=stage, A=A, b=b, c=c, bdf=(1.0, -1.0))
+    d_up, d_us = _dev(up), _dev(us)
+    ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=stage, A=A, b=b, c=c, bdf=(1.0, -1.0), sol_prev=[d_up], sol_stage=[d_us] * len(b))
+    return ts, dict(sol_prev=[up], sol_stage=[us] * len(b))
+
+
+def _assemble(plan, op, u, ts=None, **kw):
+    import torch
+    d_u = _dev(u)
+    d_res = torch.zeros(op.num_dofs, dtype=torch.float64, device=d_u.device)
+    d_jac = torch.zeros(op.nnz, dtype=torch.float64, device=d_u.device)
+    plan.assemble_jacres(d_u, d_res, d_jac, time=ts, **kw)
+    torch.cuda.synchronize()
+    return d_res.cpu().numpy(), d_jac.cpu().numpy()
+
+
+@pytest.mark.parametrize("name,cfg,opts,tableau,zero", configs.general_cases(), ids=[c[0] for c in configs.general_cases()])
+def test_general_path_matches_oracle(oracle_lib, product_lib, name, cfg, opts, tableau, zero):
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, options=dict({"kernel": "general"}, **opts))
+    assert plan.stat("general") == 1
+    u = np.zeros(op.num_dofs) if zero else helpers.manufactured_state(op)
+    ts, kw = _time(op, tableau)
+    res_ref, jac_ref = op.assemble_jacres(u, **kw)
+    res, jac = _assemble(plan, op, u, ts)
+    op.set_time(False)
+    e_res, e_jac = helpers.rel_err_vec(res, res_ref), helpers.rel_err_rows(jac, jac_ref, op.rowptr)
+    assert e_res < TOL, "residual rel err %.3e" % e_res
+    assert e_jac < TOL, "Jacobian rel err %.3e" % e_jac
+
+
+def test_default_kernel_choice(oracle_lib, product_lib):
+    """thermal HGRAD-1 takes the sweep kernel by default, every other module the general path."""
+    op = oracle_lib.OracleProblem(configs.THERMAL_3D)
+    assert helpers.plan_from_oracle(op, configs.THERMAL_3D).stat("general") == 0
+    op = oracle_lib.OracleProblem(configs.LE_3D)
+    assert helpers.plan_from_oracle(op, configs.LE_3D).stat("general") == 1
+
+
+def test_general_and_sweep_kernels_agree_on_thermal(oracle_lib, product_lib):
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 12, "Mesh/NY": 9, "Mesh/NZ": 7, "Mesh/perturb": 0.02, "Functions/thermal diffusion": "1.0+x*y"})
+    op = oracle_lib.OracleProblem(cfg)
+    u = helpers.manufactured_state(op)
+    r1, j1 = _assemble(helpers.plan_from_oracle(op, cfg), op, u)
+    r2, j2 = _assemble(helpers.plan_from_oracle(op, cfg, options={"kernel": "general"}), op, u)
+    assert helpers.rel_err_vec(r2, r1) < TOL and helpers.rel_err_rows(j2, j1, op.rowptr) < TOL
+
+
+@pytest.mark.parametrize("cfg", [configs.NS_3D, configs.MAXWELL_3D], ids=["ns3d", "maxwell"])
+def test_modes_and_reproducibility(oracle_lib, product_lib, cfg):
+    """residual-only (ScalarT path), Jacobian-only (autotune flow), overwrite == accumulate on zeroed arrays, and
+    bit-identical results run to run (the pull sums in a fixed order, no atomics)."""
+    import torch
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, options={"batch elems": 8})
+    u = helpers.manufactured_state(op)
+    r1, j1 = _assemble(plan, op, u)
+    r1b, j1b = _assemble(plan, op, u)
+    assert np.array_equal(r1, r1b) and np.array_equal(j1, j1b)
+    d_u = _dev(u)
+    d_res = torch.zeros(op.num_dofs, dtype=torch.float64, device=d_u.device)
+    plan.assemble_res(d_u, d_res)
+    torch.cuda.synchronize()
+    assert helpers.rel_err_vec(d_res.cpu().numpy(), op.assemble_res(u)) < TOL
+    assert np.array_equal(d_res.cpu().numpy(), r1)
+    d_jac = torch.zeros(op.nnz, dtype=torch.float64, device=d_u.device)
+    plan.assemble_jacres(d_u, None, d_jac, compute_residual=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_jac.cpu().numpy(), j1)
+    plan.set_option("accumulate", "false")
+    d_res.fill_(7.0)
+    d_jac.fill_(-3.0)
+    plan.assemble_jacres(d_u, d_res, d_jac)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_res.cpu().numpy(), r1) and np.array_equal(d_jac.cpu().numpy(), j1)
+
+
+def test_le_q1_properties_at_scale(product_lib, oracle_lib):
+    """48^3 hex-Q1 elasticity (too slow for the oracle's per-entry search in a unit test): rigid-body modes lie in the
+    null space of the free-free stiffness rows, the free-free block is symmetric, res(u) = res(0) - J u."""
+    import torch
+    n = 24
+    cfg = configs.variant(configs.LE_3D, **{"Mesh/NX": n, "Mesh/NY": n, "Mesh/NZ": n, "Mesh/perturb": 0.0, "Functions/lambda": "1.3", "Functions/mu": "0.9"})
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    u = helpers.manufactured_state(op)
+    res, jac = _assemble(plan, op, u)
+    res0, _ = _assemble(plan, op, np.zeros(op.num_dofs))
+    J = op.csr(jac)
+    free = op.is_fixed == 0
+    scale = np.abs(jac).max()
+    # translations: u = e_d on every node (dofs interleaved dx,dy,dz per node)
+    for d in range(3):
+        t = np.zeros(op.num_dofs)
+        t[d::3] = 1.0
+        assert np.abs((J @ t)[free]).max() < 1e-11 * scale
+    x, y = np.random.default_rng(1).standard_normal((2, op.num_dofs)) * free
+    a, b = x @ (J @ y), y @ (J @ x)
+    assert abs(a - b) < 1e-11 * max(abs(a), abs(b), 1.0)
+    lin = res0 - J @ u
+    assert np.abs((res - lin)[free]).max() < 1e-11 * max(np.abs(res).max(), 1.0)
