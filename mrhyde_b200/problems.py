@@ -93,3 +93,91 @@ class ThermalBrick:
     def algorithmic_bytes(self):
         nv = 2 ** self.dim
         return 4.0 * nv * self.n_elem + 8.0 * self.dim * self.nodes.shape[0] + 8.0 * self.n_rows + 8.0 * self.n_rows + 8.0 * self.nnz
+
+
+def _expand_graph(rowptr, colind, nvar):
+    """Node graph -> dof graph for `nvar` fields interleaved per node (dof = nvar * node + field), ascending columns."""
+    n = len(rowptr) - 1
+    cnt = np.diff(rowptr)
+    rp = np.zeros(n * nvar + 1, dtype=np.int64)
+    np.cumsum(np.repeat(cnt * nvar, nvar), out=rp[1:])
+    # every dof row of a node repeats the node's column list with each column expanded to nvar consecutive dofs
+    base = (colind.astype(np.int64)[:, None] * nvar + np.arange(nvar)[None, :]).reshape(-1)     # per node row: len*nvar entries
+    seg = np.repeat(np.arange(n), cnt * nvar)                                                     # node row of each entry in `base`
+    # rows are [node0 x nvar copies, node1 x nvar copies, ...]; build by repeating each node's segment nvar times
+    starts = np.concatenate([[0], np.cumsum(cnt * nvar)])
+    idx = np.concatenate([np.tile(np.arange(starts[r], starts[r + 1]), nvar) for r in range(n)]) if n < 4096 else None
+    if idx is None:
+        # vectorised for large meshes: position p in the output belongs to dof row rho = searchsorted(rp, p); node = rho // nvar
+        total = int(rp[-1])
+        out = np.empty(total, dtype=np.int32)
+        chunk = 1 << 24
+        for lo in range(0, total, chunk):
+            p = np.arange(lo, min(total, lo + chunk), dtype=np.int64)
+            rho = np.searchsorted(rp, p, side="right") - 1
+            node = rho // nvar
+            out[lo:lo + len(p)] = base[starts[node] + (p - rp[rho])]
+        return rp, out
+    del seg
+    return rp, base[idx].astype(np.int32)
+
+
+class SystemBrick:
+    """Steady multi-field HGRAD-Q1 system on an inline brick through the general path: "linearelasticity"
+    (dx,dy[,dz], all-boundary strong Dirichlet) or "navier stokes" (ux,pr,uy[,uz], velocity fixed on the boundary,
+    SUPG+PSPG).  DOFs are interleaved per node in the module's variable order (oracle/mesh.hpp)."""
+
+    VARS = {"linearelasticity": {2: ["dx", "dy"], 3: ["dx", "dy", "dz"]}, "navier stokes": {2: ["ux", "pr", "uy"], 3: ["ux", "pr", "uy", "uz"]}}
+
+    def __init__(self, physics, dim, n, device=0, functions=None, options=None):
+        self.physics, self.dim, self.n = physics, dim, [int(v) for v in n[:dim]]
+        names = self.VARS[physics][dim]
+        nvar = len(names)
+        nodes, conn = im.brick(dim, self.n)
+        self.nodes, self.conn = nodes, conn
+        nv = 2 ** dim
+        self.lids = np.ascontiguousarray((conn.astype(np.int64)[:, :, None] * nvar + np.arange(nvar)[None, None, :]).reshape(conn.shape[0], nv * nvar).astype(np.int32))
+        rp, ci = im.q1_graph(dim, self.n)
+        self.rowptr, self.colind = _expand_graph(rp, ci, nvar)
+        self.n_rows = nodes.shape[0] * nvar
+        self.n_owned = self.n_rows
+        bmask = im.boundary_mask(dim, self.n).astype(bool)
+        fixed = np.zeros((nodes.shape[0], nvar), dtype=np.uint8)
+        for v, name in enumerate(names):
+            if name != "pr":
+                fixed[bmask, v] = 1
+        self.is_fixed = fixed.reshape(-1)
+        self.n_elem = conn.shape[0]
+        self.nnz = int(self.rowptr[-1])
+        pts, wts, val, grad = im.q1_reference(dim)
+        offsets = np.ascontiguousarray((np.arange(nv)[None, :] * nvar + np.arange(nvar)[:, None]).astype(np.int32))
+        self.plan = AssemblyPlan(physics, dim, names, [0] * nvar, [dict(type="HGRAD", order=1, card=nv, val=val, grad=grad)], nv * nvar,
+                                 offsets, pts, wts, device=device)
+        if physics == "linearelasticity":
+            fn = {"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)", "source dy": "sin(2*pi*x)*sin(2*pi*y)"}
+            if dim == 3:
+                fn["source dz"] = "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"
+            opts = {}
+        else:
+            fn = {"source ux": "1.0", "viscosity": "1.0", "density": "1.0"}
+            opts = {"useSUPG": "true", "usePSPG": "true"}
+        fn.update(functions or {})
+        opts.update(options or {})
+        for k, v in fn.items():
+            self.plan.set_function(k, v)
+        for k, v in opts.items():
+            self.plan.set_option(k, v)
+        self.plan.set_mesh_indexed(nodes, conn, self.lids)
+        self.plan.set_graph(self.rowptr, self.colind, self.is_fixed, n_owned=self.n_owned)
+        self.plan.finalize()
+
+    def state(self, seed=20261017):
+        rng = np.random.default_rng(seed)
+        x = self.nodes
+        nvar = self.n_rows // x.shape[0]
+        u = np.stack([np.prod(np.sin((v + 1) * np.pi * x), axis=1) for v in range(nvar)], axis=1).reshape(-1)
+        return u + 1e-3 * rng.uniform(-1.0, 1.0, size=self.n_rows)
+
+    def algorithmic_bytes(self):
+        nd = self.lids.shape[1]
+        return 4.0 * nd * self.n_elem + 8.0 * self.dim * self.nodes.shape[0] + 8.0 * self.n_rows + 8.0 * self.n_rows + 8.0 * self.nnz

@@ -6,7 +6,7 @@ Run in the development container (where /root/reference exists):
 The GPU box has no /root/reference; tests read only the JSON files written here.
 
   regression_gold.json   input deck (the YAML under ANONYMOUS) + the L2-error lines of mrhyde.gold for the
-                         thermal regression cases on the hot path
+                         thermal, linear elasticity and Navier-Stokes regression cases on the hot path
   functions_valid.json   the `Functions:` block of regression/functions/Valid and the decomposition
                          forest its mrhyde.gold prints (tree -> branch expressions, in order)
 """
@@ -20,7 +20,7 @@ REF = "/root/reference/regression"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 CASES = ["thermal/2D_verification", "thermal/2D_verification_mpi", "thermal/3D_verification", "thermal/2D_verification_transient",
-         "thermal/2D_mixed_bcs"]
+         "thermal/2D_mixed_bcs", "le/3D_manufactured", "le/2D_manufactured", "navierstokes/channel"]
 # (thermal/2D_verification_nonzeroDBC is not usable as a pin: its Dirichlet data come from the solver's boundary
 #  L2 projection, solverManager_util.hpp:24-48, which is outside the path)
 

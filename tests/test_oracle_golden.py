@@ -105,3 +105,52 @@ def test_q1_laplace_stencil_and_symmetry(oracle_lib):
     op0 = oracle_lib.OracleProblem(cfg0)
     r0, _ = op0.assemble_jacres(np.ones(op0.num_dofs))
     assert np.max(np.abs(r0)) < 1e-14
+
+
+def _newton(op, cfg, maxiter=10, tol=1e-6):
+    """nonlinearSolver (solverManager_solvers.hpp:290-640): relative residual test against the first residual, then a
+    full Newton update; defaults nonlinear TOL 1e-6, max nonlinear iters 10 (solverManager_construct.hpp:58-60)."""
+    import scipy.sparse.linalg as spla
+    solver = cfg.get("Solver", {})
+    maxiter = int(solver.get("max nonlinear iters", maxiter))
+    tol = float(solver.get("nonlinear TOL", tol))
+    u = np.zeros(op.num_dofs)
+    fixed = op.is_fixed.astype(bool)
+    # the multi-field decks pinned here all carry homogeneous Dirichlet data (helpers.dirichlet_values is nodal, one field)
+    for spec in cfg.get("Physics", {}).get("Dirichlet conditions", {}).values():
+        assert all(float(v) == 0.0 for v in spec.values())
+    u[fixed] = 0.0
+    first = None
+    for it in range(maxiter + 1):
+        res, jac = op.assemble_jacres(u)
+        nrm = np.max(np.abs(res))
+        first = nrm if first is None else first
+        if first == 0.0 or nrm / first < tol or it == maxiter:
+            break
+        u = u + spla.spsolve(op.csr(jac).tocsc(), res)
+    return u
+
+
+@pytest.mark.parametrize("case", ["le/3D_manufactured", "le/2D_manufactured"])
+def test_linear_elasticity_gold(oracle_lib, case):
+    """regression/le/{2D,3D}_manufactured: nested `Functions:` sources, lambda = mu = 1, hex/quad Q1, strong Dirichlet."""
+    cfg, errs = _errs(case)
+    cfg["Physics"]["Dirichlet conditions"].pop("scalar data", None)
+    op = oracle_lib.OracleProblem(cfg)
+    u = _newton(op, cfg)
+    assert len(errs) == op.dim
+    for e in errs:
+        got = op.l2_error([e["field"]], u)
+        assert abs(got - e["value"]) <= _tol(e["value"]), (case, e, got)
+
+
+def test_navier_stokes_channel_gold(oracle_lib):
+    """regression/navierstokes/channel: 2-D PSPG-stabilised equal-order Q1, natural in/outflow, Newton to 1e-6."""
+    cfg, errs = _errs("navierstokes/channel")
+    cfg["Physics"]["Dirichlet conditions"].pop("scalar data", None)
+    op = oracle_lib.OracleProblem(cfg)
+    u = _newton(op, cfg)
+    assert {e["field"] for e in errs} == {"ux", "pr", "uy"}
+    for e in errs:
+        got = op.l2_error([e["field"]], u)
+        assert abs(got - e["value"]) <= _tol(e["value"]), (e, got)
