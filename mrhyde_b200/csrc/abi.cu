@@ -158,7 +158,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -831,6 +831,7 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
   } catch (const std::exception& e) {
     fail(MRHYDE_B200_ERR_INVALID, e.what());
   }
+  gen_set_epb(std::stoi(opt(P, "elements per cta", "0")));
   P->use_general = true;
   P->launches_per_assemble = 2 * (int)H.batches.size();
   for (auto& S : H.sides) if (S.active && !S.items.empty()) ++P->launches_per_assemble;

@@ -158,12 +158,15 @@ GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t*
   return D.release();
 }
 
+static int g_epb_override = 0;
+void gen_set_epb(int epb) { g_epb_override = epb; }
 static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items) {
   // threads per element in the derivative stage; aim for 128..256 threads and <= ~100 KB of shared memory per CTA
   const int tpe = I.N / I.K;
   const int sd = side ? I.smem_doubles_side : I.smem_doubles_volume;
   int epb = std::max(1, 256 / tpe);
-  while (epb > 1 && (size_t)epb * sd * 8 > 100 * 1024) --epb;
+  if (g_epb_override > 0) epb = g_epb_override;
+  while (epb > 1 && ((size_t)epb * sd * 8 > 100 * 1024 || epb * tpe > 256)) --epb;
   if (n_items < epb) epb = (int)std::max<int64_t>(1, n_items);
   return epb;
 }

@@ -88,6 +88,7 @@ struct GeneralPlanDev;   // device buffers
 struct GenLaunchStats { int launches = 0; };
 GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t* dev_bytes, std::string& err);
 void gen_free(GeneralPlanDev* D);
+void gen_set_epb(int epb);   // tuning: elements per CTA of the element kernel (0 = automatic)
 // the whole assemble call: element kernels + pull per batch.  Returns nullptr or an error string.
 const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                          const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,

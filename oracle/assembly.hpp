@@ -403,6 +403,15 @@ inline AssemblyManager::AssemblyManager(const Settings& s) : settings(s) {
   mesh.lo[0] = s.getd("Mesh/xmin", 0.0); mesh.hi[0] = s.getd("Mesh/xmax", 1.0);
   mesh.lo[1] = s.getd("Mesh/ymin", 0.0); mesh.hi[1] = s.getd("Mesh/ymax", 1.0);
   mesh.lo[2] = s.getd("Mesh/zmin", 0.0); mesh.hi[2] = s.getd("Mesh/zmax", 1.0);
+  // "Periodic BCs" (panzer_stk periodic matchers, meshInterface_construct.hpp): 'xz-all ...: top;bottom' pairs the y sides,
+  // 'yz-all ...: left;right' the x sides, 'xy-all ...: back;front' the z sides
+  for (auto& p : s.sub("Mesh/Periodic BCs/")) {
+    if (p.first == "Count") continue;
+    if (p.second.find("yz-all") != std::string::npos) mesh.periodic[0] = true;
+    else if (p.second.find("xz-all") != std::string::npos) mesh.periodic[1] = true;
+    else if (p.second.find("xy-all") != std::string::npos) mesh.periodic[2] = true;
+    else throw std::runtime_error("oracle: periodic condition not restated: " + p.second);
+  }
   mesh.build();
   // optional smooth vertex perturbation (synthetic non-affine meshes for parity tests; boundary nodes stay put)
   const double pert = s.getd("Mesh/perturb", 0.0);

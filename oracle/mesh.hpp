@@ -27,6 +27,7 @@ struct BrickMesh {
   int dim = 3;
   int n[3] = {1, 1, 1};
   double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+  bool periodic[3] = {false, false, false};  // "Periodic BCs" of the mesh sublist (panzer_stk periodic matchers): dof lattices wrap
   CellTopo topo;
   int num_nodes = 0, num_elems = 0;
   std::vector<double> nodes;  // (num_nodes, dim)
@@ -101,7 +102,7 @@ struct DofMap {
   // entity lattice helpers ---------------------------------------------------------
   static int64_t hgrad_entities(const BrickMesh& m, int p) {
     int64_t c = 1;
-    for (int d = 0; d < m.dim; ++d) c *= (int64_t)p * m.n[d] + 1;
+    for (int d = 0; d < m.dim; ++d) c *= (int64_t)p * m.n[d] + (m.periodic[d] ? 0 : 1);
     return c;
   }
 
@@ -116,14 +117,16 @@ struct DofMap {
     }
     gbase.assign(bases.size(), 0); lbase.assign(bases.size(), 0);
     const int nx = m.n[0], ny = m.n[1], nz = (m.dim == 3) ? m.n[2] : 0;
+    // lattice points per direction: n+1, or n when the direction is periodic (the last plane is the first)
+    const int px = nx + (m.periodic[0] ? 0 : 1), py = ny + (m.periodic[1] ? 0 : 1), pz = nz + (m.periodic[2] ? 0 : 1);
     std::vector<int64_t> nent(bases.size(), 0);
     int64_t g = 0; int l = 0;
     for (size_t b = 0; b < bases.size(); ++b) {
       const Basis& B = bases[b];
       if (B.type == "HGRAD") nent[b] = hgrad_entities(m, B.order);
       else if (B.type == "HVOL") nent[b] = m.num_elems;
-      else if (B.type == "HCURL") nent[b] = (int64_t)nx * (ny + 1) * (nz + 1) + (int64_t)(nx + 1) * ny * (nz + 1) + (int64_t)(nx + 1) * (ny + 1) * nz;
-      else if (B.type == "HDIV") nent[b] = (int64_t)(nx + 1) * ny * nz + (int64_t)nx * (ny + 1) * nz + (int64_t)nx * ny * (nz + 1);
+      else if (B.type == "HCURL") nent[b] = (int64_t)nx * py * pz + (int64_t)px * ny * pz + (int64_t)px * py * nz;
+      else if (B.type == "HDIV") nent[b] = (int64_t)px * ny * nz + (int64_t)nx * py * nz + (int64_t)nx * ny * pz;
       gbase[b] = g; lbase[b] = l;
       g += nent[b] * nvb[b]; l += B.card * nvb[b];
     }
@@ -149,33 +152,39 @@ struct DofMap {
             hgrad_ordinal_to_ijk(B, d, t);
             const int p = B.order;
             int64_t L[3], N[3];
-            for (int c = 0; c < 3; ++c) { N[c] = (c < m.dim) ? (int64_t)p * m.n[c] + 1 : 1; L[c] = (c < m.dim) ? (int64_t)p * eijk[c] + t[c] : 0; }
+            for (int c = 0; c < 3; ++c) {
+              N[c] = (c < m.dim) ? (int64_t)p * m.n[c] + (m.periodic[c] ? 0 : 1) : 1;
+              L[c] = (c < m.dim) ? ((int64_t)p * eijk[c] + t[c]) % N[c] : 0;
+            }
             ent = L[0] + N[0] * (L[1] + N[1] * L[2]);
-            for (int c = 0; c < m.dim; ++c) { side[2 * c] = (L[c] == 0); side[2 * c + 1] = (L[c] == N[c] - 1); }
+            for (int c = 0; c < m.dim; ++c) if (!m.periodic[c]) { side[2 * c] = (L[c] == 0); side[2 * c + 1] = (L[c] == N[c] - 1); }
           } else if (B.type == "HVOL") {
             ent = e;
           } else if (B.type == "HCURL") {
-            const int64_t nxe = (int64_t)nx * (ny + 1) * (nz + 1), nye = (int64_t)(nx + 1) * ny * (nz + 1);
+            const int64_t nxe = (int64_t)nx * py * pz, nye = (int64_t)px * ny * pz;
+            int i, j, k;
             if (d < 4) {  // x-directed: d = j + 2k
-              const int j = eijk[1] + (d % 2), k = eijk[2] + (d / 2), i = eijk[0];
-              ent = i + (int64_t)nx * (j + (int64_t)(ny + 1) * k);
+              j = eijk[1] + (d % 2); k = eijk[2] + (d / 2); i = eijk[0];
               side[2] = (j == 0); side[3] = (j == ny); side[4] = (k == 0); side[5] = (k == nz);
+              ent = i + (int64_t)nx * ((j % py) + (int64_t)py * (k % pz));
             } else if (d < 8) {  // y-directed: d-4 = i + 2k
-              const int i = eijk[0] + ((d - 4) % 2), k = eijk[2] + ((d - 4) / 2), j = eijk[1];
-              ent = nxe + i + (int64_t)(nx + 1) * (j + (int64_t)ny * k);
+              i = eijk[0] + ((d - 4) % 2); k = eijk[2] + ((d - 4) / 2); j = eijk[1];
               side[0] = (i == 0); side[1] = (i == nx); side[4] = (k == 0); side[5] = (k == nz);
+              ent = nxe + (i % px) + (int64_t)px * (j + (int64_t)ny * (k % pz));
             } else {  // z-directed: d-8 = i + 2j
-              const int i = eijk[0] + ((d - 8) % 2), j = eijk[1] + ((d - 8) / 2), k = eijk[2];
-              ent = nxe + nye + i + (int64_t)(nx + 1) * (j + (int64_t)(ny + 1) * k);
+              i = eijk[0] + ((d - 8) % 2); j = eijk[1] + ((d - 8) / 2); k = eijk[2];
               side[0] = (i == 0); side[1] = (i == nx); side[2] = (j == 0); side[3] = (j == ny);
+              ent = nxe + nye + (i % px) + (int64_t)px * ((j % py) + (int64_t)py * k);
             }
+            for (int c = 0; c < 3; ++c) if (m.periodic[c]) side[2 * c] = side[2 * c + 1] = 0;
           } else if (B.type == "HDIV") {
-            const int64_t nxf = (int64_t)(nx + 1) * ny * nz, nyf = (int64_t)nx * (ny + 1) * nz;
+            const int64_t nxf = (int64_t)px * ny * nz, nyf = (int64_t)nx * py * nz;
             const int dir = d / 2, s = d % 2;
             const int i = eijk[0] + (dir == 0 ? s : 0), j = eijk[1] + (dir == 1 ? s : 0), k = eijk[2] + (dir == 2 ? s : 0);
-            if (dir == 0) { ent = i + (int64_t)(nx + 1) * (j + (int64_t)ny * k); side[0] = (i == 0); side[1] = (i == nx); }
-            else if (dir == 1) { ent = nxf + i + (int64_t)nx * (j + (int64_t)(ny + 1) * k); side[2] = (j == 0); side[3] = (j == ny); }
-            else { ent = nxf + nyf + i + (int64_t)nx * (j + (int64_t)ny * k); side[4] = (k == 0); side[5] = (k == nz); }
+            if (dir == 0) { ent = (i % px) + (int64_t)px * (j + (int64_t)ny * k); side[0] = (i == 0); side[1] = (i == nx); }
+            else if (dir == 1) { ent = nxf + i + (int64_t)nx * ((j % py) + (int64_t)py * k); side[2] = (j == 0); side[3] = (j == ny); }
+            else { ent = nxf + nyf + i + (int64_t)nx * (j + (int64_t)ny * (k % pz)); side[4] = (k == 0); side[5] = (k == nz); }
+            for (int c = 0; c < 3; ++c) if (m.periodic[c]) side[2 * c] = side[2 * c + 1] = 0;
           }
           for (int r = 0; r < nvb[b]; ++r) {
             const int64_t gid = gbase[b] + ent * nvb[b] + r;

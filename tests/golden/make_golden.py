@@ -20,14 +20,20 @@ REF = "/root/reference/regression"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 CASES = ["thermal/2D_verification", "thermal/2D_verification_mpi", "thermal/3D_verification", "thermal/2D_verification_transient",
-         "thermal/2D_mixed_bcs", "le/3D_manufactured", "le/2D_manufactured", "navierstokes/channel"]
+         "thermal/2D_mixed_bcs", "le/3D_manufactured", "le/2D_manufactured", "navierstokes/channel", "maxwell/PlaneWave"]
 # (thermal/2D_verification_nonzeroDBC is not usable as a pin: its Dirichlet data come from the solver's boundary
 #  L2 projection, solverManager_util.hpp:24-48, which is outside the path)
 
 
 def load_deck(path):
+    """The ANONYMOUS list of an input deck with its `<Section> input file:` includes merged in (the reference's
+    UserInterface does the same, src/interfaces/user/userInterface.cpp)."""
     with open(path) as f:
-        return yaml.safe_load(f)["ANONYMOUS"]
+        deck = yaml.safe_load(f)["ANONYMOUS"]
+    for key in [k for k in deck if k.endswith(" input file")]:
+        with open(os.path.join(os.path.dirname(path), deck.pop(key))) as f:
+            deck.update(yaml.safe_load(f)["ANONYMOUS"])
+    return deck
 
 
 def errors(path):

@@ -130,7 +130,7 @@ def deck_to_cfg(deck):
     """mrhyde input deck (golden fixture) -> the flat-block form the oracle reads (block sublists dropped)."""
     import copy
     cfg = copy.deepcopy(deck)
-    for sec in ("Physics", "Discretization"):
+    for sec in ("Physics", "Discretization", "Postprocess"):
         blk = cfg.get(sec, {})
         keys = [k for k in blk if k.startswith("eblock")]
         for k in keys:

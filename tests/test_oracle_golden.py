@@ -154,3 +154,29 @@ def test_navier_stokes_channel_gold(oracle_lib):
     for e in errs:
         got = op.l2_error([e["field"]], u)
         assert abs(got - e["value"]) <= _tol(e["value"]), (e, got)
+
+
+def test_maxwell_planewave_gold(oracle_lib):
+    """regression/maxwell/PlaneWave: 2x2x100 hex, x/y periodic, lowest-order HCURL E + HDIV B, DIRK-1,2 with BDF1,
+    ten steps of 1e-15 s with a Gaussian-modulated current sheet.  Pins the HCURL/HDIV tabulation and push-forward
+    (Intrepid2 is not visible under /root/reference), the Maxwell module's 3-D form, the stage
+    combination of computeSolnTransientSeeded and the comparison operators of the function manager."""
+    import scipy.sparse.linalg as spla
+    cfg, errs = _errs("maxwell/PlaneWave")
+    cfg["Physics"].pop("Initial conditions", None)
+    op = oracle_lib.OracleProblem(cfg)
+    assert op.num_elems == 400 and op.ndof_elem == 18 and op.num_dofs == 1208 + 1204   # periodic edge / face counts
+    nsteps = int(cfg["Solver"]["number of steps"])
+    dt = float(cfg["Solver"]["final time"]) / nsteps
+    u = np.zeros(op.num_dofs)
+    gold = {(e["field"], n): e["value"] for e in errs for n in range(nsteps + 1) if abs(e["time"] - n * dt) < 1e-3 * dt}
+    assert len(gold) == 2 * (nsteps + 1)
+    for n in range(nsteps):
+        op.set_time(True, time=n * dt, dt=dt, stage=0, A=((0.5,),), b=(1.0,), c=(0.5,), bdf=(1.0, -1.0))
+        us = u.copy()
+        res, jac = op.assemble_jacres(us, sol_prev=[u], sol_stage=[us])   # max nonlinear iters: 1 (the problem is linear)
+        u = us + spla.spsolve(op.csr(jac).tocsc(), res)
+        for f in ("E", "B"):
+            got = op.l2_error([f + "[x]", f + "[y]", f + "[z]"], u)
+            want = gold[(f, n + 1)]
+            assert abs(got - want) <= _tol(want), (f, n + 1, got, want)
