@@ -12,17 +12,18 @@ namespace mrhyde_b200 {
 
 namespace {
 
-template <class Phys, int NQ, int NQS, int K>
+template <class Phys, int NQ, int NQS, int K, int MAXT, int MINB>
 const char* launch_entry(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream) {
   static size_t attr[2] = {0, 0};
-  const void* fn = side ? (const void*)gen_element_kernel<Phys, NQS, K, true> : (const void*)gen_element_kernel<Phys, NQ, K, false>;
+  if (threads > MAXT) return "general element kernel: more threads per CTA than the instantiation's launch bounds";
+  const void* fn = side ? (const void*)gen_element_kernel<Phys, NQS, K, true, MAXT, MINB> : (const void*)gen_element_kernel<Phys, NQ, K, false, MAXT, MINB>;
   if (smem > 48 * 1024 && smem > attr[side ? 1 : 0]) {
     const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     attr[side ? 1 : 0] = smem;
   }
-  if (side) gen_element_kernel<Phys, NQS, K, true><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
-  else gen_element_kernel<Phys, NQ, K, false><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
+  if (side) gen_element_kernel<Phys, NQS, K, true, MAXT, MINB><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
+  else gen_element_kernel<Phys, NQ, K, false, MAXT, MINB><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -30,7 +31,8 @@ const char* launch_entry(bool side, const GenParams& P, int nblocks, int threads
 std::vector<GenDeviceKernels>& device_table() {
   static std::vector<GenDeviceKernels> T;
   if (T.empty()) {
-#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS) T.push_back(GenDeviceKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER), &launch_entry<PHYS, NQ, NQS, K>});
+#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS, MAXT, MINB) \
+  T.push_back(GenDeviceKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER, MAXT, MINB), &launch_entry<PHYS, NQ, NQS, K, MAXT, MINB>});
     MRH_GEN_LIST(X)
 #undef X
   }
@@ -161,12 +163,13 @@ GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t*
 static int g_epb_override = 0;
 void gen_set_epb(int epb) { g_epb_override = epb; }
 static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items) {
-  // threads per element in the derivative stage; aim for 128..256 threads and <= ~100 KB of shared memory per CTA
+  // as many elements per CTA as the launch bounds allow, while MINB CTAs still fit the SM's shared memory
   const int tpe = I.N / I.K;
   const int sd = side ? I.smem_doubles_side : I.smem_doubles_volume;
-  int epb = std::max(1, 256 / tpe);
+  const size_t smem_cap = (size_t)(220 * 1024) / (size_t)std::max(1, I.min_blocks);
+  int epb = std::max(1, I.max_threads / tpe);
   if (g_epb_override > 0) epb = g_epb_override;
-  while (epb > 1 && ((size_t)epb * sd * 8 > 100 * 1024 || epb * tpe > 256)) --epb;
+  while (epb > 1 && ((size_t)epb * sd * 8 > smem_cap || epb * tpe > I.max_threads)) --epb;
   if (n_items < epb) epb = (int)std::max<int64_t>(1, n_items);
   return epb;
 }
@@ -192,7 +195,7 @@ const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenD
     P.epb = epb;
     const int tpe = I.N / I.K;
     int threads = ((epb * tpe + 31) / 32) * 32;
-    threads = std::max(64, std::min(256, threads));
+    threads = std::max(32, std::min(I.max_threads, threads));
     const size_t smem = (size_t)epb * (side ? I.smem_doubles_side : I.smem_doubles_volume) * sizeof(double);
     const int64_t nblocks = (n_items + epb - 1) / epb;
     ++launches;

@@ -22,6 +22,7 @@ struct GenKernelInfo {
   const char* physics;
   int dim, order, nq, nqs;
   int N, nvars, nbasis, nfn, K;
+  int max_threads, min_blocks;                  // launch bounds of the element kernel
   int smem_doubles_volume, smem_doubles_side;   // per element
   int card[2], ncb[2];                          // per basis
   int var_basis[GEN_MAXVARS];

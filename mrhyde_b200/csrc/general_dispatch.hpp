@@ -16,25 +16,26 @@ typedef NavierStokesPhys<2, 1> GenNs21;
 typedef NavierStokesPhys<3, 1> GenNs31;
 }  // namespace mrhyde_b200
 
-// X(physics name, dim, order, NQ, NQS, K, Phys)
-#define MRH_GEN_LIST(X)                                   \
-  X("thermal", 2, 1, 4, 2, 1, GenTh21)                    \
-  X("thermal", 3, 1, 8, 4, 1, GenTh31)                    \
-  X("thermal", 2, 2, 9, 3, 1, GenTh22)                    \
-  X("thermal", 3, 2, 27, 9, 1, GenTh32)                   \
-  X("linearelasticity", 2, 1, 4, 2, 1, GenLe21)           \
-  X("linearelasticity", 3, 1, 8, 4, 1, GenLe31)           \
-  X("linearelasticity", 2, 2, 9, 3, 1, GenLe22)           \
-  X("linearelasticity", 3, 2, 27, 9, 1, GenLe32)          \
-  X("navier stokes", 2, 1, 4, 2, 1, GenNs21)              \
-  X("navier stokes", 3, 1, 8, 4, 1, GenNs31)              \
-  X("maxwell", 3, 1, 8, 4, 1, MaxwellPhys)
+// X(physics name, dim, order, NQ, NQS, K, Phys, MAXT, MINB): MAXT threads per CTA at most, MINB CTAs per SM at least
+#define MRH_GEN_LIST(X)                                             \
+  X("thermal", 2, 1, 4, 2, 1, GenTh21, 256, 3)                      \
+  X("thermal", 3, 1, 8, 4, 1, GenTh31, 256, 3)                      \
+  X("thermal", 2, 2, 9, 3, 1, GenTh22, 256, 2)                      \
+  X("thermal", 3, 2, 27, 9, 1, GenTh32, 128, 3)                     \
+  X("linearelasticity", 2, 1, 4, 2, 1, GenLe21, 256, 3)             \
+  X("linearelasticity", 3, 1, 8, 4, 1, GenLe31, 256, 3)             \
+  X("linearelasticity", 2, 2, 9, 3, 1, GenLe22, 128, 4)             \
+  X("linearelasticity", 3, 2, 27, 9, 1, GenLe32, 96, 2)             \
+  X("navier stokes", 2, 1, 4, 2, 1, GenNs21, 256, 2)                \
+  X("navier stokes", 3, 1, 8, 4, 1, GenNs31, 128, 3)                \
+  X("maxwell", 3, 1, 8, 4, 1, MaxwellPhys, 128, 3)
 
 namespace mrhyde_b200 {
 template <class Phys, int NQ, int NQS, int K>
-inline GenKernelInfo gen_make_info(const char* physics, int dim, int order) {
+inline GenKernelInfo gen_make_info(const char* physics, int dim, int order, int maxt, int minb) {
   GenKernelInfo I;
   I.physics = physics; I.dim = dim; I.order = order; I.nq = NQ; I.nqs = NQS;
+  I.max_threads = maxt; I.min_blocks = minb;
   I.N = Phys::N; I.nvars = Phys::NVAR; I.nbasis = Phys::NBASIS; I.nfn = Phys::NFN; I.K = K;
   I.smem_doubles_volume = GenLayout<Phys, NQ>::SIZE;
   I.smem_doubles_side = GenLayout<Phys, NQS>::SIZE;

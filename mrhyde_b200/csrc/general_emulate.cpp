@@ -23,7 +23,7 @@ void emulate_blocks(const GenParams& P, int nblocks) {
     for (int i = 0; i < P.epb * NQ; ++i) Bk::s1(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb; ++i) Bk::s1b(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb * Phys::max_card() * NQ; ++i) Bk::s2(P, sm.data(), blk, i);
-    for (int i = 0; i < P.epb * NQ; ++i) Bk::s3(P, sm.data(), blk, i);
+    for (int i = 0; i < P.epb * NQ * Bk::S3_KINDS; ++i) Bk::s3(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb * NQ; ++i) Bk::s4a(P, sm.data(), blk, i);
     if (P.elem_jac)
       for (int i = 0; i < P.epb * Bk::TPE; ++i) Bk::s4b(P, sm.data(), blk, i);
@@ -42,7 +42,8 @@ struct HostEntry { GenHostKernels k; };
 std::vector<GenHostKernels>& host_table() {
   static std::vector<GenHostKernels> T;
   if (T.empty()) {
-#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS) T.push_back(GenHostKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER), &emulate_entry<PHYS, NQ, NQS, K>});
+#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS, MAXT, MINB) \
+    T.push_back(GenHostKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER, MAXT, MINB), &emulate_entry<PHYS, NQ, NQS, K>});
     MRH_GEN_LIST(X)
 #undef X
   }

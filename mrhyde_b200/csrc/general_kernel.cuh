@@ -75,6 +75,18 @@ MRH_HD double mrh_sqrt(double a) { return sqrt(a); }
 template <int K> MRH_HD double mrh_val(const Dual<K>& a) { return a.v; }
 MRH_HD double mrh_val(double a) { return a; }
 
+// NN consecutive doubles from 16-byte aligned shared memory (NN even): LDS.128 on the device
+template <int NN>
+MRH_HD void mrh_ldn(const double* __restrict__ p, double* __restrict__ o) {
+#if defined(__CUDA_ARCH__)
+  const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int i = 0; i < NN / 2; ++i) { const double2 t = p2[i]; o[2 * i] = t.x; o[2 * i + 1] = t.y; }
+#else
+  for (int i = 0; i < NN; ++i) o[i] = p[i];
+#endif
+}
+
 // ---- launch parameters --------------------------------------------------------------------------------------
 constexpr int GEN_MAXVARS = 4;
 constexpr int GEN_MAXFN = 16;
@@ -380,22 +392,30 @@ struct GenBlock {
     }
     for (int k = 0; k < NC; ++k) { sme[L::FV + (q * NVAR + V) * NC + k] = f[k]; sme[L::FT + (q * NVAR + V) * NC + k] = ft[k]; }
   }
+  // work item (t, el, q): t < NVAR -> fields of variable t; else coefficient function t - NVAR (the last NVAR are the
+  // boundary data of each variable on this sideset)
+  static constexpr int S3_KINDS = NVAR + Phys::NFN + NVAR;
   MRH_HD static void s3(const GenParams& P, double* sm, int /*blk*/, int idx) {
-    if (idx >= P.epb * NQ) return;
-    const int el = idx / NQ, q = idx % NQ;
+    const int neq = P.epb * NQ;
+    if (idx >= neq * S3_KINDS) return;
+    const int t = idx / neq, eq = idx % neq, el = eq / NQ, q = eq % NQ;
     double* sme = sm + el * L::SIZE;
-    s3_var<0>(P, sme, q);
-    if (NVAR > 1) s3_var<(NVAR > 1 ? 1 : 0)>(P, sme, q);
-    if (NVAR > 2) s3_var<(NVAR > 2 ? 2 : 0)>(P, sme, q);
-    if (NVAR > 3) s3_var<(NVAR > 3 ? 3 : 0)>(P, sme, q);
+    if (t < NVAR) {
+      switch (t) {
+        case 0: s3_var<0>(P, sme, q); break;
+        case 1: s3_var<(NVAR > 1 ? 1 : 0)>(P, sme, q); break;
+        case 2: s3_var<(NVAR > 2 ? 2 : 0)>(P, sme, q); break;
+        default: s3_var<(NVAR > 3 ? 3 : 0)>(P, sme, q); break;
+      }
+      return;
+    }
+    const int f = t - NVAR;
     const double* g = sme + L::G + q * L::GEO;
     const double var[7] = {g[1], g[2], g[3], P.td.time, g[24], g[25], g[26]};
-    for (int f = 0; f < Phys::NFN; ++f) sme[L::FN + q * L::NFN + f] = gen_expr_eval(P.fn[f], P.fn_op, P.fn_c, var);
-    for (int v = 0; v < NVAR; ++v) {   // boundary data of each variable on this sideset
-      double val = 0.0;
-      if (SIDE && P.bc_fn[v] >= 0) val = gen_expr_eval(P.fn[P.bc_fn[v]], P.fn_op, P.fn_c, var);
-      sme[L::FN + q * L::NFN + Phys::NFN + v] = val;
-    }
+    double val = 0.0;
+    if (f < Phys::NFN) val = gen_expr_eval(P.fn[f], P.fn_op, P.fn_c, var);
+    else if (SIDE && P.bc_fn[f - Phys::NFN] >= 0) val = gen_expr_eval(P.fn[P.bc_fn[f - Phys::NFN]], P.fn_op, P.fn_c, var);
+    sme[L::FN + q * L::NFN + f] = val;
   }
 
   MRH_HD static void make_ctx(const GenParams& P, const double* sme, int q, QpCtx& c) {
@@ -424,52 +444,8 @@ struct GenBlock {
       for (int k = 0; k < NC; ++k) sme[L::CV + (q * NVAR + v) * NC + k] = Cf[v][k];
   }
 
-  // S4b: derivative components.  Thread (el, g) owns columns (WV, i0 .. i0+K-1), WV = variable of the group.
-  template <int WV>
-  MRH_HD static void s4b_var(const GenParams& P, double* sm, int blk, int el, int i0) {
-    constexpr int B = Phys::var_basis(WV), NCB = Phys::ncb(B), NVAL = Phys::nval(B);
-    const int64_t item = item_of(P, blk, el);
-    const double* sme = sm + el * L::SIZE;
-    double acc[N][K];
-#pragma unroll
-    for (int r = 0; r < N; ++r)
-#pragma unroll
-      for (int kk = 0; kk < K; ++kk) acc[r][kk] = 0.0;
-    const double au = P.td.transient ? P.td.alpha_u : 1.0, at = P.td.transient ? P.td.alpha_t : 0.0;
-    for (int q = 0; q < NQ; ++q) {
-      QpCtx c;
-      make_ctx(P, sme, q, c);
-      Dual<K> F[NVAR][NC], Ft[NVAR][NC], Cf[NVAR][NC];
-#pragma unroll
-      for (int v = 0; v < NVAR; ++v)
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          F[v][k] = Dual<K>(sme[L::FV + (q * NVAR + v) * NC + k]);
-          Ft[v][k] = Dual<K>(sme[L::FT + (q * NVAR + v) * NC + k]);
-          Cf[v][k] = Dual<K>(0.0);
-        }
-#pragma unroll
-      for (int kk = 0; kk < K; ++kk) {
-        const double* pb = sme + L::PB + L::pb_off(B) + ((i0 + kk) * NQ + q) * NCB;
-#pragma unroll
-        for (int k = 0; k < NCB; ++k) F[WV][k].d[kk] = au * pb[k];
-#pragma unroll
-        for (int k = 0; k < NVAL; ++k) Ft[WV][k].d[kk] = at * pb[k];
-      }
-      if (SIDE) Phys::template boundary<Dual<K>>(c, P.opt, F, Ft, Cf);
-      else Phys::template volume<Dual<K>>(c, P.opt, F, Ft, Cf);
-      // test-function loop: rows in (variable, basis function) order
-      s4b_rows_all(sme + L::PB, q, Cf, acc);
-    }
-    if (item < P.item_end && P.elem_jac) {
-      double* out = P.elem_jac + (P.inst_base + (item - P.item_begin)) * (int64_t)(N * N);
-#pragma unroll
-      for (int kk = 0; kk < K; ++kk) {
-        const int col = P.off[WV][i0 + kk];
-        store_rows(P, out, col, acc, kk);
-      }
-    }
-  }
+  // S4b: derivative components.  Thread (el, g) owns columns (wv, i0 .. i0+K-1); the variable wv is a run-time value so
+  // that the lanes of a warp -- which hold different variables of one element -- execute one instruction stream.
   template <int V>
   MRH_HD static void store_var(const GenParams& P, double* out, int col, const double (&acc)[N][K], int kk) {
     constexpr int CARD = Phys::card(Phys::var_basis(V)), R0 = Phys::row0(V);
@@ -488,11 +464,12 @@ struct GenBlock {
     const double* pbq = pbase + L::pb_off(B) + q * NCB;
 #pragma unroll
     for (int i = 0; i < CARD; ++i) {
+      double b[NCB];
+      mrh_ldn<NCB>(pbq + i * NQ * NCB, b);
 #pragma unroll
       for (int k = 0; k < NCB; ++k) {
-        const double b = pbq[i * NQ * NCB + k];
 #pragma unroll
-        for (int kk = 0; kk < K; ++kk) acc[R0 + i][kk] += Cf[V][k].d[kk] * b;
+        for (int kk = 0; kk < K; ++kk) acc[R0 + i][kk] += Cf[V][k].d[kk] * b[k];
       }
     }
   }
@@ -506,18 +483,67 @@ struct GenBlock {
     if (idx >= P.epb * TPE) return;
     const int el = idx / TPE, g = idx % TPE;
     // groups are numbered variable-major: variable v owns card(v)/K consecutive groups
-    int v = 0, g0 = 0;
-    for (; v < NVAR - 1; ++v) {
-      const int ng = Phys::card_of_var(v) / K;
+    int wv = 0, g0 = 0;
+    for (; wv < NVAR - 1; ++wv) {
+      const int ng = Phys::card_of_var(wv) / K;
       if (g < g0 + ng) break;
       g0 += ng;
     }
     const int i0 = (g - g0) * K;
-    switch (v) {
-      case 0: s4b_var<0>(P, sm, blk, el, i0); break;
-      case 1: s4b_var<(NVAR > 1 ? 1 : 0)>(P, sm, blk, el, i0); break;
-      case 2: s4b_var<(NVAR > 2 ? 2 : 0)>(P, sm, blk, el, i0); break;
-      default: s4b_var<(NVAR > 3 ? 3 : 0)>(P, sm, blk, el, i0); break;
+    const int wb = Phys::var_basis_rt(wv), ncb = Phys::ncb_rt(wb), nval = Phys::nval(wb);
+    const int64_t item = item_of(P, blk, el);
+    const double* sme = sm + el * L::SIZE;
+    const double* pbw = sme + L::PB + L::pb_off(wb) + i0 * NQ * ncb;
+    double acc[N][K];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) acc[r][kk] = 0.0;
+    const bool transient = P.td.transient != 0;
+    const double au = transient ? P.td.alpha_u : 1.0, at = transient ? P.td.alpha_t : 0.0;
+    for (int q = 0; q < NQ; ++q) {
+      QpCtx c;
+      make_ctx(P, sme, q, c);
+      Dual<K> F[NVAR][NC], Ft[NVAR][NC], Cf[NVAR][NC];
+      {
+        double fv[NVAR * NC], ft[NVAR * NC];
+        mrh_ldn<NVAR * NC>(sme + L::FV + q * NVAR * NC, fv);
+        if (transient) mrh_ldn<NVAR * NC>(sme + L::FT + q * NVAR * NC, ft);
+#pragma unroll
+        for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+          for (int k = 0; k < NC; ++k) {
+            F[v][k].v = fv[v * NC + k];
+            Ft[v][k].v = transient ? ft[v * NC + k] : 0.0;
+            Cf[v][k] = Dual<K>(0.0);
+          }
+      }
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        double sd[NC];
+        const double* pb = pbw + (kk * NQ + q) * ncb;
+        if (Phys::NBASIS == 1) mrh_ldn<NC>(pb, sd);
+        else {
+#pragma unroll
+          for (int k = 0; k < NC; ++k) sd[k] = k < ncb ? pb[k] : 0.0;
+        }
+#pragma unroll
+        for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+          for (int k = 0; k < NC; ++k) {
+            F[v][k].d[kk] = (v == wv) ? au * sd[k] : 0.0;
+            Ft[v][k].d[kk] = (v == wv && k < nval) ? at * sd[k] : 0.0;
+          }
+      }
+      if (SIDE) Phys::template boundary<Dual<K>>(c, P.opt, F, Ft, Cf);
+      else Phys::template volume<Dual<K>>(c, P.opt, F, Ft, Cf);
+      // test-function loop: rows in (variable, basis function) order
+      s4b_rows_all(sme + L::PB, q, Cf, acc);
+    }
+    if (item < P.item_end && P.elem_jac) {
+      double* out = P.elem_jac + (P.inst_base + (item - P.item_begin)) * (int64_t)(N * N);
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) store_rows(P, out, (int)P.off[wv][i0 + kk], acc, kk);
     }
   }
 
@@ -545,8 +571,10 @@ struct GenBlock {
 };
 
 #if defined(__CUDACC__)
-template <class Phys, int NQ, int K, bool SIDE>
-__global__ void __launch_bounds__(256) gen_element_kernel(const __grid_constant__ GenParams P) {
+// MAXT / MINB: launch bounds chosen per instantiation (general_dispatch.hpp) so that the register allocation leaves
+// MINB CTAs of MAXT threads resident per SM
+template <class Phys, int NQ, int K, bool SIDE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) gen_element_kernel(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) double gen_smem[];
   typedef GenBlock<Phys, NQ, K, SIDE> Bk;
   const int blk = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
@@ -558,7 +586,7 @@ __global__ void __launch_bounds__(256) gen_element_kernel(const __grid_constant_
   for (int i = tid; i < P.epb; i += T) Bk::s1b(P, gen_smem, blk, i);
   for (int i = tid; i < P.epb * Phys::max_card() * NQ; i += T) Bk::s2(P, gen_smem, blk, i);
   __syncthreads();
-  for (int i = tid; i < P.epb * NQ; i += T) Bk::s3(P, gen_smem, blk, i);
+  for (int i = tid; i < P.epb * NQ * Bk::S3_KINDS; i += T) Bk::s3(P, gen_smem, blk, i);
   __syncthreads();
   for (int i = tid; i < P.epb * NQ; i += T) Bk::s4a(P, gen_smem, blk, i);
   if (P.elem_jac)

@@ -11,12 +11,12 @@ from .capi import AssemblyPlan
 THERMAL_SOURCE = {2: "8*(pi*pi)*sin(2*pi*x)*sin(2*pi*y)", 3: "12*(pi*pi)*sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)"}
 
 
-class ThermalBrick:
-    """Steady thermal, HGRAD Q1, all-boundary strong Dirichlet on an inline brick; with nranks > 1 the
-    global mesh is `nranks` bricks stacked along the last axis (weak scaling, Zprocs = nranks) and this
-    object holds rank `rank`'s slab: owned rows first, the ghost plane (owned by rank+1) last."""
+class NodeSlab:
+    """Node-level data of rank `rank`'s slab of `nranks` bricks stacked along the last axis (Zprocs = nranks):
+    owned node rows first, the ghost plane (owned by rank+1) last; the plane below a non-zero rank appears as
+    column-only ghosts (the column map of the owned Tpetra matrix that exportMatrixFromOverlapped fills)."""
 
-    def __init__(self, dim, n, device=0, rank=0, nranks=1, functions=None, options=None):
+    def __init__(self, dim, n, rank=0, nranks=1):
         self.dim, self.n, self.rank, self.nranks = dim, [int(v) for v in n[:dim]], rank, nranks
         n = self.n
         lo = [0.0] * 3
@@ -27,7 +27,6 @@ class ThermalBrick:
         # keep the global problem on the unit cube so the source term matches the regression deck
         nodes[:, dim - 1] /= float(nranks)
         self.nodes, self.conn = nodes, conn
-        self.lids = conn  # Q1 scalar field: local dof id == local node id (owned planes first by construction)
         nn = [v + 1 for v in n]
         plane = int(np.prod(nn[:-1]))
         self.n_rows = int(np.prod(nn))
@@ -63,6 +62,22 @@ class ThermalBrick:
             stride *= nn[d]
         fixed = fixed.astype(np.uint8)
         self.is_fixed = fixed
+        self.n_elem = conn.shape[0]
+
+
+class ThermalBrick:
+    """Steady thermal, HGRAD Q1, all-boundary strong Dirichlet on an inline brick; with nranks > 1 the
+    global mesh is `nranks` bricks stacked along the last axis (weak scaling, Zprocs = nranks) and this
+    object holds rank `rank`'s slab: owned rows first, the ghost plane (owned by rank+1) last."""
+
+    def __init__(self, dim, n, device=0, rank=0, nranks=1, functions=None, options=None):
+        self.dim, self.n, self.rank, self.nranks = dim, [int(v) for v in n[:dim]], rank, nranks
+        ns = NodeSlab(dim, n, rank, nranks)
+        for k in ("nodes", "conn", "n_rows", "n_owned", "row_gids", "rowptr", "colind", "col_gids", "is_fixed"):
+            setattr(self, k, getattr(ns, k))
+        conn = self.conn
+        nodes = self.nodes
+        self.lids = conn  # Q1 scalar field: local dof id == local node id (owned planes first by construction)
         self.n_elem = conn.shape[0]
         self.nnz = int(self.rowptr[-1])
         pts, wts, val, grad = im.q1_reference(dim)
@@ -129,23 +144,25 @@ class SystemBrick:
 
     VARS = {"linearelasticity": {2: ["dx", "dy"], 3: ["dx", "dy", "dz"]}, "navier stokes": {2: ["ux", "pr", "uy"], 3: ["ux", "pr", "uy", "uz"]}}
 
-    def __init__(self, physics, dim, n, device=0, functions=None, options=None):
-        self.physics, self.dim, self.n = physics, dim, [int(v) for v in n[:dim]]
+    def __init__(self, physics, dim, n, device=0, rank=0, nranks=1, functions=None, options=None):
+        self.physics, self.dim, self.n, self.rank, self.nranks = physics, dim, [int(v) for v in n[:dim]], rank, nranks
         names = self.VARS[physics][dim]
         nvar = len(names)
-        nodes, conn = im.brick(dim, self.n)
+        ns = NodeSlab(dim, n, rank, nranks)
+        nodes, conn = ns.nodes, ns.conn
         self.nodes, self.conn = nodes, conn
         nv = 2 ** dim
         self.lids = np.ascontiguousarray((conn.astype(np.int64)[:, :, None] * nvar + np.arange(nvar)[None, None, :]).reshape(conn.shape[0], nv * nvar).astype(np.int32))
-        rp, ci = im.q1_graph(dim, self.n)
-        self.rowptr, self.colind = _expand_graph(rp, ci, nvar)
-        self.n_rows = nodes.shape[0] * nvar
-        self.n_owned = self.n_rows
-        bmask = im.boundary_mask(dim, self.n).astype(bool)
-        fixed = np.zeros((nodes.shape[0], nvar), dtype=np.uint8)
+        # dofs interleaved per node: rows (owned nodes first) and column-only ghosts expand node by node
+        self.rowptr, self.colind = _expand_graph(ns.rowptr, ns.colind, nvar)
+        self.n_rows = ns.n_rows * nvar
+        self.n_owned = ns.n_owned * nvar
+        self.row_gids = (ns.row_gids[:, None] * nvar + np.arange(nvar)[None, :]).reshape(-1)
+        self.col_gids = (ns.col_gids[:, None] * nvar + np.arange(nvar)[None, :]).reshape(-1)
+        fixed = np.zeros((ns.n_rows, nvar), dtype=np.uint8)
         for v, name in enumerate(names):
             if name != "pr":
-                fixed[bmask, v] = 1
+                fixed[ns.is_fixed.astype(bool), v] = 1
         self.is_fixed = fixed.reshape(-1)
         self.n_elem = conn.shape[0]
         self.nnz = int(self.rowptr[-1])
@@ -172,11 +189,14 @@ class SystemBrick:
         self.plan.finalize()
 
     def state(self, seed=20261017):
-        rng = np.random.default_rng(seed)
         x = self.nodes
         nvar = self.n_rows // x.shape[0]
         u = np.stack([np.prod(np.sin((v + 1) * np.pi * x), axis=1) for v in range(nvar)], axis=1).reshape(-1)
-        return u + 1e-3 * rng.uniform(-1.0, 1.0, size=self.n_rows)
+        if self.nranks == 1:
+            noise = np.random.default_rng(seed).uniform(-1.0, 1.0, size=self.n_rows)
+        else:  # a function of the global id, so the replicas of a shared row agree across ranks
+            noise = np.modf(np.sin(self.row_gids * 12.9898) * 43758.5453)[0]
+        return u + 1e-3 * noise
 
     def algorithmic_bytes(self):
         nd = self.lids.shape[1]

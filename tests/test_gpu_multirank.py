@@ -12,7 +12,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N = (12, 10, 8)
 
 
-def _worker(rank, world, port, q):
+def _make(kind, n, rank, world):
+    from mrhyde_b200.problems import SystemBrick, ThermalBrick
+    if kind == "thermal":
+        return ThermalBrick(3, n, device=rank, rank=rank, nranks=world, options={"column elements": 16, "min segment levels": 2})
+    return SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[kind], 3, n, device=rank, rank=rank, nranks=world, options={"batch elems": 300})
+
+
+def _worker(rank, world, port, q, kind="thermal"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -23,7 +30,7 @@ def _worker(rank, world, port, q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        prob = ThermalBrick(3, N, device=rank, rank=rank, nranks=world, options={"column elements": 16, "min segment levels": 2})
+        prob = _make(kind, N, rank, world)
         uid = torch.from_numpy(prob.plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
         dist.broadcast(uid, 0)
         prob.plan.comm_init(uid.cpu().numpy(), rank, world)
@@ -42,7 +49,8 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_halo_sum_equals_single_gpu(product_lib):
+@pytest.mark.parametrize("kind", ["thermal", "le", "ns"])
+def test_two_gpu_halo_sum_equals_single_gpu(product_lib, kind):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -51,15 +59,15 @@ def test_two_gpu_halo_sum_equals_single_gpu(product_lib):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "le": 3, "ns": 5}[kind]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
     outs = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    glob = ThermalBrick(3, (N[0], N[1], world * N[2]), device=0)
+    glob = _make(kind, (N[0], N[1], world * N[2]), 0, 1)
     dev = torch.device("cuda:0")
     # the same state on the global mesh: value of every global row from the rank that owns it
     ug = np.zeros(glob.n_rows)

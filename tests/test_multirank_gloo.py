@@ -18,21 +18,37 @@ def _stage(gelem, stage_len):
     return np.sin(0.37 * gelem[:, None] + 1.3 * k) + 0.01 * k
 
 
-def _worker(rank, world, port, q):
+def _local_assembly(kind, rank, world):
+    """Rank-local overlapped residual / Jacobian values on a host-only plan.  thermal: the sweep plan's scatter programs on
+    staged element vectors that are a function of the global element id; le: the general path's kernel stages replayed on
+    the host (debug aid, see test_general_emulation.py) with a state that is a function of the global dof id."""
+    from mrhyde_b200.problems import SystemBrick, ThermalBrick
+    n = N if world > 1 else (N[0], N[1], 2 * N[2])
+    if kind == "thermal":
+        prob = ThermalBrick(3, n, device=-1, rank=rank, nranks=world, options={"column elements": 4, "min segment levels": 2})
+        ne = prob.n_elem
+        stage = _stage(np.arange(ne) + rank * ne, 44)
+        res, jac = np.zeros(prob.n_rows), np.zeros(prob.nnz)
+        prob.plan.debug_scatter_host(stage, 1, res, jac)
+    else:
+        prob = SystemBrick("linearelasticity", 3, n, device=-1, rank=rank, nranks=world, options={"batch elems": 40})
+        u = np.sin(0.01 * prob.row_gids) + 0.1
+        res, jac = np.zeros(prob.n_rows), np.zeros(prob.nnz)
+        prob.plan.debug_emulate(u, res, jac)
+    return prob, res, jac
+
+
+def _worker(rank, world, port, q, kind="thermal"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    from mrhyde_b200.problems import ThermalBrick
+    from mrhyde_b200.problems import SystemBrick, ThermalBrick
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        prob = ThermalBrick(3, N, device=-1, rank=rank, nranks=world, options={"column elements": 4, "min segment levels": 2})
-        ne = prob.n_elem
-        stage = _stage(np.arange(ne) + rank * ne, 44)
-        res = np.zeros(prob.n_rows)
-        jac = np.zeros(prob.nnz)
-        prob.plan.debug_scatter_host(stage, 1, res, jac)
+        res_jac = _local_assembly(kind, rank, world)
+        prob, res, jac = res_jac
         # ---- halo sum over gloo: ghost rows (local ids >= n_owned) go to the rank that owns their gid
         gids = prob.col_gids   # rows first, then column-only ghosts
         ghost = np.arange(prob.n_owned, prob.n_rows)
@@ -62,14 +78,14 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_partition_and_halo_sum_equal_single_rank(product_lib):
+@pytest.mark.parametrize("kind", ["thermal", "le"])
+def test_two_rank_partition_and_halo_sum_equal_single_rank(product_lib, kind):
     import torch.multiprocessing as mp
-    from mrhyde_b200.problems import ThermalBrick
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + (7 if kind == "le" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
     outs = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
@@ -77,11 +93,7 @@ def test_two_rank_partition_and_halo_sum_equal_single_rank(product_lib):
         p.join(timeout=60)
         assert p.exitcode == 0
     # single-rank reference: the same global mesh (N[0] x N[1] x 2 N[2]) as ONE slab
-    glob = ThermalBrick(3, (N[0], N[1], world * N[2]), device=-1, rank=0, nranks=1, options={"column elements": 4, "min segment levels": 2})
-    stage = _stage(np.arange(glob.n_elem), 44)
-    res = np.zeros(glob.n_rows)
-    jac = np.zeros(glob.nnz)
-    glob.plan.debug_scatter_host(stage, 1, res, jac)
+    glob, res, jac = _local_assembly(kind, 0, 1)
     seen = np.zeros(glob.n_rows, dtype=bool)
     for rank, gids, r_res, rp, cg, r_jac, fixed in outs:
         assert not seen[gids].any(), "a global row is owned by two ranks"
