@@ -53,8 +53,11 @@ struct PullParams {
   int32_t N, max_row_len;
 };
 
-template <int G>
+// G lanes per row, NPL = ceil(N / G) columns per lane and instance; the loads of U instances are issued before the first
+// is accumulated so that each lane has U * NPL element-matrix loads in flight (the kernel is latency-bound otherwise)
+template <int G, int NPL>
 __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ PullParams Q) {
+  constexpr int U = 4;
   extern __shared__ __align__(16) double pull_smem[];
   const int tid = threadIdx.x, lane = tid % G, grp = tid / G;
   const int64_t k = Q.row_begin + (int64_t)blockIdx.x * (blockDim.x / G) + grp;
@@ -77,10 +80,26 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
   if (Q.O.jac) {
     for (int t = lane; t < len; t += G) buf[t] = 0.0;
     __syncwarp(mask);
-    for (int64_t p = c0; p < c1; ++p) {
-      const int64_t ci = (int64_t)__ldg(Q.contrib + p) * N;
-      for (int c = lane; c < N; c += G) buf[__ldg(Q.pos + ci + c)] += __ldcs(Q.elem_jac + ci + c);
-      __syncwarp(mask);
+    for (int64_t p = c0; p < c1; p += U) {
+      double v[U][NPL];
+      int ps[U][NPL];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t ci = p + u < c1 ? (int64_t)__ldg(Q.contrib + p + u) * N : -1;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const int c = lane + j * G;
+          const bool ok = ci >= 0 && c < N;
+          ps[u][j] = ok ? (int)__ldg(Q.pos + ci + c) : -1;
+          v[u][j] = ok ? __ldcs(Q.elem_jac + ci + c) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {   // ascending instance order, one instance at a time: distinct positions within an instance
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) if (ps[u][j] >= 0) buf[ps[u][j]] += v[u][j];
+        __syncwarp(mask);
+      }
     }
     if (Q.O.accumulate) for (int t = lane; t < len; t += G) Q.O.jac[rs + t] += buf[t];
     else for (int t = lane; t < len; t += G) __stcs(Q.O.jac + rs + t, buf[t]);
@@ -208,23 +227,20 @@ const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenD
     Q.elem_jac = D->elem_jac.p; Q.elem_res = D->elem_res.p; Q.G = G; Q.O = O;
     Q.row_begin = row_begin; Q.row_end = row_end; Q.n_owned = H.n_owned; Q.N = I.N; Q.max_row_len = std::max(1, H.max_row_len);
     const int Gs = I.N <= 8 ? 8 : (I.N <= 16 ? 16 : 32);
+    const int npl = (I.N + Gs - 1) / Gs;
+    if (npl > 3) return "general pull: more than 96 dofs per element";
     const int threads = 256, rows_per_block = threads / Gs;
     const size_t smem = (size_t)rows_per_block * Q.max_row_len * sizeof(double);
     const int64_t nblocks = (row_end - row_begin + rows_per_block - 1) / rows_per_block;
     ++launches;
+    typedef void (*PullFn)(PullParams);
+    const PullFn fn = Gs == 8 ? (PullFn)gen_pull_kernel<8, 1> : Gs == 16 ? (PullFn)gen_pull_kernel<16, 1>
+                    : npl == 1 ? (PullFn)gen_pull_kernel<32, 1> : npl == 2 ? (PullFn)gen_pull_kernel<32, 2> : (PullFn)gen_pull_kernel<32, 3>;
     if (smem > 48 * 1024) {
-      static size_t attr[3] = {0, 0, 0};
-      const int ai = Gs == 8 ? 0 : (Gs == 16 ? 1 : 2);
-      if (smem > attr[ai]) {
-        const void* fn = Gs == 8 ? (const void*)gen_pull_kernel<8> : (Gs == 16 ? (const void*)gen_pull_kernel<16> : (const void*)gen_pull_kernel<32>);
-        const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cudaGetErrorString(e);
-        attr[ai] = smem;
-      }
+      const cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cudaGetErrorString(e);
     }
-    if (Gs == 8) gen_pull_kernel<8><<<(int)nblocks, threads, smem, (cudaStream_t)stream>>>(Q);
-    else if (Gs == 16) gen_pull_kernel<16><<<(int)nblocks, threads, smem, (cudaStream_t)stream>>>(Q);
-    else gen_pull_kernel<32><<<(int)nblocks, threads, smem, (cudaStream_t)stream>>>(Q);
+    fn<<<(int)nblocks, threads, smem, (cudaStream_t)stream>>>(Q);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
   };

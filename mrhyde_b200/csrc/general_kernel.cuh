@@ -70,8 +70,17 @@ template <int K> MRH_HD Dual<K> operator*(const Dual<K>& a, double b) { Dual<K> 
 template <int K> MRH_HD Dual<K> operator*(double a, const Dual<K>& b) { Dual<K> r; r.v = a * b.v; MRH_DUAL_LOOP r.d[k] = a * b.d[k]; return r; }
 template <int K> MRH_HD Dual<K> operator/(const Dual<K>& a, double b) { const double ib = 1.0 / b; Dual<K> r; r.v = a.v * ib; MRH_DUAL_LOOP r.d[k] = a.d[k] * ib; return r; }
 template <int K> MRH_HD Dual<K> operator/(double a, const Dual<K>& b) { Dual<K> r; const double ib = 1.0 / b.v; r.v = a * ib; MRH_DUAL_LOOP r.d[k] = -r.v * b.d[k] * ib; return r; }
-template <int K> MRH_HD Dual<K> mrh_sqrt(const Dual<K>& a) { Dual<K> r; r.v = sqrt(a.v); const double g = 0.5 / r.v; MRH_DUAL_LOOP r.d[k] = g * a.d[k]; return r; }
-MRH_HD double mrh_sqrt(double a) { return sqrt(a); }
+// 1/sqrt(x) and sqrt(x) = x * (1/sqrt(x)) share one reciprocal square root; the derivative factors need no division
+MRH_HD double mrh_rsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(a);
+#else
+  return 1.0 / sqrt(a);
+#endif
+}
+template <int K> MRH_HD Dual<K> mrh_rsqrt(const Dual<K>& a) { Dual<K> r; r.v = mrh_rsqrt(a.v); const double g = -0.5 * r.v * r.v * r.v; MRH_DUAL_LOOP r.d[k] = g * a.d[k]; return r; }
+template <int K> MRH_HD Dual<K> mrh_sqrt(const Dual<K>& a) { Dual<K> r; const double rs = mrh_rsqrt(a.v); r.v = a.v * rs; const double g = 0.5 * rs; MRH_DUAL_LOOP r.d[k] = g * a.d[k]; return r; }
+MRH_HD double mrh_sqrt(double a) { return a * mrh_rsqrt(a); }
 template <int K> MRH_HD double mrh_val(const Dual<K>& a) { return a.v; }
 MRH_HD double mrh_val(double a) { return a; }
 
@@ -145,7 +154,7 @@ struct GenParams {
 
 // what the physics sees at one point
 struct QpCtx {
-  double x, y, z, t, w, h, dt;
+  double x, y, z, t, w, h, ih, dt;   // ih = 1 / h
   double n[3];
   const double* fn;         // function values at this point
   int32_t transient, stage;
@@ -330,7 +339,9 @@ struct GenBlock {
     if (idx >= P.epb) return;
     double vol = 0.0;
     for (int q = 0; q < NQ; ++q) vol += sm[idx * L::SIZE + L::G + q * L::GEO];
-    sm[idx * L::SIZE + L::H] = pow(vol, 1.0 / (SIDE ? (double)DIM - 1.0 : (double)DIM));
+    const double h = pow(vol, 1.0 / (SIDE ? (double)DIM - 1.0 : (double)DIM));
+    sm[idx * L::SIZE + L::H] = h;
+    sm[idx * L::SIZE + L::H + 1] = 1.0 / h;
   }
 
   // S2: push-forward of basis b, function i, at point q
@@ -420,7 +431,7 @@ struct GenBlock {
 
   MRH_HD static void make_ctx(const GenParams& P, const double* sme, int q, QpCtx& c) {
     const double* g = sme + L::G + q * L::GEO;
-    c.w = g[0]; c.x = g[1]; c.y = g[2]; c.z = g[3]; c.t = P.td.time; c.h = sme[L::H];
+    c.w = g[0]; c.x = g[1]; c.y = g[2]; c.z = g[3]; c.t = P.td.time; c.h = sme[L::H]; c.ih = sme[L::H + 1];
     c.dt = P.td.deltat;
     c.n[0] = g[24]; c.n[1] = g[25]; c.n[2] = g[26];
     c.fn = sme + L::FN + q * L::NFN;

@@ -46,7 +46,6 @@ struct HGradSystem {
 // ---------------------------------------------------------------------------------------------------------
 template <int DIM_, int P_>
 struct ThermalPhys : HGradSystem<DIM_, P_, 1> {
-  typedef HGradSystem<DIM_, P_, 1> S;
   static constexpr int NFN = 8;
   template <class T>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[1][4], const T (&Ft)[1][4], T (&Cf)[1][4]) {
@@ -70,7 +69,7 @@ struct ThermalPhys : HGradSystem<DIM_, P_, 1> {
       T flux = F[0][1] * c.n[0] + F[0][2] * c.n[1];
       if (DIM_ > 2) flux = flux + F[0][3] * c.n[2];
       const T jump = F[0][0] - bdata;
-      Cf[0][0] = (epen / c.h * diff * jump - diff * flux) * c.w;
+      Cf[0][0] = (epen * c.ih * diff * jump - diff * flux) * c.w;
       for (int d = 0; d < DIM_; ++d) Cf[0][1 + d] = -o.form_param * diff * jump * c.w * c.n[d];
     }
   }
@@ -135,7 +134,7 @@ struct ElasticityPhys : HGradSystem<DIM_, P_, DIM_> {
       if (c.bc_type[d] == BC_NEUMANN) {
         Cf[d][0] = T(-c.fn[NFN + d] * c.w);
       } else if (c.bc_type[d] == BC_WEAK_DIRICHLET) {
-        const double penalty = o.penalty * (lam + 2.0 * mu) / c.h;
+        const double penalty = o.penalty * (lam + 2.0 * mu) * c.ih;
         T trac = s[d][0] * c.n[0] + s[d][1] * c.n[1];
         if (DIM_ > 2) trac = trac + s[d][2] * c.n[2];
         Cf[d][0] = (penalty * delta[d] - trac) * c.w;
@@ -165,14 +164,17 @@ struct NavierStokesPhys : HGradSystem<DIM_, P_, DIM_ + 1> {
   static constexpr int NVAR = DIM_ + 1;
   MRH_HD static int vel(int d) { return d == 0 ? 0 : d + 1; }   // ux 0, uy 2, uz 3; pr 1
   MRH_HD static int src(int d) { return d == 0 ? 0 : d + 1; }   // source ux 0, uy 2, uz 3
+  // computeTau (navierstokes.cpp:1053-1081): tau = [(C1 nu/h^2)^2 + (C2 |u|/h)^2 + (C3/dt)^2]^(-1/2); divisions by h, dt are
+  // multiplications by reciprocals and the square roots share one rsqrt (a few ulp, far inside the 1e-12 tolerance)
   template <class T>
-  MRH_HD static T compute_tau(const double visc, const T (&u)[3], double h, double dt, int transient) {
+  MRH_HD static T compute_tau(const double visc, const T (&u)[3], double ih, double dt, int transient) {
     const double C1 = 4.0, C2 = 2.0, C3 = transient ? 2.0 : 0.0;
     T nvel = u[0] * u[0] + u[1] * u[1];
     if (DIM_ > 2) nvel = nvel + u[2] * u[2];
     if (mrh_val(nvel) > 1E-12) nvel = mrh_sqrt(nvel);   // below the threshold the squared speed is used
-    T tau = (C2 * nvel / h) * (C2 * nvel / h) + ((C1 * visc / h / h) * (C1 * visc / h / h) + (C3 / dt) * (C3 / dt));
-    return 1.0 / mrh_sqrt(tau);
+    const double t1 = C1 * visc * ih * ih, t3 = transient ? C3 / dt : 0.0;
+    const T nv = (C2 * ih) * nvel;
+    return mrh_rsqrt(nv * nv + (t1 * t1 + t3 * t3));
   }
   template <class T>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&Ft)[NVAR][4], T (&Cf)[NVAR][4]) {
@@ -181,15 +183,16 @@ struct NavierStokesPhys : HGradSystem<DIM_, P_, DIM_ + 1> {
     for (int d = 0; d < 3; ++d) u[d] = d < DIM_ ? F[vel(d < DIM_ ? d : 0)][0] : T(0.0);
     const T pr = F[1][0];
     T tau = T(0.0);
-    if (o.useSUPG || o.usePSPG) tau = compute_tau(visc, u, c.h, c.dt, c.transient);
+    if (o.useSUPG || o.usePSPG) tau = compute_tau(visc, u, c.ih, c.dt, c.transient);
     T divu = T(0.0);
+    const double wdens = dens * c.w, pspg_w = o.usePSPG ? c.w / dens : 0.0;
 #pragma unroll
     for (int d = 0; d < DIM_; ++d) {
       const int v = vel(d);
       T conv = u[0] * F[v][1] + u[1] * F[v][2];
       if (DIM_ > 2) conv = conv + u[2] * F[v][3];
       T co[4];
-      co[0] = (Ft[v][0] + conv - c.fn[src(d)]) * (dens * c.w);
+      co[0] = (Ft[v][0] + conv - c.fn[src(d)]) * wdens;
       for (int e = 0; e < DIM_; ++e) {
         T Fe = visc * F[v][1 + e];
         if (e == d) Fe = Fe - pr;
@@ -204,7 +207,7 @@ struct NavierStokesPhys : HGradSystem<DIM_, P_, DIM_ + 1> {
       } else {
         for (int k = 0; k <= DIM_; ++k) Cf[v][k] = Cf[v][k] + co[k];
       }
-      if (o.usePSPG) Cf[1][1 + d] = stabres * (tau * c.w / dens);
+      if (o.usePSPG) Cf[1][1 + d] = stabres * (tau * pspg_w);
       divu = divu + F[v][1 + d];
     }
     Cf[1][0] = divu * c.w;
@@ -241,9 +244,10 @@ struct MaxwellPhys {
     // E equation (maxwell.cpp:262-303): (n^2 E_t + (sigma E + J)/eps) . phi - B/(mu eps) . curl phi
     if (!o.leapfrog || c.stage == 1) {
       const double mu = c.fn[3], rindex = c.fn[4], eps = c.fn[5], sigma = c.fn[6];
+      const double ieps = 1.0 / eps, cb = (-1.0 / mu * 1.0 / eps) * c.w, n2 = rindex * rindex;
       for (int d = 0; d < 3; ++d) {
-        Cf[0][d] = (rindex * rindex * Ft[0][d] + 1.0 / eps * (sigma * F[0][d] + c.fn[d])) * c.w;
-        Cf[0][3 + d] = (-1.0 / mu * 1.0 / eps) * F[1][d] * c.w;
+        Cf[0][d] = (n2 * Ft[0][d] + ieps * (sigma * F[0][d] + c.fn[d])) * c.w;
+        Cf[0][3 + d] = cb * F[1][d];
       }
     }
   }
