@@ -168,6 +168,16 @@ int mrhyde_b200_assemble_res(mrhyde_b200_plan* plan, const double* sol, const mr
 int mrhyde_b200_assemble_jacres_host(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t,
                                      int compute_jacobian, int compute_residual, double* res, double* jac_values);
 
+/* getWeightedMass (assemblyManager_mass.hpp:13-275; element matrices :1065-1146), SURVEY 8(f) rank 1: the per-variable mass
+ * blocks  M[(n,i),(n,j)] = mass_wts[n] * sum_q (phi_i . phi_j) w  summed into mass_values (order of the graph's entries;
+ * entries that couple different variables receive nothing) and the diagonal vector the reference builds beside it:
+ * lump = 0 -> the Jacobi diagonal M(r,r); lump = 1 -> the lumped mass, sum over the row's elements of sum_j |M_e(r,j)|.
+ * isFixedDOF is not consulted (the reference does not either).  mass_wts: host [nvars] (physics->mass_wts[set][block]);
+ * mass_values [nnz] / diag [n_rows]: device pointers, either may be NULL; both follow the plan's accumulate option.
+ * Needs a plan on the general path (every module except thermal HGRAD-1, or option kernel=general). */
+int mrhyde_b200_assemble_mass(mrhyde_b200_plan* plan, const double* mass_wts, int lump, double* mass_values, double* diag,
+                              void* stream);
+
 /* ---- multi-GPU: the Tpetra Export(overlapped -> owned, ADD) replacement ---------------------------
  * (linearAlgebraInterface_matrix.hpp:233-237, _vector.hpp:56-66).  Ghost rows of this rank are summed
  * into the owning rank's rows in fixed neighbour-rank order. */
@@ -214,6 +224,8 @@ int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* plan, const char* source_path, 
  * entry points never use it.  sol / res / jac_values (and t's vectors) are host buffers. */
 int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, int compute_jacobian,
                                    int compute_residual, double* res, double* jac_values);
+/* Mass-matrix counterpart of mrhyde_b200_plan_debug_emulate (host-only plans; host buffers). */
+int mrhyde_b200_plan_debug_emulate_mass(mrhyde_b200_plan* plan, const double* mass_wts, int lump, double* mass_values, double* diag);
 /* Applies the plan's scatter programs on the host to caller-supplied staged element vectors
  * stage[n_elem][stage_len] (local Jacobian entries then residual entries), with the
  * same ordering and fixed-row rules as the device pull-scatter.  Verifies plan logic only. */

@@ -26,7 +26,7 @@ SYMBOLS = [
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
     "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit",
-    "mrhyde_b200_plan_debug_emulate",
+    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
 ]
 
 
@@ -98,6 +98,8 @@ def lib():
         L.mrhyde_b200_expr_eval_host.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_scatter_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_jit.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.mrhyde_b200_assemble_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_plan_debug_emulate_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_emulate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(TimeData), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
@@ -311,6 +313,15 @@ class AssemblyPlan:
             assert a is None or (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous) or hasattr(a, "data_ptr")
         self._chk(self.L.mrhyde_b200_assemble_jacres_host(self.h, _ptr(sol), time.ref() if time is not None else None,
                                                         int(compute_jacobian), int(compute_residual), _ptr(res), _ptr(jac)))
+
+    def assemble_mass(self, mass_wts, mass_values, diag, lump=False, stream=None):
+        """getWeightedMass: weighted mass values (graph order) and the Jacobi / lumped diagonal vector (device buffers)."""
+        w = np.ascontiguousarray(mass_wts, dtype=np.float64)
+        self._chk(self.L.mrhyde_b200_assemble_mass(self.h, _ptr(w), int(lump), _ptr(mass_values), _ptr(diag), C.c_void_p(stream) if stream else None))
+
+    def debug_emulate_mass(self, mass_wts, mass_values, diag, lump=False):
+        w = np.ascontiguousarray(mass_wts, dtype=np.float64)
+        self._chk(self.L.mrhyde_b200_plan_debug_emulate_mass(self.h, _ptr(w), int(lump), _ptr(mass_values), _ptr(diag)))
 
     # ---- multi-GPU -----------------------------------------------------------------------
     def comm_unique_id(self):

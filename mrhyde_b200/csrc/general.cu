@@ -51,6 +51,10 @@ struct PullParams {
   OutDev O;
   int64_t row_begin, row_end, n_owned;
   int32_t N, max_row_len;
+  // mass pull: fixed rows are not skipped, instances >= mass_inst_end (boundary sides) are ignored, O.res receives the
+  // diagonal vector (Jacobi diagonal, or the lumped row sums of |entries| when mass_mode == 2)
+  int32_t mass_mode;
+  int64_t mass_inst_end;
 };
 
 // G lanes per row, NPL = ceil(N / G) columns per lane and instance; the loads of U instances are issued before the first
@@ -67,6 +71,31 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
   const int32_t r = __ldg(Q.row_order + k);
   const int64_t rs = __ldg(Q.G.rowptr + r);
   const int len = (int)(__ldg(Q.G.rowptr + r + 1) - rs);
+  if (Q.mass_mode) {
+    const int N = Q.N;
+    const int64_t c0 = __ldg(Q.contrib_ptr + k), c1 = __ldg(Q.contrib_ptr + k + 1);
+    for (int t = lane; t < len; t += G) buf[t] = 0.0;
+    __syncwarp(mask);
+    double lumped = 0.0;
+    for (int64_t p = c0; p < c1; ++p) {
+      const int64_t inst = __ldg(Q.contrib + p);
+      if (inst / N >= Q.mass_inst_end) continue;
+      const int64_t ci = inst * N;
+      for (int c = lane; c < N; c += G) { const double v = __ldcs(Q.elem_jac + ci + c); buf[__ldg(Q.pos + ci + c)] += v; lumped += fabs(v); }
+      __syncwarp(mask);
+    }
+    if (Q.O.jac) for (int t = lane; t < len; t += G) Q.O.jac[rs + t] = (Q.O.accumulate ? Q.O.jac[rs + t] : 0.0) + buf[t];
+    if (Q.O.res) {
+      for (int o = G / 2; o > 0; o >>= 1) lumped += __shfl_xor_sync(mask, lumped, o, G);
+      double d = lumped;
+      if (Q.mass_mode != 2) {
+        d = 0.0;
+        for (int t = 0; t < len; ++t) if (__ldg(Q.G.colind + rs + t) == r) d = buf[t];
+      }
+      if (lane == 0) Q.O.res[r] = (Q.O.accumulate ? Q.O.res[r] : 0.0) + d;
+    }
+    return;
+  }
   if (__ldg(Q.G.fixed + r)) {   // strong-Dirichlet row: skipped by the scatter (scatter.hpp:208, 253); identity row when overwriting
     if (!Q.O.accumulate) {
       if (Q.O.res && lane == 0) Q.O.res[r] = 0.0;
@@ -143,6 +172,7 @@ struct SideDev {
 }  // namespace
 
 struct GeneralPlanDev {
+  Buf<double> zero;   // state placeholder of the mass mode
   Buf<int32_t> row_order, contrib;
   Buf<int64_t> contrib_ptr;
   Buf<uint16_t> pos;
@@ -179,11 +209,15 @@ GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t*
   return D.release();
 }
 
+const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                    const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
+                    bool volume, bool boundary, void* stream, GenLaunchStats* stats, int pull_mass_mode, const double* mass_wts);
+
 static int g_epb_override = 0;
 void gen_set_epb(int epb) { g_epb_override = epb; }
 static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items) {
   // as many elements per CTA as the launch bounds allow, while MINB CTAs still fit the SM's shared memory
-  const int tpe = I.N / I.K;
+  const int tpe = I.tpe;
   const int sd = side ? I.smem_doubles_side : I.smem_doubles_volume;
   const size_t smem_cap = (size_t)(220 * 1024) / (size_t)std::max(1, I.min_blocks);
   int epb = std::max(1, I.max_threads / tpe);
@@ -196,23 +230,49 @@ static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items) {
 const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                          const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
                          bool volume, bool boundary, void* stream, GenLaunchStats* stats) {
+  return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, sol, td, volume, boundary, stream, stats, 0, nullptr);
+}
+
+const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                              const int32_t* conn, const int32_t* lids, const GraphDev& G, const double* mass_wts, bool lump, bool accumulate,
+                              double* mass, double* diag, void* stream, GenLaunchStats* stats) {
+  // the mass matrix does not depend on the state: any valid vector serves as `sol` (the element residual scratch is one)
+  TimeDev td;
+  std::memset(&td, 0, sizeof(td));
+  td.alpha_u = 1.0; td.deltat = 1.0;
+  OutDev O;
+  O.jac = mass; O.res = diag; O.accumulate = accumulate ? 1 : 0;
+  if (!D->zero.p) {
+    std::string err;
+    if (!D->zero.alloc((size_t)H.n_rows, nullptr, err)) return "general mass: cannot allocate the state placeholder";
+    cudaMemset(D->zero.p, 0, (size_t)H.n_rows * sizeof(double));
+  }
+  return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, D->zero.p, td, true, false, stream, stats, lump ? 2 : 1, mass_wts);
+}
+
+static const char* gen_run_impl_marker = nullptr;
+const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                    const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
+                    bool volume, bool boundary, void* stream, GenLaunchStats* stats, int pull_mass_mode, const double* mass_wts) {
+  (void)gen_run_impl_marker;
   const GenKernelInfo& I = H.info;
   GenParams P;
   std::memset(&P, 0, sizeof(P));
   P.vx = vx; P.vy = vy; P.vz = vz; P.conn = conn; P.lids = lids; P.orient = D->orient.n ? D->orient.p : nullptr;
   P.sol = sol; P.td = td;
+  if (pull_mass_mode) { P.mass_mode = 1; for (int v = 0; v < I.nvars; ++v) P.mass_wts[v] = mass_wts[v]; }
   std::memcpy(P.off, H.off, sizeof(P.off));
   std::memcpy(P.fn, H.fn, sizeof(P.fn));
   P.fn_op = D->fn_op.p; P.fn_c = D->fn_c.p; P.opt = H.opt;
   for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
-  P.elem_jac = O.jac ? D->elem_jac.p : nullptr;
-  P.elem_res = O.res ? D->elem_res.p : nullptr;
+  P.elem_jac = (O.jac || pull_mass_mode) ? D->elem_jac.p : nullptr;
+  P.elem_res = (O.res && !pull_mass_mode) ? D->elem_res.p : nullptr;
   int launches = 0;
   auto run_elements = [&](bool side, int64_t n_items) -> const char* {
     if (n_items <= 0) return nullptr;
     const int epb = pick_epb(I, side, n_items);
     P.epb = epb;
-    const int tpe = I.N / I.K;
+    const int tpe = I.tpe;
     int threads = ((epb * tpe + 31) / 32) * 32;
     threads = std::max(32, std::min(I.max_threads, threads));
     const size_t smem = (size_t)epb * (side ? I.smem_doubles_side : I.smem_doubles_volume) * sizeof(double);
@@ -226,6 +286,7 @@ const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenD
     Q.row_order = D->row_order.p; Q.contrib_ptr = D->contrib_ptr.p; Q.contrib = D->contrib.p; Q.pos = D->pos.p;
     Q.elem_jac = D->elem_jac.p; Q.elem_res = D->elem_res.p; Q.G = G; Q.O = O;
     Q.row_begin = row_begin; Q.row_end = row_end; Q.n_owned = H.n_owned; Q.N = I.N; Q.max_row_len = std::max(1, H.max_row_len);
+    Q.mass_mode = pull_mass_mode; Q.mass_inst_end = H.n_elem;
     const int Gs = I.N <= 8 ? 8 : (I.N <= 16 ? 16 : 32);
     const int npl = (I.N + Gs - 1) / Gs;
     if (npl > 3) return "general pull: more than 96 dofs per element";

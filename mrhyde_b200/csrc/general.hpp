@@ -22,6 +22,7 @@ struct GenKernelInfo {
   const char* physics;
   int dim, order, nq, nqs;
   int N, nvars, nbasis, nfn, K;
+  int tpe;                                      // threads per element in the derivative stage
   int max_threads, min_blocks;                  // launch bounds of the element kernel
   int smem_doubles_volume, smem_doubles_side;   // per element
   int card[2], ncb[2];                          // per basis
@@ -84,6 +85,9 @@ void gen_build_pull(const MeshGraph& m, int N, const std::vector<GenSideFamily>&
 void gen_pull_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, const double* elem_res, bool accumulate,
                    double* res, double* jac);
 
+// weighted-mass variant of the pull: no fixed-row skipping, boundary instances ignored, diagonal vector = Jacobi diagonal or lumped
+void gen_pull_mass_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, bool accumulate, bool lump, double* mass, double* diag);
+
 // ---- device side (general.cu) ---------------------------------------------------------------------------------
 struct GeneralPlanDev;   // device buffers
 struct GenLaunchStats { int launches = 0; };
@@ -94,5 +98,9 @@ void gen_set_epb(int epb);   // tuning: elements per CTA of the element kernel (
 const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                          const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
                          bool volume, bool boundary, void* stream, GenLaunchStats* stats);
+// getWeightedMass: element kernel in mass mode over the volume elements + mass pull.  mass / diag may be null.
+const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                              const int32_t* conn, const int32_t* lids, const GraphDev& G, const double* mass_wts, bool lump, bool accumulate,
+                              double* mass, double* diag, void* stream, GenLaunchStats* stats);
 
 }  // namespace mrhyde_b200

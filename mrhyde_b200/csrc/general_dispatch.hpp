@@ -36,7 +36,7 @@ inline GenKernelInfo gen_make_info(const char* physics, int dim, int order, int 
   GenKernelInfo I;
   I.physics = physics; I.dim = dim; I.order = order; I.nq = NQ; I.nqs = NQS;
   I.max_threads = maxt; I.min_blocks = minb;
-  I.N = Phys::N; I.nvars = Phys::NVAR; I.nbasis = Phys::NBASIS; I.nfn = Phys::NFN; I.K = K;
+  I.N = Phys::N; I.nvars = Phys::NVAR; I.nbasis = Phys::NBASIS; I.nfn = Phys::NFN; I.K = K; I.tpe = GenBlock<Phys, NQ, K, false>::TPE;
   I.smem_doubles_volume = GenLayout<Phys, NQ>::SIZE;
   I.smem_doubles_side = GenLayout<Phys, NQS>::SIZE;
   for (int b = 0; b < 2; ++b) { I.card[b] = b < Phys::NBASIS ? Phys::card(b) : 0; I.ncb[b] = b < Phys::NBASIS ? Phys::ncb(b) : 0; }

@@ -150,6 +150,10 @@ struct GenParams {
   double* elem_jac;         // [n_inst][N][N]   may be null
   double* elem_res;         // [n_inst][N]      may be null
   int32_t epb;              // elements per CTA
+  // mass mode (getWeightedMass, assemblyManager_mass.hpp:1065-1146): the module's point function is replaced by
+  // Cf[v][value components] = mass_wts[v] * F[v] * w, so the "Jacobian" is the weighted mass matrix
+  int32_t mass_mode;
+  double mass_wts[GEN_MAXVARS];
 };
 
 // what the physics sees at one point
@@ -222,6 +226,16 @@ MRH_HD void gen_gather_dof(const double* __restrict__ sol, const TimeDev& td, in
     bt *= td.timewt;
     ut = td.alpha_t * s + bt;
   }
+}
+
+// weighted mass "physics": block-diagonal in the variables, value components only
+template <class Phys, class T>
+MRH_HD void gen_mass_point(const QpCtx& c, const double* mw, const T (&F)[Phys::NVAR][Phys::NC], T (&Cf)[Phys::NVAR][Phys::NC]) {
+#pragma unroll
+  for (int v = 0; v < Phys::NVAR; ++v)
+#pragma unroll
+    for (int k = 0; k < Phys::NC; ++k)
+      if (k < Phys::nval(Phys::var_basis(v))) Cf[v][k] = (mw[v] * c.w) * F[v][k];
 }
 
 // ---- shared-memory layout of one element (offsets in doubles; every block is a multiple of 2 doubles) ---------
@@ -449,7 +463,8 @@ struct GenBlock {
     double F[NVAR][NC], Ft[NVAR][NC], Cf[NVAR][NC];
     for (int v = 0; v < NVAR; ++v)
       for (int k = 0; k < NC; ++k) { F[v][k] = sme[L::FV + (q * NVAR + v) * NC + k]; Ft[v][k] = sme[L::FT + (q * NVAR + v) * NC + k]; Cf[v][k] = 0.0; }
-    if (SIDE) Phys::template boundary<double>(c, P.opt, F, Ft, Cf);
+    if (P.mass_mode) gen_mass_point<Phys, double>(c, P.mass_wts, F, Cf);
+    else if (SIDE) Phys::template boundary<double>(c, P.opt, F, Ft, Cf);
     else Phys::template volume<double>(c, P.opt, F, Ft, Cf);
     for (int v = 0; v < NVAR; ++v)
       for (int k = 0; k < NC; ++k) sme[L::CV + (q * NVAR + v) * NC + k] = Cf[v][k];
@@ -546,7 +561,8 @@ struct GenBlock {
             Ft[v][k].d[kk] = (v == wv && k < nval) ? at * sd[k] : 0.0;
           }
       }
-      if (SIDE) Phys::template boundary<Dual<K>>(c, P.opt, F, Ft, Cf);
+      if (P.mass_mode) gen_mass_point<Phys, Dual<K>>(c, P.mass_wts, F, Cf);
+      else if (SIDE) Phys::template boundary<Dual<K>>(c, P.opt, F, Ft, Cf);
       else Phys::template volume<Dual<K>>(c, P.opt, F, Ft, Cf);
       // test-function loop: rows in (variable, basis function) order
       s4b_rows_all(sme + L::PB, q, Cf, acc);

@@ -6,6 +6,7 @@
 // boundary-group order, which is the order the serial reference adds them (assemblyManager_jacres.hpp:336-603) --
 // and the position of every local column inside that CSR row is tabulated once (uint16).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
@@ -112,6 +113,27 @@ void gen_build_pull(const MeshGraph& m, int N, const std::vector<GenSideFamily>&
     for (auto& t : th) t.join();
   }
   if (!err.empty()) throw std::runtime_error(err);
+}
+
+void gen_pull_mass_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, bool accumulate, bool lump, double* mass, double* diag) {
+  const int N = H.info.N;
+  std::vector<double> buf((size_t)std::max(1, H.max_row_len));
+  for (int64_t k = 0; k < H.n_rows; ++k) {
+    const int32_t r = H.row_order[(size_t)k];
+    const int64_t rs = m.rowptr[(size_t)r];
+    const int len = (int)(m.rowptr[(size_t)r + 1] - rs);
+    for (int t = 0; t < len; ++t) buf[(size_t)t] = 0.0;
+    double lumped = 0.0;
+    int dpos = -1;
+    for (int t = 0; t < len; ++t) if (m.colind[(size_t)(rs + t)] == r) dpos = t;
+    for (int64_t p = H.contrib_ptr[(size_t)k]; p < H.contrib_ptr[(size_t)k + 1]; ++p) {
+      const int64_t ci = H.contrib[(size_t)p];
+      if (ci / N >= H.n_elem) continue;   // boundary instances carry no mass
+      for (int c = 0; c < N; ++c) { buf[H.pos[(size_t)(ci * N + c)]] += elem_jac[ci * N + c]; lumped += std::fabs(elem_jac[ci * N + c]); }
+    }
+    if (mass) for (int t = 0; t < len; ++t) mass[rs + t] = (accumulate ? mass[rs + t] : 0.0) + buf[(size_t)t];
+    if (diag) diag[r] = (accumulate ? diag[r] : 0.0) + (lump ? lumped : (dpos >= 0 ? buf[(size_t)dpos] : 0.0));
+  }
 }
 
 void gen_pull_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, const double* elem_res, bool accumulate,

@@ -91,6 +91,49 @@ class AssemblyManager {
     eng_scalar->assemble(*this, sol, sol_prev, sol_stage, false, false, res, nullptr);
   }
   void computeGroupBasis(Group& g, bool boundary);
+  // getWeightedMass (assemblyManager_mass.hpp:13-275; element matrices :1065-1146): per-variable mass blocks
+  //   localmass(e, off(i), off(j)) += basis(e,i,k,d) basis(e,j,k,d) wts(e,k) mwt[n]
+  // summed into the CSR values with sumIntoValues (no isFixedDOF check), and the diagonal vector: Jacobi
+  // (localmass(e,row,row)) or lumped (sum_k |localmass(e,row,col_k)|, the LA-accessible branch :126-148)
+  void weightedMass(const double* masswts, bool lump, double* Mvals, double* diag) const {
+    const int ndofE = dofs.ndof_elem;
+    std::vector<double> lm((size_t)ndofE * ndofE);
+    for (const Group& g : groups) {
+      for (int e = 0; e < g.numElem; ++e) {
+        std::fill(lm.begin(), lm.end(), 0.0);
+        for (size_t n = 0; n < dofs.vars.size(); ++n) {
+          const int b = dofs.vars[n].basis;
+          const Basis& B = dofs.bases[b];
+          const double* cb = &g.basis[b][(size_t)e * B.card * cub.n * B.vdim];
+          const auto& off = dofs.offsets[n];
+          for (int i = 0; i < B.card; ++i)
+            for (int j = 0; j < B.card; ++j)
+              for (int k = 0; k < cub.n; ++k)
+                for (int d = 0; d < B.vdim; ++d)
+                  lm[(size_t)off[i] * ndofE + off[j]] += cb[((size_t)i * cub.n + k) * B.vdim + d] * cb[((size_t)j * cub.n + k) * B.vdim + d] * g.wts[(size_t)e * cub.n + k] * masswts[n];
+        }
+        const int* LIDs = &g.LIDs[(size_t)e * ndofE];
+        for (size_t n = 0; n < dofs.vars.size(); ++n) {
+          const auto& off = dofs.offsets[n];
+          for (size_t j = 0; j < off.size(); ++j) {
+            const int row = off[j], rowIndex = LIDs[row];
+            if (diag) {
+              double val = 0.0;
+              if (!lump) val = lm[(size_t)row * ndofE + row];
+              else for (size_t k = 0; k < off.size(); ++k) val += std::fabs(lm[(size_t)row * ndofE + off[k]]);
+              diag[rowIndex] += val;
+            }
+            if (Mvals)
+              for (size_t k = 0; k < off.size(); ++k) {
+                const int col = LIDs[off[k]];
+                for (int64_t p = graph.rowptr[rowIndex]; p < graph.rowptr[rowIndex + 1]; ++p)
+                  if (graph.colind[p] == col) { Mvals[p] += lm[(size_t)row * ndofE + off[k]]; break; }
+              }
+          }
+        }
+      }
+    }
+  }
 };
 
 // ---------------------------------------------------------------------------------------

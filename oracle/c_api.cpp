@@ -178,6 +178,13 @@ int oracle_assemble_jacres(void* hv, const double* sol, const double* const* sol
   ORACLE_CATCH(1)
 }
 
+int oracle_weighted_mass(void* hv, const double* masswts, int lump, double* Mvals, double* diag) {
+  ORACLE_TRY
+  ((OracleHandle*)hv)->am->weightedMass(masswts, lump != 0, Mvals, diag);
+  return 0;
+  ORACLE_CATCH(1)
+}
+
 int oracle_assemble_res(void* hv, const double* sol, const double* const* sol_prev, const double* const* sol_stage, double* res) {
   ORACLE_TRY
   ((OracleHandle*)hv)->am->assembleRes(sol, sol_prev, sol_stage, res);

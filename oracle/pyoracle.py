@@ -201,6 +201,13 @@ class OracleProblem:
         self._chk(self.L.oracle_assemble_res(self.h, _p(sol, C.c_double), pp, ps, _p(res, C.c_double)))
         return res
 
+    def weighted_mass(self, mass_wts, lump=False):
+        """getWeightedMass: (mass values in graph order, diagonal vector)."""
+        w = np.ascontiguousarray(mass_wts, dtype=np.float64)
+        M, d = np.zeros(self.nnz), np.zeros(self.num_dofs)
+        self._chk(self.L.oracle_weighted_mass(self.h, _p(w, C.c_double), int(lump), _p(M, C.c_double), _p(d, C.c_double)))
+        return M, d
+
     # ---- evaluation helpers (postprocess-style L2 errors, expression trees) -------------
     def group_info(self, grp, boundary=False):
         n = C.c_int64(0)

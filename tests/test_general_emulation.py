@@ -72,3 +72,20 @@ def test_unsupported_configuration_is_an_error(oracle_lib, product_lib):
     with pytest.raises(MrhydeB200Error) as e:
         helpers.plan_from_oracle(op, cfg, device=-1)
     assert "no kernel" in str(e.value)
+
+
+MASS_CASES = [("le3d", configs.LE_3D, [1.0, 2.0, 0.5]), ("maxwell", configs.MAXWELL_3D, [1.5, 0.7]), ("ns2d", configs.NS_2D, [1.0, 0.0, 1.0]),
+              ("thermal3d-q2", configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 3, "Mesh/NY": 3, "Mesh/NZ": 2, "Mesh/perturb": 0.02,
+                                                                    "Discretization/order/T": 2, "Discretization/quadrature": 4}), [2.0])]
+
+
+@pytest.mark.parametrize("name,cfg,wts", MASS_CASES, ids=[c[0] for c in MASS_CASES])
+@pytest.mark.parametrize("lump", [False, True], ids=["jacobi", "lumped"])
+def test_weighted_mass_stages_match_oracle(oracle_lib, product_lib, name, cfg, wts, lump):
+    """getWeightedMass: weighted mass values and the Jacobi / lumped diagonal vector."""
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options={"kernel": "general"})
+    Mref, dref = op.weighted_mass(wts, lump)
+    M, d = np.zeros(op.nnz), np.zeros(op.num_dofs)
+    plan.debug_emulate_mass(wts, M, d, lump=lump)
+    assert helpers.rel_err_rows(M, Mref, op.rowptr) < TOL and helpers.rel_err_vec(d, dref) < TOL

@@ -126,3 +126,27 @@ def test_le_q1_properties_at_scale(product_lib, oracle_lib):
     assert abs(a - b) < 1e-11 * max(abs(a), abs(b), 1.0)
     lin = res0 - J @ u
     assert np.abs((res - lin)[free]).max() < 1e-11 * max(np.abs(res).max(), 1.0)
+
+
+@pytest.mark.parametrize("name,cfg,wts", [("le3d", configs.LE_3D, [1.0, 2.0, 0.5]), ("maxwell", configs.MAXWELL_3D, [1.5, 0.7]), ("ns3d", configs.NS_3D, [1.0, 0.0, 1.0, 1.0])],
+                         ids=["le3d", "maxwell", "ns3d"])
+def test_weighted_mass_matches_oracle(oracle_lib, product_lib, name, cfg, wts):
+    """getWeightedMass (assemblyManager_mass.hpp:13-275) through mrhyde_b200_assemble_mass: mass values and the Jacobi /
+    lumped diagonal vector against the oracle; the mass matrix is symmetric and its entries sum to the weighted volume."""
+    import torch
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    dev = torch.device("cuda:0")
+    for lump in (False, True):
+        Mref, dref = op.weighted_mass(wts, lump)
+        d_M = torch.zeros(op.nnz, dtype=torch.float64, device=dev)
+        d_d = torch.zeros(op.num_dofs, dtype=torch.float64, device=dev)
+        plan.assemble_mass(wts, d_M, d_d, lump=lump)
+        torch.cuda.synchronize()
+        M, d = d_M.cpu().numpy(), d_d.cpu().numpy()
+        assert helpers.rel_err_rows(M, Mref, op.rowptr) < TOL and helpers.rel_err_vec(d, dref) < TOL
+    A = op.csr(M)
+    assert abs(A - A.T).max() < 1e-14 * np.abs(M).max()
+    if name == "le3d":   # HGRAD: partition of unity -> sum of all entries of variable n's block = mass_wts[n] * volume (unit cube)
+        for n in range(3):
+            assert abs(A[n::3, n::3].sum() - wts[n]) < 1e-12
