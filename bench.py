@@ -29,8 +29,12 @@ METRIC = "fp64 residual+Jacobian elements/sec"
 UNIT = "elements/s"
 
 
+WORKLOADS = {"thermal": "thermal hex-Q1", "le": "linear elasticity hex-Q1 (3 dofs/node)", "ns": "Navier-Stokes hex-Q1 ux/pr/uy/uz, SUPG+PSPG, reference uz rows"}
+_WORKLOAD = "thermal"
+
+
 def workload_name(n, world):
-    return "thermal hex-Q1 %dx%dx%d inline brick, steady, residual+Jacobian%s" % (n, n, n * world, "" if world == 1 else " (%d z-slabs of %d^3)" % (world, n))
+    return "%s %dx%dx%d inline brick, steady, residual+Jacobian%s" % (WORKLOADS[_WORKLOAD], n, n, n * world, "" if world == 1 else " (%d z-slabs of %d^3)" % (world, n))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -90,6 +94,17 @@ class ClockSampler:
 # CPU legs (the ONLY places that touch oracle/)
 # --------------------------------------------------------------------------------------------------
 def _oracle_cfg(n, nz):
+    mesh = {"dimension": 3, "element type": "hex", "xmin": 0.0, "xmax": 1.0, "ymin": 0.0, "ymax": 1.0, "zmin": 0.0, "zmax": float(nz) / n, "NX": n, "NY": n, "NZ": nz}
+    if _WORKLOAD == "le":
+        return {"Mesh": mesh, "Physics": {"modules": "linearelasticity", "Dirichlet conditions": {v: {"all boundaries": "0.0"} for v in ("dx", "dy", "dz")}},
+                "Discretization": {"order": {"dx": 1, "dy": 1, "dz": 1}, "quadrature": 2},
+                "Functions": {"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)", "source dy": "sin(2*pi*x)*sin(2*pi*y)", "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"},
+                "Solver": {"solver": "steady-state", "workset size": 100}}
+    if _WORKLOAD == "ns":
+        return {"Mesh": mesh, "Physics": {"modules": "navier stokes", "useSUPG": True, "usePSPG": True,
+                                          "Dirichlet conditions": {v: {"all boundaries": "0.0"} for v in ("ux", "uy", "uz")}},
+                "Discretization": {"order": {"ux": 1, "pr": 1, "uy": 1, "uz": 1}, "quadrature": 2},
+                "Functions": {"source ux": "1.0", "viscosity": "1.0", "density": "1.0"}, "Solver": {"solver": "steady-state", "workset size": 100}}
     return {"Mesh": {"dimension": 3, "element type": "hex", "xmin": 0.0, "xmax": 1.0, "ymin": 0.0, "ymax": 1.0, "zmin": 0.0, "zmax": float(nz) / n,
                      "NX": n, "NY": n, "NZ": nz},
             "Physics": {"modules": "thermal", "Dirichlet conditions": {"T": {"all boundaries": "0.0"}}},
@@ -124,7 +139,7 @@ def cpu_baseline_serial(n, budget_s=15.0):
     """Oracle (scalar C++ restatement, 1 thread == Kokkos::Serial) on a z-slab of the same mesh."""
     from oracle import pyoracle
     pyoracle.build()
-    nz = max(2, min(n, 16))
+    nz = max(2, min(n, 16 if _WORKLOAD == "thermal" else 4))
     _worker_init(n, nz)
     _worker_step(0)
     t_total, elems, reps = 0.0, 0, 0
@@ -149,7 +164,7 @@ def run_reference(args):
     pyoracle.build()
     n = args.n
     cores = max(1, min(os.cpu_count() or 1, 64))
-    nz = 4
+    nz = 4 if _WORKLOAD == "thermal" else 2
     ctx = mp.get_context("fork")
     pools = [ctx.Pool(1, initializer=_worker_init, initargs=(n, nz)) for _ in range(cores)]
     try:
@@ -184,7 +199,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mrhyde_b200.problems import ThermalBrick
+    from mrhyde_b200.problems import SystemBrick, ThermalBrick
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,8 +216,12 @@ def run_ours(args):
     for kv in args.opt:
         k, v = kv.split("=", 1)
         options[k] = v
-    prob = ThermalBrick(3, [n, n, n], device=local, rank=rank, nranks=world, options=options)
+    if _WORKLOAD == "thermal":
+        prob = ThermalBrick(3, [n, n, n], device=local, rank=rank, nranks=world, options=options)
+    else:
+        prob = SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[_WORKLOAD], 3, [n, n, n], device=local, rank=rank, nranks=world, options=options)
     plan = prob.plan
+    general = plan.stat("general") == 1
     if world > 1:
         uid = torch.from_numpy(plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
         dist.broadcast(uid, 0)
@@ -282,6 +301,8 @@ def run_ours(args):
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
         traffic = None
         try:
+            if general:
+                raise KeyError("no ncu traffic figure recorded for the general path")
             traffic = json.load(open(os.path.join(ROOT, "profiles", "thermal_q1_volume_traffic.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -294,7 +315,7 @@ def run_ours(args):
                            "smem_bytes": plan.stat("smem_bytes"), "row_patterns": plan.stat("n_patterns"), "kernel_build": "nvrtc plan-specialised" if plan.stat("jit") else "ahead-of-time",
                            "elements_incl_halo": plan.stat("n_elem_with_halo"), "plan_options": {k: v for k, v in options.items() if k != "accumulate"}, "parallelism": "z-slabs x%d + NCCL halo sum" % world if world > 1 else "1 GPU"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                             "kernel": "mrh_thermal_q1_3d", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                             "kernel": "gen_element_kernel + gen_pull_kernel (general path, whole assemble call)" if general else "mrh_thermal_q1_3d", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * prob.n_rows * world, "d2h_bytes_per_step": 8 * (prob.n_rows + prob.nnz) * world,
                         "steps": e2e_steps, "api": "mrhyde_b200_assemble_jacres_host (pinned host buffers)"},
@@ -313,10 +334,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=128, help="elements per brick edge (per GPU)")
+    ap.add_argument("--n", type=int, default=0, help="elements per brick edge (per GPU); default 128 (thermal), 64 (le), 96 (ns)")
+    ap.add_argument("--workload", default="thermal", choices=sorted(WORKLOADS), help="thermal = BASELINE configs[1] (the headline); le / ns: other modules through the general path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="plan option key=value (tuning experiments), repeatable")
     args = ap.parse_args()
+    global _WORKLOAD
+    _WORKLOAD = args.workload
+    if args.n <= 0:
+        args.n = {"thermal": 128, "le": 64, "ns": 96}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:
