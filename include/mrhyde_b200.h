@@ -121,7 +121,8 @@ int mrhyde_b200_plan_set_function(mrhyde_b200_plan* plan, const char* name, cons
  *   "jit"          = "auto" (default: specialise the kernel with NVRTC when available) | "true" | "false"
  *   "kernel"       = "auto" (default: the sweep kernel where it applies -- thermal, HGRAD order 1 -- else the general
  *                    element kernel + pull) | "general" | "sweep"
- *   "batch elems"  = elements per launch of the general path (0: sized so one batch of element matrices stays L2-resident)
+ *   "batch elems"  = elements per launch of the general path (default -1: one launch over all elements; N > 0: rows are
+ *                    pulled as soon as the batch that completes them has been computed)
  *   "penalty", "incplanestress"   linearelasticity module keys
  *   "column elements", "min chains", "min segment levels", "sweep axis", "threads"   sweep-plan tuning
  * Unknown keys are an error, never silently ignored. */

@@ -820,12 +820,9 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
     }
   }
   // ---- pull schedule
-  int64_t batch_elems = std::stoll(opt(P, "batch elems", "0"));
-  if (batch_elems == 0) {
-    // keep one batch of element matrices near the L2 capacity so that the pull reads them back from cache
-    const int64_t bytes_per_elem = (int64_t)I.N * I.N * 8;
-    batch_elems = std::max<int64_t>(4096, (48ll << 20) / bytes_per_elem);
-  }
+  // one batch by default: measured on the B200, splitting the element range so that a batch of element matrices stays
+  // L2-resident costs more in launch tails than the pull saves in DRAM reads (profiles/r01_general_bench.jsonl)
+  const int64_t batch_elems = std::stoll(opt(P, "batch elems", "-1"));
   try {
     gen_build_pull(M, I.N, H.sides, batch_elems, H);
   } catch (const std::exception& e) {

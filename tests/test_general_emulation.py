@@ -89,3 +89,39 @@ def test_weighted_mass_stages_match_oracle(oracle_lib, product_lib, name, cfg, w
     M, d = np.zeros(op.nnz), np.zeros(op.num_dofs)
     plan.debug_emulate_mass(wts, M, d, lump=lump)
     assert helpers.rel_err_rows(M, Mref, op.rowptr) < TOL and helpers.rel_err_vec(d, dref) < TOL
+
+
+def test_general_path_error_reporting(oracle_lib, product_lib):
+    """Set-up errors of the general path surface as status codes + messages (reference style: set-up errors are loud)."""
+    from mrhyde_b200.capi import AssemblyPlan, MrhydeB200Error
+    op = oracle_lib.OracleProblem(configs.LE_2D)
+    rb = op.ref_basis(0)
+    bases = [dict(type="HGRAD", order=1, card=rb["card"], val=rb["val"], grad=rb["grad"])]
+
+    def make(physics, names):
+        plan = AssemblyPlan(physics, 2, names, [0, 0], bases, op.ndof_elem, op.offsets, op.qpts, op.qwts, device=-1)
+        plan.set_mesh(op.elem_nodes, op.lids)
+        plan.set_graph(op.rowptr, op.colind, op.is_fixed)
+        return plan
+
+    with pytest.raises(MrhydeB200Error, match="has no device kernel"):
+        make("porous", ["dx", "dy"]).finalize()
+    with pytest.raises(MrhydeB200Error, match="variable order"):
+        make("linearelasticity", ["dy", "dx"]).finalize()
+    good = make("linear elasticity", ["dx", "dy"])       # the importer's alias (physicsImporter.cpp:170)
+    good.finalize()
+    assert good.stat("general") == 1
+    # the mass entry point needs the general path; a sweep-kernel plan says so
+    opt = oracle_lib.OracleProblem(configs.variant(configs.THERMAL_2D, **{"Mesh/NX": 4, "Mesh/NY": 4}))
+    sweep = helpers.plan_from_oracle(opt, configs.THERMAL_2D, device=-1)
+    with pytest.raises(MrhydeB200Error, match="general path"):
+        sweep.debug_emulate_mass([1.0], np.zeros(opt.nnz), np.zeros(opt.num_dofs))
+    # a graph that lacks an element coupling is rejected at plan time, not at run time
+    bad = make("linearelasticity", ["dx", "dy"])
+    rp = op.rowptr.copy()
+    keep = np.ones(op.nnz, dtype=bool)
+    keep[rp[5]] = False                                   # drop the first entry of row 5
+    rp[6:] -= 1
+    bad.set_graph(rp, op.colind[keep], op.is_fixed)
+    with pytest.raises(MrhydeB200Error, match="lacks an entry"):
+        bad.finalize()
