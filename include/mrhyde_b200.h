@@ -179,6 +179,11 @@ int mrhyde_b200_assemble_jacres_host(mrhyde_b200_plan* plan, const double* sol, 
 int mrhyde_b200_assemble_mass(mrhyde_b200_plan* plan, const double* mass_wts, int lump, double* mass_values, double* diag,
                               void* stream);
 
+/* applyMassMatrixFree (assemblyManager_mass.hpp:555-800): y (+)= M x with the same weighted per-variable mass blocks, without
+ * forming M (the element kernel's residual stage on x, then a row sum).  x, y: device [n_rows]; y follows the accumulate option
+ * (the reference adds into y). */
+int mrhyde_b200_apply_mass(mrhyde_b200_plan* plan, const double* mass_wts, const double* x, double* y, void* stream);
+
 /* ---- multi-GPU: the Tpetra Export(overlapped -> owned, ADD) replacement ---------------------------
  * (linearAlgebraInterface_matrix.hpp:233-237, _vector.hpp:56-66).  Ghost rows of this rank are summed
  * into the owning rank's rows in fixed neighbour-rank order. */
@@ -227,6 +232,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* plan, const double* sol, co
                                    int compute_residual, double* res, double* jac_values);
 /* Mass-matrix counterpart of mrhyde_b200_plan_debug_emulate (host-only plans; host buffers). */
 int mrhyde_b200_plan_debug_emulate_mass(mrhyde_b200_plan* plan, const double* mass_wts, int lump, double* mass_values, double* diag);
+int mrhyde_b200_plan_debug_emulate_apply_mass(mrhyde_b200_plan* plan, const double* mass_wts, const double* x, double* y);
 /* Applies the plan's scatter programs on the host to caller-supplied staged element vectors
  * stage[n_elem][stage_len] (local Jacobian entries then residual entries), with the
  * same ordering and fixed-row rules as the device pull-scatter.  Verifies plan logic only. */

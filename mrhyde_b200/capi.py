@@ -27,6 +27,7 @@ SYMBOLS = [
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
     "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit",
     "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
+    "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
 
 
@@ -100,6 +101,8 @@ def lib():
         L.mrhyde_b200_plan_debug_jit.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.mrhyde_b200_assemble_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_emulate_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_apply_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_plan_debug_emulate_apply_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_emulate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(TimeData), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
@@ -318,6 +321,15 @@ class AssemblyPlan:
         """getWeightedMass: weighted mass values (graph order) and the Jacobi / lumped diagonal vector (device buffers)."""
         w = np.ascontiguousarray(mass_wts, dtype=np.float64)
         self._chk(self.L.mrhyde_b200_assemble_mass(self.h, _ptr(w), int(lump), _ptr(mass_values), _ptr(diag), C.c_void_p(stream) if stream else None))
+
+    def apply_mass(self, mass_wts, x, y, stream=None):
+        """applyMassMatrixFree: y (+)= M x (device buffers)."""
+        w = np.ascontiguousarray(mass_wts, dtype=np.float64)
+        self._chk(self.L.mrhyde_b200_apply_mass(self.h, _ptr(w), _ptr(x), _ptr(y), C.c_void_p(stream) if stream else None))
+
+    def debug_emulate_apply_mass(self, mass_wts, x, y):
+        w = np.ascontiguousarray(mass_wts, dtype=np.float64)
+        self._chk(self.L.mrhyde_b200_plan_debug_emulate_apply_mass(self.h, _ptr(w), _ptr(x), _ptr(y)))
 
     def debug_emulate_mass(self, mass_wts, mass_values, diag, lump=False):
         w = np.ascontiguousarray(mass_wts, dtype=np.float64)

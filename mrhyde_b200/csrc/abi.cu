@@ -1495,6 +1495,21 @@ int mrhyde_b200_assemble_mass(mrhyde_b200_plan* P, const double* mass_wts, int l
   ABI_END
 }
 
+int mrhyde_b200_apply_mass(mrhyde_b200_plan* P, const double* mass_wts, const double* x, double* y, void* stream) {
+  ABI_BEGIN
+  check_mass_plan(P, mass_wts);
+  if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "host-only analysis plan (device = -1) cannot assemble: there is no CPU path");
+  if (!x || !y) fail(MRHYDE_B200_ERR_INVALID, "apply_mass: null vector");
+  CUDA_OK(cudaSetDevice(P->device));
+  GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
+  GenLaunchStats stats;
+  const char* err = gen_apply_mass(P->gen_dev, P->gen, P->gen_kernels, P->d_vx.p, P->d_vy.p, P->d_vz.p, P->d_conn.p, P->d_lids.p, G, mass_wts, P->accumulate,
+                                   x, y, (cudaStream_t)stream, &stats);
+  if (err) fail(MRHYDE_B200_ERR_CUDA, std::string("mass apply launch: ") + err);
+  P->launches_per_assemble = stats.launches;
+  ABI_END
+}
+
 int mrhyde_b200_plan_debug_emulate_mass(mrhyde_b200_plan* P, const double* mass_wts, int lump, double* mass_values, double* diag) {
   ABI_BEGIN
   check_mass_plan(P, mass_wts);
@@ -1522,6 +1537,36 @@ int mrhyde_b200_plan_debug_emulate_mass(mrhyde_b200_plan* P, const double* mass_
   Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
   P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
   gen_pull_mass_host(H, M, ej.data(), P->accumulate, lump != 0, mass_values, diag);
+  ABI_END
+}
+
+int mrhyde_b200_plan_debug_emulate_apply_mass(mrhyde_b200_plan* P, const double* mass_wts, const double* x, double* y) {
+  ABI_BEGIN
+  check_mass_plan(P, mass_wts);
+  if (P->device != -1) fail(MRHYDE_B200_ERR_STATE, "debug_emulate_apply_mass: only host-only analysis plans (device = -1) replay the kernel stages on the host");
+  if (!x || !y) fail(MRHYDE_B200_ERR_INVALID, "debug_emulate_apply_mass: null vector");
+  const GeneralPlanHost& H = P->gen;
+  const GenKernelInfo& I = H.info;
+  const MeshGraph& M = P->mesh;
+  std::vector<double> er((size_t)H.n_inst * (size_t)I.N, 0.0);
+  GenParams Q;
+  std::memset(&Q, 0, sizeof(Q));
+  Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
+  Q.orient = M.orient.empty() ? nullptr : M.orient.data();
+  Q.sol = x;
+  Q.td.alpha_u = 1.0; Q.td.deltat = 1.0;
+  std::memcpy(Q.off, H.off, sizeof(Q.off));
+  std::memcpy(Q.fn, H.fn, sizeof(Q.fn));
+  Q.fn_op = H.fn_op.data(); Q.fn_c = H.fn_c.data(); Q.opt = H.opt;
+  for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = 0; Q.bc_fn[v] = -1; }
+  Q.elem_jac = nullptr; Q.elem_res = er.data();
+  Q.mass_mode = 1;
+  for (int v = 0; v < I.nvars; ++v) Q.mass_wts[v] = mass_wts[v];
+  Q.epb = 3;
+  Q.items = nullptr; Q.item_begin = 0; Q.item_end = M.nelem; Q.inst_base = 0;
+  Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
+  P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
+  gen_pull_apply_host(H, er.data(), P->accumulate, y);
   ABI_END
 }
 

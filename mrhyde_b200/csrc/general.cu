@@ -71,6 +71,18 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
   const int32_t r = __ldg(Q.row_order + k);
   const int64_t rs = __ldg(Q.G.rowptr + r);
   const int len = (int)(__ldg(Q.G.rowptr + r + 1) - rs);
+  if (Q.mass_mode == 3) {   // applyMassMatrixFree: y(r) (+)= sum of the element vectors M_e x_e, volume instances, no fixed-dof handling
+    if (lane == 0) {
+      const int64_t c0 = __ldg(Q.contrib_ptr + k), c1 = __ldg(Q.contrib_ptr + k + 1);
+      double s = 0.0;
+      for (int64_t p = c0; p < c1; ++p) {
+        const int64_t inst = __ldg(Q.contrib + p);
+        if (inst / Q.N < Q.mass_inst_end) s += __ldcs(Q.elem_res + inst);
+      }
+      Q.O.res[r] = (Q.O.accumulate ? Q.O.res[r] : 0.0) + s;
+    }
+    return;
+  }
   if (Q.mass_mode) {
     const int N = Q.N;
     const int64_t c0 = __ldg(Q.contrib_ptr + k), c1 = __ldg(Q.contrib_ptr + k + 1);
@@ -250,6 +262,17 @@ const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const
   return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, D->zero.p, td, true, false, stream, stats, lump ? 2 : 1, mass_wts);
 }
 
+const char* gen_apply_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                           const int32_t* conn, const int32_t* lids, const GraphDev& G, const double* mass_wts, bool accumulate, const double* x, double* y,
+                           void* stream, GenLaunchStats* stats) {
+  TimeDev td;
+  std::memset(&td, 0, sizeof(td));
+  td.alpha_u = 1.0; td.deltat = 1.0;
+  OutDev O;
+  O.jac = nullptr; O.res = y; O.accumulate = accumulate ? 1 : 0;
+  return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, x, td, true, false, stream, stats, 3, mass_wts);
+}
+
 static const char* gen_run_impl_marker = nullptr;
 const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                     const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
@@ -265,8 +288,8 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   std::memcpy(P.fn, H.fn, sizeof(P.fn));
   P.fn_op = D->fn_op.p; P.fn_c = D->fn_c.p; P.opt = H.opt;
   for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
-  P.elem_jac = (O.jac || pull_mass_mode) ? D->elem_jac.p : nullptr;
-  P.elem_res = (O.res && !pull_mass_mode) ? D->elem_res.p : nullptr;
+  P.elem_jac = (pull_mass_mode == 3) ? nullptr : ((O.jac || pull_mass_mode) ? D->elem_jac.p : nullptr);
+  P.elem_res = (pull_mass_mode == 3 || (O.res && !pull_mass_mode)) ? D->elem_res.p : nullptr;
   int launches = 0;
   auto run_elements = [&](bool side, int64_t n_items) -> const char* {
     if (n_items <= 0) return nullptr;

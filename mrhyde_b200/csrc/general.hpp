@@ -88,6 +88,9 @@ void gen_pull_host(const GeneralPlanHost& H, const MeshGraph& m, const double* e
 // weighted-mass variant of the pull: no fixed-row skipping, boundary instances ignored, diagonal vector = Jacobi diagonal or lumped
 void gen_pull_mass_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, bool accumulate, bool lump, double* mass, double* diag);
 
+// applyMassMatrixFree: y (+)= sum over volume instances of the element vectors (no sign flip, no fixed-dof handling)
+void gen_pull_apply_host(const GeneralPlanHost& H, const double* elem_res, bool accumulate, double* y);
+
 // ---- device side (general.cu) ---------------------------------------------------------------------------------
 struct GeneralPlanDev;   // device buffers
 struct GenLaunchStats { int launches = 0; };
@@ -102,5 +105,9 @@ const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenD
 const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                               const int32_t* conn, const int32_t* lids, const GraphDev& G, const double* mass_wts, bool lump, bool accumulate,
                               double* mass, double* diag, void* stream, GenLaunchStats* stats);
+// applyMassMatrixFree: y (+)= M x without forming M (element kernel in mass mode, residual stage only)
+const char* gen_apply_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                           const int32_t* conn, const int32_t* lids, const GraphDev& G, const double* mass_wts, bool accumulate, const double* x, double* y,
+                           void* stream, GenLaunchStats* stats);
 
 }  // namespace mrhyde_b200

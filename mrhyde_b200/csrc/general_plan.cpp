@@ -136,6 +136,19 @@ void gen_pull_mass_host(const GeneralPlanHost& H, const MeshGraph& m, const doub
   }
 }
 
+void gen_pull_apply_host(const GeneralPlanHost& H, const double* elem_res, bool accumulate, double* y) {
+  const int N = H.info.N;
+  for (int64_t k = 0; k < H.n_rows; ++k) {
+    const int32_t r = H.row_order[(size_t)k];
+    double s = 0.0;
+    for (int64_t p = H.contrib_ptr[(size_t)k]; p < H.contrib_ptr[(size_t)k + 1]; ++p) {
+      const int64_t ci = H.contrib[(size_t)p];
+      if (ci / N < H.n_elem) s += elem_res[ci];
+    }
+    y[r] = (accumulate ? y[r] : 0.0) + s;
+  }
+}
+
 void gen_pull_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, const double* elem_res, bool accumulate,
                    double* res, double* jac) {
   const int N = H.info.N;

@@ -95,6 +95,28 @@ class AssemblyManager {
   //   localmass(e, off(i), off(j)) += basis(e,i,k,d) basis(e,j,k,d) wts(e,k) mwt[n]
   // summed into the CSR values with sumIntoValues (no isFixedDOF check), and the diagonal vector: Jacobi
   // (localmass(e,row,row)) or lumped (sum_k |localmass(e,row,col_k)|, the LA-accessible branch :126-148)
+  // applyMassMatrixFree (assemblyManager_mass.hpp:555-800, the !storeMass branch): y(indi) += massval x(indj) per variable block
+  void applyMassMatrixFree(const double* masswts, const double* x, double* y) const {
+    const int ndofE = dofs.ndof_elem;
+    for (const Group& g : groups)
+      for (int e = 0; e < g.numElem; ++e) {
+        const int* LIDs = &g.LIDs[(size_t)e * ndofE];
+        for (size_t n = 0; n < dofs.vars.size(); ++n) {
+          const int b = dofs.vars[n].basis;
+          const Basis& B = dofs.bases[b];
+          const double* cb = &g.basis[b][(size_t)e * B.card * cub.n * B.vdim];
+          const auto& off = dofs.offsets[n];
+          for (int i = 0; i < B.card; ++i)
+            for (int j = 0; j < B.card; ++j) {
+              double massval = 0.0;
+              for (int k = 0; k < cub.n; ++k)
+                for (int d = 0; d < B.vdim; ++d)
+                  massval += cb[((size_t)i * cub.n + k) * B.vdim + d] * cb[((size_t)j * cub.n + k) * B.vdim + d] * g.wts[(size_t)e * cub.n + k] * masswts[n];
+              y[LIDs[off[i]]] += massval * x[LIDs[off[j]]];
+            }
+        }
+      }
+  }
   void weightedMass(const double* masswts, bool lump, double* Mvals, double* diag) const {
     const int ndofE = dofs.ndof_elem;
     std::vector<double> lm((size_t)ndofE * ndofE);

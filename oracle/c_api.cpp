@@ -178,6 +178,13 @@ int oracle_assemble_jacres(void* hv, const double* sol, const double* const* sol
   ORACLE_CATCH(1)
 }
 
+int oracle_apply_mass(void* hv, const double* masswts, const double* x, double* y) {
+  ORACLE_TRY
+  ((OracleHandle*)hv)->am->applyMassMatrixFree(masswts, x, y);
+  return 0;
+  ORACLE_CATCH(1)
+}
+
 int oracle_weighted_mass(void* hv, const double* masswts, int lump, double* Mvals, double* diag) {
   ORACLE_TRY
   ((OracleHandle*)hv)->am->weightedMass(masswts, lump != 0, Mvals, diag);

@@ -201,6 +201,14 @@ class OracleProblem:
         self._chk(self.L.oracle_assemble_res(self.h, _p(sol, C.c_double), pp, ps, _p(res, C.c_double)))
         return res
 
+    def apply_mass(self, mass_wts, x):
+        """applyMassMatrixFree: y = M x (y starts at zero)."""
+        w = np.ascontiguousarray(mass_wts, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(self.num_dofs)
+        self._chk(self.L.oracle_apply_mass(self.h, _p(w, C.c_double), _p(x, C.c_double), _p(y, C.c_double)))
+        return y
+
     def weighted_mass(self, mass_wts, lump=False):
         """getWeightedMass: (mass values in graph order, diagonal vector)."""
         w = np.ascontiguousarray(mass_wts, dtype=np.float64)

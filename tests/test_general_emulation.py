@@ -125,3 +125,17 @@ def test_general_path_error_reporting(oracle_lib, product_lib):
     bad.set_graph(rp, op.colind[keep], op.is_fixed)
     with pytest.raises(MrhydeB200Error, match="lacks an entry"):
         bad.finalize()
+
+
+@pytest.mark.parametrize("name,cfg,wts", MASS_CASES, ids=[c[0] for c in MASS_CASES])
+def test_mass_apply_stages_match_oracle(oracle_lib, product_lib, name, cfg, wts):
+    """applyMassMatrixFree: y = M x without forming M, against the oracle and against the assembled mass matrix."""
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options={"kernel": "general"})
+    x = np.random.default_rng(11).standard_normal(op.num_dofs)
+    yref = op.apply_mass(wts, x)
+    y = np.zeros(op.num_dofs)
+    plan.debug_emulate_apply_mass(wts, x, y)
+    assert helpers.rel_err_vec(y, yref) < TOL
+    M, _ = op.weighted_mass(wts)
+    assert helpers.rel_err_vec(op.csr(M) @ x, yref) < 1e-12

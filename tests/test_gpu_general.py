@@ -147,6 +147,12 @@ def test_weighted_mass_matches_oracle(oracle_lib, product_lib, name, cfg, wts):
         assert helpers.rel_err_rows(M, Mref, op.rowptr) < TOL and helpers.rel_err_vec(d, dref) < TOL
     A = op.csr(M)
     assert abs(A - A.T).max() < 1e-14 * np.abs(M).max()
+    # applyMassMatrixFree: y = M x without forming M
+    x = np.random.default_rng(11).standard_normal(op.num_dofs)
+    d_y = torch.zeros(op.num_dofs, dtype=torch.float64, device=dev)
+    plan.apply_mass(wts, _dev(x), d_y)
+    torch.cuda.synchronize()
+    assert helpers.rel_err_vec(d_y.cpu().numpy(), op.apply_mass(wts, x)) < TOL
     if name == "le3d":   # HGRAD: partition of unity -> sum of all entries of variable n's block = mass_wts[n] * volume (unit cube)
         for n in range(3):
             assert abs(A[n::3, n::3].sum() - wts[n]) < 1e-12
