@@ -29,7 +29,7 @@ METRIC = "fp64 residual+Jacobian elements/sec"
 UNIT = "elements/s"
 
 
-WORKLOADS = {"thermal": "thermal hex-Q1", "le": "linear elasticity hex-Q1 (3 dofs/node)", "ns": "Navier-Stokes hex-Q1 ux/pr/uy/uz, SUPG+PSPG, reference uz rows"}
+WORKLOADS = {"thermal": "thermal hex-Q1", "le": "linear elasticity hex-Q1 (3 dofs/node)", "leq2": "linear elasticity hex-Q2 (81 dofs/element, 27 Gauss points)", "ns": "Navier-Stokes hex-Q1 ux/pr/uy/uz, SUPG+PSPG, reference uz rows"}
 _WORKLOAD = "thermal"
 
 
@@ -95,6 +95,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 def _oracle_cfg(n, nz):
     mesh = {"dimension": 3, "element type": "hex", "xmin": 0.0, "xmax": 1.0, "ymin": 0.0, "ymax": 1.0, "zmin": 0.0, "zmax": float(nz) / n, "NX": n, "NY": n, "NZ": nz}
+    if _WORKLOAD == "leq2":
+        return {"Mesh": mesh, "Physics": {"modules": "linearelasticity", "Dirichlet conditions": {v: {"all boundaries": "0.0"} for v in ("dx", "dy", "dz")}},
+                "Discretization": {"order": {"dx": 2, "dy": 2, "dz": 2}, "quadrature": 4},
+                "Functions": {"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)*sin(pi*z)", "source dy": "sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)",
+                              "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"},
+                "Solver": {"solver": "steady-state", "workset size": 100}}
     if _WORKLOAD == "le":
         return {"Mesh": mesh, "Physics": {"modules": "linearelasticity", "Dirichlet conditions": {v: {"all boundaries": "0.0"} for v in ("dx", "dy", "dz")}},
                 "Discretization": {"order": {"dx": 1, "dy": 1, "dz": 1}, "quadrature": 2},
@@ -139,7 +145,9 @@ def cpu_baseline_serial(n, budget_s=15.0):
     """Oracle (scalar C++ restatement, 1 thread == Kokkos::Serial) on a z-slab of the same mesh."""
     from oracle import pyoracle
     pyoracle.build()
-    nz = max(2, min(n, 16 if _WORKLOAD == "thermal" else 4))
+    nz = max(1, min(n, 16 if _WORKLOAD == "thermal" else (1 if _WORKLOAD == "leq2" else 4)))
+    if _WORKLOAD == "leq2":
+        n = min(n, 24)      # the oracle's SFad<81> pass over a 24 x 24 x 1 slab already takes seconds
     _worker_init(n, nz)
     _worker_step(0)
     t_total, elems, reps = 0.0, 0, 0
@@ -164,7 +172,9 @@ def run_reference(args):
     pyoracle.build()
     n = args.n
     cores = max(1, min(os.cpu_count() or 1, 64))
-    nz = 4 if _WORKLOAD == "thermal" else 2
+    nz = 4 if _WORKLOAD == "thermal" else (1 if _WORKLOAD == "leq2" else 2)
+    if _WORKLOAD == "leq2":
+        n = min(n, 24)
     ctx = mp.get_context("fork")
     pools = [ctx.Pool(1, initializer=_worker_init, initargs=(n, nz)) for _ in range(cores)]
     try:
@@ -199,7 +209,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mrhyde_b200.problems import SystemBrick, ThermalBrick
+    from mrhyde_b200.problems import ElasticityQ2Brick, SystemBrick, ThermalBrick
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,7 +228,11 @@ def run_ours(args):
     for kv in args.opt:
         k, v = kv.split("=", 1)
         options[k] = v
-    if _WORKLOAD == "thermal":
+    if _WORKLOAD == "leq2":
+        if world > 1:
+            raise RuntimeError("the hex-Q2 workload is single-GPU in this round (no slab partition of the Q2 lattice yet)")
+        prob = ElasticityQ2Brick(n, device=local, options=options)
+    elif _WORKLOAD == "thermal":
         prob = ThermalBrick(3, [n, n, n], device=local, rank=rank, nranks=world, options=options)
     else:
         prob = SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[_WORKLOAD], 3, [n, n, n], device=local, rank=rank, nranks=world, options=options)
@@ -336,7 +350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="elements per brick edge (per GPU); default 128 (thermal), 64 (le), 96 (ns)")
+    ap.add_argument("--n", type=int, default=0, help="elements per brick edge (per GPU); default 128 (thermal), 64 (le), 96 (ns), 48 (leq2; BASELINE configs[2] is 64)")
     ap.add_argument("--workload", default="thermal", choices=sorted(WORKLOADS), help="thermal = BASELINE configs[1] (the headline); le / ns: other modules through the general path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="plan option key=value (tuning experiments), repeatable")
@@ -344,7 +358,7 @@ def main():
     global _WORKLOAD
     _WORKLOAD = args.workload
     if args.n <= 0:
-        args.n = {"thermal": 128, "le": 64, "ns": 96}[args.workload]
+        args.n = {"thermal": 128, "le": 64, "ns": 96, "leq2": 48}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

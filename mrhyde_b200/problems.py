@@ -201,3 +201,102 @@ class SystemBrick:
     def algorithmic_bytes(self):
         nd = self.lids.shape[1]
         return 4.0 * nd * self.n_elem + 8.0 * self.dim * self.nodes.shape[0] + 8.0 * self.n_rows + 8.0 * self.n_rows + 8.0 * self.nnz
+
+
+def q2_reference_3d():
+    """3-point tensor Gauss rule (degree 4 = 2 * order, x fastest) and the HGRAD hex C2 (equispaced Lagrange) table at its points,
+    tensor ordinal a + 3 b + 9 c: pts (27, 3), wts (27), val (27, 27, 1), grad (27, 27, 3)."""
+    g = np.sqrt(0.6)
+    x1, w1 = np.array([-g, 0.0, g]), np.array([5.0, 8.0, 5.0]) / 9.0
+    l = np.stack([x1 * (x1 - 1.0) / 2.0, 1.0 - x1 * x1, x1 * (x1 + 1.0) / 2.0])       # l[a][point]
+    dl = np.stack([x1 - 0.5, -2.0 * x1, x1 + 0.5])
+    pts, wts = np.zeros((27, 3)), np.zeros(27)
+    val, grad = np.zeros((27, 27, 1)), np.zeros((27, 27, 3))
+    for q in range(27):
+        qi = (q % 3, (q // 3) % 3, q // 9)
+        pts[q] = [x1[qi[0]], x1[qi[1]], x1[qi[2]]]
+        wts[q] = w1[qi[0]] * w1[qi[1]] * w1[qi[2]]
+        for o in range(27):
+            a = (o % 3, (o // 3) % 3, o // 9)
+            val[o, q, 0] = l[a[0], qi[0]] * l[a[1], qi[1]] * l[a[2], qi[2]]
+            grad[o, q, 0] = dl[a[0], qi[0]] * l[a[1], qi[1]] * l[a[2], qi[2]]
+            grad[o, q, 1] = l[a[0], qi[0]] * dl[a[1], qi[1]] * l[a[2], qi[2]]
+            grad[o, q, 2] = l[a[0], qi[0]] * l[a[1], qi[1]] * dl[a[2], qi[2]]
+    return pts, wts, val, grad
+
+
+def q2_node_graph(n):
+    """CSR pattern of the nodal hex-Q2 operator on an n^3 brick ((2n+1)^3 lattice nodes): a lattice node couples to every node of
+    the elements that contain it, i.e. per axis the index range [I-2, I+2] for an even (vertex-like) index and [I-1, I+1] for an odd one."""
+    M = 2 * n + 1
+    ax = np.arange(M)
+    lo = np.where(ax % 2 == 0, np.maximum(ax - 2, 0), ax - 1)
+    hi = np.where(ax % 2 == 0, np.minimum(ax + 2, M - 1), ax + 1)
+    cnt1 = hi - lo + 1
+    K, J, I = np.meshgrid(ax, ax, ax, indexing="ij")
+    cnt = (cnt1[I] * cnt1[J] * cnt1[K]).ravel().astype(np.int64)
+    rowptr = np.zeros(M ** 3 + 1, dtype=np.int64)
+    np.cumsum(cnt, out=rowptr[1:])
+    colind = np.empty(int(rowptr[-1]), dtype=np.int32)
+    # rows grouped by their (cx, cy, cz) extents so that each group is a dense block
+    Iv, Jv, Kv = I.ravel(), J.ravel(), K.ravel()
+    for cz in (3, 4, 5):
+        for cy in (3, 4, 5):
+            for cx in (3, 4, 5):
+                sel = np.nonzero((cnt1[Iv] == cx) & (cnt1[Jv] == cy) & (cnt1[Kv] == cz))[0]
+                if len(sel) == 0:
+                    continue
+                dz, dy, dx = np.meshgrid(np.arange(cz), np.arange(cy), np.arange(cx), indexing="ij")
+                cols = ((lo[Iv[sel]][:, None] + dx.ravel()[None, :]) + M * ((lo[Jv[sel]][:, None] + dy.ravel()[None, :]) + M * (lo[Kv[sel]][:, None] + dz.ravel()[None, :])))
+                dst = rowptr[sel][:, None] + np.arange(cx * cy * cz)[None, :]
+                colind[dst.ravel()] = cols.ravel().astype(np.int32)
+    return rowptr, colind
+
+
+class ElasticityQ2Brick:
+    """BASELINE configs[2]: 3-D linear elasticity, hex Q2 (27 nodes x 3 displacement dofs = 81 per element, 3^3 Gauss points),
+    lambda = mu = 1, all-boundary strong Dirichlet, on an n^3 inline brick (Hex8 geometry: the cell topology stays
+    Hexahedron_8, discretizationInterface_basis.hpp:244-252).  One rank."""
+
+    def __init__(self, n, device=0, options=None):
+        self.n = n
+        nodes, conn = im.brick(3, [n, n, n])
+        self.nodes, self.conn = nodes, conn
+        M = 2 * n + 1
+        k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+        base = (2 * i + M * (2 * j + M * 2 * k)).ravel().astype(np.int64)
+        o = np.arange(27)
+        offs = (o % 3) + M * ((o // 3) % 3) + M * M * (o // 9)
+        lat = base[:, None] + offs[None, :]                                                      # (E, 27) lattice node of every basis function
+        self.lids = np.ascontiguousarray((lat[:, :, None] * 3 + np.arange(3)[None, None, :]).reshape(len(base), 81).astype(np.int32))
+        rp, ci = q2_node_graph(n)
+        self.rowptr, self.colind = _expand_graph(rp, ci, 3)
+        self.n_rows = 3 * M ** 3
+        self.n_owned = self.n_rows
+        idx = np.arange(M ** 3)
+        li, lj, lk = idx % M, (idx // M) % M, idx // (M * M)
+        bnd = (li == 0) | (li == M - 1) | (lj == 0) | (lj == M - 1) | (lk == 0) | (lk == M - 1)
+        self.is_fixed = np.repeat(bnd.astype(np.uint8), 3)
+        self.lattice = np.stack([li, lj, lk], axis=1) / float(M - 1)
+        self.n_elem = conn.shape[0]
+        self.nnz = int(self.rowptr[-1])
+        pts, wts, val, grad = q2_reference_3d()
+        offsets = np.ascontiguousarray((np.arange(27)[None, :] * 3 + np.arange(3)[:, None]).astype(np.int32))
+        self.plan = AssemblyPlan("linearelasticity", 3, ["dx", "dy", "dz"], [0, 0, 0], [dict(type="HGRAD", order=2, card=27, val=val, grad=grad)], 81,
+                                 offsets, pts, wts, device=device)
+        for kf, vf in {"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)*sin(pi*z)", "source dy": "sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)",
+                       "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"}.items():
+            self.plan.set_function(kf, vf)
+        for kf, vf in (options or {}).items():
+            self.plan.set_option(kf, vf)
+        self.plan.set_mesh_indexed(nodes, conn, self.lids)
+        self.plan.set_graph(self.rowptr, self.colind, self.is_fixed, n_owned=self.n_owned)
+        self.plan.finalize()
+
+    def state(self, seed=20261017):
+        x = self.lattice
+        u = np.stack([np.prod(np.sin((v + 1) * np.pi * x), axis=1) for v in range(3)], axis=1).reshape(-1)
+        return u + 1e-3 * np.random.default_rng(seed).uniform(-1.0, 1.0, size=self.n_rows)
+
+    def algorithmic_bytes(self):
+        return 4.0 * 81 * self.n_elem + 24.0 * self.nodes.shape[0] + 16.0 * self.n_rows + 8.0 * self.nnz

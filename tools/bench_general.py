@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Times the general path (element kernel + pull) on synthetic bricks: python tools/bench_general.py PHYSICS N [key=value ...]
-PHYSICS = le | ns | thermal (numpy-built bricks) | leq2 | maxwell | thq2 (set up through the oracle's mesh / DOF tables, so
+PHYSICS = le | ns | thermal | leq2 (numpy-built bricks) | maxwell | thq2 (set up through the oracle's mesh / DOF tables, so
 keep N moderate); prints one JSON line (device time per assemble call via CUDA events, elements/s, the
 algorithmic-bytes rate of SURVEY 8(d) and its fraction of the measured HBM peak)."""
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from mrhyde_b200.problems import SystemBrick, ThermalBrick
+from mrhyde_b200.problems import ElasticityQ2Brick, SystemBrick, ThermalBrick
 
 phys, n = sys.argv[1], int(sys.argv[2])
 opts = dict(a.split("=", 1) for a in sys.argv[3:])
@@ -37,6 +37,8 @@ class _OracleBacked:
 if phys == "thermal":
     opts.setdefault("kernel", "general")
     prob = ThermalBrick(3, [n, n, n], device=0, options=opts)
+elif phys == "leq2":
+    prob = ElasticityQ2Brick(n, device=0, options=opts)
 elif phys in ("le", "ns"):
     prob = SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[phys], 3, [n, n, n], device=0, options=opts)
 else:
