@@ -258,34 +258,37 @@ class ElasticityQ2Brick:
     lambda = mu = 1, all-boundary strong Dirichlet, on an n^3 inline brick (Hex8 geometry: the cell topology stays
     Hexahedron_8, discretizationInterface_basis.hpp:244-252).  One rank."""
 
-    def __init__(self, n, device=0, options=None):
+    def __init__(self, n, device=0, options=None, physics="linearelasticity"):
         self.n = n
         nodes, conn = im.brick(3, [n, n, n])
         self.nodes, self.conn = nodes, conn
+        nvar = 3 if physics == "linearelasticity" else 1      # "thermal": scalar hex-Q2 (thermal/2D_verification_highorder's 3-D analogue)
         M = 2 * n + 1
         k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
         base = (2 * i + M * (2 * j + M * 2 * k)).ravel().astype(np.int64)
         o = np.arange(27)
         offs = (o % 3) + M * ((o // 3) % 3) + M * M * (o // 9)
         lat = base[:, None] + offs[None, :]                                                      # (E, 27) lattice node of every basis function
-        self.lids = np.ascontiguousarray((lat[:, :, None] * 3 + np.arange(3)[None, None, :]).reshape(len(base), 81).astype(np.int32))
+        self.lids = np.ascontiguousarray((lat[:, :, None] * nvar + np.arange(nvar)[None, None, :]).reshape(len(base), 27 * nvar).astype(np.int32))
         rp, ci = q2_node_graph(n)
-        self.rowptr, self.colind = _expand_graph(rp, ci, 3)
-        self.n_rows = 3 * M ** 3
+        self.rowptr, self.colind = _expand_graph(rp, ci, nvar) if nvar > 1 else (rp, ci)
+        self.n_rows = nvar * M ** 3
         self.n_owned = self.n_rows
         idx = np.arange(M ** 3)
         li, lj, lk = idx % M, (idx // M) % M, idx // (M * M)
         bnd = (li == 0) | (li == M - 1) | (lj == 0) | (lj == M - 1) | (lk == 0) | (lk == M - 1)
-        self.is_fixed = np.repeat(bnd.astype(np.uint8), 3)
+        self.is_fixed = np.repeat(bnd.astype(np.uint8), nvar)
         self.lattice = np.stack([li, lj, lk], axis=1) / float(M - 1)
         self.n_elem = conn.shape[0]
         self.nnz = int(self.rowptr[-1])
         pts, wts, val, grad = q2_reference_3d()
-        offsets = np.ascontiguousarray((np.arange(27)[None, :] * 3 + np.arange(3)[:, None]).astype(np.int32))
-        self.plan = AssemblyPlan("linearelasticity", 3, ["dx", "dy", "dz"], [0, 0, 0], [dict(type="HGRAD", order=2, card=27, val=val, grad=grad)], 81,
+        offsets = np.ascontiguousarray((np.arange(27)[None, :] * nvar + np.arange(nvar)[:, None]).astype(np.int32))
+        names = ["dx", "dy", "dz"] if nvar == 3 else ["T"]
+        self.plan = AssemblyPlan(physics, 3, names, [0] * nvar, [dict(type="HGRAD", order=2, card=27, val=val, grad=grad)], 27 * nvar,
                                  offsets, pts, wts, device=device)
-        for kf, vf in {"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)*sin(pi*z)", "source dy": "sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)",
-                       "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"}.items():
+        fns = {"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)*sin(pi*z)", "source dy": "sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)",
+               "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"} if nvar == 3 else {"thermal source": THERMAL_SOURCE[3]}
+        for kf, vf in fns.items():
             self.plan.set_function(kf, vf)
         for kf, vf in (options or {}).items():
             self.plan.set_option(kf, vf)
@@ -295,8 +298,101 @@ class ElasticityQ2Brick:
 
     def state(self, seed=20261017):
         x = self.lattice
-        u = np.stack([np.prod(np.sin((v + 1) * np.pi * x), axis=1) for v in range(3)], axis=1).reshape(-1)
+        nvar = self.n_rows // x.shape[0]
+        u = np.stack([np.prod(np.sin((v + 1) * np.pi * x), axis=1) for v in range(nvar)], axis=1).reshape(-1)
         return u + 1e-3 * np.random.default_rng(seed).uniform(-1.0, 1.0, size=self.n_rows)
 
     def algorithmic_bytes(self):
-        return 4.0 * 81 * self.n_elem + 24.0 * self.nodes.shape[0] + 16.0 * self.n_rows + 8.0 * self.nnz
+        return 4.0 * self.lids.shape[1] * self.n_elem + 24.0 * self.nodes.shape[0] + 16.0 * self.n_rows + 8.0 * self.nnz
+
+
+def hcurl_hdiv_reference_3d():
+    """2-point tensor Gauss rule and the lowest-order hex HCURL (12 edge functions: x-, y-, z-directed, tensor order) and
+    HDIV (6 face functions: -x,+x,-y,+y,-z,+z normals) tables at its points.
+    Returns pts, wts, (curl_val (12,8,3), curl_curl (12,8,3)), (div_val (6,8,3), div_div (6,8))."""
+    pts, wts, _, _ = im.q1_reference(3)
+    nq = 8
+    ev, ec = np.zeros((12, nq, 3)), np.zeros((12, nq, 3))
+    fv, fd = np.zeros((6, nq, 3)), np.zeros((6, nq))
+    dl = (-0.5, 0.5)
+    for p in range(nq):
+        x, y, z = pts[p]
+        lx, ly, lz = (0.5 * (1 - x), 0.5 * (1 + x)), (0.5 * (1 - y), 0.5 * (1 + y)), (0.5 * (1 - z), 0.5 * (1 + z))
+        f = 0
+        for k in range(2):
+            for j in range(2):          # x-directed: (ly_j lz_k, 0, 0)
+                ev[f, p, 0] = ly[j] * lz[k]; ec[f, p, 1] = ly[j] * dl[k]; ec[f, p, 2] = -dl[j] * lz[k]; f += 1
+        for k in range(2):
+            for i in range(2):          # y-directed: (0, lx_i lz_k, 0)
+                ev[f, p, 1] = lx[i] * lz[k]; ec[f, p, 0] = -lx[i] * dl[k]; ec[f, p, 2] = dl[i] * lz[k]; f += 1
+        for j in range(2):
+            for i in range(2):          # z-directed: (0, 0, lx_i ly_j)
+                ev[f, p, 2] = lx[i] * ly[j]; ec[f, p, 0] = lx[i] * dl[j]; ec[f, p, 1] = -dl[i] * ly[j]; f += 1
+        c = (x, y, z)
+        f = 0
+        for d in range(3):
+            for i in range(2):          # d-normal: l_i(x_d) e_d
+                fv[f, p, d] = 0.5 * (1 - c[d]) if i == 0 else 0.5 * (1 + c[d]); fd[f, p] = dl[i]; f += 1
+    return pts, wts, (ev, ec), (fv, fd)
+
+
+class MaxwellBrick:
+    """BASELINE configs[4]: 3-D Maxwell, lowest-order HCURL E (12 edge dofs) + HDIV B (6 face dofs) per hex, eps = mu = n = 1,
+    sigma = 0, on an n^3 inline brick; transient stages are supplied per call.  DOF numbering: E edges (x-, y-, z-directed
+    lattices), then B faces (x-, y-, z-normal lattices), all orientation signs +1 on a lexicographic brick.  One rank."""
+
+    def __init__(self, n, device=0, functions=None, options=None):
+        self.n = n
+        nodes, conn = im.brick(3, [n, n, n])
+        self.nodes, self.conn = nodes, conn
+        k, j, i = [a.ravel().astype(np.int64) for a in np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")]
+        n1 = n + 1
+        nxe, nye, nze = n * n1 * n1, n1 * n * n1, n1 * n1 * n
+        cols = []
+        for d in range(12):
+            if d < 4:      # x-directed: d = j + 2k
+                jj, kk = j + (d % 2), k + (d // 2)
+                cols.append(i + n * (jj + n1 * kk))
+            elif d < 8:    # y-directed: d-4 = i + 2k
+                ii, kk = i + ((d - 4) % 2), k + ((d - 4) // 2)
+                cols.append(nxe + ii + n1 * (j + n * kk))
+            else:          # z-directed: d-8 = i + 2j
+                ii, jj = i + ((d - 8) % 2), j + ((d - 8) // 2)
+                cols.append(nxe + nye + ii + n1 * (jj + n1 * k))
+        ne_dofs = nxe + nye + nze
+        nxf, nyf = n1 * n * n, n * n1 * n
+        for d in range(6):
+            dr, s = d // 2, d % 2
+            ii, jj, kk = i + (s if dr == 0 else 0), j + (s if dr == 1 else 0), k + (s if dr == 2 else 0)
+            if dr == 0:
+                cols.append(ne_dofs + ii + n1 * (jj + n * kk))
+            elif dr == 1:
+                cols.append(ne_dofs + nxf + ii + n * (jj + n1 * kk))
+            else:
+                cols.append(ne_dofs + nxf + nyf + ii + n * (jj + n * kk))
+        self.lids = np.ascontiguousarray(np.stack(cols, axis=1).astype(np.int32))
+        self.n_rows = ne_dofs + nxf + nyf + n * n * n1
+        self.n_owned = self.n_rows
+        self.rowptr, self.colind = im.graph_from_lids(self.lids, self.n_rows)
+        self.is_fixed = np.zeros(self.n_rows, dtype=np.uint8)
+        self.n_elem = conn.shape[0]
+        self.nnz = int(self.rowptr[-1])
+        pts, wts, (ev, ec), (fv, fd) = hcurl_hdiv_reference_3d()
+        offsets = np.full((2, 12), -1, dtype=np.int32)
+        offsets[0, :] = np.arange(12)
+        offsets[1, :6] = 12 + np.arange(6)
+        self.plan = AssemblyPlan("maxwell", 3, ["E", "B"], [0, 1], [dict(type="HCURL", order=1, card=12, val=ev, curl=ec), dict(type="HDIV", order=1, card=6, val=fv, div=fd)],
+                                 18, offsets, pts, wts, device=device)
+        for kf, vf in dict({"current x": "sin(2*pi*z)"}, **(functions or {})).items():
+            self.plan.set_function(kf, vf)
+        for kf, vf in (options or {}).items():
+            self.plan.set_option(kf, vf)
+        self.plan.set_mesh_indexed(nodes, conn, self.lids)
+        self.plan.set_graph(self.rowptr, self.colind, self.is_fixed, n_owned=self.n_owned)
+        self.plan.finalize()
+
+    def state(self, seed=20261017):
+        return 0.3 * np.sin(1.0 + 0.7 * np.arange(self.n_rows) / self.n_rows) + 1e-3 * np.random.default_rng(seed).uniform(-1.0, 1.0, self.n_rows)
+
+    def algorithmic_bytes(self):
+        return 4.0 * 18 * self.n_elem + 24.0 * self.nodes.shape[0] + 16.0 * self.n_rows + 8.0 * self.nnz

@@ -208,16 +208,17 @@ def test_navier_stokes_full_size_properties(product_lib):
     assert float(res[uy_free].abs().max()) > 0.0
 
 
-def test_maxwell_full_size_properties(oracle_lib, product_lib):
+def test_maxwell_full_size_properties(product_lib):
     """BASELINE configs[4] (64^3 hex, lowest-order HCURL E + HDIV B, 1.6 M dofs): the problem is linear, so
     res(u) = res(0) - J u must hold to round-off for a BDF1 / backward-Euler stage; the dof and non-zero counts are the
-    closed forms of SURVEY 8(d).  (The oracle only BUILDS the mesh / DOF / graph arrays here; it assembles nothing.)"""
+    closed forms of SURVEY 8(d)."""
     import torch
+    from mrhyde_b200.problems import MaxwellBrick
     n = 64
-    cfg = configs.variant(configs.MAXWELL_3D, **{"Mesh/NX": n, "Mesh/NY": n, "Mesh/NZ": n, "Mesh/perturb": 0.0, "Physics/Dirichlet conditions": {}})
-    op = oracle_lib.OracleProblem(cfg)
+    op = MaxwellBrick(n, device=0, options={"accumulate": "false"})
+    op.num_dofs = op.n_rows
     assert op.num_dofs == 3 * n * (n + 1) ** 2 + 3 * n * n * (n + 1) and op.nnz == 252 * n ** 3 + 69 * n ** 2 + 3 * n
-    plan = helpers.plan_from_oracle(op, cfg, options={"accumulate": "false"})
+    plan = op.plan
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(9)
     u, up = _dev(rng.standard_normal(op.num_dofs)), _dev(rng.standard_normal(op.num_dofs))
