@@ -828,7 +828,7 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
   } catch (const std::exception& e) {
     fail(MRHYDE_B200_ERR_INVALID, e.what());
   }
-  gen_set_epb(std::stoi(opt(P, "elements per cta", "0")));
+  H.epb_override = std::stoi(opt(P, "elements per cta", "0"));
   P->use_general = true;
   P->launches_per_assemble = 2 * (int)H.batches.size();
   for (auto& S : H.sides) if (S.active && !S.items.empty()) ++P->launches_per_assemble;

@@ -14,13 +14,16 @@ namespace {
 
 template <class Phys, int NQ, int NQS, int K, int MAXT, int MINB>
 const char* launch_entry(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream) {
-  static size_t attr[2] = {0, 0};
+  static size_t attr[2][64] = {};   // opt-in shared memory already granted, per (volume | side, device)
+  int devid = 0;
+  cudaGetDevice(&devid);
+  devid &= 63;
   if (threads > MAXT) return "general element kernel: more threads per CTA than the instantiation's launch bounds";
   const void* fn = side ? (const void*)gen_element_kernel<Phys, NQS, K, true, MAXT, MINB> : (const void*)gen_element_kernel<Phys, NQ, K, false, MAXT, MINB>;
-  if (smem > 48 * 1024 && smem > attr[side ? 1 : 0]) {
+  if (smem > 48 * 1024 && smem > attr[side ? 1 : 0][devid]) {
     const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cudaGetErrorString(e);
-    attr[side ? 1 : 0] = smem;
+    attr[side ? 1 : 0][devid] = smem;
   }
   if (side) gen_element_kernel<Phys, NQS, K, true, MAXT, MINB><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
   else gen_element_kernel<Phys, NQ, K, false, MAXT, MINB><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
@@ -225,15 +228,13 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
                     const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
                     bool volume, bool boundary, void* stream, GenLaunchStats* stats, int pull_mass_mode, const double* mass_wts);
 
-static int g_epb_override = 0;
-void gen_set_epb(int epb) { g_epb_override = epb; }
-static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items) {
+static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items, int epb_override) {
   // as many elements per CTA as the launch bounds allow, while MINB CTAs still fit the SM's shared memory
   const int tpe = I.tpe;
   const int sd = side ? I.smem_doubles_side : I.smem_doubles_volume;
   const size_t smem_cap = (size_t)(220 * 1024) / (size_t)std::max(1, I.min_blocks);
   int epb = std::max(1, I.max_threads / tpe);
-  if (g_epb_override > 0) epb = g_epb_override;
+  if (epb_override > 0) epb = epb_override;
   while (epb > 1 && ((size_t)epb * sd * 8 > smem_cap || epb * tpe > I.max_threads)) --epb;
   if (n_items < epb) epb = (int)std::max<int64_t>(1, n_items);
   return epb;
@@ -293,7 +294,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   int launches = 0;
   auto run_elements = [&](bool side, int64_t n_items) -> const char* {
     if (n_items <= 0) return nullptr;
-    const int epb = pick_epb(I, side, n_items);
+    const int epb = pick_epb(I, side, n_items, H.epb_override);
     P.epb = epb;
     const int tpe = I.tpe;
     int threads = ((epb * tpe + 31) / 32) * 32;

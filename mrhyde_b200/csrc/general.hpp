@@ -62,6 +62,7 @@ struct GeneralPlanHost {
   GenKernelInfo info;
   int64_t n_elem = 0, n_inst = 0, n_rows = 0, n_owned = 0;
   int32_t max_row_len = 0;
+  int epb_override = 0;                  // option "elements per cta" (0 = automatic)
   // pull schedule
   std::vector<int32_t> row_order;        // rows sorted by completion batch
   std::vector<int64_t> contrib_ptr;      // [n_rows+1] in row_order order
@@ -96,7 +97,6 @@ struct GeneralPlanDev;   // device buffers
 struct GenLaunchStats { int launches = 0; };
 GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t* dev_bytes, std::string& err);
 void gen_free(GeneralPlanDev* D);
-void gen_set_epb(int epb);   // tuning: elements per CTA of the element kernel (0 = automatic)
 // the whole assemble call: element kernels + pull per batch.  Returns nullptr or an error string.
 const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                          const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
