@@ -224,6 +224,11 @@ int mrhyde_b200_expr_eval_host(int32_t n, const char* const* names, const char* 
  * tables and block size as constants), compiles it for sm_100a -- no device needed -- and optionally writes
  * the source / cubin to files (inspection with cuobjdump -sass).  log receives the compiler output. */
 int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* plan, const char* source_path, const char* cubin_path, char* log, size_t log_cap);
+/* Replays the metric ring of the sweep kernel on the host (element metrics by the kernel's formulas, then the plan's metric
+ * source words) for plans that use it (plan_stat "metric_ring" > 0): checks the plan analysis against the oracle on
+ * machines without a GPU.  All pointers are host pointers; no assemble_* entry point can reach this. */
+int mrhyde_b200_plan_debug_metric_host(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, int accumulate,
+                                       double* res, double* jac_values);
 /* Replays the general path's kernel stage functions (general_kernel.cuh, compiled by the host compiler) and the pull on
  * the host for a host-only plan (device = -1) built with option kernel=general: a debugging aid that lets the kernel
  * logic be checked against the oracle on machines without a GPU.  Fails with ERR_STATE on device plans; the assemble

@@ -113,7 +113,7 @@ struct mrhyde_b200_plan {
   DevBuf<StepRec> d_steps;
   DevBuf<BatchRec> d_batches;
   DevBuf<RowRec> d_rows;
-  DevBuf<uint32_t> d_desc0, d_desc1;
+  DevBuf<uint32_t> d_desc0, d_desc1, d_mdesc0, d_mdesc1;
   // plan-specialised (NVRTC) volume kernel; falls back to the ahead-of-time kernel when absent
   std::map<int, std::unique_ptr<JitKernel>> jit;   // specialised builds keyed by transient * 8 + output mode, built on first use
   bool use_jit = false;
@@ -130,6 +130,8 @@ struct mrhyde_b200_plan {
   int row_tab = 0;
   int jit_min_blocks = 1;
   size_t smem = 0;
+  int metric_ng = 0;               // > 0: the specialised kernels use the metric ring with this many metric entries per element
+  size_t smem_metric[2] = {0, 0};  // dynamic shared memory of the steady / transient metric builds
   int64_t n_affine = 0, n_box = 0;
   int launches_per_assemble = 0;   // kernels launched by the last assemble call
   bool accumulate = true;
@@ -158,7 +160,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -224,6 +226,23 @@ void fill_thermal_tables(const mrhyde_b200_plan* P, ThermalTables<DIM>& T) {
         T.Stab[k][t] = s;
       }
     }
+  // The table entries are small rationals evaluated by quadrature: entries that agree to rounding are made identical and
+  // entries that are zero to rounding exactly zero, so that equal coefficients share a register in the generated kernels
+  // and the box path drops only exact zeros.
+  auto snap = [](double* v, size_t n) {
+    double vmax = 0.0;
+    for (size_t i = 0; i < n; ++i) vmax = std::max(vmax, std::fabs(v[i]));
+    for (size_t i = 0; i < n; ++i) {
+      if (std::fabs(v[i]) <= 1e-13 * vmax) { v[i] = 0.0; continue; }
+      for (size_t j = 0; j < i; ++j) {
+        if (std::fabs(v[i] - v[j]) <= 1e-13 * std::fabs(v[j])) { v[i] = v[j]; break; }
+        if (std::fabs(v[i] + v[j]) <= 1e-13 * std::fabs(v[j])) { v[i] = -v[j]; break; }
+      }
+    }
+  };
+  snap(&T.Stab[0][0], (size_t)S::NG * S::NT);
+  snap(&T.Mtab[0], S::NT);
+  snap(&T.Ltab[0], S::NV);
 }
 
 // ---- source of the plan-specialised kernel: prelude (constants + generated coefficient functions) + embedded headers
@@ -236,9 +255,10 @@ void emit_values(std::string& o, const double* v, size_t n) {
   for (size_t i = 0; i < n; ++i) { o += hexd(v[i]); o += (i + 1 < n) ? "," : ""; }
 }
 std::string pull_codegen(const ChainPlan& cp, int max_patterns);
+std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab);
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
-                               const int64_t (&n_class)[3]) {
+                               const int64_t (&n_class)[3], int metric_ng, int max_patterns) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -251,6 +271,9 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   o += "#define MRH_JIT_HAS_BOX " + std::to_string((n_class[2] > 0 && all_const) ? 1 : 0) + "\n";
   o += "#define MRH_JIT_ALL_CONST " + std::to_string(all_const) + "\n";
   o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
+  if (metric_ng > 0) {   // metric ring (volume_kernel.cuh): parallelepiped cells + constant coefficients only
+    o += "#define MRH_JIT_METRIC 1\n#define MRH_JIT_METRIC_NG " + std::to_string(metric_ng) + "\n#define MRH_JIT_CAP " + std::to_string(cp.cap) + "\n";
+  }
   o += kKernelAbiSrc;
   o += "\nnamespace mrhyde_b200 {\n";
   o += "__device__ __forceinline__ double mrh_abs(double a) { return a < 0.0 ? -a : a; }\n";
@@ -338,18 +361,20 @@ __device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
   // gather patterns of the plan as constant data (warp-uniform reads in the pull phase hit the constant cache)
   const size_t desc_words = cp.desc[0].size();
   if (desc_words > 0 && desc_words * 4 * 2 <= 40 * 1024) {
-    o += "#define MRH_JIT_CONST_DESC 1\n";
+    o += metric_ng > 0 ? "#define MRH_JIT_CONST_MDESC 1\n" : "#define MRH_JIT_CONST_DESC 1\n";
     for (int par = 0; par < 2; ++par) {
-      o += "__constant__ uint4 mrh_desc" + std::to_string(par) + "[" + std::to_string(desc_words / 4) + "] = {";
+      const std::vector<uint32_t>& D = metric_ng > 0 ? cp.mdesc[par] : cp.desc[par];
+      o += std::string("__constant__ uint4 ") + (metric_ng > 0 ? "mrh_mdesc" : "mrh_desc") + std::to_string(par) + "[" + std::to_string(desc_words / 4) + "] = {";
       char b[64];
       for (size_t q = 0; q < desc_words / 4; ++q) {
-        std::snprintf(b, sizeof(b), "{%uu,%uu,%uu,%uu}%s", cp.desc[par][4 * q], cp.desc[par][4 * q + 1], cp.desc[par][4 * q + 2], cp.desc[par][4 * q + 3], q + 1 < desc_words / 4 ? "," : "");
+        std::snprintf(b, sizeof(b), "{%uu,%uu,%uu,%uu}%s", D[4 * q], D[4 * q + 1], D[4 * q + 2], D[4 * q + 3], q + 1 < desc_words / 4 ? "," : "");
         o += b;
       }
       o += "};\n";
     }
   }
-  o += pull_codegen(cp, 3);
+  if (metric_ng > 0) o += pull_codegen_metric(cp, max_patterns, S::NV, S::NG, metric_ng, &T.Stab[0][0], &T.Mtab[0]);
+  else o += pull_codegen(cp, max_patterns);
   o += "}  // namespace mrhyde_b200\n";
   o += kVolumeKernelSrc;
   return o;
@@ -404,6 +429,106 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns) {
         o += "        MRH_ST(" + std::to_string(k0) + ", " + std::to_string(n_jac - k0) + ")\n";
       }
       o += "      }\n      if (HAS_RES) { const double acc = " + sum_expr(n_jac) + "; if (active) { double v = -acc; if (ACC) v += *pres; *pres = v; } }\n";
+      o += "      return true;\n    }\n";
+    }
+    ++emitted;
+  }
+  o += "    default: return false;\n  }\n}\n";
+  return o;
+}
+
+
+// ---- the same for the metric ring: a CSR entry is  sum_e sum_g G_g(e) Stab[g][t_e]  with the element columns, table entries
+// and state slots of the pattern as immediates.  The metric entries of the pattern's element columns are loaded once per row.
+std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab) {
+  std::map<int32_t, int64_t> freq;
+  for (const BatchRec& B : cp.batches) if (!(B.flags & BATCH_FIXED)) freq[B.desc_begin] += B.n_rows;
+  std::vector<std::pair<int64_t, int32_t>> order;
+  for (auto& kv : freq) order.push_back({kv.second, kv.first});
+  std::sort(order.rbegin(), order.rend());
+  const int nt = nv * (nv + 1) / 2;
+  (void)ng_all;
+  std::string o;
+  o += "#define MRH_JIT_PULL_METRIC 1\n";
+  o += "#define MRH_ESB (16u * MRH_JIT_CAP)\n";
+  o += "#define MRH_MD MRH_JIT_METRIC_NG\n#define MRH_B0 (MRH_JIT_METRIC_NG + MRH_JIT_TRANSIENT)\n";
+  o += "#define MRH_U0 (MRH_B0 + " + std::to_string(nv) + ")\n#define MRH_UT0 (MRH_U0 + " + std::to_string(nv) + ")\n";
+  o += "__device__ __forceinline__ double mrh_mlds(unsigned a) { double v; asm volatile(\"ld.shared.f64 %0, [%1];\" : \"=d\"(v) : \"r\"(a)); return v; }\n";
+  o += "#define MRH_ML(off, m) mrh_mlds(rbase + (off) + (m) * MRH_ESB)\n";
+  o += "#define MRH_MST(K0, LIM) { __syncwarp(); if ((LIM) >= 4 || kk_st < (LIM)) { _Pragma(\"unroll\") for (int j = 0; j < 4; ++j) if (rv[j]) { double* p = pj[j] + (K0); "
+       "double v = wbuf[(rsub + 8 * j) * 5 + kk_st]; if (ACC) v += *p; *p = v; } } __syncwarp(); }\n";
+  o += "template <bool HAS_RES, bool HAS_JAC, bool ACC>\n__device__ __forceinline__ bool mrh_pull_metric_special(const int desc_begin, const int parity, const unsigned rbase, "
+       "double* __restrict__ wbuf, const int lane, const int rsub, const int kk_st, double* const (&pj)[4], const bool (&rv)[4], double* pres, const bool active, "
+       "const double au, const double at) {\n";
+  o += "  switch (desc_begin * 2 + parity) {\n";
+  int emitted = 0;
+  for (auto& pr : order) {
+    if (emitted >= max_patterns) break;
+    const int32_t db = pr.second;
+    int n_slots = 0;
+    for (const PatternRec& PR : cp.patterns) if (PR.desc_begin == db) n_slots = PR.n_slots;
+    if (n_slots < 2 || n_slots > 96) continue;
+    const int n_jac = n_slots - 1;
+    for (int par = 0; par < 2; ++par) {
+      auto word = [&](int k, int z) { return cp.mdesc[par][((size_t)db + (size_t)k) * SLOT_SRCS + (size_t)z]; };
+      // element columns of the pattern in order of first use
+      std::vector<uint32_t> cols;
+      auto col_of = [&](uint32_t off) {
+        for (size_t c = 0; c < cols.size(); ++c) if (cols[c] == off) return (int)c;
+        cols.push_back(off);
+        return (int)cols.size() - 1;
+      };
+      for (int k = 0; k < n_slots; ++k) for (int z = 0; z < SLOT_SRCS; ++z) if (word(k, z) != SRC_NONE) col_of(word(k, z) & MSRC_OFF_MASK);
+      o += "    case " + std::to_string(db * 2 + par) + ": {\n";
+      for (size_t c = 0; c < cols.size(); ++c) {
+        for (int g = 0; g < ngu; ++g)
+          o += "      const double g" + std::to_string(c) + "_" + std::to_string(g) + " = MRH_ML(" + std::to_string(cols[c]) + "u, " + std::to_string(g) + ");\n";
+        o += "#if MRH_JIT_TRANSIENT\n      const double m" + std::to_string(c) + " = MRH_ML(" + std::to_string(cols[c]) + "u, MRH_MD);\n#endif\n";
+      }
+      o += "      double racc = 0.0;\n";
+      for (int k0 = 0; k0 < n_jac; k0 += 4) {
+        for (int kk = 0; kk < 4 && k0 + kk < n_jac; ++kk) {
+          const int k = k0 + kk;
+          const std::string a = "a" + std::to_string(k), mm = "mm" + std::to_string(k);
+          std::string ea, em;
+          bool first_a = true, first_m = true;
+          uint32_t w0 = SRC_NONE;
+          for (int z = 0; z < SLOT_SRCS; ++z) {
+            const uint32_t w = word(k, z);
+            if (w == SRC_NONE) continue;
+            if (w0 == SRC_NONE) w0 = w;
+            const int c = col_of(w & MSRC_OFF_MASK), t = (int)((w >> MSRC_T_SHIFT) & 63u);
+            for (int g = 0; g < ngu; ++g) {
+              if (Stab[(size_t)g * nt + t] == 0.0) continue;   // exact zeros of the reference tables add nothing
+              const std::string G = "g" + std::to_string(c) + "_" + std::to_string(g), Sx = hexd(Stab[(size_t)g * nt + t]);   // literal: equal coefficients share a register
+              if (first_a) { ea += "      double " + a + " = " + G + " * " + Sx + ";\n"; first_a = false; }
+              else ea += "      " + a + " = fma(" + G + ", " + Sx + ", " + a + ");\n";
+            }
+            const std::string Mx = hexd(Mtab[t]);
+            if (first_m) { em += "      double " + mm + " = m" + std::to_string(c) + " * " + Mx + ";\n"; first_m = false; }
+            else em += "      " + mm + " = fma(m" + std::to_string(c) + ", " + Mx + ", " + mm + ");\n";
+          }
+          if (first_a) ea += "      double " + a + " = 0.0;\n";
+          if (first_m) em += "      double " + mm + " = 0.0;\n";
+          o += ea;
+          o += "#if MRH_JIT_TRANSIENT\n" + em + "#endif\n";
+          if (w0 != SRC_NONE) {
+            const std::string off = std::to_string(w0 & MSRC_OFF_MASK) + "u", j0 = std::to_string((w0 >> MSRC_J_SHIFT) & 7u);
+            o += "      if (HAS_RES) {\n        racc = fma(" + a + ", MRH_ML(" + off + ", MRH_U0 + " + j0 + "), racc);\n";
+            o += "#if MRH_JIT_TRANSIENT\n        racc = fma(" + mm + ", MRH_ML(" + off + ", MRH_UT0 + " + j0 + "), racc);\n#endif\n      }\n";
+          }
+          o += "#if MRH_JIT_TRANSIENT\n      " + a + " = fma(au, " + a + ", at * " + mm + ");\n#endif\n";
+          o += "      if (HAS_JAC) wbuf[lane * 5 + " + std::to_string(kk) + "] = " + a + ";\n";
+        }
+        o += "      if (HAS_JAC) MRH_MST(" + std::to_string(k0) + ", " + std::to_string(n_jac - k0) + ")\n";
+      }
+      o += "      if (HAS_RES) {\n        double bs = 0.0;\n";
+      for (int z = 0; z < SLOT_SRCS; ++z) {
+        const uint32_t w = word(n_jac, z);
+        if (w == SRC_NONE) continue;
+        o += "        bs += MRH_ML(" + std::to_string(w & MSRC_OFF_MASK) + "u, MRH_B0 + " + std::to_string((w >> MSRC_I_SHIFT) & 7u) + ");\n";
+      }
+      o += "        if (active) { double v = bs - racc; if (ACC) v += *pres; *pres = v; }\n      }\n";
       o += "      return true;\n    }\n";
     }
     ++emitted;
@@ -559,6 +684,14 @@ void record_end(mrhyde_b200_plan* P, cudaStream_t st, size_t slot) {
   ++P->ev_used;
 }
 
+// dynamic shared memory and launch-bound CTAs per SM of a specialised build (the metric ring is smaller in steady builds)
+size_t variant_smem(const mrhyde_b200_plan* P, bool transient) { return P->metric_ng > 0 ? P->smem_metric[transient ? 1 : 0] : P->smem; }
+int variant_min_blocks(const mrhyde_b200_plan* P, size_t smem) {
+  const int want = std::stoi(opt(P, "min blocks", "0"));
+  if (want > 0) return want;
+  return std::max(1, std::min(std::min(8, 2048 / P->threads), (int)((228 * 1024) / (smem + 1024))));
+}
+
 // Specialised kernel for (steady | transient, output mode); compiled by NVRTC on first use.
 const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std::string& log) {
   const int key = (transient ? 8 : 0) + mode;
@@ -577,7 +710,8 @@ const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std:
     return nullptr;
   }
   std::unique_ptr<JitKernel> k(new JitKernel());
-  if (!k->build(src, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, P->jit_min_blocks, P->smem, log)) return nullptr;
+  const size_t smem = variant_smem(P, transient);
+  if (!k->build(src, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, variant_min_blocks(P, smem), smem, log)) return nullptr;
   const JitKernel* raw = k.get();
   P->jit[key] = std::move(k);
   return raw;
@@ -629,7 +763,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
       jk = jit_variant(P, td.transient != 0, mode, log);
       if (!jk) fail(MRHYDE_B200_ERR_CUDA, "jit: kernel build failed: " + log);
     }
-    const char* lerr = P->use_jit ? jk->launch(params, P->cp.n_chains, P->threads, P->smem, st)
+    const char* lerr = P->use_jit ? jk->launch(params, P->cp.n_chains, P->threads, variant_smem(P, td.transient != 0), st)
                                   : launch_thermal_q1_aot(P->dim, params, P->cp.n_chains, P->threads, P->smem, st);
     if (lerr) fail(MRHYDE_B200_ERR_CUDA, std::string("volume kernel launch: ") + lerr);
     record_end(P, st, slot);
@@ -857,6 +991,66 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
 }
 
 }  // namespace
+
+// Host replay of the metric ring: element metrics by the formulas of metric_cell (volume_kernel.cuh), then the plan's
+// metric source words (host_apply_metric_plan).  Checks the plan analysis on machines without a GPU; never reached by assemble_*.
+template <int DIM>
+static void metric_host_elements(const mrhyde_b200_plan* P, const ThermalParams<DIM>& TH, const double* sol, const TimeDev& td, std::vector<double>& out) {
+  typedef Q1Shape<DIM> S;
+  constexpr int NV = S::NV, NQ = S::NQ, NG = S::NG, SL = NG + 1 + 3 * NV;
+  const MeshGraph& M = P->mesh;
+  static const int nb[4] = {0, 1, 3, 4};
+  auto fn = [&](const ExprProgram& p, const double* x) {
+    if (p.is_const) return p.cval;
+    const double v[7] = {x[0], x[1], x[2], td.time, 0.0, 0.0, 0.0};
+    return FunctionSet::eval_host(p, v);
+  };
+  const double xz[3] = {0, 0, 0};
+  const double kap = fn(TH.diffusion, xz), rc = fn(TH.density, xz) * fn(TH.specific_heat, xz);
+  out.assign((size_t)M.nelem * SL, 0.0);
+  for (int64_t e = 0; e < M.nelem; ++e) {
+    double* o = &out[(size_t)e * SL];
+    double X[DIM + 1][DIM], J[DIM][DIM], Ji[DIM][DIM];
+    for (int v = 0; v <= DIM; ++v) for (int d = 0; d < DIM; ++d) X[v][d] = M.vcoord[d][(size_t)M.conn[(size_t)e * NV + nb[v]]];
+    for (int d = 0; d < DIM; ++d) for (int a = 0; a < DIM; ++a) J[d][a] = 0.5 * (X[a + 1][d] - X[0][d]);
+    double det;
+    if (DIM == 2) {
+      det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
+    } else {
+      double c[3][3];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b)
+        c[a][b] = J[(a + 1) % 3][(b + 1) % 3] * J[(a + 2) % 3][(b + 2) % 3] - J[(a + 1) % 3][(b + 2) % 3] * J[(a + 2) % 3][(b + 1) % 3];
+      det = J[0][0] * c[0][0] + J[0][1] * c[0][1] + J[0][2] * c[0][2];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) Ji[a][b] = c[b][a] / det;
+    }
+    const double adet = std::fabs(det), kd = kap * adet;
+    int g = 0;
+    for (int a = 0; a < DIM; ++a) { double t = 0; for (int d = 0; d < DIM; ++d) t += Ji[a][d] * Ji[a][d]; o[g++] = t * kd; }
+    for (int a = 0; a < DIM; ++a) for (int b = a + 1; b < DIM; ++b) { double t = 0; for (int d = 0; d < DIM; ++d) t += Ji[a][d] * Ji[b][d]; o[g++] = t * kd; }
+    o[NG] = rc * adet;
+    for (int q = 0; q < NQ; ++q) {
+      double x[3] = {0, 0, 0};
+      for (int d = 0; d < DIM; ++d) { x[d] = X[0][d]; for (int a = 0; a < DIM; ++a) x[d] += J[d][a] * (TH.tab.qpt[q][a] + 1.0); }
+      const double fw = fn(TH.source, x) * TH.tab.qw[q] * adet;
+      for (int i = 0; i < NV; ++i) o[NG + 1 + i] += fw * TH.tab.phi[q][i];
+    }
+    for (int j = 0; j < NV; ++j) {
+      const int32_t lid = M.lids[(size_t)e * NV + j];
+      double u = sol[lid], ut = 0.0;
+      if (td.transient) {
+        const double p0 = td.prev[0][lid];
+        double bu = td.one_minus_alpha_u * p0;
+        for (int k = 0; k < td.nstage_lo; ++k) bu += td.stage_w[k] * (td.stg[k][lid] - p0);
+        u = td.alpha_u * sol[lid] + bu;
+        double bt = td.bdf[1] * p0;
+        for (int k = 2; k <= td.nprev; ++k) bt += td.bdf[k] * td.prev[k - 1][lid];
+        ut = td.alpha_t * sol[lid] + bt * td.timewt;
+      }
+      o[NG + 1 + NV + j] = u; o[NG + 1 + 2 * NV + j] = ut;
+    }
+  }
+}
 
 extern "C" {
 
@@ -1102,8 +1296,20 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   else { fill_thermal_tables<2>(P, P->th2.tab); fill_host(P->th2); }
   {
     const int64_t n_class[3] = {M.nelem - P->n_affine, P->n_affine - P->n_box, P->n_box};
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class)
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class);
+    // ring = auto | metric | full: the metric ring (volume_kernel.cuh) needs parallelepiped cells throughout and constant
+    // diffusion / specific heat / density; it exists in the plan-specialised build only
+    const std::string ring = opt(P, "ring", "auto");
+    if (ring != "auto" && ring != "metric" && ring != "full") fail(MRHYDE_B200_ERR_INVALID, "option ring must be auto|metric|full");
+    const bool all_const = dif.is_const && cp.is_const && rho.is_const;
+    const bool metric_ok = all_const && n_class[0] == 0 && !P->cp.mdesc[0].empty() && opt(P, "jit", "auto") != "false";
+    if (ring == "metric" && !metric_ok)
+      fail(MRHYDE_B200_ERR_UNSUPPORTED, "ring=metric needs parallelepiped cells throughout, constant diffusion / specific heat / density and the plan-specialised build");
+    P->metric_ng = (metric_ok && ring != "full") ? (n_class[1] == 0 ? P->dim : P->dim * (P->dim + 1) / 2) : 0;
+    for (int tr = 0; tr < 2; ++tr)
+      P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * PULL_WARP_DOUBLES * sizeof(double);
+    const int max_patterns = std::max(0, std::stoi(opt(P, "pull patterns", "3")));
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns)
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns);
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
@@ -1131,6 +1337,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   P->d_batches.upload(CP.batches, tot); P->d_rows.upload(CP.rows, tot);
   P->d_step_conn.upload(CP.step_conn, tot); P->d_step_lids.upload(CP.step_lids, tot); P->d_step_eclass.upload(CP.step_eclass, tot);
   P->d_desc0.upload(CP.desc[0], tot); P->d_desc1.upload(CP.desc[1], tot);
+  if (P->metric_ng > 0) { P->d_mdesc0.upload(CP.mdesc[0], tot); P->d_mdesc1.upload(CP.mdesc[1], tot); }
   P->d_orphans.upload(CP.orphan_rows, tot);
   {
     std::vector<int64_t> diag;
@@ -1148,6 +1355,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   D.batches = P->d_batches.p; D.rows = P->d_rows.p;
   D.step_conn = P->d_step_conn.p; D.step_lids = P->d_step_lids.p; D.step_eclass = P->d_step_eclass.p;
   D.desc0 = reinterpret_cast<const SrcQuad*>(P->d_desc0.p); D.desc1 = reinterpret_cast<const SrcQuad*>(P->d_desc1.p);
+  D.mdesc0 = reinterpret_cast<const SrcQuad*>(P->d_mdesc0.p); D.mdesc1 = reinterpret_cast<const SrcQuad*>(P->d_mdesc1.p);
   D.cap = CP.cap;
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
   auto fill_common = [&](auto& th) {
@@ -1169,8 +1377,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
       std::string log;
       // build the variant the first assemble call will most likely use (steady, residual + Jacobian, current accumulate mode)
       if (jit_variant(P, false, 3 | (P->accumulate ? 4 : 0), log)) P->use_jit = true;
-      else if (want == "true") fail(MRHYDE_B200_ERR_CUDA, "jit=true but the plan could not be specialised: " + log);
-      else P->jit_note = log;
+      else if (want == "true" || opt(P, "ring", "auto") == "metric") fail(MRHYDE_B200_ERR_CUDA, "the plan could not be specialised: " + log);
+      else { P->jit_note = log; P->metric_ng = 0; }   // the ahead-of-time kernel keeps full local systems in the ring
     }
   }
 
@@ -1319,7 +1527,8 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "max_rows_per_step") *value = P->cp.max_rows_step;
   else if (k == "kernel_launches_per_assemble") *value = P->launches_per_assemble;
   else if (k == "halo_launches_per_sum") *value = P->halo ? P->halo->launches_per_sum() : 0;
-  else if (k == "smem_bytes") *value = (int64_t)P->smem;
+  else if (k == "smem_bytes") *value = (int64_t)variant_smem(P, false);
+  else if (k == "metric_ring") *value = P->metric_ng;
   else if (k == "threads_per_block") *value = P->threads;
   else if (k == "n_elem") *value = P->mesh.nelem;
   else if (k == "n_elem_with_halo") *value = P->cp.n_elem_with_halo;
@@ -1409,7 +1618,7 @@ int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* P, const char* source_path, con
     std::fclose(f);
   }
   std::string cubin, text;
-  const int min_blocks = std::max(1, std::min(std::min(8, 2048 / P->threads), (int)((228 * 1024) / (P->smem + 1024))));
+  const int min_blocks = variant_min_blocks(P, variant_smem(P, false));
   const bool ok = nvrtc_compile(P->jit_source, P->threads, min_blocks, cubin, text);
   if (log && log_cap) { std::snprintf(log, log_cap, "%s", text.c_str()); }
   if (!ok) fail(MRHYDE_B200_ERR_CUDA, "debug_jit: " + text);
@@ -1567,6 +1776,20 @@ int mrhyde_b200_plan_debug_emulate_apply_mass(mrhyde_b200_plan* P, const double*
   Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
   P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
   gen_pull_apply_host(H, er.data(), P->accumulate, y);
+  ABI_END
+}
+
+int mrhyde_b200_plan_debug_metric_host(mrhyde_b200_plan* P, const double* sol, const mrhyde_b200_time* t, int accumulate, double* res, double* jac) {
+  ABI_BEGIN
+  if (!P || !sol) fail(MRHYDE_B200_ERR_INVALID, "debug_metric_host: null argument");
+  if (!P->finalized || P->use_general) fail(MRHYDE_B200_ERR_STATE, "debug_metric_host: needs a finalized plan on the sweep kernel");
+  if (P->metric_ng <= 0) fail(MRHYDE_B200_ERR_STATE, "debug_metric_host: this plan does not use the metric ring (general cells, non-constant coefficients or ring=full)");
+  TimeDev td;
+  fill_time(t, td, true);   // host pointers: the replay reads them on the host
+  std::vector<double> met;
+  const int ng = P->dim * (P->dim + 1) / 2;
+  if (P->dim == 3) { metric_host_elements<3>(P, P->th3, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th3.tab.Stab[0][0], &P->th3.tab.Mtab[0], td.alpha_u, td.transient ? td.alpha_t : 0.0, accumulate != 0, res, jac); }
+  else { metric_host_elements<2>(P, P->th2, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th2.tab.Stab[0][0], &P->th2.tab.Mtab[0], td.alpha_u, td.transient ? td.alpha_t : 0.0, accumulate != 0, res, jac); }
   ABI_END
 }
 

@@ -49,6 +49,17 @@ constexpr int SLOT_SRCS = 8;
 
 struct SrcQuad { uint32_t x, y, z, w; };  // half a slot descriptor (read as uint4 on the device)
 
+// METRIC ring (volume_kernel.cuh, MRH_JIT_METRIC): on parallelepiped cells with constant coefficients the local matrix is
+// a fixed linear combination of reference tables, K_e = sum_g G_g(e) Stab[g], so a step stages only the element's scaled
+// metric G (+ load vector and state) and the pull evaluates the combination per CSR entry.  The two ring slots are
+// interleaved entry by entry -- entry m of element column c in slot s sits at double (m * 2 + s) * cap + c -- so a source
+// is addressed by its element column alone.  A metric source word packs
+//   bits  0..11  byte offset of the element column relative to the row's anchor: ((rel ^ parity) * cap + le - anchor) * 8
+//   bits 12..17  upper-triangle index of the local entry (i, j)     bits 18..20  local column j     bits 21..23  local row i
+// with the same slot / source order as the plain descriptors (mdesc[parity] parallels desc[parity]).
+constexpr uint32_t MSRC_OFF_MASK = 0xFFFu;
+constexpr int MSRC_T_SHIFT = 12, MSRC_J_SHIFT = 18, MSRC_I_SHIFT = 21;
+
 struct ChainDev {
   const int32_t* chain_step_ptr;   // [n_chains+1]
   const StepRec* steps;
@@ -60,6 +71,8 @@ struct ChainDev {
   const RowRec* rows;
   const SrcQuad* desc0;            // parity 0 / 1 descriptor tables, 2 SrcQuad per slot
   const SrcQuad* desc1;
+  const SrcQuad* mdesc0;           // metric-ring source words (same indexing as desc0 / desc1)
+  const SrcQuad* mdesc1;
   int32_t cap;                     // ring slot capacity (elements)
 };
 

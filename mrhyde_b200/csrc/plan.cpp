@@ -359,6 +359,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
     out.cap = std::max(1, max_step_elems.load());
     const uint32_t cap = (uint32_t)out.cap;
     const uint32_t slot_bytes = (uint32_t)out.slot_bytes();
+    const bool metric_ok = nd <= 8 && cap <= 256;   // field widths of the metric source word
 
     // ---- pass 2: rows of every step and their gather patterns
     std::unordered_map<std::string, int32_t> pattern_ids;
@@ -368,6 +369,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       std::vector<int32_t> tag_cur, tag_prev;
       std::unordered_map<std::string, int32_t> cache;   // thread-local view of pattern_ids
       std::vector<std::vector<uint32_t>> slot_src;      // per CSR slot (+ residual): packed (slot_rel, le, t)
+      std::vector<std::vector<uint8_t>> slot_ij;        // same order: local row i << 3 | local column j (metric words)
       std::string key;
     };
     std::vector<Scratch> scratch((size_t)nthreads);
@@ -415,8 +417,8 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
             step_rows.push_back(SR);
             continue;
           }
-          if (S.slot_src.size() < (size_t)len + 1) S.slot_src.resize((size_t)len + 1);
-          for (int32_t k = 0; k <= len; ++k) S.slot_src[(size_t)k].clear();
+          if (S.slot_src.size() < (size_t)len + 1) { S.slot_src.resize((size_t)len + 1); S.slot_ij.resize((size_t)len + 1); }
+          for (int32_t k = 0; k <= len; ++k) { S.slot_src[(size_t)k].clear(); S.slot_ij[(size_t)k].clear(); }
           uint32_t anchor = 0xFFFFFFFFu;
           for (int64_t q = r2e_ptr[(size_t)r]; q < r2e_ptr[(size_t)r + 1]; ++q) {
             const int32_t e = r2e_elem[(size_t)q];
@@ -431,8 +433,10 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
               const int32_t* it = std::lower_bound(cols, cols + len, cj);
               if (it == cols + len || *it != cj) throw std::runtime_error("plan: graph is missing an element coupling (row " + std::to_string(r) + ", col " + std::to_string(cj) + ")");
               S.slot_src[(size_t)(it - cols)].push_back((rel << 31) | (le << 12) | (uint32_t)kmap[(size_t)i * nd + j]);
+              S.slot_ij[(size_t)(it - cols)].push_back((uint8_t)((i << 3) | j));
             }
             S.slot_src[(size_t)len].push_back((rel << 31) | (le << 12) | (uint32_t)rmap[(size_t)i]);
+            S.slot_ij[(size_t)len].push_back((uint8_t)(i << 3));
           }
           // slot descriptors (parity 0), keyed for de-duplication
           std::string& key = S.key;
@@ -448,6 +452,19 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
               } else put(SRC_NONE);
             }
           }
+          const size_t legacy_words = key.size() / 4;
+          if (metric_ok)   // metric-ring words (kernel_abi.h), appended to the key: a pattern is one (desc, mdesc) pair
+            for (int32_t k = 0; k <= len; ++k) {
+              const auto& src = S.slot_src[(size_t)k];
+              for (int z = 0; z < SLOT_SRCS; ++z) {
+                if ((size_t)z < src.size()) {
+                  const uint32_t rel = src[(size_t)z] >> 31, le = (src[(size_t)z] >> 12) & 0x7FFFFu;
+                  const uint32_t i = S.slot_ij[(size_t)k][(size_t)z] >> 3, j = S.slot_ij[(size_t)k][(size_t)z] & 7u;
+                  const uint32_t a = std::min(i, j), b = std::max(i, j), t = (k == len) ? 0u : a * (uint32_t)nd - (a * (a - 1)) / 2 + (b - a);
+                  put(((rel * cap + (le - anchor)) * 8u) | (t << MSRC_T_SHIFT) | (j << MSRC_J_SHIFT) | (i << MSRC_I_SHIFT));
+                } else put(SRC_NONE);
+              }
+            }
           int32_t pid;
           auto itc = S.cache.find(key);
           if (itc != S.cache.end()) pid = itc->second;
@@ -461,12 +478,22 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
               PR.desc_begin = (int32_t)(out.desc[0].size() / SLOT_SRCS); PR.n_slots = len + 1;
               out.patterns.push_back(PR);
               const uint32_t* w = (const uint32_t*)key.data();
-              for (size_t z = 0; z < key.size() / 4; ++z) {
+              for (size_t z = 0; z < legacy_words; ++z) {
                 const uint32_t s0 = w[z];
                 uint32_t s1 = s0;
                 if (s0 != SRC_NONE) s1 = (s0 >= slot_bytes) ? s0 - slot_bytes : s0 + slot_bytes;
                 out.desc[0].push_back(s0);
                 out.desc[1].push_back(s1);
+              }
+              for (size_t z = legacy_words; z < key.size() / 4; ++z) {   // parity 1: the current step writes the odd slot
+                const uint32_t s0 = w[z];
+                uint32_t s1 = s0;
+                if (s0 != SRC_NONE) {
+                  const uint32_t off = s0 & MSRC_OFF_MASK;
+                  s1 = (s0 & ~MSRC_OFF_MASK) | (off >= cap * 8u ? off - cap * 8u : off + cap * 8u);
+                }
+                out.mdesc[0].push_back(s0);
+                out.mdesc[1].push_back(s1);
               }
               pattern_ids.emplace(key, pid);
             }
@@ -583,6 +610,62 @@ void host_apply_chain_plan(const MeshGraph& m, const ChainPlan& cp, const double
             }
             if (k == len) { if (res) { if (accumulate) res[R.row] += -acc; else res[R.row] = -acc; } }
             else if (jac) { if (accumulate) jac[base + k] += acc; else jac[base + k] = acc; }
+          }
+        }
+      }
+    }
+  }
+}
+
+void host_apply_metric_plan(const MeshGraph& m, const ChainPlan& cp, const double* metric, int ng, const double* Stab, const double* Mtab,
+                            double alpha_u, double alpha_t, bool accumulate, double* res, double* jac) {
+  if (cp.mdesc[0].size() != cp.desc[0].size()) throw std::runtime_error("plan: no metric source words for this plan");
+  const int nd = m.ndof, nt = nd * (nd + 1) / 2, SL = ng + 1 + 3 * nd;
+  const int64_t cap = cp.cap, ES = 2 * cap;   // doubles between consecutive entries of one element column
+  const int MD = ng, B0 = ng + 1, U0 = B0 + nd, UT0 = U0 + nd;
+  std::vector<double> ring((size_t)(ES * SL), 0.0);
+  for (int32_t c = 0; c < cp.n_chains; ++c) {
+    for (int32_t s = cp.chain_step_ptr[(size_t)c]; s < cp.chain_step_ptr[(size_t)c + 1]; ++s) {
+      const StepRec& ST = cp.steps[(size_t)s];
+      const int parity = (s - cp.chain_step_ptr[(size_t)c]) & 1;
+      for (int32_t l = 0; l < ST.n_elem; ++l) {
+        const int32_t e = cp.step_elems[(size_t)(ST.elem_begin + l)];
+        for (int t = 0; t < SL; ++t) ring[(size_t)((int64_t)t * ES + parity * cap + l)] = metric[(size_t)e * SL + t];
+      }
+      for (int32_t b = 0; b < ST.n_batches; ++b) {
+        const BatchRec& B = cp.batches[(size_t)(ST.batch_begin + b)];
+        for (int32_t lane = 0; lane < (int32_t)B.n_rows; ++lane) {
+          const RowRec& R = cp.rows[(size_t)(ST.batch_begin + b) * 32 + (size_t)lane];
+          const int64_t base = R.base;
+          const int32_t len = (int32_t)(m.rowptr[(size_t)R.row + 1] - base);
+          if (B.flags & BATCH_FIXED) {
+            if (!accumulate) {
+              if (jac) for (int32_t k = 0; k < len; ++k) jac[base + k] = (k == (int32_t)R.aux) ? 1.0 : 0.0;
+              if (res) res[R.row] = 0.0;
+            }
+            continue;
+          }
+          double racc = 0.0;
+          for (int32_t k = 0; k <= len; ++k) {
+            const uint32_t* w = &cp.mdesc[parity][((size_t)B.desc_begin + (size_t)k) * SLOT_SRCS];
+            if (k == len) {
+              double bs = 0.0;
+              for (int z = 0; z < SLOT_SRCS && w[z] != SRC_NONE; ++z)
+                bs += ring[(size_t)((w[z] & MSRC_OFF_MASK) / 8 + R.anchor + (int64_t)(B0 + (int)((w[z] >> MSRC_I_SHIFT) & 7u)) * ES)];
+              if (res) { const double v = bs - racc; if (accumulate) res[R.row] += v; else res[R.row] = v; }
+              break;
+            }
+            double kp = 0.0, mp = 0.0;
+            for (int z = 0; z < SLOT_SRCS && w[z] != SRC_NONE; ++z) {
+              const int64_t col = (w[z] & MSRC_OFF_MASK) / 8 + R.anchor;
+              const int t = (int)((w[z] >> MSRC_T_SHIFT) & 63u);
+              for (int g = 0; g < ng; ++g) kp += ring[(size_t)(col + (int64_t)g * ES)] * Stab[(size_t)g * nt + t];
+              mp += ring[(size_t)(col + (int64_t)MD * ES)] * Mtab[t];
+            }
+            const int64_t col0 = (w[0] & MSRC_OFF_MASK) / 8 + R.anchor;
+            const int j0 = (int)((w[0] >> MSRC_J_SHIFT) & 7u);
+            racc += kp * ring[(size_t)(col0 + (int64_t)(U0 + j0) * ES)] + mp * ring[(size_t)(col0 + (int64_t)(UT0 + j0) * ES)];
+            if (jac) { const double v = alpha_u * kp + alpha_t * mp; if (accumulate) jac[base + k] += v; else jac[base + k] = v; }
           }
         }
       }

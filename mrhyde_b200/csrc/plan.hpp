@@ -54,6 +54,7 @@ struct ChainPlan {
   std::vector<RowRec> rows;
   std::vector<PatternRec> patterns;
   std::vector<uint32_t> desc[2];         // SLOT_SRCS per slot
+  std::vector<uint32_t> mdesc[2];        // metric-ring source words, parallel to desc (kernel_abi.h); empty when ndof > 8
   std::vector<int32_t> orphan_rows;      // rows no element touches
   int64_t slot_bytes() const { return (int64_t)cap * stage_len * 8; }
 };
@@ -75,5 +76,11 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
 // Applies the plan on the host to caller-supplied staged element vectors stage[nelem][stage_len], walking
 // chains, ring slots, patterns and lane items exactly like the device pull phase (plan verification).
 void host_apply_chain_plan(const MeshGraph& m, const ChainPlan& cp, const double* stage, bool accumulate, double* res, double* jac);
+
+// Host replay of the METRIC pull (kernel_abi.h): `metric` holds, per element, [ng scaled metric entries | md | load[nd] | u[nd] | ut[nd]]
+// (stride ng + 1 + 3 nd); Stab[ng][nt], Mtab[nt] are the reference tables.  Walks chains, interleaved ring slots and mdesc words
+// exactly like the device code:  J_k = alpha_u sum G Stab + alpha_t sum md Mtab,  res = -(sum_k (K_k u_k + M_k ut_k) - sum load).
+void host_apply_metric_plan(const MeshGraph& m, const ChainPlan& cp, const double* metric, int ng, const double* Stab, const double* Mtab,
+                            double alpha_u, double alpha_t, bool accumulate, double* res, double* jac);
 
 }  // namespace mrhyde_b200

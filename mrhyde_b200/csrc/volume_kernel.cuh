@@ -552,9 +552,246 @@ __device__ __forceinline__ BatchRegs fetch_batch(const ChainDev& C, const GraphD
   return R;
 }
 
-template <bool HAS_RES, bool HAS_JAC, bool ACC>
+#ifdef MRH_JIT_METRIC
+// ---------------------------------------------------------------------------------------------------------
+// METRIC ring (kernel_abi.h; plan-specialised builds only).  When every cell of the plan is a parallelepiped and
+// diffusion / specific heat / density are constants, the local matrix is K_e = sum_g G_g(e) Stab[g] (+ md_e Mtab):
+// phase 1 stages G (3 doubles on boxes, 6 on sheared cells), the load vector and the element state instead of
+// the 36 + 8 doubles of the full local system, and the pull evaluates
+//   J(row, k)  = alpha_u sum_e sum_g G_g(e) Stab[g][t_e] + alpha_t sum_e md_e Mtab[t_e]
+//   res(row)   = -( sum_k (K_k u_k + M_k ut_k) - sum_e load_e[i_e] )
+// per CSR entry (same thermal::volumeResidual integrand, thermal.cpp:70-165, summed per row instead of per element;
+// the scatter / dofConstraints rules are those of pull_batch).  Entry m of element column c in ring slot s sits at
+// double (m * 2 + s) * cap + c, so sources are addressed by their element column alone and the smaller ring lets
+// more CTAs share an SM.
+// ---------------------------------------------------------------------------------------------------------
+template <int DIM>
+struct MetricLayout {
+  typedef Q1Shape<DIM> S;
+  static constexpr int NGU = MRH_JIT_METRIC_NG;                      // DIM when every cell is an axis-aligned box, else NG
+  static constexpr int MD = NGU;                                     // rho cp |det| (transient builds only)
+  static constexpr int B0 = NGU + (MRH_JIT_TRANSIENT ? 1 : 0);       // load vector
+  static constexpr int U0 = B0 + S::NV;                              // element state
+  static constexpr int UT0 = U0 + S::NV;                             // time derivative (transient builds only)
+  static constexpr int STAGE = UT0 + (MRH_JIT_TRANSIENT ? S::NV : 0);
+  static constexpr int ES = 2 * MRH_JIT_CAP;                         // doubles between consecutive entries of a column
+  static constexpr unsigned ESB = 8u * ES;
+};
+
+template <int DIM, bool BOX>
+__device__ __forceinline__ void metric_cell(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double* __restrict__ st) {
+  typedef Q1Shape<DIM> S;
+  typedef MetricLayout<DIM> L;
+  constexpr int NV = S::NV, NQ = S::NQ, NG = S::NG;
+  const TimeDev& td = P.td;
+  double X0[DIM], J[DIM][DIM], G[NG];
+  double adet;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) X0[d] = E.xv[0][d];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) G[g] = 0.0;
+  const double xzero[3] = {0.0, 0.0, 0.0};
+  const double kap = thermal_fn<DIM, FN_DIFFUSION>(P, xzero, td.time);
+  if constexpr (BOX) {
+    double h[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) h[d] = 0.5 * (E.xv[d + 1][d] - X0[d]);
+    double det = h[0];
+#pragma unroll
+    for (int d = 1; d < DIM; ++d) det *= h[d];
+    const double inv = 1.0 / det;
+    adet = fabs(det);
+    const double kd = kap * adet;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      double ih = inv;
+#pragma unroll
+      for (int o = 0; o < DIM; ++o) if (o != d) ih *= h[o];
+      G[d] = kd * ih * ih;
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) J[d][a] = (a == d) ? h[d] : 0.0;
+  } else {
+    double Ji[DIM][DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) J[d][a] = 0.5 * (E.xv[a + 1][d] - X0[d]);
+    const double det = det_inverse<DIM>(J, Ji);
+    adet = fabs(det);
+    const double kd = kap * adet;
+    int g = 0;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) s += Ji[a][d] * Ji[a][d];
+      G[g++] = s * kd;
+    }
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int b = a + 1; b < DIM; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) s += Ji[a][d] * Ji[b][d];
+        G[g++] = s * kd;
+      }
+  }
+#pragma unroll
+  for (int g = 0; g < L::NGU; ++g) st[g * L::ES] = G[g];
+  if (MRH_JIT_TRANSIENT)
+    st[L::MD * L::ES] = thermal_fn<DIM, FN_DENSITY>(P, xzero, td.time) * thermal_fn<DIM, FN_SPECIFIC_HEAT>(P, xzero, td.time) * adet;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    st[(L::U0 + j) * L::ES] = E.u[j];
+    if (MRH_JIT_TRANSIENT) st[(L::UT0 + j) * L::ES] = E.ut[j];
+  }
+  // load vector  sum_q f(x_q) w_q |det| phi_i(q)
+  double fl[NV];
+  if (MRH_SOURCE_CONST) {
+    const double f = thermal_fn<DIM, FN_SOURCE>(P, xzero, td.time) * adet;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) fl[i] = f * MRH_CTAB(Ltab)[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) fl[i] = 0.0;
+    if constexpr (BOX) {
+      constexpr int nqa[3] = {MRH_NQA0, MRH_NQA1, MRH_NQA2};
+      double xa[3][NQ];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) xa[d][i] = (d < DIM && i < nqa[d]) ? X0[d < DIM ? d : 0] + J[d < DIM ? d : 0][d < DIM ? d : 0] * (jit_tab::qax[d][i] + 1.0) : 0.0;
+      double f[NQ];
+      mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const double fw = f[q] * MRH_CTAB(qw)[q] * adet;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) fl[i] += fw * MRH_CTAB(phi)[q][i];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        double x[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          double sx = X0[d];
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) sx += J[d][a] * (MRH_TAB(qpt)[q][a] + 1.0);
+          x[d] = sx;
+        }
+        const double fw = thermal_fn<DIM, FN_SOURCE>(P, x, td.time) * MRH_CTAB(qw)[q] * adet;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) fl[i] += fw * MRH_CTAB(phi)[q][i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) st[(L::B0 + i) * L::ES] = fl[i];
+}
+
+template <int DIM>
+__device__ __forceinline__ void thermal_element_metric(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double* __restrict__ st) {
+  if (MRH_HAS_BOX && (E.ecls == 2 || !MRH_HAS_AFFINE)) metric_cell<DIM, true>(P, E, st);
+  else metric_cell<DIM, false>(P, E, st);
+}
+
+#ifdef MRH_JIT_CONST_MDESC
+#define MRH_MDESC_LOAD(p) (*(p))
+#else
+#define MRH_MDESC_LOAD(p) __ldg(p)
+#endif
+
+// one CSR entry of this lane's row from the metric source words: jv = Jacobian value, rc = its share of the residual
+template <int DIM, bool HAS_RES>
+__device__ __forceinline__ void metric_slot(const uint4* __restrict__ desc, const int k, const unsigned rbase, const double au, const double at,
+                                            double& jv, double& rc) {
+  typedef MetricLayout<DIM> L;
+  const uint4 a = MRH_MDESC_LOAD(desc + 2 * k);
+  uint4 b = make_uint4(SRC_NONE, SRC_NONE, SRC_NONE, SRC_NONE);
+  if (a.w != SRC_NONE) b = MRH_MDESC_LOAD(desc + 2 * k + 1);
+  const unsigned w[SLOT_SRCS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  double kp = 0.0, mp = 0.0;
+#pragma unroll
+  for (int z = 0; z < SLOT_SRCS; ++z)
+    if (w[z] != SRC_NONE) {
+      const unsigned col = rbase + (w[z] & MSRC_OFF_MASK);
+      const int t = (int)((w[z] >> MSRC_T_SHIFT) & 63u);
+#pragma unroll
+      for (int g = 0; g < L::NGU; ++g) kp = fma(lds_f64(col + g * L::ESB), jit_ctab::Stab[g][t], kp);
+      if (MRH_JIT_TRANSIENT) mp = fma(lds_f64(col + L::MD * L::ESB), jit_ctab::Mtab[t], mp);
+    }
+  jv = MRH_JIT_TRANSIENT ? au * kp + at * mp : kp;
+  rc = 0.0;
+  if (HAS_RES && a.x != SRC_NONE) {
+    const unsigned col0 = rbase + (a.x & MSRC_OFF_MASK), j0 = (a.x >> MSRC_J_SHIFT) & 7u;
+    rc = kp * lds_f64(col0 + (L::U0 + j0) * L::ESB);
+    if (MRH_JIT_TRANSIENT) rc = fma(mp, lds_f64(col0 + (L::UT0 + j0) * L::ESB), rc);
+  }
+}
+
+template <int DIM, bool HAS_RES, bool HAS_JAC, bool ACC>
+__device__ __forceinline__ void pull_rows_metric(const int desc_begin, const int n_jac, const int parity, const unsigned rbase, const ChainDev& C,
+                                                 double* __restrict__ wbuf, const int lane, const int rsub, const int kk_st, double* const (&pj)[4],
+                                                 const bool (&rv)[4], double* pres, const bool active, const double au, const double at) {
+  typedef MetricLayout<DIM> L;
+  // straight-line code generated for the plan's most frequent patterns (element columns, table entries and state slots are immediates)
+  if (mrh_pull_metric_special<HAS_RES, HAS_JAC, ACC>(desc_begin, parity, rbase, wbuf, lane, rsub, kk_st, pj, rv, pres, active, au, at)) return;
+#ifdef MRH_JIT_CONST_MDESC
+  const uint4* __restrict__ desc = (parity ? mrh_mdesc1 : mrh_mdesc0) + 2 * desc_begin;
+#else
+  const uint4* __restrict__ desc = reinterpret_cast<const uint4*>(parity ? C.mdesc1 : C.mdesc0) + 2 * (size_t)desc_begin;
+#endif
+  double racc = 0.0;
+  for (int k0 = 0; k0 < n_jac; k0 += PULL_CHUNK) {
+#pragma unroll
+    for (int kk = 0; kk < PULL_CHUNK; ++kk)
+      if (k0 + kk < n_jac) {
+        double jv, rc;
+        metric_slot<DIM, HAS_RES>(desc, k0 + kk, rbase, au, at, jv, rc);
+        if (HAS_JAC) wbuf[lane * PULL_PITCH + kk] = jv;
+        racc += rc;
+      }
+    if (HAS_JAC) {
+      __syncwarp();
+      if (k0 + kk_st < n_jac) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (rv[j]) {
+            double* p = pj[j] + k0;
+            double v = wbuf[(rsub + 8 * j) * PULL_PITCH + kk_st];
+            if (ACC) v += *p;
+            *p = v;
+          }
+      }
+      __syncwarp();
+    }
+  }
+  if (HAS_RES) {
+    const uint4 a = MRH_MDESC_LOAD(desc + 2 * n_jac);
+    uint4 b = make_uint4(SRC_NONE, SRC_NONE, SRC_NONE, SRC_NONE);
+    if (a.w != SRC_NONE) b = MRH_MDESC_LOAD(desc + 2 * n_jac + 1);
+    const unsigned w[SLOT_SRCS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    double bs = 0.0;
+#pragma unroll
+    for (int z = 0; z < SLOT_SRCS; ++z)
+      if (w[z] != SRC_NONE) bs += lds_f64(rbase + (w[z] & MSRC_OFF_MASK) + (L::B0 + ((w[z] >> MSRC_I_SHIFT) & 7u)) * L::ESB);
+    if (active) {
+      double v = bs - racc;
+      if (ACC) v += *pres;
+      *pres = v;
+    }
+  }
+}
+#endif  // MRH_JIT_METRIC
+
+template <int MDIM, bool HAS_RES, bool HAS_JAC, bool ACC>   // MDIM: 0 = full local systems in the ring, else the metric ring of that dimension
 __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C, const GraphDev& G, const OutDev& O, const int parity,
-                                           const unsigned ring_s, double* __restrict__ wbuf, const int lane) {
+                                           const unsigned ring_s, double* __restrict__ wbuf, const int lane, const double au, const double at) {
   const int n_rows = R.hdr.z & 0xFFFF, n_slots = (int)((unsigned)R.hdr.z >> 16);
   const bool active = lane < n_rows;
   const int row = R.rec.x;
@@ -587,6 +824,12 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
     __syncwarp();
   }
   double* pres = HAS_RES ? (O.res + row) : nullptr;
+#ifdef MRH_JIT_METRIC
+  if constexpr (MDIM != 0) {
+    pull_rows_metric<MDIM, HAS_RES, HAS_JAC, ACC>(R.hdr.y, n_jac, parity, rbase, C, wbuf, lane, rsub, kk_st, pj, rv, pres, active, au, at);
+    return;
+  }
+#endif
 #ifdef MRH_JIT_PULL
   // straight-line code generated for the plan's most frequent patterns: ring offsets are immediates of the loads
   if (mrh_pull_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, rsub, kk_st, pj, rv, pres, active)) return;
@@ -620,15 +863,15 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
   }
 }
 
-template <bool HAS_RES, bool HAS_JAC, bool ACC>
+template <int MDIM, bool HAS_RES, bool HAS_JAC, bool ACC>
 __device__ __forceinline__ void pull_step(BatchRegs R, const ChainDev& C, const GraphDev& G, const OutDev& O, const int batch_begin, const int n_batches,
-                                          const int parity, const unsigned ring_s, double* __restrict__ wbuf) {
+                                          const int parity, const unsigned ring_s, double* __restrict__ wbuf, const double au, const double at) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int b = warp; b < n_batches; b += nwarps) {
     const int bn = b + nwarps;
     BatchRegs N = R;
     if (bn < n_batches) N = fetch_batch(C, G, batch_begin + bn, lane);   // next batch of this warp: in flight while this one is summed
-    pull_batch<HAS_RES, HAS_JAC, ACC>(R, C, G, O, parity, ring_s, wbuf, lane);
+    pull_batch<MDIM, HAS_RES, HAS_JAC, ACC>(R, C, G, O, parity, ring_s, wbuf, lane, au, at);
     R = N;
   }
 }
@@ -639,11 +882,20 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   typedef Q1Shape<DIM> S;
   const ChainDev& C = P.chains;
   const int s0 = __ldg(C.chain_step_ptr + blockIdx.x), s1 = __ldg(C.chain_step_ptr + blockIdx.x + 1);
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef MRH_JIT_METRIC
+  constexpr int MDIM = DIM;
+  constexpr int cap = MRH_JIT_CAP;
+  constexpr int slot_doubles = cap;                      // interleaved slots: slot s starts at double s * cap
+  double* wbuf = ring + 2 * cap * MetricLayout<DIM>::STAGE + warp * PULL_WARP_DOUBLES;
+#else
+  constexpr int MDIM = 0;
   const int cap = C.cap;
   const int slot_doubles = cap * S::STAGE;
-  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
   double* wbuf = ring + 2 * slot_doubles + warp * PULL_WARP_DOUBLES;
+#endif
+  const double au = P.td.alpha_u, at = P.td.alpha_t;
 #ifdef MRH_JIT_MODE
   constexpr int mode = MRH_JIT_MODE;   // output mode of this build: 1 res | 2 jac | 4 accumulate (the host picks the build)
 #else
@@ -669,17 +921,21 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     BatchRegs R;
     R.hdr = make_int4(0, 0, 0, 0); R.rec = make_int2(0, 0); R.base = 0;
     if (warp < n_batches) R = fetch_batch(C, P.graph, batch_begin + warp, lane);
+#ifdef MRH_JIT_METRIC
+    if (tid < n_elem) thermal_element_metric<DIM>(P, E, slot + tid);
+#else
     if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);
+#endif
     const bool more = (s + 1 < s1) && (tid < sr_next.y);
     if (more) elem_stage1<DIM>(P, sr_next.x + tid, E);
     __syncthreads();
     switch (mode) {
-      case 1: pull_step<true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
-      case 2: pull_step<false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
-      case 3: pull_step<true, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
-      case 5: pull_step<true, false, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
-      case 6: pull_step<false, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
-      case 7: pull_step<true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf); break;
+      case 1: pull_step<MDIM, true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+      case 2: pull_step<MDIM, false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+      case 3: pull_step<MDIM, true, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+      case 5: pull_step<MDIM, true, false, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+      case 6: pull_step<MDIM, false, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+      case 7: pull_step<MDIM, true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
       default: break;
     }
     if (more) elem_stage2<DIM>(P, E);

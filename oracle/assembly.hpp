@@ -492,6 +492,17 @@ inline AssemblyManager::AssemblyManager(const Settings& s) : settings(s) {
     }
   }
 
+  // optional affine shear of the whole brick (synthetic parallelepiped cells with a full Jacobian for parity tests)
+  const double shear = s.getd("Mesh/shear", 0.0);
+  if (shear != 0.0) {
+    for (int n = 0; n < mesh.num_nodes; ++n) {
+      double* x = &mesh.nodes[(size_t)n * mesh.dim];
+      const double y0 = x[1], z0 = (mesh.dim == 3) ? x[2] : 0.0;
+      x[0] += shear * y0 + 0.5 * shear * z0;
+      x[1] += 0.7 * shear * z0;
+    }
+  }
+
   // ---- physics modules -> variables (PhysicsInterface ctor)
   modules = split_list(s.get("Physics/modules", "thermal"));
   std::vector<VarInfo> vars;

@@ -175,3 +175,82 @@ def test_scatter_programs_equal_serial_element_loop(oracle_lib, product_lib, dim
         assert np.allclose(res, rr, rtol=0, atol=1e-13)
         assert np.allclose(jac, jr, rtol=0, atol=1e-13)
     assert plan.stat("n_chains") > 1 and plan.stat("n_patterns") < plan.stat("n_rows")
+
+
+METRIC_CASES = {
+    "2d_box": (configs.THERMAL_2D, {"Mesh/NX": 11, "Mesh/NY": 9}, {"column elements": 4, "min segment levels": 2}),
+    "3d_box": (configs.THERMAL_3D, {"Mesh/NX": 9, "Mesh/NY": 7, "Mesh/NZ": 6}, {"column elements": 6, "min segment levels": 2}),
+    "3d_stretched": (configs.THERMAL_3D, {"Mesh/xmax": 2.0, "Mesh/ymax": 0.5, "Mesh/zmin": -1.0, "Mesh/NX": 7, "Mesh/NY": 5, "Mesh/NZ": 6,
+                                          "Functions/thermal diffusion": "2.5"}, {}),
+    "3d_sheared": (configs.THERMAL_3D, {"Mesh/shear": 0.3, "Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Functions/thermal diffusion": "0.7"},
+                   {"column elements": 5, "min segment levels": 2}),
+    "2d_sheared": (configs.THERMAL_2D, {"Mesh/shear": 0.25, "Mesh/NX": 8, "Mesh/NY": 6}, {}),
+    "3d_natural_sides": (configs.THERMAL_3D, {"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Physics/assemble boundary terms": False,
+                                              "Physics/Dirichlet conditions/T": {"left": "0.0", "top": "0.0"}}, {"column elements": 4}),
+}
+
+
+@pytest.mark.parametrize("case", sorted(METRIC_CASES))
+def test_metric_ring_host_replay_matches_oracle(oracle_lib, product_lib, case):
+    """Plans whose cells are all parallelepipeds with constant coefficients stage the element metric instead of the local
+    system (kernel_abi.h, METRIC ring).  The host replay of that plan -- same source words and formulas as the kernel --
+    must reproduce the oracle's residual and Jacobian to 1e-12."""
+    base, upd, opts = METRIC_CASES[case]
+    cfg = configs.variant(base, **upd)
+    op, plan = _host_plan(oracle_lib, cfg, options=opts)
+    assert plan.stat("metric_ring") == (op.dim if "sheared" not in case else op.dim * (op.dim + 1) // 2)
+    u = helpers.manufactured_state(op)
+    res_ref, jac_ref = op.assemble_jacres(u)
+    for accumulate in (1, 0):
+        res = np.full(op.num_dofs, 0.0 if accumulate else 7.0)
+        jac = np.full(op.nnz, 0.0 if accumulate else 7.0)
+        plan.debug_metric_host(u, accumulate, res, jac)
+        jr = jac_ref.copy()
+        if accumulate:   # dofConstraints (J(d,d) = 1 on fixed rows) is a separate kernel in accumulate mode
+            for r in np.nonzero(op.is_fixed)[0]:
+                jr[op.rowptr[r]:op.rowptr[r + 1]] = 0.0
+        assert helpers.rel_err_vec(res, res_ref) < 1e-12
+        assert helpers.rel_err_rows(jac, jr, op.rowptr) < 1e-12
+
+
+def test_metric_ring_host_replay_transient(oracle_lib, product_lib):
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Functions/density": "2.0", "Functions/specific heat": "1.5",
+                                                  "Functions/thermal source": "sin(t)*x+y*z"})
+    op, plan = _host_plan(oracle_lib, cfg)
+    rng = np.random.default_rng(3)
+    u, up = rng.standard_normal(op.num_dofs), rng.standard_normal(op.num_dofs)
+    for (A, b, c) in (([[1.0]], [1.0], [1.0]), ([[0.5]], [1.0], [0.5])):
+        op.set_time(True, time=0.3, dt=0.01, stage=0, A=A, b=b, c=c, bdf=(1.0, -1.0))
+        ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=0, A=A, b=b, c=c, bdf=(1.0, -1.0), sol_prev=[up], sol_stage=[up])
+        res_ref, jac_ref = op.assemble_jacres(u, sol_prev=[up], sol_stage=[u])
+        res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+        plan.debug_metric_host(u, 0, res, jac, time=ts)
+        assert helpers.rel_err_vec(res, res_ref) < 1e-12
+        assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < 1e-12
+    op.set_time(False)
+
+
+def test_metric_ring_needs_parallelepipeds_and_constant_coefficients(oracle_lib, product_lib):
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3, "Mesh/perturb": 0.02})
+    op, plan = _host_plan(oracle_lib, cfg)
+    assert plan.stat("metric_ring") == 0
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3, "Functions/thermal diffusion": "1.0+x"})
+    op, plan = _host_plan(oracle_lib, cfg)
+    assert plan.stat("metric_ring") == 0
+    with pytest.raises(product_lib.MrhydeB200Error):
+        _host_plan(oracle_lib, cfg, options={"ring": "metric"})
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3})
+    op, plan = _host_plan(oracle_lib, cfg, options={"ring": "full"})
+    assert plan.stat("metric_ring") == 0
+
+
+def test_metric_ring_generated_kernel_compiles(oracle_lib, product_lib, tmp_path):
+    """NVRTC compiles the metric build for sm_100a without a device (steady variant; generated pull code for the frequent patterns)."""
+    for base, upd in ((configs.THERMAL_3D, {"Mesh/NX": 9, "Mesh/NY": 7, "Mesh/NZ": 6}), (configs.THERMAL_2D, {"Mesh/NX": 9, "Mesh/NY": 7}),
+                      (configs.THERMAL_3D, {"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Mesh/shear": 0.3})):
+        cfg = configs.variant(base, **upd)
+        op, plan = _host_plan(oracle_lib, cfg)
+        src = tmp_path / "k.cu"
+        plan.debug_jit(source_path=str(src))
+        text = src.read_text()
+        assert "#define MRH_JIT_METRIC 1" in text and "mrh_pull_metric_special" in text

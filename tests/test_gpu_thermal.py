@@ -207,6 +207,38 @@ def test_many_chains_and_segments(oracle_lib, product_lib, kernel_build, perturb
         _check(op, plan, helpers.manufactured_state(op))
 
 
+@pytest.mark.parametrize("mesh", ["box", "sheared", "quad"])
+def test_metric_ring_variants(oracle_lib, product_lib, kernel_build, mesh):
+    """Parallelepiped cells + constant coefficients: the specialised build stages element metrics instead of local systems
+    (volume_kernel.cuh, METRIC ring).  Generated pull code, the descriptor-driven pull (pull patterns = 0) and the full ring
+    (ring = full) must all match the oracle; natural sides leave rows of every shape in the plan."""
+    if kernel_build == "false":
+        pytest.skip("the metric ring exists in the plan-specialised build only")
+    upd = {"Mesh/NX": 13, "Mesh/NY": 11, "Mesh/NZ": 9, "Functions/thermal diffusion": "1.7", "Physics/assemble boundary terms": False,
+           "Physics/Dirichlet conditions/T": {"left": "0.0", "top": "0.0"}}
+    if mesh == "sheared":
+        upd["Mesh/shear"] = 0.3
+    cfg = configs.variant(configs.THERMAL_2D if mesh == "quad" else configs.THERMAL_3D, **upd)
+    op = oracle_lib.OracleProblem(cfg)
+    u = helpers.manufactured_state(op)
+    for options in ({"ring": "metric"}, {"ring": "metric", "pull patterns": 0}, {"ring": "full"}):
+        options.update({"column elements": 6, "min segment levels": 2})
+        plan = helpers.plan_from_oracle(op, cfg, options=options)
+        want = 0 if options["ring"] == "full" else (op.dim if mesh != "sheared" else op.dim * (op.dim + 1) // 2)
+        assert plan.stat("metric_ring") == want and plan.stat("jit") == 1
+        _check(op, plan, u)
+        import torch
+        for kw in (dict(compute_jacobian=False), dict(compute_residual=False)):   # residual-only / Jacobian-only builds
+            d_u, d_res, d_jac = _device_arrays(op, u)
+            res_ref, jac_ref = op.assemble_jacres(u)
+            plan.assemble_jacres(d_u, d_res if kw.get("compute_residual", True) else None, d_jac if kw.get("compute_jacobian", True) else None, **kw)
+            torch.cuda.synchronize()
+            if kw.get("compute_residual", True):
+                assert helpers.rel_err_vec(d_res.cpu().numpy(), res_ref) < TOL and float(d_jac.abs().max()) == 0.0
+            else:
+                assert helpers.rel_err_rows(d_jac.cpu().numpy(), jac_ref, op.rowptr) < TOL and float(d_res.abs().max()) == 0.0
+
+
 def test_full_size_properties(product_lib, kernel_build):
     """BASELINE configs[1] (128^3 hex-Q1 thermal) is too large for the oracle; check size-independent properties of the
     assembled system instead: K 1 = 0 on free rows, symmetry of the free-free block, res(u) = res(0) - J u (the problem is
