@@ -243,6 +243,10 @@ int mrhyde_b200_plan_debug_emulate_apply_mass(mrhyde_b200_plan* plan, const doub
  * same ordering and fixed-row rules as the device pull-scatter.  Verifies plan logic only. */
 int mrhyde_b200_plan_debug_scatter_host(mrhyde_b200_plan* plan, const double* stage, int64_t stage_len, int accumulate,
                                         double* res, double* jac_values);
+/* Layout of the staged element vector of a sweep-kernel plan (plan_stat "stage_len" doubles per element): kmap[i*ndof+j] =
+ * index of local-matrix entry (i,j) -- the upper-triangle index, or the entry's class on plans with the class ring
+ * (plan_stat "class_ring" > 0) -- and rmap[i] = index of residual entry i. */
+int mrhyde_b200_plan_debug_stage_map(mrhyde_b200_plan* plan, int32_t* kmap, int32_t* rmap);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mrhyde_b200_assemble_jacres", "mrhyde_b200_assemble_res", "mrhyde_b200_assemble_jacres_host",
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
-    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host",
+    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_stage_map",
     "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
     "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
@@ -99,6 +99,7 @@ def lib():
         L.mrhyde_b200_expr_eval_host.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_scatter_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_jit.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.mrhyde_b200_plan_debug_stage_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_metric_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_assemble_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_emulate_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -375,6 +376,12 @@ class AssemblyPlan:
         never an assembly path (mrhyde_b200_plan_debug_emulate)."""
         self._chk(self.L.mrhyde_b200_plan_debug_emulate(self.h, _ptr(sol), time.ref() if time is not None else None,
                                                       int(compute_jacobian), int(compute_residual), _ptr(res), _ptr(jac)))
+
+    def debug_stage_map(self, ndof):
+        """(kmap[ndof, ndof], rmap[ndof]): where local-matrix entry (i, j) / residual entry i sit in the staged element vector."""
+        kmap, rmap = np.zeros((ndof, ndof), dtype=np.int32), np.zeros(ndof, dtype=np.int32)
+        self._chk(self.L.mrhyde_b200_plan_debug_stage_map(self.h, _ptr(kmap), _ptr(rmap)))
+        return kmap, rmap
 
     def debug_metric_host(self, sol, accumulate, res, jac, time=None):
         """Host replay of the sweep kernel's metric ring (plans with stat("metric_ring") > 0): plan-analysis check, never an

@@ -131,6 +131,8 @@ struct mrhyde_b200_plan {
   int jit_min_blocks = 1;
   size_t smem = 0;
   int metric_ng = 0;               // > 0: the specialised kernels use the metric ring with this many metric entries per element
+  int class_nc = 0;                // > 0: class ring (boxes + constant coefficients): distinct local-matrix values staged per element
+  std::vector<int32_t> class_of_t, class_rep;   // upper-triangle entry -> class, class -> representative entry
   size_t smem_metric[2] = {0, 0};  // dynamic shared memory of the steady / transient metric builds
   int64_t n_affine = 0, n_box = 0;
   int launches_per_assemble = 0;   // kernels launched by the last assemble call
@@ -160,7 +162,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -254,11 +256,12 @@ std::string hexd(double v) {
 void emit_values(std::string& o, const double* v, size_t n) {
   for (size_t i = 0; i < n; ++i) { o += hexd(v[i]); o += (i + 1 < n) ? "," : ""; }
 }
-std::string pull_codegen(const ChainPlan& cp, int max_patterns);
-std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab);
+std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group);
+std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab, int group);
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
-                               const int64_t (&n_class)[3], int metric_ng, int max_patterns) {
+                               const int64_t (&n_class)[3], int metric_ng, int max_patterns, int pull_group,
+                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -271,6 +274,8 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   o += "#define MRH_JIT_HAS_BOX " + std::to_string((n_class[2] > 0 && all_const) ? 1 : 0) + "\n";
   o += "#define MRH_JIT_ALL_CONST " + std::to_string(all_const) + "\n";
   o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
+  o += "#define MRH_DEBUG_SKIP " + std::to_string(debug_skip) + "   /* timing experiments only: 1 no global stores, 2 no element work, 3 neither */\n";
+  if (!class_rep.empty()) o += "#define MRH_JIT_CLASS_NC " + std::to_string(class_rep.size()) + "\n";   // class ring (volume_kernel.cuh)
   if (metric_ng > 0) {   // metric ring (volume_kernel.cuh): parallelepiped cells + constant coefficients only
     o += "#define MRH_JIT_METRIC 1\n#define MRH_JIT_METRIC_NG " + std::to_string(metric_ng) + "\n#define MRH_JIT_CAP " + std::to_string(cp.cap) + "\n";
   }
@@ -350,6 +355,14 @@ __device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
   arr(("Mtab[" + nt + "]").c_str(), &T.Mtab[0], S::NT);
   arr(("Ltab[" + nv + "]").c_str(), &T.Ltab[0], S::NV);
   arr(("qax[3][" + nq + "]").c_str(), &qax[0][0], 3 * S::NQ);
+  if (!class_rep.empty()) {
+    auto iarr = [&](const std::string& decl, const std::vector<int32_t>& v) {
+      o += "constexpr int " + decl + "[" + std::to_string(v.size()) + "] = {";
+      for (size_t i = 0; i < v.size(); ++i) o += std::to_string(v[i]) + (i + 1 < v.size() ? "," : "");
+      o += "};\n";
+    };
+    iarr("cls", class_of_t); iarr("rep", class_rep);
+  }
   o += "}  // namespace jit_tab\nnamespace jit_ctab {\n";
   auto carr = [&](const char* decl, const double* v, size_t n) { o += std::string("__constant__ double ") + decl + " = {"; emit_values(o, v, n); o += "};\n"; };
   carr(("phi[" + nq + "][" + nv + "]").c_str(), &T.phi[0][0], S::NQ * S::NV);
@@ -373,40 +386,83 @@ __device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
       o += "};\n";
     }
   }
-  if (metric_ng > 0) o += pull_codegen_metric(cp, max_patterns, S::NV, S::NG, metric_ng, &T.Stab[0][0], &T.Mtab[0]);
-  else o += pull_codegen(cp, max_patterns);
+  if (metric_ng > 0) o += pull_codegen_metric(cp, max_patterns, S::NV, S::NG, metric_ng, &T.Stab[0][0], &T.Mtab[0], pull_group);
+  else o += pull_codegen(cp, max_patterns, pull_group);
   o += "}  // namespace mrhyde_b200\n";
   o += kVolumeKernelSrc;
   return o;
 }
 
-// ---- straight-line pull code for the plan's most frequent gather patterns (jit only) ------------------------------
-// For a pattern the slot descriptors are plan constants, so the generated code has no descriptor loads, no "unused"
-// tests and no address arithmetic: every staged value is one LDS with an immediate offset from the row's ring anchor.
-// Sums keep the ascending element order of the generic loop (slot_sum), so both paths give identical bits.
-std::string pull_codegen(const ChainPlan& cp, int max_patterns) {
+// ---- patterns that get generated pull code: the most frequent ones, by rows ------------------------------------------
+struct SpecialPattern { int32_t desc_begin; int n_slots; };
+std::vector<SpecialPattern> special_patterns(const ChainPlan& cp, int max_patterns) {
   std::map<int32_t, int64_t> freq;   // desc_begin -> rows
   for (const BatchRec& B : cp.batches) if (!(B.flags & BATCH_FIXED)) freq[B.desc_begin] += B.n_rows;
   std::vector<std::pair<int64_t, int32_t>> order;
   for (auto& kv : freq) order.push_back({kv.second, kv.first});
   std::sort(order.rbegin(), order.rend());
+  std::vector<SpecialPattern> out;
+  for (auto& pr : order) {
+    if ((int)out.size() >= max_patterns) break;
+    int n_slots = 0;
+    for (const PatternRec& PR : cp.patterns) if (PR.desc_begin == pr.second) n_slots = PR.n_slots;
+    if (n_slots < 2 || n_slots > 65) continue;   // rows of up to 64 entries go through the per-warp row buffer
+    out.push_back({pr.second, n_slots});
+  }
+  return out;
+}
+int row_pitch(int n_jac) { return n_jac | 1; }   // odd pitch: a lane per row writes the row buffer without bank conflicts
+// doubles per row of the per-warp row buffer (MRH_JIT_ROWBUF); 0 when no pattern is specialised
+int row_buffer_pitch(const ChainPlan& cp, int max_patterns) {
+  int pitch = 0;
+  for (const SpecialPattern& sp : special_patterns(cp, max_patterns)) pitch = std::max(pitch, row_pitch(sp.n_slots - 1));
+  return pitch;
+}
+// Row flush shared by the generated pull code: the warp's rows sit in rowb (row r at r * PITCH), their CSR offsets in wbase;
+// position p = lane + 32 i of the concatenated rows is written by lane `lane` in round i, so rows that are neighbours in the
+// CSR array -- the usual case: a batch holds rows in ascending order -- leave as 256-byte contiguous stores.
+const char* kFlushRowsSrc = R"MRH(
+template <int NJ, int PITCH, bool ACC>
+__device__ __forceinline__ void mrh_flush_rows(const double* rowb, const long long* wbase, double* __restrict__ jac, const int n_rows, const int lane) {
+  __syncwarp();
+  if (!(MRH_DEBUG_SKIP & 1)) {
+    int row = lane / NJ, k = lane % NJ;
+#pragma unroll 3
+    for (int i = 0; i < NJ; ++i) {
+      if (row < n_rows) {
+        double v = rowb[row * PITCH + k];
+        double* p = jac + wbase[row] + k;
+        if (ACC) v += *p;
+        *p = v;
+      }
+      row += 32 / NJ; k += 32 % NJ;
+      if (k >= NJ) { k -= NJ; ++row; }
+    }
+  }
+  __syncwarp();
+}
+)MRH";
+
+// ---- straight-line pull code for the plan's most frequent gather patterns (jit only) ------------------------------
+// For a pattern the slot descriptors are plan constants, so the generated code has no descriptor loads, no "unused"
+// tests and no address arithmetic: every staged value is one LDS with an immediate offset from the row's ring anchor.
+// Sums keep the ascending element order of the generic loop (slot_sum), so both paths give identical bits.
+std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group) {
+  group = std::max(4, (group / 4) * 4);   // sums formed before they are parked in the row buffer: loads in flight vs registers
+  const std::vector<SpecialPattern> sel = special_patterns(cp, max_patterns);
   std::string o;
-  o += "#define MRH_JIT_PULL 1\n";
+  if (sel.empty()) return o;
+  o += "#define MRH_JIT_PULL 1\n#define MRH_JIT_ROWBUF " + std::to_string(row_buffer_pitch(cp, max_patterns)) + "\n";
   o += "__device__ __forceinline__ double mrh_lds_at(unsigned a) { double v; asm volatile(\"ld.shared.f64 %0, [%1];\" : \"=d\"(v) : \"r\"(a)); return v; }\n";
   o += "#define MRH_L(off) mrh_lds_at(rbase + (off##u))\n";
-  o += "#define MRH_ST(K0, LIM) { __syncwarp(); if ((LIM) >= 4 || kk_st < (LIM)) { _Pragma(\"unroll\") for (int j = 0; j < 4; ++j) if (rv[j]) { double* p = pj[j] + (K0); "
-       "double v = wbuf[(rsub + 8 * j) * 5 + kk_st]; if (ACC) v += *p; *p = v; } } __syncwarp(); }\n";
+  o += kFlushRowsSrc;
   o += "template <bool HAS_RES, bool HAS_JAC, bool ACC>\n__device__ __forceinline__ bool mrh_pull_special(const int desc_begin, const int parity, const unsigned rbase, "
-       "double* __restrict__ wbuf, const int lane, const int rsub, const int kk_st, double* const (&pj)[4], const bool (&rv)[4], double* pres, const bool active) {\n";
+       "double* __restrict__ wbuf, const int lane, const int n_rows, const long long base, double* __restrict__ jac, double* pres, const bool active) {\n";
+  o += "  long long* const wbase = reinterpret_cast<long long*>(wbuf);\n  double* const rowb = wbuf + 32;\n";
   o += "  switch (desc_begin * 2 + parity) {\n";
-  int emitted = 0;
-  for (auto& pr : order) {
-    if (emitted >= max_patterns) break;
-    const int32_t db = pr.second;
-    int n_slots = 0;
-    for (const PatternRec& PR : cp.patterns) if (PR.desc_begin == db) n_slots = PR.n_slots;
-    if (n_slots < 2 || n_slots > 96) continue;
-    const int n_jac = n_slots - 1;
+  for (const SpecialPattern& sp : sel) {
+    const int32_t db = sp.desc_begin;
+    const int n_jac = sp.n_slots - 1, pitch = row_pitch(n_jac);
     for (int par = 0; par < 2; ++par) {
       auto sum_expr = [&](int k) {
         std::string e;
@@ -420,55 +476,44 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns) {
         }
         return cnt ? e : std::string("0.0");
       };
-      o += "    case " + std::to_string(db * 2 + par) + ": {\n      if (HAS_JAC) {\n";
-      // all sums first (the loads are independent and can be in flight together), then the transpose rounds
-      for (int k = 0; k < n_jac; ++k) o += "        const double a" + std::to_string(k) + " = " + sum_expr(k) + ";\n";
-      for (int k0 = 0; k0 < n_jac; k0 += 4) {
-        for (int kk = 0; kk < 4 && k0 + kk < n_jac; ++kk)
-          o += "        wbuf[lane * 5 + " + std::to_string(kk) + "] = a" + std::to_string(k0 + kk) + ";\n";
-        o += "        MRH_ST(" + std::to_string(k0) + ", " + std::to_string(n_jac - k0) + ")\n";
+      o += "    case " + std::to_string(db * 2 + par) + ": {\n      if (HAS_JAC) {\n        wbase[lane] = base;\n";
+      // a group of sums first (the loads are independent and can be in flight together), then they are parked in the row buffer
+      for (int g0 = 0; g0 < n_jac; g0 += group) {
+        for (int k = g0; k < g0 + group && k < n_jac; ++k) o += "        const double a" + std::to_string(k) + " = " + sum_expr(k) + ";\n";
+        for (int k = g0; k < g0 + group && k < n_jac; ++k) o += "        rowb[lane * " + std::to_string(pitch) + " + " + std::to_string(k) + "] = a" + std::to_string(k) + ";\n";
       }
+      o += "        mrh_flush_rows<" + std::to_string(n_jac) + ", " + std::to_string(pitch) + ", ACC>(rowb, wbase, jac, n_rows, lane);\n";
       o += "      }\n      if (HAS_RES) { const double acc = " + sum_expr(n_jac) + "; if (active) { double v = -acc; if (ACC) v += *pres; *pres = v; } }\n";
       o += "      return true;\n    }\n";
     }
-    ++emitted;
   }
   o += "    default: return false;\n  }\n}\n";
   return o;
 }
 
-
 // ---- the same for the metric ring: a CSR entry is  sum_e sum_g G_g(e) Stab[g][t_e]  with the element columns, table entries
 // and state slots of the pattern as immediates.  The metric entries of the pattern's element columns are loaded once per row.
-std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab) {
-  std::map<int32_t, int64_t> freq;
-  for (const BatchRec& B : cp.batches) if (!(B.flags & BATCH_FIXED)) freq[B.desc_begin] += B.n_rows;
-  std::vector<std::pair<int64_t, int32_t>> order;
-  for (auto& kv : freq) order.push_back({kv.second, kv.first});
-  std::sort(order.rbegin(), order.rend());
+std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab, int group) {
+  group = std::max(4, (group / 4) * 4);   // entries summed before their transpose rounds start (instruction-level parallelism vs registers)
+  const std::vector<SpecialPattern> sel = special_patterns(cp, max_patterns);
   const int nt = nv * (nv + 1) / 2;
   (void)ng_all;
   std::string o;
-  o += "#define MRH_JIT_PULL_METRIC 1\n";
+  o += "#define MRH_JIT_PULL_METRIC 1\n#define MRH_JIT_ROWBUF " + std::to_string(std::max(1, row_buffer_pitch(cp, max_patterns))) + "\n";
+  o += kFlushRowsSrc;
   o += "#define MRH_ESB (16u * MRH_JIT_CAP)\n";
   o += "#define MRH_MD MRH_JIT_METRIC_NG\n#define MRH_B0 (MRH_JIT_METRIC_NG + MRH_JIT_TRANSIENT)\n";
   o += "#define MRH_U0 (MRH_B0 + " + std::to_string(nv) + ")\n#define MRH_UT0 (MRH_U0 + " + std::to_string(nv) + ")\n";
   o += "__device__ __forceinline__ double mrh_mlds(unsigned a) { double v; asm volatile(\"ld.shared.f64 %0, [%1];\" : \"=d\"(v) : \"r\"(a)); return v; }\n";
   o += "#define MRH_ML(off, m) mrh_mlds(rbase + (off) + (m) * MRH_ESB)\n";
-  o += "#define MRH_MST(K0, LIM) { __syncwarp(); if ((LIM) >= 4 || kk_st < (LIM)) { _Pragma(\"unroll\") for (int j = 0; j < 4; ++j) if (rv[j]) { double* p = pj[j] + (K0); "
-       "double v = wbuf[(rsub + 8 * j) * 5 + kk_st]; if (ACC) v += *p; *p = v; } } __syncwarp(); }\n";
   o += "template <bool HAS_RES, bool HAS_JAC, bool ACC>\n__device__ __forceinline__ bool mrh_pull_metric_special(const int desc_begin, const int parity, const unsigned rbase, "
-       "double* __restrict__ wbuf, const int lane, const int rsub, const int kk_st, double* const (&pj)[4], const bool (&rv)[4], double* pres, const bool active, "
+       "double* __restrict__ wbuf, const int lane, const int n_rows, const long long base, double* __restrict__ jac, double* pres, const bool active, "
        "const double au, const double at) {\n";
+  o += "  long long* const wbase = reinterpret_cast<long long*>(wbuf);\n  double* const rowb = wbuf + 32;\n";
   o += "  switch (desc_begin * 2 + parity) {\n";
-  int emitted = 0;
-  for (auto& pr : order) {
-    if (emitted >= max_patterns) break;
-    const int32_t db = pr.second;
-    int n_slots = 0;
-    for (const PatternRec& PR : cp.patterns) if (PR.desc_begin == db) n_slots = PR.n_slots;
-    if (n_slots < 2 || n_slots > 96) continue;
-    const int n_jac = n_slots - 1;
+  for (const SpecialPattern& sp : sel) {
+    const int32_t db = sp.desc_begin;
+    const int n_slots = sp.n_slots, n_jac = n_slots - 1, pitch = row_pitch(n_jac);
     for (int par = 0; par < 2; ++par) {
       auto word = [&](int k, int z) { return cp.mdesc[par][((size_t)db + (size_t)k) * SLOT_SRCS + (size_t)z]; };
       // element columns of the pattern in order of first use
@@ -485,10 +530,9 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
           o += "      const double g" + std::to_string(c) + "_" + std::to_string(g) + " = MRH_ML(" + std::to_string(cols[c]) + "u, " + std::to_string(g) + ");\n";
         o += "#if MRH_JIT_TRANSIENT\n      const double m" + std::to_string(c) + " = MRH_ML(" + std::to_string(cols[c]) + "u, MRH_MD);\n#endif\n";
       }
-      o += "      double racc = 0.0;\n";
-      for (int k0 = 0; k0 < n_jac; k0 += 4) {
-        for (int kk = 0; kk < 4 && k0 + kk < n_jac; ++kk) {
-          const int k = k0 + kk;
+      o += "      if (HAS_JAC) wbase[lane] = base;\n      double racc = 0.0;\n";
+      for (int g0 = 0; g0 < n_jac; g0 += group) {
+        for (int k = g0; k < g0 + group && k < n_jac; ++k) {
           const std::string a = "a" + std::to_string(k), mm = "mm" + std::to_string(k);
           std::string ea, em;
           bool first_a = true, first_m = true;
@@ -518,10 +562,11 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
             o += "#if MRH_JIT_TRANSIENT\n        racc = fma(" + mm + ", MRH_ML(" + off + ", MRH_UT0 + " + j0 + "), racc);\n#endif\n      }\n";
           }
           o += "#if MRH_JIT_TRANSIENT\n      " + a + " = fma(au, " + a + ", at * " + mm + ");\n#endif\n";
-          o += "      if (HAS_JAC) wbuf[lane * 5 + " + std::to_string(kk) + "] = " + a + ";\n";
         }
-        o += "      if (HAS_JAC) MRH_MST(" + std::to_string(k0) + ", " + std::to_string(n_jac - k0) + ")\n";
+        for (int k = g0; k < g0 + group && k < n_jac; ++k)
+          o += "      if (HAS_JAC) rowb[lane * " + std::to_string(pitch) + " + " + std::to_string(k) + "] = a" + std::to_string(k) + ";\n";
       }
+      o += "      if (HAS_JAC) mrh_flush_rows<" + std::to_string(n_jac) + ", " + std::to_string(pitch) + ", ACC>(rowb, wbase, jac, n_rows, lane);\n";
       o += "      if (HAS_RES) {\n        double bs = 0.0;\n";
       for (int z = 0; z < SLOT_SRCS; ++z) {
         const uint32_t w = word(n_jac, z);
@@ -531,7 +576,6 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
       o += "        if (active) { double v = bs - racc; if (ACC) v += *pres; *pres = v; }\n      }\n";
       o += "      return true;\n    }\n";
     }
-    ++emitted;
   }
   o += "    default: return false;\n  }\n}\n";
   return o;
@@ -689,7 +733,9 @@ size_t variant_smem(const mrhyde_b200_plan* P, bool transient) { return P->metri
 int variant_min_blocks(const mrhyde_b200_plan* P, size_t smem) {
   const int want = std::stoi(opt(P, "min blocks", "0"));
   if (want > 0) return want;
-  return std::max(1, std::min(std::min(8, 2048 / P->threads), (int)((228 * 1024) / (smem + 1024))));
+  // the kernels want ~128 registers: more than "max blocks" (3) CTAs of 160 threads per SM would force spills
+  const int cap_regs = std::max(1, std::stoi(opt(P, "max blocks", "3")));
+  return std::max(1, std::min(std::min(cap_regs, 2048 / P->threads), (int)((228 * 1024) / (smem + 1024))));
 }
 
 // Specialised kernel for (steady | transient, output mode); compiled by NVRTC on first use.
@@ -711,7 +757,7 @@ const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std:
   }
   std::unique_ptr<JitKernel> k(new JitKernel());
   const size_t smem = variant_smem(P, transient);
-  if (!k->build(src, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, variant_min_blocks(P, smem), smem, log)) return nullptr;
+  if (!k->build(src, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, variant_min_blocks(P, smem), smem, log, std::stoi(opt(P, "max registers", "0")))) return nullptr;
   const JitKernel* raw = k.get();
   P->jit[key] = std::move(k);
   return raw;
@@ -1260,18 +1306,74 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   P->n_affine = 0; P->n_box = 0;
   for (uint8_t a : M.eclass) { P->n_affine += (a != 0); P->n_box += (a == 2); }
 
-  // staged vector per element: upper triangle of the local Jacobian, then the residual
-  const int NT = NV * (NV + 1) / 2, STAGE = NT + NV;
+  // reference tables first: the ring layout depends on them
+  auto fill_host = [&](auto& th) {
+    th.source = src; th.diffusion = dif; th.specific_heat = cp; th.density = rho;
+    th.all_const = (dif.is_const && cp.is_const && rho.is_const) ? 1 : 0;
+  };
+  if (P->dim == 3) { fill_thermal_tables<3>(P, P->th3.tab); fill_host(P->th3); }
+  else { fill_thermal_tables<2>(P, P->th2.tab); fill_host(P->th2); }
+  // Ring layout (option ring = auto | class | metric | full; volume_kernel.cuh).  The compressed layouts exist in the
+  // plan-specialised build only, so they need NVRTC:
+  //   class   axis-aligned boxes throughout + constant diffusion / specific heat / density: the local matrix takes NC distinct
+  //           values (classes of upper-triangle entries with identical table columns), NC + NV doubles per element
+  //   metric  parallelepipeds throughout + constant coefficients: scaled metric + load vector + state, combined in the pull
+  //   full    upper triangle of the local matrix + residual (any cell, any coefficient; the ahead-of-time kernel's layout)
+  const int NT = NV * (NV + 1) / 2;
+  const std::string ring = opt(P, "ring", "auto");
+  if (ring != "auto" && ring != "class" && ring != "metric" && ring != "full") fail(MRHYDE_B200_ERR_INVALID, "option ring must be auto|class|metric|full");
+  std::string nvrtc_why;
+  const bool all_const = dif.is_const && cp.is_const && rho.is_const;
+  const bool jit_possible = opt(P, "jit", "auto") != "false" && nvrtc_available(nvrtc_why);
+  const bool class_ok = jit_possible && all_const && P->n_box == M.nelem;
+  const bool metric_ok = jit_possible && all_const && P->n_affine == M.nelem;
+  if (ring == "class" && !class_ok) fail(MRHYDE_B200_ERR_UNSUPPORTED, "ring=class needs axis-aligned box cells throughout, constant diffusion / specific heat / density and the plan-specialised build");
+  if (ring == "metric" && !metric_ok) fail(MRHYDE_B200_ERR_UNSUPPORTED, "ring=metric needs parallelepiped cells throughout, constant diffusion / specific heat / density and the plan-specialised build");
+  const bool use_class = class_ok && (ring == "auto" || ring == "class");
+  const bool use_metric = !use_class && metric_ok && (ring == "auto" || ring == "metric");
+  P->class_nc = 0; P->class_of_t.clear(); P->class_rep.clear();
+  if (use_class) {
+    const double* St = P->dim == 3 ? &P->th3.tab.Stab[0][0] : &P->th2.tab.Stab[0][0];
+    const double* Mt = P->dim == 3 ? &P->th3.tab.Mtab[0] : &P->th2.tab.Mtab[0];
+    P->class_of_t.assign((size_t)NT, -1);
+    for (int t = 0; t < NT; ++t) {
+      for (size_t c = 0; c < P->class_rep.size() && P->class_of_t[(size_t)t] < 0; ++c) {
+        const int r = P->class_rep[c];
+        bool same = Mt[t] == Mt[r];
+        for (int g = 0; g < P->dim && same; ++g) same = St[(size_t)g * NT + t] == St[(size_t)g * NT + r];   // tables are snapped: exact compare
+        if (same) P->class_of_t[(size_t)t] = (int32_t)c;
+      }
+      if (P->class_of_t[(size_t)t] < 0) { P->class_of_t[(size_t)t] = (int32_t)P->class_rep.size(); P->class_rep.push_back(t); }
+    }
+    P->class_nc = (int)P->class_rep.size();
+  }
+  // staged vector per element: the local Jacobian (upper triangle, or one value per class), then the residual
+  const int NK = use_class ? P->class_nc : NT, STAGE = NK + NV;
   std::vector<uint16_t> kmap((size_t)NV * NV), rmap((size_t)NV);
   for (int i = 0; i < NV; ++i) {
-    rmap[(size_t)i] = (uint16_t)(NT + i);
-    for (int j = 0; j < NV; ++j) { const int a = std::min(i, j), b = std::max(i, j); kmap[(size_t)i * NV + j] = (uint16_t)(a * NV - (a * (a - 1)) / 2 + (b - a)); }
+    rmap[(size_t)i] = (uint16_t)(NK + i);
+    for (int j = 0; j < NV; ++j) {
+      const int a = std::min(i, j), b = std::max(i, j), t = a * NV - (a * (a - 1)) / 2 + (b - a);
+      kmap[(size_t)i * NV + j] = (uint16_t)(use_class ? P->class_of_t[(size_t)t] : t);
+    }
   }
   ChainOptions co;
   co.column_elems = std::stoi(opt(P, "column elements", "128"));
   co.min_chains = std::stoi(opt(P, "min chains", "592"));
   co.sweep_axis = std::stoi(opt(P, "sweep axis", "-1"));
-  co.cta_slots = std::max(1, std::stoi(opt(P, "cta slots", "296")));
+  co.cta_slots = std::max(0, std::stoi(opt(P, "cta slots", "0")));   // 0: from the device's SM count and the CTAs per SM the build allows
+  co.max_blocks_per_sm = std::max(1, std::stoi(opt(P, "max blocks", "3")));
+  if (!host_only) {
+    int n_sm = 0;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device) == cudaSuccess && n_sm > 0) co.n_sm = n_sm;
+  }
+  {
+    // shared memory of the build that will run: ring entries per element and the per-warp row buffer (longest free row)
+    int64_t max_len = 0;
+    for (int64_t r = 0; r < M.nrows; ++r) if (!M.fixed[(size_t)r]) max_len = std::max(max_len, M.rowptr[(size_t)r + 1] - M.rowptr[(size_t)r]);
+    co.ring_stage_len = use_metric ? (P->dim + 2 * NV) : STAGE;
+    co.warp_buffer_bytes = jit_possible ? std::max<size_t>(PULL_WARP_DOUBLES * 8, (size_t)(32 + 32 * (std::min<int64_t>(max_len, 64) | 1)) * 8) : (size_t)PULL_WARP_DOUBLES * 8;
+  }
   co.min_segment_levels = std::max(1, std::stoi(opt(P, "min segment levels", "8")));
   if (co.column_elems < 1 || co.min_chains < 1) fail(MRHYDE_B200_ERR_INVALID, "options 'column elements' and 'min chains' must be positive");
   build_chain_plan(M, kmap, rmap, STAGE, co, P->cp);
@@ -1284,32 +1386,22 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     P->threads = th;
   }
   // ring (2 slots) + one transpose buffer per warp
-  P->smem = (size_t)(2 * P->cp.slot_bytes()) + (size_t)(P->threads / 32) * PULL_WARP_DOUBLES * sizeof(double);
+  // per-warp transpose buffer; the specialised builds park whole rows there (generated pull code, row_buffer_pitch)
+  const int max_patterns = std::max(0, std::stoi(opt(P, "pull patterns", "3")));
+  const size_t warp_doubles = std::max<size_t>(PULL_WARP_DOUBLES, jit_possible ? 32 + 32 * (size_t)row_buffer_pitch(P->cp, max_patterns) : 0);
+  P->smem = (size_t)(2 * P->cp.slot_bytes()) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
 
   P->stage_len = STAGE;
   P->kmap = kmap; P->rmap = rmap;
-  auto fill_host = [&](auto& th) {
-    th.source = src; th.diffusion = dif; th.specific_heat = cp; th.density = rho;
-    th.all_const = (dif.is_const && cp.is_const && rho.is_const) ? 1 : 0;
-  };
-  if (P->dim == 3) { fill_thermal_tables<3>(P, P->th3.tab); fill_host(P->th3); }
-  else { fill_thermal_tables<2>(P, P->th2.tab); fill_host(P->th2); }
   {
     const int64_t n_class[3] = {M.nelem - P->n_affine, P->n_affine - P->n_box, P->n_box};
-    // ring = auto | metric | full: the metric ring (volume_kernel.cuh) needs parallelepiped cells throughout and constant
-    // diffusion / specific heat / density; it exists in the plan-specialised build only
-    const std::string ring = opt(P, "ring", "auto");
-    if (ring != "auto" && ring != "metric" && ring != "full") fail(MRHYDE_B200_ERR_INVALID, "option ring must be auto|metric|full");
-    const bool all_const = dif.is_const && cp.is_const && rho.is_const;
-    const bool metric_ok = all_const && n_class[0] == 0 && !P->cp.mdesc[0].empty() && opt(P, "jit", "auto") != "false";
-    if (ring == "metric" && !metric_ok)
-      fail(MRHYDE_B200_ERR_UNSUPPORTED, "ring=metric needs parallelepiped cells throughout, constant diffusion / specific heat / density and the plan-specialised build");
-    P->metric_ng = (metric_ok && ring != "full") ? (n_class[1] == 0 ? P->dim : P->dim * (P->dim + 1) / 2) : 0;
+    P->metric_ng = (use_metric && !P->cp.mdesc[0].empty()) ? (n_class[1] == 0 ? P->dim : P->dim * (P->dim + 1) / 2) : 0;
+    if (ring == "metric" && P->metric_ng == 0) fail(MRHYDE_B200_ERR_UNSUPPORTED, "ring=metric: the plan has no metric source words (sweep steps larger than 256 elements)");
     for (int tr = 0; tr < 2; ++tr)
-      P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * PULL_WARP_DOUBLES * sizeof(double);
-    const int max_patterns = std::max(0, std::stoi(opt(P, "pull patterns", "3")));
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns)
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns);
+      P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
+    const int pull_group = std::stoi(opt(P, "pull group", P->metric_ng > 0 ? "4" : "8"));
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")))
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")));
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
@@ -1377,7 +1469,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
       std::string log;
       // build the variant the first assemble call will most likely use (steady, residual + Jacobian, current accumulate mode)
       if (jit_variant(P, false, 3 | (P->accumulate ? 4 : 0), log)) P->use_jit = true;
-      else if (want == "true" || opt(P, "ring", "auto") == "metric") fail(MRHYDE_B200_ERR_CUDA, "the plan could not be specialised: " + log);
+      else if (want == "true" || P->class_nc > 0 || opt(P, "ring", "auto") == "metric")   // a class-ring plan has no ahead-of-time kernel
+        fail(MRHYDE_B200_ERR_CUDA, "the plan could not be specialised (option ring=full selects the layout of the ahead-of-time kernel): " + log);
       else { P->jit_note = log; P->metric_ng = 0; }   // the ahead-of-time kernel keeps full local systems in the ring
     }
   }
@@ -1529,6 +1622,8 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "halo_launches_per_sum") *value = P->halo ? P->halo->launches_per_sum() : 0;
   else if (k == "smem_bytes") *value = (int64_t)variant_smem(P, false);
   else if (k == "metric_ring") *value = P->metric_ng;
+  else if (k == "class_ring") *value = P->class_nc;
+  else if (k == "stage_len") *value = P->stage_len;
   else if (k == "threads_per_block") *value = P->threads;
   else if (k == "n_elem") *value = P->mesh.nelem;
   else if (k == "n_elem_with_halo") *value = P->cp.n_elem_with_halo;
@@ -1619,7 +1714,7 @@ int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* P, const char* source_path, con
   }
   std::string cubin, text;
   const int min_blocks = variant_min_blocks(P, variant_smem(P, false));
-  const bool ok = nvrtc_compile(P->jit_source, P->threads, min_blocks, cubin, text);
+  const bool ok = nvrtc_compile(P->jit_source, P->threads, min_blocks, cubin, text, std::stoi(opt(P, "max registers", "0")));
   if (log && log_cap) { std::snprintf(log, log_cap, "%s", text.c_str()); }
   if (!ok) fail(MRHYDE_B200_ERR_CUDA, "debug_jit: " + text);
   if (cubin_path) {
@@ -1790,6 +1885,15 @@ int mrhyde_b200_plan_debug_metric_host(mrhyde_b200_plan* P, const double* sol, c
   const int ng = P->dim * (P->dim + 1) / 2;
   if (P->dim == 3) { metric_host_elements<3>(P, P->th3, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th3.tab.Stab[0][0], &P->th3.tab.Mtab[0], td.alpha_u, td.transient ? td.alpha_t : 0.0, accumulate != 0, res, jac); }
   else { metric_host_elements<2>(P, P->th2, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th2.tab.Stab[0][0], &P->th2.tab.Mtab[0], td.alpha_u, td.transient ? td.alpha_t : 0.0, accumulate != 0, res, jac); }
+  ABI_END
+}
+
+int mrhyde_b200_plan_debug_stage_map(mrhyde_b200_plan* P, int32_t* kmap /*[ndof*ndof]*/, int32_t* rmap /*[ndof]*/) {
+  ABI_BEGIN
+  if (!P || !kmap || !rmap) fail(MRHYDE_B200_ERR_INVALID, "debug_stage_map: null argument");
+  if (!P->finalized || P->use_general) fail(MRHYDE_B200_ERR_STATE, "debug_stage_map: needs a finalized plan on the sweep kernel");
+  for (size_t i = 0; i < P->kmap.size(); ++i) kmap[i] = P->kmap[i];
+  for (size_t i = 0; i < P->rmap.size(); ++i) rmap[i] = P->rmap[i];
   ABI_END
 }
 

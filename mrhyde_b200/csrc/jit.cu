@@ -61,15 +61,16 @@ bool nvrtc_available(std::string& why) {
   return A.ok;
 }
 
-bool nvrtc_compile(const std::string& source, int threads, int min_blocks, std::string& cubin, std::string& log) {
+bool nvrtc_compile(const std::string& source, int threads, int min_blocks, std::string& cubin, std::string& log, int max_regs) {
   NvrtcApi& A = api();
   if (!A.ok) { log = A.why; return false; }
   nvrtcProgram prog;
   nvrtcResult r = A.CreateProgram(&prog, source.c_str(), "mrhyde_b200_volume_kernel.cu", 0, nullptr, nullptr);
   if (r != NVRTC_SUCCESS) { log = std::string("nvrtcCreateProgram: ") + A.GetErrorString(r); return false; }
   const std::string dthreads = "-DMRH_THREADS=" + std::to_string(threads), dblocks = "-DMRH_MIN_BLOCKS=" + std::to_string(min_blocks);
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-DMRH_JIT=1", dthreads.c_str(), dblocks.c_str()};
-  r = A.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+  const std::string dregs = "--maxrregcount=" + std::to_string(max_regs);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-DMRH_JIT=1", dthreads.c_str(), dblocks.c_str(), dregs.c_str()};
+  r = A.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])) - (max_regs > 0 ? 0 : 1), opts);
   size_t n = 0;
   if (A.GetProgramLogSize(prog, &n) == NVRTC_SUCCESS && n > 1) { log.resize(n); A.GetProgramLog(prog, &log[0]); }
   if (r != NVRTC_SUCCESS) { log = std::string("NVRTC compile failed (") + A.GetErrorString(r) + "):\n" + log; A.DestroyProgram(&prog); return false; }
@@ -84,8 +85,8 @@ JitKernel::~JitKernel() {
   if (library_) cudaLibraryUnload((cudaLibrary_t)library_);
 }
 
-bool JitKernel::build(const std::string& source, const std::string& entry, int threads, int min_blocks, size_t smem, std::string& log) {
-  if (!nvrtc_compile(source, threads, min_blocks, cubin_, log)) return false;
+bool JitKernel::build(const std::string& source, const std::string& entry, int threads, int min_blocks, size_t smem, std::string& log, int max_regs) {
+  if (!nvrtc_compile(source, threads, min_blocks, cubin_, log, max_regs)) return false;
   cudaLibrary_t lib = nullptr;
   cudaError_t e = cudaLibraryLoadData(&lib, cubin_.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (e != cudaSuccess) { log = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e); return false; }

@@ -218,6 +218,18 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
   int32_t nlevels = 0;
   for (int64_t e = 0; e < ne; ++e) nlevels = std::max(nlevels, level[(size_t)e] + 1);
 
+  // axis along which consecutive element ids are displaced most often (x on the reference's inline meshes)
+  int fast_axis = 0;
+  {
+    int64_t votes[3] = {0, 0, 0};
+    for (int64_t e = 0; e + 1 < ne; ++e) {
+      int best = 0;
+      double bd = -1.0;
+      for (int d = 0; d < dim; ++d) { const double v = std::fabs(cen[d][(size_t)e + 1] - cen[d][(size_t)e]); if (v > bd) { bd = v; best = d; } }
+      ++votes[best];
+    }
+    for (int d = 1; d < dim; ++d) if (votes[d] > votes[fast_axis]) fast_axis = d;
+  }
   const int cap_limit = (int)std::min<size_t>(opt.smem_budget / 2 / ((size_t)stage_len * 8), 256);   // one thread per element, <= 256 threads
   if (cap_limit < 1) throw std::runtime_error("plan: a single element does not fit the shared-memory ring");
   int column_elems = std::max(1, std::min(opt.column_elems, cap_limit));
@@ -251,6 +263,9 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
             axes[na] = d; spread[na] = hi - lo; ++na;
           }
           if (na == 2 && spread[1] > spread[0] * (1.0 + 1e-9)) { std::swap(axes[0], axes[1]); std::swap(spread[0], spread[1]); }
+          // equal spreads: cut across the slower axis so that columns stay long along the axis element ids run fastest in --
+          // rows of a batch then sit next to each other in the ring (conflict-free shared-memory reads) and in the CSR array
+          else if (na == 2 && !(spread[0] > spread[1] * (1.0 + 1e-9)) && axes[0] == fast_axis) { std::swap(axes[0], axes[1]); std::swap(spread[0], spread[1]); }
           for (int a = 0; a < na && !split; ++a) {
             const int d = axes[a];
             if (!(spread[a] > 0.0)) continue;
@@ -279,12 +294,24 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
     // segments along the sweep: enough chains to fill the device, preferring counts that make whole waves of
     // resident CTAs; every extra segment costs one recomputed level per column
     int32_t nseg = 1;
+    int cta_slots = opt.cta_slots;
+    if (cta_slots <= 0) {
+      // resident CTAs per SM from the shared memory of one CTA: the ring holds one step of a column plus its halo ring, estimated
+      // here from the column's cross-section (the exact capacity is only known after the chains are laid out)
+      const double side = std::sqrt((double)column_elems);
+      const double cap_est = dim == 3 ? (double)column_elems + 2.0 * side + 1.0 : (dim == 2 ? (double)column_elems + 1.0 : 1.0);
+      const int threads_est = std::max(128, std::min(256, (((int)cap_est + 31) / 32) * 32));
+      const size_t stage = (size_t)(opt.ring_stage_len > 0 ? opt.ring_stage_len : stage_len);
+      const size_t smem_est = (size_t)(2.0 * cap_est) * stage * 8 + (size_t)(threads_est / 32) * opt.warp_buffer_bytes + 1024;
+      const int blocks = std::max(1, std::min(std::min(opt.max_blocks_per_sm, 2048 / threads_est), (int)((228 * 1024) / smem_est)));
+      cta_slots = std::max(1, opt.n_sm) * blocks;
+    }
     {
       const int32_t smax = std::max(1, nlevels / std::max(1, opt.min_segment_levels));
       const int32_t smin = std::max(1, std::min(smax, (int32_t)((opt.min_chains + ncol - 1) / ncol)));
       double best = -1.0;
       for (int32_t sg = smin; sg <= std::min(smax, 4 * smin + 4); ++sg) {
-        const double waves = (double)ncol * sg / std::max(1, opt.cta_slots);
+        const double waves = (double)ncol * sg / std::max(1, cta_slots);
         const double fill = waves / std::ceil(waves);
         const double work = (double)nlevels / (double)(nlevels + sg - 1);
         const double score = fill * work;

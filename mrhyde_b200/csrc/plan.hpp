@@ -64,7 +64,12 @@ struct ChainOptions {
   int column_elems = 128;       // target owned elements per level and column
   int min_chains = 592;         // aim for at least this many chains (4 per SM) by cutting the sweep into segments
   int min_segment_levels = 8;
-  int cta_slots = 296;          // CTAs resident on the device at once (SMs x CTAs per SM): the chain count is tuned to fill whole waves
+  int cta_slots = 0;            // CTAs resident on the device at once (SMs x CTAs per SM): the chain count is tuned to fill whole waves;
+                                // 0: derived from the fields below once the ring capacity is known
+  int n_sm = 148;               // multiprocessors of the device
+  int max_blocks_per_sm = 3;    // register-limited CTAs per SM of the volume kernel (128 registers x 160 threads)
+  int ring_stage_len = 0;       // doubles per element in the ring of the build that will run (0: stage_len)
+  size_t warp_buffer_bytes = 1280;  // per-warp transpose / row buffer
   size_t smem_budget = 108 * 1024;  // ring (2 slots) must fit here; the row table (24 B per row of a step) sits behind it
 };
 

@@ -41,6 +41,17 @@ namespace mrhyde_b200 {
 #define MRH_UNROLL_Q _Pragma("unroll 1")
 #endif
 
+// CLASS ring (plan-specialised builds, MRH_JIT_CLASS_NC): on a mesh of axis-aligned boxes with constant coefficients the
+// local matrix K_e = sum_d G_d Stab[d] (+ md Mtab) takes only NC distinct values -- the classes of upper-triangle entries
+// whose table columns coincide (8 on hexahedra, 4 on quadrilaterals: K_e(i,j) depends on which axes i and j differ in).
+// A step then stages NC + NV doubles per element instead of NT + NV, with the plan's descriptors built on the class map
+// (jit_tab::cls), so the pull is unchanged; the smaller ring lets more CTAs share an SM.
+#ifdef MRH_JIT_CLASS_NC
+#define MRH_STAGE_K(NT) MRH_JIT_CLASS_NC
+#else
+#define MRH_STAGE_K(NT) (NT)
+#endif
+
 template <int NV>
 __host__ __device__ constexpr int tri(int i, int j) { return i * NV - (i * (i - 1)) / 2 + (j - i); }
 
@@ -275,6 +286,29 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
   }
   double md = 0.0;
   if (MRH_TRANSIENT(td)) md = thermal_fn<DIM, FN_DENSITY>(P, xzero, td.time) * thermal_fn<DIM, FN_SPECIFIC_HEAT>(P, xzero, td.time) * adet;
+#ifdef MRH_JIT_CLASS_NC
+  if constexpr (BOX) {   // class-ring plans hold axis-aligned boxes only: the sheared instantiation is never executed
+    constexpr int NC = MRH_JIT_CLASS_NC;
+    double kc[NC], mc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double k = 0.0;
+#pragma unroll
+      for (int g = 0; g < NGU; ++g) k += G[g] * MRH_CTAB(Stab)[g][jit_tab::rep[c]];
+      kc[c] = k; mc[c] = 0.0;
+      if (MRH_TRANSIENT(td)) { mc[c] = md * MRH_CTAB(Mtab)[jit_tab::rep[c]]; k = td.alpha_u * k + td.alpha_t * mc[c]; }
+      st[c * cap] = k;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = jit_tab::cls[tri<NV>(i < j ? i : j, i < j ? j : i)];
+        r[i] += kc[c] * u[j];
+        if (MRH_TRANSIENT(td)) r[i] += mc[c] * ut[j];
+      }
+  }
+#else
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
@@ -293,6 +327,7 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
       }
       st[t * cap] = k;
     }
+#endif
   // source
   if (MRH_SOURCE_CONST) {
     const double f = thermal_fn<DIM, FN_SOURCE>(P, xzero, td.time) * adet;
@@ -478,7 +513,7 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
     }
   }
 #pragma unroll
-  for (int i = 0; i < NV; ++i) st[(NT + i) * cap] = r[i];
+  for (int i = 0; i < NV; ++i) st[(MRH_STAGE_K(NT) + i) * cap] = r[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -499,7 +534,13 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 #endif
 constexpr int PULL_CHUNK = 4;                       // CSR entries per transpose round
 constexpr int PULL_PITCH = PULL_CHUNK + 1;          // doubles per lane in the transpose buffer (padding: no bank conflicts)
+#ifdef MRH_JIT_ROWBUF
+// generated pull code stages whole rows (32 row offsets, then 32 rows of MRH_JIT_ROWBUF doubles) and writes them out as
+// one flat, coalesced stream (mrh_flush_rows in the generated prelude)
+constexpr int PULL_WARP_DOUBLES = (32 + 32 * MRH_JIT_ROWBUF) > 32 * PULL_PITCH ? (32 + 32 * MRH_JIT_ROWBUF) : 32 * PULL_PITCH;
+#else
 constexpr int PULL_WARP_DOUBLES = 32 * PULL_PITCH;
+#endif
 #ifdef MRH_JIT_PULL
 static_assert(PULL_CHUNK == 4 && PULL_PITCH == 5, "generated pull code assumes 4-entry chunks with pitch 5");
 #endif
@@ -739,8 +780,6 @@ __device__ __forceinline__ void pull_rows_metric(const int desc_begin, const int
                                                  double* __restrict__ wbuf, const int lane, const int rsub, const int kk_st, double* const (&pj)[4],
                                                  const bool (&rv)[4], double* pres, const bool active, const double au, const double at) {
   typedef MetricLayout<DIM> L;
-  // straight-line code generated for the plan's most frequent patterns (element columns, table entries and state slots are immediates)
-  if (mrh_pull_metric_special<HAS_RES, HAS_JAC, ACC>(desc_begin, parity, rbase, wbuf, lane, rsub, kk_st, pj, rv, pres, active, au, at)) return;
 #ifdef MRH_JIT_CONST_MDESC
   const uint4* __restrict__ desc = (parity ? mrh_mdesc1 : mrh_mdesc0) + 2 * desc_begin;
 #else
@@ -811,6 +850,18 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
 #endif
   const unsigned rbase = ring_s + ((unsigned)R.rec.y & 0xFFFFu) * 8u;
   const int n_jac = n_slots - 1;
+#ifdef MRH_JIT_ROWBUF
+  // straight-line code generated for the plan's most frequent patterns: ring offsets (and, on the metric ring, table entries
+  // and state slots) are immediates; rows leave through the per-warp row buffer as one coalesced stream
+  {
+    double* const pres2 = HAS_RES ? (O.res + row) : nullptr;
+#ifdef MRH_JIT_METRIC
+    if (MDIM != 0 && mrh_pull_metric_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, n_rows, R.base, O.jac, pres2, active, au, at)) return;
+#else
+    if (mrh_pull_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, n_rows, R.base, O.jac, pres2, active)) return;
+#endif
+  }
+#endif
   // store side of the transpose: this lane writes entry (k0 + kk_st) of rows rsub + 8 j
   const int rsub = lane >> 2, kk_st = lane & 3;
   double* pj[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -829,10 +880,6 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
     pull_rows_metric<MDIM, HAS_RES, HAS_JAC, ACC>(R.hdr.y, n_jac, parity, rbase, C, wbuf, lane, rsub, kk_st, pj, rv, pres, active, au, at);
     return;
   }
-#endif
-#ifdef MRH_JIT_PULL
-  // straight-line code generated for the plan's most frequent patterns: ring offsets are immediates of the loads
-  if (mrh_pull_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, rsub, kk_st, pj, rv, pres, active)) return;
 #endif
   if (HAS_JAC) {
     for (int k0 = 0; k0 < n_jac; k0 += PULL_CHUNK) {
@@ -892,7 +939,7 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
 #else
   constexpr int MDIM = 0;
   const int cap = C.cap;
-  const int slot_doubles = cap * S::STAGE;
+  const int slot_doubles = cap * (MRH_STAGE_K(S::NT) + S::NV);
   double* wbuf = ring + 2 * slot_doubles + warp * PULL_WARP_DOUBLES;
 #endif
   const double au = P.td.alpha_u, at = P.td.alpha_t;
@@ -921,7 +968,9 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     BatchRegs R;
     R.hdr = make_int4(0, 0, 0, 0); R.rec = make_int2(0, 0); R.base = 0;
     if (warp < n_batches) R = fetch_batch(C, P.graph, batch_begin + warp, lane);
-#ifdef MRH_JIT_METRIC
+#if defined(MRH_DEBUG_SKIP) && (MRH_DEBUG_SKIP & 2)
+    if (tid < n_elem) slot[tid] = E.u[0] + E.xv[0][0];   // timing experiment: no element work
+#elif defined(MRH_JIT_METRIC)
     if (tid < n_elem) thermal_element_metric<DIM>(P, E, slot + tid);
 #else
     if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);

@@ -14,7 +14,7 @@ class JitKernel {
   ~JitKernel();
   // source: complete CUDA C++ translation unit; entry: extern "C" kernel name.  On failure returns false and
   // fills `log` (compiler output or the loader error).
-  bool build(const std::string& source, const std::string& entry, int threads, int min_blocks, size_t smem, std::string& log);
+  bool build(const std::string& source, const std::string& entry, int threads, int min_blocks, size_t smem, std::string& log, int max_regs = 0);
   bool ready() const { return kernel_ != nullptr; }
   const char* launch(const void* params, int grid, int threads, size_t smem, void* stream) const;
   int regs() const { return regs_; }
@@ -29,6 +29,6 @@ class JitKernel {
 
 bool nvrtc_available(std::string& why);
 // NVRTC only (no device needed): used by the CPU test-suite to check that generated sources compile for sm_100a.
-bool nvrtc_compile(const std::string& source, int threads, int min_blocks, std::string& cubin, std::string& log);
+bool nvrtc_compile(const std::string& source, int threads, int min_blocks, std::string& cubin, std::string& log, int max_regs = 0);
 
 }  // namespace mrhyde_b200

@@ -141,29 +141,27 @@ def test_scatter_programs_equal_serial_element_loop(oracle_lib, product_lib, dim
     cfg = configs.variant(base, **upd)
     op, plan = _host_plan(oracle_lib, cfg, options={"column elements": 4, "min segment levels": 2})
     nd = op.ndof_elem
-    nt = nd * (nd + 1) // 2
+    # staged layout: upper triangle + residual, or -- box meshes with constant coefficients, the class ring -- one value per
+    # class of entries + residual; either way local entry (i, j) is stage[e, kmap[i, j]]
+    kmap, rmap = plan.debug_stage_map(nd)
+    assert plan.stat("stage_len") == rmap.max() + 1 and (plan.stat("class_ring") > 0) == (perturb == 0.0)
+    assert np.array_equal(kmap, kmap.T)
     rng = np.random.default_rng(3)
-    stage = rng.standard_normal((op.num_elems, nt + nd))
+    stage = rng.standard_normal((op.num_elems, plan.stat("stage_len")))
     # reference loop
     res_ref = np.zeros(op.num_dofs)
     jac_ref = np.zeros(op.nnz)
     fixed = op.is_fixed.astype(bool)
-    tri = {}
-    k = 0
-    for i in range(nd):
-        for j in range(i, nd):
-            tri[(i, j)] = tri[(j, i)] = k
-            k += 1
     for e in range(op.num_elems):
         l = op.lids[e]
         for i in range(nd):
             r = l[i]
             if fixed[r]:
                 continue
-            res_ref[r] -= stage[e, nt + i]
+            res_ref[r] -= stage[e, rmap[i]]
             cols = op.colind[op.rowptr[r]:op.rowptr[r + 1]]
             for j in range(nd):
-                jac_ref[op.rowptr[r] + np.searchsorted(cols, l[j])] += stage[e, tri[(i, j)]]
+                jac_ref[op.rowptr[r] + np.searchsorted(cols, l[j])] += stage[e, kmap[i, j]]
     for accumulate in (1, 0):
         res = np.full(op.num_dofs, 0.0 if accumulate else 7.0)
         jac = np.full(op.nnz, 0.0 if accumulate else 7.0)
@@ -197,7 +195,7 @@ def test_metric_ring_host_replay_matches_oracle(oracle_lib, product_lib, case):
     must reproduce the oracle's residual and Jacobian to 1e-12."""
     base, upd, opts = METRIC_CASES[case]
     cfg = configs.variant(base, **upd)
-    op, plan = _host_plan(oracle_lib, cfg, options=opts)
+    op, plan = _host_plan(oracle_lib, cfg, options=dict(opts, ring="metric"))   # ring=auto picks the class ring on box meshes
     assert plan.stat("metric_ring") == (op.dim if "sheared" not in case else op.dim * (op.dim + 1) // 2)
     u = helpers.manufactured_state(op)
     res_ref, jac_ref = op.assemble_jacres(u)
@@ -216,7 +214,7 @@ def test_metric_ring_host_replay_matches_oracle(oracle_lib, product_lib, case):
 def test_metric_ring_host_replay_transient(oracle_lib, product_lib):
     cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Functions/density": "2.0", "Functions/specific heat": "1.5",
                                                   "Functions/thermal source": "sin(t)*x+y*z"})
-    op, plan = _host_plan(oracle_lib, cfg)
+    op, plan = _host_plan(oracle_lib, cfg, options={"ring": "metric"})
     rng = np.random.default_rng(3)
     u, up = rng.standard_normal(op.num_dofs), rng.standard_normal(op.num_dofs)
     for (A, b, c) in (([[1.0]], [1.0], [1.0]), ([[0.5]], [1.0], [0.5])):
@@ -230,27 +228,46 @@ def test_metric_ring_host_replay_transient(oracle_lib, product_lib):
     op.set_time(False)
 
 
-def test_metric_ring_needs_parallelepipeds_and_constant_coefficients(oracle_lib, product_lib):
-    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3, "Mesh/perturb": 0.02})
+def test_ring_layout_selection(oracle_lib, product_lib):
+    """ring=auto: class ring on axis-aligned boxes, metric ring on sheared parallelepipeds (both need constant coefficients),
+    full local systems otherwise; asking for a layout the plan cannot have is an error."""
+    small = {"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3}
+    stat = lambda plan: (plan.stat("class_ring"), plan.stat("metric_ring"), plan.stat("stage_len"))
+    op, plan = _host_plan(oracle_lib, configs.variant(configs.THERMAL_3D, **small))
+    assert stat(plan) == (8, 0, 16)
+    op, plan = _host_plan(oracle_lib, configs.variant(configs.THERMAL_2D, **small))
+    assert stat(plan) == (4, 0, 8)
+    op, plan = _host_plan(oracle_lib, configs.variant(configs.THERMAL_3D, **dict(small, **{"Mesh/shear": 0.2})))
+    assert stat(plan) == (0, 6, 44)
+    op, plan = _host_plan(oracle_lib, configs.variant(configs.THERMAL_3D, **dict(small, **{"Mesh/perturb": 0.02})))
+    assert stat(plan) == (0, 0, 44)
+    cfg = configs.variant(configs.THERMAL_3D, **dict(small, **{"Functions/thermal diffusion": "1.0+x"}))
     op, plan = _host_plan(oracle_lib, cfg)
-    assert plan.stat("metric_ring") == 0
-    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3, "Functions/thermal diffusion": "1.0+x"})
-    op, plan = _host_plan(oracle_lib, cfg)
-    assert plan.stat("metric_ring") == 0
+    assert stat(plan) == (0, 0, 44)
+    for ring in ("metric", "class"):
+        with pytest.raises(product_lib.MrhydeB200Error):
+            _host_plan(oracle_lib, cfg, options={"ring": ring})
     with pytest.raises(product_lib.MrhydeB200Error):
-        _host_plan(oracle_lib, cfg, options={"ring": "metric"})
-    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 3})
-    op, plan = _host_plan(oracle_lib, cfg, options={"ring": "full"})
-    assert plan.stat("metric_ring") == 0
+        _host_plan(oracle_lib, configs.variant(configs.THERMAL_3D, **dict(small, **{"Mesh/shear": 0.2})), options={"ring": "class"})
+    for ring, want in (("full", (0, 0, 44)), ("metric", (0, 3, 44)), ("class", (8, 0, 16))):
+        op, plan = _host_plan(oracle_lib, configs.variant(configs.THERMAL_3D, **small), options={"ring": ring})
+        assert stat(plan) == want
+    op, plan = _host_plan(oracle_lib, configs.variant(configs.THERMAL_3D, **small), options={"jit": "false"})   # no specialised build: full ring
+    assert stat(plan) == (0, 0, 44)
 
 
-def test_metric_ring_generated_kernel_compiles(oracle_lib, product_lib, tmp_path):
-    """NVRTC compiles the metric build for sm_100a without a device (steady variant; generated pull code for the frequent patterns)."""
-    for base, upd in ((configs.THERMAL_3D, {"Mesh/NX": 9, "Mesh/NY": 7, "Mesh/NZ": 6}), (configs.THERMAL_2D, {"Mesh/NX": 9, "Mesh/NY": 7}),
-                      (configs.THERMAL_3D, {"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Mesh/shear": 0.3})):
+def test_compressed_ring_kernels_compile(oracle_lib, product_lib, tmp_path):
+    """NVRTC compiles the class-ring and metric-ring builds for sm_100a without a device (steady variant; generated pull code
+    for the frequent patterns)."""
+    for base, upd, ring, marks in ((configs.THERMAL_3D, {"Mesh/NX": 9, "Mesh/NY": 7, "Mesh/NZ": 6}, "metric", ("#define MRH_JIT_METRIC 1", "mrh_pull_metric_special")),
+                                   (configs.THERMAL_3D, {"Mesh/NX": 9, "Mesh/NY": 7, "Mesh/NZ": 6}, "class", ("#define MRH_JIT_CLASS_NC 8", "mrh_pull_special")),
+                                   (configs.THERMAL_2D, {"Mesh/NX": 9, "Mesh/NY": 7}, "metric", ("#define MRH_JIT_METRIC 1",)),
+                                   (configs.THERMAL_2D, {"Mesh/NX": 9, "Mesh/NY": 7}, "class", ("#define MRH_JIT_CLASS_NC 4",)),
+                                   (configs.THERMAL_3D, {"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Mesh/shear": 0.3}, "auto", ("#define MRH_JIT_METRIC_NG 6",))):
         cfg = configs.variant(base, **upd)
-        op, plan = _host_plan(oracle_lib, cfg)
+        op, plan = _host_plan(oracle_lib, cfg, options={"ring": ring})
         src = tmp_path / "k.cu"
         plan.debug_jit(source_path=str(src))
         text = src.read_text()
-        assert "#define MRH_JIT_METRIC 1" in text and "mrh_pull_metric_special" in text
+        for m in marks:
+            assert m in text

@@ -27,7 +27,7 @@ def _local_assembly(kind, rank, world):
     if kind == "thermal":
         prob = ThermalBrick(3, n, device=-1, rank=rank, nranks=world, options={"column elements": 4, "min segment levels": 2})
         ne = prob.n_elem
-        stage = _stage(np.arange(ne) + rank * ne, 44)
+        stage = _stage(np.arange(ne) + rank * ne, prob.plan.stat("stage_len"))   # 44 doubles, or 16 with the class ring
         res, jac = np.zeros(prob.n_rows), np.zeros(prob.nnz)
         prob.plan.debug_scatter_host(stage, 1, res, jac)
     else:

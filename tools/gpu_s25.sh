@@ -1,0 +1,10 @@
+# coalesced row flush in the generated pull code: parity tests + timing
+timeout 900 python -m pytest tests/test_gpu_thermal.py -x -q 2>&1 | tail -5 > gpurun_out/s25_tests.log; cat gpurun_out/s25_tests.log
+rm -f gpurun_out/s25_sweep.txt
+for o in "--opt min\ blocks=3 --opt pull\ group=8 --opt cta\ slots=444" "--opt min\ blocks=3 --opt pull\ group=28 --opt cta\ slots=444" "--opt min\ blocks=4 --opt pull\ group=8" "--opt min\ blocks=2 --opt pull\ group=8" "--opt ring=metric --opt min\ blocks=2" "--opt ring=metric --opt min\ blocks=3 --opt cta\ slots=444" "--opt ring=full" "--opt min\ blocks=3 --opt pull\ group=8 --opt cta\ slots=444 --opt debug\ skip=1" "--opt min\ blocks=3 --opt pull\ group=8 --opt cta\ slots=444 --opt debug\ skip=2"; do eval python bench.py --no-cpu-baseline --steps 10 $o 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: continue
+    print(d['config'].get('plan_options'), 'ms', round(d['ms_per_step'],4), 'kernel_ms', round(d['roofline']['kernel_ms'],4), 'frac', round(d['roofline']['frac'],4), 'chains', d['config']['chains'], 'smem', d['config']['smem_bytes'])
+" >> gpurun_out/s25_sweep.txt; done; cat gpurun_out/s25_sweep.txt
