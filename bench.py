@@ -206,6 +206,17 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def ring_name(plan, general):
+    """What a sweep step stages per element."""
+    if general:
+        return "n/a (general path)"
+    if plan.stat("class_ring"):
+        return "class (%d values + residual)" % plan.stat("class_ring")
+    if plan.stat("metric_ring"):
+        return "metric (%d metric entries + load + state)" % plan.stat("metric_ring")
+    return "full (upper triangle + residual)"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -328,7 +339,7 @@ def run_ours(args):
                            "l2": "inputs+outputs %.2f GB per GPU exceed the 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
                            "output_mode": "overwrite (accumulate=false)", "chains": plan.stat("n_chains"), "columns": plan.stat("n_columns"),
                            "segments": plan.stat("n_segments"), "ring_capacity": plan.stat("ring_capacity"), "threads_per_block": plan.stat("threads_per_block"),
-                           "smem_bytes": plan.stat("smem_bytes"), "row_patterns": plan.stat("n_patterns"), "kernel_build": "nvrtc plan-specialised" if plan.stat("jit") else "ahead-of-time",
+                           "smem_bytes": plan.stat("smem_bytes"), "row_patterns": plan.stat("n_patterns"), "ring": ring_name(plan, general), "kernel_build": "nvrtc plan-specialised" if plan.stat("jit") else "ahead-of-time",
                            "elements_incl_halo": plan.stat("n_elem_with_halo"), "plan_options": {k: v for k, v in options.items() if k != "accumulate"}, "parallelism": "z-slabs x%d + NCCL halo sum" % world if world > 1 else "1 GPU"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                              "kernel": "gen_element_kernel + gen_pull_kernel (general path, whole assemble call)" if general else "mrh_thermal_q1_3d", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,

@@ -162,7 +162,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -261,7 +261,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
                                const int64_t (&n_class)[3], int metric_ng, int max_patterns, int pull_group,
-                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip) {
+                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, bool flush_rows, int flush_unroll, bool early_stage2) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -274,6 +274,11 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   o += "#define MRH_JIT_HAS_BOX " + std::to_string((n_class[2] > 0 && all_const) ? 1 : 0) + "\n";
   o += "#define MRH_JIT_ALL_CONST " + std::to_string(all_const) + "\n";
   o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
+  if (late_stage1) o += "#define MRH_JIT_LATE_STAGE1 1\n";
+  if (early_stage2) o += "#define MRH_JIT_EARLY_STAGE2 1\n";
+  o += "/*@stagger@*/\n";
+  o += "#define MRH_JIT_FLUSH_UNROLL " + std::to_string(flush_unroll) + "\n";
+  o += std::string("#define MRH_JIT_FLUSH ") + (flush_rows ? "1" : "0") + "   /* 1: one store instruction per row, 0: flat stream over the batch */\n";
   o += "#define MRH_DEBUG_SKIP " + std::to_string(debug_skip) + "   /* timing experiments only: 1 no global stores, 2 no element work, 3 neither */\n";
   if (!class_rep.empty()) o += "#define MRH_JIT_CLASS_NC " + std::to_string(class_rep.size()) + "\n";   // class ring (volume_kernel.cuh)
   if (metric_ng > 0) {   // metric ring (volume_kernel.cuh): parallelepiped cells + constant coefficients only
@@ -418,10 +423,35 @@ int row_buffer_pitch(const ChainPlan& cp, int max_patterns) {
   for (const SpecialPattern& sp : special_patterns(cp, max_patterns)) pitch = std::max(pitch, row_pitch(sp.n_slots - 1));
   return pitch;
 }
-// Row flush shared by the generated pull code: the warp's rows sit in rowb (row r at r * PITCH), their CSR offsets in wbase;
-// position p = lane + 32 i of the concatenated rows is written by lane `lane` in round i, so rows that are neighbours in the
-// CSR array -- the usual case: a batch holds rows in ascending order -- leave as 256-byte contiguous stores.
+// Row flush shared by the generated pull code: the warp's rows sit in rowb (row r at r * PITCH), their CSR offsets in wbase.
+// One store instruction writes one row (lane = entry), so a row leaves as one contiguous piece of NJ doubles whatever the
+// neighbouring rows are, and every shared-memory offset is an immediate.
 const char* kFlushRowsSrc = R"MRH(
+#if MRH_JIT_FLUSH == 1
+template <int NJ, int PITCH, bool ACC>
+__device__ __forceinline__ void mrh_flush_rows(const double* rowb, const long long* wbase, double* __restrict__ jac, const int n_rows, const int lane) {
+  __syncwarp();
+  if (!(MRH_DEBUG_SKIP & 1)) {
+    if (n_rows == 32) {   // full batch: no per-row tests
+#pragma unroll MRH_JIT_FLUSH_UNROLL
+      for (int r = 0; r < 32; ++r) {
+#pragma unroll
+        for (int c = 0; c < NJ; c += 32) {
+          const int k = c + lane;
+          if (k < NJ) { double v = rowb[r * PITCH + k]; double* p = jac + wbase[r] + k; if (ACC) v += *p; *p = v; }
+        }
+      }
+    } else {
+      for (int r = 0; r < n_rows; ++r) {
+        for (int k = lane; k < NJ; k += 32) { double v = rowb[r * PITCH + k]; double* p = jac + wbase[r] + k; if (ACC) v += *p; *p = v; }
+      }
+    }
+  }
+  __syncwarp();
+}
+#else
+// flat variant: position p = lane + 32 i of the concatenated rows is written by lane `lane` in round i, so rows that are
+// neighbours in the CSR array -- a batch holds rows in ascending order -- leave as 256-byte contiguous stores
 template <int NJ, int PITCH, bool ACC>
 __device__ __forceinline__ void mrh_flush_rows(const double* rowb, const long long* wbase, double* __restrict__ jac, const int n_rows, const int lane) {
   __syncwarp();
@@ -441,6 +471,7 @@ __device__ __forceinline__ void mrh_flush_rows(const double* rowb, const long lo
   }
   __syncwarp();
 }
+#endif
 )MRH";
 
 // ---- straight-line pull code for the plan's most frequent gather patterns (jit only) ------------------------------
@@ -757,6 +788,14 @@ const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std:
   }
   std::unique_ptr<JitKernel> k(new JitKernel());
   const size_t smem = variant_smem(P, transient);
+  {
+    const int stagger = std::max(0, std::stoi(opt(P, "stagger ns", "0")));
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device);
+    const int blocks = variant_min_blocks(P, smem);
+    swap_define("/*@stagger@*/", "#define MRH_JIT_STAGGER_NS " + std::to_string(stagger) + "u\n#define MRH_JIT_STAGGER_SMS " + std::to_string(n_sm) +
+                                 "u\n#define MRH_JIT_STAGGER_BLOCKS " + std::to_string(blocks) + "u\n#define MRH_JIT_STAGGER_SLOTS " + std::to_string(n_sm * blocks) + "u");
+  }
   if (!k->build(src, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, variant_min_blocks(P, smem), smem, log, std::stoi(opt(P, "max registers", "0")))) return nullptr;
   const JitKernel* raw = k.get();
   P->jit[key] = std::move(k);
@@ -1399,9 +1438,9 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     if (ring == "metric" && P->metric_ng == 0) fail(MRHYDE_B200_ERR_UNSUPPORTED, "ring=metric: the plan has no metric source words (sweep steps larger than 256 elements)");
     for (int tr = 0; tr < 2; ++tr)
       P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
-    const int pull_group = std::stoi(opt(P, "pull group", P->metric_ng > 0 ? "4" : "8"));
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")))
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")));
+    const int pull_group = std::stoi(opt(P, "pull group", "8"));
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", opt(P, "flush", "row") == "row", std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early")
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", opt(P, "flush", "row") == "row", std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early");
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface

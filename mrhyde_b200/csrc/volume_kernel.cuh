@@ -169,6 +169,9 @@ __device__ __forceinline__ double thermal_fn(const ThermalParams<DIM>& P, const 
 #endif
 }
 
+#if defined(MRH_JIT) && !MRH_JIT_HAS_GENERAL && !defined(MRH_JIT_LATE_STAGE1)
+#define MRH_EARLY_STAGE1 1
+#endif
 #ifdef MRH_JIT
 #define MRH_HAS_BOX (MRH_JIT_HAS_BOX != 0)
 #define MRH_HAS_AFFINE (MRH_JIT_HAS_AFFINE != 0)
@@ -953,6 +956,18 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   //   after compute s : connectivity / LIDs of s+1 (step order: no element-id indirection)
   //   after pull s    : state and vertices of s+1 (need the LIDs / connectivity requested before the pull)
   // so no load is issued right behind the load that produces its address.
+#if defined(MRH_JIT_STAGGER_NS) && MRH_JIT_STAGGER_NS > 0
+  // CTAs of the first wave start in step with each other and, since every step costs about the same, stay so: all SMs then
+  // compute, read and write at the same moments.  Offsetting the co-resident CTAs of an SM (and neighbouring SMs) by a
+  // fraction of a step lets element work, shared-memory sums and the store stream of different CTAs overlap.
+  if (blockIdx.x < MRH_JIT_STAGGER_SLOTS) {
+    const unsigned d = ((blockIdx.x / MRH_JIT_STAGGER_SMS) % MRH_JIT_STAGGER_BLOCKS) * (MRH_JIT_STAGGER_NS / MRH_JIT_STAGGER_BLOCKS) +
+                       ((blockIdx.x % MRH_JIT_STAGGER_SMS) % 4u) * (MRH_JIT_STAGGER_NS / (4u * MRH_JIT_STAGGER_BLOCKS));
+    const long long t0 = clock64();
+    const long long ticks = (long long)d * 2;   // ~2 GHz SM clock: the offset need not be exact
+    while (clock64() - t0 < ticks) {}
+  }
+#endif
   int4 sr = __ldg(reinterpret_cast<const int4*>(C.steps + s0));
   int4 sr_next = sr;
   if (s0 + 1 < s1) sr_next = __ldg(reinterpret_cast<const int4*>(C.steps + s0 + 1));
@@ -968,6 +983,13 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     BatchRegs R;
     R.hdr = make_int4(0, 0, 0, 0); R.rec = make_int2(0, 0); R.base = 0;
     if (warp < n_batches) R = fetch_batch(C, P.graph, batch_begin + warp, lane);
+    const bool more = (s + 1 < s1) && (tid < sr_next.y);
+#ifdef MRH_EARLY_STAGE1
+    // builds without general cells no longer need this step's connectivity: the next step's connectivity / LIDs are requested
+    // before the element work, so they have arrived by the pull and never share a scoreboard with its first loads
+    ElemPre<DIM> Nx;
+    if (more) elem_stage1<DIM>(P, sr_next.x + tid, Nx);
+#endif
 #if defined(MRH_DEBUG_SKIP) && (MRH_DEBUG_SKIP & 2)
     if (tid < n_elem) slot[tid] = E.u[0] + E.xv[0][0];   // timing experiment: no element work
 #elif defined(MRH_JIT_METRIC)
@@ -975,9 +997,20 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
 #else
     if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);
 #endif
-    const bool more = (s + 1 < s1) && (tid < sr_next.y);
+#ifndef MRH_EARLY_STAGE1
     if (more) elem_stage1<DIM>(P, sr_next.x + tid, E);
+#endif
     __syncthreads();
+#if defined(MRH_EARLY_STAGE1) && defined(MRH_JIT_EARLY_STAGE2)
+    // the next step's state and vertices are requested before the pull (their addresses arrived during the element work),
+    // so no global-memory latency is left exposed between two steps; costs the registers that hold them across the pull
+    if (more) {
+      E.ecls = Nx.ecls;
+#pragma unroll
+      for (int i = 0; i < (1 << DIM); ++i) { E.cn[i] = Nx.cn[i]; E.ld[i] = Nx.ld[i]; }
+      elem_stage2<DIM>(P, E);
+    }
+#endif
     switch (mode) {
       case 1: pull_step<MDIM, true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
       case 2: pull_step<MDIM, false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
@@ -987,7 +1020,18 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
       case 7: pull_step<MDIM, true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
       default: break;
     }
+#if defined(MRH_EARLY_STAGE1) && defined(MRH_JIT_EARLY_STAGE2)
+    // requested before the pull
+#else
+#ifdef MRH_EARLY_STAGE1
+    if (more) {
+      E.ecls = Nx.ecls;
+#pragma unroll
+      for (int i = 0; i < (1 << DIM); ++i) { E.cn[i] = Nx.cn[i]; E.ld[i] = Nx.ld[i]; }
+    }
+#endif
     if (more) elem_stage2<DIM>(P, E);
+#endif
     sr = sr_next; sr_next = sr_next2;
     __syncthreads();  // the next step overwrites the slot this pull read as "previous"
   }
