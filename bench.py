@@ -200,7 +200,7 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": workload_name(n, 1), "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -308,12 +308,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = total_elems * e2e_steps / e2e_s
-    # the same load for ~1 s more so the clock sampler sees the kernel under load
-    t_end = time.perf_counter() + 1.0
-    while time.perf_counter() < t_end:
-        for _ in range(20):
-            step()
-        torch.cuda.synchronize()
+    # the same load for ~1 s more so the clock sampler sees the kernel under load.  The iteration count comes from the
+    # max-reduced step time, so every rank runs the same number of halo sums (a wall-clock loop can leave one rank an
+    # iteration short and the send/recv pairs unmatched)
+    n_load = max(1, min(20000, int(1.0 / max(1e-6, ms / args.steps * 1e-3))))
+    for i in range(n_load):
+        step()
+        if i % 20 == 19:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     assert bool(torch.isfinite(d_res).all()) and bool(torch.isfinite(d_jac[:: 97]).all())
 
@@ -349,13 +352,32 @@ def run_ours(args):
                 "gpu_launches": int(args.steps * launches_per_step), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_serial(n)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_STDOUT_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def main():
+    # Libraries below us write to file descriptor 1 (NCCL prints its version banner there when a communicator is created):
+    # keep the original stdout for the JSON line and point fd 1 at stderr for everything else.
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

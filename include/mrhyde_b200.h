@@ -124,7 +124,12 @@ int mrhyde_b200_plan_set_function(mrhyde_b200_plan* plan, const char* name, cons
  *   "batch elems"  = elements per launch of the general path (default -1: one launch over all elements; N > 0: rows are
  *                    pulled as soon as the batch that completes them has been computed)
  *   "penalty", "incplanestress"   linearelasticity module keys
- *   "column elements", "min chains", "min segment levels", "sweep axis", "threads"   sweep-plan tuning
+ *   "ring"         = "auto" (default) | "class" | "metric" | "full": what a sweep step stages per element;
+ *                    asking for a layout the mesh / coefficients do not allow is MRHYDE_B200_ERR_UNSUPPORTED
+ *   "column elements", "min chains", "min segment levels", "sweep axis", "threads", "cta slots", "max blocks", "min blocks",
+ *   "max registers", "pull patterns", "pull group", "flush", "flush unroll", "stage1", "stage2", "stagger ns"
+ *                    sweep-plan / specialised-build tuning (defaults are the measured best)
+ *   "debug skip"     timing experiments only (parts of the specialised kernel compiled out; results are then wrong)
  * Unknown keys are an error, never silently ignored. */
 int mrhyde_b200_plan_set_option(mrhyde_b200_plan* plan, const char* key, const char* value);
 

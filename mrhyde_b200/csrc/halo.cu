@@ -66,6 +66,13 @@ __global__ void unpack_add_kernel(const double* __restrict__ src, const int64_t*
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n && pos[i] >= 0) dst[pos[i]] += src[i];
 }
+// residual and matrix values of one source rank in one launch: [0, n_res) -> res, [n_res, n_res + n_jac) -> jac
+__global__ void unpack_add2_kernel(const double* __restrict__ src, const int64_t* __restrict__ pos_res, int64_t n_res, double* __restrict__ res,
+                                   const int64_t* __restrict__ pos_jac, int64_t n_jac, double* __restrict__ jac) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_res) { if (pos_res[i] >= 0) res[pos_res[i]] += src[i]; }
+  else if (i < n_res + n_jac) { const int64_t p = pos_jac[i - n_res]; if (p >= 0) jac[p] += src[i]; }
+}
 
 template <class T>
 bool to_device(T** d, const std::vector<T>& h, std::string& err) {
@@ -204,6 +211,14 @@ bool HaloExchange::setup(int64_t n_rows, int64_t n_owned, int64_t n_cols, const 
     Peer& P = peers_[(size_t)p];
     P.n_send_res = (int64_t)send_res[(size_t)p].size(); P.n_send_jac = (int64_t)send_jac[(size_t)p].size();
     P.n_recv_res = (int64_t)recv_res.size(); P.n_recv_jac = (int64_t)recv_jac.size();
+    // ghost rows come last in the overlapped numbering, so what goes to a neighbour is usually one contiguous slice of res and
+    // one of the value array: those are sent in place, without a pack kernel
+    auto contiguous = [](const std::vector<int64_t>& v) {
+      for (size_t i = 1; i < v.size(); ++i) if (v[i] != v[i - 1] + 1) return false;
+      return !v.empty();
+    };
+    P.send_res_first = contiguous(send_res[(size_t)p]) ? send_res[(size_t)p][0] : -1;
+    P.send_jac_first = contiguous(send_jac[(size_t)p]) ? send_jac[(size_t)p][0] : -1;
     if (!to_device(&P.d_send_res, send_res[(size_t)p], err) || !to_device(&P.d_send_jac, send_jac[(size_t)p], err) ||
         !to_device(&P.d_recv_res, recv_res, err) || !to_device(&P.d_recv_jac, recv_jac, err)) return false;
     CU_TRY(cudaMalloc(&P.d_sendbuf, std::max<int64_t>(1, P.n_send_res + P.n_send_jac) * sizeof(double)));
@@ -221,25 +236,28 @@ bool HaloExchange::sum(double* res, double* jac, cudaStream_t st, std::string& e
   for (int p = 0; p < nranks_; ++p) {
     Peer& P = peers_[(size_t)p];
     if (p == rank_) continue;
-    if (res && P.n_send_res) pack_kernel<<<blocks(P.n_send_res), 256, 0, st>>>(res, P.d_send_res, P.n_send_res, P.d_sendbuf), ++launched;
-    if (jac && P.n_send_jac) pack_kernel<<<blocks(P.n_send_jac), 256, 0, st>>>(jac, P.d_send_jac, P.n_send_jac, P.d_sendbuf + P.n_send_res), ++launched;
+    if (res && P.n_send_res && P.send_res_first < 0) pack_kernel<<<blocks(P.n_send_res), 256, 0, st>>>(res, P.d_send_res, P.n_send_res, P.d_sendbuf), ++launched;
+    if (jac && P.n_send_jac && P.send_jac_first < 0) pack_kernel<<<blocks(P.n_send_jac), 256, 0, st>>>(jac, P.d_send_jac, P.n_send_jac, P.d_sendbuf + P.n_send_res), ++launched;
   }
   NCCL_TRY(A.GroupStart());
   for (int p = 0; p < nranks_; ++p) {
     Peer& P = peers_[(size_t)p];
     if (p == rank_) continue;
-    const int64_t ns = (res ? P.n_send_res : 0) + (jac ? P.n_send_jac : 0);
-    const int64_t nr = (res ? P.n_recv_res : 0) + (jac ? P.n_recv_jac : 0);
-    // layout in the buffers is [res | jac]; when only one of them is exchanged send just that slice
-    double* sb = P.d_sendbuf + (res ? 0 : P.n_send_res);
-    double* rb = P.d_recvbuf + (res ? 0 : P.n_recv_res);
-    if (ns) NCCL_TRY(A.Send(sb, (size_t)ns, ncclFloat64, p, comm, st));
-    if (nr) NCCL_TRY(A.Recv(rb, (size_t)nr, ncclFloat64, p, comm, st));
+    // two messages per peer and direction (residual entries, matrix values); the receive buffer is laid out [res | jac]
+    if (res && P.n_send_res) NCCL_TRY(A.Send(P.send_res_first >= 0 ? res + P.send_res_first : P.d_sendbuf, (size_t)P.n_send_res, ncclFloat64, p, comm, st));
+    if (jac && P.n_send_jac) NCCL_TRY(A.Send(P.send_jac_first >= 0 ? jac + P.send_jac_first : P.d_sendbuf + P.n_send_res, (size_t)P.n_send_jac, ncclFloat64, p, comm, st));
+    if (res && P.n_recv_res) NCCL_TRY(A.Recv(P.d_recvbuf, (size_t)P.n_recv_res, ncclFloat64, p, comm, st));
+    if (jac && P.n_recv_jac) NCCL_TRY(A.Recv(P.d_recvbuf + P.n_recv_res, (size_t)P.n_recv_jac, ncclFloat64, p, comm, st));
   }
   NCCL_TRY(A.GroupEnd());
   for (int p = 0; p < nranks_; ++p) {  // ascending source rank: fixed summation order
     Peer& P = peers_[(size_t)p];
     if (p == rank_) continue;
+    if (res && jac && P.n_recv_res + P.n_recv_jac) {
+      unpack_add2_kernel<<<blocks(P.n_recv_res + P.n_recv_jac), 256, 0, st>>>(P.d_recvbuf, P.d_recv_res, P.n_recv_res, res, P.d_recv_jac, P.n_recv_jac, jac);
+      ++launched;
+      continue;
+    }
     if (res && P.n_recv_res) unpack_add_kernel<<<blocks(P.n_recv_res), 256, 0, st>>>(P.d_recvbuf, P.d_recv_res, P.n_recv_res, res), ++launched;
     if (jac && P.n_recv_jac) unpack_add_kernel<<<blocks(P.n_recv_jac), 256, 0, st>>>(P.d_recvbuf + P.n_recv_res, P.d_recv_jac, P.n_recv_jac, jac), ++launched;
   }

@@ -37,6 +37,7 @@ class HaloExchange {
   // per peer: what I send (positions in my res / jac arrays) and where received values are added
   struct Peer {
     int64_t n_send_res = 0, n_send_jac = 0, n_recv_res = 0, n_recv_jac = 0;
+    int64_t send_res_first = -1, send_jac_first = -1;   // >= 0: the send positions are one contiguous slice starting here (sent in place)
     int64_t* d_send_res = nullptr; int64_t* d_send_jac = nullptr;   // source positions
     int64_t* d_recv_res = nullptr; int64_t* d_recv_jac = nullptr;   // destination positions (-1: column absent on the owner)
     double* d_sendbuf = nullptr; double* d_recvbuf = nullptr;
