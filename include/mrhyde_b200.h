@@ -188,6 +188,13 @@ int mrhyde_b200_assemble_mass(mrhyde_b200_plan* plan, const double* mass_wts, in
  * forming M (the element kernel's residual stage on x, then a row sum).  x, y: device [n_rows]; y follows the accumulate option
  * (the reference adds into y). */
 int mrhyde_b200_apply_mass(mrhyde_b200_plan* plan, const double* mass_wts, const double* x, double* y, void* stream);
+/* setInitial, right-hand side of the L2 projection of the initial conditions (assemblyManager_initial.hpp:36-76 with
+ * getInitial(project = true), :260-311): rhs(row) (+)= sum_e sum_q initial_var(x_q) phi_i(x_q) w_q, vector-valued for HCURL / HDIV
+ * variables.  The `Initial conditions` entries are passed through plan_set_function as "initial <var>" (HGRAD / HVOL) or
+ * "initial <var>[x]" / "[y]" / "[z]" (HCURL / HDIV) -- the names the reference registers, physicsInterface_functions.hpp:154-226;
+ * unnamed variables start from 0.0.  The mass matrix of the projection is mrhyde_b200_assemble_mass with unit weights.  No
+ * isFixedDOF check (the reference has none here); rhs: device [n_rows], follows the accumulate option; time = initial time. */
+int mrhyde_b200_project_initial(mrhyde_b200_plan* plan, double time, double* rhs, void* stream);
 
 /* ---- multi-GPU: the Tpetra Export(overlapped -> owned, ADD) replacement ---------------------------
  * (linearAlgebraInterface_matrix.hpp:233-237, _vector.hpp:56-66).  Ghost rows of this rank are summed
@@ -243,6 +250,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* plan, const double* sol, co
 /* Mass-matrix counterpart of mrhyde_b200_plan_debug_emulate (host-only plans; host buffers). */
 int mrhyde_b200_plan_debug_emulate_mass(mrhyde_b200_plan* plan, const double* mass_wts, int lump, double* mass_values, double* diag);
 int mrhyde_b200_plan_debug_emulate_apply_mass(mrhyde_b200_plan* plan, const double* mass_wts, const double* x, double* y);
+int mrhyde_b200_plan_debug_emulate_initial(mrhyde_b200_plan* plan, double time, double* rhs);
 /* Applies the plan's scatter programs on the host to caller-supplied staged element vectors
  * stage[n_elem][stage_len] (local Jacobian entries then residual entries), with the
  * same ordering and fixed-row rules as the device pull-scatter.  Verifies plan logic only. */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mrhyde_b200_assemble_jacres", "mrhyde_b200_assemble_res", "mrhyde_b200_assemble_jacres_host",
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
-    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_stage_map",
+    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
     "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
     "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
@@ -99,6 +99,8 @@ def lib():
         L.mrhyde_b200_expr_eval_host.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_scatter_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_jit.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.mrhyde_b200_project_initial.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_plan_debug_emulate_initial.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.mrhyde_b200_plan_debug_stage_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_metric_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_assemble_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -376,6 +378,14 @@ class AssemblyPlan:
         never an assembly path (mrhyde_b200_plan_debug_emulate)."""
         self._chk(self.L.mrhyde_b200_plan_debug_emulate(self.h, _ptr(sol), time.ref() if time is not None else None,
                                                       int(compute_jacobian), int(compute_residual), _ptr(res), _ptr(jac)))
+
+    def project_initial(self, rhs, time=0.0, stream=0):
+        """setInitial: rhs (+)= sum_q initial(x_q) phi_i w (device vector); functions "initial <var>[...]" come from set_function."""
+        self._chk(self.L.mrhyde_b200_project_initial(self.h, float(time), _ptr(rhs), C.c_void_p(stream)))
+
+    def debug_emulate_initial(self, rhs, time=0.0):
+        """Host replay of project_initial on a host-only plan (debugging aid, never an assembly path)."""
+        self._chk(self.L.mrhyde_b200_plan_debug_emulate_initial(self.h, float(time), _ptr(rhs)))
 
     def debug_stage_map(self, ndof):
         """(kmap[ndof, ndof], rmap[ndof]): where local-matrix entry (i, j) / residual entry i sit in the staged element vector."""

@@ -645,6 +645,18 @@ std::vector<std::string> module_variables(const std::string& phys, int dim) {
   return {};
 }
 
+std::vector<std::string> initial_function_names(const mrhyde_b200_plan* P, int v) {
+  const std::string& t = P->bases[(size_t)P->var_basis[(size_t)v]].type;
+  const std::string base = "initial " + P->var_names[(size_t)v];
+  if (t == "HCURL" || t == "HDIV") {
+    std::vector<std::string> out;
+    static const char* comp[3] = {"[x]", "[y]", "[z]"};
+    for (int d = 0; d < P->dim; ++d) out.push_back(base + comp[d]);
+    return out;
+  }
+  return {base};
+}
+
 FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side) {
   FunctionSet fs;
   // module defaults (thermal::defineFunctions, thermal.cpp:47-65), then user overrides
@@ -657,6 +669,10 @@ FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side) {
     fs.set("robin alpha", "0.0");
   }
   for (const ModuleFn* f = module_functions(canonical_physics(P->physics)); f && f->key; ++f) if (P->physics != "thermal") fs.set(f->key, f->def);
+  // "initial <var>" (HGRAD / HVOL) or "initial <var>[x|y|z]" (HCURL / HDIV): variables the Initial conditions sublist does not
+  // name start from 0.0 (physicsInterface_functions.hpp:154-226)
+  for (size_t v = 0; v < P->var_names.size(); ++v)
+    for (const std::string& nm : initial_function_names(P, (int)v)) fs.set(nm, "0.0");
   for (auto& kv : P->functions) fs.set(kv.first, kv.second);
   std::vector<std::string> sol;
   static const char* comps[3] = {"[x]", "[y]", "[z]"};
@@ -1001,6 +1017,12 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
     std::vector<std::string> names = fnames;
     names.resize(GEN_MAXFN);
     compile_functions(fs, names, H.fn, H.fn_op, H.fn_c);
+    // initial conditions in (variable, component) order: the function slots of the projection mode (gen_initial_point)
+    std::vector<std::string> inames;
+    for (int v = 0; v < P->nvars; ++v) for (const std::string& nm : initial_function_names(P, v)) inames.push_back(nm);
+    if ((int)inames.size() > I.nfn) fail(MRHYDE_B200_ERR_UNSUPPORTED, "general path: more initial-condition components than function slots");
+    inames.resize(GEN_MAXFN);
+    compile_functions(fs, inames, H.init_fn, H.fn_op, H.fn_c);
   }
   // ---- boundary families
   H.sides.clear();
@@ -1850,6 +1872,52 @@ int mrhyde_b200_apply_mass(mrhyde_b200_plan* P, const double* mass_wts, const do
                                    x, y, (cudaStream_t)stream, &stats);
   if (err) fail(MRHYDE_B200_ERR_CUDA, std::string("mass apply launch: ") + err);
   P->launches_per_assemble = stats.launches;
+  ABI_END
+}
+
+int mrhyde_b200_project_initial(mrhyde_b200_plan* P, double time, double* rhs, void* stream) {
+  ABI_BEGIN
+  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0};
+  check_mass_plan(P, ones);
+  if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "host-only analysis plan (device = -1) cannot assemble: there is no CPU path");
+  if (!rhs) fail(MRHYDE_B200_ERR_INVALID, "project_initial: null vector");
+  CUDA_OK(cudaSetDevice(P->device));
+  GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
+  GenLaunchStats stats;
+  const char* err = gen_project_initial(P->gen_dev, P->gen, P->gen_kernels, P->d_vx.p, P->d_vy.p, P->d_vz.p, P->d_conn.p, P->d_lids.p, G, time, P->accumulate,
+                                        rhs, (cudaStream_t)stream, &stats);
+  if (err) fail(MRHYDE_B200_ERR_CUDA, std::string("initial projection launch: ") + err);
+  P->launches_per_assemble = stats.launches;
+  ABI_END
+}
+
+int mrhyde_b200_plan_debug_emulate_initial(mrhyde_b200_plan* P, double time, double* rhs) {
+  ABI_BEGIN
+  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0};
+  check_mass_plan(P, ones);
+  if (P->device != -1) fail(MRHYDE_B200_ERR_STATE, "debug_emulate_initial: only host-only analysis plans (device = -1) replay the kernel stages on the host");
+  if (!rhs) fail(MRHYDE_B200_ERR_INVALID, "debug_emulate_initial: null vector");
+  const GeneralPlanHost& H = P->gen;
+  const GenKernelInfo& I = H.info;
+  const MeshGraph& M = P->mesh;
+  std::vector<double> er((size_t)H.n_inst * (size_t)I.N, 0.0), zero((size_t)M.nrows, 0.0);
+  GenParams Q;
+  std::memset(&Q, 0, sizeof(Q));
+  Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
+  Q.orient = M.orient.empty() ? nullptr : M.orient.data();
+  Q.sol = zero.data();
+  Q.td.alpha_u = 1.0; Q.td.deltat = 1.0; Q.td.time = time;
+  std::memcpy(Q.off, H.off, sizeof(Q.off));
+  std::memcpy(Q.fn, H.init_fn, sizeof(Q.fn));
+  Q.fn_op = H.fn_op.data(); Q.fn_c = H.fn_c.data(); Q.opt = H.opt;
+  for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = 0; Q.bc_fn[v] = -1; Q.mass_wts[v] = 1.0; }
+  Q.elem_jac = nullptr; Q.elem_res = er.data();
+  Q.mass_mode = 2;
+  Q.epb = 3;
+  Q.items = nullptr; Q.item_begin = 0; Q.item_end = M.nelem; Q.inst_base = 0;
+  Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
+  P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
+  gen_pull_apply_host(H, er.data(), P->accumulate, rhs);
   ABI_END
 }
 

@@ -274,6 +274,18 @@ const char* gen_apply_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const Ge
   return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, x, td, true, false, stream, stats, 3, mass_wts);
 }
 
+const char* gen_project_initial(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                                const int32_t* conn, const int32_t* lids, const GraphDev& G, double time, bool accumulate, double* rhs, void* stream,
+                                GenLaunchStats* stats) {
+  TimeDev td;
+  std::memset(&td, 0, sizeof(td));
+  td.alpha_u = 1.0; td.deltat = 1.0; td.time = time;
+  OutDev O;
+  O.jac = nullptr; O.res = rhs; O.accumulate = accumulate ? 1 : 0;
+  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0};
+  return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, rhs /* state is not read in this mode: any valid vector */, td, true, false, stream, stats, 4, ones);
+}
+
 static const char* gen_run_impl_marker = nullptr;
 const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                     const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
@@ -284,9 +296,11 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   std::memset(&P, 0, sizeof(P));
   P.vx = vx; P.vy = vy; P.vz = vz; P.conn = conn; P.lids = lids; P.orient = D->orient.n ? D->orient.p : nullptr;
   P.sol = sol; P.td = td;
-  if (pull_mass_mode) { P.mass_mode = 1; for (int v = 0; v < I.nvars; ++v) P.mass_wts[v] = mass_wts[v]; }
+  const bool initial = (pull_mass_mode == 4);   // projection of the initial conditions: the pull is the one of applyMassMatrixFree
+  if (initial) pull_mass_mode = 3;
+  if (pull_mass_mode) { P.mass_mode = initial ? 2 : 1; for (int v = 0; v < I.nvars; ++v) P.mass_wts[v] = mass_wts[v]; }
   std::memcpy(P.off, H.off, sizeof(P.off));
-  std::memcpy(P.fn, H.fn, sizeof(P.fn));
+  std::memcpy(P.fn, initial ? H.init_fn : H.fn, sizeof(P.fn));
   P.fn_op = D->fn_op.p; P.fn_c = D->fn_c.p; P.opt = H.opt;
   for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
   P.elem_jac = (pull_mass_mode == 3) ? nullptr : ((O.jac || pull_mass_mode) ? D->elem_jac.p : nullptr);
@@ -344,7 +358,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
     const GenBatch& B = H.batches[(size_t)b];
     if (volume) {
       P.items = nullptr; P.item_begin = B.elem_begin; P.item_end = B.elem_end; P.inst_base = B.elem_begin;
-      std::memcpy(P.fn, H.fn, sizeof(P.fn));
+      std::memcpy(P.fn, initial ? H.init_fn : H.fn, sizeof(P.fn));
       for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
       P.geo_N = D->geo_N.p; P.geo_dN = D->geo_dN.p; P.ref_tab = D->ref_tab.p; P.qwts = D->qwts.p;
       if (const char* e = run_elements(false, B.elem_end - B.elem_begin)) return e;

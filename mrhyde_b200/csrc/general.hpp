@@ -74,6 +74,7 @@ struct GeneralPlanHost {
   std::vector<uint8_t> fn_op;
   std::vector<double> fn_c;
   GenFnRec fn[GEN_MAXFN];
+  GenFnRec init_fn[GEN_MAXFN];           // "initial <var>[...]" functions in (variable, component) order (setInitial)
   int16_t off[GEN_MAXVARS][GEN_MAXDOF];
   GenOpts opt;
   std::vector<GenSideFamily> sides;
@@ -105,6 +106,10 @@ const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenD
 const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                               const int32_t* conn, const int32_t* lids, const GraphDev& G, const double* mass_wts, bool lump, bool accumulate,
                               double* mass, double* diag, void* stream, GenLaunchStats* stats);
+// setInitial, projection right-hand side: rhs (+)= sum_e sum_q initial(x_q) phi_i w (element kernel in initial mode, residual stage only)
+const char* gen_project_initial(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
+                                const int32_t* conn, const int32_t* lids, const GraphDev& G, double time, bool accumulate, double* rhs, void* stream,
+                                GenLaunchStats* stats);
 // applyMassMatrixFree: y (+)= M x without forming M (element kernel in mass mode, residual stage only)
 const char* gen_apply_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                            const int32_t* conn, const int32_t* lids, const GraphDev& G, const double* mass_wts, bool accumulate, const double* x, double* y,

@@ -151,7 +151,8 @@ struct GenParams {
   double* elem_res;         // [n_inst][N]      may be null
   int32_t epb;              // elements per CTA
   // mass mode (getWeightedMass, assemblyManager_mass.hpp:1065-1146): the module's point function is replaced by
-  // Cf[v][value components] = mass_wts[v] * F[v] * w, so the "Jacobian" is the weighted mass matrix
+  // Cf[v][value components] = mass_wts[v] * F[v] * w, so the "Jacobian" is the weighted mass matrix; 2: projection of the
+  // initial conditions (gen_initial_point, residual stage only)
   int32_t mass_mode;
   double mass_wts[GEN_MAXVARS];
 };
@@ -236,6 +237,19 @@ MRH_HD void gen_mass_point(const QpCtx& c, const double* mw, const T (&F)[Phys::
 #pragma unroll
     for (int k = 0; k < Phys::NC; ++k)
       if (k < Phys::nval(Phys::var_basis(v))) Cf[v][k] = (mw[v] * c.w) * F[v][k];
+}
+
+// setInitial, right-hand side of the L2 projection (assemblyManager_initial.hpp:260-311): the point function is replaced by
+// Cf[v][value components] = initial_v[component](x) * w; in this mode the function slots hold the "initial <var>[...]" functions
+// in (variable, component) order instead of the module's coefficient functions
+template <class Phys, class T>
+MRH_HD void gen_initial_point(const QpCtx& c, T (&Cf)[Phys::NVAR][Phys::NC]) {
+  int slot = 0;
+#pragma unroll
+  for (int v = 0; v < Phys::NVAR; ++v)
+#pragma unroll
+    for (int k = 0; k < Phys::NC; ++k)
+      if (k < Phys::nval(Phys::var_basis(v))) Cf[v][k] = c.fn[slot++] * c.w;
 }
 
 // ---- shared-memory layout of one element (offsets in doubles; every block is a multiple of 2 doubles) ---------
@@ -463,7 +477,8 @@ struct GenBlock {
     double F[NVAR][NC], Ft[NVAR][NC], Cf[NVAR][NC];
     for (int v = 0; v < NVAR; ++v)
       for (int k = 0; k < NC; ++k) { F[v][k] = sme[L::FV + (q * NVAR + v) * NC + k]; Ft[v][k] = sme[L::FT + (q * NVAR + v) * NC + k]; Cf[v][k] = 0.0; }
-    if (P.mass_mode) gen_mass_point<Phys, double>(c, P.mass_wts, F, Cf);
+    if (P.mass_mode == 2) gen_initial_point<Phys, double>(c, Cf);
+    else if (P.mass_mode) gen_mass_point<Phys, double>(c, P.mass_wts, F, Cf);
     else if (SIDE) Phys::template boundary<double>(c, P.opt, F, Ft, Cf);
     else Phys::template volume<double>(c, P.opt, F, Ft, Cf);
     for (int v = 0; v < NVAR; ++v)

@@ -56,6 +56,7 @@ struct EngineBase {
   virtual std::string printTree(const std::string& name, const std::string& loc) = 0;
   virtual void evalFunction(AssemblyManager& am, const std::string& name, const std::string& loc, int grp, double* out) = 0;
   virtual void evalField(AssemblyManager& am, const std::string& label, const double* sol, int grp, double* out) = 0;
+  virtual void projectInitial(AssemblyManager& am, double* rhs) = 0;
 };
 
 class AssemblyManager {
@@ -197,6 +198,17 @@ struct Engine : EngineBase {
         else if (b.type == "Neumann")
           fm.addFunction("Neumann " + am.dofs.vars[v].name + " " + am.mesh.side_names[s], b.expr, "side ip");
       }
+    // initial conditions (physicsInterface_functions.hpp:154-226): "initial <var>" for HGRAD / HVOL variables, "initial <var>[x|y|z]"
+    // for HCURL / HDIV ones; variables the sublist does not name start from 0.0
+    for (size_t v = 0; v < am.dofs.vars.size(); ++v) {
+      const std::string& var = am.dofs.vars[v].name;
+      const std::string bt = am.dofs.bases[am.dofs.vars[v].basis].type;
+      if (bt == "HCURL" || bt == "HDIV") {
+        for (const char* c : {"[x]", "[y]", "[z]"}) fm.addFunction("initial " + var + c, am.settings.get("Physics/Initial conditions/" + var + c, "0.0"), "ip");
+      } else {
+        fm.addFunction("initial " + var, am.settings.get("Physics/Initial conditions/" + var, "0.0"), "ip");
+      }
+    }
     // true solutions (postprocess) so the gold L2 errors can be reproduced
     for (auto& p : am.settings.sub("Postprocess/True solutions/")) {
       fm.addFunction("true " + p.first, p.second, "ip");
@@ -360,6 +372,34 @@ struct Engine : EngineBase {
     for (int e = 0; e < g.numElem; ++e)
       for (int q = 0; q < np; ++q) out[(size_t)e * np + q] = ADTraits<EvalT>::val(v(e, q));
     wkset.isOnSide = false;
+  }
+
+  // setInitial, right-hand side of the L2 projection (assemblyManager_initial.hpp:36-76 with getInitial(project = true), :260-311, and
+  // PhysicsInterface::getInitial, physicsInterface_initial.hpp:30-95):
+  //   rhs(LID(e, off(dof))) += sum_pt initial_var(e, pt[, dim]) basis(e, dof, pt[, dim]) wts(e, pt)      (no isFixedDOF check)
+  void projectInitial(AssemblyManager& am, double* rhs) override {
+    const int ndofE = am.dofs.ndof_elem, np = wkset.numip, dim = am.mesh.dim;
+    wkset.isOnSide = false;
+    wkset.time = am.td.time;
+    static const char* comp[3] = {"[x]", "[y]", "[z]"};
+    for (const Group& g : am.groups) {
+      pointAtGroup(am, g, false);
+      wkset.reset();
+      for (size_t n = 0; n < am.dofs.vars.size(); ++n) {
+        const int b = am.dofs.vars[n].basis;
+        const Basis& B = am.dofs.bases[b];
+        const auto& off = am.dofs.offsets[n];
+        const double* cb = &g.basis[b][0];
+        const bool vec = (B.type == "HCURL" || B.type == "HDIV");
+        for (int d = 0; d < (vec ? dim : 1); ++d) {
+          Vista<EvalT> v = fm.evaluate("initial " + am.dofs.vars[n].name + (vec ? comp[d] : ""), "ip");
+          for (int e = 0; e < g.numElem; ++e)
+            for (int dof = 0; dof < B.card; ++dof)
+              for (int pt = 0; pt < np; ++pt)
+                rhs[g.LIDs[(size_t)e * ndofE + off[dof]]] += ADTraits<EvalT>::val(v(e, pt)) * cb[(((size_t)e * B.card + dof) * np + pt) * B.vdim + d] * g.wts[(size_t)e * np + pt];
+        }
+      }
+    }
   }
 
   void evalField(AssemblyManager& am, const std::string& label, const double* sol, int grp, double* out) override {

@@ -185,6 +185,14 @@ int oracle_apply_mass(void* hv, const double* masswts, const double* x, double* 
   ORACLE_CATCH(1)
 }
 
+int oracle_project_initial(void* hv, double* rhs) {
+  ORACLE_TRY
+  auto* h = (OracleHandle*)hv;
+  h->am->eng_scalar->projectInitial(*h->am, rhs);
+  return 0;
+  ORACLE_CATCH(1)
+}
+
 int oracle_weighted_mass(void* hv, const double* masswts, int lump, double* Mvals, double* diag) {
   ORACLE_TRY
   ((OracleHandle*)hv)->am->weightedMass(masswts, lump != 0, Mvals, diag);

@@ -209,6 +209,12 @@ class OracleProblem:
         self._chk(self.L.oracle_apply_mass(self.h, _p(w, C.c_double), _p(x, C.c_double), _p(y, C.c_double)))
         return y
 
+    def project_initial(self):
+        """setInitial: right-hand side of the L2 projection of the `Initial conditions` (sum_q u0 phi_i w per row)."""
+        rhs = np.zeros(self.num_dofs)
+        self._chk(self.L.oracle_project_initial(self.h, _p(rhs, C.c_double)))
+        return rhs
+
     def weighted_mass(self, mass_wts, lump=False):
         """getWeightedMass: (mass values in graph order, diagonal vector)."""
         w = np.ascontiguousarray(mass_wts, dtype=np.float64)

@@ -25,6 +25,8 @@ def plan_from_oracle(op, cfg, device=0, options=None, indexed=False):
         plan.set_function(k, v)
     phys = cfg.get("Physics", {})
     solver = cfg.get("Solver", {})
+    for k, v in phys.get("Initial conditions", {}).items():   # "initial <var>" / "initial <var>[x]" (physicsInterface_functions.hpp:154-226)
+        plan.set_function("initial " + k, str(v))
     for key in ("form_param", "include advection", "useSUPG", "usePSPG", "assemble boundary terms", "assemble volume terms", "penalty",
                 "incplanestress", "ns3d_uz_rows", "use leap frog"):
         if key in phys:

@@ -139,3 +139,34 @@ def test_mass_apply_stages_match_oracle(oracle_lib, product_lib, name, cfg, wts)
     assert helpers.rel_err_vec(y, yref) < TOL
     M, _ = op.weighted_mass(wts)
     assert helpers.rel_err_vec(op.csr(M) @ x, yref) < 1e-12
+
+
+INITIAL_CASES = [
+    ("le3d", configs.variant(configs.LE_3D, **{"Physics/Initial conditions": {"dx": "sin(pi*x)*y", "dy": "1.0+z"}}), 0.0),
+    ("maxwell", configs.variant(configs.MAXWELL_3D, **{"Physics/Initial conditions": {"E[x]": "sin(pi*z)", "E[y]": "x*y", "B[z]": "cos(pi*x)+y"}}), 0.0),
+    ("ns2d", configs.variant(configs.NS_2D, **{"Physics/Initial conditions": {"ux": "1.0-y*y", "pr": "x"}}), 0.0),
+    ("thermal3d-q2", configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 3, "Mesh/NY": 3, "Mesh/NZ": 2, "Mesh/perturb": 0.02, "Discretization/order/T": 2,
+                                                           "Discretization/quadrature": 4, "Physics/Initial conditions": {"T": "exp(-x)*y+t"}}), 0.3),
+]
+
+
+@pytest.mark.parametrize("name,cfg,time", INITIAL_CASES, ids=[c[0] for c in INITIAL_CASES])
+def test_initial_projection_stages_match_oracle(oracle_lib, product_lib, name, cfg, time):
+    """setInitial: right-hand side of the L2 projection of the `Initial conditions`, scalar and vector-valued
+    bases; the mass matrix of the projection is getMass = the weighted mass with unit weights (tested above)."""
+    op = oracle_lib.OracleProblem(cfg)
+    op.set_time(False, time=time)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options={"kernel": "general"})
+    ref = op.project_initial()
+    op.set_time(False)
+    assert np.abs(ref).max() > 0
+    rhs = np.zeros(op.num_dofs)
+    plan.debug_emulate_initial(rhs, time=time)
+    assert helpers.rel_err_vec(rhs, ref) < TOL
+    if name == "ns2d":   # solving M u = rhs with the consistent mass matrix reproduces a function of the discrete space: pr = x
+        import scipy.sparse.linalg as spla
+        M, _ = op.weighted_mass([1.0, 1.0, 1.0])
+        u = spla.spsolve(op.csr(M).tocsc(), rhs)
+        pr = op.offsets[1]
+        for e in range(op.num_elems):
+            assert np.allclose(u[op.lids[e][pr]], op.elem_nodes[e][:, 0], atol=1e-12)

@@ -158,6 +158,26 @@ def test_weighted_mass_matches_oracle(oracle_lib, product_lib, name, cfg, wts):
             assert abs(A[n::3, n::3].sum() - wts[n]) < 1e-12
 
 
+@pytest.mark.parametrize("name,cfg,time", [
+    ("le3d", configs.variant(configs.LE_3D, **{"Physics/Initial conditions": {"dx": "sin(pi*x)*y", "dy": "1.0+z"}}), 0.0),
+    ("maxwell", configs.variant(configs.MAXWELL_3D, **{"Physics/Initial conditions": {"E[x]": "sin(pi*z)", "E[y]": "x*y", "B[z]": "cos(pi*x)+y"}}), 0.0),
+    ("ns3d", configs.variant(configs.NS_3D, **{"Physics/Initial conditions": {"ux": "1.0-y*y", "pr": "x+t", "uz": "z*z"}}), 0.25)],
+    ids=["le3d", "maxwell", "ns3d"])
+def test_initial_projection_matches_oracle(oracle_lib, product_lib, name, cfg, time):
+    """setInitial (assemblyManager_initial.hpp:36-76, 260-311) through mrhyde_b200_project_initial: right-hand side of the L2
+    projection of the `Initial conditions` against the oracle, adding into the caller's vector like the reference."""
+    import torch
+    op = oracle_lib.OracleProblem(cfg)
+    op.set_time(False, time=time)
+    ref = op.project_initial()
+    op.set_time(False)
+    plan = helpers.plan_from_oracle(op, cfg)
+    d_rhs = torch.full((op.num_dofs,), 2.0, dtype=torch.float64, device=torch.device("cuda:0"))
+    plan.project_initial(d_rhs, time=time)
+    torch.cuda.synchronize()
+    assert np.abs(ref).max() > 0 and helpers.rel_err_vec(d_rhs.cpu().numpy() - 2.0, ref) < 1e-12
+
+
 def _spmv(rowptr, colind, vals, x):
     import torch
     J = torch.sparse_csr_tensor(torch.from_numpy(rowptr).to(x.device), torch.from_numpy(colind.astype(np.int64)).to(x.device), vals, size=(len(rowptr) - 1, len(rowptr) - 1))
