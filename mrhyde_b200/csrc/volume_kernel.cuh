@@ -33,11 +33,17 @@ namespace mrhyde_b200 {
 #define MRH_TRANSIENT(td) (MRH_JIT_TRANSIENT != 0)
 #define MRH_TAB(f) jit_tab::f      /* constexpr copy: folds into immediates / index arithmetic */
 #define MRH_CTAB(f) jit_ctab::f    /* __constant__ copy: the value is a constant-bank operand of the FMA */
+#ifdef MRH_JIT_LITERAL_TABLES
+#define MRH_LTAB(f) jit_tab::f     /* literal: equal table entries (the tables are snapped) share one register */
+#else
+#define MRH_LTAB(f) jit_ctab::f
+#endif
 #define MRH_UNROLL_Q _Pragma("unroll")
 #else
 #define MRH_TRANSIENT(td) ((td).transient != 0)
 #define MRH_TAB(f) P.tab.f
 #define MRH_CTAB(f) P.tab.f
+#define MRH_LTAB(f) P.tab.f
 #define MRH_UNROLL_Q _Pragma("unroll 1")
 #endif
 
@@ -297,9 +303,9 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
     for (int c = 0; c < NC; ++c) {
       double k = 0.0;
 #pragma unroll
-      for (int g = 0; g < NGU; ++g) k += G[g] * MRH_CTAB(Stab)[g][jit_tab::rep[c]];
+      for (int g = 0; g < NGU; ++g) k += G[g] * MRH_LTAB(Stab)[g][jit_tab::rep[c]];
       kc[c] = k; mc[c] = 0.0;
-      if (MRH_TRANSIENT(td)) { mc[c] = md * MRH_CTAB(Mtab)[jit_tab::rep[c]]; k = td.alpha_u * k + td.alpha_t * mc[c]; }
+      if (MRH_TRANSIENT(td)) { mc[c] = md * MRH_LTAB(Mtab)[jit_tab::rep[c]]; k = td.alpha_u * k + td.alpha_t * mc[c]; }
       st[c * cap] = k;
     }
 #pragma unroll
@@ -351,9 +357,9 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
     mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const double fw = f[q] * MRH_CTAB(qw)[q] * adet;
+      const double fw = f[q] * MRH_LTAB(qw)[q] * adet;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) r[i] -= fw * MRH_CTAB(phi)[q][i];
+      for (int i = 0; i < NV; ++i) r[i] -= fw * MRH_LTAB(phi)[q][i];
     }
   }
 #endif
@@ -713,9 +719,9 @@ __device__ __forceinline__ void metric_cell(const ThermalParams<DIM>& P, const E
       mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        const double fw = f[q] * MRH_CTAB(qw)[q] * adet;
+        const double fw = f[q] * MRH_LTAB(qw)[q] * adet;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) fl[i] += fw * MRH_CTAB(phi)[q][i];
+        for (int i = 0; i < NV; ++i) fl[i] += fw * MRH_LTAB(phi)[q][i];
       }
     } else {
 #pragma unroll
