@@ -260,6 +260,9 @@ int mrhyde_b200_plan_debug_scatter_host(mrhyde_b200_plan* plan, const double* st
  * index of local-matrix entry (i,j) -- the upper-triangle index, or the entry's class on plans with the class ring
  * (plan_stat "class_ring" > 0) -- and rmap[i] = index of residual entry i. */
 int mrhyde_b200_plan_debug_stage_map(mrhyde_b200_plan* plan, int32_t* kmap, int32_t* rmap);
+/* mask[r] = 1 for every row the sweep chains [chain_begin, chain_end) write.  Multi-rank plans number the chains that complete
+ * ghost rows first (plan_stat "n_early_chains"): option "overlap halo" launches those, starts the exchange, then launches the rest. */
+int mrhyde_b200_plan_debug_chain_rows(mrhyde_b200_plan* plan, int32_t chain_begin, int32_t chain_end, uint8_t* mask);
 
 #ifdef __cplusplus
 }

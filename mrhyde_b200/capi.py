@@ -25,7 +25,7 @@ SYMBOLS = [
     "mrhyde_b200_assemble_jacres", "mrhyde_b200_assemble_res", "mrhyde_b200_assemble_jacres_host",
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
-    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
+    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_plan_debug_chain_rows", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
     "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
     "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
@@ -101,6 +101,7 @@ def lib():
         L.mrhyde_b200_plan_debug_jit.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.mrhyde_b200_project_initial.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_emulate_initial.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.mrhyde_b200_plan_debug_chain_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.mrhyde_b200_plan_debug_stage_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_metric_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_assemble_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -386,6 +387,12 @@ class AssemblyPlan:
     def debug_emulate_initial(self, rhs, time=0.0):
         """Host replay of project_initial on a host-only plan (debugging aid, never an assembly path)."""
         self._chk(self.L.mrhyde_b200_plan_debug_emulate_initial(self.h, float(time), _ptr(rhs)))
+
+    def debug_chain_rows(self, chain_begin, chain_end, n_rows):
+        """Boolean mask of the rows the sweep chains [chain_begin, chain_end) write."""
+        mask = np.zeros(n_rows, dtype=np.uint8)
+        self._chk(self.L.mrhyde_b200_plan_debug_chain_rows(self.h, int(chain_begin), int(chain_end), _ptr(mask)))
+        return mask.astype(bool)
 
     def debug_stage_map(self, ndof):
         """(kmap[ndof, ndof], rmap[ndof]): where local-matrix entry (i, j) / residual entry i sit in the staged element vector."""

@@ -130,6 +130,8 @@ struct mrhyde_b200_plan {
   int row_tab = 0;
   int jit_min_blocks = 1;
   size_t smem = 0;
+  bool suppress_overlap = false;
+  int64_t overlapped_assembles = 0;   // assemble calls that started the halo exchange after the ghost-row chains
   int metric_ng = 0;               // > 0: the specialised kernels use the metric ring with this many metric entries per element
   int class_nc = 0;                // > 0: class ring (boxes + constant coefficients): distinct local-matrix values staged per element
   std::vector<int32_t> class_of_t, class_rep;   // upper-triangle entry -> class, class -> representative entry
@@ -162,7 +164,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -867,8 +869,31 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
       jk = jit_variant(P, td.transient != 0, mode, log);
       if (!jk) fail(MRHYDE_B200_ERR_CUDA, "jit: kernel build failed: " + log);
     }
-    const char* lerr = P->use_jit ? jk->launch(params, P->cp.n_chains, P->threads, variant_smem(P, td.transient != 0), st)
-                                  : launch_thermal_q1_aot(P->dim, params, P->cp.n_chains, P->threads, P->smem, st);
+    // Multi-rank plans with option "overlap halo": the chains that complete the ghost rows run first (plan.cpp gives them the
+    // lowest ids); their rows are final after that launch -- every row is written by exactly one chain -- so the exchange with
+    // the owners starts there and runs beside the rest of the assembly.  mrhyde_b200_halo_sum then only waits and adds.
+    const int n_early = P->cp.n_early_chains;
+    const bool overlap = !P->suppress_overlap && opt_bool(P, "overlap halo", false) && P->halo && P->halo->can_start() && want_jac && want_res &&
+                         n_early > 0 && n_early < P->cp.n_chains && P->boundary.groups.empty() && P->cp.orphan_rows.empty();
+    if (P->halo) P->halo->drain(st);
+    auto launch_range = [&](int first, int count) -> const char* {
+      if (P->dim == 3) P->th3.chains.chain_offset = first; else P->th2.chains.chain_offset = first;
+      return P->use_jit ? jk->launch(params, count, P->threads, variant_smem(P, td.transient != 0), st)
+                        : launch_thermal_q1_aot(P->dim, params, count, P->threads, P->smem, st);
+    };
+    const char* lerr = nullptr;
+    if (overlap) {
+      lerr = launch_range(0, n_early);
+      if (!lerr) {
+        std::string herr;
+        if (!P->halo->start(res, jac, st, herr)) fail(MRHYDE_B200_ERR_NCCL, herr);
+        ++P->overlapped_assembles;
+        lerr = launch_range(n_early, P->cp.n_chains - n_early);
+        ++launched;
+      }
+    } else {
+      lerr = launch_range(0, P->cp.n_chains);
+    }
     if (lerr) fail(MRHYDE_B200_ERR_CUDA, std::string("volume kernel launch: ") + lerr);
     record_end(P, st, slot);
     ++launched;
@@ -1506,7 +1531,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     P->d_fixed_diag.upload(diag, tot);
     if (diag.empty()) P->d_fixed_diag.n = 0;
   }
-  ChainDev D;
+  ChainDev D{};
   D.chain_step_ptr = P->d_chain_step_ptr.p; D.steps = P->d_steps.p; D.step_elems = P->d_step_elems.p;
   D.batches = P->d_batches.p; D.rows = P->d_rows.p;
   D.step_conn = P->d_step_conn.p; D.step_lids = P->d_step_lids.p; D.step_eclass = P->d_step_eclass.p;
@@ -1619,7 +1644,10 @@ int mrhyde_b200_assemble_jacres_host(mrhyde_b200_plan* P, const double* sol, con
     P->h_jac.resize(nnz, nullptr);
     if (P->accumulate) CUDA_OK(cudaMemcpyAsync(P->h_jac.p, jac_values, nnz * sizeof(double), cudaMemcpyHostToDevice, st));
   }
-  do_assemble(P, P->h_sol.p, td, compute_jacobian != 0, compute_residual != 0, P->h_res.p, P->h_jac.p, st);
+  P->suppress_overlap = true;   // host buffers: there is no halo_sum on the library's scratch arrays
+  try { do_assemble(P, P->h_sol.p, td, compute_jacobian != 0, compute_residual != 0, P->h_res.p, P->h_jac.p, st); }
+  catch (...) { P->suppress_overlap = false; throw; }
+  P->suppress_overlap = false;
   if (compute_residual) CUDA_OK(cudaMemcpyAsync(res, P->h_res.p, nr * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (compute_jacobian) CUDA_OK(cudaMemcpyAsync(jac_values, P->h_jac.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
@@ -1686,6 +1714,8 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "halo_launches_per_sum") *value = P->halo ? P->halo->launches_per_sum() : 0;
   else if (k == "smem_bytes") *value = (int64_t)variant_smem(P, false);
   else if (k == "metric_ring") *value = P->metric_ng;
+  else if (k == "overlapped_assembles") *value = P->overlapped_assembles;
+  else if (k == "n_early_chains") *value = P->cp.n_early_chains;
   else if (k == "class_ring") *value = P->class_nc;
   else if (k == "stage_len") *value = P->stage_len;
   else if (k == "threads_per_block") *value = P->threads;
@@ -1995,6 +2025,23 @@ int mrhyde_b200_plan_debug_metric_host(mrhyde_b200_plan* P, const double* sol, c
   const int ng = P->dim * (P->dim + 1) / 2;
   if (P->dim == 3) { metric_host_elements<3>(P, P->th3, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th3.tab.Stab[0][0], &P->th3.tab.Mtab[0], td.alpha_u, td.transient ? td.alpha_t : 0.0, accumulate != 0, res, jac); }
   else { metric_host_elements<2>(P, P->th2, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th2.tab.Stab[0][0], &P->th2.tab.Mtab[0], td.alpha_u, td.transient ? td.alpha_t : 0.0, accumulate != 0, res, jac); }
+  ABI_END
+}
+
+int mrhyde_b200_plan_debug_chain_rows(mrhyde_b200_plan* P, int32_t chain_begin, int32_t chain_end, uint8_t* mask /*[n_rows]*/) {
+  ABI_BEGIN
+  if (!P || !mask) fail(MRHYDE_B200_ERR_INVALID, "debug_chain_rows: null argument");
+  if (!P->finalized || P->use_general) fail(MRHYDE_B200_ERR_STATE, "debug_chain_rows: needs a finalized plan on the sweep kernel");
+  const ChainPlan& cp = P->cp;
+  if (chain_begin < 0 || chain_end > cp.n_chains || chain_begin > chain_end) fail(MRHYDE_B200_ERR_INVALID, "debug_chain_rows: chain range out of bounds");
+  for (int32_t c = chain_begin; c < chain_end; ++c)
+    for (int32_t st = cp.chain_step_ptr[(size_t)c]; st < cp.chain_step_ptr[(size_t)c + 1]; ++st) {
+      const StepRec& S = cp.steps[(size_t)st];
+      for (int32_t b = 0; b < S.n_batches; ++b) {
+        const BatchRec& B = cp.batches[(size_t)(S.batch_begin + b)];
+        for (int l = 0; l < (int)B.n_rows; ++l) mask[cp.rows[(size_t)(S.batch_begin + b) * 32 + (size_t)l].row] = 1;
+      }
+    }
   ABI_END
 }
 

@@ -98,6 +98,7 @@ HaloExchange::~HaloExchange() {
     cudaFree(p.d_send_res); cudaFree(p.d_send_jac); cudaFree(p.d_recv_res); cudaFree(p.d_recv_jac);
     cudaFree(p.d_sendbuf); cudaFree(p.d_recvbuf);
   }
+  if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); cudaEventDestroy(ev_ready_); cudaEventDestroy(ev_done_); }
   if (comm_ && api().ok) api().CommDestroy((ncclComm_t)comm_);
 }
 
@@ -228,11 +229,63 @@ bool HaloExchange::setup(int64_t n_rows, int64_t n_owned, int64_t n_cols, const 
   return true;
 }
 
+bool HaloExchange::can_start() const {
+  if (!ready_) return false;
+  for (int p = 0; p < nranks_; ++p) {
+    const Peer& P = peers_[(size_t)p];
+    if (p == rank_) continue;
+    if ((P.n_send_res && P.send_res_first < 0) || (P.n_send_jac && P.send_jac_first < 0)) return false;   // would need a pack kernel
+  }
+  return true;
+}
+
+bool HaloExchange::start(double* res, double* jac, cudaStream_t st, std::string& err) {
+  NcclApi& A = api();
+  ncclComm_t comm = (ncclComm_t)comm_;
+  if (!can_start() || !res || !jac) { err = "halo: start() needs contiguous ghost slices and both arrays"; return false; }
+  if (!side_) {
+    CU_TRY(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&ev_ready_, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
+  }
+  CU_TRY(cudaEventRecord(ev_ready_, st));
+  CU_TRY(cudaStreamWaitEvent(side_, ev_ready_, 0));
+  NCCL_TRY(A.GroupStart());
+  for (int p = 0; p < nranks_; ++p) {
+    Peer& P = peers_[(size_t)p];
+    if (p == rank_) continue;
+    if (P.n_send_res) NCCL_TRY(A.Send(res + P.send_res_first, (size_t)P.n_send_res, ncclFloat64, p, comm, side_));
+    if (P.n_send_jac) NCCL_TRY(A.Send(jac + P.send_jac_first, (size_t)P.n_send_jac, ncclFloat64, p, comm, side_));
+    if (P.n_recv_res) NCCL_TRY(A.Recv(P.d_recvbuf, (size_t)P.n_recv_res, ncclFloat64, p, comm, side_));
+    if (P.n_recv_jac) NCCL_TRY(A.Recv(P.d_recvbuf + P.n_recv_res, (size_t)P.n_recv_jac, ncclFloat64, p, comm, side_));
+  }
+  NCCL_TRY(A.GroupEnd());
+  CU_TRY(cudaEventRecord(ev_done_, side_));
+  started_ = true; started_res_ = res; started_jac_ = jac;
+  return true;
+}
+
 bool HaloExchange::sum(double* res, double* jac, cudaStream_t st, std::string& err) {
   NcclApi& A = api();
   ncclComm_t comm = (ncclComm_t)comm_;
   auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
   int launched = 0;
+  if (started_) {   // the exchange of these arrays is already in flight (start()): wait for it, then add on `st`
+    if (res != started_res_ || jac != started_jac_) { err = "halo: sum() after start() must be given the same arrays"; return false; }
+    started_ = false;
+    CU_TRY(cudaStreamWaitEvent(st, ev_done_, 0));
+    for (int p = 0; p < nranks_; ++p) {  // ascending source rank: fixed summation order
+      Peer& P = peers_[(size_t)p];
+      if (p == rank_) continue;
+      if (P.n_recv_res + P.n_recv_jac) {
+        unpack_add2_kernel<<<blocks(P.n_recv_res + P.n_recv_jac), 256, 0, st>>>(P.d_recvbuf, P.d_recv_res, P.n_recv_res, res, P.d_recv_jac, P.n_recv_jac, jac);
+        ++launched;
+      }
+    }
+    launches_ = launched;
+    CU_TRY(cudaGetLastError());
+    return true;
+  }
   for (int p = 0; p < nranks_; ++p) {
     Peer& P = peers_[(size_t)p];
     if (p == rank_) continue;

@@ -26,6 +26,13 @@ class HaloExchange {
   // collective: builds send/receive maps from the global row ids of every rank
   bool setup(int64_t n_rows, int64_t n_owned, int64_t n_cols, const int64_t* col_gids, const int64_t* rowptr, const int32_t* colind, std::string& err);
   bool sum(double* res, double* jac, cudaStream_t st, std::string& err);
+  // Overlapped form of sum(): start() is called once the ghost rows of res / jac are final on `st` (the caller may keep
+  // launching work that does not touch them); the send/recv run on an internal stream.  sum() called afterwards with the same
+  // arrays waits for them and adds the received values on `st`.  Ghost slices must be contiguous (in-place send) for start().
+  bool can_start() const;
+  bool start(double* res, double* jac, cudaStream_t st, std::string& err);
+  // an exchange started earlier whose sum() was never called: `st` waits for it before the arrays are written again
+  void drain(cudaStream_t st) { if (started_) { cudaStreamWaitEvent(st, ev_done_, 0); started_ = false; } }
   bool ready() const { return ready_; }
   int launches_per_sum() const { return launches_; }
 
@@ -34,6 +41,11 @@ class HaloExchange {
   int rank_ = 0, nranks_ = 1;
   bool ready_ = false;
   int launches_ = 0;
+  // overlapped exchange
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t ev_ready_ = nullptr, ev_done_ = nullptr;
+  double* started_res_ = nullptr; double* started_jac_ = nullptr;
+  bool started_ = false;
   // per peer: what I send (positions in my res / jac arrays) and where received values are added
   struct Peer {
     int64_t n_send_res = 0, n_send_jac = 0, n_recv_res = 0, n_recv_jac = 0;

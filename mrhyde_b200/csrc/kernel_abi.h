@@ -74,6 +74,7 @@ struct ChainDev {
   const SrcQuad* mdesc0;           // metric-ring source words (same indexing as desc0 / desc1)
   const SrcQuad* mdesc1;
   int32_t cap;                     // ring slot capacity (elements)
+  int32_t chain_offset;            // first chain of this launch (a multi-rank assemble launches the ghost-row chains first)
 };
 
 struct GraphDev {

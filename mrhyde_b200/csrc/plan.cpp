@@ -338,6 +338,21 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       row_level[(size_t)r] = bl;
       ++chain_row_ptr[(size_t)row_chain[(size_t)r] + 1];
     }
+    // multi-rank plans: chains that complete ghost rows (rows another rank owns, local id >= nowned) get the lowest chain ids,
+    // so that they can be launched first and their rows sent to the owner while the remaining chains are assembled
+    out.n_early_chains = 0;
+    if (m.nowned > 0 && m.nowned < nr) {
+      std::vector<uint8_t> early((size_t)nchains, 0);
+      for (int64_t r = m.nowned; r < nr; ++r) if (row_chain[(size_t)r] >= 0) early[(size_t)row_chain[(size_t)r]] = 1;
+      std::vector<int32_t> newid((size_t)nchains, 0);
+      int32_t k = 0;
+      for (int32_t c = 0; c < nchains; ++c) if (early[(size_t)c]) newid[(size_t)c] = k++;
+      out.n_early_chains = k;
+      for (int32_t c = 0; c < nchains; ++c) if (!early[(size_t)c]) newid[(size_t)c] = k++;
+      std::fill(chain_row_ptr.begin(), chain_row_ptr.end(), 0);
+      for (int64_t r = 0; r < nr; ++r)
+        if (row_chain[(size_t)r] >= 0) { row_chain[(size_t)r] = newid[(size_t)row_chain[(size_t)r]]; ++chain_row_ptr[(size_t)row_chain[(size_t)r] + 1]; }
+    }
     for (int32_t c = 0; c < nchains; ++c) chain_row_ptr[(size_t)c + 1] += chain_row_ptr[(size_t)c];
     std::vector<int32_t> chain_rows((size_t)chain_row_ptr[(size_t)nchains]);
     {

@@ -41,6 +41,7 @@ struct MeshGraph {  // host inputs of one block
 
 struct ChainPlan {
   int32_t n_chains = 0, n_levels = 0, n_columns = 0, n_segments = 0;
+  int32_t n_early_chains = 0;  // chains [0, n_early_chains) complete every ghost row of a multi-rank plan (0: none / single rank)
   int32_t cap = 0;             // ring slot capacity in elements (max elements of any step)
   int32_t stage_len = 0;       // staged doubles per element
   int32_t max_rows_step = 0, max_batches_step = 0;

@@ -937,7 +937,8 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   extern __shared__ double ring[];
   typedef Q1Shape<DIM> S;
   const ChainDev& C = P.chains;
-  const int s0 = __ldg(C.chain_step_ptr + blockIdx.x), s1 = __ldg(C.chain_step_ptr + blockIdx.x + 1);
+  const int chain = (int)blockIdx.x + C.chain_offset;
+  const int s0 = __ldg(C.chain_step_ptr + chain), s1 = __ldg(C.chain_step_ptr + chain + 1);
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef MRH_JIT_METRIC

@@ -271,3 +271,22 @@ def test_compressed_ring_kernels_compile(oracle_lib, product_lib, tmp_path):
         text = src.read_text()
         for m in marks:
             assert m in text
+
+
+def test_ghost_row_chains_come_first(product_lib):
+    """Multi-rank plans number the chains that complete ghost rows first, so that option "overlap halo" can launch them, start
+    the exchange and launch the rest: chains [0, n_early) write every ghost row, and every row is written by exactly one chain."""
+    from mrhyde_b200.problems import ThermalBrick
+    for rank, world in ((0, 2), (1, 3), (2, 3), (0, 1)):
+        prob = ThermalBrick(3, (12, 10, 8), device=-1, rank=rank, nranks=world, options={"column elements": 16, "min segment levels": 2})
+        plan = prob.plan
+        n_early, n_chains = plan.stat("n_early_chains"), plan.stat("n_chains")
+        ghosts = np.arange(prob.n_rows) >= prob.n_owned
+        if not ghosts.any():
+            assert n_early == 0
+            continue
+        assert 0 < n_early < n_chains
+        early = plan.debug_chain_rows(0, n_early, prob.n_rows)
+        late = plan.debug_chain_rows(n_early, n_chains, prob.n_rows)
+        assert early[ghosts].all() and not late[ghosts].any()
+        assert not (early & late).any() and (early | late).all()

@@ -14,8 +14,11 @@ N = (12, 10, 8)
 
 def _make(kind, n, rank, world):
     from mrhyde_b200.problems import SystemBrick, ThermalBrick
-    if kind == "thermal":
-        return ThermalBrick(3, n, device=rank, rank=rank, nranks=world, options={"column elements": 16, "min segment levels": 2})
+    if kind.startswith("thermal"):
+        options = {"column elements": 16, "min segment levels": 2}
+        if kind == "thermal_overlap" and world > 1:   # ghost-row chains first, exchange beside the rest of the assembly
+            options["overlap halo"] = "true"
+        return ThermalBrick(3, n, device=rank, rank=rank, nranks=world, options=options)
     return SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[kind], 3, n, device=rank, rank=rank, nranks=world, options={"batch elems": 300})
 
 
@@ -30,26 +33,40 @@ def _worker(rank, world, port, q, kind="thermal"):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        prob = _make(kind, N, rank, world)
-        uid = torch.from_numpy(prob.plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
-        dist.broadcast(uid, 0)
-        prob.plan.comm_init(uid.cpu().numpy(), rank, world)
-        prob.plan.set_halo(prob.col_gids)
-        u = torch.from_numpy(prob.state()).to(dev)
-        res = torch.zeros(prob.n_rows, dtype=torch.float64, device=dev)
-        jac = torch.zeros(prob.nnz, dtype=torch.float64, device=dev)
-        prob.plan.assemble_jacres(u, res, jac)
-        prob.plan.halo_sum(res, jac)
-        torch.cuda.synchronize()
-        no = prob.n_owned
-        q.put((rank, prob.col_gids.copy(), res[:no].cpu().numpy(), prob.rowptr[: no + 1].copy(), prob.colind[: prob.rowptr[no]].copy(),
-               jac[: prob.rowptr[no]].cpu().numpy(), prob.state()[:no].copy()))
-        dist.barrier()
+        _worker_body(rank, world, q, kind, dev)
+    except Exception as e:   # report instead of leaving the parent to wait for the queue time-out
+        q.put(("error", rank, repr(e)))
+        os._exit(1)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["thermal", "le", "ns"])
+def _worker_body(rank, world, q, kind, dev):
+    import torch
+    import torch.distributed as dist
+    prob = _make(kind, N, rank, world)
+    uid = torch.from_numpy(prob.plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
+    dist.broadcast(uid, 0)
+    prob.plan.comm_init(uid.cpu().numpy(), rank, world)
+    prob.plan.set_halo(prob.col_gids)
+    u = torch.from_numpy(prob.state()).to(dev)
+    res = torch.zeros(prob.n_rows, dtype=torch.float64, device=dev)
+    jac = torch.zeros(prob.nnz, dtype=torch.float64, device=dev)
+    for _ in range(2 if kind == "thermal_overlap" else 1):   # twice: the second exchange reuses the side stream and events
+        res.zero_()
+        jac.zero_()
+        prob.plan.assemble_jacres(u, res, jac)
+        prob.plan.halo_sum(res, jac)
+    torch.cuda.synchronize()
+    if kind == "thermal_overlap" and prob.n_owned < prob.n_rows:   # only ranks that hold ghost rows start an exchange early
+        assert prob.plan.stat("overlapped_assembles") == 2 and 0 < prob.plan.stat("n_early_chains") < prob.plan.stat("n_chains")
+    no = prob.n_owned
+    q.put((rank, prob.col_gids.copy(), res[:no].cpu().numpy(), prob.rowptr[: no + 1].copy(), prob.colind[: prob.rowptr[no]].copy(),
+           jac[: prob.rowptr[no]].cpu().numpy(), prob.state()[:no].copy()))
+    dist.barrier()
+
+
+@pytest.mark.parametrize("kind", ["thermal", "thermal_overlap", "le", "ns"])
 def test_two_gpu_halo_sum_equals_single_gpu(product_lib, kind):
     import torch
     if torch.cuda.device_count() < 2:
@@ -59,11 +76,19 @@ def test_two_gpu_halo_sum_equals_single_gpu(product_lib, kind):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "le": 3, "ns": 5}[kind]
+    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "thermal_overlap": 7, "le": 3, "ns": 5}[kind]
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
-    outs = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    outs = []
+    for _ in range(world):
+        item = q.get(timeout=180)
+        if item[0] == "error":
+            for p in procs:
+                p.terminate()
+            pytest.fail("rank %d: %s" % (item[1], item[2]))
+        outs.append(item)
+    outs.sort(key=lambda t: t[0])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
