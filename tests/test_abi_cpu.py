@@ -273,6 +273,23 @@ def test_compressed_ring_kernels_compile(oracle_lib, product_lib, tmp_path):
             assert m in text
 
 
+def test_build_option_variants_compile(oracle_lib, product_lib, tmp_path):
+    """Every tuning option of the specialised build still yields a translation unit NVRTC accepts (the options are measured
+    alternatives kept for experiments); unknown values are rejected at finalize."""
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 9, "Mesh/NY": 7, "Mesh/NZ": 6})
+    variants = [{"flush": "flat"}, {"flush": "row", "flush unroll": 4}, {"pull group": 28}, {"pull patterns": 0}, {"stage1": "early"},
+                {"stage1": "early", "stage2": "early"}, {"tables": "literal"}, {"stagger ns": 3000}, {"max registers": 96},
+                {"ring": "metric", "pull group": 4}, {"ring": "full", "flush": "flat"}]
+    for options in variants:
+        op, plan = _host_plan(oracle_lib, cfg, options=options)
+        log = plan.debug_jit(source_path=str(tmp_path / "k.cu"))
+        assert "error" not in log.lower()
+    with pytest.raises(product_lib.MrhydeB200Error):
+        _host_plan(oracle_lib, cfg, options={"ring": "sparse"})
+    with pytest.raises(product_lib.MrhydeB200Error):
+        _host_plan(oracle_lib, cfg, options={"no such option": 1})
+
+
 def test_ghost_row_chains_come_first(product_lib):
     """Multi-rank plans number the chains that complete ghost rows first, so that option "overlap halo" can launch them, start
     the exchange and launch the rest: chains [0, n_early) write every ghost row, and every row is written by exactly one chain."""

@@ -239,6 +239,18 @@ def test_metric_ring_variants(oracle_lib, product_lib, kernel_build, mesh):
                 assert helpers.rel_err_rows(d_jac.cpu().numpy(), jac_ref, op.rowptr) < TOL and float(d_res.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("options", [{"flush": "flat"}, {"stage1": "early"}, {"pull group": 28}, {"flush": "flat", "ring": "metric"}],
+                         ids=["flush-flat", "stage1-early", "group-28", "metric-flat"])
+def test_measured_build_alternatives_match_oracle(oracle_lib, product_lib, kernel_build, options):
+    """Alternatives of the specialised build that were measured on the B200 and kept as options stay correct."""
+    if kernel_build == "false":
+        pytest.skip("options of the plan-specialised build")
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 13, "Mesh/NY": 11, "Mesh/NZ": 9})
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, options=dict(options, **{"column elements": 6, "min segment levels": 2}))
+    _check(op, plan, helpers.manufactured_state(op))
+
+
 def test_full_size_properties(product_lib, kernel_build):
     """BASELINE configs[1] (128^3 hex-Q1 thermal) is too large for the oracle; check size-independent properties of the
     assembled system instead: K 1 = 0 on free rows, symmetry of the free-free block, res(u) = res(0) - J u (the problem is
