@@ -236,6 +236,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
     options = {"accumulate": "false"}
+    if world > 1 and _WORKLOAD == "thermal" and os.environ.get("MRHYDE_B200_OVERLAP_HALO", "0") == "1":
+        options["overlap halo"] = "true"   # opt-in until the overlapped exchange has been measured
     for kv in args.opt:
         k, v = kv.split("=", 1)
         options[k] = v

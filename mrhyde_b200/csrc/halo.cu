@@ -244,7 +244,10 @@ bool HaloExchange::start(double* res, double* jac, cudaStream_t st, std::string&
   ncclComm_t comm = (ncclComm_t)comm_;
   if (!can_start() || !res || !jac) { err = "halo: start() needs contiguous ghost slices and both arrays"; return false; }
   if (!side_) {
-    CU_TRY(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    // highest priority: the few CTAs of the send/recv kernel should get onto the SMs as soon as CTAs of the assembly retire
+    CU_TRY(cudaStreamCreateWithPriority(&side_, cudaStreamNonBlocking, prio_hi));
     CU_TRY(cudaEventCreateWithFlags(&ev_ready_, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
   }
