@@ -164,7 +164,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -791,10 +791,8 @@ int variant_min_blocks(const mrhyde_b200_plan* P, size_t smem) {
 }
 
 // Specialised kernel for (steady | transient, output mode); compiled by NVRTC on first use.
-const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std::string& log) {
-  const int key = (transient ? 8 : 0) + mode;
-  auto it = P->jit.find(key);
-  if (it != P->jit.end()) return it->second.get();
+// the plan's translation unit with the markers of one build replaced: steady | transient, output mode, start-up stagger
+std::string specialise_source(const mrhyde_b200_plan* P, bool transient, int mode, std::string& log) {
   std::string src = P->jit_source;
   auto swap_define = [&](const std::string& mark, const std::string& with) {
     const size_t at = src.find(mark);
@@ -805,18 +803,25 @@ const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std:
   if (!swap_define("#define MRH_JIT_TRANSIENT 0  /*@transient@*/", std::string("#define MRH_JIT_TRANSIENT ") + (transient ? "1" : "0")) ||
       !swap_define("#define MRH_JIT_MODE 7  /*@mode@*/", "#define MRH_JIT_MODE " + std::to_string(mode))) {
     log = "specialisation markers missing from the generated source";
-    return nullptr;
+    return std::string();
   }
+  const int stagger = std::max(0, std::stoi(opt(P, "stagger ns", "0")));
+  int n_sm = 148;
+  if (P->device >= 0) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device);
+  const int blocks = variant_min_blocks(P, variant_smem(P, transient));
+  swap_define("/*@stagger@*/", "#define MRH_JIT_STAGGER_NS " + std::to_string(stagger) + "u\n#define MRH_JIT_STAGGER_SMS " + std::to_string(n_sm) +
+                               "u\n#define MRH_JIT_STAGGER_BLOCKS " + std::to_string(blocks) + "u\n#define MRH_JIT_STAGGER_SLOTS " + std::to_string(n_sm * blocks) + "u");
+  return src;
+}
+
+const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std::string& log) {
+  const int key = (transient ? 8 : 0) + mode;
+  auto it = P->jit.find(key);
+  if (it != P->jit.end()) return it->second.get();
+  const std::string src = specialise_source(P, transient, mode, log);
+  if (src.empty()) return nullptr;
   std::unique_ptr<JitKernel> k(new JitKernel());
   const size_t smem = variant_smem(P, transient);
-  {
-    const int stagger = std::max(0, std::stoi(opt(P, "stagger ns", "0")));
-    int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, P->device);
-    const int blocks = variant_min_blocks(P, smem);
-    swap_define("/*@stagger@*/", "#define MRH_JIT_STAGGER_NS " + std::to_string(stagger) + "u\n#define MRH_JIT_STAGGER_SMS " + std::to_string(n_sm) +
-                                 "u\n#define MRH_JIT_STAGGER_BLOCKS " + std::to_string(blocks) + "u\n#define MRH_JIT_STAGGER_SLOTS " + std::to_string(n_sm * blocks) + "u");
-  }
   if (!k->build(src, P->dim == 3 ? "mrh_thermal_q1_3d" : "mrh_thermal_q1_2d", P->threads, variant_min_blocks(P, smem), smem, log, std::stoi(opt(P, "max registers", "0")))) return nullptr;
   const JitKernel* raw = k.get();
   P->jit[key] = std::move(k);
@@ -1250,7 +1255,7 @@ int mrhyde_b200_plan_set_option(mrhyde_b200_plan* P, const char* key, const char
   for (const char** k = kKnownOptions; *k; ++k) if (std::string(*k) == key) known = true;
   if (!known) fail(MRHYDE_B200_ERR_INVALID, std::string("set_option: unknown key '") + key + "'");
   const std::string k(key), v(value);
-  if (P->finalized && k != "accumulate" && k != "assemble boundary terms" && k != "assemble volume terms") fail(MRHYDE_B200_ERR_STATE, "set_option: '" + k + "' must be set before finalize");
+  if (P->finalized && k != "accumulate" && k != "assemble boundary terms" && k != "assemble volume terms" && k != "debug transient" && k != "debug mode") fail(MRHYDE_B200_ERR_STATE, "set_option: '" + k + "' must be set before finalize");
   if (k == "accumulate") {
     if (v != "true" && v != "false") fail(MRHYDE_B200_ERR_INVALID, "set_option: accumulate must be true|false");
     P->accumulate = (v == "true");
@@ -1807,8 +1812,18 @@ int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* P, const char* source_path, con
     std::fclose(f);
   }
   std::string cubin, text;
-  const int min_blocks = variant_min_blocks(P, variant_smem(P, false));
-  const bool ok = nvrtc_compile(P->jit_source, P->threads, min_blocks, cubin, text, std::stoi(opt(P, "max registers", "0")));
+  // which build: options "debug transient" (0 | 1) and "debug mode" (1 res | 2 jac | 4 accumulate, summed); default steady, mode 7
+  const bool transient = opt(P, "debug transient", "0") == "1";
+  const int mode = std::stoi(opt(P, "debug mode", "7"));
+  if (mode < 1 || mode > 7 || (mode & 3) == 0) fail(MRHYDE_B200_ERR_INVALID, "debug_jit: option 'debug mode' must have the residual and/or Jacobian bit set");
+  const std::string variant = specialise_source(P, transient, mode, text);
+  if (variant.empty()) fail(MRHYDE_B200_ERR_CUDA, "debug_jit: " + text);
+  if (source_path) {   // the specialised text replaces the template written above
+    FILE* f = std::fopen(source_path, "wb");
+    if (f) { std::fwrite(variant.data(), 1, variant.size(), f); std::fclose(f); }
+  }
+  const int min_blocks = variant_min_blocks(P, variant_smem(P, transient));
+  const bool ok = nvrtc_compile(variant, P->threads, min_blocks, cubin, text, std::stoi(opt(P, "max registers", "0")));
   if (log && log_cap) { std::snprintf(log, log_cap, "%s", text.c_str()); }
   if (!ok) fail(MRHYDE_B200_ERR_CUDA, "debug_jit: " + text);
   if (cubin_path) {

@@ -290,6 +290,21 @@ def test_build_option_variants_compile(oracle_lib, product_lib, tmp_path):
         _host_plan(oracle_lib, cfg, options={"no such option": 1})
 
 
+@pytest.mark.parametrize("ring,shear", [("class", 0.0), ("metric", 0.0), ("metric", 0.3), ("full", 0.0)])
+def test_every_build_variant_compiles(oracle_lib, product_lib, ring, shear):
+    """The specialised kernel is built per (steady | transient, output mode): a sample of the twelve builds of every ring layout compiles for sm_100a."""
+    upd = {"Mesh/NX": 7, "Mesh/NY": 5, "Mesh/NZ": 4, "Functions/density": "2.0", "Functions/specific heat": "1.5", "Functions/thermal source": "sin(t)*x+y*z"}
+    if shear:
+        upd["Mesh/shear"] = shear
+    op, plan = _host_plan(oracle_lib, configs.variant(configs.THERMAL_3D, **upd), options={"ring": ring})
+    for transient in (0, 1):
+        for mode in (1, 3, 6):   # residual only, residual + Jacobian overwrite, Jacobian only accumulate
+            plan.set_option("debug transient", transient)
+            plan.set_option("debug mode", mode)
+            log = plan.debug_jit()
+            assert "error" not in log.lower(), (transient, mode, log[-400:])
+
+
 def test_ghost_row_chains_come_first(product_lib):
     """Multi-rank plans number the chains that complete ghost rows first, so that option "overlap halo" can launch them, start
     the exchange and launch the rest: chains [0, n_early) write every ghost row, and every row is written by exactly one chain."""

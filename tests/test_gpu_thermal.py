@@ -251,6 +251,32 @@ def test_measured_build_alternatives_match_oracle(oracle_lib, product_lib, kerne
     _check(op, plan, helpers.manufactured_state(op))
 
 
+@pytest.mark.parametrize("shear", [0.0, 0.3], ids=["box", "sheared"])
+def test_metric_ring_transient(oracle_lib, product_lib, kernel_build, shear):
+    """Transient builds of the metric ring (mass entry + time derivative staged, J = alpha_u K + alpha_t M in the pull): the layout a
+    sheared mesh gets by default.  Checked on the host (replay + NVRTC); first GPU run pending -- set MRHYDE_B200_TEST_UNVALIDATED=1."""
+    import os
+    import torch
+    if kernel_build == "false":
+        pytest.skip("the metric ring exists in the plan-specialised build only")
+    if os.environ.get("MRHYDE_B200_TEST_UNVALIDATED", "0") != "1":
+        pytest.skip("transient metric-ring builds have not run on a GPU yet (set MRHYDE_B200_TEST_UNVALIDATED=1)")
+    upd = {"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Functions/density": "2.0", "Functions/specific heat": "1.5", "Functions/thermal source": "sin(t)*x+y*z"}
+    if shear:
+        upd["Mesh/shear"] = shear
+    cfg = configs.variant(configs.THERMAL_3D, **upd)
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, options={"ring": "metric"})
+    rng = np.random.default_rng(3)
+    u, up = rng.standard_normal(op.num_dofs), rng.standard_normal(op.num_dofs)
+    d_up = torch.from_numpy(up).to(torch.device("cuda:0"))
+    for (A, b, c) in (([[1.0]], [1.0], [1.0]), ([[0.5]], [1.0], [0.5])):
+        op.set_time(True, time=0.3, dt=0.01, stage=0, A=A, b=b, c=c, bdf=(1.0, -1.0))
+        ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=0, A=A, b=b, c=c, bdf=(1.0, -1.0), sol_prev=[d_up], sol_stage=[d_up])
+        _check(op, plan, u, time=ts, oracle_kw=dict(sol_prev=[up], sol_stage=[u]))
+    op.set_time(False)
+
+
 def test_full_size_properties(product_lib, kernel_build):
     """BASELINE configs[1] (128^3 hex-Q1 thermal) is too large for the oracle; check size-independent properties of the
     assembled system instead: K 1 = 0 on free rows, symmetry of the free-free block, res(u) = res(0) - J u (the problem is

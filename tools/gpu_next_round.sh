@@ -2,6 +2,8 @@
 # 1. parity of the overlapped halo exchange (option "overlap halo"), bounded so a hang costs little
 # 2. weak-scaling bench line with and without it
 N=${1:-2}
+# 0. paths that were only checked on the host so far: transient builds of the metric ring
+MRHYDE_B200_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_thermal.py -x -q -k metric_ring_transient 2>&1 | tail -4
 MRHYDE_B200_TEST_OVERLAP=1 timeout 240 python -m pytest tests/test_gpu_multirank.py -x -q -k thermal 2>&1 | tail -4
 for e in 0 1; do
   MRHYDE_B200_OVERLAP_HALO=$e timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$e \
