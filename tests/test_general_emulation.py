@@ -170,3 +170,21 @@ def test_initial_projection_stages_match_oracle(oracle_lib, product_lib, name, c
         pr = op.offsets[1]
         for e in range(op.num_elems):
             assert np.allclose(u[op.lids[e][pr]], op.elem_nodes[e][:, 0], atol=1e-12)
+
+
+def test_initial_projection_reproduces_reference_gold(oracle_lib, product_lib):
+    """regression/maxwell/NonzeroIC through the kernel stages: projection right-hand side and unit-weight mass matrix from the
+    host replay of the general path, solved on the host, give the L2 errors mrhyde.gold prints at time 0."""
+    import scipy.sparse.linalg as spla
+    deck, errs = helpers.gold_errors("maxwell/NonzeroIC")
+    cfg = helpers.deck_to_cfg(deck)
+    gold = {e["field"]: e["value"] for e in errs if e["time"] == 0.0}
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options={"kernel": "general"})
+    rhs, M, d = np.zeros(op.num_dofs), np.zeros(op.nnz), np.zeros(op.num_dofs)
+    plan.debug_emulate_initial(rhs)
+    plan.debug_emulate_mass([1.0, 1.0], M, d)
+    u = spla.spsolve(op.csr(M).tocsc(), rhs)
+    for f in ("E", "B"):
+        got = op.l2_error([f + "[x]", f + "[y]", f + "[z]"], u)
+        assert abs(got - gold[f]) <= 0.5e-5 * gold[f], (f, got, gold[f])

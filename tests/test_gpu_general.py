@@ -178,6 +178,29 @@ def test_initial_projection_matches_oracle(oracle_lib, product_lib, name, cfg, t
     assert np.abs(ref).max() > 0 and helpers.rel_err_vec(d_rhs.cpu().numpy() - 2.0, ref) < 1e-12
 
 
+def test_set_initial_reproduces_reference_gold(oracle_lib, product_lib):
+    """regression/maxwell/NonzeroIC on the GPU: mrhyde_b200_project_initial + mrhyde_b200_assemble_mass (unit weights), solved on the
+    host, give the L2 errors the reference prints at time 0 (E 0.0692758, B 0.0976523)."""
+    import scipy.sparse.linalg as spla
+    import torch
+    deck, errs = helpers.gold_errors("maxwell/NonzeroIC")
+    cfg = helpers.deck_to_cfg(deck)
+    gold = {e["field"]: e["value"] for e in errs if e["time"] == 0.0}
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    dev = torch.device("cuda:0")
+    d_rhs = torch.zeros(op.num_dofs, dtype=torch.float64, device=dev)
+    d_M = torch.zeros(op.nnz, dtype=torch.float64, device=dev)
+    d_d = torch.zeros(op.num_dofs, dtype=torch.float64, device=dev)
+    plan.project_initial(d_rhs)
+    plan.assemble_mass([1.0, 1.0], d_M, d_d)
+    torch.cuda.synchronize()
+    u = spla.spsolve(op.csr(d_M.cpu().numpy()).tocsc(), d_rhs.cpu().numpy())
+    for f in ("E", "B"):
+        got = op.l2_error([f + "[x]", f + "[y]", f + "[z]"], u)
+        assert abs(got - gold[f]) <= 0.5e-5 * gold[f], (f, got, gold[f])
+
+
 def _spmv(rowptr, colind, vals, x):
     import torch
     J = torch.sparse_csr_tensor(torch.from_numpy(rowptr).to(x.device), torch.from_numpy(colind.astype(np.int64)).to(x.device), vals, size=(len(rowptr) - 1, len(rowptr) - 1))

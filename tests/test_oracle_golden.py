@@ -180,3 +180,29 @@ def test_maxwell_planewave_gold(oracle_lib):
             got = op.l2_error([f + "[x]", f + "[y]", f + "[z]"], u)
             want = gold[(f, n + 1)]
             assert abs(got - want) <= _tol(want), (f, n + 1, got, want)
+
+
+def test_maxwell_nonzero_ic_gold(oracle_lib):
+    """regression/maxwell/NonzeroIC: 8^3 hex, E (HCURL) and B (HDIV) start from sin(pi x) sin(pi y) sin(pi z) in every component
+    through the default `initial type: L2-projection` (solverManager_util.hpp:252-267): pins setInitial -- the projection right-hand
+    side (assemblyManager_initial.hpp:260-311) and getMass -- for vector-valued bases at time 0, and one DIRK-1,2 step from a
+    non-zero state at time 0.01."""
+    import scipy.sparse.linalg as spla
+    cfg, errs = _errs("maxwell/NonzeroIC")
+    gold = {(e["field"], e["time"]): e["value"] for e in errs}
+    assert set(gold) == {("E", 0.0), ("B", 0.0), ("E", 0.01), ("B", 0.01)}
+    op = oracle_lib.OracleProblem(cfg)
+    M, _ = op.weighted_mass([1.0, 1.0])
+    u = spla.spsolve(op.csr(M).tocsc(), op.project_initial())
+    for f in ("E", "B"):
+        got = op.l2_error([f + "[x]", f + "[y]", f + "[z]"], u)
+        assert abs(got - gold[(f, 0.0)]) <= _tol(gold[(f, 0.0)]), (f, got)
+    dt = float(cfg["Solver"]["final time"]) / int(cfg["Solver"]["number of steps"])
+    op.set_time(True, time=0.0, dt=dt, stage=0, A=((0.5,),), b=(1.0,), c=(0.5,), bdf=(1.0, -1.0))
+    us = u.copy()
+    res, jac = op.assemble_jacres(us, sol_prev=[u], sol_stage=[us])
+    u1 = us + spla.spsolve(op.csr(jac).tocsc(), res)
+    for f in ("E", "B"):
+        got = op.l2_error([f + "[x]", f + "[y]", f + "[z]"], u1)
+        assert abs(got - gold[(f, 0.01)]) <= _tol(gold[(f, 0.01)]), (f, got)
+    op.set_time(False)
