@@ -241,6 +241,10 @@ int mrhyde_b200_plan_debug_jit(mrhyde_b200_plan* plan, const char* source_path, 
  * machines without a GPU.  All pointers are host pointers; no assemble_* entry point can reach this. */
 int mrhyde_b200_plan_debug_metric_host(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, int accumulate,
                                        double* res, double* jac_values);
+/* The same for plans on the class ring (plan_stat "class_ring" > 0): one local-matrix value per class + the residual per element, by
+ * the kernel's formulas, then the plan's scatter programs. */
+int mrhyde_b200_plan_debug_class_host(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, int accumulate,
+                                      double* res, double* jac_values);
 /* Replays the general path's kernel stage functions (general_kernel.cuh, compiled by the host compiler) and the pull on
  * the host for a host-only plan (device = -1) built with option kernel=general: a debugging aid that lets the kernel
  * logic be checked against the oracle on machines without a GPU.  Fails with ERR_STATE on device plans; the assemble

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mrhyde_b200_assemble_jacres", "mrhyde_b200_assemble_res", "mrhyde_b200_assemble_jacres_host",
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
-    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_plan_debug_chain_rows", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
+    "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_class_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_plan_debug_chain_rows", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
     "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
     "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
@@ -104,6 +104,7 @@ def lib():
         L.mrhyde_b200_plan_debug_chain_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.mrhyde_b200_plan_debug_stage_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_metric_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_plan_debug_class_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_assemble_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_emulate_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_apply_mass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -404,6 +405,10 @@ class AssemblyPlan:
         """Host replay of the sweep kernel's metric ring (plans with stat("metric_ring") > 0): plan-analysis check, never an
         assembly path (mrhyde_b200_plan_debug_metric_host)."""
         self._chk(self.L.mrhyde_b200_plan_debug_metric_host(self.h, _ptr(sol), time.ref() if time is not None else None, int(accumulate), _ptr(res), _ptr(jac)))
+
+    def debug_class_host(self, sol, accumulate, res, jac, time=None):
+        """Host replay of the sweep kernel's class ring (plans with stat("class_ring") > 0): plan-analysis check, never an assembly path."""
+        self._chk(self.L.mrhyde_b200_plan_debug_class_host(self.h, _ptr(sol), time.ref() if time is not None else None, int(accumulate), _ptr(res), _ptr(jac)))
 
     def debug_jit(self, source_path=None, cubin_path=None):
         """Generates + NVRTC-compiles the plan-specialised kernel (no device needed); returns the compiler log."""

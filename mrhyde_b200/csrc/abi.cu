@@ -2060,6 +2060,48 @@ int mrhyde_b200_plan_debug_chain_rows(mrhyde_b200_plan* P, int32_t chain_begin, 
   ABI_END
 }
 
+// Host replay of the class ring: element metrics and load vectors by the kernel's formulas (metric_host_elements), one local-matrix
+// value per class + the residual as thermal_affine stages them, then the plan's scatter programs (host_apply_chain_plan).
+int mrhyde_b200_plan_debug_class_host(mrhyde_b200_plan* P, const double* sol, const mrhyde_b200_time* t, int accumulate, double* res, double* jac) {
+  ABI_BEGIN
+  if (!P || !sol) fail(MRHYDE_B200_ERR_INVALID, "debug_class_host: null argument");
+  if (!P->finalized || P->use_general) fail(MRHYDE_B200_ERR_STATE, "debug_class_host: needs a finalized plan on the sweep kernel");
+  if (P->class_nc <= 0) fail(MRHYDE_B200_ERR_STATE, "debug_class_host: this plan does not use the class ring (needs box cells, constant coefficients, ring=auto|class)");
+  TimeDev td;
+  fill_time(t, td, true);   // host pointers: the replay reads them on the host
+  const int dim = P->dim, NV = 1 << dim, NT = NV * (NV + 1) / 2, NG = dim * (dim + 1) / 2, SLM = NG + 1 + 3 * NV, NC = P->class_nc, SL = NC + NV;
+  std::vector<double> met;
+  if (dim == 3) metric_host_elements<3>(P, P->th3, sol, td, met); else metric_host_elements<2>(P, P->th2, sol, td, met);
+  const double* St = dim == 3 ? &P->th3.tab.Stab[0][0] : &P->th2.tab.Stab[0][0];
+  const double* Mt = dim == 3 ? &P->th3.tab.Mtab[0] : &P->th2.tab.Mtab[0];
+  const MeshGraph& M = P->mesh;
+  std::vector<double> stage((size_t)M.nelem * SL, 0.0);
+  for (int64_t e = 0; e < M.nelem; ++e) {
+    const double* m = &met[(size_t)e * SLM];
+    double* o = &stage[(size_t)e * SL];
+    std::vector<double> kc((size_t)NC), mc((size_t)NC, 0.0);
+    for (int c = 0; c < NC; ++c) {
+      const int rep = P->class_rep[(size_t)c];
+      double k = 0.0;
+      for (int g = 0; g < dim; ++g) k += m[g] * St[(size_t)g * NT + rep];   // boxes: the diagonal metric entries only
+      kc[(size_t)c] = k;
+      if (td.transient) { mc[(size_t)c] = m[NG] * Mt[rep]; k = td.alpha_u * k + td.alpha_t * mc[(size_t)c]; }
+      o[c] = k;
+    }
+    for (int i = 0; i < NV; ++i) {
+      double r = 0.0;
+      for (int j = 0; j < NV; ++j) {
+        const int a = std::min(i, j), b = std::max(i, j), c = P->class_of_t[(size_t)(a * NV - (a * (a - 1)) / 2 + (b - a))];
+        r += kc[(size_t)c] * m[NG + 1 + NV + j];
+        if (td.transient) r += mc[(size_t)c] * m[NG + 1 + 2 * NV + j];
+      }
+      o[NC + i] = r - m[NG + 1 + i];
+    }
+  }
+  host_apply_chain_plan(M, P->cp, stage.data(), accumulate != 0, res, jac);
+  ABI_END
+}
+
 int mrhyde_b200_plan_debug_stage_map(mrhyde_b200_plan* P, int32_t* kmap /*[ndof*ndof]*/, int32_t* rmap /*[ndof]*/) {
   ABI_BEGIN
   if (!P || !kmap || !rmap) fail(MRHYDE_B200_ERR_INVALID, "debug_stage_map: null argument");

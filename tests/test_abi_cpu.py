@@ -228,6 +228,50 @@ def test_metric_ring_host_replay_transient(oracle_lib, product_lib):
     op.set_time(False)
 
 
+CLASS_CASES = {k: v for k, v in METRIC_CASES.items() if "sheared" not in k}
+
+
+@pytest.mark.parametrize("case", sorted(CLASS_CASES))
+def test_class_ring_host_replay_matches_oracle(oracle_lib, product_lib, case):
+    """The layout the headline workload runs on (boxes + constant coefficients, ring=auto): one local-matrix value per class of
+    entries + the residual per element.  Host replay of that plan -- the kernel's formulas, the plan's class map and scatter
+    programs -- against the oracle to 1e-12, steady and transient."""
+    base, upd, opts = CLASS_CASES[case]
+    cfg = configs.variant(base, **upd)
+    op, plan = _host_plan(oracle_lib, cfg, options=opts)
+    assert plan.stat("class_ring") == (8 if op.dim == 3 else 4) and plan.stat("metric_ring") == 0
+    u = helpers.manufactured_state(op)
+    res_ref, jac_ref = op.assemble_jacres(u)
+    for accumulate in (1, 0):
+        res = np.full(op.num_dofs, 0.0 if accumulate else 7.0)
+        jac = np.full(op.nnz, 0.0 if accumulate else 7.0)
+        plan.debug_class_host(u, accumulate, res, jac)
+        jr = jac_ref.copy()
+        if accumulate:   # dofConstraints (J(d,d) = 1 on fixed rows) is a separate kernel in accumulate mode
+            for r in np.nonzero(op.is_fixed)[0]:
+                jr[op.rowptr[r]:op.rowptr[r + 1]] = 0.0
+        assert helpers.rel_err_vec(res, res_ref) < 1e-12
+        assert helpers.rel_err_rows(jac, jr, op.rowptr) < 1e-12
+
+
+def test_class_ring_host_replay_transient(oracle_lib, product_lib):
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Functions/density": "2.0", "Functions/specific heat": "1.5",
+                                                  "Functions/thermal source": "sin(t)*x+y*z"})
+    op, plan = _host_plan(oracle_lib, cfg)
+    assert plan.stat("class_ring") == 8
+    rng = np.random.default_rng(3)
+    u, up = rng.standard_normal(op.num_dofs), rng.standard_normal(op.num_dofs)
+    for (A, b, c) in (([[1.0]], [1.0], [1.0]), ([[0.5]], [1.0], [0.5])):
+        op.set_time(True, time=0.3, dt=0.01, stage=0, A=A, b=b, c=c, bdf=(1.0, -1.0))
+        ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=0, A=A, b=b, c=c, bdf=(1.0, -1.0), sol_prev=[up], sol_stage=[up])
+        res_ref, jac_ref = op.assemble_jacres(u, sol_prev=[up], sol_stage=[u])
+        res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+        plan.debug_class_host(u, 0, res, jac, time=ts)
+        assert helpers.rel_err_vec(res, res_ref) < 1e-12
+        assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < 1e-12
+    op.set_time(False)
+
+
 def test_ring_layout_selection(oracle_lib, product_lib):
     """ring=auto: class ring on axis-aligned boxes, metric ring on sheared parallelepipeds (both need constant coefficients),
     full local systems otherwise; asking for a layout the plan cannot have is an error."""
