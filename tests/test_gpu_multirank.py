@@ -71,8 +71,6 @@ def test_two_gpu_halo_sum_equals_single_gpu(product_lib, kind):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if kind == "thermal_overlap" and os.environ.get("MRHYDE_B200_TEST_OVERLAP", "0") != "1":
-        pytest.skip("option 'overlap halo' has not run on GPUs yet (DESIGN.md section 6): set MRHYDE_B200_TEST_OVERLAP=1 to run its parity test")
     import torch.multiprocessing as mp
     from mrhyde_b200.problems import ThermalBrick
     world = 2

@@ -254,13 +254,10 @@ def test_measured_build_alternatives_match_oracle(oracle_lib, product_lib, kerne
 @pytest.mark.parametrize("shear", [0.0, 0.3], ids=["box", "sheared"])
 def test_metric_ring_transient(oracle_lib, product_lib, kernel_build, shear):
     """Transient builds of the metric ring (mass entry + time derivative staged, J = alpha_u K + alpha_t M in the pull): the layout a
-    sheared mesh gets by default.  Checked on the host (replay + NVRTC); first GPU run pending -- set MRHYDE_B200_TEST_UNVALIDATED=1."""
-    import os
+    sheared mesh gets by default (first GPU run: profiles/r02_s1_first_gpu_runs.log)."""
     import torch
     if kernel_build == "false":
         pytest.skip("the metric ring exists in the plan-specialised build only")
-    if os.environ.get("MRHYDE_B200_TEST_UNVALIDATED", "0") != "1":
-        pytest.skip("transient metric-ring builds have not run on a GPU yet (set MRHYDE_B200_TEST_UNVALIDATED=1)")
     upd = {"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4, "Functions/density": "2.0", "Functions/specific heat": "1.5", "Functions/thermal source": "sin(t)*x+y*z"}
     if shear:
         upd["Mesh/shear"] = shear
