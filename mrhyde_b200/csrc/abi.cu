@@ -164,7 +164,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "debug transient", "debug mode", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -260,12 +260,12 @@ std::string hexd(double v) {
 void emit_values(std::string& o, const double* v, size_t n) {
   for (size_t i = 0; i < n; ++i) { o += hexd(v[i]); o += (i + 1 < n) ? "," : ""; }
 }
-std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group);
-std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab, int group);
+std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group, int flush_mode);
+std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab, int group, int flush_mode);
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
                                const int64_t (&n_class)[3], int metric_ng, int max_patterns, int pull_group,
-                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, bool flush_rows, int flush_unroll, bool early_stage2, bool literal_tables) {
+                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -283,7 +283,13 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   if (literal_tables) o += "#define MRH_JIT_LITERAL_TABLES 1\n";
   o += "/*@stagger@*/\n";
   o += "#define MRH_JIT_FLUSH_UNROLL " + std::to_string(flush_unroll) + "\n";
-  o += std::string("#define MRH_JIT_FLUSH ") + (flush_rows ? "1" : "0") + "   /* 1: one store instruction per row, 0: flat stream over the batch */\n";
+  o += "#define MRH_JIT_FLUSH " + std::to_string(flush_mode) + "   /* 2: bulk-copy engine (cp.async.bulk shared -> global per run of CSR-contiguous rows), 1: one store instruction per row, 0: flat stream over the batch */\n";
+  if (lids_are_conn) o += "#define MRH_JIT_LIDS_ARE_CONN 1   /* dof ids == vertex ids for every element: one connectivity stream */\n";
+  {
+    int present = 0, only = -1;
+    for (int c = 0; c < 3; ++c) if (n_class[c] > 0) { ++present; only = c; }
+    if (present == 1) o += "#define MRH_JIT_ONLY_ECLASS " + std::to_string(only) + "   /* every cell of the mesh has this class: no per-element class load */\n";
+  }
   o += "#define MRH_DEBUG_SKIP " + std::to_string(debug_skip) + "   /* timing experiments only: 1 no global stores, 2 no element work, 3 neither */\n";
   if (!class_rep.empty()) o += "#define MRH_JIT_CLASS_NC " + std::to_string(class_rep.size()) + "\n";   // class ring (volume_kernel.cuh)
   if (metric_ng > 0) {   // metric ring (volume_kernel.cuh): parallelepiped cells + constant coefficients only
@@ -396,8 +402,8 @@ __device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
       o += "};\n";
     }
   }
-  if (metric_ng > 0) o += pull_codegen_metric(cp, max_patterns, S::NV, S::NG, metric_ng, &T.Stab[0][0], &T.Mtab[0], pull_group);
-  else o += pull_codegen(cp, max_patterns, pull_group);
+  if (metric_ng > 0) o += pull_codegen_metric(cp, max_patterns, S::NV, S::NG, metric_ng, &T.Stab[0][0], &T.Mtab[0], pull_group, flush_mode);
+  else o += pull_codegen(cp, max_patterns, pull_group, flush_mode);
   o += "}  // namespace mrhyde_b200\n";
   o += kVolumeKernelSrc;
   return o;
@@ -423,9 +429,13 @@ std::vector<SpecialPattern> special_patterns(const ChainPlan& cp, int max_patter
 }
 int row_pitch(int n_jac) { return n_jac | 1; }   // odd pitch: a lane per row writes the row buffer without bank conflicts
 // doubles per row of the per-warp row buffer (MRH_JIT_ROWBUF); 0 when no pattern is specialised
-int row_buffer_pitch(const ChainPlan& cp, int max_patterns) {
+// flush_mode 2 (bulk copies): rows sit back to back (pitch = row length) from the start of the warp's buffer (the 32 row offsets of
+// the other modes are not stored), and every run of CSR-contiguous rows may be shifted by up to 2 * 31 + 1 doubles so that its
+// shared-memory address has the 16-byte phase of its global address: 32 NJ + 63 <= 32 + 32 (NJ + 1) doubles
+int row_buffer_pitch(const ChainPlan& cp, int max_patterns, int flush_mode) {
   int pitch = 0;
-  for (const SpecialPattern& sp : special_patterns(cp, max_patterns)) pitch = std::max(pitch, row_pitch(sp.n_slots - 1));
+  for (const SpecialPattern& sp : special_patterns(cp, max_patterns))
+    pitch = std::max(pitch, flush_mode == 2 ? sp.n_slots - 1 + 1 : row_pitch(sp.n_slots - 1));
   return pitch;
 }
 // Row flush shared by the generated pull code: the warp's rows sit in rowb (row r at r * PITCH), their CSR offsets in wbase.
@@ -477,18 +487,62 @@ __device__ __forceinline__ void mrh_flush_rows(const double* rowb, const long lo
   __syncwarp();
 }
 #endif
+#if MRH_JIT_FLUSH == 2
+// Bulk-copy flush.  Rows of a batch that follow each other in the CSR value array form a RUN; the lanes of a run park their rows back
+// to back (pitch NJ), the run shifted by 0..1 doubles so that shared and global address agree modulo 16 bytes, and the first lane of
+// the run hands the whole run to the bulk-copy engine (cp.async.bulk shared::cta -> global; an odd first / last double is peeled off
+// with a plain store).  The warp no longer reads the buffer back or issues one store per row: the LSU pipe only sees the parking
+// stores.  Accumulate mode uses the reducing form (cp.reduce.async.bulk .add.f64): every entry receives exactly one addend per call.
+struct MrhRun { double* rl; unsigned starts; bool start; };
+__device__ __forceinline__ void mrh_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int NJ>
+__device__ __forceinline__ MrhRun mrh_run_begin(double* rowb, const double* jac, const long long base, const int n_rows, const int lane) {
+  mrh_bulk_wait_read();   // the previous batch of this warp has left the buffer (the issuing lanes wait; a no-op for the others)
+  __syncwarp();
+  const long long prev = __shfl_up_sync(0xffffffffu, base, 1);
+  MrhRun R;
+  R.start = lane < n_rows && (lane == 0 || base != prev + NJ);
+  R.starts = __ballot_sync(0xffffffffu, R.start);
+  const int ridx = __popc(R.starts & (0xffffffffu >> (31 - lane))) - 1;   // runs that begin at or below this lane, minus one
+  const int e = (int)(((long long)(reinterpret_cast<unsigned long long>(jac + base) >> 3) - (long long)(lane * NJ)) & 1);   // constant within a run
+  // idle lanes (they park garbage sums) sit one run further up so that they cannot touch the last row of the last run
+  R.rl = rowb + lane * NJ + 2 * (ridx + (lane >= n_rows ? 1 : 0)) + e;
+  return R;
+}
+template <int NJ, bool ACC>
+__device__ __forceinline__ void mrh_run_flush(const MrhRun& R, const long long base, double* __restrict__ jac, const int n_rows, const int lane) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores of this lane -> visible to the bulk-copy engine
+  __syncwarp();
+  if (R.start && !(MRH_DEBUG_SKIP & 1)) {
+    const unsigned later = R.starts & ~(0xffffffffu >> (31 - lane));
+    const int end = later ? (__ffs((int)later) - 1) : n_rows;
+    int cnt = (end - lane) * NJ;
+    long long g = base;
+    const double* s = R.rl;
+    if ((reinterpret_cast<unsigned long long>(jac + g) >> 3) & 1) { double v = s[0]; if (ACC) v += jac[g]; jac[g] = v; ++g; ++s; --cnt; }
+    if (cnt & 1) { double v = s[cnt - 1]; if (ACC) v += jac[g + cnt - 1]; jac[g + cnt - 1] = v; --cnt; }
+    if (cnt > 0) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+      if (ACC) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" :: "l"(jac + g), "r"(sa), "r"(cnt * 8) : "memory");
+      else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(jac + g), "r"(sa), "r"(cnt * 8) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+#endif
 )MRH";
 
 // ---- straight-line pull code for the plan's most frequent gather patterns (jit only) ------------------------------
 // For a pattern the slot descriptors are plan constants, so the generated code has no descriptor loads, no "unused"
 // tests and no address arithmetic: every staged value is one LDS with an immediate offset from the row's ring anchor.
 // Sums keep the ascending element order of the generic loop (slot_sum), so both paths give identical bits.
-std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group) {
+std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group, int flush_mode) {
+  const bool bulk = flush_mode == 2;
   group = std::max(4, (group / 4) * 4);   // sums formed before they are parked in the row buffer: loads in flight vs registers
   const std::vector<SpecialPattern> sel = special_patterns(cp, max_patterns);
   std::string o;
   if (sel.empty()) return o;
-  o += "#define MRH_JIT_PULL 1\n#define MRH_JIT_ROWBUF " + std::to_string(row_buffer_pitch(cp, max_patterns)) + "\n";
+  o += "#define MRH_JIT_PULL 1\n#define MRH_JIT_ROWBUF " + std::to_string(row_buffer_pitch(cp, max_patterns, flush_mode)) + "\n";
   o += "__device__ __forceinline__ double mrh_lds_at(unsigned a) { double v; asm volatile(\"ld.shared.f64 %0, [%1];\" : \"=d\"(v) : \"r\"(a)); return v; }\n";
   o += "#define MRH_L(off) mrh_lds_at(rbase + (off##u))\n";
   o += kFlushRowsSrc;
@@ -512,13 +566,18 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group) {
         }
         return cnt ? e : std::string("0.0");
       };
-      o += "    case " + std::to_string(db * 2 + par) + ": {\n      if (HAS_JAC) {\n        wbase[lane] = base;\n";
+      o += "    case " + std::to_string(db * 2 + par) + ": {\n      if (HAS_JAC) {\n";
+      if (bulk) o += "        const MrhRun run = mrh_run_begin<" + std::to_string(n_jac) + ">(wbuf, jac, base, n_rows, lane);\n";
+      else o += "        wbase[lane] = base;\n";
       // a group of sums first (the loads are independent and can be in flight together), then they are parked in the row buffer
       for (int g0 = 0; g0 < n_jac; g0 += group) {
         for (int k = g0; k < g0 + group && k < n_jac; ++k) o += "        const double a" + std::to_string(k) + " = " + sum_expr(k) + ";\n";
-        for (int k = g0; k < g0 + group && k < n_jac; ++k) o += "        rowb[lane * " + std::to_string(pitch) + " + " + std::to_string(k) + "] = a" + std::to_string(k) + ";\n";
+        for (int k = g0; k < g0 + group && k < n_jac; ++k)
+          o += bulk ? "        run.rl[" + std::to_string(k) + "] = a" + std::to_string(k) + ";\n"
+                    : "        rowb[lane * " + std::to_string(pitch) + " + " + std::to_string(k) + "] = a" + std::to_string(k) + ";\n";
       }
-      o += "        mrh_flush_rows<" + std::to_string(n_jac) + ", " + std::to_string(pitch) + ", ACC>(rowb, wbase, jac, n_rows, lane);\n";
+      if (bulk) o += "        mrh_run_flush<" + std::to_string(n_jac) + ", ACC>(run, base, jac, n_rows, lane);\n";
+      else o += "        mrh_flush_rows<" + std::to_string(n_jac) + ", " + std::to_string(pitch) + ", ACC>(rowb, wbase, jac, n_rows, lane);\n";
       o += "      }\n      if (HAS_RES) { const double acc = " + sum_expr(n_jac) + "; if (active) { double v = -acc; if (ACC) v += *pres; *pres = v; } }\n";
       o += "      return true;\n    }\n";
     }
@@ -529,13 +588,14 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group) {
 
 // ---- the same for the metric ring: a CSR entry is  sum_e sum_g G_g(e) Stab[g][t_e]  with the element columns, table entries
 // and state slots of the pattern as immediates.  The metric entries of the pattern's element columns are loaded once per row.
-std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab, int group) {
+std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, int ng_all, int ngu, const double* Stab, const double* Mtab, int group, int flush_mode) {
+  const bool bulk = flush_mode == 2;
   group = std::max(4, (group / 4) * 4);   // entries summed before their transpose rounds start (instruction-level parallelism vs registers)
   const std::vector<SpecialPattern> sel = special_patterns(cp, max_patterns);
   const int nt = nv * (nv + 1) / 2;
   (void)ng_all;
   std::string o;
-  o += "#define MRH_JIT_PULL_METRIC 1\n#define MRH_JIT_ROWBUF " + std::to_string(std::max(1, row_buffer_pitch(cp, max_patterns))) + "\n";
+  o += "#define MRH_JIT_PULL_METRIC 1\n#define MRH_JIT_ROWBUF " + std::to_string(std::max(1, row_buffer_pitch(cp, max_patterns, flush_mode))) + "\n";
   o += kFlushRowsSrc;
   o += "#define MRH_ESB (16u * MRH_JIT_CAP)\n";
   o += "#define MRH_MD MRH_JIT_METRIC_NG\n#define MRH_B0 (MRH_JIT_METRIC_NG + MRH_JIT_TRANSIENT)\n";
@@ -566,7 +626,8 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
           o += "      const double g" + std::to_string(c) + "_" + std::to_string(g) + " = MRH_ML(" + std::to_string(cols[c]) + "u, " + std::to_string(g) + ");\n";
         o += "#if MRH_JIT_TRANSIENT\n      const double m" + std::to_string(c) + " = MRH_ML(" + std::to_string(cols[c]) + "u, MRH_MD);\n#endif\n";
       }
-      o += "      if (HAS_JAC) wbase[lane] = base;\n      double racc = 0.0;\n";
+      if (bulk) o += "      MrhRun run; run.rl = rowb; run.starts = 0u; run.start = false;\n      if (HAS_JAC) run = mrh_run_begin<" + std::to_string(n_jac) + ">(wbuf, jac, base, n_rows, lane);\n      double racc = 0.0;\n";
+      else o += "      if (HAS_JAC) wbase[lane] = base;\n      double racc = 0.0;\n";
       for (int g0 = 0; g0 < n_jac; g0 += group) {
         for (int k = g0; k < g0 + group && k < n_jac; ++k) {
           const std::string a = "a" + std::to_string(k), mm = "mm" + std::to_string(k);
@@ -600,9 +661,11 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
           o += "#if MRH_JIT_TRANSIENT\n      " + a + " = fma(au, " + a + ", at * " + mm + ");\n#endif\n";
         }
         for (int k = g0; k < g0 + group && k < n_jac; ++k)
-          o += "      if (HAS_JAC) rowb[lane * " + std::to_string(pitch) + " + " + std::to_string(k) + "] = a" + std::to_string(k) + ";\n";
+          o += bulk ? "      if (HAS_JAC) run.rl[" + std::to_string(k) + "] = a" + std::to_string(k) + ";\n"
+                    : "      if (HAS_JAC) rowb[lane * " + std::to_string(pitch) + " + " + std::to_string(k) + "] = a" + std::to_string(k) + ";\n";
       }
-      o += "      if (HAS_JAC) mrh_flush_rows<" + std::to_string(n_jac) + ", " + std::to_string(pitch) + ", ACC>(rowb, wbase, jac, n_rows, lane);\n";
+      if (bulk) o += "      if (HAS_JAC) mrh_run_flush<" + std::to_string(n_jac) + ", ACC>(run, base, jac, n_rows, lane);\n";
+      else o += "      if (HAS_JAC) mrh_flush_rows<" + std::to_string(n_jac) + ", " + std::to_string(pitch) + ", ACC>(rowb, wbase, jac, n_rows, lane);\n";
       o += "      if (HAS_RES) {\n        double bs = 0.0;\n";
       for (int z = 0; z < SLOT_SRCS; ++z) {
         const uint32_t w = word(n_jac, z);
@@ -1451,6 +1514,12 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
       kmap[(size_t)i * NV + j] = (uint16_t)(use_class ? P->class_of_t[(size_t)t] : t);
     }
   }
+  // how the generated pull code writes finished rows: bulk (cp.async.bulk per run of CSR-contiguous rows, default) | row | flat
+  const std::string flush_opt = opt(P, "flush", "bulk");
+  if (flush_opt != "bulk" && flush_opt != "row" && flush_opt != "flat") fail(MRHYDE_B200_ERR_INVALID, "option flush must be bulk|row|flat");
+  const int flush_mode = flush_opt == "bulk" ? 2 : (flush_opt == "row" ? 1 : 0);
+  // one scalar field numbered like the vertices (the reference's Q1 thermal blocks): dof ids == vertex ids, one connectivity stream
+  const bool lids_are_conn = M.lids.size() == M.conn.size() && M.lids == M.conn;
   ChainOptions co;
   co.column_elems = std::stoi(opt(P, "column elements", "128"));
   co.min_chains = std::stoi(opt(P, "min chains", "592"));
@@ -1466,7 +1535,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     int64_t max_len = 0;
     for (int64_t r = 0; r < M.nrows; ++r) if (!M.fixed[(size_t)r]) max_len = std::max(max_len, M.rowptr[(size_t)r + 1] - M.rowptr[(size_t)r]);
     co.ring_stage_len = use_metric ? (P->dim + 2 * NV) : STAGE;
-    co.warp_buffer_bytes = jit_possible ? std::max<size_t>(PULL_WARP_DOUBLES * 8, (size_t)(32 + 32 * (std::min<int64_t>(max_len, 64) | 1)) * 8) : (size_t)PULL_WARP_DOUBLES * 8;
+    co.warp_buffer_bytes = jit_possible ? std::max<size_t>(PULL_WARP_DOUBLES * 8, (size_t)(32 + 32 * (flush_mode == 2 ? std::min<int64_t>(max_len, 64) + 1 : (std::min<int64_t>(max_len, 64) | 1))) * 8) : (size_t)PULL_WARP_DOUBLES * 8;
   }
   co.min_segment_levels = std::max(1, std::stoi(opt(P, "min segment levels", "8")));
   if (co.column_elems < 1 || co.min_chains < 1) fail(MRHYDE_B200_ERR_INVALID, "options 'column elements' and 'min chains' must be positive");
@@ -1482,8 +1551,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   // ring (2 slots) + one transpose buffer per warp
   // per-warp transpose buffer; the specialised builds park whole rows there (generated pull code, row_buffer_pitch)
   const int max_patterns = std::max(0, std::stoi(opt(P, "pull patterns", "3")));
-  const size_t warp_doubles = std::max<size_t>(PULL_WARP_DOUBLES, jit_possible ? 32 + 32 * (size_t)row_buffer_pitch(P->cp, max_patterns) : 0);
-  P->smem = (size_t)(2 * P->cp.slot_bytes()) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
+  const size_t warp_doubles = std::max<size_t>(PULL_WARP_DOUBLES, jit_possible ? 32 + 32 * (size_t)row_buffer_pitch(P->cp, max_patterns, flush_mode) : 0);
+  P->smem = (size_t)(2 * P->cp.slot_bytes()) + 8 /* the row buffers start 16-byte aligned */ + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
 
   P->stage_len = STAGE;
   P->kmap = kmap; P->rmap = rmap;
@@ -1494,8 +1563,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     for (int tr = 0; tr < 2; ++tr)
       P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
     const int pull_group = std::stoi(opt(P, "pull group", "8"));
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", opt(P, "flush", "row") == "row", std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal")
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", opt(P, "flush", "row") == "row", std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal");
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn)
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn);
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
@@ -1521,7 +1590,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   P->d_rowptr.upload(M.rowptr, tot); P->d_colind.upload(M.colind, tot); P->d_fixed.upload(M.fixed, tot); P->d_eclass.upload(M.eclass, tot);
   P->d_chain_step_ptr.upload(CP.chain_step_ptr, tot); P->d_steps.upload(CP.steps, tot); P->d_step_elems.upload(CP.step_elems, tot);
   P->d_batches.upload(CP.batches, tot); P->d_rows.upload(CP.rows, tot);
-  P->d_step_conn.upload(CP.step_conn, tot); P->d_step_lids.upload(CP.step_lids, tot); P->d_step_eclass.upload(CP.step_eclass, tot);
+  P->d_step_conn.upload(CP.step_conn, tot); P->d_step_eclass.upload(CP.step_eclass, tot);
+  if (!lids_are_conn) P->d_step_lids.upload(CP.step_lids, tot);   // else the kernels read the one connectivity stream for both
   P->d_desc0.upload(CP.desc[0], tot); P->d_desc1.upload(CP.desc[1], tot);
   if (P->metric_ng > 0) { P->d_mdesc0.upload(CP.mdesc[0], tot); P->d_mdesc1.upload(CP.mdesc[1], tot); }
   P->d_orphans.upload(CP.orphan_rows, tot);
@@ -1539,7 +1609,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   ChainDev D{};
   D.chain_step_ptr = P->d_chain_step_ptr.p; D.steps = P->d_steps.p; D.step_elems = P->d_step_elems.p;
   D.batches = P->d_batches.p; D.rows = P->d_rows.p;
-  D.step_conn = P->d_step_conn.p; D.step_lids = P->d_step_lids.p; D.step_eclass = P->d_step_eclass.p;
+  D.step_conn = P->d_step_conn.p; D.step_lids = lids_are_conn ? P->d_step_conn.p : P->d_step_lids.p; D.step_eclass = P->d_step_eclass.p;
   D.desc0 = reinterpret_cast<const SrcQuad*>(P->d_desc0.p); D.desc1 = reinterpret_cast<const SrcQuad*>(P->d_desc1.p);
   D.mdesc0 = reinterpret_cast<const SrcQuad*>(P->d_mdesc0.p); D.mdesc1 = reinterpret_cast<const SrcQuad*>(P->d_mdesc1.p);
   D.cap = CP.cap;
@@ -1686,6 +1756,7 @@ int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* P, int64_t n_cols, const int64_t
   for (int32_t c : P->mesh.colind) if (c < 0 || c >= n_cols) fail(MRHYDE_B200_ERR_INVALID, "set_halo: a column index of the graph is outside [0, n_cols)");
   CUDA_OK(cudaSetDevice(P->device));
   std::string err;
+  P->halo->set_transport(opt(P, "halo transport", "auto"));
   if (!P->halo->setup(P->mesh.nrows, P->mesh.nowned, n_cols, col_gids, P->mesh.rowptr.data(), P->mesh.colind.data(), err)) fail(MRHYDE_B200_ERR_NCCL, err);
   ABI_END
 }
@@ -1717,6 +1788,7 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "max_rows_per_step") *value = P->cp.max_rows_step;
   else if (k == "kernel_launches_per_assemble") *value = P->launches_per_assemble;
   else if (k == "halo_launches_per_sum") *value = P->halo ? P->halo->launches_per_sum() : 0;
+  else if (k == "halo_p2p") *value = (P->halo && P->halo->p2p()) ? 1 : 0;
   else if (k == "smem_bytes") *value = (int64_t)variant_smem(P, false);
   else if (k == "metric_ring") *value = P->metric_ng;
   else if (k == "overlapped_assembles") *value = P->overlapped_assembles;

@@ -6,6 +6,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 
@@ -74,6 +75,95 @@ __global__ void unpack_add2_kernel(const double* __restrict__ src, const int64_t
   else if (i < n_res + n_jac) { const int64_t p = pos_jac[i - n_res]; if (p >= 0) jac[p] += src[i]; }
 }
 
+// ---- p2p transport -------------------------------------------------------------------------------------------------
+// Region of rank r (one cudaMalloc, mapped by its neighbours): [arrive[nranks] | ack[nranks]] 64-bit flags, then for every source
+// rank two receive slabs (double-buffered by the parity of the call counter), each laid out [res | pad to even | jac].
+struct P2PPeerDev {
+  // what goes to this peer
+  const int64_t* send_res_pos; const int64_t* send_jac_pos;
+  int64_t n_send_res, n_send_jac, send_res_first, send_jac_first, send_jac_off;
+  double* remote_slab[2];
+  unsigned long long* remote_arrive;      // peer's arrive[me]
+  unsigned long long* local_ack;          // my ack[peer]: the peer is done reading what I stored in call `value`
+  // what comes from this peer
+  const int64_t* recv_res_pos; const int64_t* recv_jac_pos;
+  int64_t n_recv_res, n_recv_jac, recv_jac_off;
+  const double* local_slab[2];
+  unsigned long long* local_arrive;       // my arrive[peer]
+  unsigned long long* remote_ack;         // peer's ack[me]
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// One launch per halo sum, at most one CTA per SM (all CTAs are resident, so the flag waits cannot starve a CTA that has not started).
+//   phase 1  every CTA stores its share of the ghost rows into the owners' slabs; the last CTA to finish a peer raises arrive[me] there
+//   phase 2  source rank by source rank (ascending: fixed summation order): wait for arrive[source], add the slab, last CTA acknowledges
+// counters[0 .. n): CTAs that finished the push to peer i; counters[n .. 2n): CTAs that finished the add from peer i (both reset by
+// their last CTA); counters[2n]: running ticket of the grid barrier between two sources.
+__global__ void __launch_bounds__(256) halo_p2p_kernel(const P2PPeerDev* __restrict__ peers, int n, unsigned long long epoch, double* __restrict__ res,
+                                                        double* __restrict__ jac, unsigned* counters) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int par = (int)(epoch & 1ull);
+  for (int i = 0; i < n; ++i) {
+    const P2PPeerDev& P = peers[i];
+    const int64_t nr = res ? P.n_send_res : 0, nj = jac ? P.n_send_jac : 0;
+    if (nr + nj == 0) continue;
+    if (threadIdx.x == 0) while (ld_acquire_sys(P.local_ack) + 2ull < epoch) {}   // the slab of this parity was read two calls ago
+    __syncthreads();
+    double* slab = P.remote_slab[par];
+    if (P.send_res_first >= 0) for (int64_t k = tid; k < nr; k += nth) slab[k] = res[P.send_res_first + k];
+    else for (int64_t k = tid; k < nr; k += nth) slab[k] = res[P.send_res_pos[k]];
+    double* sj = slab + P.send_jac_off;
+    if (P.send_jac_first >= 0) for (int64_t k = tid; k < nj; k += nth) sj[k] = jac[P.send_jac_first + k];
+    else for (int64_t k = tid; k < nj; k += nth) sj[k] = jac[P.send_jac_pos[k]];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(&counters[i], 1u) == gridDim.x - 1) {
+        counters[i] = 0u;
+        __threadfence_system();
+        st_release_sys(P.remote_arrive, epoch);
+      }
+    }
+  }
+  bool first = true;
+  for (int i = 0; i < n; ++i) {
+    const P2PPeerDev& P = peers[i];
+    const int64_t nr = res ? P.n_recv_res : 0, nj = jac ? P.n_recv_jac : 0;
+    if (nr + nj == 0) continue;
+    if (threadIdx.x == 0) {
+      if (!first) {   // rows shared with several ranks: the previous source must be added everywhere before this one starts
+        const unsigned ticket = atomicAdd(&counters[2 * n], 1u);
+        const unsigned target = (ticket / gridDim.x + 1u) * gridDim.x;
+        while (*(volatile unsigned*)&counters[2 * n] < target) {}
+        __threadfence();
+      }
+      while (ld_acquire_sys(P.local_arrive) < epoch) {}
+    }
+    first = false;
+    __syncthreads();
+    const double* slab = P.local_slab[par];
+    for (int64_t k = tid; k < nr; k += nth) { const int64_t q = P.recv_res_pos[k]; if (q >= 0) res[q] += __ldcg(slab + k); }
+    const double* sj = slab + P.recv_jac_off;
+    for (int64_t k = tid; k < nj; k += nth) { const int64_t q = P.recv_jac_pos[k]; if (q >= 0) jac[q] += __ldcg(sj + k); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(&counters[n + i], 1u) == gridDim.x - 1) {
+        counters[n + i] = 0u;
+        st_release_sys(P.remote_ack, epoch);
+      }
+    }
+  }
+}
+
 template <class T>
 bool to_device(T** d, const std::vector<T>& h, std::string& err) {
   CU_TRY(cudaMalloc((void**)d, std::max<size_t>(h.size(), 1) * sizeof(T)));
@@ -98,6 +188,8 @@ HaloExchange::~HaloExchange() {
     cudaFree(p.d_send_res); cudaFree(p.d_send_jac); cudaFree(p.d_recv_res); cudaFree(p.d_recv_jac);
     cudaFree(p.d_sendbuf); cudaFree(p.d_recvbuf);
   }
+  for (size_t p = 0; p < p2p_remote_.size(); ++p) if (p2p_remote_[p]) cudaIpcCloseMemHandle(p2p_remote_[p]);
+  cudaFree(p2p_region_); cudaFree(p2p_peers_dev_); cudaFree(p2p_counters_);
   if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); cudaEventDestroy(ev_ready_); cudaEventDestroy(ev_done_); }
   if (comm_ && api().ok) api().CommDestroy((ncclComm_t)comm_);
 }
@@ -225,7 +317,136 @@ bool HaloExchange::setup(int64_t n_rows, int64_t n_owned, int64_t n_cols, const 
     CU_TRY(cudaMalloc(&P.d_sendbuf, std::max<int64_t>(1, P.n_send_res + P.n_send_jac) * sizeof(double)));
     CU_TRY(cudaMalloc(&P.d_recvbuf, std::max<int64_t>(1, P.n_recv_res + P.n_recv_jac) * sizeof(double)));
   }
+  if (!setup_p2p(err)) return false;
   ready_ = true;
+  return true;
+}
+
+// Collective.  Every rank allocates its region, publishes the IPC handle and the slab sizes it expects, maps the regions of the
+// ranks it sends to, and the ranks agree (all-gather of a success word) whether the p2p transport is used.
+bool HaloExchange::setup_p2p(std::string& err) {
+  NcclApi& A = api();
+  ncclComm_t comm = (ncclComm_t)comm_;
+  p2p_ = false;
+  const char* env = getenv("MRHYDE_B200_HALO_TRANSPORT");
+  const std::string want = env && *env ? std::string(env) : transport_;
+  if (want != "auto" && want != "p2p" && want != "nccl") { err = "halo transport must be auto|p2p|nccl"; return false; }
+  // layout of my region
+  const size_t flag_bytes = (size_t)nranks_ * 2 * sizeof(unsigned long long);
+  std::vector<int64_t> slab_off((size_t)nranks_, -1), slab_len((size_t)nranks_, 0);
+  size_t total = (flag_bytes + 255) & ~(size_t)255;
+  for (int p = 0; p < nranks_; ++p) {
+    if (p == rank_) continue;
+    const Peer& P = peers_[(size_t)p];
+    if (P.n_recv_res + P.n_recv_jac == 0) continue;
+    slab_len[(size_t)p] = ((P.n_recv_res + 1) & ~(int64_t)1) + P.n_recv_jac;
+    slab_off[(size_t)p] = (int64_t)total;
+    total += (((size_t)slab_len[(size_t)p] * sizeof(double) + 255) & ~(size_t)255) * 2;
+  }
+  int ok = want == "nccl" ? 0 : 1;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    if (cudaMalloc(&p2p_region_, total) != cudaSuccess || cudaMemset(p2p_region_, 0, total) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, p2p_region_) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  // publish: [ok, handle (64 bytes = 8 words), slab_off[nranks]]
+  const size_t words = 1 + 8 + (size_t)nranks_;
+  std::vector<int64_t> pub(words, 0), all(words * (size_t)nranks_, 0);
+  pub[0] = ok;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(&pub[1], &mine, 64);
+  for (int p = 0; p < nranks_; ++p) pub[9 + (size_t)p] = slab_off[(size_t)p];
+  auto gather = [&](std::vector<int64_t>& in, std::vector<int64_t>& out) -> bool {
+    int64_t *d_in = nullptr, *d_out = nullptr;
+    CU_TRY(cudaMalloc(&d_in, in.size() * sizeof(int64_t)));
+    CU_TRY(cudaMalloc(&d_out, out.size() * sizeof(int64_t)));
+    CU_TRY(cudaMemcpy(d_in, in.data(), in.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    NCCL_TRY(A.AllGather(d_in, d_out, in.size(), ncclInt64, comm, 0));
+    CU_TRY(cudaStreamSynchronize(0));
+    CU_TRY(cudaMemcpy(out.data(), d_out, out.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    cudaFree(d_in); cudaFree(d_out);
+    return true;
+  };
+  if (!gather(pub, all)) return false;
+  for (int p = 0; p < nranks_; ++p) if (!all[words * (size_t)p]) ok = 0;
+  // map the regions of the ranks I exchange with
+  p2p_remote_.assign((size_t)nranks_, nullptr);
+  if (ok) {
+    for (int p = 0; p < nranks_ && ok; ++p) {
+      if (p == rank_) continue;
+      const Peer& P = peers_[(size_t)p];
+      if (P.n_send_res + P.n_send_jac + P.n_recv_res + P.n_recv_jac == 0) continue;
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, &all[words * (size_t)p + 1], 64);
+      if (cudaIpcOpenMemHandle(&p2p_remote_[(size_t)p], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; p2p_remote_[(size_t)p] = nullptr; cudaGetLastError(); }
+    }
+  }
+  std::vector<int64_t> okv(1, ok), okall((size_t)nranks_, 0);
+  if (!gather(okv, okall)) return false;
+  for (int p = 0; p < nranks_; ++p) if (!okall[(size_t)p]) ok = 0;
+  if (!ok) {
+    if (want == "p2p") { err = "halo transport p2p: a rank could not allocate, export or map a receive region (CUDA IPC / peer access)"; return false; }
+    for (auto& r : p2p_remote_) if (r) { cudaIpcCloseMemHandle(r); r = nullptr; }
+    cudaFree(p2p_region_); p2p_region_ = nullptr;
+    return true;   // the nccl transport stays in place
+  }
+  // device-side peer table
+  std::vector<P2PPeerDev> tab;
+  for (int p = 0; p < nranks_; ++p) {   // ascending rank: the order the received values are added in
+    if (p == rank_) continue;
+    const Peer& P = peers_[(size_t)p];
+    if (P.n_send_res + P.n_send_jac + P.n_recv_res + P.n_recv_jac == 0) continue;
+    P2PPeerDev D;
+    std::memset(&D, 0, sizeof(D));
+    char* remote = (char*)p2p_remote_[(size_t)p];
+    char* local = (char*)p2p_region_;
+    D.send_res_pos = P.d_send_res; D.send_jac_pos = P.d_send_jac;
+    D.n_send_res = P.n_send_res; D.n_send_jac = P.n_send_jac; D.send_res_first = P.send_res_first; D.send_jac_first = P.send_jac_first;
+    D.send_jac_off = (P.n_send_res + 1) & ~(int64_t)1;
+    const int64_t roff = all[words * (size_t)p + 9 + (size_t)rank_];   // where the peer keeps the slabs for what I send
+    if (P.n_send_res + P.n_send_jac > 0) {
+      if (roff < 0) { err = "halo p2p: the owner expects nothing from a rank that has ghost rows for it (inconsistent maps)"; return false; }
+      const size_t len = (((size_t)(D.send_jac_off + P.n_send_jac) * sizeof(double) + 255) & ~(size_t)255);
+      D.remote_slab[0] = (double*)(remote + roff); D.remote_slab[1] = (double*)(remote + roff + len);
+    }
+    D.remote_arrive = (unsigned long long*)remote + rank_;
+    D.local_ack = (unsigned long long*)local + nranks_ + p;
+    D.recv_res_pos = P.d_recv_res; D.recv_jac_pos = P.d_recv_jac;
+    D.n_recv_res = P.n_recv_res; D.n_recv_jac = P.n_recv_jac;
+    D.recv_jac_off = (P.n_recv_res + 1) & ~(int64_t)1;
+    if (slab_off[(size_t)p] >= 0) {
+      const size_t len = (((size_t)slab_len[(size_t)p] * sizeof(double) + 255) & ~(size_t)255);
+      D.local_slab[0] = (const double*)(local + slab_off[(size_t)p]); D.local_slab[1] = (const double*)(local + slab_off[(size_t)p] + len);
+    }
+    D.local_arrive = (unsigned long long*)local + p;
+    D.remote_ack = (unsigned long long*)remote + nranks_ + rank_;
+    tab.push_back(D);
+  }
+  p2p_active_ = (int)tab.size();
+  CU_TRY(cudaMalloc(&p2p_peers_dev_, std::max<size_t>(1, tab.size()) * sizeof(P2PPeerDev)));
+  if (!tab.empty()) CU_TRY(cudaMemcpy(p2p_peers_dev_, tab.data(), tab.size() * sizeof(P2PPeerDev), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMalloc((void**)&p2p_counters_, (2 * tab.size() + 1) * sizeof(unsigned)));
+  CU_TRY(cudaMemset(p2p_counters_, 0, (2 * tab.size() + 1) * sizeof(unsigned)));
+  int dev = 0, n_sm = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  CU_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  int64_t most = 0;
+  for (const P2PPeerDev& D : tab) most = std::max<int64_t>(most, std::max(D.n_send_res + D.n_send_jac, D.n_recv_res + D.n_recv_jac));
+  p2p_grid_ = (int)std::max<int64_t>(1, std::min<int64_t>(n_sm, (most + 1023) / 1024));   // <= one CTA per SM: all resident
+  p2p_epoch_ = 0;
+  CU_TRY(cudaDeviceSynchronize());
+  p2p_ = true;
+  return true;
+}
+
+bool HaloExchange::sum_p2p(double* res, double* jac, cudaStream_t st, std::string& err) {
+  ++p2p_epoch_;
+  launches_ = 0;
+  if (p2p_active_ == 0) return true;
+  halo_p2p_kernel<<<p2p_grid_, 256, 0, st>>>((const P2PPeerDev*)p2p_peers_dev_, p2p_active_, p2p_epoch_, res, jac, p2p_counters_);
+  launches_ = 1;
+  CU_TRY(cudaGetLastError());
   return true;
 }
 
@@ -269,6 +490,7 @@ bool HaloExchange::start(double* res, double* jac, cudaStream_t st, std::string&
 }
 
 bool HaloExchange::sum(double* res, double* jac, cudaStream_t st, std::string& err) {
+  if (p2p_ && !started_) return sum_p2p(res, jac, st, err);
   NcclApi& A = api();
   ncclComm_t comm = (ncclComm_t)comm_;
   auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };

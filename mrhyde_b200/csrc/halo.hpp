@@ -7,6 +7,12 @@
 // over NVLink, and added into the owner's row at positions matched through global column ids at
 // set-up.  Contributions are added source rank by source rank in ascending order, so the result is
 // reproducible.  NCCL is resolved with dlopen at run time (the library loads without it).
+//
+// Two transports (option "halo transport" = auto | p2p | nccl, or MRHYDE_B200_HALO_TRANSPORT):
+//   p2p   one kernel per halo sum and no NCCL on the data path: every rank maps its neighbours' receive slabs (CUDA IPC over
+//         NVLink), stores its ghost rows straight into the owner's slab, raises a flag there and then adds what its own neighbours
+//         stored (halo_p2p_kernel).  Used when every rank of the communicator could map its peers (one node).
+//   nccl  grouped ncclSend/ncclRecv + an add kernel per source (the round-1 path; also the fallback across nodes).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,6 +31,8 @@ class HaloExchange {
   bool init(const uint8_t* id128, int rank, int nranks, std::string& err);
   // collective: builds send/receive maps from the global row ids of every rank
   bool setup(int64_t n_rows, int64_t n_owned, int64_t n_cols, const int64_t* col_gids, const int64_t* rowptr, const int32_t* colind, std::string& err);
+  void set_transport(const std::string& t) { transport_ = t; }   // before setup(): auto | p2p | nccl
+  bool p2p() const { return p2p_; }
   bool sum(double* res, double* jac, cudaStream_t st, std::string& err);
   // Overlapped form of sum(): start() is called once the ghost rows of res / jac are final on `st` (the caller may keep
   // launching work that does not touch them); the send/recv run on an internal stream.  sum() called afterwards with the same
@@ -55,6 +63,17 @@ class HaloExchange {
     double* d_sendbuf = nullptr; double* d_recvbuf = nullptr;
   };
   std::vector<Peer> peers_;
+  // ---- p2p transport
+  bool setup_p2p(std::string& err);
+  bool sum_p2p(double* res, double* jac, cudaStream_t st, std::string& err);
+  std::string transport_ = "auto";
+  bool p2p_ = false;
+  void* p2p_region_ = nullptr;            // my flags + receive slabs (cudaMalloc, exported with cudaIpcGetMemHandle)
+  std::vector<void*> p2p_remote_;         // peers' regions mapped here (cudaIpcOpenMemHandle), nullptr where unused
+  void* p2p_peers_dev_ = nullptr;         // P2PPeerDev[n_active]
+  unsigned* p2p_counters_ = nullptr;      // CTA arrival counters of the kernel
+  int p2p_active_ = 0, p2p_grid_ = 0;
+  unsigned long long p2p_epoch_ = 0;
 };
 
 }  // namespace mrhyde_b200

@@ -393,6 +393,15 @@ template <int DIM>
 __device__ __forceinline__ void elem_stage1(const ThermalParams<DIM>& P, const int k, ElemPre<DIM>& E) {
   constexpr int NV = 1 << DIM;
   const int4* c4 = reinterpret_cast<const int4*>(P.chains.step_conn + (size_t)k * NV);
+#ifdef MRH_JIT_LIDS_ARE_CONN
+  // dof ids equal vertex ids on every element of the plan (one scalar HGRAD-C1 field numbered like the nodes): one stream
+#pragma unroll
+  for (int k = 0; k < NV / 4; ++k) {
+    const int4 a = __ldg(c4 + k);
+    E.cn[4 * k] = a.x; E.cn[4 * k + 1] = a.y; E.cn[4 * k + 2] = a.z; E.cn[4 * k + 3] = a.w;
+    E.ld[4 * k] = a.x; E.ld[4 * k + 1] = a.y; E.ld[4 * k + 2] = a.z; E.ld[4 * k + 3] = a.w;
+  }
+#else
   const int4* l4 = reinterpret_cast<const int4*>(P.chains.step_lids + (size_t)k * NV);
 #pragma unroll
   for (int k = 0; k < NV / 4; ++k) {
@@ -400,7 +409,12 @@ __device__ __forceinline__ void elem_stage1(const ThermalParams<DIM>& P, const i
     E.cn[4 * k] = a.x; E.cn[4 * k + 1] = a.y; E.cn[4 * k + 2] = a.z; E.cn[4 * k + 3] = a.w;
     E.ld[4 * k] = b.x; E.ld[4 * k + 1] = b.y; E.ld[4 * k + 2] = b.z; E.ld[4 * k + 3] = b.w;
   }
+#endif
+#ifdef MRH_JIT_ONLY_ECLASS
+  E.ecls = MRH_JIT_ONLY_ECLASS;
+#else
   E.ecls = P.chains.step_eclass[k];
+#endif
 }
 
 template <int DIM>
@@ -870,6 +884,10 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
     if (mrh_pull_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, n_rows, R.base, O.jac, pres2, active)) return;
 #endif
   }
+#if MRH_JIT_FLUSH == 2
+  mrh_bulk_wait_read();   // the generic path below reuses the row buffer a bulk copy of this warp may still be reading
+  __syncwarp();
+#endif
 #endif
   // store side of the transpose: this lane writes entry (k0 + kk_st) of rows rsub + 8 j
   const int rsub = lane >> 2, kk_st = lane & 3;
@@ -950,7 +968,7 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   constexpr int MDIM = 0;
   const int cap = C.cap;
   const int slot_doubles = cap * (MRH_STAGE_K(S::NT) + S::NV);
-  double* wbuf = ring + 2 * slot_doubles + warp * PULL_WARP_DOUBLES;
+  double* wbuf = ring + ((2 * slot_doubles + 1) & ~1) + warp * PULL_WARP_DOUBLES;   // 16-byte aligned (bulk copies read it)
 #endif
   const double au = P.td.alpha_u, at = P.td.alpha_t;
 #ifdef MRH_JIT_MODE
@@ -1042,6 +1060,9 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     sr = sr_next; sr_next = sr_next2;
     __syncthreads();  // the next step overwrites the slot this pull read as "previous"
   }
+#if defined(MRH_JIT_ROWBUF) && MRH_JIT_FLUSH == 2
+  mrh_bulk_wait_read();   // shared memory must outlive the bulk copies that read it
+#endif
 }
 
 #ifndef MRH_THREADS

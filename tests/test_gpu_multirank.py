@@ -1,6 +1,8 @@
-"""Two-GPU check of the NCCL halo sum (the Tpetra Export(overlapped -> owned, ADD) replacement): two ranks assemble
-their z-slabs on their own GPUs, exchange ghost rows, and the owned rows must equal the single-GPU assembly of the whole
-mesh to 1e-12.  Skipped on boxes with one GPU (the driver's gpu tier); run with `gpurun --gpus 2`."""
+"""Two-GPU check of the halo sum (the Tpetra Export(overlapped -> owned, ADD) replacement, linearAlgebraInterface_matrix.hpp:233-237):
+two ranks assemble their z-slabs on their own GPUs, exchange ghost rows -- through the p2p transport (peer stores over NVLink, the
+default on one node) and through the NCCL transport -- and the owned rows must equal BOTH the single-GPU assembly of the whole mesh
+and the CPU oracle's assembly of the whole mesh to 1e-12.  Skipped on boxes with one GPU (the driver's gpu tier); run with
+`gpurun --gpus 2` (log of the last run: profiles/r02_multirank_2gpu.log)."""
 import os
 import sys
 
@@ -18,6 +20,8 @@ def _make(kind, n, rank, world):
         options = {"column elements": 16, "min segment levels": 2}
         if kind == "thermal_overlap" and world > 1:   # ghost-row chains first, exchange beside the rest of the assembly
             options["overlap halo"] = "true"
+        if kind == "thermal_nccl":
+            options["halo transport"] = "nccl"
         return ThermalBrick(3, n, device=rank, rank=rank, nranks=world, options=options)
     return SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[kind], 3, n, device=rank, rank=rank, nranks=world, options={"batch elems": 300})
 
@@ -52,22 +56,38 @@ def _worker_body(rank, world, q, kind, dev):
     u = torch.from_numpy(prob.state()).to(dev)
     res = torch.zeros(prob.n_rows, dtype=torch.float64, device=dev)
     jac = torch.zeros(prob.nnz, dtype=torch.float64, device=dev)
-    for _ in range(2 if kind == "thermal_overlap" else 1):   # twice: the second exchange reuses the side stream and events
+    assert prob.plan.stat("halo_p2p") == (0 if kind == "thermal_nccl" else 1)
+    for _ in range(4 if kind in ("thermal_overlap", "thermal") else 1):   # repeated: side stream / events, both slab parities of the p2p transport
         res.zero_()
         jac.zero_()
         prob.plan.assemble_jacres(u, res, jac)
         prob.plan.halo_sum(res, jac)
     torch.cuda.synchronize()
     if kind == "thermal_overlap" and prob.n_owned < prob.n_rows:   # only ranks that hold ghost rows start an exchange early
-        assert prob.plan.stat("overlapped_assembles") == 2 and 0 < prob.plan.stat("n_early_chains") < prob.plan.stat("n_chains")
+        assert prob.plan.stat("overlapped_assembles") == 4 and 0 < prob.plan.stat("n_early_chains") < prob.plan.stat("n_chains")
     no = prob.n_owned
     q.put((rank, prob.col_gids.copy(), res[:no].cpu().numpy(), prob.rowptr[: no + 1].copy(), prob.colind[: prob.rowptr[no]].copy(),
            jac[: prob.rowptr[no]].cpu().numpy(), prob.state()[:no].copy()))
     dist.barrier()
 
 
-@pytest.mark.parametrize("kind", ["thermal", "thermal_overlap", "le", "ns"])
-def test_two_gpu_halo_sum_equals_single_gpu(product_lib, kind):
+def _oracle_global(oracle_lib, kind, n, ug):
+    """The CPU oracle on the whole mesh with the same state (the builders number dofs like the oracle: tests/test_builders.py)."""
+    import configs
+    mesh = {"Mesh/NX": n[0], "Mesh/NY": n[1], "Mesh/NZ": n[2], "Mesh/perturb": 0.0}
+    if kind.startswith("thermal"):
+        cfg = configs.variant(configs.THERMAL_3D, **mesh)
+    elif kind == "le":
+        cfg = configs.variant(configs.LE_3D, **dict(mesh, Functions={"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)",
+                                                                       "source dy": "sin(2*pi*x)*sin(2*pi*y)", "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"}))
+    else:
+        cfg = configs.variant(configs.NS_3D, **dict(mesh, Functions={"source ux": "1.0", "viscosity": "1.0", "density": "1.0"}))
+    op = oracle_lib.OracleProblem(cfg)
+    return op.assemble_jacres(ug)
+
+
+@pytest.mark.parametrize("kind", ["thermal", "thermal_nccl", "thermal_overlap", "le", "ns"])
+def test_two_gpu_halo_sum_equals_single_gpu(oracle_lib, product_lib, kind):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -76,7 +96,7 @@ def test_two_gpu_halo_sum_equals_single_gpu(product_lib, kind):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "thermal_overlap": 7, "le": 3, "ns": 5}[kind]
+    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "thermal_overlap": 7, "le": 3, "ns": 5, "thermal_nccl": 9}[kind]
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
@@ -105,6 +125,9 @@ def test_two_gpu_halo_sum_equals_single_gpu(product_lib, kind):
     torch.cuda.synchronize()
     res_g, jac_g = d_res.cpu().numpy(), d_jac.cpu().numpy()
     scale_r, scale_j = np.abs(res_g).max(), np.abs(jac_g).max()
+    # oracle leg: the single-GPU assembly of the whole mesh is itself the oracle's (same rows, same graph)
+    res_o, jac_o = _oracle_global(oracle_lib, kind, (N[0], N[1], world * N[2]), ug)
+    assert np.max(np.abs(res_g - res_o)) <= 1e-12 * scale_r and np.max(np.abs(jac_g - jac_o)) <= 1e-12 * scale_j
     for rank, gids, res, rp, ci, jac, st in outs:
         own = gids[: len(st)]
         assert np.max(np.abs(res - res_g[own])) <= 1e-12 * scale_r
