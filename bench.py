@@ -29,12 +29,48 @@ METRIC = "fp64 residual+Jacobian elements/sec"
 UNIT = "elements/s"
 
 
-WORKLOADS = {"thermal": "thermal hex-Q1", "le": "linear elasticity hex-Q1 (3 dofs/node)", "leq2": "linear elasticity hex-Q2 (81 dofs/element, 27 Gauss points)", "ns": "Navier-Stokes hex-Q1 ux/pr/uy/uz, SUPG+PSPG, reference uz rows"}
+WORKLOADS = {"thermal": "thermal hex-Q1", "le": "linear elasticity hex-Q1 (3 dofs/node)", "leq2": "linear elasticity hex-Q2 (81 dofs/element, 27 Gauss points)", "ns": "Navier-Stokes hex-Q1 ux/pr/uy/uz, SUPG+PSPG, reference uz rows",
+             "maxwell": "Maxwell hex HCURL E (12 edge dofs) + HDIV B (6 face dofs), one DIRK-1,2 stage"}
 _WORKLOAD = "thermal"
 
 
-def workload_name(n, world):
-    return "%s %dx%dx%d inline brick, steady, residual+Jacobian%s" % (WORKLOADS[_WORKLOAD], n, n, n * world, "" if world == 1 else " (%d z-slabs of %d^3)" % (world, n))
+def workload_name(n, world, nz=None):
+    nz = n if nz is None else nz
+    return "%s %dx%dx%d inline brick, %s, residual+Jacobian%s" % (WORKLOADS[_WORKLOAD], n, n, nz * world, "transient stage" if _WORKLOAD == "maxwell" else "steady", "" if world == 1 else " (%d z-slabs of %dx%dx%d)" % (world, n, n, nz))
+
+
+def measure_traffic(args, kernel_regex, n_kernels):
+    """DRAM bytes (read + write) of one launch of the dominant kernel(s), measured by an ncu pass over a child run of this same
+    command (1 GPU, one timed step): dram__bytes_read.sum + dram__bytes_write.sum.  Returns None when ncu is unavailable."""
+    import csv
+    import io
+    import shutil
+    if shutil.which("ncu") is None:
+        return None
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:" + kernel_regex, "-s", str(3 * n_kernels),
+           "-c", str(n_kernels), "--csv", sys.executable, os.path.abspath(__file__), "--traffic-child", "--workload", _WORKLOAD, "--n", str(args.n), "--steps", "1", "--warmup", "3"]
+    for kv in args.opt:
+        cmd += ["--opt", kv]
+    for kv in args.fn:
+        cmd += ["--fn", kv]
+    if args.perturb:
+        cmd += ["--perturb", str(args.perturb)]
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env).stdout
+        rows = [r for r in csv.reader(io.StringIO(out)) if len(r) > 5]
+        hdr = next(r for r in rows if "Metric Name" in r)
+        im, iv, iu = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for r in rows:
+            if r is not hdr and r[im] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
+        return total if total > 0 else None
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -106,6 +142,10 @@ def _oracle_cfg(n, nz):
                 "Discretization": {"order": {"dx": 1, "dy": 1, "dz": 1}, "quadrature": 2},
                 "Functions": {"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)", "source dy": "sin(2*pi*x)*sin(2*pi*y)", "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"},
                 "Solver": {"solver": "steady-state", "workset size": 100}}
+    if _WORKLOAD == "maxwell":
+        return {"Mesh": mesh, "Physics": {"modules": "maxwell", "Dirichlet conditions": {}},
+                "Discretization": {"order": {"E": 1, "B": 1}, "quadrature": 2},
+                "Functions": {"current x": "sin(2*pi*z)"}, "Solver": {"solver": "transient", "workset size": 100}}
     if _WORKLOAD == "ns":
         return {"Mesh": mesh, "Physics": {"modules": "navier stokes", "useSUPG": True, "usePSPG": True,
                                           "Dirichlet conditions": {v: {"all boundaries": "0.0"} for v in ("ux", "uy", "uz")}},
@@ -130,6 +170,10 @@ def _worker_init(n, nz):
     _W["u"] = rng.uniform(-1.0, 1.0, op.num_dofs)
     _W["res"] = np.zeros(op.num_dofs)
     _W["jac"] = np.zeros(op.nnz)
+    _W["kw"] = {}
+    if _WORKLOAD == "maxwell":   # the same DIRK-1,2 stage the GPU arm assembles
+        op.set_time(True, time=0.3, dt=0.01, stage=0, A=[[0.5]], b=[1.0], c=[0.5], bdf=(1.0, -1.0))
+        _W["kw"] = dict(sol_prev=[rng.uniform(-1.0, 1.0, op.num_dofs)], sol_stage=[_W["u"]])
 
 
 def _worker_step(_):
@@ -137,7 +181,7 @@ def _worker_step(_):
     _W["res"][:] = 0.0
     _W["jac"][:] = 0.0
     t0 = time.perf_counter()
-    op.assemble_jacres(_W["u"], res=_W["res"], jac=_W["jac"])
+    op.assemble_jacres(_W["u"], res=_W["res"], jac=_W["jac"], **_W["kw"])
     return time.perf_counter() - t0, op.num_elems
 
 
@@ -194,10 +238,11 @@ def run_reference(args):
         for p in pools:
             p.terminate()
     value = elems / t_total
-    sample = "%d processes x (%dx%dx%d z-slab of the workload) per step" % (cores, n, n, nz)
+    full = float(args.n) ** 3
+    sample = "%d processes x (%dx%dx%d z-slab of the workload) per step = %.4f of the workload's %d elements per step" % (cores, n, n, nz, cores * n * n * nz / full, int(full))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": workload_name(n, 1), "sample": sample},
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(n, 1), "sample": sample, "sampled_fraction_per_step": cores * n * n * nz / full},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
@@ -220,7 +265,7 @@ def ring_name(plan, general):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mrhyde_b200.problems import ElasticityQ2Brick, SystemBrick, ThermalBrick
+    from mrhyde_b200.problems import ElasticityQ2Brick, MaxwellBrick, SystemBrick, ThermalBrick
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,20 +280,26 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
+    nz = n
+    if args.scaling == "strong" and world > 1:
+        if n % world:
+            raise RuntimeError("--scaling strong needs n divisible by the number of GPUs")
+        nz = n // world
     options = {"accumulate": "false"}
     if world > 1 and _WORKLOAD == "thermal" and os.environ.get("MRHYDE_B200_OVERLAP_HALO", "0") == "1":
         options["overlap halo"] = "true"   # opt-in until the overlapped exchange has been measured
     for kv in args.opt:
         k, v = kv.split("=", 1)
         options[k] = v
+    functions = dict(kv.split("=", 1) for kv in args.fn)
     if _WORKLOAD == "leq2":
-        if world > 1:
-            raise RuntimeError("the hex-Q2 workload is single-GPU in this round (no slab partition of the Q2 lattice yet)")
-        prob = ElasticityQ2Brick(n, device=local, options=options)
+        prob = ElasticityQ2Brick(n, device=local, options=options, rank=rank, nranks=world, nz=nz)
+    elif _WORKLOAD == "maxwell":
+        prob = MaxwellBrick(n, device=local, options=options, functions=functions or None, rank=rank, nranks=world, nz=nz)
     elif _WORKLOAD == "thermal":
-        prob = ThermalBrick(3, [n, n, n], device=local, rank=rank, nranks=world, options=options)
+        prob = ThermalBrick(3, [n, n, nz], device=local, rank=rank, nranks=world, options=options, functions=functions or None, perturb=args.perturb)
     else:
-        prob = SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[_WORKLOAD], 3, [n, n, n], device=local, rank=rank, nranks=world, options=options)
+        prob = SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[_WORKLOAD], 3, [n, n, nz], device=local, rank=rank, nranks=world, options=options)
     plan = prob.plan
     general = plan.stat("general") == 1
     if world > 1:
@@ -261,8 +312,14 @@ def run_ours(args):
     d_jac = torch.empty(prob.nnz, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
+    time_spec = None
+    if _WORKLOAD == "maxwell":   # one DIRK-1,2 stage (regression/maxwell/PlaneWave's integrator) from a previous-step state
+        from mrhyde_b200.capi import TimeSpec
+        d_up = (0.5 * d_u).contiguous()
+        time_spec = TimeSpec(time=0.3, deltat=0.01, stage=0, A=[[0.5]], b=[1.0], c=[0.5], bdf=(1.0, -1.0), sol_prev=[d_up], sol_stage=[d_u])
+
     def step():
-        plan.assemble_jacres(d_u, d_res, d_jac, stream=stream)
+        plan.assemble_jacres(d_u, d_res, d_jac, stream=stream, time=time_spec)
         if world > 1:
             plan.halo_sum(d_res, d_jac, stream=stream)
 
@@ -271,25 +328,31 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.traffic_child:   # profiled by the parent's ncu pass: warm-up launches, one more, done
+        for _ in range(max(3, args.warmup) + args.steps):
+            step()
+        torch.cuda.synchronize()
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
     plan.kernel_time(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
         step()
-    e1.record()
+        evs[i + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = evs[0].elapsed_time(evs[-1])
+    ms_median = float(np.median([evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]))   # median of the repetitions
     barrier()
     kern_ms, kern_n = plan.kernel_time(reset=True)
     launches_per_step = plan.stat("kernel_launches_per_assemble") + (plan.stat("halo_launches_per_sum") if world > 1 else 0)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_median], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, ms_median = float(t[0].item()), float(t[1].item())
     total_elems = prob.n_elem * world
     value = total_elems * args.steps / (ms * 1e-3)
 
@@ -298,11 +361,17 @@ def run_ours(args):
     h_res = torch.empty(prob.n_rows, dtype=torch.float64).pin_memory()
     h_jac = torch.empty(prob.nnz, dtype=torch.float64).pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
-    plan.assemble_jacres_host(h_u.numpy(), h_res.numpy(), h_jac.numpy())
+    h_time, h2d_vectors = None, 1
+    if _WORKLOAD == "maxwell":
+        from mrhyde_b200.capi import TimeSpec
+        h_up = (0.5 * h_u).pin_memory()
+        h_time = TimeSpec(time=0.3, deltat=0.01, stage=0, A=[[0.5]], b=[1.0], c=[0.5], bdf=(1.0, -1.0), sol_prev=[h_up.numpy()], sol_stage=[h_u.numpy()])
+        h2d_vectors = 2   # the stage state and the previous step's state go to the device every step
+    plan.assemble_jacres_host(h_u.numpy(), h_res.numpy(), h_jac.numpy(), time=h_time)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        plan.assemble_jacres_host(h_u.numpy(), h_res.numpy(), h_jac.numpy())
+        plan.assemble_jacres_host(h_u.numpy(), h_res.numpy(), h_jac.numpy(), time=h_time)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -331,25 +400,23 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = prob.algorithmic_bytes()
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        # DRAM traffic of the dominant kernel(s), measured now by an ncu pass over a child run of this command (not read from a file)
         traffic = None
-        try:
-            if general:
-                raise KeyError("no ncu traffic figure recorded for the general path")
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "thermal_q1_volume_traffic.json"))).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        if world == 1 and not args.no_traffic:
+            traffic = measure_traffic(args, "gen_element_kernel|gen_pull_kernel" if general else "mrh_thermal_q1", 2 if general else 1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(n, world), "elements_per_gpu": prob.n_elem, "rows_per_gpu": prob.n_rows, "nnz_per_gpu": prob.nnz,
+                "ms_per_step": ms / args.steps, "ms_per_step_median": ms_median, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(n, world, nz), "elements_per_gpu": prob.n_elem, "rows_per_gpu": prob.n_rows, "nnz_per_gpu": prob.nnz,
                            "l2": "inputs+outputs %.2f GB per GPU exceed the 126 MB L2 (no flush needed)" % (alg_bytes / 1e9),
                            "output_mode": "overwrite (accumulate=false)", "chains": plan.stat("n_chains"), "columns": plan.stat("n_columns"),
                            "segments": plan.stat("n_segments"), "ring_capacity": plan.stat("ring_capacity"), "threads_per_block": plan.stat("threads_per_block"),
                            "smem_bytes": plan.stat("smem_bytes"), "row_patterns": plan.stat("n_patterns"), "ring": ring_name(plan, general), "kernel_build": "nvrtc plan-specialised" if plan.stat("jit") else "ahead-of-time",
-                           "elements_incl_halo": plan.stat("n_elem_with_halo"), "plan_options": {k: v for k, v in options.items() if k != "accumulate"}, "parallelism": "z-slabs x%d + NCCL halo sum" % world if world > 1 else "1 GPU"},
+                           "elements_incl_halo": plan.stat("n_elem_with_halo"), "plan_options": {k: v for k, v in options.items() if k != "accumulate"}, "functions": functions, "perturb": args.perturb, "parallelism": ("z-slabs x%d + halo sum (%s)" % (world, "p2p peer stores over NVLink" if plan.stat("halo_p2p") else "NCCL send/recv")) if world > 1 else "1 GPU"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, measured in this run" if traffic else None,
                              "kernel": "gen_element_kernel + gen_pull_kernel (general path, whole assemble call)" if general else "mrh_thermal_q1_3d", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * prob.n_rows * world, "d2h_bytes_per_step": 8 * (prob.n_rows + prob.nnz) * world,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * prob.n_rows * world * h2d_vectors, "d2h_bytes_per_step": 8 * (prob.n_rows + prob.nnz) * world,
                         "steps": e2e_steps, "api": "mrhyde_b200_assemble_jacres_host (pinned host buffers)"},
                 "gpu_launches": int(args.steps * launches_per_step), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
@@ -385,15 +452,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="elements per brick edge (per GPU); default 128 (thermal), 64 (le), 96 (ns), 48 (leq2; BASELINE configs[2] is 64)")
+    ap.add_argument("--n", type=int, default=0, help="elements per brick edge (per GPU); default 128 (thermal), 64 (le), 96 (ns), 64 (leq2), 64 (maxwell): the BASELINE sizes")
     ap.add_argument("--workload", default="thermal", choices=sorted(WORKLOADS), help="thermal = BASELINE configs[1] (the headline); le / ns: other modules through the general path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="plan option key=value (tuning experiments), repeatable")
+    ap.add_argument("--fn", action="append", default=[], help="Functions entry name=expression overriding the workload's deck (e.g. 'thermal diffusion=1.0+0.5*x*x'), repeatable")
+    ap.add_argument("--perturb", type=float, default=0.0, help="thermal: move interior nodes by up to this fraction of h (general cells instead of boxes)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: n^3 elements PER GPU (z-slabs stacked); strong: n^3 elements in total, n/N layers per GPU")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu pass that measures the dominant kernel's DRAM traffic (roofline.traffic = null)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     global _WORKLOAD
     _WORKLOAD = args.workload
     if args.n <= 0:
-        args.n = {"thermal": 128, "le": 64, "ns": 96, "leq2": 48}[args.workload]
+        args.n = {"thermal": 128, "le": 64, "ns": 96, "leq2": 64, "maxwell": 64}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -164,7 +164,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "debug transient", "debug mode", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "scratch GB", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -265,7 +265,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
                                const int64_t (&n_class)[3], int metric_ng, int max_patterns, int pull_group,
-                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn) {
+                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -292,9 +292,12 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   }
   o += "#define MRH_DEBUG_SKIP " + std::to_string(debug_skip) + "   /* timing experiments only: 1 no global stores, 2 no element work, 3 neither */\n";
   if (!class_rep.empty()) o += "#define MRH_JIT_CLASS_NC " + std::to_string(class_rep.size()) + "\n";   // class ring (volume_kernel.cuh)
+  if (!class_rep.empty() && pipe > 0) o += "#define MRH_JIT_PIPE " + std::to_string(pipe) + "   /* register-staged pipeline: 2 = even / odd warps run pull and element work in opposite order, 1 = same order */\n";
   if (metric_ng > 0) {   // metric ring (volume_kernel.cuh): parallelepiped cells + constant coefficients only
-    o += "#define MRH_JIT_METRIC 1\n#define MRH_JIT_METRIC_NG " + std::to_string(metric_ng) + "\n#define MRH_JIT_CAP " + std::to_string(cp.cap) + "\n";
+    o += "#define MRH_JIT_METRIC 1\n#define MRH_JIT_METRIC_NG " + std::to_string(metric_ng) + "\n";
   }
+  o += "#define MRH_JIT_CAP " + std::to_string(cp.cap) + "   /* ring slot capacity: staging offsets become immediates */\n";
+  o += "#define MRH_JIT_STORE_HINT " + std::to_string(store_hint) + "   /* 1: finished rows leave with an L2 evict-first policy (state / vertices stay L2-resident) */\n";
   o += kKernelAbiSrc;
   o += "\nnamespace mrhyde_b200 {\n";
   o += "__device__ __forceinline__ double mrh_abs(double a) { return a < 0.0 ? -a : a; }\n";
@@ -523,8 +526,15 @@ __device__ __forceinline__ void mrh_run_flush(const MrhRun& R, const long long b
     if (cnt & 1) { double v = s[cnt - 1]; if (ACC) v += jac[g + cnt - 1]; jac[g + cnt - 1] = v; --cnt; }
     if (cnt > 0) {
       const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+#if MRH_JIT_STORE_HINT
+      unsigned long long pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      if (ACC) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.L2::cache_hint.add.f64 [%0], [%1], %2, %3;" :: "l"(jac + g), "r"(sa), "r"(cnt * 8), "l"(pol) : "memory");
+      else asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" :: "l"(jac + g), "r"(sa), "r"(cnt * 8), "l"(pol) : "memory");
+#else
       if (ACC) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" :: "l"(jac + g), "r"(sa), "r"(cnt * 8) : "memory");
       else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(jac + g), "r"(sa), "r"(cnt * 8) : "memory");
+#endif
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
@@ -1160,8 +1170,15 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
   // one batch by default: measured on the B200, splitting the element range so that a batch of element matrices stays
   // L2-resident costs more in launch tails than the pull saves in DRAM reads (profiles/r01_general_bench.jsonl)
   const int64_t batch_elems = std::stoll(opt(P, "batch elems", "-1"));
+  // element scratch budget: option "scratch GB" or a quarter of the free device memory; a plan that fits runs one batch, otherwise
+  // the element range is cut into batches whose scratch ring fits (plan_stat "general_scratch_bytes", "general_batches")
+  int64_t budget = (int64_t)(std::stod(opt(P, "scratch GB", "0")) * 1e9);
+  if (budget <= 0 && !host_only) {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = (int64_t)(fr / 4);
+  }
   try {
-    gen_build_pull(M, I.N, H.sides, batch_elems, H);
+    gen_build_pull(M, I.N, H.sides, batch_elems, budget, H);
   } catch (const std::exception& e) {
     fail(MRHYDE_B200_ERR_INVALID, e.what());
   }
@@ -1563,8 +1580,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     for (int tr = 0; tr < 2; ++tr)
       P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
     const int pull_group = std::stoi(opt(P, "pull group", "8"));
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn)
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn);
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0)
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0);
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
@@ -1756,7 +1773,8 @@ int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* P, int64_t n_cols, const int64_t
   for (int32_t c : P->mesh.colind) if (c < 0 || c >= n_cols) fail(MRHYDE_B200_ERR_INVALID, "set_halo: a column index of the graph is outside [0, n_cols)");
   CUDA_OK(cudaSetDevice(P->device));
   std::string err;
-  P->halo->set_transport(opt(P, "halo transport", "auto"));
+  // "overlap halo" starts the exchange of some ranks with NCCL send/recv from inside assemble: every rank must then use that transport
+  P->halo->set_transport(opt_bool(P, "overlap halo", false) ? std::string("nccl") : opt(P, "halo transport", "auto"));
   if (!P->halo->setup(P->mesh.nrows, P->mesh.nowned, n_cols, col_gids, P->mesh.rowptr.data(), P->mesh.colind.data(), err)) fail(MRHYDE_B200_ERR_NCCL, err);
   ABI_END
 }
@@ -1811,7 +1829,9 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "general") *value = P->use_general ? 1 : 0;
   else if (k == "general_batches") *value = (int64_t)P->gen.batches.size();
   else if (k == "general_instances") *value = P->gen.n_inst;
-  else if (k == "general_scratch_bytes") *value = P->gen.n_inst * (int64_t)P->gen.info.N * (P->gen.info.N + 1) * 8;
+  else if (k == "general_scratch_bytes") *value = gen_scratch_instances(P->gen) * (int64_t)P->gen.info.N * (P->gen.info.N + 1) * 8;
+  else if (k == "general_batches") *value = (int64_t)P->gen.batches.size();
+  else if (k == "general_pos_tables") *value = P->gen.info.N > 0 ? (int64_t)(P->gen.pos_tab.size() / ((size_t)P->gen.info.N * P->gen.info.N)) : 0;
   else fail(MRHYDE_B200_ERR_INVALID, "plan_stat: unknown key '" + k + "'");
   ABI_END
 }

@@ -46,7 +46,8 @@ std::vector<GenDeviceKernels>& device_table() {
 struct PullParams {
   const int32_t* row_order;
   const int64_t* contrib_ptr;
-  const int32_t* contrib;
+  const int32_t* contrib;       // scratch slot * N + local row of every contribution (ascending instance order)
+  const int32_t* contrib_pos;   // row of the (de-duplicated) column-position table: pos_id[instance] * N + local row
   const uint16_t* pos;
   const double* elem_jac;
   const double* elem_res;
@@ -57,7 +58,7 @@ struct PullParams {
   // mass pull: fixed rows are not skipped, instances >= mass_inst_end (boundary sides) are ignored, O.res receives the
   // diagonal vector (Jacobi diagonal, or the lumped row sums of |entries| when mass_mode == 2)
   int32_t mass_mode;
-  int64_t mass_inst_end;
+  int64_t mass_inst_end;        // scratch slots >= this one hold boundary-side instances
 };
 
 // G lanes per row, NPL = ceil(N / G) columns per lane and instance; the loads of U instances are issued before the first
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
       double s = 0.0;
       for (int64_t p = c0; p < c1; ++p) {
         const int64_t inst = __ldg(Q.contrib + p);
-        if (inst / Q.N < Q.mass_inst_end) s += __ldcs(Q.elem_res + inst);
+        if (inst / Q.N < Q.mass_inst_end) s += __ldcs(Q.elem_res + inst);   // inst = slot * N + row
       }
       Q.O.res[r] = (Q.O.accumulate ? Q.O.res[r] : 0.0) + s;
     }
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
     for (int64_t p = c0; p < c1; ++p) {
       const int64_t inst = __ldg(Q.contrib + p);
       if (inst / N >= Q.mass_inst_end) continue;
-      const int64_t ci = inst * N;
-      for (int c = lane; c < N; c += G) { const double v = __ldcs(Q.elem_jac + ci + c); buf[__ldg(Q.pos + ci + c)] += v; lumped += fabs(v); }
+      const int64_t ci = inst * N, pi = (int64_t)__ldg(Q.contrib_pos + p) * N;
+      for (int c = lane; c < N; c += G) { const double v = __ldcs(Q.elem_jac + ci + c); buf[__ldg(Q.pos + pi + c)] += v; lumped += fabs(v); }
       __syncwarp(mask);
     }
     if (Q.O.jac) for (int t = lane; t < len; t += G) Q.O.jac[rs + t] = (Q.O.accumulate ? Q.O.jac[rs + t] : 0.0) + buf[t];
@@ -130,11 +131,12 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t ci = p + u < c1 ? (int64_t)__ldg(Q.contrib + p + u) * N : -1;
+        const int64_t pi = p + u < c1 ? (int64_t)__ldg(Q.contrib_pos + p + u) * N : 0;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
           const int c = lane + j * G;
           const bool ok = ci >= 0 && c < N;
-          ps[u][j] = ok ? (int)__ldg(Q.pos + ci + c) : -1;
+          ps[u][j] = ok ? (int)__ldg(Q.pos + pi + c) : -1;
           v[u][j] = ok ? __ldcs(Q.elem_jac + ci + c) : 0.0;
         }
       }
@@ -188,7 +190,7 @@ struct SideDev {
 
 struct GeneralPlanDev {
   Buf<double> zero;   // state placeholder of the mass mode
-  Buf<int32_t> row_order, contrib;
+  Buf<int32_t> row_order, contrib, contrib_pos;
   Buf<int64_t> contrib_ptr;
   Buf<uint16_t> pos;
   Buf<double> geo_N, geo_dN, ref_tab, qwts, fn_c, elem_jac, elem_res;
@@ -208,10 +210,34 @@ void gen_free(GeneralPlanDev* D) { delete D; }
 GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t* tot, std::string& err) {
   std::unique_ptr<GeneralPlanDev> D(new GeneralPlanDev());
   const size_t N = (size_t)H.info.N;
-  bool ok = D->row_order.upload(H.row_order, tot, err) && D->contrib.upload(H.contrib, tot, err) && D->contrib_ptr.upload(H.contrib_ptr, tot, err) &&
-            D->pos.upload(H.pos, tot, err) && D->geo_N.upload(H.geo_N, tot, err) && D->geo_dN.upload(H.geo_dN, tot, err) &&
+  // contributions by scratch slot and by position-table row (the host plan lists them by instance)
+  // Tensor-core kernels index the scratch variable-major, (v, i) -> v * card + i (GenParams::var_major): kperm maps the
+  // element-local dof to that index and the contribution list / position tables are permuted to match.
+  std::vector<int> kperm(N);
+  for (size_t i = 0; i < N; ++i) kperm[i] = (int)i;
+  if (H.info.tensor)
+    for (int v = 0; v < H.info.nvars; ++v)
+      for (int i = 0; i < H.info.card[0]; ++i) kperm[(size_t)H.off[v][i]] = v * H.info.card[0] + i;
+  std::vector<int32_t> cslot(H.contrib.size()), cpos(H.contrib.size());
+  for (size_t p = 0; p < H.contrib.size(); ++p) {
+    const int64_t inst = H.contrib[p] / (int64_t)N, i = kperm[(size_t)(H.contrib[p] % (int64_t)N)];
+    cslot[p] = (int32_t)(gen_slot(H, inst) * (int64_t)N + i);
+    cpos[p] = (int32_t)((int64_t)H.pos_id[(size_t)inst] * (int64_t)N + i);
+  }
+  std::vector<uint16_t> pos_dev;
+  if (H.info.tensor) {
+    pos_dev.resize(H.pos_tab.size());
+    const size_t ntab = H.pos_tab.size() / (N * N);
+    for (size_t t = 0; t < ntab; ++t)
+      for (size_t r = 0; r < N; ++r)
+        for (size_t c = 0; c < N; ++c) pos_dev[(t * N + (size_t)kperm[r]) * N + (size_t)kperm[c]] = H.pos_tab[(t * N + r) * N + c];
+  }
+  const std::vector<uint16_t>& pos_up = H.info.tensor ? pos_dev : H.pos_tab;
+  const size_t n_scratch = (size_t)gen_scratch_instances(H);
+  bool ok = D->row_order.upload(H.row_order, tot, err) && D->contrib.upload(cslot, tot, err) && D->contrib_pos.upload(cpos, tot, err) && D->contrib_ptr.upload(H.contrib_ptr, tot, err) &&
+            D->pos.upload(pos_up, tot, err) && D->geo_N.upload(H.geo_N, tot, err) && D->geo_dN.upload(H.geo_dN, tot, err) &&
             D->ref_tab.upload(H.ref_tab, tot, err) && D->qwts.upload(H.qwts, tot, err) && D->fn_c.upload(H.fn_c, tot, err) &&
-            D->fn_op.upload(H.fn_op, tot, err) && D->elem_jac.alloc((size_t)H.n_inst * N * N, tot, err) && D->elem_res.alloc((size_t)H.n_inst * N, tot, err);
+            D->fn_op.upload(H.fn_op, tot, err) && D->elem_jac.alloc(n_scratch * N * N, tot, err) && D->elem_res.alloc(n_scratch * N, tot, err);
   if (ok && !m.orient.empty()) ok = D->orient.upload(m.orient, tot, err);
   for (auto& s : H.sides) {
     if (!ok) break;
@@ -234,8 +260,9 @@ static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items, int epb_
   const int sd = side ? I.smem_doubles_side : I.smem_doubles_volume;
   const size_t smem_cap = (size_t)(220 * 1024) / (size_t)std::max(1, I.min_blocks);
   int epb = std::max(1, I.max_threads / tpe);
+  if (I.tensor) epb = 16;   // tensor-core kernels: any thread count serves any element count (work items are strided over the CTA)
   if (epb_override > 0) epb = epb_override;
-  while (epb > 1 && ((size_t)epb * sd * 8 > smem_cap || epb * tpe > I.max_threads)) --epb;
+  while (epb > 1 && ((size_t)epb * sd * 8 > smem_cap || (!I.tensor && epb * tpe > I.max_threads))) --epb;
   if (n_items < epb) epb = (int)std::max<int64_t>(1, n_items);
   return epb;
 }
@@ -296,6 +323,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   std::memset(&P, 0, sizeof(P));
   P.vx = vx; P.vy = vy; P.vz = vz; P.conn = conn; P.lids = lids; P.orient = D->orient.n ? D->orient.p : nullptr;
   P.sol = sol; P.td = td;
+  P.var_major = I.tensor ? 1 : 0;
   const bool initial = (pull_mass_mode == 4);   // projection of the initial conditions: the pull is the one of applyMassMatrixFree
   if (initial) pull_mass_mode = 3;
   if (pull_mass_mode) { P.mass_mode = initial ? 2 : 1; for (int v = 0; v < I.nvars; ++v) P.mass_wts[v] = mass_wts[v]; }
@@ -313,6 +341,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
     const int tpe = I.tpe;
     int threads = ((epb * tpe + 31) / 32) * 32;
     threads = std::max(32, std::min(I.max_threads, threads));
+    if (I.tensor) threads = std::max(32, std::min(I.max_threads, 32 * std::max(2, epb * I.nvars * I.nvars)));   // one warp per (element, variable pair) block, two warps at least
     const size_t smem = (size_t)epb * (side ? I.smem_doubles_side : I.smem_doubles_volume) * sizeof(double);
     const int64_t nblocks = (n_items + epb - 1) / epb;
     ++launches;
@@ -321,10 +350,10 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   auto run_pull = [&](int64_t row_begin, int64_t row_end) -> const char* {
     if (row_end <= row_begin) return nullptr;
     PullParams Q;
-    Q.row_order = D->row_order.p; Q.contrib_ptr = D->contrib_ptr.p; Q.contrib = D->contrib.p; Q.pos = D->pos.p;
+    Q.row_order = D->row_order.p; Q.contrib_ptr = D->contrib_ptr.p; Q.contrib = D->contrib.p; Q.contrib_pos = D->contrib_pos.p; Q.pos = D->pos.p;
     Q.elem_jac = D->elem_jac.p; Q.elem_res = D->elem_res.p; Q.G = G; Q.O = O;
     Q.row_begin = row_begin; Q.row_end = row_end; Q.n_owned = H.n_owned; Q.N = I.N; Q.max_row_len = std::max(1, H.max_row_len);
-    Q.mass_mode = pull_mass_mode; Q.mass_inst_end = H.n_elem;
+    Q.mass_mode = pull_mass_mode; Q.mass_inst_end = H.scratch_cap;
     const int Gs = I.N <= 8 ? 8 : (I.N <= 16 ? 16 : 32);
     const int npl = (I.N + Gs - 1) / Gs;
     if (npl > 3) return "general pull: more than 96 dofs per element";
@@ -345,19 +374,19 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   };
   const bool any_side = boundary && std::any_of(H.sides.begin(), H.sides.end(), [](const GenSideFamily& s) { return s.active && !s.items.empty(); });
   // instances that are not computed in this call must read as zero: clear the scratch ranges that are skipped
-  if (!volume) {
-    if (P.elem_jac) cudaMemsetAsync(D->elem_jac.p, 0, (size_t)H.n_elem * I.N * I.N * sizeof(double), (cudaStream_t)stream);
-    if (P.elem_res) cudaMemsetAsync(D->elem_res.p, 0, (size_t)H.n_elem * I.N * sizeof(double), (cudaStream_t)stream);
+  if (!volume) {   // the whole ring reads as zero
+    if (P.elem_jac) cudaMemsetAsync(D->elem_jac.p, 0, (size_t)H.scratch_cap * I.N * I.N * sizeof(double), (cudaStream_t)stream);
+    if (P.elem_res) cudaMemsetAsync(D->elem_res.p, 0, (size_t)H.scratch_cap * I.N * sizeof(double), (cudaStream_t)stream);
   }
   if (!any_side && H.n_inst > H.n_elem) {
-    if (P.elem_jac) cudaMemsetAsync(D->elem_jac.p + (size_t)H.n_elem * I.N * I.N, 0, (size_t)(H.n_inst - H.n_elem) * I.N * I.N * sizeof(double), (cudaStream_t)stream);
-    if (P.elem_res) cudaMemsetAsync(D->elem_res.p + (size_t)H.n_elem * I.N, 0, (size_t)(H.n_inst - H.n_elem) * I.N * sizeof(double), (cudaStream_t)stream);
+    if (P.elem_jac) cudaMemsetAsync(D->elem_jac.p + (size_t)H.scratch_cap * I.N * I.N, 0, (size_t)(H.n_inst - H.n_elem) * I.N * I.N * sizeof(double), (cudaStream_t)stream);
+    if (P.elem_res) cudaMemsetAsync(D->elem_res.p + (size_t)H.scratch_cap * I.N, 0, (size_t)(H.n_inst - H.n_elem) * I.N * sizeof(double), (cudaStream_t)stream);
   }
   const int nb = (int)H.batches.size();
   for (int b = 0; b < nb; ++b) {
     const GenBatch& B = H.batches[(size_t)b];
     if (volume) {
-      P.items = nullptr; P.item_begin = B.elem_begin; P.item_end = B.elem_end; P.inst_base = B.elem_begin;
+      P.items = nullptr; P.item_begin = B.elem_begin; P.item_end = B.elem_end; P.inst_base = B.elem_begin % H.scratch_cap;   // batches do not wrap: the ring is a multiple of the batch size
       std::memcpy(P.fn, initial ? H.init_fn : H.fn, sizeof(P.fn));
       for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
       P.geo_N = D->geo_N.p; P.geo_dN = D->geo_dN.p; P.ref_tab = D->ref_tab.p; P.qwts = D->qwts.p;
@@ -368,7 +397,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
         const GenSideFamily& S = H.sides[s];
         if (!S.active || S.items.empty()) continue;
         const SideDev& sd = *D->sides[s];
-        P.items = sd.items.p; P.item_begin = 0; P.item_end = (int64_t)S.items.size(); P.inst_base = S.inst_base;
+        P.items = sd.items.p; P.item_begin = 0; P.item_end = (int64_t)S.items.size(); P.inst_base = H.scratch_cap + (S.inst_base - H.n_elem);
         P.geo_N = sd.geo_N.p; P.geo_dN = sd.geo_dN.p; P.ref_tab = sd.ref_tab.p; P.qwts = sd.qwts.p;
         for (int d = 0; d < 3; ++d) { P.tan_u[d] = S.tan_u[d]; P.tan_v[d] = S.tan_v[d]; }
         for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = S.bc_type[v]; P.bc_fn[v] = S.bc_fn[v]; }

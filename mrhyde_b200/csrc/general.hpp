@@ -23,6 +23,7 @@ struct GenKernelInfo {
   int dim, order, nq, nqs;
   int N, nvars, nbasis, nfn, K;
   int tpe;                                      // threads per element in the derivative stage
+  int tensor;                                   // 1: Jacobian by field-direction derivatives + FP64 tensor-core contraction (general_kernel.cuh, S4d / S4m)
   int max_threads, min_blocks;                  // launch bounds of the element kernel
   int smem_doubles_volume, smem_doubles_side;   // per element
   int card[2], ncb[2];                          // per basis
@@ -67,7 +68,12 @@ struct GeneralPlanHost {
   std::vector<int32_t> row_order;        // rows sorted by completion batch
   std::vector<int64_t> contrib_ptr;      // [n_rows+1] in row_order order
   std::vector<int32_t> contrib;          // inst * N + local row, ascending instance
-  std::vector<uint16_t> pos;             // [n_inst][N][N]: position of column LID(c) inside row LID(i)
+  std::vector<uint16_t> pos_tab;         // [n_pos_patterns][N][N]: position of column LID(c) inside row LID(i); instances with
+  std::vector<int32_t> pos_id;           // identical tables share one (pos_id[inst]): a handful on structured meshes, L2-resident
+  // element scratch: volume instances live in a RING of `scratch_cap` instances (slot = inst % scratch_cap, a multiple of the batch
+  // size), chosen at plan time so that an instance is overwritten only after every row it feeds has been pulled; boundary-side
+  // instances follow the ring (slot = scratch_cap + inst - n_elem).  One batch: scratch_cap = n_elem.
+  int64_t scratch_cap = 0;
   std::vector<GenBatch> batches;         // volume batches; rows completed by side instances sit in the last batch
   // launch tables (volume)
   std::vector<double> geo_N, geo_dN, ref_tab, qwts;
@@ -81,7 +87,10 @@ struct GeneralPlanHost {
 };
 
 // builds contrib / pos / row_order / batches from the mesh graph and the side families' items
-void gen_build_pull(const MeshGraph& m, int N, const std::vector<GenSideFamily>& sides, int64_t batch_elems, GeneralPlanHost& out);
+// batch_elems <= 0: chosen from scratch_budget_bytes (the largest batch whose ring fits; one batch if everything fits)
+void gen_build_pull(const MeshGraph& m, int N, const std::vector<GenSideFamily>& sides, int64_t batch_elems, int64_t scratch_budget_bytes, GeneralPlanHost& out);
+inline int64_t gen_slot(const GeneralPlanHost& H, int64_t inst) { return inst < H.n_elem ? inst % H.scratch_cap : H.scratch_cap + (inst - H.n_elem); }
+inline int64_t gen_scratch_instances(const GeneralPlanHost& H) { return H.scratch_cap + (H.n_inst - H.n_elem); }
 
 // host replay of the pull (plan verification and the emulation hook)
 void gen_pull_host(const GeneralPlanHost& H, const MeshGraph& m, const double* elem_jac, const double* elem_res, bool accumulate,

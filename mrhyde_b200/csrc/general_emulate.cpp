@@ -25,8 +25,14 @@ void emulate_blocks(const GenParams& P, int nblocks) {
     for (int i = 0; i < P.epb * Phys::max_card() * NQ; ++i) Bk::s2(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb * NQ * Bk::S3_KINDS; ++i) Bk::s3(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb * NQ; ++i) Bk::s4a(P, sm.data(), blk, i);
-    if (P.elem_jac)
-      for (int i = 0; i < P.epb * Bk::TPE; ++i) Bk::s4b(P, sm.data(), blk, i);
+    if (P.elem_jac) {
+      if (Bk::TC) {   // field-direction derivatives + contraction (the device runs the contraction on the FP64 tensor cores)
+        for (int i = 0; i < P.epb * NQ * Bk::NCV; ++i) Bk::s4d(P, sm.data(), blk, i);
+        for (int i = 0; i < P.epb * L::NVAR * L::NVAR; ++i) Bk::s4m_item(P, sm.data(), blk, i);
+      } else {
+        for (int i = 0; i < P.epb * Bk::TPE; ++i) Bk::s4b(P, sm.data(), blk, i);
+      }
+    }
     for (int i = 0; i < P.epb * L::N; ++i) Bk::s5(P, sm.data(), blk, i);
   }
 }

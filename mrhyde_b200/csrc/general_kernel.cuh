@@ -155,6 +155,10 @@ struct GenParams {
   // initial conditions (gen_initial_point, residual stage only)
   int32_t mass_mode;
   double mass_wts[GEN_MAXVARS];
+  // 1: the scratch element matrices / vectors are indexed variable-major, (v, i) -> v * card + i, instead of by the element-local
+  // dof off[v][i] (device plans of the tensor-core contraction: a fragment row then is a contiguous run in global memory; the
+  // pull's contribution list and position tables are permuted to match at upload, general.cu)
+  int32_t var_major;
 };
 
 // what the physics sees at one point
@@ -271,8 +275,19 @@ struct GenLayout {
   static constexpr int FT = FV + NQ * NVAR * NC;
   static constexpr int FN = FT + NQ * NVAR * NC;
   static constexpr int CV = FN + even(NQ * NFN);
-  static constexpr int SIZE = CV + NQ * NVAR * NC;
+  // tensor-core contraction (single-basis HGRAD modules): D_q = d Cf / d F at every point, [q][(v,k)][(w,l)]
+  static constexpr bool TC = (Phys::NBASIS == 1);
+  static constexpr int NCV = NVAR * NC;
+  static constexpr int DM = CV + NQ * NVAR * NC;
+  static constexpr int SIZE = DM + (TC ? NQ * NCV * NCV : 0);
 };
+
+#if defined(__CUDA_ARCH__)
+// FP64 tensor-core tile: C (8x8) += A (8x4, row) * B (4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2 (l%4) + {0,1}].
+__device__ __forceinline__ void mrh_dmma(double (&c)[2], const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+#endif
 
 // ---- the stages ----------------------------------------------------------------------------------------------
 template <class Phys, int NQ, int K, bool SIDE>
@@ -589,6 +604,124 @@ struct GenBlock {
     }
   }
 
+  // ---- tensor-core form of the Jacobian (single-basis HGRAD modules; north_star: "fp64 DMMA for the per-element B^T D B") ----
+  // The AD derivative lanes run over FIELD DIRECTIONS instead of element dofs: one evaluation of the module's point function
+  // on Dual<1> per (point, direction (w,l)) gives column (w,l) of  D_q = alpha_u dCf/dF + alpha_t dCf/dF_t  (NVAR NC columns
+  // instead of N), and the element matrix is the contraction
+  //     J[(v,i),(w,j)] = sum_q sum_k sum_l PB[i][q][k] D_q[(v,k),(w,l)] PB[j][q][l]
+  // done per variable pair (v,w) as a GEMM on the FP64 tensor cores: A[i][(q,k)] = PB (already laid out that way in shared
+  // memory), B[(q,k)][j] = sum_l D_q[(v,k),(w,l)] PB[j][q][l] built in registers, one mma.m8n8k4 k-step per point.
+  static constexpr bool TC = L::TC;
+  static constexpr int NCV = L::NCV, CARD = Phys::card(0), IT = (CARD + 7) / 8;
+  MRH_HD static int row_index(const GenParams& P, int v, int i) { return P.var_major ? v * CARD + i : (int)P.off[v][i]; }
+
+  // S4d: column `dir` of D at (element, point)
+  MRH_HD static void s4d(const GenParams& P, double* sm, int /*blk*/, int idx) {
+    if (idx >= P.epb * NQ * NCV) return;
+    const int el = idx / (NQ * NCV), r = idx % (NQ * NCV), q = r / NCV, dir = r % NCV;
+    double* sme = sm + el * L::SIZE;
+    QpCtx c;
+    make_ctx(P, sme, q, c);
+    const bool transient = P.td.transient != 0;
+    const double au = transient ? P.td.alpha_u : 1.0, at = transient ? P.td.alpha_t : 0.0;
+    Dual<1> F[NVAR][NC], Ft[NVAR][NC], Cf[NVAR][NC];
+#pragma unroll
+    for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const bool mine = (v * NC + k) == dir;
+        F[v][k].v = sme[L::FV + (q * NVAR + v) * NC + k];
+        F[v][k].d[0] = mine ? au : 0.0;
+        Ft[v][k].v = transient ? sme[L::FT + (q * NVAR + v) * NC + k] : 0.0;
+        Ft[v][k].d[0] = (mine && k < Phys::nval(0)) ? at : 0.0;
+        Cf[v][k] = Dual<1>(0.0);
+      }
+    if (P.mass_mode) gen_mass_point<Phys, Dual<1>>(c, P.mass_wts, F, Cf);
+    else if (SIDE) Phys::template boundary<Dual<1>>(c, P.opt, F, Ft, Cf);
+    else Phys::template volume<Dual<1>>(c, P.opt, F, Ft, Cf);
+    double* D = sme + L::DM + q * NCV * NCV;
+#pragma unroll
+    for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+      for (int k = 0; k < NC; ++k) D[(v * NC + k) * NCV + dir] = Cf[v][k].d[0];
+  }
+
+#if defined(__CUDA_ARCH__)
+  // S4m: one warp, one (element, v, w) block of the element matrix
+  __device__ __forceinline__ static void s4m_warp(const GenParams& P, const double* sm, int blk, int item, int lane) {
+    const int el = item / (NVAR * NVAR), vw = item % (NVAR * NVAR), v = vw / NVAR, w = vw % NVAR;
+    const double* sme = sm + el * L::SIZE;
+    const double* pb = sme + L::PB;
+    const double* D = sme + L::DM + (v * NC + (lane & 3)) * NCV + w * NC;
+    const int g = lane >> 2, t = lane & 3;
+    double acc[IT][IT][2];
+    int ro[IT];
+#pragma unroll
+    for (int a = 0; a < IT; ++a) {
+      ro[a] = ((a * 8 + g) < CARD ? (a * 8 + g) : (CARD - 1)) * NQ * NC;   // rows beyond the basis repeat the last one (their results are dropped)
+#pragma unroll
+      for (int b = 0; b < IT; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    }
+#pragma unroll 1
+    for (int q = 0; q < NQ; ++q) {
+      double d[NC], fa[IT], fb[IT];
+      mrh_ldn<NC>(D + q * NCV * NCV, d);
+#pragma unroll
+      for (int a = 0; a < IT; ++a) {
+        double pr[NC];
+        mrh_ldn<NC>(pb + ro[a] + q * NC, pr);
+        fa[a] = t == 0 ? pr[0] : (t == 1 ? pr[1] : (t == 2 ? pr[2] : pr[3]));
+        fb[a] = d[0] * pr[0] + d[1] * pr[1] + d[2] * pr[2] + d[3] * pr[3];
+      }
+#pragma unroll
+      for (int a = 0; a < IT; ++a)
+#pragma unroll
+        for (int b = 0; b < IT; ++b) mrh_dmma(acc[a][b], fa[a], fb[b]);
+    }
+    const int64_t it = item_of(P, blk, el);
+    if (it < P.item_end && P.elem_jac) {
+      double* out = P.elem_jac + (P.inst_base + (it - P.item_begin)) * (int64_t)(N * N);
+#pragma unroll
+      for (int a = 0; a < IT; ++a) {
+        const int i = a * 8 + g;
+        if (i < CARD) {
+          double* orow = out + (int64_t)row_index(P, v, i) * N;
+#pragma unroll
+          for (int b = 0; b < IT; ++b)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              const int j = b * 8 + 2 * t + x;
+              if (j < CARD) orow[row_index(P, w, j)] = acc[a][b][x];
+            }
+        }
+      }
+    }
+  }
+#endif
+  // host replay of S4m (one work item = one (element, v, w) block, plain loops)
+  MRH_HD static void s4m_item(const GenParams& P, const double* sm, int blk, int item) {
+    if (item >= P.epb * NVAR * NVAR) return;
+    const int el = item / (NVAR * NVAR), vw = item % (NVAR * NVAR), v = vw / NVAR, w = vw % NVAR;
+    const int64_t it = item_of(P, blk, el);
+    if (it >= P.item_end || !P.elem_jac) return;
+    const double* sme = sm + el * L::SIZE;
+    const double* pb = sme + L::PB;
+    double* out = P.elem_jac + (P.inst_base + (it - P.item_begin)) * (int64_t)(N * N);
+    for (int i = 0; i < CARD; ++i)
+      for (int j = 0; j < CARD; ++j) {
+        double s = 0.0;
+        for (int q = 0; q < NQ; ++q) {
+          const double* D = sme + L::DM + q * NCV * NCV;
+          for (int k = 0; k < NC; ++k) {
+            double b = 0.0;
+            for (int l = 0; l < NC; ++l) b += D[(v * NC + k) * NCV + w * NC + l] * pb[(j * NQ + q) * NC + l];
+            s += pb[(i * NQ + q) * NC + k] * b;
+          }
+        }
+        out[(int64_t)row_index(P, v, i) * N + row_index(P, w, j)] = s;
+      }
+  }
+
   // S5: residual rows
   MRH_HD static void s5(const GenParams& P, double* sm, int blk, int idx) {
     if (idx >= P.epb * N || !P.elem_res) return;
@@ -608,7 +741,7 @@ struct GenBlock {
     double s = 0.0;
     for (int q = 0; q < NQ; ++q)
       for (int k = 0; k < ncb; ++k) s += sme[L::CV + (q * NVAR + v) * NC + k] * pb[q * ncb + k];
-    P.elem_res[(P.inst_base + (item - P.item_begin)) * (int64_t)N + P.off[v][i]] = s;
+    P.elem_res[(P.inst_base + (item - P.item_begin)) * (int64_t)N + (P.var_major ? r : (int)P.off[v][i])] = s;
   }
 };
 
@@ -631,9 +764,17 @@ __global__ void __launch_bounds__(MAXT, MINB) gen_element_kernel(const __grid_co
   for (int i = tid; i < P.epb * NQ * Bk::S3_KINDS; i += T) Bk::s3(P, gen_smem, blk, i);
   __syncthreads();
   for (int i = tid; i < P.epb * NQ; i += T) Bk::s4a(P, gen_smem, blk, i);
-  if (P.elem_jac)
-    for (int i = tid; i < P.epb * Bk::TPE; i += T) Bk::s4b(P, gen_smem, blk, i);
-  __syncthreads();
+  if constexpr (Bk::TC) {
+    if (P.elem_jac)
+      for (int i = tid; i < P.epb * NQ * Bk::NCV; i += T) Bk::s4d(P, gen_smem, blk, i);
+    __syncthreads();
+    if (P.elem_jac)
+      for (int item = tid >> 5; item < P.epb * L::NVAR * L::NVAR; item += T >> 5) Bk::s4m_warp(P, gen_smem, blk, item, tid & 31);
+  } else {
+    if (P.elem_jac)
+      for (int i = tid; i < P.epb * Bk::TPE; i += T) Bk::s4b(P, gen_smem, blk, i);
+    __syncthreads();
+  }
   for (int i = tid; i < P.epb * L::N; i += T) Bk::s5(P, gen_smem, blk, i);
 }
 #endif

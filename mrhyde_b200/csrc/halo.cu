@@ -107,7 +107,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 //   phase 2  source rank by source rank (ascending: fixed summation order): wait for arrive[source], add the slab, last CTA acknowledges
 // counters[0 .. n): CTAs that finished the push to peer i; counters[n .. 2n): CTAs that finished the add from peer i (both reset by
 // their last CTA); counters[2n]: running ticket of the grid barrier between two sources.
-__global__ void __launch_bounds__(256) halo_p2p_kernel(const P2PPeerDev* __restrict__ peers, int n, unsigned long long epoch, double* __restrict__ res,
+__global__ void __launch_bounds__(1024) halo_p2p_kernel(const P2PPeerDev* __restrict__ peers, int n, unsigned long long epoch, double* __restrict__ res,
                                                         double* __restrict__ jac, unsigned* counters) {
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   const int par = (int)(epoch & 1ull);
@@ -121,8 +121,14 @@ __global__ void __launch_bounds__(256) halo_p2p_kernel(const P2PPeerDev* __restr
     if (P.send_res_first >= 0) for (int64_t k = tid; k < nr; k += nth) slab[k] = res[P.send_res_first + k];
     else for (int64_t k = tid; k < nr; k += nth) slab[k] = res[P.send_res_pos[k]];
     double* sj = slab + P.send_jac_off;
-    if (P.send_jac_first >= 0) for (int64_t k = tid; k < nj; k += nth) sj[k] = jac[P.send_jac_first + k];
-    else for (int64_t k = tid; k < nj; k += nth) sj[k] = jac[P.send_jac_pos[k]];
+    if (P.send_jac_first >= 0) {
+      const double* src = jac + P.send_jac_first;
+#pragma unroll 4
+      for (int64_t k = tid; k < nj; k += nth) sj[k] = __ldcs(src + k);   // independent loads in flight, posted stores over NVLink
+    } else {
+#pragma unroll 4
+      for (int64_t k = tid; k < nj; k += nth) sj[k] = jac[P.send_jac_pos[k]];
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
@@ -152,7 +158,8 @@ __global__ void __launch_bounds__(256) halo_p2p_kernel(const P2PPeerDev* __restr
     const double* slab = P.local_slab[par];
     for (int64_t k = tid; k < nr; k += nth) { const int64_t q = P.recv_res_pos[k]; if (q >= 0) res[q] += __ldcg(slab + k); }
     const double* sj = slab + P.recv_jac_off;
-    for (int64_t k = tid; k < nj; k += nth) { const int64_t q = P.recv_jac_pos[k]; if (q >= 0) jac[q] += __ldcg(sj + k); }
+#pragma unroll 4
+    for (int64_t k = tid; k < nj; k += nth) { const int64_t q = __ldcs(P.recv_jac_pos + k); if (q >= 0) jac[q] += __ldcg(sj + k); }
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
@@ -433,7 +440,7 @@ bool HaloExchange::setup_p2p(std::string& err) {
   CU_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   int64_t most = 0;
   for (const P2PPeerDev& D : tab) most = std::max<int64_t>(most, std::max(D.n_send_res + D.n_send_jac, D.n_recv_res + D.n_recv_jac));
-  p2p_grid_ = (int)std::max<int64_t>(1, std::min<int64_t>(n_sm, (most + 1023) / 1024));   // <= one CTA per SM: all resident
+  p2p_grid_ = (int)std::max<int64_t>(1, std::min<int64_t>(n_sm, (most + 2047) / 2048));   // <= one CTA of 1024 threads per SM: all resident
   p2p_epoch_ = 0;
   CU_TRY(cudaDeviceSynchronize());
   p2p_ = true;
@@ -444,7 +451,7 @@ bool HaloExchange::sum_p2p(double* res, double* jac, cudaStream_t st, std::strin
   ++p2p_epoch_;
   launches_ = 0;
   if (p2p_active_ == 0) return true;
-  halo_p2p_kernel<<<p2p_grid_, 256, 0, st>>>((const P2PPeerDev*)p2p_peers_dev_, p2p_active_, p2p_epoch_, res, jac, p2p_counters_);
+  halo_p2p_kernel<<<p2p_grid_, 1024, 0, st>>>((const P2PPeerDev*)p2p_peers_dev_, p2p_active_, p2p_epoch_, res, jac, p2p_counters_);
   launches_ = 1;
   CU_TRY(cudaGetLastError());
   return true;

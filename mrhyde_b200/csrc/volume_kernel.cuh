@@ -230,9 +230,10 @@ struct ElemPre {
   double xv[DIM + 1][DIM];        // vertex 0 and its +xi, +eta, +zeta neighbours (Shards vertices 1, 3, 4)
 };
 
+// kreg: class-ring builds of the register-staged pipeline (MRH_JIT_PIPE) return the class values here instead of storing them
 template <int DIM, bool BOX>
 __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double (&r)[1 << DIM], const int cap,
-                                               double* __restrict__ st) {
+                                               double* __restrict__ st, double* __restrict__ kreg = nullptr) {
   const double (&u)[1 << DIM] = E.u;
   const double (&ut)[1 << DIM] = E.ut;
   typedef Q1Shape<DIM> S;
@@ -306,7 +307,11 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
       for (int g = 0; g < NGU; ++g) k += G[g] * MRH_LTAB(Stab)[g][jit_tab::rep[c]];
       kc[c] = k; mc[c] = 0.0;
       if (MRH_TRANSIENT(td)) { mc[c] = md * MRH_LTAB(Mtab)[jit_tab::rep[c]]; k = td.alpha_u * k + td.alpha_t * mc[c]; }
+#ifdef MRH_JIT_PIPE
+      kreg[c] = k;
+#else
       st[c * cap] = k;
+#endif
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i)
@@ -538,6 +543,20 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 #pragma unroll
   for (int i = 0; i < NV; ++i) st[(MRH_STAGE_K(NT) + i) * cap] = r[i];
 }
+
+#ifdef MRH_JIT_PIPE
+// Class ring, register-staged: the NC class values and the NV residual entries of one element (plans of axis-aligned boxes only)
+template <int DIM>
+__device__ __forceinline__ void thermal_element_class(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double (&out)[MRH_JIT_CLASS_NC + (1 << DIM)]) {
+  constexpr int NV = 1 << DIM, NC = MRH_JIT_CLASS_NC;
+  double r[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r[i] = 0.0;
+  thermal_affine<DIM, true>(P, E, r, 0, nullptr, out);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) out[NC + i] = r[i];
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // Phase 2: rows completed by this step.  A warp takes a BATCH of up to 32 rows that share one gather pattern,
@@ -966,7 +985,11 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   double* wbuf = ring + 2 * cap * MetricLayout<DIM>::STAGE + warp * PULL_WARP_DOUBLES;
 #else
   constexpr int MDIM = 0;
+#ifdef MRH_JIT_CAP
+  constexpr int cap = MRH_JIT_CAP;
+#else
   const int cap = C.cap;
+#endif
   const int slot_doubles = cap * (MRH_STAGE_K(S::NT) + S::NV);
   double* wbuf = ring + ((2 * slot_doubles + 1) & ~1) + warp * PULL_WARP_DOUBLES;   // 16-byte aligned (bulk copies read it)
 #endif
@@ -993,6 +1016,82 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     while (clock64() - t0 < ticks) {}
   }
 #endif
+#ifdef MRH_JIT_PIPE
+  // Register-staged pipeline (class ring).  Per warp and step s:   P(s) = pull of the rows step s completes,  E(s+1) = element work of
+  // the next step with its NC + NV staged values kept in REGISTERS;  then  barrier | store E(s+1) into the slot step s-1 occupied |
+  // barrier.  P(s) and E(s+1) are independent -- P reads the slots of steps s and s-1, E reads global memory only -- so a warp runs
+  // them back to back without a barrier in between, and even / odd warps run them in opposite order: at any time some warps of the
+  // CTA are in the FP64-heavy element code and the others in the shared-memory / store-heavy pull, instead of all warps being in
+  // the same phase (the two-barrier loop below).  Inputs: connectivity two steps ahead, state / vertices one step ahead.
+  {
+    constexpr int NST = MRH_JIT_CLASS_NC + S::NV;
+    int4 sr = __ldg(reinterpret_cast<const int4*>(C.steps + s0));
+    int4 sr1 = sr, sr2 = sr;
+    if (s0 + 1 < s1) sr1 = __ldg(reinterpret_cast<const int4*>(C.steps + s0 + 1));
+    if (s0 + 2 < s1) sr2 = __ldg(reinterpret_cast<const int4*>(C.steps + s0 + 2));
+    ElemPre<DIM> E;
+    double stg[NST];
+    if (tid < sr.y) {
+      elem_stage1<DIM>(P, sr.x + tid, E); elem_stage2<DIM>(P, E);
+      thermal_element_class<DIM>(P, E, stg);
+#pragma unroll
+      for (int m = 0; m < NST; ++m) ring[m * cap + tid] = stg[m];
+    }
+    if (s0 + 1 < s1 && tid < sr1.y) { elem_stage1<DIM>(P, sr1.x + tid, E); elem_stage2<DIM>(P, E); }
+    ElemPre<DIM> Nx;   // connectivity of step s + 2
+    if (s0 + 2 < s1 && tid < sr2.y) elem_stage1<DIM>(P, sr2.x + tid, Nx);
+    BatchRegs Rn;      // this warp's first batch of the next step
+    Rn.hdr = make_int4(0, 0, 0, 0); Rn.rec = make_int2(0, 0); Rn.base = 0;
+    if (warp < sr.w) Rn = fetch_batch(C, P.graph, sr.z + warp, lane);
+    __syncthreads();
+    for (int s = s0; s < s1; ++s) {
+      const int batch_begin = sr.z, n_batches = sr.w;
+      const int parity = (s - s0) & 1;
+      const bool more = (s + 1 < s1) && (tid < sr1.y);        // this thread has an element in step s + 1 (inputs in E)
+      const bool more2 = (s + 2 < s1) && (tid < sr2.y);       // ... and in step s + 2 (connectivity in Nx)
+      int4 sr3 = sr2;
+      if (s + 3 < s1) sr3 = ldg_pinned_v4(C.steps + s + 3);
+      BatchRegs R = Rn;   // requested one step ahead
+      if (s + 1 < s1) { Rn.hdr = make_int4(0, 0, 0, 0); Rn.rec = make_int2(0, 0); Rn.base = 0; if (warp < sr1.w) Rn = fetch_batch(C, P.graph, sr1.z + warp, lane); }
+      auto pull = [&]() {
+        switch (mode) {
+          case 1: pull_step<MDIM, true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+          case 2: pull_step<MDIM, false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+          case 3: pull_step<MDIM, true, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+          case 5: pull_step<MDIM, true, false, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+          case 6: pull_step<MDIM, false, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+          case 7: pull_step<MDIM, true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+          default: break;
+        }
+      };
+      auto element = [&]() {
+        if (more) thermal_element_class<DIM>(P, E, stg);
+        if (more2) {   // the next step's connectivity has arrived: request its state / vertices, then the connectivity after it
+          E.ecls = Nx.ecls;
+#pragma unroll
+          for (int i = 0; i < (1 << DIM); ++i) { E.cn[i] = Nx.cn[i]; E.ld[i] = Nx.ld[i]; }
+          elem_stage2<DIM>(P, E);
+        }
+        if ((s + 3 < s1) && (tid < sr3.y)) elem_stage1<DIM>(P, sr3.x + tid, Nx);
+      };
+#if MRH_JIT_PIPE == 2
+      // one copy of each body in the instruction stream: the order is a run-time property of the warp
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) { if (((warp ^ h) & 1) == 0) pull(); else element(); }
+#else
+      pull(); element();
+#endif
+      __syncthreads();   // every pull of step s is done: the slot of step s - 1 is free
+      if (more) {
+        double* slot = ring + (parity ^ 1) * slot_doubles;
+#pragma unroll
+        for (int m = 0; m < NST; ++m) slot[m * cap + tid] = stg[m];
+      }
+      sr = sr1; sr1 = sr2; sr2 = sr3;
+      __syncthreads();   // step s + 1 is staged
+    }
+  }
+#else
   int4 sr = __ldg(reinterpret_cast<const int4*>(C.steps + s0));
   int4 sr_next = sr;
   if (s0 + 1 < s1) sr_next = __ldg(reinterpret_cast<const int4*>(C.steps + s0 + 1));
@@ -1060,6 +1159,7 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     sr = sr_next; sr_next = sr_next2;
     __syncthreads();  // the next step overwrites the slot this pull read as "previous"
   }
+#endif  // MRH_JIT_PIPE
 #if defined(MRH_JIT_ROWBUF) && MRH_JIT_FLUSH == 2
   mrh_bulk_wait_read();   // shared memory must outlive the bulk copies that read it
 #endif

@@ -70,12 +70,19 @@ class ThermalBrick:
     global mesh is `nranks` bricks stacked along the last axis (weak scaling, Zprocs = nranks) and this
     object holds rank `rank`'s slab: owned rows first, the ghost plane (owned by rank+1) last."""
 
-    def __init__(self, dim, n, device=0, rank=0, nranks=1, functions=None, options=None):
+    def __init__(self, dim, n, device=0, rank=0, nranks=1, functions=None, options=None, perturb=0.0):
         self.dim, self.n, self.rank, self.nranks = dim, [int(v) for v in n[:dim]], rank, nranks
         ns = NodeSlab(dim, n, rank, nranks)
         for k in ("nodes", "conn", "n_rows", "n_owned", "row_gids", "rowptr", "colind", "col_gids", "is_fixed"):
             setattr(self, k, getattr(ns, k))
         conn = self.conn
+        if perturb:
+            # general (non-parallelepiped) cells: every node not on the global boundary moves by up to perturb * h per axis; the
+            # displacement is a function of the global node id, so the replicas of a shared node agree across ranks
+            h = np.array([1.0 / v for v in self.n]); h[dim - 1] /= nranks
+            g = self.row_gids.astype(np.float64)
+            d = np.stack([np.modf(np.sin(g * (12.9898 + 7.233 * a)) * 43758.5453)[0] for a in range(dim)], axis=1)
+            self.nodes = self.nodes + (self.is_fixed == 0)[:, None] * (perturb * h)[None, :] * d
         nodes = self.nodes
         self.lids = conn  # Q1 scalar field: local dof id == local node id (owned planes first by construction)
         self.n_elem = conn.shape[0]
@@ -226,30 +233,36 @@ def q2_reference_3d():
 
 
 def q2_node_graph(n):
-    """CSR pattern of the nodal hex-Q2 operator on an n^3 brick ((2n+1)^3 lattice nodes): a lattice node couples to every node of
-    the elements that contain it, i.e. per axis the index range [I-2, I+2] for an even (vertex-like) index and [I-1, I+1] for an odd one."""
-    M = 2 * n + 1
-    ax = np.arange(M)
-    lo = np.where(ax % 2 == 0, np.maximum(ax - 2, 0), ax - 1)
-    hi = np.where(ax % 2 == 0, np.minimum(ax + 2, M - 1), ax + 1)
-    cnt1 = hi - lo + 1
-    K, J, I = np.meshgrid(ax, ax, ax, indexing="ij")
-    cnt = (cnt1[I] * cnt1[J] * cnt1[K]).ravel().astype(np.int64)
-    rowptr = np.zeros(M ** 3 + 1, dtype=np.int64)
+    """CSR pattern of the nodal hex-Q2 operator on a brick of n = (nx, ny, nz) elements (an int means a cube): a lattice node couples to
+    every node of the elements that contain it, i.e. per axis the index range [I-2, I+2] for an even (vertex-like) index and
+    [I-1, I+1] for an odd one."""
+    nn = [int(n)] * 3 if np.isscalar(n) else [int(v) for v in n]
+    M = [2 * v + 1 for v in nn]
+    lo, hi, cnt1 = [], [], []
+    for d in range(3):
+        ax = np.arange(M[d])
+        lo.append(np.where(ax % 2 == 0, np.maximum(ax - 2, 0), ax - 1))
+        hi.append(np.where(ax % 2 == 0, np.minimum(ax + 2, M[d] - 1), ax + 1))
+        cnt1.append(hi[d] - lo[d] + 1)
+    K, J, I = np.meshgrid(np.arange(M[2]), np.arange(M[1]), np.arange(M[0]), indexing="ij")
+    Iv, Jv, Kv = I.ravel(), J.ravel(), K.ravel()
+    cnt = (cnt1[0][Iv] * cnt1[1][Jv] * cnt1[2][Kv]).astype(np.int64)
+    rowptr = np.zeros(M[0] * M[1] * M[2] + 1, dtype=np.int64)
     np.cumsum(cnt, out=rowptr[1:])
     colind = np.empty(int(rowptr[-1]), dtype=np.int32)
     # rows grouped by their (cx, cy, cz) extents so that each group is a dense block
-    Iv, Jv, Kv = I.ravel(), J.ravel(), K.ravel()
     for cz in (3, 4, 5):
         for cy in (3, 4, 5):
             for cx in (3, 4, 5):
-                sel = np.nonzero((cnt1[Iv] == cx) & (cnt1[Jv] == cy) & (cnt1[Kv] == cz))[0]
+                sel = np.nonzero((cnt1[0][Iv] == cx) & (cnt1[1][Jv] == cy) & (cnt1[2][Kv] == cz))[0]
                 if len(sel) == 0:
                     continue
                 dz, dy, dx = np.meshgrid(np.arange(cz), np.arange(cy), np.arange(cx), indexing="ij")
-                cols = ((lo[Iv[sel]][:, None] + dx.ravel()[None, :]) + M * ((lo[Jv[sel]][:, None] + dy.ravel()[None, :]) + M * (lo[Kv[sel]][:, None] + dz.ravel()[None, :])))
-                dst = rowptr[sel][:, None] + np.arange(cx * cy * cz)[None, :]
-                colind[dst.ravel()] = cols.ravel().astype(np.int32)
+                for a in range(0, len(sel), 1 << 18):   # bounded temporaries
+                    ss = sel[a:a + (1 << 18)]
+                    cols = ((lo[0][Iv[ss]][:, None] + dx.ravel()[None, :]) + M[0] * ((lo[1][Jv[ss]][:, None] + dy.ravel()[None, :]) + M[1] * (lo[2][Kv[ss]][:, None] + dz.ravel()[None, :])))
+                    dst = rowptr[ss][:, None] + np.arange(cx * cy * cz)[None, :]
+                    colind[dst.ravel()] = cols.ravel().astype(np.int32)
     return rowptr, colind
 
 
@@ -258,27 +271,54 @@ class ElasticityQ2Brick:
     lambda = mu = 1, all-boundary strong Dirichlet, on an n^3 inline brick (Hex8 geometry: the cell topology stays
     Hexahedron_8, discretizationInterface_basis.hpp:244-252).  One rank."""
 
-    def __init__(self, n, device=0, options=None, physics="linearelasticity"):
-        self.n = n
-        nodes, conn = im.brick(3, [n, n, n])
+    def __init__(self, n, device=0, options=None, physics="linearelasticity", rank=0, nranks=1, nz=None):
+        """nranks > 1: the n x n x (nz * nranks) brick is cut into z-slabs of nz element layers (Zprocs = nranks).  Rank `rank` numbers
+        the lattice nodes of its slab x-fastest, so the owned planes come first and the top plane (owned by rank + 1) last as ghost
+        rows; the two lattice planes under a non-zero rank are column-only ghosts of its bottom plane."""
+        self.n, self.rank, self.nranks = n, rank, nranks
+        nz = n if nz is None else int(nz)
+        nzt = nz * nranks
+        nodes, conn = im.brick(3, [n, n, nz], [0.0, 0.0, float(rank)], [1.0, 1.0, float(rank + 1)])
+        nodes[:, 2] /= float(nranks)
         self.nodes, self.conn = nodes, conn
         nvar = 3 if physics == "linearelasticity" else 1      # "thermal": scalar hex-Q2 (thermal/2D_verification_highorder's 3-D analogue)
-        M = 2 * n + 1
-        k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+        M, Mz = 2 * n + 1, 2 * nz + 1
+        k, j, i = np.meshgrid(np.arange(nz), np.arange(n), np.arange(n), indexing="ij")
         base = (2 * i + M * (2 * j + M * 2 * k)).ravel().astype(np.int64)
         o = np.arange(27)
         offs = (o % 3) + M * ((o // 3) % 3) + M * M * (o // 9)
         lat = base[:, None] + offs[None, :]                                                      # (E, 27) lattice node of every basis function
         self.lids = np.ascontiguousarray((lat[:, :, None] * nvar + np.arange(nvar)[None, None, :]).reshape(len(base), 27 * nvar).astype(np.int32))
-        rp, ci = q2_node_graph(n)
-        self.rowptr, self.colind = _expand_graph(rp, ci, nvar) if nvar > 1 else (rp, ci)
-        self.n_rows = nvar * M ** 3
-        self.n_owned = self.n_rows
-        idx = np.arange(M ** 3)
-        li, lj, lk = idx % M, (idx // M) % M, idx // (M * M)
-        bnd = (li == 0) | (li == M - 1) | (lj == 0) | (lj == M - 1) | (lk == 0) | (lk == M - 1)
+        plane = M * M
+        n_nodes = plane * Mz
+        if rank == 0:
+            rp, ci = q2_node_graph((n, n, nz))
+            node_gids_cols = np.arange(n_nodes, dtype=np.int64)
+        else:
+            # box extended by one element layer (two lattice planes) below: ext id = local id + 2 planes; the rows of those planes are
+            # dropped and their ids become column-only ghosts (local column ids >= n_nodes)
+            rpe, cie = q2_node_graph((n, n, nz + 1))
+            a = int(rpe[2 * plane])
+            rp = rpe[2 * plane:] - a
+            ci = cie[a:].astype(np.int64) - 2 * plane
+            ci = np.where(ci < 0, n_nodes + (ci + 2 * plane), ci)
+            rows = np.repeat(np.arange(n_nodes), np.diff(rp))
+            order = np.lexsort((ci, rows))
+            ci = ci[order].astype(np.int32)
+            node_gids_cols = np.concatenate([np.arange(n_nodes, dtype=np.int64), np.arange(2 * plane, dtype=np.int64) - 2 * plane])
+        node_gid0 = rank * 2 * nz * plane                       # global lattice id of local node 0
+        node_gids_cols = node_gids_cols + node_gid0
+        self.rowptr, self.colind = _expand_graph(rp, ci, nvar) if nvar > 1 else (rp.astype(np.int64), ci.astype(np.int32))
+        self.n_rows = nvar * n_nodes
+        self.n_owned = self.n_rows if rank == nranks - 1 else nvar * (n_nodes - plane)
+        self.col_gids = (node_gids_cols[:, None] * nvar + np.arange(nvar)[None, :]).reshape(-1)
+        self.row_gids = self.col_gids[: self.n_rows]
+        idx = np.arange(n_nodes)
+        li, lj, lk = idx % M, (idx // M) % M, idx // plane + rank * 2 * nz
+        Mzt = 2 * nzt + 1
+        bnd = (li == 0) | (li == M - 1) | (lj == 0) | (lj == M - 1) | (lk == 0) | (lk == Mzt - 1)
         self.is_fixed = np.repeat(bnd.astype(np.uint8), nvar)
-        self.lattice = np.stack([li, lj, lk], axis=1) / float(M - 1)
+        self.lattice = np.stack([li / float(M - 1), lj / float(M - 1), lk / float(Mzt - 1)], axis=1)
         self.n_elem = conn.shape[0]
         self.nnz = int(self.rowptr[-1])
         pts, wts, val, grad = q2_reference_3d()
@@ -300,7 +340,9 @@ class ElasticityQ2Brick:
         x = self.lattice
         nvar = self.n_rows // x.shape[0]
         u = np.stack([np.prod(np.sin((v + 1) * np.pi * x), axis=1) for v in range(nvar)], axis=1).reshape(-1)
-        return u + 1e-3 * np.random.default_rng(seed).uniform(-1.0, 1.0, size=self.n_rows)
+        if self.nranks == 1:
+            return u + 1e-3 * np.random.default_rng(seed).uniform(-1.0, 1.0, size=self.n_rows)
+        return u + 1e-3 * np.modf(np.sin(self.row_gids * 12.9898) * 43758.5453)[0]   # same values on shared rows of every rank
 
     def algorithmic_bytes(self):
         return 4.0 * self.lids.shape[1] * self.n_elem + 24.0 * self.nodes.shape[0] + 16.0 * self.n_rows + 8.0 * self.nnz
@@ -336,15 +378,103 @@ def hcurl_hdiv_reference_3d():
     return pts, wts, (ev, ec), (fv, fd)
 
 
+def slab_partition(lids_mine, lids_below, lids_above, fixed_of_gid=None):
+    """Overlapped numbering of one rank of an element-wise z-slab partition from GLOBAL element dof lists (SURVEY 8(e);
+    discretizationInterface_dof.hpp:129-137: owned dofs first, then ghosts): `lids_mine` are the rank's elements, `lids_below` the
+    element layer under the slab (rank - 1's top layer, or None) and `lids_above` the layer over it (rank + 1's first layer, or None).
+    A dof shared with the rank above is a GHOST row here (owned there); dofs that only the layer below touches are column-only
+    ghosts of the owned interface rows.  Returns dict(lids local, n_rows, n_owned, col_gids, rowptr, colind, is_fixed)."""
+    mine = np.unique(lids_mine)
+    ghost_mask = np.isin(mine, np.unique(lids_above)) if lids_above is not None and len(lids_above) else np.zeros(len(mine), dtype=bool)
+    owned, ghost = mine[~ghost_mask], mine[ghost_mask]
+    colonly = np.setdiff1d(np.unique(lids_below), mine) if lids_below is not None and len(lids_below) else np.zeros(0, dtype=mine.dtype)
+    col_gids = np.concatenate([owned, ghost, colonly]).astype(np.int64)
+    order = np.argsort(col_gids, kind="stable")
+    sorted_g = col_gids[order]
+
+    def g2l(a):
+        return order[np.searchsorted(sorted_g, a)].astype(np.int32)
+    n_rows, n_owned = len(owned) + len(ghost), len(owned)
+    local = g2l(lids_mine)
+    ext = local if len(colonly) == 0 and (lids_below is None or not len(lids_below)) else np.concatenate([local, g2l(lids_below)], axis=0)
+    rp, ci = im.graph_from_lids(ext, len(col_gids))
+    rp, ci = rp[: n_rows + 1], ci[: rp[n_rows]]
+    fixed = np.zeros(n_rows, dtype=np.uint8) if fixed_of_gid is None else fixed_of_gid(col_gids[:n_rows]).astype(np.uint8)
+    return dict(lids=np.ascontiguousarray(local), n_rows=n_rows, n_owned=n_owned, col_gids=col_gids, row_gids=col_gids[:n_rows],
+                rowptr=rp.astype(np.int64), colind=ci.astype(np.int32), is_fixed=fixed)
+
+
+def maxwell_lids(n, nzt, k0, k1):
+    """Global dof lists of the elements of layers [k0, k1) of an n x n x nzt brick: E edges (x-, y-, z-directed lattices), then B
+    faces (x-, y-, z-normal lattices)."""
+    if k1 <= k0:
+        return np.zeros((0, 18), dtype=np.int64)
+    k, j, i = [a.ravel().astype(np.int64) for a in np.meshgrid(np.arange(k0, k1), np.arange(n), np.arange(n), indexing="ij")]
+    n1, nz1 = n + 1, nzt + 1
+    nxe, nye, nze = n * n1 * nz1, n1 * n * nz1, n1 * n1 * nzt
+    cols = []
+    for d in range(12):
+        if d < 4:      # x-directed: d = j + 2k
+            jj, kk = j + (d % 2), k + (d // 2)
+            cols.append(i + n * (jj + n1 * kk))
+        elif d < 8:    # y-directed: d-4 = i + 2k
+            ii, kk = i + ((d - 4) % 2), k + ((d - 4) // 2)
+            cols.append(nxe + ii + n1 * (j + n * kk))
+        else:          # z-directed: d-8 = i + 2j
+            ii, jj = i + ((d - 8) % 2), j + ((d - 8) // 2)
+            cols.append(nxe + nye + ii + n1 * (jj + n1 * k))
+    ne_dofs = nxe + nye + nze
+    nxf, nyf = n1 * n * nzt, n * n1 * nzt
+    for d in range(6):
+        dr, s_ = d // 2, d % 2
+        ii, jj, kk = i + (s_ if dr == 0 else 0), j + (s_ if dr == 1 else 0), k + (s_ if dr == 2 else 0)
+        if dr == 0:
+            cols.append(ne_dofs + ii + n1 * (jj + n * kk))
+        elif dr == 1:
+            cols.append(ne_dofs + nxf + ii + n * (jj + n1 * kk))
+        else:
+            cols.append(ne_dofs + nxf + nyf + ii + n * (jj + n * kk))
+    return np.stack(cols, axis=1)
+
+
 class MaxwellBrick:
     """BASELINE configs[4]: 3-D Maxwell, lowest-order HCURL E (12 edge dofs) + HDIV B (6 face dofs) per hex, eps = mu = n = 1,
-    sigma = 0, on an n^3 inline brick; transient stages are supplied per call.  DOF numbering: E edges (x-, y-, z-directed
-    lattices), then B faces (x-, y-, z-normal lattices), all orientation signs +1 on a lexicographic brick.  One rank."""
+    sigma = 0, on an inline brick; transient stages are supplied per call.  DOF numbering: E edges (x-, y-, z-directed
+    lattices), then B faces (x-, y-, z-normal lattices), all orientation signs +1 on a lexicographic brick.  With nranks > 1 the
+    n x n x (nz * nranks) brick is cut into z-slabs of nz layers (`slab_partition`): rank `rank` holds its owned edge / face dofs
+    first, the dofs of its top plane (owned by rank + 1) as ghost rows, and the layer below as column-only ghosts."""
 
-    def __init__(self, n, device=0, functions=None, options=None):
-        self.n = n
-        nodes, conn = im.brick(3, [n, n, n])
+    def __init__(self, n, device=0, functions=None, options=None, rank=0, nranks=1, nz=None):
+        self.n, self.rank, self.nranks = n, rank, nranks
+        nz = n if nz is None else int(nz)
+        nzt = nz * nranks
+        if nranks > 1:
+            lo, hi = [0.0, 0.0, float(rank)], [1.0, 1.0, float(rank + 1)]
+            nodes, conn = im.brick(3, [n, n, nz], lo, hi)
+            nodes[:, 2] /= float(nranks)
+            k0 = rank * nz
+            part = slab_partition(maxwell_lids(n, nzt, k0, k0 + nz), maxwell_lids(n, nzt, k0 - 1, k0) if rank > 0 else None,
+                                  maxwell_lids(n, nzt, k0 + nz, k0 + nz + 1) if rank < nranks - 1 else None)
+            self.nodes, self.conn = nodes, conn
+            for key in ("lids", "n_rows", "n_owned", "col_gids", "row_gids", "rowptr", "colind", "is_fixed"):
+                setattr(self, key, part[key])
+            self.n_elem = conn.shape[0]
+            self.nnz = int(self.rowptr[-1])
+            self._finish(device, functions, options)
+            return
+        nodes, conn = im.brick(3, [n, n, nz])
         self.nodes, self.conn = nodes, conn
+        if nz != n:
+            self.lids = np.ascontiguousarray(maxwell_lids(n, nz, 0, nz).astype(np.int32))
+            self.n_rows = int(self.lids.max()) + 1
+            self.n_owned = self.n_rows
+            self.row_gids = self.col_gids = np.arange(self.n_rows, dtype=np.int64)
+            self.rowptr, self.colind = im.graph_from_lids(self.lids, self.n_rows)
+            self.is_fixed = np.zeros(self.n_rows, dtype=np.uint8)
+            self.n_elem = conn.shape[0]
+            self.nnz = int(self.rowptr[-1])
+            self._finish(device, functions, options)
+            return
         k, j, i = [a.ravel().astype(np.int64) for a in np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")]
         n1 = n + 1
         nxe, nye, nze = n * n1 * n1, n1 * n * n1, n1 * n1 * n
@@ -373,10 +503,15 @@ class MaxwellBrick:
         self.lids = np.ascontiguousarray(np.stack(cols, axis=1).astype(np.int32))
         self.n_rows = ne_dofs + nxf + nyf + n * n * n1
         self.n_owned = self.n_rows
+        self.row_gids = self.col_gids = np.arange(self.n_rows, dtype=np.int64)
         self.rowptr, self.colind = im.graph_from_lids(self.lids, self.n_rows)
         self.is_fixed = np.zeros(self.n_rows, dtype=np.uint8)
         self.n_elem = conn.shape[0]
         self.nnz = int(self.rowptr[-1])
+        self._finish(device, functions, options)
+
+    def _finish(self, device, functions, options):
+        nodes, conn = self.nodes, self.conn
         pts, wts, (ev, ec), (fv, fd) = hcurl_hdiv_reference_3d()
         offsets = np.full((2, 12), -1, dtype=np.int32)
         offsets[0, :] = np.arange(12)
@@ -392,7 +527,10 @@ class MaxwellBrick:
         self.plan.finalize()
 
     def state(self, seed=20261017):
-        return 0.3 * np.sin(1.0 + 0.7 * np.arange(self.n_rows) / self.n_rows) + 1e-3 * np.random.default_rng(seed).uniform(-1.0, 1.0, self.n_rows)
+        if self.nranks == 1:
+            return 0.3 * np.sin(1.0 + 0.7 * np.arange(self.n_rows) / self.n_rows) + 1e-3 * np.random.default_rng(seed).uniform(-1.0, 1.0, self.n_rows)
+        g = self.row_gids.astype(np.float64)   # a function of the global id: replicas of a shared row agree across ranks
+        return 0.3 * np.sin(1.0 + 0.7e-6 * g) + 1e-3 * np.modf(np.sin(g * 12.9898) * 43758.5453)[0]
 
     def algorithmic_bytes(self):
         return 4.0 * 18 * self.n_elem + 24.0 * self.nodes.shape[0] + 16.0 * self.n_rows + 8.0 * self.nnz

@@ -78,3 +78,33 @@ def test_maxwell_brick_matches_oracle(oracle_lib, product_lib):
     ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=0, A=[[0.5]], b=[1.0], c=[0.5], bdf=(1.0, -1.0), sol_prev=[up], sol_stage=[us])
     _same_assembly(pb, op, time=ts, oracle_kw=dict(sol_prev=[up], sol_stage=[us]))
     op.set_time(False)
+
+
+@pytest.mark.parametrize("kind", ["maxwell", "leq2"])
+def test_slab_partitions_reassemble_the_global_graph(product_lib, kind):
+    """Element-wise z-slab partitions of the edge / face lattices (Maxwell) and of the hex-Q2 node lattice: every global dof is owned
+    by exactly one rank, owned rows carry the global CSR row (through col_gids, column-only ghosts included), ghost rows come last,
+    and the strong-Dirichlet mask / state are functions of the global id (meshInterface_construct.hpp:143-160 element partition,
+    discretizationInterface_dof.hpp:129-137 owned-then-ghost numbering)."""
+    from mrhyde_b200.problems import ElasticityQ2Brick, MaxwellBrick
+    n, nz, world = (4, 2, 3) if kind == "maxwell" else (3, 2, 3)
+    make = (lambda **kw: MaxwellBrick(n, device=-1, **kw)) if kind == "maxwell" else (lambda **kw: ElasticityQ2Brick(n, device=-1, **kw))
+    g = make(nz=nz * world)
+    seen = np.zeros(g.n_rows, dtype=int)
+    for r in range(world):
+        p = make(rank=r, nranks=world, nz=nz)
+        assert p.n_owned == p.n_rows if r == world - 1 else p.n_owned < p.n_rows
+        seen[p.row_gids[: p.n_owned]] += 1
+        assert np.array_equal(p.is_fixed, g.is_fixed[p.row_gids])
+        for i in range(0, p.n_owned, 5):
+            gi = p.row_gids[i]
+            cols = np.sort(p.col_gids[p.colind[p.rowptr[i]:p.rowptr[i + 1]]])
+            assert np.array_equal(cols, g.colind[g.rowptr[gi]:g.rowptr[gi + 1]])
+        for i in range(p.n_owned, p.n_rows):      # ghost rows hold the couplings of this rank's elements only: a subset of the global row
+            gi = p.row_gids[i]
+            cols = p.col_gids[p.colind[p.rowptr[i]:p.rowptr[i + 1]]]
+            assert np.isin(cols, g.colind[g.rowptr[gi]:g.rowptr[gi + 1]]).all() and (p.colind[p.rowptr[i]:p.rowptr[i + 1]] < p.n_rows).all()
+        # the element dof lists address local rows, and map to the global lists of the same elements
+        e0 = r * nz * n * n
+        assert np.array_equal(p.row_gids[p.lids], g.lids[e0:e0 + p.n_elem].astype(np.int64))
+    assert (seen == 1).all()
