@@ -164,7 +164,7 @@ struct mrhyde_b200_plan {
 namespace {
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "scratch GB", "debug transient", "debug mode", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "scratch GB", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -265,7 +265,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
                                const int64_t (&n_class)[3], int metric_ng, int max_patterns, int pull_group,
-                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint) {
+                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint, bool prefetch2) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -279,6 +279,7 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   o += "#define MRH_JIT_ALL_CONST " + std::to_string(all_const) + "\n";
   o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
   if (late_stage1) o += "#define MRH_JIT_LATE_STAGE1 1\n";
+  if (prefetch2) o += "#define MRH_JIT_PREFETCH2 1   /* L2 prefetch of the next step's state / vertices before the pull */\n";
   if (early_stage2) o += "#define MRH_JIT_EARLY_STAGE2 1\n";
   if (literal_tables) o += "#define MRH_JIT_LITERAL_TABLES 1\n";
   o += "/*@stagger@*/\n";
@@ -735,7 +736,7 @@ std::vector<std::string> initial_function_names(const mrhyde_b200_plan* P, int v
   return {base};
 }
 
-FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side) {
+FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side, bool state_slots = false) {
   FunctionSet fs;
   // module defaults (thermal::defineFunctions, thermal.cpp:47-65), then user overrides
   if (P->physics == "thermal") {
@@ -764,6 +765,26 @@ FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side) {
     sol.push_back("div(" + v + ")");
   }
   fs.set_solution_fields(sol);
+  if (state_slots) {
+    // general path: the evaluator reads solution fields from slots v * NC + k (fields F[v][k] of general_physics.cuh), time
+    // derivatives of the values NVAR * NC further on.  HGRAD: value, grad x y z; HCURL: value x y z, curl x y z; HDIV: value x y z, div
+    std::map<std::string, int> slots;
+    const int NC = canonical_physics(P->physics) == "maxwell" ? 6 : 4, NCV = NC * (int)P->var_names.size();
+    for (size_t v = 0; v < P->var_names.size(); ++v) {
+      const std::string& nm = P->var_names[v];
+      const std::string& bt = P->bases[(size_t)P->var_basis[v]].type;
+      const int base = (int)v * NC;
+      if (bt == "HGRAD") {
+        slots[nm] = base; slots[nm + "_t"] = NCV + base;
+        for (int d = 0; d < 3; ++d) slots["grad(" + nm + ")" + comps[d]] = base + 1 + d;
+      } else if (bt == "HCURL" || bt == "HDIV") {
+        for (int d = 0; d < 3; ++d) { slots[nm + comps[d]] = base + d; slots[nm + "_t" + comps[d]] = NCV + base + d; }
+        if (bt == "HCURL") for (int d = 0; d < 3; ++d) slots["curl(" + nm + ")" + comps[d]] = base + 3 + d;
+        else slots["div(" + nm + ")"] = base + 3;
+      }
+    }
+    fs.set_solution_slots(slots);
+  }
   if (side) fs.set_scalar_fields({"x", "y", "z", "", "n[x]", "n[y]", "n[z]"});
   else fs.set_scalar_fields({"x", "y", "z"});
   // boundary data functions at side ip: "Dirichlet <var> <side>" / "Neumann <var> <side>"
@@ -1035,6 +1056,7 @@ void compile_functions(const FunctionSet& fs, const std::vector<std::string>& na
     if (!names[f].empty()) {
       const LongProgram lp = fs.compile_long(names[f]);
       r.is_const = lp.is_const ? 1 : 0; r.cval = lp.cval;
+      r.pad = lp.uses_state ? 1 : 0;   // reads a solution field: evaluated after the fields, differentiated in the Jacobian stages
       if (!lp.is_const) {
         r.begin = (int32_t)ops.size(); r.n = (int32_t)lp.op.size();
         ops.insert(ops.end(), lp.op.begin(), lp.op.end());
@@ -1119,7 +1141,7 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
   if ((int)fnames.size() != I.nfn) fail(MRHYDE_B200_ERR_INVALID, "general path: module function table out of step with the kernel");
   H.fn_op.clear(); H.fn_c.clear();
   {
-    FunctionSet fs = make_function_set(P, false);
+    FunctionSet fs = make_function_set(P, false, true);
     std::vector<std::string> names = fnames;
     names.resize(GEN_MAXFN);
     compile_functions(fs, names, H.fn, H.fn_op, H.fn_c);
@@ -1134,7 +1156,7 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
   H.sides.clear();
   int64_t inst = M.nelem;
   if (!P->bgroups.empty()) {
-    FunctionSet fss = make_function_set(P, true);
+    FunctionSet fss = make_function_set(P, true, true);
     for (auto& g : P->bgroups) {
       GenSideFamily S;
       S.sideset = g.sideset; S.local_side = g.local_side; S.nqs = g.nqp;
@@ -1183,6 +1205,14 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
     fail(MRHYDE_B200_ERR_INVALID, e.what());
   }
   H.epb_override = std::stoi(opt(P, "elements per cta", "0"));
+  {
+    // which build of the element kernel assembles Jacobians: tensor = field-direction derivatives + FP64 tensor-core contraction
+    // (single-basis HGRAD modules), lanes = one derivative lane per element dof (every module)
+    const std::string jm = opt(P, "jacobian", "auto");
+    if (jm != "auto" && jm != "tensor" && jm != "lanes") fail(MRHYDE_B200_ERR_INVALID, "option jacobian must be auto|tensor|lanes");
+    if (jm == "tensor" && !I.tensor) fail(MRHYDE_B200_ERR_UNSUPPORTED, "jacobian=tensor: the module's basis layout has no tensor-core build");
+    H.use_tensor = I.tensor && jm != "lanes";
+  }
   P->use_general = true;
   P->launches_per_assemble = 2 * (int)H.batches.size();
   for (auto& S : H.sides) if (S.active && !S.items.empty()) ++P->launches_per_assemble;
@@ -1469,6 +1499,13 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     bool sweep_ok = phys == "thermal" && P->nvars == 1 && B.type == "HGRAD" && B.order == 1 && B.card == NV && P->ndof_elem == NV && P->nqp == NV && !B.grad.empty() &&
                     !opt_bool(P, "include advection", false);
     for (int i = 0; sweep_ok && i < NV; ++i) if (P->offsets[i] != i) sweep_ok = false;
+    if (sweep_ok) {
+      // a coefficient that reads the solution (e.g. thermal diffusion: 1.0+T*T) needs derivative lanes through the function
+      // evaluation (functionManager_evaluate.hpp:59-229): the sweep kernel's collapsed Jacobian does not apply -> general path
+      FunctionSet probe = make_function_set(P, false, true);
+      for (const char* nm : {"thermal source", "thermal diffusion", "specific heat", "density"})
+        if (probe.compile_long(nm).uses_state) sweep_ok = false;
+    }
     if (want == "sweep" && !sweep_ok) fail(MRHYDE_B200_ERR_UNSUPPORTED, "kernel=sweep: the sweep kernel covers thermal, HGRAD order 1, 2-point Gauss rule, no advection only");
     if (want == "general" || !sweep_ok) { finalize_general(P, phys); return MRHYDE_B200_OK; }
   }
@@ -1580,8 +1617,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     for (int tr = 0; tr < 2; ++tr)
       P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
     const int pull_group = std::stoi(opt(P, "pull group", "8"));
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0)
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0);
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, opt_bool(P, "prefetch", true))
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, opt_bool(P, "prefetch", true));
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
@@ -1942,6 +1979,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
   std::vector<double> ej(compute_jacobian ? (size_t)H.n_inst * N * N : 0, 0.0), er(compute_residual ? (size_t)H.n_inst * N : 0, 0.0);
   GenParams Q;
   std::memset(&Q, 0, sizeof(Q));
+  Q.tensor = H.use_tensor ? 1 : 0;
   Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
   Q.orient = M.orient.empty() ? nullptr : M.orient.data();
   Q.sol = sol; Q.td = td;
@@ -1954,6 +1992,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
     Q.items = nullptr; Q.item_begin = 0; Q.item_end = M.nelem; Q.inst_base = 0;
     Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
     std::memcpy(Q.fn, H.fn, sizeof(Q.fn));
+    Q.fn_state = 0; for (int f = 0; f < GEN_MAXFN; ++f) if (Q.fn[f].pad && !Q.fn[f].is_const) Q.fn_state = 1;
     for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = 0; Q.bc_fn[v] = -1; }
     P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
   }
@@ -1966,6 +2005,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
       for (int d = 0; d < 3; ++d) { Q.tan_u[d] = S.tan_u[d]; Q.tan_v[d] = S.tan_v[d]; }
       for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = S.bc_type[v]; Q.bc_fn[v] = S.bc_fn[v]; }
       std::memcpy(Q.fn, S.fn, sizeof(Q.fn));
+      Q.fn_state = 0; for (int f = 0; f < GEN_MAXFN; ++f) if (Q.fn[f].pad && !Q.fn[f].is_const) Q.fn_state = 1;
       P->gen_host->emulate(true, Q, (int)((Q.item_end + Q.epb - 1) / Q.epb));
     }
   gen_pull_host(H, M, compute_jacobian ? ej.data() : nullptr, compute_residual ? er.data() : nullptr, P->accumulate, compute_residual ? res : nullptr,
@@ -2043,6 +2083,7 @@ int mrhyde_b200_plan_debug_emulate_initial(mrhyde_b200_plan* P, double time, dou
   std::vector<double> er((size_t)H.n_inst * (size_t)I.N, 0.0), zero((size_t)M.nrows, 0.0);
   GenParams Q;
   std::memset(&Q, 0, sizeof(Q));
+  Q.tensor = H.use_tensor ? 1 : 0;
   Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
   Q.orient = M.orient.empty() ? nullptr : M.orient.data();
   Q.sol = zero.data();
@@ -2072,6 +2113,7 @@ int mrhyde_b200_plan_debug_emulate_mass(mrhyde_b200_plan* P, const double* mass_
   std::vector<double> ej((size_t)H.n_inst * N * N, 0.0), zero((size_t)M.nrows, 0.0);
   GenParams Q;
   std::memset(&Q, 0, sizeof(Q));
+  Q.tensor = H.use_tensor ? 1 : 0;
   Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
   Q.orient = M.orient.empty() ? nullptr : M.orient.data();
   Q.sol = zero.data();
@@ -2102,6 +2144,7 @@ int mrhyde_b200_plan_debug_emulate_apply_mass(mrhyde_b200_plan* P, const double*
   std::vector<double> er((size_t)H.n_inst * (size_t)I.N, 0.0);
   GenParams Q;
   std::memset(&Q, 0, sizeof(Q));
+  Q.tensor = H.use_tensor ? 1 : 0;
   Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
   Q.orient = M.orient.empty() ? nullptr : M.orient.data();
   Q.sol = x;

@@ -195,7 +195,13 @@ int FunctionSet::build(const std::string& expr, std::vector<Node>& nodes, std::s
   nodes.emplace_back();
   // 1. solution fields of the workset (AD data): a coefficient that depends on the state
   for (auto& f : soln_fields_)
-    if (expr == f) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "solution-dependent coefficient '" + expr + "' has no device kernel in this build");
+    if (expr == f) {
+      auto slot = soln_slots_.find(expr);
+      if (slot == soln_slots_.end())
+        throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "solution-dependent coefficient '" + expr + "' has no device kernel in this build");
+      nodes[me].kind = Node::VAR; nodes[me].var = EXPR_STATE0 + slot->second;   // functionManager_create.hpp: a workset solution field (AD data)
+      return me;
+    }
   // 2. scalar fields of the workset (x, y, z; n[x].. on sides)
   for (size_t j = 0; j < scalar_fields_.size(); ++j)
     if (!scalar_fields_[j].empty() && expr == scalar_fields_[j]) { nodes[me].kind = Node::VAR; nodes[me].var = (int)j; return me; }
@@ -323,6 +329,9 @@ ExprProgram FunctionSet::compile(const std::string& name) const {
     p.op[p.n] = op; p.c[p.n] = c; ++p.n;
   };
   emit(nodes, root, push_op, depth, maxdepth);
+  for (int i = 0; i < p.n; ++i)
+    if ((p.op[i] == OP_PUSHV || (p.op[i] >= OP_ADDV && p.op[i] <= OP_DIVV)) && (int)p.c[i] >= EXPR_STATE0)
+      throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "solution-dependent coefficient '" + name + "' needs the general path");
   p.op[p.n] = OP_END;
   if (maxdepth > EXPR_MAXSTACK) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression nests too deeply for the device evaluator: " + name);
   return p;
@@ -476,6 +485,8 @@ LongProgram FunctionSet::compile_long(const std::string& name) const {
   auto push_op = [&](uint8_t op, double c) { p.op.push_back(op); p.c.push_back(c); };
   emit(nodes, root, push_op, depth, maxdepth);
   if (maxdepth > 16) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression nests too deeply for the device evaluator: " + name);
+  for (size_t i = 0; i < p.op.size(); ++i)
+    if ((p.op[i] == OP_PUSHV || (p.op[i] >= OP_ADDV && p.op[i] <= OP_DIVV)) && (int)p.c[i] >= EXPR_STATE0) p.uses_state = true;
   return p;
 }
 

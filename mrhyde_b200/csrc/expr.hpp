@@ -33,6 +33,7 @@ struct ExprError : std::runtime_error {
 // Variable-length program for the general kernels (bytecode kept in global memory): same ops, no length limit, stack <= 16.
 struct LongProgram {
   bool is_const = false;
+  bool uses_state = false;   // reads a solution field (variable slots >= EXPR_STATE0): its value depends on the state
   double cval = 0.0;
   std::vector<uint8_t> op;
   std::vector<double> c;
@@ -46,6 +47,9 @@ class FunctionSet {
   // names of fields the workset would provide (solution fields); referencing one is "unsupported"
   void set_solution_fields(const std::vector<std::string>& f) { soln_fields_.assign(f.begin(), f.end()); }
   void set_scalar_fields(const std::vector<std::string>& f) { scalar_fields_ = f; }  // index = variable slot
+  // solution fields the evaluator can read (general path): name -> slot; the leaf becomes variable EXPR_STATE0 + slot.  Fields that are
+  // listed by set_solution_fields but have no slot stay "unsupported" (the sweep kernel's fixed-size programs)
+  void set_solution_slots(const std::map<std::string, int>& m) { soln_slots_ = m; }
   ExprProgram compile(const std::string& name) const;
   LongProgram compile_long(const std::string& name) const;
   // The same tree as a C++ expression in x, y, z, t (and nx, ny, nz on sides) for the plan-specialised (NVRTC)
@@ -75,6 +79,7 @@ class FunctionSet {
   static std::string gen_chain(const Node& n, const std::function<std::string(int)>& child);
   std::map<std::string, std::string> funcs_;
   std::vector<std::string> soln_fields_;
+  std::map<std::string, int> soln_slots_;
   std::vector<std::string> scalar_fields_ = {"x", "y", "z"};
 };
 

@@ -12,30 +12,39 @@ namespace mrhyde_b200 {
 
 namespace {
 
-template <class Phys, int NQ, int NQS, int K, int MAXT, int MINB>
+template <class Phys, int NQ, int NQS, int K, int MAXT, int MINB, bool TCK>
 const char* launch_entry(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream) {
   static size_t attr[2][64] = {};   // opt-in shared memory already granted, per (volume | side, device)
   int devid = 0;
   cudaGetDevice(&devid);
   devid &= 63;
   if (threads > MAXT) return "general element kernel: more threads per CTA than the instantiation's launch bounds";
-  const void* fn = side ? (const void*)gen_element_kernel<Phys, NQS, K, true, MAXT, MINB> : (const void*)gen_element_kernel<Phys, NQ, K, false, MAXT, MINB>;
+  const void* fn = side ? (const void*)gen_element_kernel<Phys, NQS, K, true, MAXT, MINB, TCK> : (const void*)gen_element_kernel<Phys, NQ, K, false, MAXT, MINB, TCK>;
   if (smem > 48 * 1024 && smem > attr[side ? 1 : 0][devid]) {
     const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     attr[side ? 1 : 0][devid] = smem;
   }
-  if (side) gen_element_kernel<Phys, NQS, K, true, MAXT, MINB><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
-  else gen_element_kernel<Phys, NQ, K, false, MAXT, MINB><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
+  if (side) gen_element_kernel<Phys, NQS, K, true, MAXT, MINB, TCK><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
+  else gen_element_kernel<Phys, NQ, K, false, MAXT, MINB, TCK><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+template <class Phys, int NQ, int NQS, int K, int MAXT, int MINB, int MAXT_L, int MINB_L>
+GenDeviceKernels make_device_entry(const char* name, int dim, int order) {
+  GenDeviceKernels k;
+  k.info = gen_make_info<Phys, NQ, NQS, K>(name, dim, order, MAXT, MINB, MAXT_L, MINB_L);
+  k.launch = &launch_entry<Phys, NQ, NQS, K, MAXT_L, MINB_L, false>;
+  k.launch_tc = nullptr;
+  if constexpr (GenLayout<Phys, NQ>::TC) k.launch_tc = &launch_entry<Phys, NQ, NQS, K, MAXT, MINB, true>;
+  return k;
 }
 
 std::vector<GenDeviceKernels>& device_table() {
   static std::vector<GenDeviceKernels> T;
   if (T.empty()) {
-#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS, MAXT, MINB) \
-  T.push_back(GenDeviceKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER, MAXT, MINB), &launch_entry<PHYS, NQ, NQS, K, MAXT, MINB>});
+#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS, MAXT, MINB, MAXT_L, MINB_L) T.push_back(make_device_entry<PHYS, NQ, NQS, K, MAXT, MINB, MAXT_L, MINB_L>(NAME, DIM, ORDER));
     MRH_GEN_LIST(X)
 #undef X
   }
@@ -215,7 +224,7 @@ GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t*
   // element-local dof to that index and the contribution list / position tables are permuted to match.
   std::vector<int> kperm(N);
   for (size_t i = 0; i < N; ++i) kperm[i] = (int)i;
-  if (H.info.tensor)
+  if (H.use_tensor)
     for (int v = 0; v < H.info.nvars; ++v)
       for (int i = 0; i < H.info.card[0]; ++i) kperm[(size_t)H.off[v][i]] = v * H.info.card[0] + i;
   std::vector<int32_t> cslot(H.contrib.size()), cpos(H.contrib.size());
@@ -225,14 +234,14 @@ GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t*
     cpos[p] = (int32_t)((int64_t)H.pos_id[(size_t)inst] * (int64_t)N + i);
   }
   std::vector<uint16_t> pos_dev;
-  if (H.info.tensor) {
+  if (H.use_tensor) {
     pos_dev.resize(H.pos_tab.size());
     const size_t ntab = H.pos_tab.size() / (N * N);
     for (size_t t = 0; t < ntab; ++t)
       for (size_t r = 0; r < N; ++r)
         for (size_t c = 0; c < N; ++c) pos_dev[(t * N + (size_t)kperm[r]) * N + (size_t)kperm[c]] = H.pos_tab[(t * N + r) * N + c];
   }
-  const std::vector<uint16_t>& pos_up = H.info.tensor ? pos_dev : H.pos_tab;
+  const std::vector<uint16_t>& pos_up = H.use_tensor ? pos_dev : H.pos_tab;
   const size_t n_scratch = (size_t)gen_scratch_instances(H);
   bool ok = D->row_order.upload(H.row_order, tot, err) && D->contrib.upload(cslot, tot, err) && D->contrib_pos.upload(cpos, tot, err) && D->contrib_ptr.upload(H.contrib_ptr, tot, err) &&
             D->pos.upload(pos_up, tot, err) && D->geo_N.upload(H.geo_N, tot, err) && D->geo_dN.upload(H.geo_dN, tot, err) &&
@@ -254,15 +263,16 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
                     const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
                     bool volume, bool boundary, void* stream, GenLaunchStats* stats, int pull_mass_mode, const double* mass_wts);
 
-static int pick_epb(const GenKernelInfo& I, bool side, int64_t n_items, int epb_override) {
+static int pick_epb(const GenKernelInfo& I, bool tensor, bool side, int64_t n_items, int epb_override) {
   // as many elements per CTA as the launch bounds allow, while MINB CTAs still fit the SM's shared memory
   const int tpe = I.tpe;
   const int sd = side ? I.smem_doubles_side : I.smem_doubles_volume;
-  const size_t smem_cap = (size_t)(220 * 1024) / (size_t)std::max(1, I.min_blocks);
-  int epb = std::max(1, I.max_threads / tpe);
-  if (I.tensor) epb = 16;   // tensor-core kernels: any thread count serves any element count (work items are strided over the CTA)
+  const int max_threads = tensor ? I.tc_max_threads : I.max_threads;
+  const size_t smem_cap = (size_t)(220 * 1024) / (size_t)std::max(1, tensor ? std::max(2, I.tc_min_blocks) : I.min_blocks);
+  int epb = std::max(1, max_threads / tpe);
+  if (tensor) epb = 16;   // tensor-core kernels: any thread count serves any element count (work items are strided over the CTA)
   if (epb_override > 0) epb = epb_override;
-  while (epb > 1 && ((size_t)epb * sd * 8 > smem_cap || (!I.tensor && epb * tpe > I.max_threads))) --epb;
+  while (epb > 1 && ((size_t)epb * sd * 8 > smem_cap || (!tensor && epb * tpe > max_threads))) --epb;
   if (n_items < epb) epb = (int)std::max<int64_t>(1, n_items);
   return epb;
 }
@@ -323,12 +333,14 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   std::memset(&P, 0, sizeof(P));
   P.vx = vx; P.vy = vy; P.vz = vz; P.conn = conn; P.lids = lids; P.orient = D->orient.n ? D->orient.p : nullptr;
   P.sol = sol; P.td = td;
-  P.var_major = I.tensor ? 1 : 0;
+  P.var_major = H.use_tensor ? 1 : 0;
   const bool initial = (pull_mass_mode == 4);   // projection of the initial conditions: the pull is the one of applyMassMatrixFree
   if (initial) pull_mass_mode = 3;
   if (pull_mass_mode) { P.mass_mode = initial ? 2 : 1; for (int v = 0; v < I.nvars; ++v) P.mass_wts[v] = mass_wts[v]; }
   std::memcpy(P.off, H.off, sizeof(P.off));
   std::memcpy(P.fn, initial ? H.init_fn : H.fn, sizeof(P.fn));
+  auto mark_state = [&]() { P.fn_state = 0; if (!pull_mass_mode) for (int f = 0; f < GEN_MAXFN; ++f) if (P.fn[f].pad && !P.fn[f].is_const) P.fn_state = 1; };
+  mark_state();
   P.fn_op = D->fn_op.p; P.fn_c = D->fn_c.p; P.opt = H.opt;
   for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
   P.elem_jac = (pull_mass_mode == 3) ? nullptr : ((O.jac || pull_mass_mode) ? D->elem_jac.p : nullptr);
@@ -336,16 +348,17 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   int launches = 0;
   auto run_elements = [&](bool side, int64_t n_items) -> const char* {
     if (n_items <= 0) return nullptr;
-    const int epb = pick_epb(I, side, n_items, H.epb_override);
+    const bool tensor = H.use_tensor && P.elem_jac != nullptr;   // residual-only calls have no use for the wider CTAs
+    const int epb = pick_epb(I, tensor, side, n_items, H.epb_override);
     P.epb = epb;
     const int tpe = I.tpe;
     int threads = ((epb * tpe + 31) / 32) * 32;
     threads = std::max(32, std::min(I.max_threads, threads));
-    if (I.tensor) threads = std::max(32, std::min(I.max_threads, 32 * std::max(2, epb * I.nvars * I.nvars)));   // one warp per (element, variable pair) block, two warps at least
+    if (tensor) threads = std::max(64, std::min(I.tc_max_threads, 32 * epb * I.nvars * I.nvars * (I.card[0] > 24 ? 2 : 1)));   // one warp per block of the contraction (S4m), two warps at least
     const size_t smem = (size_t)epb * (side ? I.smem_doubles_side : I.smem_doubles_volume) * sizeof(double);
     const int64_t nblocks = (n_items + epb - 1) / epb;
     ++launches;
-    return kd->launch(side, P, (int)nblocks, threads, smem, stream);
+    return tensor ? kd->launch_tc(side, P, (int)nblocks, threads, smem, stream) : kd->launch(side, P, (int)nblocks, threads, smem, stream);
   };
   auto run_pull = [&](int64_t row_begin, int64_t row_end) -> const char* {
     if (row_end <= row_begin) return nullptr;
@@ -388,6 +401,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
     if (volume) {
       P.items = nullptr; P.item_begin = B.elem_begin; P.item_end = B.elem_end; P.inst_base = B.elem_begin % H.scratch_cap;   // batches do not wrap: the ring is a multiple of the batch size
       std::memcpy(P.fn, initial ? H.init_fn : H.fn, sizeof(P.fn));
+      mark_state();
       for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
       P.geo_N = D->geo_N.p; P.geo_dN = D->geo_dN.p; P.ref_tab = D->ref_tab.p; P.qwts = D->qwts.p;
       if (const char* e = run_elements(false, B.elem_end - B.elem_begin)) return e;
@@ -402,6 +416,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
         for (int d = 0; d < 3; ++d) { P.tan_u[d] = S.tan_u[d]; P.tan_v[d] = S.tan_v[d]; }
         for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = S.bc_type[v]; P.bc_fn[v] = S.bc_fn[v]; }
         std::memcpy(P.fn, S.fn, sizeof(P.fn));
+        mark_state();
         if (const char* e = run_elements(true, (int64_t)S.items.size())) return e;
       }
     }

@@ -24,7 +24,8 @@ struct GenKernelInfo {
   int N, nvars, nbasis, nfn, K;
   int tpe;                                      // threads per element in the derivative stage
   int tensor;                                   // 1: Jacobian by field-direction derivatives + FP64 tensor-core contraction (general_kernel.cuh, S4d / S4m)
-  int max_threads, min_blocks;                  // launch bounds of the element kernel
+  int max_threads, min_blocks;                  // launch bounds of the element kernel (derivative-lane build)
+  int tc_max_threads, tc_min_blocks;            // launch bounds of the tensor-core build
   int smem_doubles_volume, smem_doubles_side;   // per element
   int card[2], ncb[2];                          // per basis
   int var_basis[GEN_MAXVARS];
@@ -33,6 +34,7 @@ struct GenDeviceKernels {
   GenKernelInfo info;
   // returns nullptr on success, else a static error string
   const char* (*launch)(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream);
+  const char* (*launch_tc)(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream);   // null: no tensor-core build
 };
 struct GenHostKernels {
   GenKernelInfo info;
@@ -64,6 +66,7 @@ struct GeneralPlanHost {
   int64_t n_elem = 0, n_inst = 0, n_rows = 0, n_owned = 0;
   int32_t max_row_len = 0;
   int epb_override = 0;                  // option "elements per cta" (0 = automatic)
+  bool use_tensor = false;               // option "jacobian" = auto | tensor | lanes: which build of the element kernel assembles Jacobians
   // pull schedule
   std::vector<int32_t> row_order;        // rows sorted by completion batch
   std::vector<int64_t> contrib_ptr;      // [n_rows+1] in row_order order

@@ -16,28 +16,30 @@ typedef NavierStokesPhys<2, 1> GenNs21;
 typedef NavierStokesPhys<3, 1> GenNs31;
 }  // namespace mrhyde_b200
 
-// X(physics name, dim, order, NQ, NQS, K, Phys, MAXT, MINB): MAXT threads per CTA at most, MINB CTAs per SM at least
-// The single-basis HGRAD modules run the tensor-core contraction (S4d / S4m): their CTAs hold as many elements as the shared
-// memory of MINB resident CTAs allows and MAXT threads whatever the element size (one warp per (element, variable pair) block).
-#define MRH_GEN_LIST(X)                                             \
-  X("thermal", 2, 1, 4, 2, 1, GenTh21, 256, 3)                      \
-  X("thermal", 3, 1, 8, 4, 1, GenTh31, 256, 3)                      \
-  X("thermal", 2, 2, 9, 3, 1, GenTh22, 256, 3)                      \
-  X("thermal", 3, 2, 27, 9, 1, GenTh32, 128, 4)                     \
-  X("linearelasticity", 2, 1, 4, 2, 1, GenLe21, 256, 3)             \
-  X("linearelasticity", 3, 1, 8, 4, 1, GenLe31, 256, 3)             \
-  X("linearelasticity", 2, 2, 9, 3, 1, GenLe22, 256, 3)             \
-  X("linearelasticity", 3, 2, 27, 9, 1, GenLe32, 288, 2)            \
-  X("navier stokes", 2, 1, 4, 2, 1, GenNs21, 256, 3)                \
-  X("navier stokes", 3, 1, 8, 4, 1, GenNs31, 256, 2)                \
-  X("maxwell", 3, 1, 8, 4, 1, MaxwellPhys, 128, 3)
+// X(physics name, dim, order, NQ, NQS, K, Phys, MAXT, MINB, MAXT_L, MINB_L): launch bounds (threads per CTA at most, CTAs per SM at
+// least) of the tensor-core build (S4d / S4m: CTAs hold as many elements as the shared memory of MINB resident CTAs allows and MAXT
+// threads whatever the element size, one warp per (element, variable pair) block) and of the derivative-lane build (S4b: one thread
+// per element dof).  The two-basis Maxwell layout has the lane build only.
+#define MRH_GEN_LIST(X)                                                     \
+  X("thermal", 2, 1, 4, 2, 1, GenTh21, 256, 3, 256, 3)                      \
+  X("thermal", 3, 1, 8, 4, 1, GenTh31, 256, 3, 256, 3)                      \
+  X("thermal", 2, 2, 9, 3, 1, GenTh22, 256, 3, 256, 2)                      \
+  X("thermal", 3, 2, 27, 9, 1, GenTh32, 128, 4, 128, 3)                     \
+  X("linearelasticity", 2, 1, 4, 2, 1, GenLe21, 256, 3, 256, 3)             \
+  X("linearelasticity", 3, 1, 8, 4, 1, GenLe31, 256, 3, 256, 3)             \
+  X("linearelasticity", 2, 2, 9, 3, 1, GenLe22, 256, 3, 128, 4)             \
+  X("linearelasticity", 3, 2, 27, 9, 1, GenLe32, 576, 1, 96, 2)             \
+  X("navier stokes", 2, 1, 4, 2, 1, GenNs21, 256, 3, 256, 2)                \
+  X("navier stokes", 3, 1, 8, 4, 1, GenNs31, 256, 2, 128, 3)                \
+  X("maxwell", 3, 1, 8, 4, 1, MaxwellPhys, 128, 3, 128, 3)
 
 namespace mrhyde_b200 {
 template <class Phys, int NQ, int NQS, int K>
-inline GenKernelInfo gen_make_info(const char* physics, int dim, int order, int maxt, int minb) {
+inline GenKernelInfo gen_make_info(const char* physics, int dim, int order, int maxt, int minb, int maxt_l, int minb_l) {
   GenKernelInfo I;
   I.physics = physics; I.dim = dim; I.order = order; I.nq = NQ; I.nqs = NQS;
-  I.max_threads = maxt; I.min_blocks = minb;
+  I.tc_max_threads = maxt; I.tc_min_blocks = minb;
+  I.max_threads = maxt_l; I.min_blocks = minb_l;
   I.N = Phys::N; I.nvars = Phys::NVAR; I.nbasis = Phys::NBASIS; I.nfn = Phys::NFN; I.K = K; I.tpe = GenBlock<Phys, NQ, K, false>::TPE; I.tensor = GenLayout<Phys, NQ>::TC ? 1 : 0;
   I.smem_doubles_volume = GenLayout<Phys, NQ>::SIZE;
   I.smem_doubles_side = GenLayout<Phys, NQS>::SIZE;

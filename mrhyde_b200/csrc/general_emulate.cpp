@@ -24,9 +24,10 @@ void emulate_blocks(const GenParams& P, int nblocks) {
     for (int i = 0; i < P.epb; ++i) Bk::s1b(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb * Phys::max_card() * NQ; ++i) Bk::s2(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb * NQ * Bk::S3_KINDS; ++i) Bk::s3(P, sm.data(), blk, i);
+    for (int i = 0; i < P.epb * NQ * Bk::S3F_KINDS; ++i) Bk::s3f(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb * NQ; ++i) Bk::s4a(P, sm.data(), blk, i);
     if (P.elem_jac) {
-      if (Bk::TC) {   // field-direction derivatives + contraction (the device runs the contraction on the FP64 tensor cores)
+      if (Bk::TC && P.tensor) {   // field-direction derivatives + contraction (the device runs the contraction on the FP64 tensor cores)
         for (int i = 0; i < P.epb * NQ * Bk::NCV; ++i) Bk::s4d(P, sm.data(), blk, i);
         for (int i = 0; i < P.epb * L::NVAR * L::NVAR; ++i) Bk::s4m_item(P, sm.data(), blk, i);
       } else {
@@ -48,8 +49,8 @@ struct HostEntry { GenHostKernels k; };
 std::vector<GenHostKernels>& host_table() {
   static std::vector<GenHostKernels> T;
   if (T.empty()) {
-#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS, MAXT, MINB) \
-    T.push_back(GenHostKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER, MAXT, MINB), &emulate_entry<PHYS, NQ, NQS, K>});
+#define X(NAME, DIM, ORDER, NQ, NQS, K, PHYS, MAXT, MINB, MAXT_L, MINB_L) \
+    T.push_back(GenHostKernels{gen_make_info<PHYS, NQ, NQS, K>(NAME, DIM, ORDER, MAXT, MINB, MAXT_L, MINB_L), &emulate_entry<PHYS, NQ, NQS, K>});
     MRH_GEN_LIST(X)
 #undef X
   }

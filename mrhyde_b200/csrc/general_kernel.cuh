@@ -159,6 +159,8 @@ struct GenParams {
   // dof off[v][i] (device plans of the tensor-core contraction: a fragment row then is a contiguous run in global memory; the
   // pull's contribution list and position tables are permuted to match at upload, general.cu)
   int32_t var_major;
+  int32_t tensor;     // host replay only: 1 = replay the tensor-core build's stages (S4d / S4m), 0 = the derivative-lane build's (S4b)
+  int32_t fn_state;   // some coefficient function of this launch reads a solution field (GenFnRec::pad marks which)
 };
 
 // what the physics sees at one point
@@ -166,12 +168,33 @@ struct QpCtx {
   double x, y, z, t, w, h, ih, dt;   // ih = 1 / h
   double n[3];
   const double* fn;         // function values at this point
+  const double* dfn;        // derivative components of the function values (state-dependent coefficients), [function][K]; may be null
   int32_t transient, stage;
   const int32_t* bc_type;
 };
 
+// Coefficient function i at the point, as the module's point function sees it.  STATE = false (no `Functions:` entry of the plan
+// reads a solution field): a plain double, exactly as before.  STATE = true: the value type of the evaluation, i.e. for Dual<K> the
+// value together with its derivative components -- the reference carries Sacado types through FunctionManager::evaluate for the
+// same reason (functionManager_evaluate.hpp:59-229, the is_AD_ branches).
+template <bool STATE>
+MRH_HD double fn_get(const QpCtx& c, int i, const double*) { return c.fn[i]; }
+template <bool STATE, int K>
+MRH_HD auto fn_get(const QpCtx& c, int i, const Dual<K>*) {
+  if constexpr (STATE) {
+    Dual<K> r;
+    r.v = c.fn[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.d[k] = c.dfn ? c.dfn[i * K + k] : 0.0;
+    return r;
+  } else {
+    return c.fn[i];
+  }
+}
+#define MRH_FN(i) fn_get<STATE>(c, (i), (const T*)nullptr)
+
 // ---- bytecode evaluation (same op set and order as volume_kernel.cuh / expr.cpp) ----------------------------
-MRH_HD double gen_expr_eval(const GenFnRec& f, const uint8_t* __restrict__ ops, const double* __restrict__ cs, const double (&var)[7]) {
+MRH_HD double gen_expr_eval(const GenFnRec& f, const uint8_t* __restrict__ ops, const double* __restrict__ cs, const double* __restrict__ var) {
   if (f.is_const) return f.cval;
   double st[16];
   int sp = 0;
@@ -215,6 +238,57 @@ MRH_HD double gen_expr_eval(const GenFnRec& f, const uint8_t* __restrict__ ops, 
     }
   }
   return a;
+}
+
+// The same program on (value, one derivative component): var / dvar hold the variables and their derivative components.  Comparisons,
+// abs at 0 and max / min ties take the branch of the values (their derivative is that of the selected operand), as Sacado does.
+MRH_HD void gen_expr_eval_dual(const GenFnRec& f, const uint8_t* __restrict__ ops, const double* __restrict__ cs, const double* __restrict__ var,
+                               const double* __restrict__ dvar, double& val, double& der) {
+  if (f.is_const) { val = f.cval; der = 0.0; return; }
+  double st[16], sd[16];
+  int sp = 0;
+  double a = 0.0, da = 0.0;
+  for (int i = f.begin; i < f.begin + f.n; ++i) {
+    const double c = MRH_LDG(cs + i);
+    const int op = MRH_LDG(ops + i);
+    switch (op) {
+      case OP_PUSHC: st[sp & 15] = a; sd[sp & 15] = da; ++sp; a = c; da = 0.0; break;
+      case OP_PUSHV: st[sp & 15] = a; sd[sp & 15] = da; ++sp; a = var[(int)c]; da = dvar[(int)c]; break;
+      case OP_ADD: --sp; a = st[sp & 15] + a; da = sd[sp & 15] + da; break;
+      case OP_SUB: --sp; a = st[sp & 15] + (-a); da = sd[sp & 15] - da; break;
+      case OP_MUL: { --sp; const double l = st[sp & 15], dl = sd[sp & 15]; da = dl * a + l * da; a = l * a; } break;
+      case OP_DIV: { --sp; const double l = st[sp & 15], dl = sd[sp & 15]; const double q = l / a; da = (dl - q * da) / a; a = q; } break;
+      case OP_POW: { --sp; const double l = st[sp & 15], dl = sd[sp & 15]; const double p = pow(l, a);
+                     da = (a != 0.0 ? a * pow(l, a - 1.0) * dl : 0.0) + (da != 0.0 ? p * log(l) * da : 0.0); a = p; } break;
+      case OP_LT: --sp; a = st[sp & 15] < a ? 1.0 : 0.0; da = 0.0; break;
+      case OP_LTE: --sp; a = st[sp & 15] <= a ? 1.0 : 0.0; da = 0.0; break;
+      case OP_GT: --sp; a = st[sp & 15] > a ? 1.0 : 0.0; da = 0.0; break;
+      case OP_GTE: --sp; a = st[sp & 15] >= a ? 1.0 : 0.0; da = 0.0; break;
+      case OP_MAX: { --sp; const double l = st[sp & 15]; if (!(a > l)) { a = l; da = sd[sp & 15]; } } break;
+      case OP_MIN: { --sp; const double l = st[sp & 15]; if (!(a < l)) { a = l; da = sd[sp & 15]; } } break;
+      case OP_MEAN: --sp; a = 0.5 * st[sp & 15] + 0.5 * a; da = 0.5 * sd[sp & 15] + 0.5 * da; break;
+      case OP_ADDC: a = a + c; break;
+      case OP_SUBC: a = a + (-c); break;
+      case OP_MULC: a = a * c; da = da * c; break;
+      case OP_DIVC: a = a / c; da = da / c; break;
+      case OP_POWC: da = c != 0.0 ? c * pow(a, c - 1.0) * da : 0.0; a = pow(a, c); break;
+      case OP_ADDV: a = a + var[(int)c]; da = da + dvar[(int)c]; break;
+      case OP_SUBV: a = a + (-var[(int)c]); da = da - dvar[(int)c]; break;
+      case OP_MULV: { const double r = var[(int)c]; da = da * r + a * dvar[(int)c]; a = a * r; } break;
+      case OP_DIVV: { const double r = var[(int)c]; const double q = a / r; da = (da - q * dvar[(int)c]) / r; a = q; } break;
+      case OP_SIN: da = cos(a) * da; a = sin(a); break;
+      case OP_COS: da = -sin(a) * da; a = cos(a); break;
+      case OP_TAN: { const double tt = tan(a); da = (1.0 + tt * tt) * da; a = tt; } break;
+      case OP_EXP: a = exp(a); da = a * da; break;
+      case OP_LOG: da = da / a; a = log(a); break;
+      case OP_ABS: if (a < 0.0) { a = -a; da = -da; } break;
+      case OP_SQRT: if (a <= 0.0) { a = 0.0; da = 0.0; } else { a = sqrt(a); da = 0.5 * da / a; } break;
+      case OP_SINH: da = cosh(a) * da; a = sinh(a); break;
+      case OP_COSH: da = sinh(a) * da; a = cosh(a); break;
+      default: break;
+    }
+  }
+  val = a; der = da;
 }
 
 // computeSolnTransientSeeded folded into the gather (same formulas as volume_kernel.cuh: gather_dof)
@@ -263,8 +337,13 @@ struct GenLayout {
   static constexpr int N = Phys::N;
   static constexpr int GEO = 28;   // w, x y z, Jinv[9], J[9], det, pad, n[3], pad
   static MRH_CE int even(int x) { return (x + 1) & ~1; }
-  static MRH_CE int pb_size() { int s = 0; for (int b = 0; b < Phys::NBASIS; ++b) s += Phys::card(b) * NQ * Phys::ncb(b); return s; }
-  static MRH_CE int pb_off(int b) { int s = 0; for (int c = 0; c < b; ++c) s += Phys::card(c) * NQ * Phys::ncb(c); return s; }
+  // PB[b][i][q][k]: one basis function is a ROW of prs(b) doubles; the single-basis layouts pad the row by two doubles so that the
+  // eight rows a tensor-core fragment load touches fall into distinct shared-memory banks (an unpadded row is a multiple of 128 bytes)
+  static MRH_CE int prs(int b) { return NQ * Phys::ncb(b) + (Phys::NBASIS == 1 ? 2 : 0); }
+  static MRH_HD int prs_rt(int b) { return NQ * Phys::ncb_rt(b) + (Phys::NBASIS == 1 ? 2 : 0); }
+  static MRH_CE int pb_size() { int s = 0; for (int b = 0; b < Phys::NBASIS; ++b) s += Phys::card(b) * prs(b); return s; }
+  static MRH_CE int pb_off(int b) { int s = 0; for (int c = 0; c < b; ++c) s += Phys::card(c) * prs(c); return s; }
+  static MRH_CE int rt_off(int b) { int s = 0; for (int c = 0; c < b; ++c) s += Phys::card(c) * NQ * Phys::ncb(c); return s; }   // reference tables (global memory, unpadded)
   static constexpr int U = 0;
   static constexpr int UT = U + even(N);
   static constexpr int VX = UT + even(N);
@@ -279,7 +358,8 @@ struct GenLayout {
   static constexpr bool TC = (Phys::NBASIS == 1);
   static constexpr int NCV = NVAR * NC;
   static constexpr int DM = CV + NQ * NVAR * NC;
-  static constexpr int SIZE = DM + (TC ? NQ * NCV * NCV : 0);
+  static constexpr int DS = NCV + 2;   // row stride of D (padded: the four rows a fragment load touches sit in distinct banks)
+  static constexpr int SIZE = DM + (TC ? NQ * NCV * DS : 0);
 };
 
 #if defined(__CUDA_ARCH__)
@@ -394,8 +474,8 @@ struct GenBlock {
     if (idx >= P.epb * CARD * NQ) return;
     const int el = idx / (CARD * NQ), r = idx % (CARD * NQ), i = r / NQ, q = r % NQ;
     const double* g = sm + el * L::SIZE + L::G + q * L::GEO;
-    const double* rt = P.ref_tab + L::pb_off(B) + (i * NQ + q) * NCB;
-    double* out = sm + el * L::SIZE + L::PB + L::pb_off(B) + (i * NQ + q) * NCB;
+    const double* rt = P.ref_tab + L::rt_off(B) + (i * NQ + q) * NCB;
+    double* out = sm + el * L::SIZE + L::PB + L::pb_off(B) + i * L::prs(B) + q * NCB;
     if (BT == BT_HGRAD) {
       out[0] = MRH_LDG(rt);
       for (int d = 0; d < 3; ++d) {
@@ -441,35 +521,64 @@ struct GenBlock {
     for (int i = 0; i < CARD; ++i) {
       const int c = P.off[V][i];
       const double u = sme[L::U + c], ut = sme[L::UT + c];
-      for (int k = 0; k < NCB; ++k) f[k] += u * pb[i * NQ * NCB + k];
-      for (int k = 0; k < NVAL; ++k) ft[k] += ut * pb[i * NQ * NCB + k];
+      for (int k = 0; k < NCB; ++k) f[k] += u * pb[i * L::prs(B) + k];
+      for (int k = 0; k < NVAL; ++k) ft[k] += ut * pb[i * L::prs(B) + k];
     }
     for (int k = 0; k < NC; ++k) { sme[L::FV + (q * NVAR + V) * NC + k] = f[k]; sme[L::FT + (q * NVAR + V) * NC + k] = ft[k]; }
   }
-  // work item (t, el, q): t < NVAR -> fields of variable t; else coefficient function t - NVAR (the last NVAR are the
-  // boundary data of each variable on this sideset)
-  static constexpr int S3_KINDS = NVAR + Phys::NFN + NVAR;
+  // S3: work item (t, el, q) = fields of variable t at the point
+  static constexpr int S3_KINDS = NVAR;
   MRH_HD static void s3(const GenParams& P, double* sm, int /*blk*/, int idx) {
     const int neq = P.epb * NQ;
     if (idx >= neq * S3_KINDS) return;
     const int t = idx / neq, eq = idx % neq, el = eq / NQ, q = eq % NQ;
     double* sme = sm + el * L::SIZE;
-    if (t < NVAR) {
-      switch (t) {
-        case 0: s3_var<0>(P, sme, q); break;
-        case 1: s3_var<(NVAR > 1 ? 1 : 0)>(P, sme, q); break;
-        case 2: s3_var<(NVAR > 2 ? 2 : 0)>(P, sme, q); break;
-        default: s3_var<(NVAR > 3 ? 3 : 0)>(P, sme, q); break;
-      }
-      return;
+    switch (t) {
+      case 0: s3_var<0>(P, sme, q); break;
+      case 1: s3_var<(NVAR > 1 ? 1 : 0)>(P, sme, q); break;
+      case 2: s3_var<(NVAR > 2 ? 2 : 0)>(P, sme, q); break;
+      default: s3_var<(NVAR > 3 ? 3 : 0)>(P, sme, q); break;
     }
-    const int f = t - NVAR;
+  }
+  // variables of the expression evaluator at a point: x y z t n[x] n[y] n[z], then (plans with state-dependent coefficients) the
+  // solution fields F[v][k] and their time derivatives Ft[v][k] (slots of FunctionSet::set_solution_slots, abi.cu)
+  static constexpr int NXV = EXPR_STATE0 + 2 * NVAR * NC;
+  MRH_HD static void expr_vars(const GenParams& P, const double* sme, int q, double (&var)[NXV]) {
     const double* g = sme + L::G + q * L::GEO;
-    const double var[7] = {g[1], g[2], g[3], P.td.time, g[24], g[25], g[26]};
-    double val = 0.0;
-    if (f < Phys::NFN) val = gen_expr_eval(P.fn[f], P.fn_op, P.fn_c, var);
-    else if (SIDE && P.bc_fn[f - Phys::NFN] >= 0) val = gen_expr_eval(P.fn[P.bc_fn[f - Phys::NFN]], P.fn_op, P.fn_c, var);
-    sme[L::FN + q * L::NFN + f] = val;
+    var[0] = g[1]; var[1] = g[2]; var[2] = g[3]; var[3] = P.td.time; var[4] = g[24]; var[5] = g[25]; var[6] = g[26];
+    if (P.fn_state) {
+      for (int j = 0; j < NVAR * NC; ++j) {
+        var[EXPR_STATE0 + j] = sme[L::FV + q * NVAR * NC + j];
+        var[EXPR_STATE0 + NVAR * NC + j] = P.td.transient ? sme[L::FT + q * NVAR * NC + j] : 0.0;
+      }
+    }
+  }
+  MRH_HD static const GenFnRec* fn_rec(const GenParams& P, int f) {
+    if (f < Phys::NFN) return &P.fn[f];
+    if (SIDE && P.bc_fn[f - Phys::NFN] >= 0) return &P.fn[P.bc_fn[f - Phys::NFN]];
+    return nullptr;
+  }
+  // S3f (after the fields): work item (f, el, q) = coefficient function f at the point (the last NVAR are the boundary data of each
+  // variable on this sideset)
+  static constexpr int S3F_KINDS = Phys::NFN + NVAR;
+  MRH_HD static void s3f(const GenParams& P, double* sm, int /*blk*/, int idx) {
+    const int neq = P.epb * NQ;
+    if (idx >= neq * S3F_KINDS) return;
+    const int f = idx / neq, eq = idx % neq, el = eq / NQ, q = eq % NQ;
+    double* sme = sm + el * L::SIZE;
+    double var[NXV];
+    expr_vars(P, sme, q, var);
+    const GenFnRec* fr = fn_rec(P, f);
+    sme[L::FN + q * L::NFN + f] = fr ? gen_expr_eval(*fr, P.fn_op, P.fn_c, var) : 0.0;
+  }
+  // derivative components of the state-dependent coefficient functions at a point for the seeds dvar (others: 0)
+  MRH_HD static void fn_derivatives(const GenParams& P, const double* sme, int q, const double (&var)[NXV], const double (&dvar)[NXV], double* dfn, int stride, int kk) {
+    for (int f = 0; f < S3F_KINDS; ++f) {
+      const GenFnRec* fr = fn_rec(P, f);
+      double v = 0.0, d = 0.0;
+      if (fr && fr->pad) gen_expr_eval_dual(*fr, P.fn_op, P.fn_c, var, dvar, v, d);
+      dfn[f * stride + kk] = d;
+    }
   }
 
   MRH_HD static void make_ctx(const GenParams& P, const double* sme, int q, QpCtx& c) {
@@ -478,6 +587,7 @@ struct GenBlock {
     c.dt = P.td.deltat;
     c.n[0] = g[24]; c.n[1] = g[25]; c.n[2] = g[26];
     c.fn = sme + L::FN + q * L::NFN;
+    c.dfn = nullptr;
     c.transient = P.td.transient; c.stage = P.td.nstage_lo;
     c.bc_type = P.bc_type;
   }
@@ -494,8 +604,8 @@ struct GenBlock {
       for (int k = 0; k < NC; ++k) { F[v][k] = sme[L::FV + (q * NVAR + v) * NC + k]; Ft[v][k] = sme[L::FT + (q * NVAR + v) * NC + k]; Cf[v][k] = 0.0; }
     if (P.mass_mode == 2) gen_initial_point<Phys, double>(c, Cf);
     else if (P.mass_mode) gen_mass_point<Phys, double>(c, P.mass_wts, F, Cf);
-    else if (SIDE) Phys::template boundary<double>(c, P.opt, F, Ft, Cf);
-    else Phys::template volume<double>(c, P.opt, F, Ft, Cf);
+    else if (SIDE) Phys::template boundary<double, false>(c, P.opt, F, Ft, Cf);
+    else Phys::template volume<double, false>(c, P.opt, F, Ft, Cf);
     for (int v = 0; v < NVAR; ++v)
       for (int k = 0; k < NC; ++k) sme[L::CV + (q * NVAR + v) * NC + k] = Cf[v][k];
   }
@@ -521,7 +631,7 @@ struct GenBlock {
 #pragma unroll
     for (int i = 0; i < CARD; ++i) {
       double b[NCB];
-      mrh_ldn<NCB>(pbq + i * NQ * NCB, b);
+      mrh_ldn<NCB>(pbq + i * L::prs(B), b);
 #pragma unroll
       for (int k = 0; k < NCB; ++k) {
 #pragma unroll
@@ -549,7 +659,7 @@ struct GenBlock {
     const int wb = Phys::var_basis_rt(wv), ncb = Phys::ncb_rt(wb), nval = Phys::nval(wb);
     const int64_t item = item_of(P, blk, el);
     const double* sme = sm + el * L::SIZE;
-    const double* pbw = sme + L::PB + L::pb_off(wb) + i0 * NQ * ncb;
+    const double* pbw = sme + L::PB + L::pb_off(wb) + i0 * L::prs_rt(wb);
     double acc[N][K];
 #pragma unroll
     for (int r = 0; r < N; ++r)
@@ -577,7 +687,7 @@ struct GenBlock {
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         double sd[NC];
-        const double* pb = pbw + (kk * NQ + q) * ncb;
+        const double* pb = pbw + kk * L::prs_rt(wb) + q * ncb;
         if (Phys::NBASIS == 1) mrh_ldn<NC>(pb, sd);
         else {
 #pragma unroll
@@ -592,8 +702,28 @@ struct GenBlock {
           }
       }
       if (P.mass_mode) gen_mass_point<Phys, Dual<K>>(c, P.mass_wts, F, Cf);
-      else if (SIDE) Phys::template boundary<Dual<K>>(c, P.opt, F, Ft, Cf);
-      else Phys::template volume<Dual<K>>(c, P.opt, F, Ft, Cf);
+      else if (P.fn_state) {
+        // coefficients that read solution fields: their derivative components for this thread's columns
+        double var[NXV], dvar[NXV], dfn[S3F_KINDS * K];
+        expr_vars(P, sme, q, var);
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+          for (int j = 0; j < EXPR_STATE0; ++j) dvar[j] = 0.0;
+#pragma unroll
+          for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+              dvar[EXPR_STATE0 + v * NC + k] = F[v][k].d[kk];
+              dvar[EXPR_STATE0 + NVAR * NC + v * NC + k] = Ft[v][k].d[kk];
+            }
+          fn_derivatives(P, sme, q, var, dvar, dfn, K, kk);
+        }
+        c.dfn = dfn;
+        if (SIDE) Phys::template boundary<Dual<K>, true>(c, P.opt, F, Ft, Cf);
+        else Phys::template volume<Dual<K>, true>(c, P.opt, F, Ft, Cf);
+      }
+      else if (SIDE) Phys::template boundary<Dual<K>, false>(c, P.opt, F, Ft, Cf);
+      else Phys::template volume<Dual<K>, false>(c, P.opt, F, Ft, Cf);
       // test-function loop: rows in (variable, basis function) order
       s4b_rows_all(sme + L::PB, q, Cf, acc);
     }
@@ -637,46 +767,61 @@ struct GenBlock {
         Cf[v][k] = Dual<1>(0.0);
       }
     if (P.mass_mode) gen_mass_point<Phys, Dual<1>>(c, P.mass_wts, F, Cf);
-    else if (SIDE) Phys::template boundary<Dual<1>>(c, P.opt, F, Ft, Cf);
-    else Phys::template volume<Dual<1>>(c, P.opt, F, Ft, Cf);
-    double* D = sme + L::DM + q * NCV * NCV;
+    else if (P.fn_state) {
+      double var[NXV], dvar[NXV], dfn[S3F_KINDS];
+      expr_vars(P, sme, q, var);
+      for (int j = 0; j < NXV; ++j) dvar[j] = 0.0;
+      dvar[EXPR_STATE0 + dir] = au;
+      dvar[EXPR_STATE0 + NVAR * NC + dir] = (dir % NC) < Phys::nval(0) ? at : 0.0;
+      fn_derivatives(P, sme, q, var, dvar, dfn, 1, 0);
+      c.dfn = dfn;
+      if (SIDE) Phys::template boundary<Dual<1>, true>(c, P.opt, F, Ft, Cf);
+      else Phys::template volume<Dual<1>, true>(c, P.opt, F, Ft, Cf);
+    }
+    else if (SIDE) Phys::template boundary<Dual<1>, false>(c, P.opt, F, Ft, Cf);
+    else Phys::template volume<Dual<1>, false>(c, P.opt, F, Ft, Cf);
+    double* D = sme + L::DM + q * NCV * L::DS;
 #pragma unroll
     for (int v = 0; v < NVAR; ++v)
 #pragma unroll
-      for (int k = 0; k < NC; ++k) D[(v * NC + k) * NCV + dir] = Cf[v][k].d[0];
+      for (int k = 0; k < NC; ++k) D[(v * NC + k) * L::DS + dir] = Cf[v][k].d[0];
   }
 
 #if defined(__CUDA_ARCH__)
-  // S4m: one warp, one (element, v, w) block of the element matrix
+  // S4m: one warp, one (element, v, w) block of the element matrix -- or, for bases of more than 24 functions, one half of its
+  // column tiles (JSPLIT = 2), so that a warp's accumulators stay within 32 registers and twice as many warps share the work
+  static constexpr int JSPLIT = IT >= 4 ? 2 : 1, JT = IT / JSPLIT;
+  static constexpr int S4M_ITEMS = NVAR * NVAR * JSPLIT;   // per element
   __device__ __forceinline__ static void s4m_warp(const GenParams& P, const double* sm, int blk, int item, int lane) {
-    const int el = item / (NVAR * NVAR), vw = item % (NVAR * NVAR), v = vw / NVAR, w = vw % NVAR;
+    const int el = item / S4M_ITEMS, r = item % S4M_ITEMS, vw = r / JSPLIT, jh = r % JSPLIT, v = vw / NVAR, w = vw % NVAR;
     const double* sme = sm + el * L::SIZE;
     const double* pb = sme + L::PB;
-    const double* D = sme + L::DM + (v * NC + (lane & 3)) * NCV + w * NC;
     const int g = lane >> 2, t = lane & 3;
-    double acc[IT][IT][2];
+    const double* D = sme + L::DM + (v * NC + t) * L::DS + w * NC;
+    double acc[IT][JT][2];
     int ro[IT];
 #pragma unroll
     for (int a = 0; a < IT; ++a) {
-      ro[a] = ((a * 8 + g) < CARD ? (a * 8 + g) : (CARD - 1)) * NQ * NC;   // rows beyond the basis repeat the last one (their results are dropped)
+      ro[a] = ((a * 8 + g) < CARD ? (a * 8 + g) : (CARD - 1)) * L::prs(0);   // rows beyond the basis repeat the last one (their results are dropped)
 #pragma unroll
-      for (int b = 0; b < IT; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+      for (int b = 0; b < JT; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
     }
-#pragma unroll 1
+#pragma unroll 2
     for (int q = 0; q < NQ; ++q) {
-      double d[NC], fa[IT], fb[IT];
-      mrh_ldn<NC>(D + q * NCV * NCV, d);
+      double d[NC], fa[IT], fb[JT];
+      mrh_ldn<NC>(D + q * NCV * L::DS, d);
 #pragma unroll
-      for (int a = 0; a < IT; ++a) {
+      for (int a = 0; a < IT; ++a) fa[a] = pb[ro[a] + q * NC + t];     // A fragment: entry t of basis row a * 8 + g
+#pragma unroll
+      for (int b = 0; b < JT; ++b) {                                  // B fragment: (D_q^{vw} PB_j)[t] for basis column (jh JT + b) * 8 + g
         double pr[NC];
-        mrh_ldn<NC>(pb + ro[a] + q * NC, pr);
-        fa[a] = t == 0 ? pr[0] : (t == 1 ? pr[1] : (t == 2 ? pr[2] : pr[3]));
-        fb[a] = d[0] * pr[0] + d[1] * pr[1] + d[2] * pr[2] + d[3] * pr[3];
+        mrh_ldn<NC>(pb + ro[jh * JT + b] + q * NC, pr);
+        fb[b] = d[0] * pr[0] + d[1] * pr[1] + d[2] * pr[2] + d[3] * pr[3];
       }
 #pragma unroll
       for (int a = 0; a < IT; ++a)
 #pragma unroll
-        for (int b = 0; b < IT; ++b) mrh_dmma(acc[a][b], fa[a], fb[b]);
+        for (int b = 0; b < JT; ++b) mrh_dmma(acc[a][b], fa[a], fb[b]);
     }
     const int64_t it = item_of(P, blk, el);
     if (it < P.item_end && P.elem_jac) {
@@ -687,10 +832,10 @@ struct GenBlock {
         if (i < CARD) {
           double* orow = out + (int64_t)row_index(P, v, i) * N;
 #pragma unroll
-          for (int b = 0; b < IT; ++b)
+          for (int b = 0; b < JT; ++b)
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
-              const int j = b * 8 + 2 * t + x;
+              const int j = (jh * JT + b) * 8 + 2 * t + x;
               if (j < CARD) orow[row_index(P, w, j)] = acc[a][b][x];
             }
         }
@@ -711,11 +856,11 @@ struct GenBlock {
       for (int j = 0; j < CARD; ++j) {
         double s = 0.0;
         for (int q = 0; q < NQ; ++q) {
-          const double* D = sme + L::DM + q * NCV * NCV;
+          const double* D = sme + L::DM + q * NCV * L::DS;
           for (int k = 0; k < NC; ++k) {
             double b = 0.0;
-            for (int l = 0; l < NC; ++l) b += D[(v * NC + k) * NCV + w * NC + l] * pb[(j * NQ + q) * NC + l];
-            s += pb[(i * NQ + q) * NC + k] * b;
+            for (int l = 0; l < NC; ++l) b += D[(v * NC + k) * L::DS + w * NC + l] * pb[j * L::prs(0) + q * NC + l];
+            s += pb[i * L::prs(0) + q * NC + k] * b;
           }
         }
         out[(int64_t)row_index(P, v, i) * N + row_index(P, w, j)] = s;
@@ -737,7 +882,7 @@ struct GenBlock {
     const int i = r - r0;
     const int b = Phys::var_basis_rt(v), ncb = Phys::ncb_rt(b);
     const double* sme = sm + el * L::SIZE;
-    const double* pb = sme + L::PB + L::pb_off(b) + i * NQ * ncb;
+    const double* pb = sme + L::PB + L::pb_off(b) + i * L::prs_rt(b);
     double s = 0.0;
     for (int q = 0; q < NQ; ++q)
       for (int k = 0; k < ncb; ++k) s += sme[L::CV + (q * NVAR + v) * NC + k] * pb[q * ncb + k];
@@ -748,7 +893,9 @@ struct GenBlock {
 #if defined(__CUDACC__)
 // MAXT / MINB: launch bounds chosen per instantiation (general_dispatch.hpp) so that the register allocation leaves
 // MINB CTAs of MAXT threads resident per SM
-template <class Phys, int NQ, int K, bool SIDE, int MAXT, int MINB>
+// TCK: Jacobian by field-direction derivatives + tensor-core contraction (S4d / S4m; single-basis layouts only), else by one
+// derivative lane per element dof (S4b)
+template <class Phys, int NQ, int K, bool SIDE, int MAXT, int MINB, bool TCK>
 __global__ void __launch_bounds__(MAXT, MINB) gen_element_kernel(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) double gen_smem[];
   typedef GenBlock<Phys, NQ, K, SIDE> Bk;
@@ -762,14 +909,16 @@ __global__ void __launch_bounds__(MAXT, MINB) gen_element_kernel(const __grid_co
   for (int i = tid; i < P.epb * Phys::max_card() * NQ; i += T) Bk::s2(P, gen_smem, blk, i);
   __syncthreads();
   for (int i = tid; i < P.epb * NQ * Bk::S3_KINDS; i += T) Bk::s3(P, gen_smem, blk, i);
+  if (P.fn_state) __syncthreads();   // coefficient functions that read solution fields wait for the fields
+  for (int i = tid; i < P.epb * NQ * Bk::S3F_KINDS; i += T) Bk::s3f(P, gen_smem, blk, i);
   __syncthreads();
   for (int i = tid; i < P.epb * NQ; i += T) Bk::s4a(P, gen_smem, blk, i);
-  if constexpr (Bk::TC) {
+  if constexpr (TCK && Bk::TC) {
     if (P.elem_jac)
       for (int i = tid; i < P.epb * NQ * Bk::NCV; i += T) Bk::s4d(P, gen_smem, blk, i);
     __syncthreads();
     if (P.elem_jac)
-      for (int item = tid >> 5; item < P.epb * L::NVAR * L::NVAR; item += T >> 5) Bk::s4m_warp(P, gen_smem, blk, item, tid & 31);
+      for (int item = tid >> 5; item < P.epb * Bk::S4M_ITEMS; item += T >> 5) Bk::s4m_warp(P, gen_smem, blk, item, tid & 31);
   } else {
     if (P.elem_jac)
       for (int i = tid; i < P.epb * Bk::TPE; i += T) Bk::s4b(P, gen_smem, blk, i);

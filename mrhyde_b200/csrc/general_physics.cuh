@@ -47,23 +47,23 @@ struct HGradSystem {
 template <int DIM_, int P_>
 struct ThermalPhys : HGradSystem<DIM_, P_, 1> {
   static constexpr int NFN = 8;
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[1][4], const T (&Ft)[1][4], T (&Cf)[1][4]) {
-    const double source = c.fn[0], diff = c.fn[1], cp = c.fn[2], rho = c.fn[3];
+    const auto source = MRH_FN(0), diff = MRH_FN(1), cp = MRH_FN(2), rho = MRH_FN(3);
     Cf[0][0] = (rho * cp * Ft[0][0] - source) * c.w;
     for (int d = 0; d < DIM_; ++d) Cf[0][1 + d] = diff * F[0][1 + d] * c.w;
     if (o.have_advection) {
-      T adv = c.fn[4] * F[0][1];
-      if (DIM_ > 1) adv = adv + c.fn[5] * F[0][2];
-      if (DIM_ > 2) adv = adv + c.fn[6] * F[0][3];
+      T adv = MRH_FN(4) * F[0][1];
+      if (DIM_ > 1) adv = adv + MRH_FN(5) * F[0][2];
+      if (DIM_ > 2) adv = adv + MRH_FN(6) * F[0][3];
       Cf[0][0] = Cf[0][0] + adv * c.w;
     }
   }
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void boundary(const QpCtx& c, const GenOpts& o, const T (&F)[1][4], const T (&)[1][4], T (&Cf)[1][4]) {
-    const double diff = c.fn[1], bdata = c.fn[NFN + 0];
+    const auto diff = MRH_FN(1), bdata = MRH_FN(NFN + 0);
     if (c.bc_type[0] == BC_NEUMANN) {
-      Cf[0][0] = T(-bdata * c.w);
+      Cf[0][0] = T(0.0) - bdata * c.w;
     } else if (c.bc_type[0] == BC_WEAK_DIRICHLET) {
       const double epen = 10.0;
       T flux = F[0][1] * c.n[0] + F[0][2] * c.n[1];
@@ -82,9 +82,9 @@ template <int DIM_, int P_>
 struct ElasticityPhys : HGradSystem<DIM_, P_, DIM_> {
   static constexpr int NFN = 5;
   static constexpr int NVAR = DIM_;
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void stress(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], T (&s)[3][3]) {
-    const double lambda = c.fn[0], mu = c.fn[1];
+    const auto lambda = MRH_FN(0), mu = MRH_FN(1);
     // computeStress (linearelasticity.cpp:1158-1240)
     if (DIM_ == 2) {
       if (o.incplanestress) {
@@ -109,32 +109,32 @@ struct ElasticityPhys : HGradSystem<DIM_, P_, DIM_> {
       s[2][2] = (2.0 * mu + lambda) * F[Z][3] + lambda * (F[X][1] + F[Y][2]);
     }
   }
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&)[NVAR][4], T (&Cf)[NVAR][4]) {
     T s[3][3];
-    stress(c, o, F, s);
+    stress<T, STATE>(c, o, F, s);
     for (int d = 0; d < DIM_; ++d) {
-      Cf[d][0] = T(-c.fn[2 + d] * c.w);
+      Cf[d][0] = T(0.0) - MRH_FN(2 + d) * c.w;
       for (int e = 0; e < DIM_; ++e) Cf[d][1 + e] = s[d][e] * c.w;
     }
   }
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void boundary(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&)[NVAR][4], T (&Cf)[NVAR][4]) {
-    const double lam = c.fn[0], mu = c.fn[1];
+    const auto lam = MRH_FN(0), mu = MRH_FN(1);
     bool any = false;
     for (int d = 0; d < DIM_; ++d) any = any || c.bc_type[d] == BC_WEAK_DIRICHLET;
     T s[3][3], delta[3];
     if (any) {
-      stress(c, o, F, s);
+      stress<T, STATE>(c, o, F, s);
       // data of a variable that is neither Neumann nor weak Dirichlet on this side is an unset Vista in the reference
       // (linearelasticity.cpp:264-283); it reads as 0 here
-      for (int d = 0; d < DIM_; ++d) delta[d] = F[d][0] - c.fn[NFN + d];
+      for (int d = 0; d < DIM_; ++d) delta[d] = F[d][0] - MRH_FN(NFN + d);
     }
     for (int d = 0; d < DIM_; ++d) {
       if (c.bc_type[d] == BC_NEUMANN) {
-        Cf[d][0] = T(-c.fn[NFN + d] * c.w);
+        Cf[d][0] = T(0.0) - MRH_FN(NFN + d) * c.w;
       } else if (c.bc_type[d] == BC_WEAK_DIRICHLET) {
-        const double penalty = o.penalty * (lam + 2.0 * mu) * c.ih;
+        const auto penalty = o.penalty * (lam + 2.0 * mu) * c.ih;
         T trac = s[d][0] * c.n[0] + s[d][1] * c.n[1];
         if (DIM_ > 2) trac = trac + s[d][2] * c.n[2];
         Cf[d][0] = (penalty * delta[d] - trac) * c.w;
@@ -166,40 +166,43 @@ struct NavierStokesPhys : HGradSystem<DIM_, P_, DIM_ + 1> {
   MRH_HD static int src(int d) { return d == 0 ? 0 : d + 1; }   // source ux 0, uy 2, uz 3
   // computeTau (navierstokes.cpp:1053-1081): tau = [(C1 nu/h^2)^2 + (C2 |u|/h)^2 + (C3/dt)^2]^(-1/2); divisions by h, dt are
   // multiplications by reciprocals and the square roots share one rsqrt (a few ulp, far inside the 1e-12 tolerance)
-  template <class T>
-  MRH_HD static T compute_tau(const double visc, const T (&u)[3], double ih, double dt, int transient) {
+  template <class T, class V>
+  MRH_HD static T compute_tau(const V visc, const T (&u)[3], double ih, double dt, int transient) {
     const double C1 = 4.0, C2 = 2.0, C3 = transient ? 2.0 : 0.0;
     T nvel = u[0] * u[0] + u[1] * u[1];
     if (DIM_ > 2) nvel = nvel + u[2] * u[2];
     if (mrh_val(nvel) > 1E-12) nvel = mrh_sqrt(nvel);   // below the threshold the squared speed is used
-    const double t1 = C1 * visc * ih * ih, t3 = transient ? C3 / dt : 0.0;
+    const auto t1 = (C1 * ih * ih) * visc;
+    const double t3 = transient ? C3 / dt : 0.0;
     const T nv = (C2 * ih) * nvel;
     return mrh_rsqrt(nv * nv + (t1 * t1 + t3 * t3));
   }
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&Ft)[NVAR][4], T (&Cf)[NVAR][4]) {
-    const double dens = c.fn[4], visc = c.fn[5];
+    const auto dens = MRH_FN(4), visc = MRH_FN(5);
     T u[3];
     for (int d = 0; d < 3; ++d) u[d] = d < DIM_ ? F[vel(d < DIM_ ? d : 0)][0] : T(0.0);
     const T pr = F[1][0];
     T tau = T(0.0);
     if (o.useSUPG || o.usePSPG) tau = compute_tau(visc, u, c.ih, c.dt, c.transient);
     T divu = T(0.0);
-    const double wdens = dens * c.w, pspg_w = o.usePSPG ? c.w / dens : 0.0;
+    const auto wdens = dens * c.w;
+    auto pspg_w = c.w / dens;
+    if (!o.usePSPG) pspg_w = pspg_w * 0.0;
 #pragma unroll
     for (int d = 0; d < DIM_; ++d) {
       const int v = vel(d);
       T conv = u[0] * F[v][1] + u[1] * F[v][2];
       if (DIM_ > 2) conv = conv + u[2] * F[v][3];
       T co[4];
-      co[0] = (Ft[v][0] + conv - c.fn[src(d)]) * wdens;
+      co[0] = (Ft[v][0] + conv - MRH_FN(src(d))) * wdens;
       for (int e = 0; e < DIM_; ++e) {
         T Fe = visc * F[v][1 + e];
         if (e == d) Fe = Fe - pr;
         co[1 + e] = Fe * c.w;
       }
       T stabres = T(0.0);
-      if (o.useSUPG || o.usePSPG) stabres = dens * Ft[v][0] + dens * conv + F[1][1 + d] - dens * c.fn[src(d)];
+      if (o.useSUPG || o.usePSPG) stabres = dens * Ft[v][0] + dens * conv + F[1][1 + d] - dens * MRH_FN(src(d));
       if (o.useSUPG) for (int e = 0; e < DIM_; ++e) co[1 + e] = co[1 + e] + tau * stabres * u[e] * c.w;
       // [g1] navierstokes.cpp:688: the 3-D z-momentum block writes through the uy offsets
       if (DIM_ == 3 && d == 2 && o.uz_reference) {
@@ -212,10 +215,10 @@ struct NavierStokesPhys : HGradSystem<DIM_, P_, DIM_ + 1> {
     }
     Cf[1][0] = divu * c.w;
   }
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void boundary(const QpCtx& c, const GenOpts&, const T (&)[NVAR][4], const T (&)[NVAR][4], T (&Cf)[NVAR][4]) {
     for (int d = 0; d < DIM_; ++d)
-      if (c.bc_type[vel(d)] == BC_NEUMANN) Cf[vel(d)][0] = T(-c.fn[NFN + vel(d)] * c.w);
+      if (c.bc_type[vel(d)] == BC_NEUMANN) Cf[vel(d)][0] = T(0.0) - MRH_FN(NFN + vel(d)) * c.w;
   }
 };
 
@@ -236,22 +239,22 @@ struct MaxwellPhys {
   static MRH_CE int card_of_var(int v) { return v == 0 ? 12 : 6; }
   static MRH_CE int row0(int v) { return v == 0 ? 0 : 12; }
   static MRH_CE int max_card() { return 12; }
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[2][6], const T (&Ft)[2][6], T (&Cf)[2][6]) {
     // B equation: (B_t + curl E) . psi; leap-frog keeps curl E in stage 0 only (maxwell.cpp:138-209)
     const bool with_curl = !o.leapfrog || c.stage == 0;
     for (int d = 0; d < 3; ++d) Cf[1][d] = with_curl ? (Ft[1][d] + F[0][3 + d]) * c.w : Ft[1][d] * c.w;
     // E equation (maxwell.cpp:262-303): (n^2 E_t + (sigma E + J)/eps) . phi - B/(mu eps) . curl phi
     if (!o.leapfrog || c.stage == 1) {
-      const double mu = c.fn[3], rindex = c.fn[4], eps = c.fn[5], sigma = c.fn[6];
-      const double ieps = 1.0 / eps, cb = (-1.0 / mu * 1.0 / eps) * c.w, n2 = rindex * rindex;
+      const auto mu = MRH_FN(3), rindex = MRH_FN(4), eps = MRH_FN(5), sigma = MRH_FN(6);
+      const auto ieps = 1.0 / eps, cb = (-1.0 / mu * 1.0 / eps) * c.w, n2 = rindex * rindex;
       for (int d = 0; d < 3; ++d) {
-        Cf[0][d] = (n2 * Ft[0][d] + ieps * (sigma * F[0][d] + c.fn[d])) * c.w;
+        Cf[0][d] = (n2 * Ft[0][d] + ieps * (sigma * F[0][d] + MRH_FN(d))) * c.w;
         Cf[0][3 + d] = cb * F[1][d];
       }
     }
   }
-  template <class T>
+  template <class T, bool STATE = false>
   MRH_HD static void boundary(const QpCtx& c, const GenOpts&, const T (&F)[2][6], const T (&)[2][6], T (&Cf)[2][6]) {
     if (c.bc_type[1] != BC_NEUMANN) return;   // "really ABC" (maxwell.cpp:341)
     const double gamma = -0.9944;

@@ -103,6 +103,7 @@ enum ExprOp : uint8_t {
 constexpr int EXPR_MAXOPS = 56;
 constexpr int EXPR_MAXSTACK = 8;
 constexpr int EXPR_NVARS = 10;  // x y z t n[x] n[y] n[z] + spare
+constexpr int EXPR_STATE0 = 7;  // general path: variable EXPR_STATE0 + s is solution-field slot s (fields F[v][k], then their time derivatives)
 
 struct ExprProgram {  // POD, copied into kernel parameters
   int32_t n = 0;

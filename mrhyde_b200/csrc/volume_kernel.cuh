@@ -435,6 +435,26 @@ __device__ __forceinline__ void elem_stage2(const ThermalParams<DIM>& P, ElemPre
     for (int d = 0; d < DIM; ++d) E.xv[v][d] = __ldg(vc[d] + E.cn[nb[v]]);
 }
 
+// L2 prefetch of what elem_stage2 will load: issued as soon as the next step's connectivity is in registers (before the pull), so the
+// loads after the pull find their lines in L2 instead of paying the DRAM latency at the top of the next step.  No registers are held.
+template <int DIM>
+__device__ __forceinline__ void elem_prefetch2(const ThermalParams<DIM>& P, const ElemPre<DIM>& E) {
+  constexpr int NV = 1 << DIM;
+  constexpr int nb[4] = {0, 1, 3, 4};
+  const double* vc[3] = {P.vx, P.vy, P.vz};
+#pragma unroll
+  for (int i = 0; i < NV; ++i) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.sol + E.ld[i]));
+  if (MRH_TRANSIENT(P.td)) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.td.prev[0] + E.ld[i]));
+  }
+#pragma unroll
+  for (int v = 0; v <= DIM; ++v)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+      if (v == 0 || MRH_HAS_GENERAL || MRH_HAS_AFFINE || d == v - 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(vc[d] + E.cn[nb[v]]));
+}
+
 template <int DIM>
 __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, const int cap, double* __restrict__ st) {
   typedef Q1Shape<DIM> S;
@@ -1125,6 +1145,9 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     if (more) elem_stage1<DIM>(P, sr_next.x + tid, E);
 #endif
     __syncthreads();
+#if defined(MRH_JIT_PREFETCH2) && !defined(MRH_EARLY_STAGE1)
+    if (more) elem_prefetch2<DIM>(P, E);   // E holds the next step's connectivity (requested before the barrier)
+#endif
 #if defined(MRH_EARLY_STAGE1) && defined(MRH_JIT_EARLY_STAGE2)
     // the next step's state and vertices are requested before the pull (their addresses arrived during the element work),
     // so no global-memory latency is left exposed between two steps; costs the registers that hold them across the pull

@@ -126,4 +126,14 @@ def general_cases():
         ("maxwell-dirk", MAXWELL_3D, {}, DIRK12, False),
         ("maxwell-abc-bwe", variant(MAXWELL_3D, **MAXWELL_ABC), {}, BWE, False),
         ("le3d-batched", variant(LE_3D, **{"Mesh/NX": 5, "Mesh/NY": 4, "Mesh/NZ": 4}), {"batch elems": 16}, None, False),
+        # coefficients that read the solution: the reference carries its AD type through FunctionManager::evaluate
+        # (functionManager_evaluate.hpp:59-229); here the bytecode is differentiated in the Jacobian stages
+        ("thermal3d-state-diffusion", variant(t3, **{"Functions/thermal diffusion": "1.0+T*T", "Functions/thermal source": "sin(x)*T+y"}), {}, None, False),
+        ("thermal3d-state-dirk", variant(t3, **{"Functions/thermal diffusion": "exp(0.3*T)+0.1*grad(T)[x]*grad(T)[x]", "Functions/specific heat": "1.0+0.2*T",
+                                                "Functions/density": "2.0"}), {}, DIRK12, False),
+        ("thermal3d-q2-state", variant(t3, **{"Discretization/order/T": 2, "Discretization/quadrature": 4, "Functions/thermal diffusion": "max(0.5,1.0+T)"}), {}, None, False),
+        ("le3d-state-mu", variant(LE_3D, **{"Functions/mu": "1.0+0.2*dx*dx+0.1*grad(dy)[z]"}), {}, None, False),
+        ("ns2d-state-viscosity", variant(NS_2D, **{"Functions/viscosity": "0.5+0.1*ux*ux+0.05*sqrt(1.0+uy*uy)"}), {}, None, False),
+        ("maxwell-state-sigma", variant(MAXWELL_3D, **{"Functions/conductivity": "0.2+E[x]*E[x]+0.1*B[z]"}), {}, DIRK12, False),
+        ("thermal2d-weak-state", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Functions/thermal diffusion": "1.0+0.5*T*T"})), {}, None, False),
     ]

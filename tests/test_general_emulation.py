@@ -39,6 +39,30 @@ def test_kernel_stages_match_oracle(oracle_lib, product_lib, name, cfg, opts, ta
         assert plan.stat("general_batches") > 1
 
 
+@pytest.mark.parametrize("name", ["thermal3d-state-dirk", "le3d-state-mu", "ns2d-state-viscosity", "maxwell-state-sigma", "le3d", "ns3d-neumann", "thermal3d-q2"])
+def test_derivative_lane_stages_match_oracle(oracle_lib, product_lib, name):
+    """option jacobian=lanes: the stage functions of the build with one derivative lane per element dof (S4b), including coefficients
+    that read solution fields, against the oracle (the default replay above runs the tensor-core build's stages for the HGRAD modules)."""
+    _, cfg, opts, tableau, zero = next(c for c in configs.general_cases() if c[0] == name)
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options=dict({"kernel": "general", "jacobian": "lanes"}, **opts))
+    u = np.zeros(op.num_dofs) if zero else helpers.manufactured_state(op)
+    ts, kw = _setup_time(op, tableau)
+    res_ref, jac_ref = op.assemble_jacres(u, **kw)
+    res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+    plan.debug_emulate(u, res, jac, time=ts)
+    op.set_time(False)
+    assert helpers.rel_err_vec(res, res_ref) < TOL and helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL
+
+
+def test_state_dependent_thermal_coefficient_leaves_the_sweep_kernel(oracle_lib, product_lib):
+    """thermal diffusion: 1.0+T*T on HGRAD-1: the sweep kernel's collapsed (linear) Jacobian does not apply, the plan takes the general path."""
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 4, "Mesh/NY": 3, "Mesh/NZ": 3, "Functions/thermal diffusion": "1.0+T*T"})
+    op = oracle_lib.OracleProblem(cfg)
+    assert helpers.plan_from_oracle(op, cfg, device=-1).stat("general") == 1
+    assert helpers.plan_from_oracle(op, configs.variant(cfg, **{"Functions/thermal diffusion": "1.0+x*x"}), device=-1).stat("general") == 0
+
+
 def test_host_only_plan_cannot_assemble(oracle_lib, product_lib):
     from mrhyde_b200.capi import MrhydeB200Error
     op = oracle_lib.OracleProblem(configs.LE_2D)
