@@ -452,7 +452,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="elements per brick edge (per GPU); default 128 (thermal), 64 (le), 96 (ns), 64 (leq2), 64 (maxwell): the BASELINE sizes")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=0, help="elements per brick edge (per GPU); default 128 (thermal), 64 (le), 96 (ns), 64 (leq2), 64 (maxwell): the BASELINE sizes")
     ap.add_argument("--workload", default="thermal", choices=sorted(WORKLOADS), help="thermal = BASELINE configs[1] (the headline); le / ns: other modules through the general path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="plan option key=value (tuning experiments), repeatable")

@@ -167,6 +167,10 @@ int mrhyde_b200_assemble_jacres(mrhyde_b200_plan* plan, const double* sol, const
                                 int compute_jacobian, int compute_residual, double* res, double* jac_values,
                                 void* stream);
 /* assembleRes (jacres.hpp:668-875): residual only (the ScalarT workset path). */
+/* Builds the plan-specialised kernel variant an upcoming call will need -- (steady | transient stage) x (residual, Jacobian, both) in
+ * the plan's output mode -- so that no assemble call compiles (NVRTC) on the hot path and build failures surface at set-up.
+ * finalize pre-builds the steady residual + Jacobian variant only.  No-op for plans on the ahead-of-time kernels. */
+int mrhyde_b200_plan_warmup(mrhyde_b200_plan* plan, int transient, int compute_jacobian, int compute_residual);
 int mrhyde_b200_assemble_res(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, double* res,
                              void* stream);
 /* Same as assemble_jacres but sol/res/jac_values (and t->sol_prev/sol_stage) are HOST buffers:
@@ -249,6 +253,9 @@ int mrhyde_b200_plan_debug_class_host(mrhyde_b200_plan* plan, const double* sol,
  * the host for a host-only plan (device = -1) built with option kernel=general: a debugging aid that lets the kernel
  * logic be checked against the oracle on machines without a GPU.  Fails with ERR_STATE on device plans; the assemble
  * entry points never use it.  sol / res / jac_values (and t's vectors) are host buffers. */
+/* Registers the host replay of the general kernel's stage functions.  It lives in the TEST-ONLY library libmrhyde_b200_emulate.so
+ * (symbol mrhyde_b200_emulator_lookup), not in this one: without it the mrhyde_b200_plan_debug_emulate* calls fail with ERR_STATE. */
+int mrhyde_b200_debug_set_emulator(void* lookup);
 int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, int compute_jacobian,
                                    int compute_residual, double* res, double* jac_values);
 /* Mass-matrix counterpart of mrhyde_b200_plan_debug_emulate (host-only plans; host buffers). */

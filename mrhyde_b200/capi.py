@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrhyde_b200.so")
 _LIB = None
+_EMU = None
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_PARSE, ERR_CUDA, ERR_STATE, ERR_NCCL = range(7)
 
@@ -26,7 +27,7 @@ SYMBOLS = [
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
     "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_class_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_plan_debug_chain_rows", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
-    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
+    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_debug_set_emulator", "mrhyde_b200_plan_warmup", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
     "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
 
@@ -71,6 +72,13 @@ def lib():
             raise ImportError("mrhyde_b200: %s is missing; build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)" % LIB_PATH)
         L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        # test-only companion (host replay of the general kernel's stages for debug_emulate on host-only plans): registered when present
+        emu = os.path.join(os.path.dirname(LIB_PATH), "libmrhyde_b200_emulate.so")
+        if os.path.exists(emu):
+            global _EMU
+            _EMU = C.CDLL(emu)
+            L.mrhyde_b200_debug_set_emulator.argtypes = [C.c_void_p]
+            L.mrhyde_b200_debug_set_emulator(C.cast(_EMU.mrhyde_b200_emulator_lookup, C.c_void_p))
         L.mrhyde_b200_version.restype = C.c_char_p
         L.mrhyde_b200_last_error.restype = C.c_char_p
         L.mrhyde_b200_plan_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Desc), C.c_int]
@@ -316,6 +324,10 @@ class AssemblyPlan:
     def assemble_res(self, sol, res, time=None, stream=None):
         self._chk(self.L.mrhyde_b200_assemble_res(self.h, _ptr(sol), time.ref() if time is not None else None, _ptr(res),
                                                 C.c_void_p(stream) if stream else None))
+
+    def warmup(self, transient=False, compute_jacobian=True, compute_residual=True):
+        """Builds the specialised kernel variant of an upcoming call now (no NVRTC compile inside the first assemble call)."""
+        self._chk(self.L.mrhyde_b200_plan_warmup(self.h, int(transient), int(compute_jacobian), int(compute_residual)))
 
     def assemble_jacres_host(self, sol, res, jac, time=None, compute_jacobian=True, compute_residual=True):
         for a in (sol, res, jac):

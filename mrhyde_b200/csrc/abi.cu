@@ -19,6 +19,7 @@
 #include "expr.hpp"
 #include "general.hpp"
 #include "halo.hpp"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3 (the injection library is looked up at run time; no-ops without a profiler)
 #include "plan.hpp"
 #include "volume_kernel.cuh"
 #include "volume_launch.hpp"
@@ -162,6 +163,13 @@ struct mrhyde_b200_plan {
 };
 
 namespace {
+
+// NVTX ranges named like the reference's Teuchos timers (assemblyManager.hpp:2183-2198, linearAlgebraInterface.hpp:640-650), so that a
+// timeline of a MrHyDE run with this library reads like the reference's `print timers` table
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
                                "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "scratch GB", "debug transient", "debug mode", nullptr};
@@ -811,7 +819,7 @@ __global__ void orphan_rows_kernel(const int32_t* __restrict__ rows, int n, Grap
   const int32_t r = rows[i];
   if (O.res) O.res[r] = 0.0;
   if (O.jac)
-    for (int64_t p = G.rowptr[r]; p < G.rowptr[r + 1]; ++p) O.jac[p] = (G.fixed[r] && G.colind[p] == r) ? 1.0 : 0.0;
+    for (int64_t p = G.rowptr[r]; p < G.rowptr[r + 1]; ++p) O.jac[p] = (G.fixed[r] && G.colind[p] == r && O.diag_one) ? 1.0 : 0.0;
 }
 
 // dofConstraints -> setJacobianConstraints: J(d,d) = 1 on strong-Dirichlet dofs (replaceLocalValues)
@@ -929,10 +937,13 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
   if (want_res && !res) fail(MRHYDE_B200_ERR_INVALID, "res is null");
   if (want_jac && !jac) fail(MRHYDE_B200_ERR_INVALID, "jac_values is null");
   CUDA_OK(cudaSetDevice(P->device));
+  NvtxRange total(want_jac ? (want_res ? "MrHyDE::AssemblyManager::computeJacRes() - total assembly" : "MrHyDE::AssemblyManager::computeJac() - Jacobian assembly")
+                           : "MrHyDE::AssemblyManager::computeRes() - residual assembly");
   OutDev out;
   out.res = want_res ? res : nullptr;
   out.jac = want_jac ? jac : nullptr;
   out.accumulate = P->accumulate ? 1 : 0;
+  out.diag_one = opt_bool(P, "use strong DBCs", true) ? 1 : 0;   // the reference calls setJacobianConstraints only then (assemblyManager_constraints.hpp:250)
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
   const bool volume = opt_bool(P, "assemble volume terms", true);
   int launched = 0;
@@ -942,11 +953,13 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     size_t slot = 0;
     record_begin(P, st, slot);
     GenLaunchStats stats;
+    NvtxRange physics("MrHyDE::AssemblyManager::computeJacRes() - physics evaluation");   // gather + physics + boundary + scatter, fused
     const char* err = gen_assemble(P->gen_dev, P->gen, P->gen_kernels, P->d_vx.p, P->d_vy.p, P->d_vz.p, P->d_conn.p, P->d_lids.p, G, out, sol, td, volume, bnd, st, &stats);
     if (err) fail(MRHYDE_B200_ERR_CUDA, std::string("general assembly launch: ") + err);
     record_end(P, st, slot);
     launched = stats.launches;
     if (want_jac && P->accumulate && P->d_fixed_diag.n > 0 && opt_bool(P, "use strong DBCs", true)) {
+      NvtxRange dbc("MrHyDE::AssemblyManager::dofConstraints()");
       const int n = (int)P->d_fixed_diag.n;
       fixed_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(P->d_fixed_diag.p, n, jac);
       ++launched;
@@ -956,6 +969,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     return;
   }
   if (volume) {
+    NvtxRange physics("MrHyDE::AssemblyManager::computeJacRes() - physics evaluation");   // gather + physics + scatter + constraints, one launch
     size_t slot = 0;
     record_begin(P, st, slot);
     const void* params;
@@ -1006,6 +1020,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     fail(MRHYDE_B200_ERR_UNSUPPORTED, "accumulate=false needs the volume pass (it defines every entry)");
   }
   if (!P->boundary.groups.empty() && opt_bool(P, "assemble boundary terms", true)) {
+    NvtxRange boundary("MrHyDE::AssemblyManager::computeJacRes() - boundary evaluation");
     OutDev bout = out;
     bout.accumulate = 1;  // boundary groups always add on top of the volume result
     launch_boundary(P->boundary, sol, td, G, bout, st);
@@ -1013,6 +1028,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     CUDA_OK(cudaGetLastError());
   }
   if (want_jac && P->accumulate && P->d_fixed_diag.n > 0 && opt_bool(P, "use strong DBCs", true)) {
+    NvtxRange dbc("MrHyDE::AssemblyManager::dofConstraints()");
     const int n = (int)P->d_fixed_diag.n;
     fixed_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(P->d_fixed_diag.p, n, jac);
     ++launched;
@@ -1074,15 +1090,12 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
   const int dim = P->dim;
   const int order = P->bases[(size_t)P->var_basis[0]].order;
   const int nqs = P->bgroups.empty() ? 0 : P->bgroups[0].nqp;
-  P->gen_host = gen_find_host(phys, dim, order, P->nqp, nqs);
-  if (!P->gen_host)
+  P->gen_host = gen_find_host(phys, dim, order, P->nqp, nqs);   // null unless the test-only emulator library is registered
+  P->gen_kernels = gen_find_device(phys, dim, order, P->nqp, nqs);   // the instantiation table (no CUDA call: host-only plans read its sizes too)
+  if (!P->gen_kernels)
     fail(MRHYDE_B200_ERR_UNSUPPORTED, "no kernel for physics '" + P->physics + "' dim " + std::to_string(dim) + " order " + std::to_string(order) + " with " +
                                           std::to_string(P->nqp) + " volume / " + std::to_string(nqs) + " side points; built: " + gen_supported_list());
-  if (!host_only) {
-    P->gen_kernels = gen_find_device(phys, dim, order, P->nqp, nqs);
-    if (!P->gen_kernels) fail(MRHYDE_B200_ERR_UNSUPPORTED, "general path: device kernel table lacks the configuration the host table has");
-  }
-  const GenKernelInfo& I = P->gen_host->info;
+  const GenKernelInfo& I = P->gen_kernels->info;
   H.info = I;
   // ---- the block must be the module's own variable / basis layout
   const std::vector<std::string> want = module_variables(phys, dim);
@@ -1211,7 +1224,10 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
     const std::string jm = opt(P, "jacobian", "auto");
     if (jm != "auto" && jm != "tensor" && jm != "lanes") fail(MRHYDE_B200_ERR_INVALID, "option jacobian must be auto|tensor|lanes");
     if (jm == "tensor" && !I.tensor) fail(MRHYDE_B200_ERR_UNSUPPORTED, "jacobian=tensor: the module's basis layout has no tensor-core build");
-    H.use_tensor = I.tensor && jm != "lanes";
+    // auto = lanes: measured on the B200 (profiles/r02_s7_general_tensor_vs_lanes.log), the FP64 tensor-core contraction does not beat
+    // the derivative lanes -- DMMA.8x8x4 runs at the FP64 FMA rate, the 27 -> 32 padding of hex-Q2 costs 40 % more FMAs, and the
+    // fragment set-up of 8 x 8 tiles outweighs the saved issue slots on Q1
+    H.use_tensor = I.tensor && jm == "tensor";
   }
   P->use_general = true;
   P->launches_per_assemble = 2 * (int)H.batches.size();
@@ -1302,7 +1318,21 @@ static void metric_host_elements(const mrhyde_b200_plan* P, const ThermalParams<
   }
 }
 
+static const GenHostKernels* need_emulator(mrhyde_b200_plan* P) {
+  if (!P->gen_host) {
+    const GenKernelInfo& I = P->gen.info;
+    P->gen_host = gen_find_host(I.physics, I.dim, I.order, I.nq, I.nqs);
+  }
+  if (!P->gen_host) fail(MRHYDE_B200_ERR_STATE, "debug_emulate: the test-only library libmrhyde_b200_emulate.so is not registered (mrhyde_b200_debug_set_emulator)");
+  return P->gen_host;
+}
+
 extern "C" {
+
+int mrhyde_b200_debug_set_emulator(void* lookup) {
+  gen_set_emulator(reinterpret_cast<GenEmulatorLookup>(lookup));
+  return MRHYDE_B200_OK;
+}
 
 const char* mrhyde_b200_version(void) { return "mrhyde_b200 0.1 (sm_100a)"; }
 const char* mrhyde_b200_last_error(void) { return g_error.c_str(); }
@@ -1360,6 +1390,15 @@ int mrhyde_b200_plan_set_function(mrhyde_b200_plan* P, const char* name, const c
 
 int mrhyde_b200_plan_set_option(mrhyde_b200_plan* P, const char* key, const char* value) {
   ABI_BEGIN
+  if (key) {
+    // experiment keys that compile parts of the kernel out or force a build variant: results may be wrong, so a production host
+    // cannot set them by accident -- they need MRHYDE_B200_DEBUG_OPTIONS=1 in the environment
+    const std::string k(key);
+    if (k == "debug skip" || k == "debug transient" || k == "debug mode") {
+      const char* e = getenv("MRHYDE_B200_DEBUG_OPTIONS");
+      if (!e || std::string(e) != "1") fail(MRHYDE_B200_ERR_INVALID, "option '" + k + "' is a kernel-debugging key: set MRHYDE_B200_DEBUG_OPTIONS=1 to allow it");
+    }
+  }
   if (!P || !key || !value) fail(MRHYDE_B200_ERR_INVALID, "set_option: null argument");
   bool known = false;
   for (const char** k = kKnownOptions; *k; ++k) if (std::string(*k) == key) known = true;
@@ -1728,6 +1767,21 @@ int mrhyde_b200_assemble_jacres(mrhyde_b200_plan* P, const double* sol, const mr
   ABI_END
 }
 
+int mrhyde_b200_plan_warmup(mrhyde_b200_plan* P, int transient, int compute_jacobian, int compute_residual) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "plan_warmup: null plan");
+  if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "plan_warmup called before mrhyde_b200_plan_finalize");
+  if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "host-only analysis plan (device = -1) has no kernels to build");
+  if (!compute_jacobian && !compute_residual) fail(MRHYDE_B200_ERR_INVALID, "plan_warmup: nothing requested");
+  if (P->use_jit && !P->use_general) {
+    CUDA_OK(cudaSetDevice(P->device));
+    const int mode = (compute_residual ? 1 : 0) | (compute_jacobian ? 2 : 0) | (P->accumulate ? 4 : 0);
+    std::string log;
+    if (!jit_variant(P, transient != 0, mode, log)) fail(MRHYDE_B200_ERR_CUDA, "jit: kernel build failed: " + log);
+  }
+  ABI_END
+}
+
 int mrhyde_b200_assemble_res(mrhyde_b200_plan* P, const double* sol, const mrhyde_b200_time* t, double* res, void* stream) {
   ABI_BEGIN
   if (!P) fail(MRHYDE_B200_ERR_INVALID, "assemble_res: null plan");
@@ -1821,6 +1875,7 @@ int mrhyde_b200_halo_sum(mrhyde_b200_plan* P, double* res, double* jac_values, v
   if (!P) fail(MRHYDE_B200_ERR_INVALID, "halo_sum: null plan");
   if (!P->halo || !P->halo->ready()) fail(MRHYDE_B200_ERR_STATE, "halo_sum: call plan_comm_init and plan_set_halo first");
   CUDA_OK(cudaSetDevice(P->device));
+  NvtxRange exp("MrHyDE::LinearAlgebraInterface::export*()");
   std::string err;
   if (!P->halo->sum(res, jac_values, (cudaStream_t)stream, err)) fail(MRHYDE_B200_ERR_NCCL, err);
   ABI_END
@@ -1994,7 +2049,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
     std::memcpy(Q.fn, H.fn, sizeof(Q.fn));
     Q.fn_state = 0; for (int f = 0; f < GEN_MAXFN; ++f) if (Q.fn[f].pad && !Q.fn[f].is_const) Q.fn_state = 1;
     for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = 0; Q.bc_fn[v] = -1; }
-    P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
+    need_emulator(P)->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
   }
   if (opt_bool(P, "assemble boundary terms", true))
     for (auto& S : H.sides) {
@@ -2006,7 +2061,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
       for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = S.bc_type[v]; Q.bc_fn[v] = S.bc_fn[v]; }
       std::memcpy(Q.fn, S.fn, sizeof(Q.fn));
       Q.fn_state = 0; for (int f = 0; f < GEN_MAXFN; ++f) if (Q.fn[f].pad && !Q.fn[f].is_const) Q.fn_state = 1;
-      P->gen_host->emulate(true, Q, (int)((Q.item_end + Q.epb - 1) / Q.epb));
+      need_emulator(P)->emulate(true, Q, (int)((Q.item_end + Q.epb - 1) / Q.epb));
     }
   gen_pull_host(H, M, compute_jacobian ? ej.data() : nullptr, compute_residual ? er.data() : nullptr, P->accumulate, compute_residual ? res : nullptr,
                 compute_jacobian ? jac : nullptr);
@@ -2097,7 +2152,7 @@ int mrhyde_b200_plan_debug_emulate_initial(mrhyde_b200_plan* P, double time, dou
   Q.epb = 3;
   Q.items = nullptr; Q.item_begin = 0; Q.item_end = M.nelem; Q.inst_base = 0;
   Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
-  P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
+  need_emulator(P)->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
   gen_pull_apply_host(H, er.data(), P->accumulate, rhs);
   ABI_END
 }
@@ -2128,7 +2183,7 @@ int mrhyde_b200_plan_debug_emulate_mass(mrhyde_b200_plan* P, const double* mass_
   Q.epb = 3;
   Q.items = nullptr; Q.item_begin = 0; Q.item_end = M.nelem; Q.inst_base = 0;
   Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
-  P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
+  need_emulator(P)->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
   gen_pull_mass_host(H, M, ej.data(), P->accumulate, lump != 0, mass_values, diag);
   ABI_END
 }
@@ -2159,7 +2214,7 @@ int mrhyde_b200_plan_debug_emulate_apply_mass(mrhyde_b200_plan* P, const double*
   Q.epb = 3;
   Q.items = nullptr; Q.item_begin = 0; Q.item_end = M.nelem; Q.inst_base = 0;
   Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
-  P->gen_host->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
+  need_emulator(P)->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
   gen_pull_apply_host(H, er.data(), P->accumulate, y);
   ABI_END
 }

@@ -37,7 +37,7 @@ GenDeviceKernels make_device_entry(const char* name, int dim, int order) {
   k.info = gen_make_info<Phys, NQ, NQS, K>(name, dim, order, MAXT, MINB, MAXT_L, MINB_L);
   k.launch = &launch_entry<Phys, NQ, NQS, K, MAXT_L, MINB_L, false>;
   k.launch_tc = nullptr;
-  if constexpr (GenLayout<Phys, NQ>::TC) k.launch_tc = &launch_entry<Phys, NQ, NQS, K, MAXT, MINB, true>;
+  if constexpr (GenLayout<Phys, NQ>::TC_CAPABLE) k.launch_tc = &launch_entry<Phys, NQ, NQS, K, MAXT, MINB, true>;
   return k;
 }
 
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
     if (!Q.O.accumulate) {
       if (Q.O.res && lane == 0) Q.O.res[r] = 0.0;
       if (Q.O.jac)
-        for (int t = lane; t < len; t += G) Q.O.jac[rs + t] = (__ldg(Q.G.colind + rs + t) == r && r < Q.n_owned) ? 1.0 : 0.0;
+        for (int t = lane; t < len; t += G) Q.O.jac[rs + t] = (__ldg(Q.G.colind + rs + t) == r && r < Q.n_owned && Q.O.diag_one) ? 1.0 : 0.0;
     }
     return;
   }
@@ -214,6 +214,20 @@ const GenDeviceKernels* gen_find_device(const std::string& physics, int dim, int
   return nullptr;
 }
 
+static GenEmulatorLookup g_emulator = nullptr;
+void gen_set_emulator(GenEmulatorLookup fn) { g_emulator = fn; }
+const GenHostKernels* gen_find_host(const std::string& physics, int dim, int order, int nq, int nqs) {
+  return g_emulator ? static_cast<const GenHostKernels*>(g_emulator(physics.c_str(), dim, order, nq, nqs)) : nullptr;
+}
+std::string gen_supported_list() {
+  std::string s;
+  for (auto& k : device_table()) {
+    if (!s.empty()) s += "; ";
+    s += std::string(k.info.physics) + " dim " + std::to_string(k.info.dim) + " order " + std::to_string(k.info.order) + " nqp " + std::to_string(k.info.nq);
+  }
+  return s;
+}
+
 void gen_free(GeneralPlanDev* D) { delete D; }
 
 GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t* tot, std::string& err) {
@@ -266,7 +280,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
 static int pick_epb(const GenKernelInfo& I, bool tensor, bool side, int64_t n_items, int epb_override) {
   // as many elements per CTA as the launch bounds allow, while MINB CTAs still fit the SM's shared memory
   const int tpe = I.tpe;
-  const int sd = side ? I.smem_doubles_side : I.smem_doubles_volume;
+  const int sd = tensor ? (side ? I.tc_smem_doubles_side : I.tc_smem_doubles_volume) : (side ? I.smem_doubles_side : I.smem_doubles_volume);
   const int max_threads = tensor ? I.tc_max_threads : I.max_threads;
   const size_t smem_cap = (size_t)(220 * 1024) / (size_t)std::max(1, tensor ? std::max(2, I.tc_min_blocks) : I.min_blocks);
   int epb = std::max(1, max_threads / tpe);
@@ -291,7 +305,7 @@ const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const
   std::memset(&td, 0, sizeof(td));
   td.alpha_u = 1.0; td.deltat = 1.0;
   OutDev O;
-  O.jac = mass; O.res = diag; O.accumulate = accumulate ? 1 : 0;
+  O.jac = mass; O.res = diag; O.accumulate = accumulate ? 1 : 0; O.diag_one = 1;
   if (!D->zero.p) {
     std::string err;
     if (!D->zero.alloc((size_t)H.n_rows, nullptr, err)) return "general mass: cannot allocate the state placeholder";
@@ -307,7 +321,7 @@ const char* gen_apply_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const Ge
   std::memset(&td, 0, sizeof(td));
   td.alpha_u = 1.0; td.deltat = 1.0;
   OutDev O;
-  O.jac = nullptr; O.res = y; O.accumulate = accumulate ? 1 : 0;
+  O.jac = nullptr; O.res = y; O.accumulate = accumulate ? 1 : 0; O.diag_one = 1;
   return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, x, td, true, false, stream, stats, 3, mass_wts);
 }
 
@@ -318,7 +332,7 @@ const char* gen_project_initial(GeneralPlanDev* D, const GeneralPlanHost& H, con
   std::memset(&td, 0, sizeof(td));
   td.alpha_u = 1.0; td.deltat = 1.0; td.time = time;
   OutDev O;
-  O.jac = nullptr; O.res = rhs; O.accumulate = accumulate ? 1 : 0;
+  O.jac = nullptr; O.res = rhs; O.accumulate = accumulate ? 1 : 0; O.diag_one = 1;
   const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0};
   return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, rhs /* state is not read in this mode: any valid vector */, td, true, false, stream, stats, 4, ones);
 }
@@ -355,7 +369,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
     int threads = ((epb * tpe + 31) / 32) * 32;
     threads = std::max(32, std::min(I.max_threads, threads));
     if (tensor) threads = std::max(64, std::min(I.tc_max_threads, 32 * epb * I.nvars * I.nvars * (I.card[0] > 24 ? 2 : 1)));   // one warp per block of the contraction (S4m), two warps at least
-    const size_t smem = (size_t)epb * (side ? I.smem_doubles_side : I.smem_doubles_volume) * sizeof(double);
+    const size_t smem = (size_t)epb * (tensor ? (side ? I.tc_smem_doubles_side : I.tc_smem_doubles_volume) : (side ? I.smem_doubles_side : I.smem_doubles_volume)) * sizeof(double);
     const int64_t nblocks = (n_items + epb - 1) / epb;
     ++launches;
     return tensor ? kd->launch_tc(side, P, (int)nblocks, threads, smem, stream) : kd->launch(side, P, (int)nblocks, threads, smem, stream);

@@ -26,7 +26,8 @@ struct GenKernelInfo {
   int tensor;                                   // 1: Jacobian by field-direction derivatives + FP64 tensor-core contraction (general_kernel.cuh, S4d / S4m)
   int max_threads, min_blocks;                  // launch bounds of the element kernel (derivative-lane build)
   int tc_max_threads, tc_min_blocks;            // launch bounds of the tensor-core build
-  int smem_doubles_volume, smem_doubles_side;   // per element
+  int smem_doubles_volume, smem_doubles_side;   // per element (derivative-lane build)
+  int tc_smem_doubles_volume, tc_smem_doubles_side;   // per element (tensor-core build: + the D region)
   int card[2], ncb[2];                          // per basis
   int var_basis[GEN_MAXVARS];
 };
@@ -41,6 +42,10 @@ struct GenHostKernels {
   void (*emulate)(bool side, const GenParams& P, int nblocks);
 };
 const GenDeviceKernels* gen_find_device(const std::string& physics, int dim, int order, int nq, int nqs);
+// host replay of the kernel stages: lives in the test-only library libmrhyde_b200_emulate.so and is registered at run time
+// (mrhyde_b200_debug_set_emulator); null in a process that has not loaded it
+typedef const void* (*GenEmulatorLookup)(const char* physics, int dim, int order, int nq, int nqs);
+void gen_set_emulator(GenEmulatorLookup fn);
 const GenHostKernels* gen_find_host(const std::string& physics, int dim, int order, int nq, int nqs);
 std::string gen_supported_list();
 

@@ -40,9 +40,11 @@ inline GenKernelInfo gen_make_info(const char* physics, int dim, int order, int 
   I.physics = physics; I.dim = dim; I.order = order; I.nq = NQ; I.nqs = NQS;
   I.tc_max_threads = maxt; I.tc_min_blocks = minb;
   I.max_threads = maxt_l; I.min_blocks = minb_l;
-  I.N = Phys::N; I.nvars = Phys::NVAR; I.nbasis = Phys::NBASIS; I.nfn = Phys::NFN; I.K = K; I.tpe = GenBlock<Phys, NQ, K, false>::TPE; I.tensor = GenLayout<Phys, NQ>::TC ? 1 : 0;
-  I.smem_doubles_volume = GenLayout<Phys, NQ>::SIZE;
-  I.smem_doubles_side = GenLayout<Phys, NQS>::SIZE;
+  I.N = Phys::N; I.nvars = Phys::NVAR; I.nbasis = Phys::NBASIS; I.nfn = Phys::NFN; I.K = K; I.tpe = GenBlock<Phys, NQ, K, false>::TPE; I.tensor = GenLayout<Phys, NQ>::TC_CAPABLE ? 1 : 0;
+  I.smem_doubles_volume = GenLayout<Phys, NQ, false>::SIZE;
+  I.smem_doubles_side = GenLayout<Phys, NQS, false>::SIZE;
+  I.tc_smem_doubles_volume = GenLayout<Phys, NQ, true>::SIZE;
+  I.tc_smem_doubles_side = GenLayout<Phys, NQS, true>::SIZE;
   for (int b = 0; b < 2; ++b) { I.card[b] = b < Phys::NBASIS ? Phys::card(b) : 0; I.ncb[b] = b < Phys::NBASIS ? Phys::ncb(b) : 0; }
   for (int v = 0; v < GEN_MAXVARS; ++v) I.var_basis[v] = v < Phys::NVAR ? Phys::var_basis(v) : 0;
   return I;

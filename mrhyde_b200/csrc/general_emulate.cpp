@@ -1,6 +1,7 @@
 // Host replay of the general element kernel's stage functions (general_kernel.cuh compiled by the host compiler).
-// A debugging aid for machines without a GPU: reachable only through mrhyde_b200_plan_debug_emulate on host-only
-// plans (device = -1); mrhyde_b200_assemble_* never calls it -- there is no CPU fallback.
+// TEST-ONLY LIBRARY: this file is NOT part of libmrhyde_b200.so.  It builds into libmrhyde_b200_emulate.so, which tests load next to
+// the product library and register with mrhyde_b200_debug_set_emulator; the mrhyde_b200_plan_debug_emulate* entry points (host-only
+// plans, device = -1) then replay the kernel stages on the CPU.  mrhyde_b200_assemble_* never reaches it -- there is no CPU fallback.
 #include <cstring>
 #include <vector>
 
@@ -11,10 +12,10 @@ namespace mrhyde_b200 {
 
 namespace {
 
-template <class Phys, int NQ, int K, bool SIDE>
+template <class Phys, int NQ, int K, bool SIDE, bool TCK>
 void emulate_blocks(const GenParams& P, int nblocks) {
-  typedef GenBlock<Phys, NQ, K, SIDE> Bk;
-  typedef GenLayout<Phys, NQ> L;
+  typedef GenBlock<Phys, NQ, K, SIDE, TCK> Bk;
+  typedef GenLayout<Phys, NQ, TCK> L;
   std::vector<double> sm((size_t)P.epb * L::SIZE);
   for (int blk = 0; blk < nblocks; ++blk) {
     std::fill(sm.begin(), sm.end(), 0.0);
@@ -27,7 +28,7 @@ void emulate_blocks(const GenParams& P, int nblocks) {
     for (int i = 0; i < P.epb * NQ * Bk::S3F_KINDS; ++i) Bk::s3f(P, sm.data(), blk, i);
     for (int i = 0; i < P.epb * NQ; ++i) Bk::s4a(P, sm.data(), blk, i);
     if (P.elem_jac) {
-      if (Bk::TC && P.tensor) {   // field-direction derivatives + contraction (the device runs the contraction on the FP64 tensor cores)
+      if constexpr (Bk::TC) {   // field-direction derivatives + contraction (the device runs the contraction on the FP64 tensor cores)
         for (int i = 0; i < P.epb * NQ * Bk::NCV; ++i) Bk::s4d(P, sm.data(), blk, i);
         for (int i = 0; i < P.epb * L::NVAR * L::NVAR; ++i) Bk::s4m_item(P, sm.data(), blk, i);
       } else {
@@ -40,11 +41,16 @@ void emulate_blocks(const GenParams& P, int nblocks) {
 
 template <class Phys, int NQ, int NQS, int K>
 void emulate_entry(bool side, const GenParams& P, int nblocks) {
-  if (side) emulate_blocks<Phys, NQS, K, true>(P, nblocks);
-  else emulate_blocks<Phys, NQ, K, false>(P, nblocks);
+  if (P.tensor && GenLayout<Phys, NQ>::TC_CAPABLE) {   // replay the stages of the build the plan selected (option jacobian)
+    if (side) emulate_blocks<Phys, NQS, K, true, true>(P, nblocks);
+    else emulate_blocks<Phys, NQ, K, false, true>(P, nblocks);
+    return;
+  }
+  if (side) emulate_blocks<Phys, NQS, K, true, false>(P, nblocks);
+  else emulate_blocks<Phys, NQ, K, false, false>(P, nblocks);
 }
 
-struct HostEntry { GenHostKernels k; };
+}  // namespace
 
 std::vector<GenHostKernels>& host_table() {
   static std::vector<GenHostKernels> T;
@@ -57,21 +63,11 @@ std::vector<GenHostKernels>& host_table() {
   return T;
 }
 
-}  // namespace
+}  // namespace mrhyde_b200
 
-const GenHostKernels* gen_find_host(const std::string& physics, int dim, int order, int nq, int nqs) {
-  for (auto& k : host_table())
-    if (physics == k.info.physics && dim == k.info.dim && order == k.info.order && nq == k.info.nq && (nqs == 0 || nqs == k.info.nqs)) return &k;
+// what mrhyde_b200_debug_set_emulator takes: (physics, dim, order, volume points, side points) -> const GenHostKernels* or null
+extern "C" const void* mrhyde_b200_emulator_lookup(const char* physics, int dim, int order, int nq, int nqs) {
+  for (auto& k : mrhyde_b200::host_table())
+    if (std::string(physics) == k.info.physics && dim == k.info.dim && order == k.info.order && nq == k.info.nq && (nqs == 0 || nqs == k.info.nqs)) return &k;
   return nullptr;
 }
-
-std::string gen_supported_list() {
-  std::string s;
-  for (auto& k : host_table()) {
-    if (!s.empty()) s += "; ";
-    s += std::string(k.info.physics) + " dim " + std::to_string(k.info.dim) + " order " + std::to_string(k.info.order) + " nqp " + std::to_string(k.info.nq);
-  }
-  return s;
-}
-
-}  // namespace mrhyde_b200

@@ -331,7 +331,7 @@ MRH_HD void gen_initial_point(const QpCtx& c, T (&Cf)[Phys::NVAR][Phys::NC]) {
 }
 
 // ---- shared-memory layout of one element (offsets in doubles; every block is a multiple of 2 doubles) ---------
-template <class Phys, int NQ>
+template <class Phys, int NQ, bool WITH_D = false>   // WITH_D: the tensor-core build's D region (requested for single-basis layouts only)
 struct GenLayout {
   static constexpr int DIM = Phys::DIM, NV = 1 << DIM, NVAR = Phys::NVAR, NC = Phys::NC, NFN = Phys::NFN + GEN_MAXVARS;
   static constexpr int N = Phys::N;
@@ -355,7 +355,8 @@ struct GenLayout {
   static constexpr int FN = FT + NQ * NVAR * NC;
   static constexpr int CV = FN + even(NQ * NFN);
   // tensor-core contraction (single-basis HGRAD modules): D_q = d Cf / d F at every point, [q][(v,k)][(w,l)]
-  static constexpr bool TC = (Phys::NBASIS == 1);
+  static constexpr bool TC_CAPABLE = (Phys::NBASIS == 1);
+  static constexpr bool TC = TC_CAPABLE && WITH_D;
   static constexpr int NCV = NVAR * NC;
   static constexpr int DM = CV + NQ * NVAR * NC;
   static constexpr int DS = NCV + 2;   // row stride of D (padded: the four rows a fragment load touches sit in distinct banks)
@@ -370,9 +371,9 @@ __device__ __forceinline__ void mrh_dmma(double (&c)[2], const double a, const d
 #endif
 
 // ---- the stages ----------------------------------------------------------------------------------------------
-template <class Phys, int NQ, int K, bool SIDE>
+template <class Phys, int NQ, int K, bool SIDE, bool TCK = false>
 struct GenBlock {
-  typedef GenLayout<Phys, NQ> L;
+  typedef GenLayout<Phys, NQ, TCK> L;
   static constexpr int DIM = Phys::DIM, NV = L::NV, N = L::N, NVAR = L::NVAR, NC = L::NC;
   static constexpr int TPE = N / K;   // threads per element in the derivative stage
   static_assert(N % K == 0, "K must divide the element dof count");
@@ -898,9 +899,9 @@ struct GenBlock {
 template <class Phys, int NQ, int K, bool SIDE, int MAXT, int MINB, bool TCK>
 __global__ void __launch_bounds__(MAXT, MINB) gen_element_kernel(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) double gen_smem[];
-  typedef GenBlock<Phys, NQ, K, SIDE> Bk;
+  typedef GenBlock<Phys, NQ, K, SIDE, TCK> Bk;
   const int blk = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
-  typedef GenLayout<Phys, NQ> L;
+  typedef GenLayout<Phys, NQ, TCK> L;
   for (int i = tid; i < P.epb * (L::N > L::NV ? L::N : L::NV); i += T) Bk::s0(P, gen_smem, blk, i);
   __syncthreads();
   for (int i = tid; i < P.epb * NQ; i += T) Bk::s1(P, gen_smem, blk, i);

@@ -87,6 +87,7 @@ struct OutDev {
   double* res;       // may be null (compute_residual = 0)
   double* jac;       // may be null (compute_jacobian = 0)
   int accumulate;    // 1: += into caller-zeroed arrays (reference contract); 0: overwrite
+  int diag_one;      // overwrite mode: strong-Dirichlet rows get J(d,d) = 1 (setJacobianConstraints, only with `use strong DBCs`) or stay zero rows
 };
 
 // ---- flattened expression programs (expr.hpp) -------------------------------------------------------------

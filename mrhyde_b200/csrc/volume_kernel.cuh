@@ -900,7 +900,7 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
     if (!ACC && active) {
       const int len = (int)(__ldg(G.rowptr + row + 1) - R.base);
       const int diag_k = (int)((unsigned)R.rec.y >> 16);
-      if (HAS_JAC) for (int k = 0; k < len; ++k) O.jac[R.base + k] = (k == diag_k) ? 1.0 : 0.0;
+      if (HAS_JAC) for (int k = 0; k < len; ++k) O.jac[R.base + k] = (k == diag_k && O.diag_one) ? 1.0 : 0.0;
       if (HAS_RES) O.res[row] = 0.0;
     }
     return;

@@ -341,6 +341,12 @@ def test_every_build_variant_compiles(oracle_lib, product_lib, ring, shear):
     if shear:
         upd["Mesh/shear"] = shear
     op, plan = _host_plan(oracle_lib, configs.variant(configs.THERMAL_3D, **upd), options={"ring": ring})
+    import os
+    from mrhyde_b200.capi import MrhydeB200Error
+    os.environ.pop("MRHYDE_B200_DEBUG_OPTIONS", None)
+    with pytest.raises(MrhydeB200Error):        # kernel-debugging keys are refused unless the environment allows them
+        plan.set_option("debug transient", 1)
+    os.environ["MRHYDE_B200_DEBUG_OPTIONS"] = "1"
     for transient in (0, 1):
         for mode in (1, 3, 6):   # residual only, residual + Jacobian overwrite, Jacobian only accumulate
             plan.set_option("debug transient", transient)

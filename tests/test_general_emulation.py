@@ -39,13 +39,15 @@ def test_kernel_stages_match_oracle(oracle_lib, product_lib, name, cfg, opts, ta
         assert plan.stat("general_batches") > 1
 
 
-@pytest.mark.parametrize("name", ["thermal3d-state-dirk", "le3d-state-mu", "ns2d-state-viscosity", "maxwell-state-sigma", "le3d", "ns3d-neumann", "thermal3d-q2"])
-def test_derivative_lane_stages_match_oracle(oracle_lib, product_lib, name):
-    """option jacobian=lanes: the stage functions of the build with one derivative lane per element dof (S4b), including coefficients
-    that read solution fields, against the oracle (the default replay above runs the tensor-core build's stages for the HGRAD modules)."""
+@pytest.mark.parametrize("name", ["thermal3d-state-dirk", "le3d-state-mu", "ns2d-state-viscosity", "thermal2d-weak-state", "le3d", "le3d-q2", "le2d-weak-neumann",
+                                  "ns3d-neumann", "ns2d-bwe", "thermal3d-q2", "thermal3d-advection"])
+def test_tensor_core_build_stages_match_oracle(oracle_lib, product_lib, name):
+    """option jacobian=tensor (single-basis HGRAD modules): field-direction derivatives (S4d) + the contraction the device runs on the
+    FP64 tensor cores (S4m), including coefficients that read solution fields, against the oracle.  The default replay above runs
+    the stages of the derivative-lane build (S4b)."""
     _, cfg, opts, tableau, zero = next(c for c in configs.general_cases() if c[0] == name)
     op = oracle_lib.OracleProblem(cfg)
-    plan = helpers.plan_from_oracle(op, cfg, device=-1, options=dict({"kernel": "general", "jacobian": "lanes"}, **opts))
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options=dict({"kernel": "general", "jacobian": "tensor"}, **opts))
     u = np.zeros(op.num_dofs) if zero else helpers.manufactured_state(op)
     ts, kw = _setup_time(op, tableau)
     res_ref, jac_ref = op.assemble_jacres(u, **kw)

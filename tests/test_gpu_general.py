@@ -56,14 +56,15 @@ def test_general_path_matches_oracle(oracle_lib, product_lib, name, cfg, opts, t
     assert e_jac < TOL, "Jacobian rel err %.3e" % e_jac
 
 
-@pytest.mark.parametrize("name", ["thermal3d-q2", "le3d", "le3d-q2", "le2d-weak-neumann", "ns2d-bwe", "ns3d-reference-uz-rows", "ns3d-neumann"])
-def test_derivative_lane_build_matches_oracle(oracle_lib, product_lib, name):
-    """The single-basis modules assemble Jacobians with the tensor-core build by default (field-direction derivatives + mma.m8n8k4
-    contraction); option jacobian=lanes selects the build with one derivative lane per element dof -- both must match the oracle."""
+@pytest.mark.parametrize("name", ["thermal3d-q2", "le3d", "le3d-q2", "le2d-weak-neumann", "ns2d-bwe", "ns3d-reference-uz-rows", "ns3d-neumann",
+                                  "thermal3d-state-dirk", "le3d-state-mu", "ns2d-state-viscosity"])
+def test_tensor_core_build_matches_oracle(oracle_lib, product_lib, name):
+    """option jacobian=tensor: field-direction derivatives + mma.m8n8k4 (FP64 tensor core) contraction for the single-basis HGRAD modules;
+    the default (jacobian=lanes, one derivative lane per element dof) is what test_general_path_matches_oracle runs -- both must match the oracle."""
     case = next(c for c in configs.general_cases() if c[0] == name)
     _, cfg, opts, tableau, zero = case
     op = oracle_lib.OracleProblem(cfg)
-    plan = helpers.plan_from_oracle(op, cfg, options=dict({"kernel": "general", "jacobian": "lanes"}, **opts))
+    plan = helpers.plan_from_oracle(op, cfg, options=dict({"kernel": "general", "jacobian": "tensor"}, **opts))
     u = np.zeros(op.num_dofs) if zero else helpers.manufactured_state(op)
     ts, kw = _time(op, tableau)
     res_ref, jac_ref = op.assemble_jacres(u, **kw)

@@ -23,7 +23,17 @@ def _make(kind, n, rank, world):
         if kind == "thermal_nccl":
             options["halo transport"] = "nccl"
         return ThermalBrick(3, n, device=rank, rank=rank, nranks=world, options=options)
+    if kind == "maxwell":      # edge / face lattices cut into z-slabs (problems.slab_partition); n[0] == n[1]
+        from mrhyde_b200.problems import MaxwellBrick
+        return MaxwellBrick(n[0], device=rank, rank=rank, nranks=world, nz=n[2])
+    if kind == "leq2":         # hex-Q2 node lattice cut into z-slabs
+        from mrhyde_b200.problems import ElasticityQ2Brick
+        return ElasticityQ2Brick(n[0], device=rank, rank=rank, nranks=world, nz=n[2])
     return SystemBrick({"le": "linearelasticity", "ns": "navier stokes"}[kind], 3, n, device=rank, rank=rank, nranks=world, options={"batch elems": 300})
+
+
+def _size(kind):
+    return {"maxwell": (6, 6, 4), "leq2": (4, 4, 3)}.get(kind, N)
 
 
 def _worker(rank, world, port, q, kind="thermal"):
@@ -48,7 +58,7 @@ def _worker(rank, world, port, q, kind="thermal"):
 def _worker_body(rank, world, q, kind, dev):
     import torch
     import torch.distributed as dist
-    prob = _make(kind, N, rank, world)
+    prob = _make(kind, _size(kind), rank, world)
     uid = torch.from_numpy(prob.plan.comm_unique_id()).to(dev) if rank == 0 else torch.zeros(128, dtype=torch.uint8, device=dev)
     dist.broadcast(uid, 0)
     prob.plan.comm_init(uid.cpu().numpy(), rank, world)
@@ -77,6 +87,12 @@ def _oracle_global(oracle_lib, kind, n, ug):
     mesh = {"Mesh/NX": n[0], "Mesh/NY": n[1], "Mesh/NZ": n[2], "Mesh/perturb": 0.0}
     if kind.startswith("thermal"):
         cfg = configs.variant(configs.THERMAL_3D, **mesh)
+    elif kind == "maxwell":
+        cfg = configs.variant(configs.MAXWELL_3D, **dict(mesh, **{"Physics/Dirichlet conditions": {}, "Functions": {"current x": "sin(2*pi*z)"}}))
+    elif kind == "leq2":
+        cfg = configs.variant(configs.LE_3D, **dict(mesh, **{"Discretization/order": {"dx": 2, "dy": 2, "dz": 2}, "Discretization/quadrature": 4,
+                                                             "Functions": {"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)*sin(pi*z)",
+                                                                           "source dy": "sin(2*pi*x)*sin(2*pi*y)*sin(2*pi*z)", "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"}}))
     elif kind == "le":
         cfg = configs.variant(configs.LE_3D, **dict(mesh, Functions={"lambda": "1.0", "mu": "1.0", "source dx": "sin(pi*x)*sin(pi*y)",
                                                                        "source dy": "sin(2*pi*x)*sin(2*pi*y)", "source dz": "sin(3*pi*x)*sin(3*pi*y)*sin(3*pi*z)"}))
@@ -86,7 +102,7 @@ def _oracle_global(oracle_lib, kind, n, ug):
     return op.assemble_jacres(ug)
 
 
-@pytest.mark.parametrize("kind", ["thermal", "thermal_nccl", "thermal_overlap", "le", "ns"])
+@pytest.mark.parametrize("kind", ["thermal", "thermal_nccl", "thermal_overlap", "le", "ns", "maxwell", "leq2"])
 def test_two_gpu_halo_sum_equals_single_gpu(oracle_lib, product_lib, kind):
     import torch
     if torch.cuda.device_count() < 2:
@@ -96,7 +112,7 @@ def test_two_gpu_halo_sum_equals_single_gpu(oracle_lib, product_lib, kind):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "thermal_overlap": 7, "le": 3, "ns": 5, "thermal_nccl": 9}[kind]
+    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "thermal_overlap": 7, "le": 3, "ns": 5, "thermal_nccl": 9, "maxwell": 11, "leq2": 13}[kind]
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
@@ -115,7 +131,8 @@ def test_two_gpu_halo_sum_equals_single_gpu(oracle_lib, product_lib, kind):
             if p.is_alive():
                 p.kill()
     outs.sort(key=lambda t: t[0])
-    glob = _make(kind, (N[0], N[1], world * N[2]), 0, 1)
+    n = _size(kind)
+    glob = _make(kind, (n[0], n[1], world * n[2]), 0, 1)
     dev = torch.device("cuda:0")
     # the same state on the global mesh: value of every global row from the rank that owns it
     ug = np.zeros(glob.n_rows)
@@ -129,7 +146,7 @@ def test_two_gpu_halo_sum_equals_single_gpu(oracle_lib, product_lib, kind):
     res_g, jac_g = d_res.cpu().numpy(), d_jac.cpu().numpy()
     scale_r, scale_j = np.abs(res_g).max(), np.abs(jac_g).max()
     # oracle leg: the single-GPU assembly of the whole mesh is itself the oracle's (same rows, same graph)
-    res_o, jac_o = _oracle_global(oracle_lib, kind, (N[0], N[1], world * N[2]), ug)
+    res_o, jac_o = _oracle_global(oracle_lib, kind, (n[0], n[1], world * n[2]), ug)
     assert np.max(np.abs(res_g - res_o)) <= 1e-12 * scale_r and np.max(np.abs(jac_g - jac_o)) <= 1e-12 * scale_j
     for rank, gids, res, rp, ci, jac, st in outs:
         own = gids[: len(st)]

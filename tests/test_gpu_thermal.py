@@ -327,3 +327,30 @@ def test_full_size_properties(product_lib, kernel_build):
     plan.assemble_jacres(u, res2, jac2)
     torch.cuda.synchronize()
     assert torch.equal(res2, res) and torch.equal(jac2, jac)
+
+
+def test_overwrite_mode_without_strong_dbcs_leaves_fixed_rows_zero(oracle_lib, product_lib, kernel_build):
+    """`use strong DBCs: false` with is_fixed rows present: the reference's scatter still skips those rows but never calls
+    setJacobianConstraints (assemblyManager_constraints.hpp:250), so they stay zero rows -- in overwrite mode as in accumulate mode
+    (ADVICE round 1).  Also: plan.warmup builds the variants up front, so these calls do not compile."""
+    import torch
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 6, "Mesh/NY": 5, "Mesh/NZ": 4})
+    op = oracle_lib.OracleProblem(cfg)
+    u = helpers.manufactured_state(op)
+    outs = {}
+    for kernel in ("sweep", "general"):
+        for acc in ("true", "false"):
+            plan = helpers.plan_from_oracle(op, cfg, options={"use strong DBCs": "false", "accumulate": acc, "kernel": kernel})
+            plan.warmup(transient=False, compute_jacobian=True, compute_residual=True)
+            d_u, d_res, d_jac = _device_arrays(op, u)
+            if acc == "false":
+                d_res.fill_(7.0); d_jac.fill_(7.0)
+            plan.assemble_jacres(d_u, d_res, d_jac)
+            torch.cuda.synchronize()
+            outs[(kernel, acc)] = (d_res.cpu().numpy(), d_jac.cpu().numpy())
+    fixed = op.is_fixed.astype(bool)
+    rows = np.repeat(np.arange(op.num_dofs), np.diff(op.rowptr))
+    for key, (res, jac) in outs.items():
+        assert np.all(jac[fixed[rows]] == 0.0) and np.all(res[fixed] == 0.0), key
+        assert np.array_equal(res, outs[("sweep", "true")][0]) or helpers.rel_err_vec(res, outs[("sweep", "true")][0]) < TOL
+        assert helpers.rel_err_rows(jac, outs[("sweep", "true")][1], op.rowptr) < TOL

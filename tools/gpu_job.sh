@@ -1,38 +1,24 @@
 #!/bin/bash
-# The GPU job of the moment: `gpurun --timeout T -- 'bash tools/gpu_job.sh'`.  Overwritten between calls; results that matter are copied to profiles/.
+# The GPU job of the moment: `gpurun --gpus N --timeout T -- 'bash tools/gpu_job.sh N'`.  Overwritten between calls; results that matter are copied to profiles/.
 mkdir -p gpurun_out
-L=gpurun_out/r02_s7.log
+L=gpurun_out/r02_s9.log
 : > $L
+N=${1:-8}
 b() {
   python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: continue
-    r=d['roofline']; print('$1', 'ms', round(d['ms_per_step'],4), 'kernel_ms', round(r['kernel_ms'],4), 'frac', round(r['frac'],4), 'M elem/s', round(d['value']/1e6,2), 'e2e M/s', round(d['e2e']['value']/1e6,2))
+    r=d['roofline']; print('$1', 'n_gpus', d['n_gpus'], d['scaling'], 'ms', round(d['ms_per_step'],4), 'median', round(d.get('ms_per_step_median',0),4), 'kernel_ms', round(r['kernel_ms'],4), 'G elem/s', round(d['value']/1e9,4), 'e2e M/s', round(d['e2e']['value']/1e6,1), d['config'].get('parallelism'))
+    open('gpurun_out/r02_s9_lines.jsonl','a').write(l)
 "
 }
-echo "== general path tests" >> $L
-timeout 900 python -m pytest tests/test_gpu_general.py tests/test_gpu_fullsize.py -x -q -k "not thermal_128" 2>&1 | tail -3 >> $L
-echo "== bench general (tensor | lanes)" >> $L
-for w in ns leq2 le; do
-  for j in tensor lanes; do
-    timeout 400 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-traffic --opt jacobian=$j 2>> gpurun_out/r02_s7.err | b "[$w $j]" >> $L
-  done
-done
-timeout 400 python bench.py --workload maxwell --steps 10 --warmup 3 --no-cpu-baseline --no-traffic 2>> gpurun_out/r02_s7.err | b "[maxwell]" >> $L
-echo "== launch lists" >> $L
-for w in ns leq2; do
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 4 -c 2 --csv python bench.py --workload $w --traffic-child --steps 1 --warmup 3 2>/dev/null | grep -E "gen_|mrh_" | cut -c60-300 >> $L
-done
-echo "== thermal variants" >> $L
-run() { v2=$(echo "$*" | sed 's/_/\\ /g'); eval timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-traffic $v2 2>> gpurun_out/r02_s7.err | b "[$*]" >> $L; }
-run
-run --opt prefetch=false
-run --opt stage1=early
-run --opt stage1=early --opt prefetch=false
-timeout 300 python -m pytest tests/test_gpu_thermal.py -x -q 2>&1 | tail -2 >> $L
-echo "== ncu" >> $L
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gen_element -s 3 -c 1 -o gpurun_out/r02_s7_leq2_elem -f python bench.py --workload leq2 --n 40 --traffic-child --steps 1 --warmup 3 > /dev/null 2>> gpurun_out/r02_s7.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gen_element -s 3 -c 1 -o gpurun_out/r02_s7_ns_elem -f python bench.py --workload ns --n 64 --traffic-child --steps 1 --warmup 3 > /dev/null 2>> gpurun_out/r02_s7.err
+tr() { n=$1; timeout -k 5 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $2 bench.py --gpus $n --steps 30 --warmup 5 --no-cpu-baseline "${@:3}" 2>> gpurun_out/r02_s9.err; }
+tr 8 29511 | b "[thermal weak]" >> $L
+tr 8 29512 --scaling strong | b "[thermal strong]" >> $L
+tr 4 29513 | b "[thermal weak]" >> $L
+tr 8 29514 --workload maxwell --scaling strong | b "[maxwell strong]" >> $L
+tr 8 29515 --workload leq2 --scaling strong | b "[leq2 strong]" >> $L
+MRHYDE_B200_HALO_TRANSPORT=nccl tr 8 29516 | b "[thermal weak nccl]" >> $L
 cat $L

@@ -7,6 +7,7 @@ sys.path.insert(0, ROOT)
 from mrhyde_b200.problems import ThermalBrick
 
 def main():
+    os.environ["MRHYDE_B200_DEBUG_OPTIONS"] = "1"   # the tool forces build variants through the kernel-debugging keys
     n, out = int(sys.argv[1]), sys.argv[2]
     opts, transient, mode = {}, 0, None
     args = sys.argv[3:]
