@@ -167,6 +167,12 @@ int mrhyde_b200_assemble_jacres(mrhyde_b200_plan* plan, const double* sol, const
                                 int compute_jacobian, int compute_residual, double* res, double* jac_values,
                                 void* stream);
 /* assembleRes (jacres.hpp:668-875): residual only (the ScalarT workset path). */
+/* assembleJacRes(..., useadjoint = true, ...) (assemblyManager_jacres.hpp:119-630 with the useadjoint branches: updateJac :1459-1475,
+ * updateJacBoundary :1047-1062): the residual is the forward one, every local Jacobian is filled TRANSPOSED before the scatter --
+ * entry (row, col) receives d res(col) / d u(row), strong-Dirichlet rows are skipped as rows of the transposed matrix -- and thermal's
+ * weak-Dirichlet sides use sf = 1 (thermal.cpp:197-201).  Seeding modes for discretized-parameter sensitivities (seedwhat = 3) and the
+ * previous-step Jacobians (seedwhat = 2) are not built. */
+int mrhyde_b200_assemble_jacres_adjoint(mrhyde_b200_plan* plan, const double* sol, const mrhyde_b200_time* t, double* res, double* jac_values, void* stream);
 /* Builds the plan-specialised kernel variant an upcoming call will need -- (steady | transient stage) x (residual, Jacobian, both) in
  * the plan's output mode -- so that no assemble call compiles (NVRTC) on the hot path and build failures surface at set-up.
  * finalize pre-builds the steady residual + Jacobian variant only.  No-op for plans on the ahead-of-time kernels. */
@@ -211,6 +217,13 @@ int mrhyde_b200_plan_comm_init(mrhyde_b200_plan* plan, const uint8_t* id128, int
  * exportMatrixFromOverlapped fills).  n_cols >= n_rows.  Collective over the communicator. */
 int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* plan, int64_t n_cols, const int64_t* col_gids /*host [n_cols]*/);
 int mrhyde_b200_halo_sum(mrhyde_b200_plan* plan, double* res, double* jac_values, void* stream);
+/* The OWNED matrix after halo_sum, i.e. what the reference obtains with fillComplete(J_over) -> Export(ADD) -> fillComplete(J)
+ * (solverManager_solvers.hpp:463-466, linearAlgebraInterface_matrix.hpp:233-237), needs no compaction pass here: owned rows come
+ * first in the overlapped numbering, so the owned CSR matrix is the PREFIX of the arrays the caller already holds --
+ *   rows [0, n_owned_rows), row_map[0 .. n_owned_rows], entries / jac_values [0, nnz_owned) --
+ * with column ids in the local numbering of set_halo's col_gids (owned, ghost rows, column-only ghosts = the Tpetra column map of J).
+ * Ghost rows [n_owned_rows, n_rows) hold this rank's partial sums only and are not part of the owned matrix. */
+int mrhyde_b200_plan_owned_extent(mrhyde_b200_plan* plan, int64_t* n_owned_rows, int64_t* nnz_owned);
 
 /* ---- introspection (tests, bench) ----------------------------------------------------------- */
 /* keys: "n_chains" "n_columns" "n_segments" "n_levels" "n_steps" "n_patterns" "n_pattern_slots" "n_batches" "max_batches_per_step" "ring_capacity"

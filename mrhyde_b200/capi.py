@@ -27,7 +27,7 @@ SYMBOLS = [
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
     "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_class_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_plan_debug_chain_rows", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
-    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_debug_set_emulator", "mrhyde_b200_plan_warmup", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
+    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_debug_set_emulator", "mrhyde_b200_plan_warmup", "mrhyde_b200_assemble_jacres_adjoint", "mrhyde_b200_plan_owned_extent", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
     "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
 
@@ -94,6 +94,8 @@ def lib():
         L.mrhyde_b200_plan_add_boundary_group.argtypes = [C.c_void_p, C.POINTER(BoundaryGroup)]
         L.mrhyde_b200_plan_finalize.argtypes = [C.c_void_p]
         L.mrhyde_b200_assemble_jacres.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(TimeData), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_assemble_jacres_adjoint.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(TimeData), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_plan_warmup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.mrhyde_b200_assemble_res.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(TimeData), C.c_void_p, C.c_void_p]
         L.mrhyde_b200_assemble_jacres_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(TimeData), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_comm_unique_id.argtypes = [C.c_void_p]
@@ -325,6 +327,11 @@ class AssemblyPlan:
         self._chk(self.L.mrhyde_b200_assemble_res(self.h, _ptr(sol), time.ref() if time is not None else None, _ptr(res),
                                                 C.c_void_p(stream) if stream else None))
 
+    def assemble_jacres_adjoint(self, sol, res, jac, time=None, stream=None):
+        """useadjoint = true: forward residual, transposed local Jacobians (device buffers)."""
+        self._chk(self.L.mrhyde_b200_assemble_jacres_adjoint(self.h, _ptr(sol), time.ref() if time is not None else None, _ptr(res), _ptr(jac),
+                                                              C.c_void_p(stream) if stream else None))
+
     def warmup(self, transient=False, compute_jacobian=True, compute_residual=True):
         """Builds the specialised kernel variant of an upcoming call now (no NVRTC compile inside the first assemble call)."""
         self._chk(self.L.mrhyde_b200_plan_warmup(self.h, int(transient), int(compute_jacobian), int(compute_residual)))
@@ -367,6 +374,12 @@ class AssemblyPlan:
         """col_gids: global ids of the local column ids (rows first, then column-only ghosts)."""
         g = np.ascontiguousarray(col_gids, dtype=np.int64)
         self._chk(self.L.mrhyde_b200_plan_set_halo(self.h, len(g), _ptr(g)))
+
+    def owned_extent(self):
+        """(owned rows, non-zeros of the owned rows): the owned matrix after halo_sum is the prefix of the caller's CSR arrays."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._chk(self.L.mrhyde_b200_plan_owned_extent(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def halo_sum(self, res, jac, stream=None):
         self._chk(self.L.mrhyde_b200_halo_sum(self.h, _ptr(res), _ptr(jac), C.c_void_p(stream) if stream else None))

@@ -930,7 +930,7 @@ const JitKernel* jit_variant(mrhyde_b200_plan* P, bool transient, int mode, std:
   return raw;
 }
 
-void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool want_jac, bool want_res, double* res, double* jac, cudaStream_t st) {
+void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool want_jac, bool want_res, double* res, double* jac, cudaStream_t st, bool adjoint = false) {
   if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "assemble called before mrhyde_b200_plan_finalize");
   if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "host-only analysis plan (device = -1) cannot assemble: there is no CPU path");
   if (!sol) fail(MRHYDE_B200_ERR_INVALID, "sol is null");
@@ -954,7 +954,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     record_begin(P, st, slot);
     GenLaunchStats stats;
     NvtxRange physics("MrHyDE::AssemblyManager::computeJacRes() - physics evaluation");   // gather + physics + boundary + scatter, fused
-    const char* err = gen_assemble(P->gen_dev, P->gen, P->gen_kernels, P->d_vx.p, P->d_vy.p, P->d_vz.p, P->d_conn.p, P->d_lids.p, G, out, sol, td, volume, bnd, st, &stats);
+    const char* err = gen_assemble(P->gen_dev, P->gen, P->gen_kernels, P->d_vx.p, P->d_vy.p, P->d_vz.p, P->d_conn.p, P->d_lids.p, G, out, sol, td, volume, bnd, st, &stats, adjoint);
     if (err) fail(MRHYDE_B200_ERR_CUDA, std::string("general assembly launch: ") + err);
     record_end(P, st, slot);
     launched = stats.launches;
@@ -1023,7 +1023,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     NvtxRange boundary("MrHyDE::AssemblyManager::computeJacRes() - boundary evaluation");
     OutDev bout = out;
     bout.accumulate = 1;  // boundary groups always add on top of the volume result
-    launch_boundary(P->boundary, sol, td, G, bout, st);
+    launch_boundary(P->boundary, sol, td, G, bout, st, adjoint);
     launched += (int)P->boundary.groups.size();
     CUDA_OK(cudaGetLastError());
   }
@@ -1767,6 +1767,17 @@ int mrhyde_b200_assemble_jacres(mrhyde_b200_plan* P, const double* sol, const mr
   ABI_END
 }
 
+int mrhyde_b200_assemble_jacres_adjoint(mrhyde_b200_plan* P, const double* sol, const mrhyde_b200_time* t, double* res, double* jac_values, void* stream) {
+  ABI_BEGIN
+  if (!P) fail(MRHYDE_B200_ERR_INVALID, "assemble_jacres_adjoint: null plan");
+  TimeDev td;
+  fill_time(t, td, true);
+  // the sweep kernel's local matrices are symmetric (thermal without advection and without state-dependent coefficients): the
+  // transposed fill changes nothing there; its boundary kernel and the general path transpose explicitly
+  do_assemble(P, sol, td, true, true, res, jac_values, (cudaStream_t)stream, true);
+  ABI_END
+}
+
 int mrhyde_b200_plan_warmup(mrhyde_b200_plan* P, int transient, int compute_jacobian, int compute_residual) {
   ABI_BEGIN
   if (!P) fail(MRHYDE_B200_ERR_INVALID, "plan_warmup: null plan");
@@ -1878,6 +1889,15 @@ int mrhyde_b200_halo_sum(mrhyde_b200_plan* P, double* res, double* jac_values, v
   NvtxRange exp("MrHyDE::LinearAlgebraInterface::export*()");
   std::string err;
   if (!P->halo->sum(res, jac_values, (cudaStream_t)stream, err)) fail(MRHYDE_B200_ERR_NCCL, err);
+  ABI_END
+}
+
+int mrhyde_b200_plan_owned_extent(mrhyde_b200_plan* P, int64_t* n_owned_rows, int64_t* nnz_owned) {
+  ABI_BEGIN
+  if (!P || !n_owned_rows || !nnz_owned) fail(MRHYDE_B200_ERR_INVALID, "plan_owned_extent: null argument");
+  if (!P->have_graph) fail(MRHYDE_B200_ERR_STATE, "plan_owned_extent: call set_graph first");
+  *n_owned_rows = P->mesh.nowned > 0 ? P->mesh.nowned : P->mesh.nrows;
+  *nnz_owned = P->mesh.rowptr[(size_t)*n_owned_rows];
   ABI_END
 }
 

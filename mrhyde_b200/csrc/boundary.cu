@@ -19,6 +19,7 @@ struct BoundaryParams {
   const BoundaryGroupDev* groups;
   int32_t first, count;
   double formparam;
+  int32_t adjoint;   // useadjoint: local matrices are filled transposed and sf = 1 (thermal.cpp:197-201, updateJacBoundary :1047-1062)
   ExprProgram diffusion;
   TimeDev td;
   const double* vx; const double* vy; const double* vz;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(64) thermal_boundary_kernel(const __grid_const
 
   double r[NV], K[NV][NV];
   for (int i = 0; i < NV; ++i) { r[i] = 0.0; for (int j = 0; j < NV; ++j) K[i][j] = 0.0; }
-  const double epen = 10.0, sf = P.formparam;
+  const double epen = 10.0, sf = P.adjoint ? 1.0 : P.formparam;
   for (int q = 0; q < g.nqp; ++q) {
     ExprVars in;
     in.v[0] = xq[q][0]; in.v[1] = xq[q][1]; in.v[2] = xq[q][2]; in.v[3] = P.td.time;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(64) thermal_boundary_kernel(const __grid_const
         int64_t lo = rs, hi = re - 1;
         const int col = ld[j];
         while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (P.graph.colind[mid] < col) lo = mid + 1; else hi = mid; }
-        P.out.jac[lo] += K[i][j];
+        P.out.jac[lo] += P.adjoint ? K[j][i] : K[i][j];
       }
     }
   }
@@ -222,8 +223,9 @@ void build_boundary_plan(const BoundarySetup& bs, const std::vector<BoundaryGrou
   up(&out.d_item_elem, se); up(&out.d_item_group, sg); up(&out.d_groups, gd);
 }
 
-void launch_boundary(const BoundaryPlan& B, const double* sol, const TimeDev& td, const GraphDev& G, const OutDev& O, void* stream) {
+void launch_boundary(const BoundaryPlan& B, const double* sol, const TimeDev& td, const GraphDev& G, const OutDev& O, void* stream, bool adjoint) {
   BoundaryParams P;
+  P.adjoint = adjoint ? 1 : 0;
   P.item_elem = B.d_item_elem; P.item_group = B.d_item_group; P.groups = B.d_groups;
   P.formparam = B.formparam; P.diffusion = B.diffusion; P.td = td;
   P.vx = B.vx; P.vy = B.vy; P.vz = B.vz; P.conn = B.conn; P.lids = B.lids; P.sol = sol; P.graph = G; P.out = O;

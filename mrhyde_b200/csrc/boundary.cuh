@@ -62,6 +62,6 @@ struct BoundaryPlan {
 };
 
 void build_boundary_plan(const BoundarySetup& bs, const std::vector<BoundaryGroupHost>& groups, const MeshGraph& m, BoundaryPlan& out, size_t* dev_bytes);
-void launch_boundary(const BoundaryPlan& B, const double* sol, const TimeDev& td, const GraphDev& G, const OutDev& O, void* stream);
+void launch_boundary(const BoundaryPlan& B, const double* sol, const TimeDev& td, const GraphDev& G, const OutDev& O, void* stream, bool adjoint = false);
 
 }  // namespace mrhyde_b200

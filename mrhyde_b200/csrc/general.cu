@@ -275,7 +275,7 @@ GeneralPlanDev* gen_upload(const GeneralPlanHost& H, const MeshGraph& m, size_t*
 
 const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                     const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
-                    bool volume, bool boundary, void* stream, GenLaunchStats* stats, int pull_mass_mode, const double* mass_wts);
+                    bool volume, bool boundary, void* stream, GenLaunchStats* stats, int pull_mass_mode, const double* mass_wts, bool adjoint = false);
 
 static int pick_epb(const GenKernelInfo& I, bool tensor, bool side, int64_t n_items, int epb_override) {
   // as many elements per CTA as the launch bounds allow, while MINB CTAs still fit the SM's shared memory
@@ -293,8 +293,8 @@ static int pick_epb(const GenKernelInfo& I, bool tensor, bool side, int64_t n_it
 
 const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                          const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
-                         bool volume, bool boundary, void* stream, GenLaunchStats* stats) {
-  return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, sol, td, volume, boundary, stream, stats, 0, nullptr);
+                         bool volume, bool boundary, void* stream, GenLaunchStats* stats, bool adjoint) {
+  return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, sol, td, volume, boundary, stream, stats, 0, nullptr, adjoint);
 }
 
 const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
@@ -340,7 +340,7 @@ const char* gen_project_initial(GeneralPlanDev* D, const GeneralPlanHost& H, con
 static const char* gen_run_impl_marker = nullptr;
 const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                     const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
-                    bool volume, bool boundary, void* stream, GenLaunchStats* stats, int pull_mass_mode, const double* mass_wts) {
+                    bool volume, bool boundary, void* stream, GenLaunchStats* stats, int pull_mass_mode, const double* mass_wts, bool adjoint) {
   (void)gen_run_impl_marker;
   const GenKernelInfo& I = H.info;
   GenParams P;
@@ -348,6 +348,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   P.vx = vx; P.vy = vy; P.vz = vz; P.conn = conn; P.lids = lids; P.orient = D->orient.n ? D->orient.p : nullptr;
   P.sol = sol; P.td = td;
   P.var_major = H.use_tensor ? 1 : 0;
+  P.adjoint = adjoint ? 1 : 0;
   const bool initial = (pull_mass_mode == 4);   // projection of the initial conditions: the pull is the one of applyMassMatrixFree
   if (initial) pull_mass_mode = 3;
   if (pull_mass_mode) { P.mass_mode = initial ? 2 : 1; for (int v = 0; v < I.nvars; ++v) P.mass_wts[v] = mass_wts[v]; }
@@ -356,6 +357,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   auto mark_state = [&]() { P.fn_state = 0; if (!pull_mass_mode) for (int f = 0; f < GEN_MAXFN; ++f) if (P.fn[f].pad && !P.fn[f].is_const) P.fn_state = 1; };
   mark_state();
   P.fn_op = D->fn_op.p; P.fn_c = D->fn_c.p; P.opt = H.opt;
+  if (adjoint && std::string(I.physics) == "thermal") P.opt.form_param = 1.0;   // thermal.cpp:197-201, 292-296: sf = 1 when wkset->isAdjoint
   for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
   P.elem_jac = (pull_mass_mode == 3) ? nullptr : ((O.jac || pull_mass_mode) ? D->elem_jac.p : nullptr);
   P.elem_res = (pull_mass_mode == 3 || (O.res && !pull_mass_mode)) ? D->elem_res.p : nullptr;

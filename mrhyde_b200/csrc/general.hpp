@@ -118,7 +118,7 @@ void gen_free(GeneralPlanDev* D);
 // the whole assemble call: element kernels + pull per batch.  Returns nullptr or an error string.
 const char* gen_assemble(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                          const int32_t* conn, const int32_t* lids, const GraphDev& G, const OutDev& O, const double* sol, const TimeDev& td,
-                         bool volume, bool boundary, void* stream, GenLaunchStats* stats);
+                         bool volume, bool boundary, void* stream, GenLaunchStats* stats, bool adjoint = false);
 // getWeightedMass: element kernel in mass mode over the volume elements + mass pull.  mass / diag may be null.
 const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDeviceKernels* kd, const double* vx, const double* vy, const double* vz,
                               const int32_t* conn, const int32_t* lids, const GraphDev& G, const double* mass_wts, bool lump, bool accumulate,

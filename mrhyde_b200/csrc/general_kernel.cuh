@@ -159,6 +159,7 @@ struct GenParams {
   // dof off[v][i] (device plans of the tensor-core contraction: a fragment row then is a contiguous run in global memory; the
   // pull's contribution list and position tables are permuted to match at upload, general.cu)
   int32_t var_major;
+  int32_t adjoint;    // useadjoint: element matrices are stored transposed (updateJac, assemblyManager_jacres.hpp:1459-1475)
   int32_t tensor;     // host replay only: 1 = replay the tensor-core build's stages (S4d / S4m), 0 = the derivative-lane build's (S4b)
   int32_t fn_state;   // some coefficient function of this launch reads a solution field (GenFnRec::pad marks which)
 };
@@ -617,7 +618,7 @@ struct GenBlock {
   MRH_HD static void store_var(const GenParams& P, double* out, int col, const double (&acc)[N][K], int kk) {
     constexpr int CARD = Phys::card(Phys::var_basis(V)), R0 = Phys::row0(V);
 #pragma unroll
-    for (int i = 0; i < CARD; ++i) out[(int)P.off[V][i] * N + col] = acc[R0 + i][kk];
+    for (int i = 0; i < CARD; ++i) out[P.adjoint ? col * N + (int)P.off[V][i] : (int)P.off[V][i] * N + col] = acc[R0 + i][kk];
   }
   MRH_HD static void store_rows(const GenParams& P, double* out, int col, const double (&acc)[N][K], int kk) {
     store_var<0>(P, out, col, acc, kk);
@@ -831,13 +832,13 @@ struct GenBlock {
       for (int a = 0; a < IT; ++a) {
         const int i = a * 8 + g;
         if (i < CARD) {
-          double* orow = out + (int64_t)row_index(P, v, i) * N;
+          const int ri = row_index(P, v, i);
 #pragma unroll
           for (int b = 0; b < JT; ++b)
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
               const int j = (jh * JT + b) * 8 + 2 * t + x;
-              if (j < CARD) orow[row_index(P, w, j)] = acc[a][b][x];
+              if (j < CARD) { const int cj = row_index(P, w, j); out[P.adjoint ? (int64_t)cj * N + ri : (int64_t)ri * N + cj] = acc[a][b][x]; }
             }
         }
       }
@@ -864,7 +865,8 @@ struct GenBlock {
             s += pb[i * L::prs(0) + q * NC + k] * b;
           }
         }
-        out[(int64_t)row_index(P, v, i) * N + row_index(P, w, j)] = s;
+        const int ri = row_index(P, v, i), cj = row_index(P, w, j);
+        out[P.adjoint ? (int64_t)cj * N + ri : (int64_t)ri * N + cj] = s;
       }
   }
 

@@ -79,6 +79,7 @@ class AssemblyManager {
   std::vector<std::string> modules;
   int type_AD = 0, maxdof = 0;
   bool assemble_volume_terms = true, assemble_boundary_terms = true, use_strong_DBCs = true;
+  bool useadjoint = false;   // assembleJacRes(..., useadjoint, ...): transposed local Jacobians (updateJac, assemblyManager_jacres.hpp:1459-1475)
   TimeData td;
   std::unique_ptr<EngineBase> eng_scalar, eng_ad;
   std::vector<int8_t> orient_sign;  // (num_elems, ndof_elem), +1 on lexicographic bricks
@@ -298,7 +299,9 @@ struct Engine : EngineBase {
             for (size_t m = 0; m < offsets.size(); ++m)
               for (size_t k = 0; k < offsets[m].size(); ++k) {
                 const int col = offsets[m][k];
-                vals[col] = ADTraits<EvalT>::dx(res(elem, row), col);
+                // adjoint: local_J(elem, offsets(m,k), offsets(n,j)) += res(elem, offsets(n,j)).dx(offsets(m,k)), i.e. the entry in
+                // (row, col) of the scattered matrix is d res(col) / d u(row)   (updateJac / updateJacBoundary, useadjoint branch)
+                vals[col] = am.useadjoint ? ADTraits<EvalT>::dx(res(elem, col), row) : ADTraits<EvalT>::dx(res(elem, row), col);
                 cols[col] = LIDs[col];
               }
             // KokkosSparse::CrsMatrix::sumIntoValues(row, cols, n, vals, is_sorted=false): linear search per entry
@@ -315,6 +318,7 @@ struct Engine : EngineBase {
                 bool compute_jacobian, bool doseed, double* res, double* Jvals) override {
     // updateWorksetTime (assemblyManager_workset.hpp): t = current stage time, alpha = 1/dt
     wkset.isTransient = am.td.isTransient;
+    wkset.isAdjoint = am.useadjoint;
     wkset.td = am.td;
     wkset.deltat = am.td.deltat;
     wkset.alpha = 1.0 / am.td.deltat;

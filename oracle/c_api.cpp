@@ -170,6 +170,11 @@ int oracle_set_time(void* hv, int isTransient, double time, double deltat, int s
   return 0;
 }
 
+int oracle_set_adjoint(void* hv, int useadjoint) {
+  ((OracleHandle*)hv)->am->useadjoint = useadjoint != 0;
+  return 0;
+}
+
 int oracle_assemble_jacres(void* hv, const double* sol, const double* const* sol_prev, const double* const* sol_stage,
                            int compute_jacobian, double* res, double* Jvals) {
   ORACLE_TRY

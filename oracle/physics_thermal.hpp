@@ -94,7 +94,7 @@ class thermal : public PhysicsBase<EvalT> {
     else if (bctype == "Neumann") nsource = functionManager->evaluate("Neumann T " + wkset->sidename, "side ip");
     diff_side = functionManager->evaluate("thermal diffusion", "side ip");
     robin_alpha = functionManager->evaluate("robin alpha", "side ip");
-    const double sf = formparam;
+    const double sf = wkset->isAdjoint ? 1.0 : formparam;   // thermal.cpp:197-201
     auto h = wkset->getSideElementSize();
     auto& res = wkset->res;
     const auto& off = wkset->offsets[T_num];

@@ -172,6 +172,10 @@ class OracleProblem:
         self.L.oracle_set_time(self.h, int(transient), C.c_double(time), C.c_double(dt), int(stage), len(b),
                                _p(A, C.c_double), _p(b, C.c_double), _p(c, C.c_double), len(bdf), _p(bdf, C.c_double))
 
+    def set_adjoint(self, useadjoint):
+        """assembleJacRes(..., useadjoint = true): the Jacobian is filled transposed (and thermal's weak-Dirichlet sides use sf = 1)."""
+        self.L.oracle_set_adjoint(self.h, int(bool(useadjoint)))
+
     def _ptrs(self, vecs, n):
         if not getattr(self, "_transient", False):
             return None, None

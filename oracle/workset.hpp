@@ -103,6 +103,7 @@ class Workset {
   std::vector<ScalarField> scalar_fields, side_scalar_fields;
 
   bool isOnSide = false, isTransient = false;
+  bool isAdjoint = false;   // Workset::isAdjoint (updateWorksetAdjoint, assemblyManager_workset.hpp:310-350)
   double time = 0.0, deltat = 1.0, alpha = 1.0;
   int current_stage = 0;
   TimeData td;

@@ -293,3 +293,54 @@ def test_maxwell_full_size_properties(product_lib):
     torch.cuda.synchronize()
     lin = res0 - _spmv(op.rowptr, op.colind, jac, u)
     assert float((res - lin).abs().max()) < 1e-11 * float(res.abs().max())
+
+
+@pytest.mark.parametrize("name", ["thermal3d-advection", "thermal2d-weak-neumann", "le3d-weak-neumann", "ns3d-reference-uz-rows", "ns2d-bwe", "maxwell-dirk",
+                                  "thermal3d-state-diffusion"])
+@pytest.mark.parametrize("jacobian", ["lanes", "tensor"])
+def test_adjoint_assembly_matches_oracle(oracle_lib, product_lib, name, jacobian):
+    """assembleJacRes(useadjoint = true): forward residual, local Jacobians filled transposed before the scatter (updateJac / updateJacBoundary,
+    assemblyManager_jacres.hpp:1459-1475, 1047-1062), sf = 1 on thermal's weak-Dirichlet sides -- against the oracle's restatement."""
+    import torch
+    _, cfg, opts, tableau, zero = next(c for c in configs.general_cases() if c[0] == name)
+    if jacobian == "tensor" and name.startswith("maxwell"):
+        pytest.skip("two-basis layout: derivative-lane build only")
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, options=dict({"kernel": "general", "jacobian": jacobian}, **opts))
+    u = np.zeros(op.num_dofs) if zero else helpers.manufactured_state(op)
+    ts, kw = _time(op, tableau)
+    op.set_adjoint(True)
+    res_ref, jac_ref = op.assemble_jacres(u, **kw)
+    op.set_adjoint(False)
+    res_fwd, jac_fwd = op.assemble_jacres(u, **kw)
+    d_u = _dev(u)
+    d_res = torch.zeros(op.num_dofs, dtype=torch.float64, device=d_u.device)
+    d_jac = torch.zeros(op.nnz, dtype=torch.float64, device=d_u.device)
+    plan.assemble_jacres_adjoint(d_u, d_res, d_jac, time=ts)
+    torch.cuda.synchronize()
+    op.set_time(False)
+    assert helpers.rel_err_vec(d_res.cpu().numpy(), res_ref) < TOL
+    assert helpers.rel_err_rows(d_jac.cpu().numpy(), jac_ref, op.rowptr) < TOL
+    if "weak" not in name:   # (sf differs on weak-Dirichlet sides) the free-free block is the transpose of the forward Jacobian
+        free = op.is_fixed == 0
+        A, F = op.csr(jac_ref).tocsr()[free][:, free], op.csr(jac_fwd).tocsr()[free][:, free]
+        assert abs(A - F.T).max() <= 1e-12 * abs(F).max()
+
+
+def test_adjoint_thermal_sweep_plan_matches_oracle(oracle_lib, product_lib):
+    """Thermal on the sweep kernel (symmetric local matrices) + its boundary kernel (Nitsche sides: transposed, sf = 1) in adjoint mode."""
+    import torch
+    cfg = configs.variant(configs.THERMAL_3D, **dict(configs.THERMAL_WEAK, **{"Mesh/NZ": 4, "Physics/form_param": -1.0}))
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    assert plan.stat("general") == 0
+    u = helpers.manufactured_state(op)
+    op.set_adjoint(True)
+    res_ref, jac_ref = op.assemble_jacres(u)
+    op.set_adjoint(False)
+    d_u = _dev(u)
+    d_res = torch.zeros(op.num_dofs, dtype=torch.float64, device=d_u.device)
+    d_jac = torch.zeros(op.nnz, dtype=torch.float64, device=d_u.device)
+    plan.assemble_jacres_adjoint(d_u, d_res, d_jac)
+    torch.cuda.synchronize()
+    assert helpers.rel_err_vec(d_res.cpu().numpy(), res_ref) < TOL and helpers.rel_err_rows(d_jac.cpu().numpy(), jac_ref, op.rowptr) < TOL

@@ -76,6 +76,7 @@ def _worker_body(rank, world, q, kind, dev):
     if kind == "thermal_overlap" and prob.n_owned < prob.n_rows:   # only ranks that hold ghost rows start an exchange early
         assert prob.plan.stat("overlapped_assembles") == 4 and 0 < prob.plan.stat("n_early_chains") < prob.plan.stat("n_chains")
     no = prob.n_owned
+    assert prob.plan.owned_extent() == (no, int(prob.rowptr[no]))   # the owned matrix is the prefix of the local CSR arrays (no compaction pass)
     q.put((rank, prob.col_gids.copy(), res[:no].cpu().numpy(), prob.rowptr[: no + 1].copy(), prob.colind[: prob.rowptr[no]].copy(),
            jac[: prob.rowptr[no]].cpu().numpy(), prob.state()[:no].copy()))
     dist.barrier()
