@@ -14,6 +14,7 @@
 #include "../../include/mrhyde_b200.h"
 #include <cstdio>
 #include <cstdlib>
+#include <set>
 
 #include "boundary.cuh"
 #include "expr.hpp"
@@ -132,6 +133,8 @@ struct mrhyde_b200_plan {
   int jit_min_blocks = 1;
   size_t smem = 0;
   bool suppress_overlap = false;
+  bool push_ok = false;            // the specialised kernels can push ghost rows into the owner's slab themselves (in-kernel halo push)
+  int64_t pushed_assembles = 0;    // assemble calls that did
   int64_t overlapped_assembles = 0;   // assemble calls that started the halo exchange after the ghost-row chains
   int metric_ng = 0;               // > 0: the specialised kernels use the metric ring with this many metric entries per element
   int class_nc = 0;                // > 0: class ring (boxes + constant coefficients): distinct local-matrix values staged per element
@@ -172,7 +175,7 @@ struct NvtxRange {
 };
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "scratch GB", "debug transient", "debug mode", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "scratch GB", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -273,7 +276,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
                                const int64_t (&n_class)[3], int metric_ng, int max_patterns, int pull_group,
-                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint, bool prefetch2) {
+                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint, bool prefetch2, bool push) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -287,6 +290,7 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   o += "#define MRH_JIT_ALL_CONST " + std::to_string(all_const) + "\n";
   o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
   if (late_stage1) o += "#define MRH_JIT_LATE_STAGE1 1\n";
+  if (push) o += "#define MRH_JIT_PUSH 1   /* multi-rank plan: ghost rows are also stored into the owner's receive slab (kernel_abi.h: PushDev) */\n";
   if (prefetch2) o += "#define MRH_JIT_PREFETCH2 1   /* L2 prefetch of the next step's state / vertices before the pull */\n";
   if (early_stage2) o += "#define MRH_JIT_EARLY_STAGE2 1\n";
   if (literal_tables) o += "#define MRH_JIT_LITERAL_TABLES 1\n";
@@ -430,12 +434,19 @@ std::vector<SpecialPattern> special_patterns(const ChainPlan& cp, int max_patter
   for (auto& kv : freq) order.push_back({kv.second, kv.first});
   std::sort(order.rbegin(), order.rend());
   std::vector<SpecialPattern> out;
+  if (max_patterns <= 0) return out;
+  auto slots_of = [&](int32_t db) { int n = 0; for (const PatternRec& PR : cp.patterns) if (PR.desc_begin == db) n = PR.n_slots; return n; };
   for (auto& pr : order) {
     if ((int)out.size() >= max_patterns) break;
-    int n_slots = 0;
-    for (const PatternRec& PR : cp.patterns) if (PR.desc_begin == pr.second) n_slots = PR.n_slots;
+    const int n_slots = slots_of(pr.second);
     if (n_slots < 2 || n_slots > 65) continue;   // rows of up to 64 entries go through the per-warp row buffer
     out.push_back({pr.second, n_slots});
+  }
+  for (int32_t db : cp.ghost_patterns) {   // patterns of ghost rows (in-kernel halo push), whatever their frequency
+    bool have = false;
+    for (const SpecialPattern& sp : out) if (sp.desc_begin == db) have = true;
+    const int n_slots = slots_of(db);
+    if (!have && n_slots >= 2 && n_slots <= 65) out.push_back({db, n_slots});
   }
   return out;
 }
@@ -508,12 +519,15 @@ __device__ __forceinline__ void mrh_flush_rows(const double* rowb, const long lo
 struct MrhRun { double* rl; unsigned starts; bool start; };
 __device__ __forceinline__ void mrh_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 template <int NJ>
-__device__ __forceinline__ MrhRun mrh_run_begin(double* rowb, const double* jac, const long long base, const int n_rows, const int lane) {
+__device__ __forceinline__ MrhRun mrh_run_begin(double* rowb, const double* jac, const long long base, const int n_rows, const int lane, const PushDev* X) {
   mrh_bulk_wait_read();   // the previous batch of this warp has left the buffer (the issuing lanes wait; a no-op for the others)
   __syncwarp();
   const long long prev = __shfl_up_sync(0xffffffffu, base, 1);
   MrhRun R;
   R.start = lane < n_rows && (lane == 0 || base != prev + NJ);
+#ifdef MRH_JIT_PUSH
+  if (X->enabled) R.start = R.start || (lane < n_rows && ((base >= X->ghost_base) != (prev >= X->ghost_base)));   // a run is owned rows or ghost rows, never both
+#endif
   R.starts = __ballot_sync(0xffffffffu, R.start);
   const int ridx = __popc(R.starts & (0xffffffffu >> (31 - lane))) - 1;   // runs that begin at or below this lane, minus one
   const int e = (int)(((long long)(reinterpret_cast<unsigned long long>(jac + base) >> 3) - (long long)(lane * NJ)) & 1);   // constant within a run
@@ -522,7 +536,7 @@ __device__ __forceinline__ MrhRun mrh_run_begin(double* rowb, const double* jac,
   return R;
 }
 template <int NJ, bool ACC>
-__device__ __forceinline__ void mrh_run_flush(const MrhRun& R, const long long base, double* __restrict__ jac, const int n_rows, const int lane) {
+__device__ __forceinline__ void mrh_run_flush(const MrhRun& R, const long long base, double* __restrict__ jac, const int n_rows, const int lane, const PushDev* X) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores of this lane -> visible to the bulk-copy engine
   __syncwarp();
   if (R.start && !(MRH_DEBUG_SKIP & 1)) {
@@ -545,9 +559,37 @@ __device__ __forceinline__ void mrh_run_flush(const MrhRun& R, const long long b
       else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(jac + g), "r"(sa), "r"(cnt * 8) : "memory");
 #endif
     }
+#ifdef MRH_JIT_PUSH
+    if (X->enabled && base >= X->ghost_base) {
+      // ghost rows: the same run once more, into the owner's receive slab over NVLink (plain copies: the slab holds this call's
+      // values; its 16-byte phase equals the local array's, PushDev::shift)
+      int c2 = (end - lane) * NJ;
+      long long g2 = base - X->ghost_base;
+      const double* s2 = R.rl;
+      double* rj = X->remote_jac;
+      if ((reinterpret_cast<unsigned long long>(rj + g2) >> 3) & 1) { rj[g2] = s2[0]; ++g2; ++s2; --c2; }
+      if (c2 & 1) { rj[g2 + c2 - 1] = s2[c2 - 1]; --c2; }
+      if (c2 > 0) {
+        const unsigned sa2 = (unsigned)__cvta_generic_to_shared(s2);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(rj + g2), "r"(sa2), "r"(c2 * 8) : "memory");
+      }
+    }
+#endif
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
 }
+#ifdef MRH_JIT_PUSH
+// residual entry of a ghost row: also into the owner's slab
+__device__ __forceinline__ void mrh_push_res(const PushDev* X, const double* pres, const double v) {
+  if (X->enabled) {
+    const long long row = pres - X->res_base;
+    if (row >= X->n_owned) X->remote_res[row - X->n_owned] = v;
+  }
+}
+#define MRH_PUSH_RES(pres, v) mrh_push_res(X, (pres), (v))
+#else
+#define MRH_PUSH_RES(pres, v)
+#endif
 #endif
 )MRH";
 
@@ -566,7 +608,7 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group, int f
   o += "#define MRH_L(off) mrh_lds_at(rbase + (off##u))\n";
   o += kFlushRowsSrc;
   o += "template <bool HAS_RES, bool HAS_JAC, bool ACC>\n__device__ __forceinline__ bool mrh_pull_special(const int desc_begin, const int parity, const unsigned rbase, "
-       "double* __restrict__ wbuf, const int lane, const int n_rows, const long long base, double* __restrict__ jac, double* pres, const bool active) {\n";
+       "double* __restrict__ wbuf, const int lane, const int n_rows, const long long base, double* __restrict__ jac, double* pres, const bool active, const PushDev* X) {\n";
   o += "  long long* const wbase = reinterpret_cast<long long*>(wbuf);\n  double* const rowb = wbuf + 32;\n";
   o += "  switch (desc_begin * 2 + parity) {\n";
   for (const SpecialPattern& sp : sel) {
@@ -586,7 +628,7 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group, int f
         return cnt ? e : std::string("0.0");
       };
       o += "    case " + std::to_string(db * 2 + par) + ": {\n      if (HAS_JAC) {\n";
-      if (bulk) o += "        const MrhRun run = mrh_run_begin<" + std::to_string(n_jac) + ">(wbuf, jac, base, n_rows, lane);\n";
+      if (bulk) o += "        const MrhRun run = mrh_run_begin<" + std::to_string(n_jac) + ">(wbuf, jac, base, n_rows, lane, X);\n";
       else o += "        wbase[lane] = base;\n";
       // a group of sums first (the loads are independent and can be in flight together), then they are parked in the row buffer
       for (int g0 = 0; g0 < n_jac; g0 += group) {
@@ -595,9 +637,9 @@ std::string pull_codegen(const ChainPlan& cp, int max_patterns, int group, int f
           o += bulk ? "        run.rl[" + std::to_string(k) + "] = a" + std::to_string(k) + ";\n"
                     : "        rowb[lane * " + std::to_string(pitch) + " + " + std::to_string(k) + "] = a" + std::to_string(k) + ";\n";
       }
-      if (bulk) o += "        mrh_run_flush<" + std::to_string(n_jac) + ", ACC>(run, base, jac, n_rows, lane);\n";
+      if (bulk) o += "        mrh_run_flush<" + std::to_string(n_jac) + ", ACC>(run, base, jac, n_rows, lane, X);\n";
       else o += "        mrh_flush_rows<" + std::to_string(n_jac) + ", " + std::to_string(pitch) + ", ACC>(rowb, wbase, jac, n_rows, lane);\n";
-      o += "      }\n      if (HAS_RES) { const double acc = " + sum_expr(n_jac) + "; if (active) { double v = -acc; if (ACC) v += *pres; *pres = v; } }\n";
+      o += "      }\n      if (HAS_RES) { const double acc = " + sum_expr(n_jac) + "; if (active) { double v = -acc; if (ACC) v += *pres; *pres = v; " + (bulk ? "MRH_PUSH_RES(pres, v); " : "") + "} }\n";
       o += "      return true;\n    }\n";
     }
   }
@@ -623,7 +665,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
   o += "#define MRH_ML(off, m) mrh_mlds(rbase + (off) + (m) * MRH_ESB)\n";
   o += "template <bool HAS_RES, bool HAS_JAC, bool ACC>\n__device__ __forceinline__ bool mrh_pull_metric_special(const int desc_begin, const int parity, const unsigned rbase, "
        "double* __restrict__ wbuf, const int lane, const int n_rows, const long long base, double* __restrict__ jac, double* pres, const bool active, "
-       "const double au, const double at) {\n";
+       "const double au, const double at, const PushDev* X) {\n";
   o += "  long long* const wbase = reinterpret_cast<long long*>(wbuf);\n  double* const rowb = wbuf + 32;\n";
   o += "  switch (desc_begin * 2 + parity) {\n";
   for (const SpecialPattern& sp : sel) {
@@ -645,7 +687,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
           o += "      const double g" + std::to_string(c) + "_" + std::to_string(g) + " = MRH_ML(" + std::to_string(cols[c]) + "u, " + std::to_string(g) + ");\n";
         o += "#if MRH_JIT_TRANSIENT\n      const double m" + std::to_string(c) + " = MRH_ML(" + std::to_string(cols[c]) + "u, MRH_MD);\n#endif\n";
       }
-      if (bulk) o += "      MrhRun run; run.rl = rowb; run.starts = 0u; run.start = false;\n      if (HAS_JAC) run = mrh_run_begin<" + std::to_string(n_jac) + ">(wbuf, jac, base, n_rows, lane);\n      double racc = 0.0;\n";
+      if (bulk) o += "      MrhRun run; run.rl = rowb; run.starts = 0u; run.start = false;\n      if (HAS_JAC) run = mrh_run_begin<" + std::to_string(n_jac) + ">(wbuf, jac, base, n_rows, lane, X);\n      double racc = 0.0;\n";
       else o += "      if (HAS_JAC) wbase[lane] = base;\n      double racc = 0.0;\n";
       for (int g0 = 0; g0 < n_jac; g0 += group) {
         for (int k = g0; k < g0 + group && k < n_jac; ++k) {
@@ -683,7 +725,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
           o += bulk ? "      if (HAS_JAC) run.rl[" + std::to_string(k) + "] = a" + std::to_string(k) + ";\n"
                     : "      if (HAS_JAC) rowb[lane * " + std::to_string(pitch) + " + " + std::to_string(k) + "] = a" + std::to_string(k) + ";\n";
       }
-      if (bulk) o += "      if (HAS_JAC) mrh_run_flush<" + std::to_string(n_jac) + ", ACC>(run, base, jac, n_rows, lane);\n";
+      if (bulk) o += "      if (HAS_JAC) mrh_run_flush<" + std::to_string(n_jac) + ", ACC>(run, base, jac, n_rows, lane, X);\n";
       else o += "      if (HAS_JAC) mrh_flush_rows<" + std::to_string(n_jac) + ", " + std::to_string(pitch) + ", ACC>(rowb, wbase, jac, n_rows, lane);\n";
       o += "      if (HAS_RES) {\n        double bs = 0.0;\n";
       for (int z = 0; z < SLOT_SRCS; ++z) {
@@ -691,7 +733,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
         if (w == SRC_NONE) continue;
         o += "        bs += MRH_ML(" + std::to_string(w & MSRC_OFF_MASK) + "u, MRH_B0 + " + std::to_string((w >> MSRC_I_SHIFT) & 7u) + ");\n";
       }
-      o += "        if (active) { double v = bs - racc; if (ACC) v += *pres; *pres = v; }\n      }\n";
+      o += std::string("        if (active) { double v = bs - racc; if (ACC) v += *pres; *pres = v; ") + (bulk ? "MRH_PUSH_RES(pres, v); " : "") + "}\n      }\n";
       o += "      return true;\n    }\n";
     }
   }
@@ -975,6 +1017,14 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     const void* params;
     if (P->dim == 3) { P->th3.sol = sol; P->th3.td = td; P->th3.out = out; params = &P->th3; }
     else { P->th2.sol = sol; P->th2.td = td; P->th2.out = out; params = &P->th2; }
+    // in-kernel halo push: the assembly kernel stores ghost rows into the owner's slab as it completes them
+    PushDev push;
+    std::memset(&push, 0, sizeof(push));
+    if (P->push_ok && P->use_jit && P->halo && !P->suppress_overlap && want_jac && want_res && !adjoint && P->boundary.groups.empty() && P->cp.orphan_rows.empty() &&
+        !opt_bool(P, "overlap halo", false)) {
+      if (P->halo->push_params(res, jac, P->mesh.nowned, P->mesh.rowptr[(size_t)P->mesh.nowned], P->cp.n_early_chains, push)) ++P->pushed_assembles;
+    }
+    if (P->dim == 3) P->th3.push = push; else P->th2.push = push;
     const JitKernel* jk = nullptr;
     if (P->use_jit) {
       const int mode = (out.res ? 1 : 0) | (out.jac ? 2 : 0) | (out.accumulate ? 4 : 0);
@@ -1633,6 +1683,16 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   co.min_segment_levels = std::max(1, std::stoi(opt(P, "min segment levels", "8")));
   if (co.column_elems < 1 || co.min_chains < 1) fail(MRHYDE_B200_ERR_INVALID, "options 'column elements' and 'min chains' must be positive");
   build_chain_plan(M, kmap, rmap, STAGE, co, P->cp);
+  if (M.nowned > 0 && M.nowned < M.nrows && jit_possible && flush_mode == 2 && opt_bool(P, "halo push", true)) {
+    // patterns of the batches that hold ghost rows: at most 8 get generated pull code on top of the most frequent ones
+    std::set<int32_t> gp;
+    for (size_t b = 0; b < P->cp.batches.size(); ++b) {
+      const BatchRec& B = P->cp.batches[b];
+      if (B.flags & BATCH_FIXED) continue;
+      for (int l = 0; l < (int)B.n_rows; ++l) if (P->cp.rows[b * 32 + (size_t)l].row >= M.nowned) { gp.insert(B.desc_begin); break; }
+    }
+    if (gp.size() <= 8) P->cp.ghost_patterns.assign(gp.begin(), gp.end());
+  }
   {
     const int want = std::stoi(opt(P, "threads", "0"));
     int th = want > 0 ? want : std::max(128, std::min(256, ((P->cp.cap + 31) / 32) * 32));
@@ -1650,14 +1710,32 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   P->stage_len = STAGE;
   P->kmap = kmap; P->rmap = rmap;
   {
+    // In-kernel halo push: possible when every batch that holds ghost rows is written by the generated bulk-flush code (one of
+    // the specialised patterns) or is a batch of strong-Dirichlet rows (those stay zero in the owner's slab), and the chains that
+    // complete ghost rows are the first n_early_chains of the plan.  The transport is checked per call (HaloExchange::push_params).
+    P->push_ok = false;
+    if (jit_possible && flush_mode == 2 && !use_metric && M.nowned > 0 && M.nowned < M.nrows && P->cp.n_early_chains > 0 && opt_bool(P, "halo push", true)) {
+      std::set<int32_t> special;
+      for (const SpecialPattern& sp : special_patterns(P->cp, max_patterns)) special.insert(sp.desc_begin);
+      bool ok = true;
+      for (size_t b = 0; b < P->cp.batches.size() && ok; ++b) {
+        const BatchRec& B = P->cp.batches[b];
+        bool ghost = false;
+        for (int l = 0; l < (int)B.n_rows; ++l) if (P->cp.rows[b * 32 + (size_t)l].row >= M.nowned) ghost = true;
+        if (ghost && !(B.flags & BATCH_FIXED) && !special.count(B.desc_begin)) ok = false;
+      }
+      P->push_ok = ok;
+    }
+  }
+  {
     const int64_t n_class[3] = {M.nelem - P->n_affine, P->n_affine - P->n_box, P->n_box};
     P->metric_ng = (use_metric && !P->cp.mdesc[0].empty()) ? (n_class[1] == 0 ? P->dim : P->dim * (P->dim + 1) / 2) : 0;
     if (ring == "metric" && P->metric_ng == 0) fail(MRHYDE_B200_ERR_UNSUPPORTED, "ring=metric: the plan has no metric source words (sweep steps larger than 256 elements)");
     for (int tr = 0; tr < 2; ++tr)
       P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
     const int pull_group = std::stoi(opt(P, "pull group", "8"));
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, opt_bool(P, "prefetch", true))
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, opt_bool(P, "prefetch", true));
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, opt_bool(P, "prefetch", true), P->push_ok)
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, opt_bool(P, "prefetch", true), P->push_ok);
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
@@ -1918,6 +1996,7 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "max_rows_per_step") *value = P->cp.max_rows_step;
   else if (k == "kernel_launches_per_assemble") *value = P->launches_per_assemble;
   else if (k == "halo_launches_per_sum") *value = P->halo ? P->halo->launches_per_sum() : 0;
+  else if (k == "pushed_assembles") *value = P->pushed_assembles;
   else if (k == "halo_p2p") *value = (P->halo && P->halo->p2p()) ? 1 : 0;
   else if (k == "smem_bytes") *value = (int64_t)variant_smem(P, false);
   else if (k == "metric_ring") *value = P->metric_ng;

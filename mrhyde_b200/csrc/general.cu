@@ -12,21 +12,21 @@ namespace mrhyde_b200 {
 
 namespace {
 
-template <class Phys, int NQ, int NQS, int K, int MAXT, int MINB, bool TCK>
+template <class Phys, int NQ, int NQS, int K, int MAXT, int MINB, bool TCK, bool STATEK>
 const char* launch_entry(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream) {
   static size_t attr[2][64] = {};   // opt-in shared memory already granted, per (volume | side, device)
   int devid = 0;
   cudaGetDevice(&devid);
   devid &= 63;
   if (threads > MAXT) return "general element kernel: more threads per CTA than the instantiation's launch bounds";
-  const void* fn = side ? (const void*)gen_element_kernel<Phys, NQS, K, true, MAXT, MINB, TCK> : (const void*)gen_element_kernel<Phys, NQ, K, false, MAXT, MINB, TCK>;
+  const void* fn = side ? (const void*)gen_element_kernel<Phys, NQS, K, true, MAXT, MINB, TCK, STATEK> : (const void*)gen_element_kernel<Phys, NQ, K, false, MAXT, MINB, TCK, STATEK>;
   if (smem > 48 * 1024 && smem > attr[side ? 1 : 0][devid]) {
     const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     attr[side ? 1 : 0][devid] = smem;
   }
-  if (side) gen_element_kernel<Phys, NQS, K, true, MAXT, MINB, TCK><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
-  else gen_element_kernel<Phys, NQ, K, false, MAXT, MINB, TCK><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
+  if (side) gen_element_kernel<Phys, NQS, K, true, MAXT, MINB, TCK, STATEK><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
+  else gen_element_kernel<Phys, NQ, K, false, MAXT, MINB, TCK, STATEK><<<nblocks, threads, smem, (cudaStream_t)stream>>>(P);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -35,9 +35,13 @@ template <class Phys, int NQ, int NQS, int K, int MAXT, int MINB, int MAXT_L, in
 GenDeviceKernels make_device_entry(const char* name, int dim, int order) {
   GenDeviceKernels k;
   k.info = gen_make_info<Phys, NQ, NQS, K>(name, dim, order, MAXT, MINB, MAXT_L, MINB_L);
-  k.launch = &launch_entry<Phys, NQ, NQS, K, MAXT_L, MINB_L, false>;
-  k.launch_tc = nullptr;
-  if constexpr (GenLayout<Phys, NQ>::TC_CAPABLE) k.launch_tc = &launch_entry<Phys, NQ, NQS, K, MAXT, MINB, true>;
+  k.launch[0] = &launch_entry<Phys, NQ, NQS, K, MAXT_L, MINB_L, false, false>;
+  k.launch[1] = &launch_entry<Phys, NQ, NQS, K, MAXT_L, MINB_L, false, true>;
+  k.launch_tc[0] = k.launch_tc[1] = nullptr;
+  if constexpr (GenLayout<Phys, NQ>::TC_CAPABLE) {
+    k.launch_tc[0] = &launch_entry<Phys, NQ, NQS, K, MAXT, MINB, true, false>;
+    k.launch_tc[1] = &launch_entry<Phys, NQ, NQS, K, MAXT, MINB, true, true>;
+  }
   return k;
 }
 
@@ -374,7 +378,8 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
     const size_t smem = (size_t)epb * (tensor ? (side ? I.tc_smem_doubles_side : I.tc_smem_doubles_volume) : (side ? I.smem_doubles_side : I.smem_doubles_volume)) * sizeof(double);
     const int64_t nblocks = (n_items + epb - 1) / epb;
     ++launches;
-    return tensor ? kd->launch_tc(side, P, (int)nblocks, threads, smem, stream) : kd->launch(side, P, (int)nblocks, threads, smem, stream);
+    const int st = P.fn_state ? 1 : 0;
+    return tensor ? kd->launch_tc[st](side, P, (int)nblocks, threads, smem, stream) : kd->launch[st](side, P, (int)nblocks, threads, smem, stream);
   };
   auto run_pull = [&](int64_t row_begin, int64_t row_end) -> const char* {
     if (row_end <= row_begin) return nullptr;

@@ -34,8 +34,9 @@ struct GenKernelInfo {
 struct GenDeviceKernels {
   GenKernelInfo info;
   // returns nullptr on success, else a static error string
-  const char* (*launch)(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream);
-  const char* (*launch_tc)(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream);   // null: no tensor-core build
+  // [state]: 0 = no coefficient function reads a solution field, 1 = the build that evaluates / differentiates such functions
+  const char* (*launch[2])(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream);
+  const char* (*launch_tc[2])(bool side, const GenParams& P, int nblocks, int threads, size_t smem, void* stream);   // null: no tensor-core build
 };
 struct GenHostKernels {
   GenKernelInfo info;

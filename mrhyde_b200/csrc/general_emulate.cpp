@@ -12,9 +12,9 @@ namespace mrhyde_b200 {
 
 namespace {
 
-template <class Phys, int NQ, int K, bool SIDE, bool TCK>
+template <class Phys, int NQ, int K, bool SIDE, bool TCK, bool STATEK>
 void emulate_blocks(const GenParams& P, int nblocks) {
-  typedef GenBlock<Phys, NQ, K, SIDE, TCK> Bk;
+  typedef GenBlock<Phys, NQ, K, SIDE, TCK, STATEK> Bk;
   typedef GenLayout<Phys, NQ, TCK> L;
   std::vector<double> sm((size_t)P.epb * L::SIZE);
   for (int blk = 0; blk < nblocks; ++blk) {
@@ -41,13 +41,17 @@ void emulate_blocks(const GenParams& P, int nblocks) {
 
 template <class Phys, int NQ, int NQS, int K>
 void emulate_entry(bool side, const GenParams& P, int nblocks) {
-  if (P.tensor && GenLayout<Phys, NQ>::TC_CAPABLE) {   // replay the stages of the build the plan selected (option jacobian)
-    if (side) emulate_blocks<Phys, NQS, K, true, true>(P, nblocks);
-    else emulate_blocks<Phys, NQ, K, false, true>(P, nblocks);
+  // replay the stages of the build the plan would launch: option jacobian (tensor | lanes) x state-dependent coefficients (or not)
+  const bool tc = P.tensor && GenLayout<Phys, NQ>::TC_CAPABLE, st = P.fn_state != 0;
+  if (tc) {
+    if constexpr (GenLayout<Phys, NQ>::TC_CAPABLE) {
+      if (st) { if (side) emulate_blocks<Phys, NQS, K, true, true, true>(P, nblocks); else emulate_blocks<Phys, NQ, K, false, true, true>(P, nblocks); }
+      else { if (side) emulate_blocks<Phys, NQS, K, true, true, false>(P, nblocks); else emulate_blocks<Phys, NQ, K, false, true, false>(P, nblocks); }
+    }
     return;
   }
-  if (side) emulate_blocks<Phys, NQS, K, true, false>(P, nblocks);
-  else emulate_blocks<Phys, NQ, K, false, false>(P, nblocks);
+  if (st) { if (side) emulate_blocks<Phys, NQS, K, true, false, true>(P, nblocks); else emulate_blocks<Phys, NQ, K, false, false, true>(P, nblocks); }
+  else { if (side) emulate_blocks<Phys, NQS, K, true, false, false>(P, nblocks); else emulate_blocks<Phys, NQ, K, false, false, false>(P, nblocks); }
 }
 
 }  // namespace

@@ -372,7 +372,9 @@ __device__ __forceinline__ void mrh_dmma(double (&c)[2], const double a, const d
 #endif
 
 // ---- the stages ----------------------------------------------------------------------------------------------
-template <class Phys, int NQ, int K, bool SIDE, bool TCK = false>
+// STATEK: build for plans whose coefficient functions read solution fields (their values are evaluated after the fields and
+// differentiated in the Jacobian stages); plans without such functions run the STATEK = false build and pay nothing for the feature
+template <class Phys, int NQ, int K, bool SIDE, bool TCK = false, bool STATEK = false>
 struct GenBlock {
   typedef GenLayout<Phys, NQ, TCK> L;
   static constexpr int DIM = Phys::DIM, NV = L::NV, N = L::N, NVAR = L::NVAR, NC = L::NC;
@@ -544,11 +546,11 @@ struct GenBlock {
   }
   // variables of the expression evaluator at a point: x y z t n[x] n[y] n[z], then (plans with state-dependent coefficients) the
   // solution fields F[v][k] and their time derivatives Ft[v][k] (slots of FunctionSet::set_solution_slots, abi.cu)
-  static constexpr int NXV = EXPR_STATE0 + 2 * NVAR * NC;
+  static constexpr int NXV = EXPR_STATE0 + (STATEK ? 2 * NVAR * NC : 0);
   MRH_HD static void expr_vars(const GenParams& P, const double* sme, int q, double (&var)[NXV]) {
     const double* g = sme + L::G + q * L::GEO;
     var[0] = g[1]; var[1] = g[2]; var[2] = g[3]; var[3] = P.td.time; var[4] = g[24]; var[5] = g[25]; var[6] = g[26];
-    if (P.fn_state) {
+    if constexpr (STATEK) {
       for (int j = 0; j < NVAR * NC; ++j) {
         var[EXPR_STATE0 + j] = sme[L::FV + q * NVAR * NC + j];
         var[EXPR_STATE0 + NVAR * NC + j] = P.td.transient ? sme[L::FT + q * NVAR * NC + j] : 0.0;
@@ -592,6 +594,53 @@ struct GenBlock {
     c.dfn = nullptr;
     c.transient = P.td.transient; c.stage = P.td.nstage_lo;
     c.bc_type = P.bc_type;
+  }
+
+  // The module's point function on Dual<KK> when coefficient functions read solution fields: the derivative components of those
+  // functions follow from the seeds of F / Ft (bytecode evaluated on (value, derivative) pairs).  It rebuilds the seeded fields itself
+  // (seed_var < 0: direction seed_idx of the tensor-core build; else the KK columns i0.. of variable seed_var of the derivative-lane
+  // build); only the STATEK builds of the kernel contain it.
+  template <int KK>
+  MRH_HD static void point_state(const GenParams& P, const double* sme, int q, int seed_var, int seed_idx, Dual<KK> (&Cf)[NVAR][NC]) {
+    QpCtx c;
+    make_ctx(P, sme, q, c);
+    const bool transient = P.td.transient != 0;
+    const double au = transient ? P.td.alpha_u : 1.0, at = transient ? P.td.alpha_t : 0.0;
+    Dual<KK> F[NVAR][NC], Ft[NVAR][NC];
+    for (int v = 0; v < NVAR; ++v)
+      for (int k = 0; k < NC; ++k) {
+        F[v][k] = Dual<KK>(sme[L::FV + (q * NVAR + v) * NC + k]);
+        Ft[v][k] = Dual<KK>(transient ? sme[L::FT + (q * NVAR + v) * NC + k] : 0.0);
+        Cf[v][k] = Dual<KK>(0.0);
+      }
+    if (seed_var < 0) {
+      const int v = seed_idx / NC, k = seed_idx % NC;
+      F[v][k].d[0] = au;
+      if (k < Phys::nval(Phys::var_basis_rt(v))) Ft[v][k].d[0] = at;
+    } else {
+      const int wb = Phys::var_basis_rt(seed_var), ncb = Phys::ncb_rt(wb), nval = Phys::nval(wb);
+      const double* pbw = sme + L::PB + L::pb_off(wb) + seed_idx * L::prs_rt(wb);
+      for (int kk = 0; kk < KK; ++kk)
+        for (int k = 0; k < ncb; ++k) {
+          const double sd = pbw[kk * L::prs_rt(wb) + q * ncb + k];
+          F[seed_var][k].d[kk] = au * sd;
+          if (k < nval) Ft[seed_var][k].d[kk] = at * sd;
+        }
+    }
+    double var[NXV], dvar[NXV], dfn[S3F_KINDS * KK];
+    expr_vars(P, sme, q, var);
+    for (int kk = 0; kk < KK; ++kk) {
+      for (int j = 0; j < EXPR_STATE0; ++j) dvar[j] = 0.0;
+      for (int v = 0; v < NVAR; ++v)
+        for (int k = 0; k < NC; ++k) {
+          dvar[EXPR_STATE0 + v * NC + k] = F[v][k].d[kk];
+          dvar[EXPR_STATE0 + NVAR * NC + v * NC + k] = Ft[v][k].d[kk];
+        }
+      fn_derivatives(P, sme, q, var, dvar, dfn, KK, kk);
+    }
+    c.dfn = dfn;
+    if (SIDE) Phys::template boundary<Dual<KK>, true>(c, P.opt, F, Ft, Cf);
+    else Phys::template volume<Dual<KK>, true>(c, P.opt, F, Ft, Cf);
   }
 
   // S4a: coefficient values
@@ -704,26 +753,7 @@ struct GenBlock {
           }
       }
       if (P.mass_mode) gen_mass_point<Phys, Dual<K>>(c, P.mass_wts, F, Cf);
-      else if (P.fn_state) {
-        // coefficients that read solution fields: their derivative components for this thread's columns
-        double var[NXV], dvar[NXV], dfn[S3F_KINDS * K];
-        expr_vars(P, sme, q, var);
-#pragma unroll
-        for (int kk = 0; kk < K; ++kk) {
-          for (int j = 0; j < EXPR_STATE0; ++j) dvar[j] = 0.0;
-#pragma unroll
-          for (int v = 0; v < NVAR; ++v)
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-              dvar[EXPR_STATE0 + v * NC + k] = F[v][k].d[kk];
-              dvar[EXPR_STATE0 + NVAR * NC + v * NC + k] = Ft[v][k].d[kk];
-            }
-          fn_derivatives(P, sme, q, var, dvar, dfn, K, kk);
-        }
-        c.dfn = dfn;
-        if (SIDE) Phys::template boundary<Dual<K>, true>(c, P.opt, F, Ft, Cf);
-        else Phys::template volume<Dual<K>, true>(c, P.opt, F, Ft, Cf);
-      }
+      else if (STATEK) point_state<K>(P, sme, q, wv, i0, Cf);   // coefficients that read solution fields (STATEK builds only)
       else if (SIDE) Phys::template boundary<Dual<K>, false>(c, P.opt, F, Ft, Cf);
       else Phys::template volume<Dual<K>, false>(c, P.opt, F, Ft, Cf);
       // test-function loop: rows in (variable, basis function) order
@@ -769,17 +799,7 @@ struct GenBlock {
         Cf[v][k] = Dual<1>(0.0);
       }
     if (P.mass_mode) gen_mass_point<Phys, Dual<1>>(c, P.mass_wts, F, Cf);
-    else if (P.fn_state) {
-      double var[NXV], dvar[NXV], dfn[S3F_KINDS];
-      expr_vars(P, sme, q, var);
-      for (int j = 0; j < NXV; ++j) dvar[j] = 0.0;
-      dvar[EXPR_STATE0 + dir] = au;
-      dvar[EXPR_STATE0 + NVAR * NC + dir] = (dir % NC) < Phys::nval(0) ? at : 0.0;
-      fn_derivatives(P, sme, q, var, dvar, dfn, 1, 0);
-      c.dfn = dfn;
-      if (SIDE) Phys::template boundary<Dual<1>, true>(c, P.opt, F, Ft, Cf);
-      else Phys::template volume<Dual<1>, true>(c, P.opt, F, Ft, Cf);
-    }
+    else if (STATEK) point_state<1>(P, sme, q, -1, dir, Cf);
     else if (SIDE) Phys::template boundary<Dual<1>, false>(c, P.opt, F, Ft, Cf);
     else Phys::template volume<Dual<1>, false>(c, P.opt, F, Ft, Cf);
     double* D = sme + L::DM + q * NCV * L::DS;
@@ -898,10 +918,10 @@ struct GenBlock {
 // MINB CTAs of MAXT threads resident per SM
 // TCK: Jacobian by field-direction derivatives + tensor-core contraction (S4d / S4m; single-basis layouts only), else by one
 // derivative lane per element dof (S4b)
-template <class Phys, int NQ, int K, bool SIDE, int MAXT, int MINB, bool TCK>
+template <class Phys, int NQ, int K, bool SIDE, int MAXT, int MINB, bool TCK, bool STATEK>
 __global__ void __launch_bounds__(MAXT, MINB) gen_element_kernel(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) double gen_smem[];
-  typedef GenBlock<Phys, NQ, K, SIDE, TCK> Bk;
+  typedef GenBlock<Phys, NQ, K, SIDE, TCK, STATEK> Bk;
   const int blk = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
   typedef GenLayout<Phys, NQ, TCK> L;
   for (int i = tid; i < P.epb * (L::N > L::NV ? L::N : L::NV); i += T) Bk::s0(P, gen_smem, blk, i);
@@ -912,7 +932,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gen_element_kernel(const __grid_co
   for (int i = tid; i < P.epb * Phys::max_card() * NQ; i += T) Bk::s2(P, gen_smem, blk, i);
   __syncthreads();
   for (int i = tid; i < P.epb * NQ * Bk::S3_KINDS; i += T) Bk::s3(P, gen_smem, blk, i);
-  if (P.fn_state) __syncthreads();   // coefficient functions that read solution fields wait for the fields
+  if (STATEK) __syncthreads();   // coefficient functions that read solution fields wait for the fields
   for (int i = tid; i < P.epb * NQ * Bk::S3F_KINDS; i += T) Bk::s3f(P, gen_smem, blk, i);
   __syncthreads();
   for (int i = tid; i < P.epb * NQ; i += T) Bk::s4a(P, gen_smem, blk, i);

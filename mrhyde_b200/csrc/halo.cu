@@ -91,6 +91,8 @@ struct P2PPeerDev {
   const double* local_slab[2];
   unsigned long long* local_arrive;       // my arrive[peer]
   unsigned long long* remote_ack;         // peer's ack[me]
+  unsigned long long* remote_shift;       // peer's shift[me]: doubles between the slab's matrix part and its first value (0 here; the in-kernel push may use 1)
+  const unsigned long long* local_shift;  // my shift[peer]
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -108,13 +110,13 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // counters[0 .. n): CTAs that finished the push to peer i; counters[n .. 2n): CTAs that finished the add from peer i (both reset by
 // their last CTA); counters[2n]: running ticket of the grid barrier between two sources.
 __global__ void __launch_bounds__(1024) halo_p2p_kernel(const P2PPeerDev* __restrict__ peers, int n, unsigned long long epoch, double* __restrict__ res,
-                                                        double* __restrict__ jac, unsigned* counters) {
+                                                        double* __restrict__ jac, unsigned* counters, int pushed_peer) {
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   const int par = (int)(epoch & 1ull);
   for (int i = 0; i < n; ++i) {
     const P2PPeerDev& P = peers[i];
     const int64_t nr = res ? P.n_send_res : 0, nj = jac ? P.n_send_jac : 0;
-    if (nr + nj == 0) continue;
+    if (nr + nj == 0 || i == pushed_peer) continue;   // pushed_peer: the assembly kernel already stored these rows and raised the flag
     if (threadIdx.x == 0) while (ld_acquire_sys(P.local_ack) + 2ull < epoch) {}   // the slab of this parity was read two calls ago
     __syncthreads();
     double* slab = P.remote_slab[par];
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(1024) halo_p2p_kernel(const P2PPeerDev* __rest
       if (atomicAdd(&counters[i], 1u) == gridDim.x - 1) {
         counters[i] = 0u;
         __threadfence_system();
+        st_release_sys(P.remote_shift, 0ull);
         st_release_sys(P.remote_arrive, epoch);
       }
     }
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(1024) halo_p2p_kernel(const P2PPeerDev* __rest
     __syncthreads();
     const double* slab = P.local_slab[par];
     for (int64_t k = tid; k < nr; k += nth) { const int64_t q = P.recv_res_pos[k]; if (q >= 0) res[q] += __ldcg(slab + k); }
-    const double* sj = slab + P.recv_jac_off;
+    const double* sj = slab + P.recv_jac_off + (int64_t)ld_acquire_sys(P.local_shift);
 #pragma unroll 4
     for (int64_t k = tid; k < nj; k += nth) { const int64_t q = __ldcs(P.recv_jac_pos + k); if (q >= 0) jac[q] += __ldcg(sj + k); }
     __syncthreads();
@@ -196,7 +199,7 @@ HaloExchange::~HaloExchange() {
     cudaFree(p.d_sendbuf); cudaFree(p.d_recvbuf);
   }
   for (size_t p = 0; p < p2p_remote_.size(); ++p) if (p2p_remote_[p]) cudaIpcCloseMemHandle(p2p_remote_[p]);
-  cudaFree(p2p_region_); cudaFree(p2p_peers_dev_); cudaFree(p2p_counters_);
+  cudaFree(p2p_region_); cudaFree(p2p_peers_dev_); cudaFree(p2p_counters_); cudaFree(p2p_push_counter_);
   if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); cudaEventDestroy(ev_ready_); cudaEventDestroy(ev_done_); }
   if (comm_ && api().ok) api().CommDestroy((ncclComm_t)comm_);
 }
@@ -339,14 +342,14 @@ bool HaloExchange::setup_p2p(std::string& err) {
   const std::string want = env && *env ? std::string(env) : transport_;
   if (want != "auto" && want != "p2p" && want != "nccl") { err = "halo transport must be auto|p2p|nccl"; return false; }
   // layout of my region
-  const size_t flag_bytes = (size_t)nranks_ * 2 * sizeof(unsigned long long);
+  const size_t flag_bytes = (size_t)nranks_ * 3 * sizeof(unsigned long long);   // arrive[], ack[], shift[]
   std::vector<int64_t> slab_off((size_t)nranks_, -1), slab_len((size_t)nranks_, 0);
   size_t total = (flag_bytes + 255) & ~(size_t)255;
   for (int p = 0; p < nranks_; ++p) {
     if (p == rank_) continue;
     const Peer& P = peers_[(size_t)p];
     if (P.n_recv_res + P.n_recv_jac == 0) continue;
-    slab_len[(size_t)p] = ((P.n_recv_res + 1) & ~(int64_t)1) + P.n_recv_jac;
+    slab_len[(size_t)p] = ((P.n_recv_res + 1) & ~(int64_t)1) + P.n_recv_jac + 2;   // + room for the in-kernel push's one-double shift
     slab_off[(size_t)p] = (int64_t)total;
     total += (((size_t)slab_len[(size_t)p] * sizeof(double) + 255) & ~(size_t)255) * 2;
   }
@@ -400,6 +403,9 @@ bool HaloExchange::setup_p2p(std::string& err) {
   }
   // device-side peer table
   std::vector<P2PPeerDev> tab;
+  p2p_tab_rank_.clear();
+  p2p_slab_remote_.assign((size_t)nranks_, nullptr);
+  p2p_slab_stride_.assign((size_t)nranks_, 0);
   for (int p = 0; p < nranks_; ++p) {   // ascending rank: the order the received values are added in
     if (p == rank_) continue;
     const Peer& P = peers_[(size_t)p];
@@ -414,8 +420,9 @@ bool HaloExchange::setup_p2p(std::string& err) {
     const int64_t roff = all[words * (size_t)p + 9 + (size_t)rank_];   // where the peer keeps the slabs for what I send
     if (P.n_send_res + P.n_send_jac > 0) {
       if (roff < 0) { err = "halo p2p: the owner expects nothing from a rank that has ghost rows for it (inconsistent maps)"; return false; }
-      const size_t len = (((size_t)(D.send_jac_off + P.n_send_jac) * sizeof(double) + 255) & ~(size_t)255);
+      const size_t len = (((size_t)(D.send_jac_off + P.n_send_jac + 2) * sizeof(double) + 255) & ~(size_t)255);
       D.remote_slab[0] = (double*)(remote + roff); D.remote_slab[1] = (double*)(remote + roff + len);
+      p2p_slab_remote_[(size_t)p] = remote + roff; p2p_slab_stride_[(size_t)p] = len;
     }
     D.remote_arrive = (unsigned long long*)remote + rank_;
     D.local_ack = (unsigned long long*)local + nranks_ + p;
@@ -428,13 +435,18 @@ bool HaloExchange::setup_p2p(std::string& err) {
     }
     D.local_arrive = (unsigned long long*)local + p;
     D.remote_ack = (unsigned long long*)remote + nranks_ + rank_;
+    D.remote_shift = (unsigned long long*)remote + 2 * nranks_ + rank_;
+    D.local_shift = (const unsigned long long*)local + 2 * nranks_ + p;
     tab.push_back(D);
+    p2p_tab_rank_.push_back(p);
   }
   p2p_active_ = (int)tab.size();
   CU_TRY(cudaMalloc(&p2p_peers_dev_, std::max<size_t>(1, tab.size()) * sizeof(P2PPeerDev)));
   if (!tab.empty()) CU_TRY(cudaMemcpy(p2p_peers_dev_, tab.data(), tab.size() * sizeof(P2PPeerDev), cudaMemcpyHostToDevice));
   CU_TRY(cudaMalloc((void**)&p2p_counters_, (2 * tab.size() + 1) * sizeof(unsigned)));
   CU_TRY(cudaMemset(p2p_counters_, 0, (2 * tab.size() + 1) * sizeof(unsigned)));
+  CU_TRY(cudaMalloc((void**)&p2p_push_counter_, sizeof(unsigned)));
+  CU_TRY(cudaMemset(p2p_push_counter_, 0, sizeof(unsigned)));
   int dev = 0, n_sm = 0;
   CU_TRY(cudaGetDevice(&dev));
   CU_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -447,11 +459,50 @@ bool HaloExchange::setup_p2p(std::string& err) {
   return true;
 }
 
+bool HaloExchange::push_params(const double* res, const double* jac, int64_t n_owned, int64_t ghost_base, int n_push_chains, PushDev& X) {
+  std::memset(&X, 0, sizeof(X));
+  push_peer_ = -1;
+  if (!p2p_ || !ready_ || !res || !jac || n_push_chains <= 0) return false;
+  int owner = -1, n_owners = 0;
+  for (int p = 0; p < nranks_; ++p) {
+    if (p == rank_) continue;
+    const Peer& P = peers_[(size_t)p];
+    if (P.n_send_res + P.n_send_jac > 0) { owner = p; ++n_owners; }
+  }
+  if (n_owners != 1) return false;
+  const Peer& P = peers_[(size_t)owner];
+  if (P.send_res_first != n_owned || P.send_jac_first != ghost_base || !p2p_slab_remote_[(size_t)owner]) return false;
+  int ti = -1;
+  for (size_t k = 0; k < p2p_tab_rank_.size(); ++k) if (p2p_tab_rank_[k] == owner) ti = (int)k;
+  if (ti < 0) return false;
+  const unsigned long long epoch = p2p_epoch_ + 1;   // the call counter of the sum() that follows this assembly
+  char* slab = p2p_slab_remote_[(size_t)owner] + (size_t)(epoch & 1ull) * p2p_slab_stride_[(size_t)owner];
+  double* slab_jac = (double*)slab + ((P.n_send_res + 1) & ~(int64_t)1);
+  // one double of shift gives the slab the 16-byte phase of the local array (bulk copies need matching phases)
+  const int shift = (int)(((reinterpret_cast<uintptr_t>(jac) >> 3) + (uintptr_t)ghost_base - (reinterpret_cast<uintptr_t>(slab_jac) >> 3)) & 1u);
+  char* remote = (char*)p2p_remote_[(size_t)owner];
+  X.remote_jac = slab_jac + shift;
+  X.remote_res = (double*)slab;
+  X.res_base = res;
+  X.remote_arrive = (unsigned long long*)remote + rank_;
+  X.remote_shift = (unsigned long long*)remote + 2 * nranks_ + rank_;
+  X.local_ack = (const unsigned long long*)p2p_region_ + nranks_ + owner;
+  X.counter = p2p_push_counter_;
+  X.epoch = epoch;
+  X.ghost_base = ghost_base;
+  X.n_owned = (int32_t)n_owned; X.n_push_chains = n_push_chains; X.shift = shift; X.enabled = 1;
+  push_peer_ = ti; pushed_res_ = res; pushed_jac_ = jac;
+  return true;
+}
+
 bool HaloExchange::sum_p2p(double* res, double* jac, cudaStream_t st, std::string& err) {
   ++p2p_epoch_;
   launches_ = 0;
+  const int pushed = (push_peer_ >= 0 && res == pushed_res_ && jac == pushed_jac_) ? push_peer_ : -1;
+  if (push_peer_ >= 0 && pushed < 0) { err = "halo: the assembly pushed its ghost rows for other arrays than the ones passed to halo_sum"; return false; }
+  push_peer_ = -1;
   if (p2p_active_ == 0) return true;
-  halo_p2p_kernel<<<p2p_grid_, 1024, 0, st>>>((const P2PPeerDev*)p2p_peers_dev_, p2p_active_, p2p_epoch_, res, jac, p2p_counters_);
+  halo_p2p_kernel<<<p2p_grid_, 1024, 0, st>>>((const P2PPeerDev*)p2p_peers_dev_, p2p_active_, p2p_epoch_, res, jac, p2p_counters_, pushed);
   launches_ = 1;
   CU_TRY(cudaGetLastError());
   return true;

@@ -16,6 +16,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "kernel_abi.h"
+
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -33,6 +35,10 @@ class HaloExchange {
   bool setup(int64_t n_rows, int64_t n_owned, int64_t n_cols, const int64_t* col_gids, const int64_t* rowptr, const int32_t* colind, std::string& err);
   void set_transport(const std::string& t) { transport_ = t; }   // before setup(): auto | p2p | nccl
   bool p2p() const { return p2p_; }
+  // In-kernel push (kernel_abi.h: PushDev): when this rank's ghost rows go to ONE owner as the contiguous tails res[n_owned ..) and
+  // jac[ghost_base ..), fills X for the assembly kernel that is about to write res / jac -- the next sum() on the same arrays then
+  // skips its own copy phase.  Returns false (X.enabled = 0) when the layout or the transport does not allow it.
+  bool push_params(const double* res, const double* jac, int64_t n_owned, int64_t ghost_base, int n_push_chains, PushDev& X);
   bool sum(double* res, double* jac, cudaStream_t st, std::string& err);
   // Overlapped form of sum(): start() is called once the ghost rows of res / jac are final on `st` (the caller may keep
   // launching work that does not touch them); the send/recv run on an internal stream.  sum() called afterwards with the same
@@ -74,6 +80,12 @@ class HaloExchange {
   unsigned* p2p_counters_ = nullptr;      // CTA arrival counters of the kernel
   int p2p_active_ = 0, p2p_grid_ = 0;
   unsigned long long p2p_epoch_ = 0;
+  unsigned* p2p_push_counter_ = nullptr;  // push chains of the assembly kernel that have finished
+  int push_peer_ = -1;                    // index (device peer table) of the owner the last push_params prepared, -1: none pending
+  const double* pushed_res_ = nullptr; const double* pushed_jac_ = nullptr;
+  std::vector<int> p2p_tab_rank_;         // rank of every entry of the device peer table
+  std::vector<char*> p2p_slab_remote_;    // per rank: the owner's slabs for what I send (parity 0; parity 1 follows at p2p_slab_stride_)
+  std::vector<size_t> p2p_slab_stride_;
 };
 
 }  // namespace mrhyde_b200

@@ -90,6 +90,24 @@ struct OutDev {
   int diag_one;      // overwrite mode: strong-Dirichlet rows get J(d,d) = 1 (setJacobianConstraints, only with `use strong DBCs`) or stay zero rows
 };
 
+// ---- in-kernel halo push (multi-rank plans on the p2p transport, halo.hpp) ------------------------------------------
+// The chains that complete ghost rows (the first n_push_chains of the plan) write those rows a second time, straight into the owning
+// rank's receive slab over NVLink (bulk copies for the matrix rows, plain stores for the residual entries), and the last of them to
+// finish raises the owner's arrival flag: the exchange of Tpetra's Export(ADD) rides on the assembly kernel, and
+// mrhyde_b200_halo_sum is left with waiting for the flag and adding the slab.
+struct PushDev {
+  double* remote_jac;                 // owner's slab, matrix part (already shifted to the 16-byte phase of the local array): index = CSR offset - ghost_base
+  double* remote_res;                 // owner's slab, residual part: index = row - n_owned
+  const double* res_base;             // this call's residual array (to recover the row from a residual pointer)
+  unsigned long long* remote_arrive;  // owner's arrive[this rank]
+  unsigned long long* remote_shift;   // owner's shift[this rank]: 0 | 1 doubles between the slab's matrix part and the first value
+  const unsigned long long* local_ack;  // my ack[owner]: the call whose slab the owner has finished reading
+  unsigned* counter;                  // push chains that have finished (reset by the last one)
+  unsigned long long epoch;           // call counter of the halo sum this push belongs to (slab parity = epoch & 1)
+  int64_t ghost_base;                 // row_map[n_owned]: CSR offset of the first ghost row
+  int32_t n_owned, n_push_chains, shift, enabled;
+};
+
 // ---- flattened expression programs (expr.hpp) -------------------------------------------------------------
 enum ExprOp : uint8_t {
   OP_END = 0,
@@ -174,6 +192,7 @@ struct ThermalParams {
   ChainDev chains;
   GraphDev graph;
   OutDev out;
+  PushDev push;
 };
 
 }  // namespace mrhyde_b200

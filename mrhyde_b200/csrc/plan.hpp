@@ -57,6 +57,8 @@ struct ChainPlan {
   std::vector<uint32_t> desc[2];         // SLOT_SRCS per slot
   std::vector<uint32_t> mdesc[2];        // metric-ring source words, parallel to desc (kernel_abi.h); empty when ndof > 8
   std::vector<int32_t> orphan_rows;      // rows no element touches
+  std::vector<int32_t> ghost_patterns;   // desc_begin of the patterns of batches that hold ghost rows (multi-rank plans): they always get
+                                         // generated pull code, so that the in-kernel halo push covers every ghost row
   int64_t slot_bytes() const { return (int64_t)cap * stage_len * 8; }
 };
 

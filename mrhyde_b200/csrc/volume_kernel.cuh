@@ -892,7 +892,7 @@ __device__ __forceinline__ void pull_rows_metric(const int desc_begin, const int
 
 template <int MDIM, bool HAS_RES, bool HAS_JAC, bool ACC>   // MDIM: 0 = full local systems in the ring, else the metric ring of that dimension
 __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C, const GraphDev& G, const OutDev& O, const int parity,
-                                           const unsigned ring_s, double* __restrict__ wbuf, const int lane, const double au, const double at) {
+                                           const unsigned ring_s, double* __restrict__ wbuf, const int lane, const double au, const double at, const PushDev* X) {
   const int n_rows = R.hdr.z & 0xFFFF, n_slots = (int)((unsigned)R.hdr.z >> 16);
   const bool active = lane < n_rows;
   const int row = R.rec.x;
@@ -918,9 +918,9 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
   {
     double* const pres2 = HAS_RES ? (O.res + row) : nullptr;
 #ifdef MRH_JIT_METRIC
-    if (MDIM != 0 && mrh_pull_metric_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, n_rows, R.base, O.jac, pres2, active, au, at)) return;
+    if (MDIM != 0 && mrh_pull_metric_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, n_rows, R.base, O.jac, pres2, active, au, at, X)) return;
 #else
-    if (mrh_pull_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, n_rows, R.base, O.jac, pres2, active)) return;
+    if (mrh_pull_special<HAS_RES, HAS_JAC, ACC>(R.hdr.y, parity, rbase, wbuf, lane, n_rows, R.base, O.jac, pres2, active, X)) return;
 #endif
   }
 #if MRH_JIT_FLUSH == 2
@@ -978,13 +978,13 @@ __device__ __forceinline__ void pull_batch(const BatchRegs& R, const ChainDev& C
 
 template <int MDIM, bool HAS_RES, bool HAS_JAC, bool ACC>
 __device__ __forceinline__ void pull_step(BatchRegs R, const ChainDev& C, const GraphDev& G, const OutDev& O, const int batch_begin, const int n_batches,
-                                          const int parity, const unsigned ring_s, double* __restrict__ wbuf, const double au, const double at) {
+                                          const int parity, const unsigned ring_s, double* __restrict__ wbuf, const double au, const double at, const PushDev* X) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int b = warp; b < n_batches; b += nwarps) {
     const int bn = b + nwarps;
     BatchRegs N = R;
     if (bn < n_batches) N = fetch_batch(C, G, batch_begin + bn, lane);   // next batch of this warp: in flight while this one is summed
-    pull_batch<MDIM, HAS_RES, HAS_JAC, ACC>(R, C, G, O, parity, ring_s, wbuf, lane, au, at);
+    pull_batch<MDIM, HAS_RES, HAS_JAC, ACC>(R, C, G, O, parity, ring_s, wbuf, lane, au, at, X);
     R = N;
   }
 }
@@ -1036,6 +1036,13 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     while (clock64() - t0 < ticks) {}
   }
 #endif
+#ifdef MRH_JIT_PUSH
+  const bool pushing = P.push.enabled && chain < P.push.n_push_chains;
+  if (pushing && tid == 0) {   // the slab of this parity was read by the owner two calls ago (practically never waits)
+    unsigned long long a;
+    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(P.push.local_ack) : "memory"); } while (a + 2ull < P.push.epoch);
+  }
+#endif
 #ifdef MRH_JIT_PIPE
   // Register-staged pipeline (class ring).  Per warp and step s:   P(s) = pull of the rows step s completes,  E(s+1) = element work of
   // the next step with its NC + NV staged values kept in REGISTERS;  then  barrier | store E(s+1) into the slot step s-1 occupied |
@@ -1075,12 +1082,12 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
       if (s + 1 < s1) { Rn.hdr = make_int4(0, 0, 0, 0); Rn.rec = make_int2(0, 0); Rn.base = 0; if (warp < sr1.w) Rn = fetch_batch(C, P.graph, sr1.z + warp, lane); }
       auto pull = [&]() {
         switch (mode) {
-          case 1: pull_step<MDIM, true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-          case 2: pull_step<MDIM, false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-          case 3: pull_step<MDIM, true, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-          case 5: pull_step<MDIM, true, false, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-          case 6: pull_step<MDIM, false, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-          case 7: pull_step<MDIM, true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+          case 1: pull_step<MDIM, true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+          case 2: pull_step<MDIM, false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+          case 3: pull_step<MDIM, true, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+          case 5: pull_step<MDIM, true, false, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+          case 6: pull_step<MDIM, false, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+          case 7: pull_step<MDIM, true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
           default: break;
         }
       };
@@ -1159,12 +1166,12 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     }
 #endif
     switch (mode) {
-      case 1: pull_step<MDIM, true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-      case 2: pull_step<MDIM, false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-      case 3: pull_step<MDIM, true, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-      case 5: pull_step<MDIM, true, false, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-      case 6: pull_step<MDIM, false, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
-      case 7: pull_step<MDIM, true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at); break;
+      case 1: pull_step<MDIM, true, false, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+      case 2: pull_step<MDIM, false, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+      case 3: pull_step<MDIM, true, true, false>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+      case 5: pull_step<MDIM, true, false, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+      case 6: pull_step<MDIM, false, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
+      case 7: pull_step<MDIM, true, true, true>(R, C, P.graph, P.out, batch_begin, n_batches, parity, ring_s, wbuf, au, at, &P.push); break;
       default: break;
     }
 #if defined(MRH_EARLY_STAGE1) && defined(MRH_JIT_EARLY_STAGE2)
@@ -1185,6 +1192,22 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
 #endif  // MRH_JIT_PIPE
 #if defined(MRH_JIT_ROWBUF) && MRH_JIT_FLUSH == 2
   mrh_bulk_wait_read();   // shared memory must outlive the bulk copies that read it
+#endif
+#ifdef MRH_JIT_PUSH
+  if (pushing) {
+    // every row this chain pushed has landed in the owner's slab; the last push chain of the grid raises the owner's flag
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      if (atomicAdd(P.push.counter, 1u) == (unsigned)P.push.n_push_chains - 1u) {
+        *P.push.counter = 0u;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(P.push.remote_shift), "l"((unsigned long long)P.push.shift) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(P.push.remote_arrive), "l"(P.push.epoch) : "memory");
+      }
+    }
+  }
 #endif
 }
 

@@ -22,6 +22,8 @@ def _make(kind, n, rank, world):
             options["overlap halo"] = "true"
         if kind == "thermal_nccl":
             options["halo transport"] = "nccl"
+        if kind == "thermal_nopush":   # p2p transport with the copy phase in the halo kernel instead of the assembly kernel
+            options["halo push"] = "false"
         return ThermalBrick(3, n, device=rank, rank=rank, nranks=world, options=options)
     if kind == "maxwell":      # edge / face lattices cut into z-slabs (problems.slab_partition); n[0] == n[1]
         from mrhyde_b200.problems import MaxwellBrick
@@ -67,12 +69,14 @@ def _worker_body(rank, world, q, kind, dev):
     res = torch.zeros(prob.n_rows, dtype=torch.float64, device=dev)
     jac = torch.zeros(prob.nnz, dtype=torch.float64, device=dev)
     assert prob.plan.stat("halo_p2p") == (0 if kind in ("thermal_nccl", "thermal_overlap") else 1)
-    for _ in range(4 if kind in ("thermal_overlap", "thermal") else 1):   # repeated: side stream / events, both slab parities of the p2p transport
+    for _ in range(4 if kind in ("thermal_overlap", "thermal", "thermal_nopush") else 1):   # repeated: side stream / events, both slab parities of the p2p transport
         res.zero_()
         jac.zero_()
         prob.plan.assemble_jacres(u, res, jac)
         prob.plan.halo_sum(res, jac)
     torch.cuda.synchronize()
+    if kind in ("thermal", "thermal_nopush"):   # in-kernel halo push: the assembly kernel of a rank with ghost rows stores them into the owner's slab
+        assert prob.plan.stat("pushed_assembles") == (4 if kind == "thermal" and prob.n_owned < prob.n_rows else 0)
     if kind == "thermal_overlap" and prob.n_owned < prob.n_rows:   # only ranks that hold ghost rows start an exchange early
         assert prob.plan.stat("overlapped_assembles") == 4 and 0 < prob.plan.stat("n_early_chains") < prob.plan.stat("n_chains")
     no = prob.n_owned
@@ -103,7 +107,7 @@ def _oracle_global(oracle_lib, kind, n, ug):
     return op.assemble_jacres(ug)
 
 
-@pytest.mark.parametrize("kind", ["thermal", "thermal_nccl", "thermal_overlap", "le", "ns", "maxwell", "leq2"])
+@pytest.mark.parametrize("kind", ["thermal", "thermal_nopush", "thermal_nccl", "thermal_overlap", "le", "ns", "maxwell", "leq2"])
 def test_two_gpu_halo_sum_equals_single_gpu(oracle_lib, product_lib, kind):
     import torch
     if torch.cuda.device_count() < 2:
@@ -113,7 +117,7 @@ def test_two_gpu_halo_sum_equals_single_gpu(oracle_lib, product_lib, kind):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "thermal_overlap": 7, "le": 3, "ns": 5, "thermal_nccl": 9, "maxwell": 11, "leq2": 13}[kind]
+    port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "thermal_overlap": 7, "le": 3, "ns": 5, "thermal_nccl": 9, "maxwell": 11, "leq2": 13, "thermal_nopush": 15}[kind]
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
