@@ -1122,7 +1122,7 @@ void compile_functions(const FunctionSet& fs, const std::vector<std::string>& na
     if (!names[f].empty()) {
       const LongProgram lp = fs.compile_long(names[f]);
       r.is_const = lp.is_const ? 1 : 0; r.cval = lp.cval;
-      r.pad = lp.uses_state ? 1 : 0;   // reads a solution field: evaluated after the fields, differentiated in the Jacobian stages
+      r.pad = (lp.uses_state ? 1 : 0) | (lp.uses_reduction ? 2 : 0);   // bit 0: reads a solution field (evaluated after the fields, differentiated in the Jacobian stages); bit 1: element reduction
       if (!lp.is_const) {
         r.begin = (int32_t)ops.size(); r.n = (int32_t)lp.op.size();
         ops.insert(ops.end(), lp.op.begin(), lp.op.end());
@@ -1593,7 +1593,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
       // evaluation (functionManager_evaluate.hpp:59-229): the sweep kernel's collapsed Jacobian does not apply -> general path
       FunctionSet probe = make_function_set(P, false, true);
       for (const char* nm : {"thermal source", "thermal diffusion", "specific heat", "density"})
-        if (probe.compile_long(nm).uses_state) sweep_ok = false;
+        { const LongProgram lp = probe.compile_long(nm); if (lp.uses_state || lp.uses_reduction) sweep_ok = false; }   // element reductions (emax / emin / emean) too
     }
     if (want == "sweep" && !sweep_ok) fail(MRHYDE_B200_ERR_UNSUPPORTED, "kernel=sweep: the sweep kernel covers thermal, HGRAD order 1, 2-point Gauss rule, no advection only");
     if (want == "general" || !sweep_ok) { finalize_general(P, phys); return MRHYDE_B200_OK; }
@@ -2146,7 +2146,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
     Q.items = nullptr; Q.item_begin = 0; Q.item_end = M.nelem; Q.inst_base = 0;
     Q.geo_N = H.geo_N.data(); Q.geo_dN = H.geo_dN.data(); Q.ref_tab = H.ref_tab.data(); Q.qwts = H.qwts.data();
     std::memcpy(Q.fn, H.fn, sizeof(Q.fn));
-    Q.fn_state = 0; for (int f = 0; f < GEN_MAXFN; ++f) if (Q.fn[f].pad && !Q.fn[f].is_const) Q.fn_state = 1;
+    Q.fn_state = 0; for (int f = 0; f < GEN_MAXFN; ++f) if ((Q.fn[f].pad & 1) && !Q.fn[f].is_const) Q.fn_state = 1;
     for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = 0; Q.bc_fn[v] = -1; }
     need_emulator(P)->emulate(false, Q, (int)((M.nelem + Q.epb - 1) / Q.epb));
   }
@@ -2159,7 +2159,7 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
       for (int d = 0; d < 3; ++d) { Q.tan_u[d] = S.tan_u[d]; Q.tan_v[d] = S.tan_v[d]; }
       for (int v = 0; v < GEN_MAXVARS; ++v) { Q.bc_type[v] = S.bc_type[v]; Q.bc_fn[v] = S.bc_fn[v]; }
       std::memcpy(Q.fn, S.fn, sizeof(Q.fn));
-      Q.fn_state = 0; for (int f = 0; f < GEN_MAXFN; ++f) if (Q.fn[f].pad && !Q.fn[f].is_const) Q.fn_state = 1;
+      Q.fn_state = 0; for (int f = 0; f < GEN_MAXFN; ++f) if ((Q.fn[f].pad & 1) && !Q.fn[f].is_const) Q.fn_state = 1;
       need_emulator(P)->emulate(true, Q, (int)((Q.item_end + Q.epb - 1) / Q.epb));
     }
   gen_pull_host(H, M, compute_jacobian ? ej.data() : nullptr, compute_residual ? er.data() : nullptr, P->accumulate, compute_residual ? res : nullptr,

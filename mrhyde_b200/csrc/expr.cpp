@@ -131,6 +131,8 @@ Pieces split_expression(std::string s) {
   return out;
 }
 
+bool is_reduction(const std::string& op) { return op == "emax" || op == "emin" || op == "emean"; }
+
 double apply_binary(const std::string& op, double a, double b) {  // functionManager_evaluate.hpp:237-560
   if (op == "plus") return a + b;
   if (op == "minus") return a + (-b);
@@ -156,10 +158,11 @@ double apply_unary(const std::string& op, double a) {
   if (op == "sqrt") return a <= 0.0 ? 0.0 : std::sqrt(a);
   if (op == "sinh") return std::sinh(a);
   if (op == "cosh") return std::cosh(a);
+  if (is_reduction(op)) return a;   // scalar forms: a constant argument is its own max / min / mean (functionManager_evaluate.hpp:1311-1319)
   throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression operator not supported on the device path: " + op);
 }
 bool is_unary(const std::string& op) {
-  return op == "sin" || op == "cos" || op == "tan" || op == "exp" || op == "log" || op == "abs" || op == "sqrt" || op == "sinh" || op == "cosh";
+  return is_reduction(op) || op == "sin" || op == "cos" || op == "tan" || op == "exp" || op == "log" || op == "abs" || op == "sqrt" || op == "sinh" || op == "cosh";
 }
 uint8_t binary_code(const std::string& op) {
   if (op == "plus") return OP_ADD;
@@ -185,6 +188,9 @@ uint8_t unary_code(const std::string& op) {
   if (op == "abs") return OP_ABS;
   if (op == "sqrt") return OP_SQRT;
   if (op == "sinh") return OP_SINH;
+  if (op == "emax") return OP_EMAX;
+  if (op == "emin") return OP_EMIN;
+  if (op == "emean") return OP_EMEAN;
   return OP_COSH;
 }
 
@@ -290,9 +296,19 @@ void FunctionSet::emit(const std::vector<Node>& nodes, int idx, const std::funct
       if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: assignment in a chained position");
       emit(nodes, n.deps[k].second, push_op, depth, maxdepth);
     } else if (is_unary(op)) {
-      emit(nodes, n.deps[k].second, push_op, depth, maxdepth);
       if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: unary operator in a chained position");
-      push_op(unary_code(op), 0.0);
+      if (is_reduction(op)) {
+        // the argument is bracketed so that the evaluator can re-run it at the other points of the element; the closing op carries the
+        // distance back to its OP_EBEGIN (relative: programs are concatenated into one table)
+        int count = 0;
+        auto counting = [&](uint8_t o, double c) { ++count; push_op(o, c); };
+        push_op(OP_EBEGIN, 0.0);
+        emit(nodes, n.deps[k].second, counting, depth, maxdepth);
+        push_op(unary_code(op), (double)(count + 1));
+      } else {
+        emit(nodes, n.deps[k].second, push_op, depth, maxdepth);
+        push_op(unary_code(op), 0.0);
+      }
     } else {
       if (k == 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: binary operator without a left operand");
       const uint8_t code = binary_code(op);
@@ -330,6 +346,8 @@ ExprProgram FunctionSet::compile(const std::string& name) const {
   };
   emit(nodes, root, push_op, depth, maxdepth);
   for (int i = 0; i < p.n; ++i)
+    if (p.op[i] == OP_EBEGIN) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "element reduction (emax / emin / emean) in '" + name + "' needs the general path");
+  for (int i = 0; i < p.n; ++i)
     if ((p.op[i] == OP_PUSHV || (p.op[i] >= OP_ADDV && p.op[i] <= OP_DIVV)) && (int)p.c[i] >= EXPR_STATE0)
       throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "solution-dependent coefficient '" + name + "' needs the general path");
   p.op[p.n] = OP_END;
@@ -361,6 +379,7 @@ std::string FunctionSet::gen_chain(const Node& n, const std::function<std::strin
       acc = d;
     } else if (is_unary(op)) {
       if (k > 0) throw ExprError(MRHYDE_B200_ERR_PARSE, "Error: unary operator in a chained position");
+      if (is_reduction(op)) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "element reduction (" + op + ") needs the general path");
       if (op == "abs") acc = "mrh_abs(" + d + ")";
       else if (op == "sqrt") acc = "mrh_sqrt(" + d + ")";
       else if (op == "sin" || op == "cos") acc = "mrh_" + op + "(" + d + ")";   // table-free kernels (jit prelude)
@@ -485,8 +504,14 @@ LongProgram FunctionSet::compile_long(const std::string& name) const {
   auto push_op = [&](uint8_t op, double c) { p.op.push_back(op); p.c.push_back(c); };
   emit(nodes, root, push_op, depth, maxdepth);
   if (maxdepth > 16) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "expression nests too deeply for the device evaluator: " + name);
-  for (size_t i = 0; i < p.op.size(); ++i)
+  int open = 0;
+  for (size_t i = 0; i < p.op.size(); ++i) {
     if ((p.op[i] == OP_PUSHV || (p.op[i] >= OP_ADDV && p.op[i] <= OP_DIVV)) && (int)p.c[i] >= EXPR_STATE0) p.uses_state = true;
+    if (p.op[i] == OP_EBEGIN) { p.uses_reduction = true; if (++open > 1) throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "nested element reductions in '" + name + "'"); }
+    if (p.op[i] == OP_EMAX || p.op[i] == OP_EMIN || p.op[i] == OP_EMEAN) --open;
+  }
+  if (p.uses_reduction && p.uses_state)
+    throw ExprError(MRHYDE_B200_ERR_UNSUPPORTED, "'" + name + "': an element reduction over a solution-dependent expression has no device kernel in this build");
   return p;
 }
 
@@ -537,7 +562,7 @@ double FunctionSet::eval_host(const ExprProgram& p, const double* vars) {
 std::string FunctionSet::disassemble(const ExprProgram& p) {
   static const char* names[] = {"end", "pushc", "pushv", "add", "sub", "mul", "div", "pow", "lt", "lte", "gt", "gte", "max", "min", "mean",
                                 "addc", "subc", "mulc", "divc", "powc", "addv", "subv", "mulv", "divv",
-                                "sin", "cos", "tan", "exp", "log", "abs", "sqrt", "sinh", "cosh"};
+                                "sin", "cos", "tan", "exp", "log", "abs", "sqrt", "sinh", "cosh", "ebegin", "emax", "emin", "emean"};
   std::ostringstream os;
   os.precision(17);
   if (p.is_const) { os << "const " << p.cval; return os.str(); }

@@ -33,6 +33,7 @@ struct ExprError : std::runtime_error {
 // Variable-length program for the general kernels (bytecode kept in global memory): same ops, no length limit, stack <= 16.
 struct LongProgram {
   bool is_const = false;
+  bool uses_reduction = false;   // contains emax / emin / emean: evaluated over all points of the element (general path only)
   bool uses_state = false;   // reads a solution field (variable slots >= EXPR_STATE0): its value depends on the state
   double cval = 0.0;
   std::vector<uint8_t> op;

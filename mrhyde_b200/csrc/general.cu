@@ -358,7 +358,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   if (pull_mass_mode) { P.mass_mode = initial ? 2 : 1; for (int v = 0; v < I.nvars; ++v) P.mass_wts[v] = mass_wts[v]; }
   std::memcpy(P.off, H.off, sizeof(P.off));
   std::memcpy(P.fn, initial ? H.init_fn : H.fn, sizeof(P.fn));
-  auto mark_state = [&]() { P.fn_state = 0; if (!pull_mass_mode) for (int f = 0; f < GEN_MAXFN; ++f) if (P.fn[f].pad && !P.fn[f].is_const) P.fn_state = 1; };
+  auto mark_state = [&]() { P.fn_state = 0; if (!pull_mass_mode) for (int f = 0; f < GEN_MAXFN; ++f) if ((P.fn[f].pad & 1) && !P.fn[f].is_const) P.fn_state = 1; };
   mark_state();
   P.fn_op = D->fn_op.p; P.fn_c = D->fn_c.p; P.opt = H.opt;
   if (adjoint && std::string(I.physics) == "thermal") P.opt.form_param = 1.0;   // thermal.cpp:197-201, 292-296: sf = 1 when wkset->isAdjoint

@@ -195,14 +195,37 @@ MRH_HD auto fn_get(const QpCtx& c, int i, const Dual<K>*) {
 #define MRH_FN(i) fn_get<STATE>(c, (i), (const T*)nullptr)
 
 // ---- bytecode evaluation (same op set and order as volume_kernel.cuh / expr.cpp) ----------------------------
-MRH_HD double gen_expr_eval(const GenFnRec& f, const uint8_t* __restrict__ ops, const double* __restrict__ cs, const double* __restrict__ var) {
-  if (f.is_const) return f.cval;
+// instructions [i0, i1) on an empty stack; `other` (may be null) fills the variables of another point of the element: it serves the
+// element reductions, whose argument is re-run at every point (no nesting: the inner call passes null)
+struct GenNoPoints { static constexpr bool kHasPoints = false; MRH_HD void operator()(int, double*) const {} };
+template <int NXV, class Other>
+MRH_HD double gen_expr_range(const uint8_t* __restrict__ ops, const double* __restrict__ cs, int i0, int i1, const double* __restrict__ var, int npts, const Other& other) {
   double st[16];
   int sp = 0;
   double a = 0.0;
-  for (int i = f.begin; i < f.begin + f.n; ++i) {
+  for (int i = i0; i < i1; ++i) {
     const double c = MRH_LDG(cs + i);
-    switch (MRH_LDG(ops + i)) {
+    const int opc = MRH_LDG(ops + i);
+    if (opc >= OP_EBEGIN) {
+      if (opc == OP_EBEGIN) continue;
+      // functionManager_evaluate.hpp:413-460, literally: emax / emin keep the LAST value that beats the value at point 0; emean adds the
+      // value at point 0 twice
+      if constexpr (Other::kHasPoints) {   // (the argument's own evaluation never reduces again: no recursion in device code)
+        const int b0 = i - (int)c + 1;
+        double t0 = 0.0, r = 0.0;
+        for (int qq = 0; qq < npts; ++qq) {
+          double vq[NXV] = {0.0};
+          other(qq, vq);
+          const double t = gen_expr_range<NXV>(ops, cs, b0, i, vq, 0, GenNoPoints());
+          if (qq == 0) { t0 = t; r = opc == OP_EMEAN ? t / (double)npts : t; }
+          if (opc == OP_EMEAN) r += t / (double)npts;
+          else if (opc == OP_EMAX ? (t > t0) : (t < t0)) r = t;
+        }
+        a = r;
+      }
+      continue;
+    }
+    switch (opc) {
       case OP_PUSHC: st[sp & 15] = a; ++sp; a = c; break;
       case OP_PUSHV: st[sp & 15] = a; ++sp; a = var[(int)c]; break;
       case OP_ADD: --sp; a = st[sp & 15] + a; break;
@@ -239,6 +262,10 @@ MRH_HD double gen_expr_eval(const GenFnRec& f, const uint8_t* __restrict__ ops, 
     }
   }
   return a;
+}
+MRH_HD double gen_expr_eval(const GenFnRec& f, const uint8_t* __restrict__ ops, const double* __restrict__ cs, const double* __restrict__ var) {
+  if (f.is_const) return f.cval;
+  return gen_expr_range<7>(ops, cs, f.begin, f.begin + f.n, var, 0, GenNoPoints());
 }
 
 // The same program on (value, one derivative component): var / dvar hold the variables and their derivative components.  Comparisons,
@@ -557,6 +584,11 @@ struct GenBlock {
       }
     }
   }
+  struct OtherPoints {   // variables of point qq of the same element / side (element reductions)
+    static constexpr bool kHasPoints = true;
+    const GenParams* P; const double* sme;
+    MRH_HD void operator()(int qq, double* vq) const { double t[NXV]; expr_vars(*P, sme, qq, t); for (int j = 0; j < NXV; ++j) vq[j] = t[j]; }
+  };
   MRH_HD static const GenFnRec* fn_rec(const GenParams& P, int f) {
     if (f < Phys::NFN) return &P.fn[f];
     if (SIDE && P.bc_fn[f - Phys::NFN] >= 0) return &P.fn[P.bc_fn[f - Phys::NFN]];
@@ -573,14 +605,21 @@ struct GenBlock {
     double var[NXV];
     expr_vars(P, sme, q, var);
     const GenFnRec* fr = fn_rec(P, f);
-    sme[L::FN + q * L::NFN + f] = fr ? gen_expr_eval(*fr, P.fn_op, P.fn_c, var) : 0.0;
+    double val = 0.0;
+    if (fr) {
+      if (fr->is_const) val = fr->cval;
+      else if (fr->pad & 2) {   // element reduction inside: its argument is evaluated at every point of this element / side
+        val = gen_expr_range<NXV>(P.fn_op, P.fn_c, fr->begin, fr->begin + fr->n, var, NQ, OtherPoints{&P, sme});
+      } else val = gen_expr_range<NXV>(P.fn_op, P.fn_c, fr->begin, fr->begin + fr->n, var, 0, GenNoPoints());
+    }
+    sme[L::FN + q * L::NFN + f] = val;
   }
   // derivative components of the state-dependent coefficient functions at a point for the seeds dvar (others: 0)
   MRH_HD static void fn_derivatives(const GenParams& P, const double* sme, int q, const double (&var)[NXV], const double (&dvar)[NXV], double* dfn, int stride, int kk) {
     for (int f = 0; f < S3F_KINDS; ++f) {
       const GenFnRec* fr = fn_rec(P, f);
       double v = 0.0, d = 0.0;
-      if (fr && fr->pad) gen_expr_eval_dual(*fr, P.fn_op, P.fn_c, var, dvar, v, d);
+      if (fr && (fr->pad & 1)) gen_expr_eval_dual(*fr, P.fn_op, P.fn_c, var, dvar, v, d);
       dfn[f * stride + kk] = d;
     }
   }

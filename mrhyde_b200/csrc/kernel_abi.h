@@ -117,6 +117,10 @@ enum ExprOp : uint8_t {
   OP_ADDC, OP_SUBC, OP_MULC, OP_DIVC, OP_POWC,        // binary with constant right operand
   OP_ADDV, OP_SUBV, OP_MULV, OP_DIVV,                 // binary with variable right operand
   OP_SIN, OP_COS, OP_TAN, OP_EXP, OP_LOG, OP_ABS, OP_SQRT, OP_SINH, OP_COSH,  // unary on top of stack
+  // element reductions (functionManager_evaluate.hpp:413-460): the argument -- the instructions between OP_EBEGIN and the closing op, whose
+  // constant holds the index of its OP_EBEGIN -- is evaluated at EVERY point of the element / side and the reduced value replaces the top of
+  // the stack at all of them.  General path only (long programs).
+  OP_EBEGIN, OP_EMAX, OP_EMIN, OP_EMEAN,
 };
 
 constexpr int EXPR_MAXOPS = 56;

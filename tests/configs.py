@@ -135,5 +135,9 @@ def general_cases():
         ("le3d-state-mu", variant(LE_3D, **{"Functions/mu": "1.0+0.2*dx*dx+0.1*grad(dy)[z]"}), {}, None, False),
         ("ns2d-state-viscosity", variant(NS_2D, **{"Functions/viscosity": "0.5+0.1*ux*ux+0.05*sqrt(1.0+uy*uy)"}), {}, None, False),
         ("maxwell-state-sigma", variant(MAXWELL_3D, **{"Functions/conductivity": "0.2+E[x]*E[x]+0.1*B[z]"}), {}, DIRK12, False),
+        # element reductions inside an expression (functionManager_evaluate.hpp:413-460, literal semantics incl. emean's double count of point 0)
+        ("thermal3d-emax", variant(t3, **{"Functions/thermal diffusion": "1.0+emax(x*y)", "Functions/thermal source": "emean(x)+emin(y*z)*x"}), {}, None, False),
+        ("le3d-emean", variant(LE_3D, **{"Functions/lambda": "1.0+emean(x*z)", "Functions/source dy": "emax(y*z)+x"}), {}, None, False),
+        ("thermal2d-weak-emin", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Functions/thermal diffusion": "1.0+emin(x+y)"})), {}, None, False),
         ("thermal2d-weak-state", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Functions/thermal diffusion": "1.0+0.5*T*T"})), {}, None, False),
     ]

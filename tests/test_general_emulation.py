@@ -63,6 +63,8 @@ def test_state_dependent_thermal_coefficient_leaves_the_sweep_kernel(oracle_lib,
     op = oracle_lib.OracleProblem(cfg)
     assert helpers.plan_from_oracle(op, cfg, device=-1).stat("general") == 1
     assert helpers.plan_from_oracle(op, configs.variant(cfg, **{"Functions/thermal diffusion": "1.0+x*x"}), device=-1).stat("general") == 0
+    # element reductions are evaluated over all points of an element: general path too
+    assert helpers.plan_from_oracle(op, configs.variant(cfg, **{"Functions/thermal diffusion": "1.0+emax(x*y)"}), device=-1).stat("general") == 1
 
 
 def test_host_only_plan_cannot_assemble(oracle_lib, product_lib):
