@@ -175,7 +175,7 @@ struct NvtxRange {
 };
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "scratch GB", "debug transient", "debug mode", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "lump mass", "scratch GB", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -1268,6 +1268,7 @@ void finalize_general(mrhyde_b200_plan* P, const std::string& phys) {
     fail(MRHYDE_B200_ERR_INVALID, e.what());
   }
   H.epb_override = std::stoi(opt(P, "elements per cta", "0"));
+  H.lump_mass = opt_bool(P, "lump mass", false);
   {
     // which build of the element kernel assembles Jacobians: tensor = field-direction derivatives + FP64 tensor-core contraction
     // (single-basis HGRAD modules), lanes = one derivative lane per element dof (every module)
@@ -1588,6 +1589,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     bool sweep_ok = phys == "thermal" && P->nvars == 1 && B.type == "HGRAD" && B.order == 1 && B.card == NV && P->ndof_elem == NV && P->nqp == NV && !B.grad.empty() &&
                     !opt_bool(P, "include advection", false);
     for (int i = 0; sweep_ok && i < NV; ++i) if (P->offsets[i] != i) sweep_ok = false;
+    if (opt_bool(P, "lump mass", false)) sweep_ok = false;   // the column redirect of the lumped scatter lives in the general path's pull
     if (sweep_ok) {
       // a coefficient that reads the solution (e.g. thermal diffusion: 1.0+T*T) needs derivative lanes through the function
       // evaluation (functionManager_evaluate.hpp:59-229): the sweep kernel's collapsed Jacobian does not apply -> general path

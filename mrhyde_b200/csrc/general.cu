@@ -71,6 +71,7 @@ struct PullParams {
   // mass pull: fixed rows are not skipped, instances >= mass_inst_end (boundary sides) are ignored, O.res receives the
   // diagonal vector (Jacobi diagonal, or the lumped row sums of |entries| when mass_mode == 2)
   int32_t mass_mode;
+  int32_t lump;                 // Solver: lump mass -- every entry of an element row is added to the row's diagonal (assemblyManager_scatter.hpp:263-268)
   int64_t mass_inst_end;        // scratch slots >= this one hold boundary-side instances
 };
 
@@ -135,6 +136,11 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
   }
   const int N = Q.N;
   const int64_t c0 = __ldg(Q.contrib_ptr + k), c1 = __ldg(Q.contrib_ptr + k + 1);
+  int dpos = -1;
+  if (Q.lump) {   // position of the diagonal entry in this row
+    for (int t = lane; t < len; t += G) if (__ldg(Q.G.colind + rs + t) == r) dpos = t;
+    for (int o = G / 2; o > 0; o >>= 1) dpos = max(dpos, __shfl_xor_sync(mask, dpos, o, G));
+  }
   if (Q.O.jac) {
     for (int t = lane; t < len; t += G) buf[t] = 0.0;
     __syncwarp(mask);
@@ -155,8 +161,16 @@ __global__ void __launch_bounds__(256) gen_pull_kernel(const __grid_constant__ P
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {   // ascending instance order, one instance at a time: distinct positions within an instance
+        if (Q.lump) {
+          double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) if (ps[u][j] >= 0) buf[ps[u][j]] += v[u][j];
+          for (int j = 0; j < NPL; ++j) if (ps[u][j] >= 0) s += v[u][j];
+          for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o, G);
+          if (lane == 0 && dpos >= 0) buf[dpos] += s;
+        } else {
+#pragma unroll
+          for (int j = 0; j < NPL; ++j) if (ps[u][j] >= 0) buf[ps[u][j]] += v[u][j];
+        }
         __syncwarp(mask);
       }
     }
@@ -388,6 +402,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
     Q.elem_jac = D->elem_jac.p; Q.elem_res = D->elem_res.p; Q.G = G; Q.O = O;
     Q.row_begin = row_begin; Q.row_end = row_end; Q.n_owned = H.n_owned; Q.N = I.N; Q.max_row_len = std::max(1, H.max_row_len);
     Q.mass_mode = pull_mass_mode; Q.mass_inst_end = H.scratch_cap;
+    Q.lump = (H.lump_mass && !pull_mass_mode) ? 1 : 0;
     const int Gs = I.N <= 8 ? 8 : (I.N <= 16 ? 16 : 32);
     const int npl = (I.N + Gs - 1) / Gs;
     if (npl > 3) return "general pull: more than 96 dofs per element";

@@ -72,6 +72,7 @@ struct GeneralPlanHost {
   int64_t n_elem = 0, n_inst = 0, n_rows = 0, n_owned = 0;
   int32_t max_row_len = 0;
   int epb_override = 0;                  // option "elements per cta" (0 = automatic)
+  bool lump_mass = false;                // Solver: lump mass (fused scatter's column redirect to the diagonal)
   bool use_tensor = false;               // option "jacobian" = auto | tensor | lanes: which build of the element kernel assembles Jacobians
   // pull schedule
   std::vector<int32_t> row_order;        // rows sorted by completion batch

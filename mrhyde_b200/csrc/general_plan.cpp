@@ -228,7 +228,15 @@ void gen_pull_host(const GeneralPlanHost& H, const MeshGraph& m, const double* e
     for (int64_t p = H.contrib_ptr[(size_t)k]; p < H.contrib_ptr[(size_t)k + 1]; ++p) {
       const int64_t ci = H.contrib[(size_t)p];
       const uint16_t* ps = &H.pos_tab[((size_t)H.pos_id[(size_t)(ci / N)] * N + (size_t)(ci % N)) * N];
-      if (elem_jac && jac) for (int c = 0; c < N; ++c) buf[ps[c]] += elem_jac[ci * N + c];
+      if (elem_jac && jac) {
+        if (H.lump_mass) {   // every entry of the element row goes to the diagonal
+          int dpos = -1;
+          for (int t = 0; t < len; ++t) if (m.colind[(size_t)(rs + t)] == r) dpos = t;
+          if (dpos >= 0) for (int c = 0; c < N; ++c) buf[(size_t)dpos] += elem_jac[ci * N + c];
+        } else {
+          for (int c = 0; c < N; ++c) buf[ps[c]] += elem_jac[ci * N + c];
+        }
+      }
       if (elem_res) rsum += elem_res[ci];
     }
     if (jac) for (int t = 0; t < len; ++t) jac[rs + t] = (accumulate ? jac[rs + t] : 0.0) + buf[(size_t)t];

@@ -79,6 +79,7 @@ class AssemblyManager {
   std::vector<std::string> modules;
   int type_AD = 0, maxdof = 0;
   bool assemble_volume_terms = true, assemble_boundary_terms = true, use_strong_DBCs = true;
+  bool lump_mass = false;    // Solver: lump mass (assemblyManager_construct.hpp:36): the fused scatter sends every entry of a row to its diagonal
   bool useadjoint = false;   // assembleJacRes(..., useadjoint, ...): transposed local Jacobians (updateJac, assemblyManager_jacres.hpp:1459-1475)
   TimeData td;
   std::unique_ptr<EngineBase> eng_scalar, eng_ad;
@@ -302,7 +303,7 @@ struct Engine : EngineBase {
                 // adjoint: local_J(elem, offsets(m,k), offsets(n,j)) += res(elem, offsets(n,j)).dx(offsets(m,k)), i.e. the entry in
                 // (row, col) of the scattered matrix is d res(col) / d u(row)   (updateJac / updateJacBoundary, useadjoint branch)
                 vals[col] = am.useadjoint ? ADTraits<EvalT>::dx(res(elem, col), row) : ADTraits<EvalT>::dx(res(elem, row), col);
-                cols[col] = LIDs[col];
+                cols[col] = am.lump_mass ? rowIndex : LIDs[col];   // assemblyManager_scatter.hpp:263-268
               }
             // KokkosSparse::CrsMatrix::sumIntoValues(row, cols, n, vals, is_sorted=false): linear search per entry
             const int64_t rs = am.graph.rowptr[rowIndex], re = am.graph.rowptr[rowIndex + 1];
@@ -582,6 +583,7 @@ inline AssemblyManager::AssemblyManager(const Settings& s) : settings(s) {
   // ---- solver / assembly flags
   workset_size = s.geti("Solver/workset size", 100);
   use_strong_DBCs = s.getb("Solver/use strong DBCs", true);
+  lump_mass = s.getb("Solver/lump mass", false);
   assemble_volume_terms = s.getb("Physics/assemble volume terms", true);
   assemble_boundary_terms = s.getb("Physics/assemble boundary terms", true);
 

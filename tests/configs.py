@@ -139,5 +139,8 @@ def general_cases():
         ("thermal3d-emax", variant(t3, **{"Functions/thermal diffusion": "1.0+emax(x*y)", "Functions/thermal source": "emean(x)+emin(y*z)*x"}), {}, None, False),
         ("le3d-emean", variant(LE_3D, **{"Functions/lambda": "1.0+emean(x*z)", "Functions/source dy": "emax(y*z)+x"}), {}, None, False),
         ("thermal2d-weak-emin", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Functions/thermal diffusion": "1.0+emin(x+y)"})), {}, None, False),
+        # Solver: lump mass -- the fused scatter adds every entry of a row to its diagonal (assemblyManager_scatter.hpp:263-268)
+        ("thermal3d-lump-dirk", variant(t3, **{"Solver/lump mass": True, "Functions/density": "2.0"}), {}, DIRK12, False),
+        ("thermal2d-lump-dirk", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Solver/lump mass": True})), {}, DIRK12, False),
         ("thermal2d-weak-state", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Functions/thermal diffusion": "1.0+0.5*T*T"})), {}, None, False),
     ]

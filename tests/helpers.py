@@ -33,6 +33,8 @@ def plan_from_oracle(op, cfg, device=0, options=None, indexed=False):
             plan.set_option(key, phys[key])
     if "use strong DBCs" in solver:
         plan.set_option("use strong DBCs", solver["use strong DBCs"])
+    if "lump mass" in solver:
+        plan.set_option("lump mass", solver["lump mass"])
     for k, v in list(DEFAULT_OPTIONS.items()) + list((options or {}).items()):
         plan.set_option(k, v)
     if indexed:

@@ -65,6 +65,9 @@ def test_state_dependent_thermal_coefficient_leaves_the_sweep_kernel(oracle_lib,
     assert helpers.plan_from_oracle(op, configs.variant(cfg, **{"Functions/thermal diffusion": "1.0+x*x"}), device=-1).stat("general") == 0
     # element reductions are evaluated over all points of an element: general path too
     assert helpers.plan_from_oracle(op, configs.variant(cfg, **{"Functions/thermal diffusion": "1.0+emax(x*y)"}), device=-1).stat("general") == 1
+    # Solver: lump mass redirects the scatter's columns: general path's pull
+    lump = configs.variant(cfg, **{"Functions/thermal diffusion": "1.0", "Solver/lump mass": True})
+    assert helpers.plan_from_oracle(op, lump, device=-1).stat("general") == 1
 
 
 def test_host_only_plan_cannot_assemble(oracle_lib, product_lib):
