@@ -114,7 +114,8 @@ def test_two_gpu_halo_sum_equals_single_gpu(oracle_lib, product_lib, kind):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from mrhyde_b200.problems import ThermalBrick
-    world = 2
+    # MRHYDE_B200_TEST_WORLD=4 (or 8) on a larger box: interior ranks hold ghost rows AND receive them (push to one side, add from the other)
+    world = max(2, min(torch.cuda.device_count(), int(os.environ.get("MRHYDE_B200_TEST_WORLD", "2"))))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 2000) + {"thermal": 0, "thermal_overlap": 7, "le": 3, "ns": 5, "thermal_nccl": 9, "maxwell": 11, "leq2": 13, "thermal_nopush": 15}[kind]
