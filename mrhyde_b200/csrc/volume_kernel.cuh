@@ -1128,8 +1128,8 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     const int n_elem = sr.y, batch_begin = sr.z, n_batches = sr.w;
     const int parity = (s - s0) & 1;
     double* slot = ring + parity * slot_doubles;
-    int4 sr_next2 = sr_next;
-    if (s + 2 < s1) sr_next2 = ldg_pinned_v4(C.steps + s + 2);
+    // unconditional (clamped) load: a predicated one needs a select right behind it, which waits for the load
+    const int4 sr_next2 = ldg_pinned_v4(C.steps + min(s + 2, s1 - 1));
     // this warp's first batch of the step
     BatchRegs R;
     R.hdr = make_int4(0, 0, 0, 0); R.rec = make_int2(0, 0); R.base = 0;
@@ -1150,6 +1150,9 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
 #endif
 #ifndef MRH_EARLY_STAGE1
     if (more) elem_stage1<DIM>(P, sr_next.x + tid, E);
+#endif
+#if defined(MRH_JIT_PREFETCH2) && defined(MRH_EARLY_STAGE1)
+    if (more) elem_prefetch2<DIM>(P, Nx);  // the next step's connectivity arrived during the element work: nothing waits here
 #endif
     __syncthreads();
 #if defined(MRH_JIT_PREFETCH2) && !defined(MRH_EARLY_STAGE1)
