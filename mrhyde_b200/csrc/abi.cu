@@ -175,7 +175,7 @@ struct NvtxRange {
 };
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "lump mass", "scratch GB", "debug transient", "debug mode", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "lump mass", "prefetch records", "scratch GB", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -184,6 +184,10 @@ std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::st
 bool opt_bool(const mrhyde_b200_plan* P, const std::string& key, bool def) {
   const std::string v = opt(P, key, def ? "true" : "false");
   return v == "true" || v == "True" || v == "1";
+}
+int prefetch_mode(const mrhyde_b200_plan* P) {   // "prefetch": true | false | lean (first vertex / dof of an element only)
+  if (opt(P, "prefetch", "true") == "lean") return 2;
+  return opt_bool(P, "prefetch", true) ? 1 : 0;
 }
 
 // Hex8 / Quad4 nodal shape functions in Shards vertex order (CellTools::setJacobian uses the cell's
@@ -276,7 +280,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
                                const int64_t (&n_class)[3], int metric_ng, int max_patterns, int pull_group,
-                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint, bool prefetch2, bool push) {
+                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint, int prefetch2, bool push, bool prefetch_meta) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -291,8 +295,9 @@ std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& f
   o += "#define MRH_JIT_SOURCE_CONST " + std::to_string(source_const) + "\n";
   if (late_stage1) o += "#define MRH_JIT_LATE_STAGE1 1\n";
   if (push) o += "#define MRH_JIT_PUSH 1   /* multi-rank plan: ghost rows are also stored into the owner's receive slab (kernel_abi.h: PushDev) */\n";
-  if (prefetch2) o += "#define MRH_JIT_PREFETCH2 1   /* L2 prefetch of the next step's state / vertices before the pull */\n";
+  if (prefetch2) o += "#define MRH_JIT_PREFETCH2 " + std::to_string(prefetch2) + "   /* L2 prefetch of the next step's state / vertices before the pull (2: first vertex only) */\n";
   if (early_stage2) o += "#define MRH_JIT_EARLY_STAGE2 1\n";
+  if (prefetch_meta) o += "#define MRH_JIT_PREFETCH_META 1   /* L2 prefetch of the record streams of step s + 2 */\n";
   if (literal_tables) o += "#define MRH_JIT_LITERAL_TABLES 1\n";
   o += "/*@stagger@*/\n";
   o += "#define MRH_JIT_FLUSH_UNROLL " + std::to_string(flush_unroll) + "\n";
@@ -1736,8 +1741,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     for (int tr = 0; tr < 2; ++tr)
       P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
     const int pull_group = std::stoi(opt(P, "pull group", "8"));
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, opt_bool(P, "prefetch", true), P->push_ok)
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, opt_bool(P, "prefetch", true), P->push_ok);
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, prefetch_mode(P), P->push_ok, opt_bool(P, "prefetch records", true))
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, prefetch_mode(P), P->push_ok, opt_bool(P, "prefetch records", true));
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface

@@ -442,14 +442,20 @@ __device__ __forceinline__ void elem_prefetch2(const ThermalParams<DIM>& P, cons
   constexpr int NV = 1 << DIM;
   constexpr int nb[4] = {0, 1, 3, 4};
   const double* vc[3] = {P.vx, P.vy, P.vz};
+#if defined(MRH_JIT_PREFETCH2) && MRH_JIT_PREFETCH2 == 2
+  // lean: the lines of the element's first vertex / dof only -- the other seven are some neighbour's first one on all but the rim of a column
+  constexpr int NP = 1, VP = 0;
+#else
+  constexpr int NP = NV, VP = DIM;
+#endif
 #pragma unroll
-  for (int i = 0; i < NV; ++i) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.sol + E.ld[i]));
+  for (int i = 0; i < NP; ++i) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.sol + E.ld[i]));
   if (MRH_TRANSIENT(P.td)) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.td.prev[0] + E.ld[i]));
+    for (int i = 0; i < NP; ++i) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.td.prev[0] + E.ld[i]));
   }
 #pragma unroll
-  for (int v = 0; v <= DIM; ++v)
+  for (int v = 0; v <= VP; ++v)
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
       if (v == 0 || MRH_HAS_GENERAL || MRH_HAS_AFFINE || d == v - 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(vc[d] + E.cn[nb[v]]));
@@ -1188,6 +1194,26 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     }
 #endif
     if (more) elem_stage2<DIM>(P, E);
+#endif
+#ifdef MRH_JIT_PREFETCH_META
+    // the record streams of step s + 2 (connectivity, row and batch records: each byte is read once, so every load of them is a DRAM
+    // miss) are requested into L2 one whole step ahead, one 128-byte line per thread: no register, no scoreboard
+    if (s + 2 < s1) {
+      // only lines that hold bytes of the step: first line = the one of its first byte, count from the line of its last byte
+      const unsigned long long c0 = reinterpret_cast<unsigned long long>(P.chains.step_conn + (size_t)sr_next2.x * (1 << DIM));
+      const int cl = (int)((((c0 + (unsigned long long)(sr_next2.y * (1 << DIM) * 4 - 1)) >> 7) - (c0 >> 7)) + 1ull);
+      const char* cb = reinterpret_cast<const char*>(c0 & ~127ull);
+      const char* rb = reinterpret_cast<const char*>(C.rows + (size_t)sr_next2.z * 32);
+      const int rl = sr_next2.w * 4;   // 32 records of 16 bytes per batch
+      const char* p = nullptr;
+      if (tid < cl) p = cb + tid * 128;
+      else if (tid < cl + rl) p = rb + (tid - cl) * 128;
+      else if (tid == cl + rl) p = reinterpret_cast<const char*>(C.batches + sr_next2.z);
+#ifndef MRH_JIT_LIDS_ARE_CONN
+      else if (tid - cl - rl - 1 < cl) p = cb + (reinterpret_cast<const char*>(P.chains.step_lids) - reinterpret_cast<const char*>(P.chains.step_conn)) + (tid - cl - rl - 1) * 128;
+#endif
+      if (p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    }
 #endif
     sr = sr_next; sr_next = sr_next2;
     __syncthreads();  // the next step overwrites the slot this pull read as "previous"

@@ -322,7 +322,7 @@ def test_build_option_variants_compile(oracle_lib, product_lib, tmp_path):
     alternatives kept for experiments); unknown values are rejected at finalize."""
     cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 9, "Mesh/NY": 7, "Mesh/NZ": 6})
     variants = [{"flush": "flat"}, {"flush": "row", "flush unroll": 4}, {"pull group": 28}, {"pull patterns": 0}, {"stage1": "early"},
-                {"stage1": "early", "stage2": "early"}, {"tables": "literal"}, {"stagger ns": 3000}, {"max registers": 96},
+                {"stage1": "early", "stage2": "early"}, {"stage1": "early", "prefetch": "lean", "prefetch records": True}, {"tables": "literal"}, {"stagger ns": 3000}, {"max registers": 96},
                 {"ring": "metric", "pull group": 4}, {"ring": "full", "flush": "flat"}]
     for options in variants:
         op, plan = _host_plan(oracle_lib, cfg, options=options)
