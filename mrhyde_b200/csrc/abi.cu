@@ -111,7 +111,7 @@ struct mrhyde_b200_plan {
   DevBuf<double> d_vx, d_vy, d_vz;
   DevBuf<int32_t> d_conn, d_lids, d_colind, d_chain_step_ptr, d_step_elems, d_step_conn, d_step_lids, d_orphans;
   DevBuf<int64_t> d_rowptr, d_fixed_diag;
-  DevBuf<uint8_t> d_fixed, d_eclass, d_step_eclass;
+  DevBuf<uint8_t> d_fixed, d_eclass, d_step_eclass, d_chain_invariant;
   DevBuf<StepRec> d_steps;
   DevBuf<BatchRec> d_batches;
   DevBuf<RowRec> d_rows;
@@ -175,7 +175,7 @@ struct NvtxRange {
 };
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "lump mass", "prefetch records", "scratch GB", "debug transient", "debug mode", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "lump mass", "prefetch records", "column cache", "scratch GB", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -184,6 +184,18 @@ std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::st
 bool opt_bool(const mrhyde_b200_plan* P, const std::string& key, bool def) {
   const std::string v = opt(P, key, def ? "true" : "false");
   return v == "true" || v == "True" || v == "1";
+}
+// Axes whose one-coordinate sub-expressions stay the same along most chains of the plan (an extruded column changes the sweep coordinate only):
+// the generated source function keeps their values per thread ("column cache", default on).
+int column_cache_axes(const mrhyde_b200_plan* P) {
+  if (!opt_bool(P, "column cache", true) || P->cp.chain_invariant.empty()) return 0;
+  int axes = 0;
+  for (int d = 0; d < P->dim; ++d) {
+    size_t n = 0;
+    for (uint8_t f : P->cp.chain_invariant) n += (f >> d) & 1;
+    if (2 * n > P->cp.chain_invariant.size()) axes |= 1 << d;
+  }
+  return axes;
 }
 int prefetch_mode(const mrhyde_b200_plan* P) {   // "prefetch": true | false | lean (first vertex / dof of an element only)
   if (opt(P, "prefetch", "true") == "lean") return 2;
@@ -280,7 +292,7 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
 template <int DIM>
 std::string thermal_jit_source(const ThermalTables<DIM>& T, const FunctionSet& fs, int all_const, int source_const, const ChainPlan& cp,
                                const int64_t (&n_class)[3], int metric_ng, int max_patterns, int pull_group,
-                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint, int prefetch2, bool push, bool prefetch_meta) {
+                               const std::vector<int32_t>& class_of_t, const std::vector<int32_t>& class_rep, int debug_skip, bool late_stage1, int flush_mode, int flush_unroll, bool early_stage2, bool literal_tables, bool lids_are_conn, int pipe, int store_hint, int prefetch2, bool push, bool prefetch_meta, int cache_axes) {
   typedef Q1Shape<DIM> S;
   std::string o;
   o += "// generated by mrhyde_b200 (abi.cu: thermal_jit_source)\n";
@@ -377,7 +389,9 @@ __device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
       qidx[q * 3 + d] = f;
     }
   }
-  o += fs.codegen_tensor("thermal source", "mrh_fn_source_box", S::NQ, nqa, qidx);
+  int cache_n = 0;
+  o += fs.codegen_tensor("thermal source", "mrh_fn_source_box", S::NQ, nqa, qidx, cache_axes, &cache_n);
+  o += "#define MRH_SRC_CACHE_N " + std::to_string(cache_n) + "   /* one-coordinate sub-expression values of the source a thread keeps along its chain (axes mask " + std::to_string(cache_axes) + ") */\n";
   o += "#define MRH_NQA0 " + std::to_string(nqa[0]) + "\n#define MRH_NQA1 " + std::to_string(nqa[1]) + "\n#define MRH_NQA2 " + std::to_string(nqa[2]) + "\n";
   o += "namespace jit_tab {\n";
   auto arr = [&](const char* decl, const double* v, size_t n) { o += std::string("constexpr double ") + decl + " = {"; emit_values(o, v, n); o += "};\n"; };
@@ -1741,8 +1755,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
     for (int tr = 0; tr < 2; ++tr)
       P->smem_metric[tr] = (size_t)(2 * P->cp.cap) * (size_t)(P->metric_ng + tr + NV * (2 + tr)) * sizeof(double) + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
     const int pull_group = std::stoi(opt(P, "pull group", "8"));
-    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, prefetch_mode(P), P->push_ok, opt_bool(P, "prefetch records", true))
-                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, prefetch_mode(P), P->push_ok, opt_bool(P, "prefetch records", true));
+    P->jit_source = P->dim == 3 ? thermal_jit_source<3>(P->th3.tab, fs, P->th3.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, prefetch_mode(P), P->push_ok, opt_bool(P, "prefetch records", true), column_cache_axes(P))
+                                : thermal_jit_source<2>(P->th2.tab, fs, P->th2.all_const, src.is_const, P->cp, n_class, P->metric_ng, max_patterns, pull_group, P->class_of_t, P->class_rep, std::stoi(opt(P, "debug skip", "0")), opt(P, "stage1", "late") != "early", flush_mode, std::max(1, std::stoi(opt(P, "flush unroll", "8"))), opt(P, "stage2", "late") == "early", opt(P, "tables", "constant") == "literal", lids_are_conn, std::max(0, std::min(2, std::stoi(opt(P, "pipeline", "0")))), opt_bool(P, "store hint", false) ? 1 : 0, prefetch_mode(P), P->push_ok, opt_bool(P, "prefetch records", true), column_cache_axes(P));
   }
   if (host_only) {
     // boundary groups still get their expressions compiled so that set-up errors surface
@@ -1769,6 +1783,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   P->d_chain_step_ptr.upload(CP.chain_step_ptr, tot); P->d_steps.upload(CP.steps, tot); P->d_step_elems.upload(CP.step_elems, tot);
   P->d_batches.upload(CP.batches, tot); P->d_rows.upload(CP.rows, tot);
   P->d_step_conn.upload(CP.step_conn, tot); P->d_step_eclass.upload(CP.step_eclass, tot);
+  P->d_chain_invariant.upload(CP.chain_invariant, tot);
   if (!lids_are_conn) P->d_step_lids.upload(CP.step_lids, tot);   // else the kernels read the one connectivity stream for both
   P->d_desc0.upload(CP.desc[0], tot); P->d_desc1.upload(CP.desc[1], tot);
   if (P->metric_ng > 0) { P->d_mdesc0.upload(CP.mdesc[0], tot); P->d_mdesc1.upload(CP.mdesc[1], tot); }
@@ -1791,6 +1806,7 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   D.desc0 = reinterpret_cast<const SrcQuad*>(P->d_desc0.p); D.desc1 = reinterpret_cast<const SrcQuad*>(P->d_desc1.p);
   D.mdesc0 = reinterpret_cast<const SrcQuad*>(P->d_mdesc0.p); D.mdesc1 = reinterpret_cast<const SrcQuad*>(P->d_mdesc1.p);
   D.cap = CP.cap;
+  D.chain_invariant = CP.chain_invariant.empty() ? nullptr : P->d_chain_invariant.p;
   GraphDev G{P->d_rowptr.p, P->d_colind.p, P->d_fixed.p};
   auto fill_common = [&](auto& th) {
     th.vx = P->d_vx.p; th.vy = P->d_vy.p; th.vz = P->d_vz.p;
@@ -2009,6 +2025,8 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "metric_ring") *value = P->metric_ng;
   else if (k == "overlapped_assembles") *value = P->overlapped_assembles;
   else if (k == "n_early_chains") *value = P->cp.n_early_chains;
+  else if (k == "column_cache_axes") *value = column_cache_axes(P);   // axes whose one-coordinate source sub-expressions a thread keeps along its chain
+  else if (k == "n_invariant_chains") { int64_t n = 0; for (uint8_t f : P->cp.chain_invariant) n += f != 0; *value = n; }
   else if (k == "class_ring") *value = P->class_nc;
   else if (k == "stage_len") *value = P->stage_len;
   else if (k == "threads_per_block") *value = P->threads;

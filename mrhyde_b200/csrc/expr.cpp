@@ -426,7 +426,7 @@ std::string FunctionSet::codegen(const std::string& name) const {
   return gen(nodes, root);
 }
 
-std::string FunctionSet::codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx) const {
+std::string FunctionSet::codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx, int cache_axes, int* cache_n) const {
   auto it = funcs_.find(name);
   if (it == funcs_.end()) throw ExprError(MRHYDE_B200_ERR_INVALID, "function not registered: " + name);
   std::vector<Node> nodes;
@@ -443,7 +443,7 @@ std::string FunctionSet::codegen_tensor(const std::string& name, const std::stri
     return m;
   };
   std::string decls;
-  int ntemp = 0;
+  int ntemp = 0, ncache = 0;
   static const char* axis_arr[3] = {"xs", "ys", "zs"};
   static const char* axis_var[3] = {"x", "y", "z"};
   static const char* axis_tok[3] = {"@x", "@y", "@z"};
@@ -460,8 +460,16 @@ std::string FunctionSet::codegen_tensor(const std::string& name, const std::stri
       if (m == (1 << a)) {  // depends on one coordinate only: evaluate once per distinct coordinate value
         const std::string h = "h" + std::to_string(ntemp++);
         decls += "  double " + h + "[" + std::to_string(std::max(1, nqa[a])) + "];\n";
-        decls += "  _Pragma(\"unroll\") for (int i = 0; i < " + std::to_string(nqa[a]) + "; ++i) { const double " + axis_var[a] + " = " + axis_arr[a] + "[i]; " + h +
-                 "[i] = " + gen(nodes, idx) + "; }\n";
+        const std::string loop = "_Pragma(\"unroll\") for (int i = 0; i < " + std::to_string(nqa[a]) + "; ++i) ";
+        const std::string eval = "const double " + std::string(axis_var[a]) + " = " + axis_arr[a] + "[i]; " + h + "[i] = " + gen(nodes, idx) + ";";
+        if ((cache_axes >> a) & 1) {
+          const std::string off = std::to_string(ncache);
+          ncache += nqa[a];
+          decls += "  if ((reuse >> " + std::to_string(a) + ") & 1) { " + loop + h + "[i] = cache[" + off + " + i]; }\n";
+          decls += "  else { " + loop + "{ " + eval + " cache[" + off + " + i] = " + h + "[i]; } }\n";
+        } else {
+          decls += "  " + loop + "{ " + eval + " }\n";
+        }
         return h + "[" + axis_tok[a] + "]";
       }
     if (m == 8) {
@@ -472,7 +480,9 @@ std::string FunctionSet::codegen_tensor(const std::string& name, const std::stri
     return gen_chain(n, gen_t);
   };
   const std::string body = gen_t(root);
-  std::string o = "__device__ __forceinline__ void " + fname + "(const double* xs, const double* ys, const double* zs, double t, double* out) {\n";
+  if (cache_n) *cache_n = ncache;
+  std::string o = "__device__ __forceinline__ void " + fname + "(const double* xs, const double* ys, const double* zs, double t, double* out" +
+                  (ncache > 0 ? ", double* cache, const int reuse" : "") + ") {\n";
   o += decls;
   for (int q = 0; q < nq; ++q) {
     std::string e = body;

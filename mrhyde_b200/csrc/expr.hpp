@@ -60,7 +60,9 @@ class FunctionSet {
   // the function at the nq points (xs[qidx[q][0]], ys[qidx[q][1]], zs[qidx[q][2]]) of a tensor-product point set with
   // nqa[a] distinct coordinates per axis: sub-trees that depend on one coordinate only are evaluated once per distinct
   // value (they are loop invariants of the reference's point loop); every value equals the pointwise evaluation bit for bit.
-  std::string codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx) const;
+  // cache_axes: bit a set = one-coordinate sub-expressions of axis a are kept in a caller-owned array and reused when the caller says the
+  // coordinate values did not change (extra parameters `double* cache, int reuse`); *cache_n receives the array length
+  std::string codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx, int cache_axes = 0, int* cache_n = nullptr) const;
   // human-readable flattened program (tests)
   static std::string disassemble(const ExprProgram& p);
   // reference-style host evaluation of a program (used for constant folding checks in tests)

@@ -613,6 +613,31 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       std::memcpy(&out.step_lids[(size_t)k * nd], &m.lids[(size_t)e * nd], sizeof(int32_t) * (size_t)nd);
       out.step_eclass[(size_t)k] = m.eclass.empty() ? 0 : m.eclass[(size_t)e];
     }
+    // step-invariant axes per chain (extruded columns: the sweep changes one coordinate only)
+    out.chain_invariant.assign((size_t)out.n_chains, 0);
+    if (nv == (1 << m.dim)) {
+      static const int nb[3] = {1, 3, 4};   // +xi, +eta, +zeta neighbours of vertex 0 (Shards order)
+      for (int32_t c = 0; c < out.n_chains; ++c) {
+        const int32_t b = out.chain_step_ptr[(size_t)c], e = out.chain_step_ptr[(size_t)c + 1];
+        uint8_t inv = (uint8_t)((1 << m.dim) - 1);
+        const StepRec& S0 = out.steps[(size_t)b];
+        for (int32_t s = b + 1; s < e && inv; ++s) {
+          const StepRec& S = out.steps[(size_t)s];
+          if (S.n_elem != S0.n_elem) { inv = 0; break; }
+          for (int32_t t = 0; t < S.n_elem && inv; ++t) {
+            const int32_t* c0 = &out.step_conn[(size_t)(S0.elem_begin + t) * nv];
+            const int32_t* c1 = &out.step_conn[(size_t)(S.elem_begin + t) * nv];
+            if (out.step_eclass[(size_t)(S0.elem_begin + t)] != out.step_eclass[(size_t)(S.elem_begin + t)]) { inv = 0; break; }   // box code fills the cache
+            for (int d = 0; d < m.dim; ++d) {
+              const std::vector<double>& X = m.vcoord[d];
+              if (std::memcmp(&X[(size_t)c0[0]], &X[(size_t)c1[0]], 8) != 0 || std::memcmp(&X[(size_t)c0[nb[d]]], &X[(size_t)c1[nb[d]]], 8) != 0) inv &= (uint8_t)~(1 << d);
+            }
+          }
+        }
+        if (e - b < 2) inv = 0;
+        out.chain_invariant[(size_t)c] = inv;
+      }
+    }
     break;
   }
 }

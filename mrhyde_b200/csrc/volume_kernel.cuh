@@ -233,7 +233,7 @@ struct ElemPre {
 // kreg: class-ring builds of the register-staged pipeline (MRH_JIT_PIPE) return the class values here instead of storing them
 template <int DIM, bool BOX>
 __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double (&r)[1 << DIM], const int cap,
-                                               double* __restrict__ st, double* __restrict__ kreg = nullptr) {
+                                               double* __restrict__ st, double* __restrict__ kreg = nullptr, double* src_cache = nullptr, const int src_reuse = 0) {
   const double (&u)[1 << DIM] = E.u;
   const double (&ut)[1 << DIM] = E.ut;
   typedef Q1Shape<DIM> S;
@@ -359,7 +359,13 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
 #pragma unroll
       for (int i = 0; i < NQ; ++i) xa[d][i] = (d < DIM && i < nqa[d]) ? X0[d < DIM ? d : 0] + J[d < DIM ? d : 0][d < DIM ? d : 0] * (jit_tab::qax[d][i] + 1.0) : 0.0;
     double f[NQ];
+#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
+    // column cache: the one-coordinate sub-expressions of the axes the chain does not move along keep their values from step to step
+    double fresh[MRH_SRC_CACHE_N];
+    mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f, src_cache ? src_cache : fresh, src_cache ? src_reuse : 0);
+#else
     mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f);
+#endif
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const double fw = f[q] * MRH_LTAB(qw)[q] * adet;
@@ -462,7 +468,8 @@ __device__ __forceinline__ void elem_prefetch2(const ThermalParams<DIM>& P, cons
 }
 
 template <int DIM>
-__device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, const int cap, double* __restrict__ st) {
+__device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, const int cap, double* __restrict__ st,
+                                                double* src_cache = nullptr, const int src_reuse = 0) {
   typedef Q1Shape<DIM> S;
   constexpr int NV = S::NV, NQ = S::NQ, NT = S::NT;
   const TimeDev& td = P.td;
@@ -478,7 +485,7 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 
   // MRH_HAS_*: cell classes present in the plan's mesh (the specialised build drops the paths it cannot take)
   if (ecls != 0 && MRH_ALL_CONST && (MRH_HAS_BOX || MRH_HAS_AFFINE)) {
-    if (MRH_HAS_BOX && (ecls == 2 || !MRH_HAS_AFFINE)) thermal_affine<DIM, true>(P, E, r, cap, st);
+    if (MRH_HAS_BOX && (ecls == 2 || !MRH_HAS_AFFINE)) thermal_affine<DIM, true>(P, E, r, cap, st, nullptr, src_cache, src_reuse);
     else if (MRH_HAS_AFFINE) thermal_affine<DIM, false>(P, E, r, cap, st);
   } else if (MRH_HAS_GENERAL) {
     // ================= general path: per-point Jacobian and coefficients =================
@@ -688,7 +695,8 @@ struct MetricLayout {
 };
 
 template <int DIM, bool BOX>
-__device__ __forceinline__ void metric_cell(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double* __restrict__ st) {
+__device__ __forceinline__ void metric_cell(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double* __restrict__ st, double* src_cache = nullptr,
+                                            const int src_reuse = 0) {
   typedef Q1Shape<DIM> S;
   typedef MetricLayout<DIM> L;
   constexpr int NV = S::NV, NQ = S::NQ, NG = S::NG;
@@ -775,7 +783,12 @@ __device__ __forceinline__ void metric_cell(const ThermalParams<DIM>& P, const E
 #pragma unroll
         for (int i = 0; i < NQ; ++i) xa[d][i] = (d < DIM && i < nqa[d]) ? X0[d < DIM ? d : 0] + J[d < DIM ? d : 0][d < DIM ? d : 0] * (jit_tab::qax[d][i] + 1.0) : 0.0;
       double f[NQ];
+#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
+      double fresh[MRH_SRC_CACHE_N];
+      mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f, src_cache ? src_cache : fresh, src_cache ? src_reuse : 0);
+#else
       mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f);
+#endif
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const double fw = f[q] * MRH_LTAB(qw)[q] * adet;
@@ -804,8 +817,9 @@ __device__ __forceinline__ void metric_cell(const ThermalParams<DIM>& P, const E
 }
 
 template <int DIM>
-__device__ __forceinline__ void thermal_element_metric(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double* __restrict__ st) {
-  if (MRH_HAS_BOX && (E.ecls == 2 || !MRH_HAS_AFFINE)) metric_cell<DIM, true>(P, E, st);
+__device__ __forceinline__ void thermal_element_metric(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double* __restrict__ st, double* src_cache = nullptr,
+                                                       const int src_reuse = 0) {
+  if (MRH_HAS_BOX && (E.ecls == 2 || !MRH_HAS_AFFINE)) metric_cell<DIM, true>(P, E, st, src_cache, src_reuse);
   else metric_cell<DIM, false>(P, E, st);
 }
 
@@ -1130,6 +1144,12 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   if (s0 + 1 < s1) sr_next = __ldg(reinterpret_cast<const int4*>(C.steps + s0 + 1));
   ElemPre<DIM> E;
   if (tid < sr.y) { elem_stage1<DIM>(P, sr.x + tid, E); elem_stage2<DIM>(P, E); }
+#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
+  double src_cache[MRH_SRC_CACHE_N];
+#pragma unroll
+  for (int i = 0; i < MRH_SRC_CACHE_N; ++i) src_cache[i] = 0.0;
+  const int chain_inv = C.chain_invariant ? (int)C.chain_invariant[chain] : 0;
+#endif
   for (int s = s0; s < s1; ++s) {
     const int n_elem = sr.y, batch_begin = sr.z, n_batches = sr.w;
     const int parity = (s - s0) & 1;
@@ -1150,9 +1170,17 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
 #if defined(MRH_DEBUG_SKIP) && (MRH_DEBUG_SKIP & 2)
     if (tid < n_elem) slot[tid] = E.u[0] + E.xv[0][0];   // timing experiment: no element work
 #elif defined(MRH_JIT_METRIC)
+#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
+    if (tid < n_elem) thermal_element_metric<DIM>(P, E, slot + tid, src_cache, s > s0 ? chain_inv : 0);
+#else
     if (tid < n_elem) thermal_element_metric<DIM>(P, E, slot + tid);
+#endif
+#else
+#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
+    if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid, src_cache, s > s0 ? chain_inv : 0);
 #else
     if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);
+#endif
 #endif
 #ifndef MRH_EARLY_STAGE1
     if (more) elem_stage1<DIM>(P, sr_next.x + tid, E);

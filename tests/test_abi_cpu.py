@@ -372,3 +372,16 @@ def test_ghost_row_chains_come_first(product_lib):
         late = plan.debug_chain_rows(n_early, n_chains, prob.n_rows)
         assert early[ghosts].all() and not late[ghosts].any()
         assert not (early & late).any() and (early | late).all()
+
+
+def test_column_cache_flags(product_lib):
+    """Chains of an extruded brick keep their x / y intervals from step to step (bitwise): the plan marks them and the generated source
+    function caches the one-coordinate sub-expressions of those axes; a perturbed mesh has no such chain."""
+    from mrhyde_b200.problems import ThermalBrick
+    brick = ThermalBrick(3, [12, 10, 9], device=-1, options={"column elements": 16, "min segment levels": 2})
+    assert brick.plan.stat("column_cache_axes") == 3 and brick.plan.stat("n_invariant_chains") > 0
+    assert ThermalBrick(3, [12, 10, 9], device=-1, options={"column elements": 16, "min segment levels": 2, "column cache": False}).plan.stat("column_cache_axes") == 0
+    bent = ThermalBrick(3, [12, 10, 9], device=-1, perturb=0.1, options={"column elements": 16, "min segment levels": 2})
+    assert bent.plan.stat("column_cache_axes") == 0 and bent.plan.stat("n_invariant_chains") == 0
+    x_sweep = ThermalBrick(3, [12, 10, 9], device=-1, options={"column elements": 16, "min segment levels": 2, "sweep axis": 0})
+    assert x_sweep.plan.stat("column_cache_axes") == 6

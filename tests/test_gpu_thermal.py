@@ -240,8 +240,8 @@ def test_metric_ring_variants(oracle_lib, product_lib, kernel_build, mesh):
 
 
 @pytest.mark.parametrize("options", [{"flush": "flat"}, {"stage1": "early"}, {"pull group": 28}, {"flush": "flat", "ring": "metric"},
-                                     {"stage1": "early", "prefetch": "lean", "prefetch records": True}, {"stage1": "late", "prefetch": True, "prefetch records": True}],
-                         ids=["flush-flat", "stage1-early", "group-28", "metric-flat", "early-lean-records", "late-records"])
+                                     {"stage1": "early", "prefetch": "lean", "prefetch records": True}, {"stage1": "late", "prefetch": True, "prefetch records": True}, {"column cache": False}, {"column cache": True, "sweep axis": 0}],
+                         ids=["flush-flat", "stage1-early", "group-28", "metric-flat", "early-lean-records", "late-records", "no-column-cache", "x-sweep-cache"])
 def test_measured_build_alternatives_match_oracle(oracle_lib, product_lib, kernel_build, options):
     """Alternatives of the specialised build that were measured on the B200 and kept as options stay correct."""
     if kernel_build == "false":
