@@ -187,13 +187,20 @@ bool opt_bool(const mrhyde_b200_plan* P, const std::string& key, bool def) {
 }
 // Axes whose one-coordinate sub-expressions stay the same along most chains of the plan (an extruded column changes the sweep coordinate only):
 // the generated source function keeps their values per thread ("column cache", default on).
+static bool all_boxes(const mrhyde_b200_plan* P) {   // every cell of the plan is an axis-aligned box (class 2)
+  for (uint8_t c : P->cp.step_eclass) if (c != 2) return false;
+  return !P->cp.step_eclass.empty();
+}
 int column_cache_axes(const mrhyde_b200_plan* P) {
-  if (!opt_bool(P, "column cache", true) || P->cp.chain_invariant.empty()) return 0;
+  const std::string mode = opt(P, "column cache", "true");   // true | false | registers (no CTA-shared values)
+  if ((mode != "registers" && !opt_bool(P, "column cache", true)) || P->cp.chain_invariant.empty()) return 0;
   int axes = 0;
   for (int d = 0; d < P->dim; ++d) {
-    size_t n = 0;
-    for (uint8_t f : P->cp.chain_invariant) n += (f >> d) & 1;
+    size_t n = 0, u = 0;
+    for (uint8_t f : P->cp.chain_invariant) { n += (f >> d) & 1; u += (f >> (4 + d)) & 1; }
     if (2 * n > P->cp.chain_invariant.size()) axes |= 1 << d;
+    // bits 4-6: not step-invariant, but the same for all elements of a step on most chains; only plans made of axis-aligned boxes
+    else if (mode != "registers" && 2 * u > P->cp.chain_invariant.size() && all_boxes(P)) axes |= 16 << d;
   }
   return axes;
 }
@@ -389,8 +396,16 @@ __device__ __forceinline__ double mrh_cos(double x) { return mrh_sincos(x, 1); }
       qidx[q * 3 + d] = f;
     }
   }
-  int cache_n = 0;
-  o += fs.codegen_tensor("thermal source", "mrh_fn_source_box", S::NQ, nqa, qidx, cache_axes, &cache_n);
+  int cache_n = 0, shared_n = 0;
+  const int shared_axes = (cache_axes >> 4) & 7;   // packed by column_cache_axes: bits 0-2 per-thread cache, bits 4-6 CTA-shared values
+  cache_axes &= 7;
+  {
+    std::string gen = fs.codegen_tensor("thermal source", "mrh_fn_source_box", S::NQ, nqa, qidx, cache_axes, &cache_n, shared_axes, &shared_n);
+    if (shared_n > 8) gen = fs.codegen_tensor("thermal source", "mrh_fn_source_box", S::NQ, nqa, qidx, cache_axes, &cache_n, 0, &shared_n);   // 64 bytes are reserved
+    o += gen;
+  }
+  o += "#define MRH_SRC_SHARED_N " + std::to_string(shared_n) + "   /* sub-expression values all elements of a step share (shared memory, axes mask " + std::to_string(shared_n > 0 ? shared_axes : 0) + ") */\n";
+  o += "#define MRH_SRC_SHARED_AXES " + std::to_string(shared_n > 0 ? shared_axes : 0) + "\n";
   o += "#define MRH_SRC_CACHE_N " + std::to_string(cache_n) + "   /* one-coordinate sub-expression values of the source a thread keeps along its chain (axes mask " + std::to_string(cache_axes) + ") */\n";
   o += "#define MRH_NQA0 " + std::to_string(nqa[0]) + "\n#define MRH_NQA1 " + std::to_string(nqa[1]) + "\n#define MRH_NQA2 " + std::to_string(nqa[2]) + "\n";
   o += "namespace jit_tab {\n";
@@ -1726,7 +1741,8 @@ int mrhyde_b200_plan_finalize(mrhyde_b200_plan* P) {
   // per-warp transpose buffer; the specialised builds park whole rows there (generated pull code, row_buffer_pitch)
   const int max_patterns = std::max(0, std::stoi(opt(P, "pull patterns", "3")));
   const size_t warp_doubles = std::max<size_t>(PULL_WARP_DOUBLES, jit_possible ? 32 + 32 * (size_t)row_buffer_pitch(P->cp, max_patterns, flush_mode) : 0);
-  P->smem = (size_t)(2 * P->cp.slot_bytes()) + 8 /* the row buffers start 16-byte aligned */ + (size_t)(P->threads / 32) * warp_doubles * sizeof(double);
+  P->smem = (size_t)(2 * P->cp.slot_bytes()) + 8 /* the row buffers start 16-byte aligned */ + (size_t)(P->threads / 32) * warp_doubles * sizeof(double)
+            + 64 /* CTA-shared sub-expression values of the source (up to 8 doubles, behind the row buffers) */;
 
   P->stage_len = STAGE;
   P->kmap = kmap; P->rmap = rmap;
@@ -2025,7 +2041,8 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "metric_ring") *value = P->metric_ng;
   else if (k == "overlapped_assembles") *value = P->overlapped_assembles;
   else if (k == "n_early_chains") *value = P->cp.n_early_chains;
-  else if (k == "column_cache_axes") *value = column_cache_axes(P);   // axes whose one-coordinate source sub-expressions a thread keeps along its chain
+  else if (k == "column_cache_axes") *value = column_cache_axes(P) & 7;
+  else if (k == "step_shared_axes") *value = (column_cache_axes(P) >> 4) & 7;   // axes whose sub-expressions one warp evaluates for the whole CTA   // axes whose one-coordinate source sub-expressions a thread keeps along its chain
   else if (k == "n_invariant_chains") { int64_t n = 0; for (uint8_t f : P->cp.chain_invariant) n += f != 0; *value = n; }
   else if (k == "class_ring") *value = P->class_nc;
   else if (k == "stage_len") *value = P->stage_len;

@@ -426,7 +426,8 @@ std::string FunctionSet::codegen(const std::string& name) const {
   return gen(nodes, root);
 }
 
-std::string FunctionSet::codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx, int cache_axes, int* cache_n) const {
+std::string FunctionSet::codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx, int cache_axes, int* cache_n, int shared_axes,
+                                        int* shared_n) const {
   auto it = funcs_.find(name);
   if (it == funcs_.end()) throw ExprError(MRHYDE_B200_ERR_INVALID, "function not registered: " + name);
   std::vector<Node> nodes;
@@ -443,7 +444,8 @@ std::string FunctionSet::codegen_tensor(const std::string& name, const std::stri
     return m;
   };
   std::string decls;
-  int ntemp = 0, ncache = 0;
+  int ntemp = 0, ncache = 0, nshared = 0;
+  std::string shared_body;   // body of <fname>_shared
   static const char* axis_arr[3] = {"xs", "ys", "zs"};
   static const char* axis_var[3] = {"x", "y", "z"};
   static const char* axis_tok[3] = {"@x", "@y", "@z"};
@@ -467,6 +469,12 @@ std::string FunctionSet::codegen_tensor(const std::string& name, const std::stri
           ncache += nqa[a];
           decls += "  if ((reuse >> " + std::to_string(a) + ") & 1) { " + loop + h + "[i] = cache[" + off + " + i]; }\n";
           decls += "  else { " + loop + "{ " + eval + " cache[" + off + " + i] = " + h + "[i]; } }\n";
+        } else if ((shared_axes >> a) & 1) {
+          const std::string off = std::to_string(nshared);
+          nshared += nqa[a];
+          decls += "  if ((reuse >> " + std::to_string(4 + a) + ") & 1) { " + loop + h + "[i] = shv[" + off + " + i]; }\n";
+          decls += "  else { " + loop + "{ " + eval + " } }\n";
+          shared_body += "  { double " + h + "[" + std::to_string(std::max(1, nqa[a])) + "]; " + loop + "{ " + eval + " vals[" + off + " + i] = " + h + "[i]; } }\n";
         } else {
           decls += "  " + loop + "{ " + eval + " }\n";
         }
@@ -481,8 +489,11 @@ std::string FunctionSet::codegen_tensor(const std::string& name, const std::stri
   };
   const std::string body = gen_t(root);
   if (cache_n) *cache_n = ncache;
-  std::string o = "__device__ __forceinline__ void " + fname + "(const double* xs, const double* ys, const double* zs, double t, double* out" +
-                  (ncache > 0 ? ", double* cache, const int reuse" : "") + ") {\n";
+  if (shared_n) *shared_n = nshared;
+  std::string o;
+  if (nshared > 0) o += "__device__ __forceinline__ void " + fname + "_shared(const double* xs, const double* ys, const double* zs, double t, double* vals) {\n" + shared_body + "}\n";
+  o += "__device__ __forceinline__ void " + fname + "(const double* xs, const double* ys, const double* zs, double t, double* out" +
+       (ncache + nshared > 0 ? ", double* cache, const int reuse" : "") + (nshared > 0 ? ", const double* shv" : "") + ") {\n";
   o += decls;
   for (int q = 0; q < nq; ++q) {
     std::string e = body;

@@ -62,7 +62,10 @@ class FunctionSet {
   // value (they are loop invariants of the reference's point loop); every value equals the pointwise evaluation bit for bit.
   // cache_axes: bit a set = one-coordinate sub-expressions of axis a are kept in a caller-owned array and reused when the caller says the
   // coordinate values did not change (extra parameters `double* cache, int reuse`); *cache_n receives the array length
-  std::string codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx, int cache_axes = 0, int* cache_n = nullptr) const;
+  // shared_axes: sub-expressions of these axes may instead be read from a caller-supplied array (`const double* shv`, bit 4 + a of `reuse`) that
+  // the companion function <fname>_shared(xs, ys, zs, t, vals) fills; *shared_n receives its length
+  std::string codegen_tensor(const std::string& name, const std::string& fname, int nq, const int nqa[3], const int* qidx, int cache_axes = 0, int* cache_n = nullptr,
+                             int shared_axes = 0, int* shared_n = nullptr) const;
   // human-readable flattened program (tests)
   static std::string disassemble(const ExprProgram& p);
   // reference-style host evaluation of a program (used for constant folding checks in tests)

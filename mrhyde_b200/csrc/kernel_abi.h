@@ -77,6 +77,7 @@ struct ChainDev {
   int32_t chain_offset;            // first chain of this launch (a multi-rank assemble launches the ghost-row chains first)
   const uint8_t* chain_invariant;  // [n_chains] bit d: along the whole chain, thread t's element keeps the axis-d coordinates of its box
                                    // (vertex 0 and the +axis neighbour, bitwise): one-coordinate sub-expressions of axis d are step-invariant
+                                   // bit 4 + d: all elements of a step share their axis-d interval: such sub-expressions are the same for the whole CTA
 };
 
 struct GraphDev {

@@ -635,7 +635,20 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
           }
         }
         if (e - b < 2) inv = 0;
-        out.chain_invariant[(size_t)c] = inv;
+        // bit 4 + d: in every step of the chain all elements span the same axis-d interval (a level of an extruded mesh)
+        uint8_t uni = (uint8_t)((1 << m.dim) - 1);
+        for (int32_t s = b; s < e && uni; ++s) {
+          const StepRec& S = out.steps[(size_t)s];
+          const int32_t* c0 = &out.step_conn[(size_t)S.elem_begin * nv];
+          for (int32_t t = 1; t < S.n_elem && uni; ++t) {
+            const int32_t* c1 = &out.step_conn[(size_t)(S.elem_begin + t) * nv];
+            for (int d = 0; d < m.dim; ++d) {
+              const std::vector<double>& X = m.vcoord[d];
+              if (std::memcmp(&X[(size_t)c0[0]], &X[(size_t)c1[0]], 8) != 0 || std::memcmp(&X[(size_t)c0[nb[d]]], &X[(size_t)c1[nb[d]]], 8) != 0) uni &= (uint8_t)~(1 << d);
+            }
+          }
+        }
+        out.chain_invariant[(size_t)c] = (uint8_t)(inv | (uni << 4));
       }
     }
     break;

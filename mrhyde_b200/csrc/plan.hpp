@@ -58,6 +58,7 @@ struct ChainPlan {
   std::vector<uint32_t> mdesc[2];        // metric-ring source words, parallel to desc (kernel_abi.h); empty when ndof > 8
   std::vector<uint8_t> chain_invariant;  // [n_chains] bit d: every step of the chain has the same element count and element t of every step spans the
                                          // same axis-d interval (bitwise equal coordinates of vertex 0 and its +d neighbour) as element t of the first step
+                                         // bit 4 + d: within every step of the chain all elements span one and the same axis-d interval
   std::vector<int32_t> orphan_rows;      // rows no element touches
   std::vector<int32_t> ghost_patterns;   // desc_begin of the patterns of batches that hold ghost rows (multi-rank plans): they always get
                                          // generated pull code, so that the in-kernel halo push covers every ghost row

@@ -230,10 +230,36 @@ struct ElemPre {
   double xv[DIM + 1][DIM];        // vertex 0 and its +xi, +eta, +zeta neighbours (Shards vertices 1, 3, 4)
 };
 
+#if defined(MRH_JIT)
+#ifndef MRH_SRC_CACHE_N
+#define MRH_SRC_CACHE_N 0
+#endif
+#ifndef MRH_SRC_SHARED_N
+#define MRH_SRC_SHARED_N 0
+#endif
+#define MRH_SRC_REUSE (MRH_SRC_CACHE_N + MRH_SRC_SHARED_N > 0)
+// Distinct quadrature-point coordinates per axis of an axis-aligned box (tensor-product points): the one place that computes them, so that
+// the thread that fills the CTA-shared sub-expression values sees bitwise the coordinates every other thread would use.
+template <int DIM>
+__device__ __forceinline__ void box_axis_points(const ElemPre<DIM>& E, double (&xa)[3][1 << DIM]) {
+  constexpr int NQ = 1 << DIM;
+  constexpr int nqa[3] = {MRH_NQA0, MRH_NQA1, MRH_NQA2};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int dd = d < DIM ? d : 0;
+    const double x0 = E.xv[0][dd];
+    const double h = 0.5 * (E.xv[dd + 1][dd] - x0);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) xa[d][i] = (d < DIM && i < nqa[d]) ? x0 + h * (jit_tab::qax[d][i] + 1.0) : 0.0;
+  }
+}
+#endif
+
 // kreg: class-ring builds of the register-staged pipeline (MRH_JIT_PIPE) return the class values here instead of storing them
 template <int DIM, bool BOX>
 __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, double (&r)[1 << DIM], const int cap,
-                                               double* __restrict__ st, double* __restrict__ kreg = nullptr, double* src_cache = nullptr, const int src_reuse = 0) {
+                                               double* __restrict__ st, double* __restrict__ kreg = nullptr, double* src_cache = nullptr, const int src_reuse = 0,
+                                               const double* src_shared = nullptr) {
   const double (&u)[1 << DIM] = E.u;
   const double (&ut)[1 << DIM] = E.ut;
   typedef Q1Shape<DIM> S;
@@ -352,17 +378,18 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
   else if constexpr (BOX) {
     // tensor-product points of an axis-aligned box: coordinates take MRH_NQAd distinct values per axis, and the generated
     // mrh_fn_source_box evaluates every one-coordinate sub-expression once per distinct value
-    constexpr int nqa[3] = {MRH_NQA0, MRH_NQA1, MRH_NQA2};
     double xa[3][NQ];
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) xa[d][i] = (d < DIM && i < nqa[d]) ? X0[d < DIM ? d : 0] + J[d < DIM ? d : 0][d < DIM ? d : 0] * (jit_tab::qax[d][i] + 1.0) : 0.0;
+    box_axis_points<DIM>(E, xa);
     double f[NQ];
-#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
-    // column cache: the one-coordinate sub-expressions of the axes the chain does not move along keep their values from step to step
-    double fresh[MRH_SRC_CACHE_N];
+#if MRH_SRC_REUSE
+    // column cache: the one-coordinate sub-expressions of the axes the chain does not move along keep their values from step to step;
+    // those of an axis along which all elements of a step agree come from shared memory (one warp evaluated them during the previous pull)
+    double fresh[MRH_SRC_CACHE_N > 0 ? MRH_SRC_CACHE_N : 1];
+#if MRH_SRC_SHARED_N > 0
+    mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f, src_cache ? src_cache : fresh, src_cache ? src_reuse : 0, src_shared);
+#else
     mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f, src_cache ? src_cache : fresh, src_cache ? src_reuse : 0);
+#endif
 #else
     mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f);
 #endif
@@ -469,7 +496,7 @@ __device__ __forceinline__ void elem_prefetch2(const ThermalParams<DIM>& P, cons
 
 template <int DIM>
 __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, const ElemPre<DIM>& E, const int cap, double* __restrict__ st,
-                                                double* src_cache = nullptr, const int src_reuse = 0) {
+                                                double* src_cache = nullptr, const int src_reuse = 0, const double* src_shared = nullptr) {
   typedef Q1Shape<DIM> S;
   constexpr int NV = S::NV, NQ = S::NQ, NT = S::NT;
   const TimeDev& td = P.td;
@@ -485,7 +512,7 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 
   // MRH_HAS_*: cell classes present in the plan's mesh (the specialised build drops the paths it cannot take)
   if (ecls != 0 && MRH_ALL_CONST && (MRH_HAS_BOX || MRH_HAS_AFFINE)) {
-    if (MRH_HAS_BOX && (ecls == 2 || !MRH_HAS_AFFINE)) thermal_affine<DIM, true>(P, E, r, cap, st, nullptr, src_cache, src_reuse);
+    if (MRH_HAS_BOX && (ecls == 2 || !MRH_HAS_AFFINE)) thermal_affine<DIM, true>(P, E, r, cap, st, nullptr, src_cache, src_reuse, src_shared);
     else if (MRH_HAS_AFFINE) thermal_affine<DIM, false>(P, E, r, cap, st);
   } else if (MRH_HAS_GENERAL) {
     // ================= general path: per-point Jacobian and coefficients =================
@@ -776,16 +803,16 @@ __device__ __forceinline__ void metric_cell(const ThermalParams<DIM>& P, const E
 #pragma unroll
     for (int i = 0; i < NV; ++i) fl[i] = 0.0;
     if constexpr (BOX) {
-      constexpr int nqa[3] = {MRH_NQA0, MRH_NQA1, MRH_NQA2};
       double xa[3][NQ];
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) xa[d][i] = (d < DIM && i < nqa[d]) ? X0[d < DIM ? d : 0] + J[d < DIM ? d : 0][d < DIM ? d : 0] * (jit_tab::qax[d][i] + 1.0) : 0.0;
+      box_axis_points<DIM>(E, xa);
       double f[NQ];
-#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
-      double fresh[MRH_SRC_CACHE_N];
+#if MRH_SRC_REUSE
+      double fresh[MRH_SRC_CACHE_N > 0 ? MRH_SRC_CACHE_N : 1];
+#if MRH_SRC_SHARED_N > 0
+      mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f, src_cache ? src_cache : fresh, src_cache ? (src_reuse & 7) : 0, nullptr);   // no CTA-shared values in the metric build
+#else
       mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f, src_cache ? src_cache : fresh, src_cache ? src_reuse : 0);
+#endif
 #else
       mrh_fn_source_box(xa[0], xa[1], xa[2], td.time, f);
 #endif
@@ -1144,11 +1171,19 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   if (s0 + 1 < s1) sr_next = __ldg(reinterpret_cast<const int4*>(C.steps + s0 + 1));
   ElemPre<DIM> E;
   if (tid < sr.y) { elem_stage1<DIM>(P, sr.x + tid, E); elem_stage2<DIM>(P, E); }
-#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
-  double src_cache[MRH_SRC_CACHE_N];
+#if MRH_SRC_REUSE
+  double src_cache[MRH_SRC_CACHE_N > 0 ? MRH_SRC_CACHE_N : 1];
 #pragma unroll
-  for (int i = 0; i < MRH_SRC_CACHE_N; ++i) src_cache[i] = 0.0;
-  const int chain_inv = C.chain_invariant ? (int)C.chain_invariant[chain] : 0;
+  for (int i = 0; i < (MRH_SRC_CACHE_N > 0 ? MRH_SRC_CACHE_N : 1); ++i) src_cache[i] = 0.0;
+  const int chain_flags = C.chain_invariant ? (int)C.chain_invariant[chain] : 0;
+  const int chain_inv = chain_flags & 7;
+#if MRH_SRC_SHARED_N > 0
+  // sub-expression values every element of a step shares: the last warp evaluates those of step s + 1 once it is through with the pull of
+  // step s (interior steps leave it without a batch) and the barrier that ends the step publishes them
+  const double* src_shared = wbuf - warp * PULL_WARP_DOUBLES + (MRH_THREADS / 32) * PULL_WARP_DOUBLES;
+  const bool chain_shares = ((chain_flags >> 4) & MRH_SRC_SHARED_AXES) == MRH_SRC_SHARED_AXES;
+  bool shared_ready = false;
+#endif
 #endif
   for (int s = s0; s < s1; ++s) {
     const int n_elem = sr.y, batch_begin = sr.z, n_batches = sr.w;
@@ -1170,14 +1205,18 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
 #if defined(MRH_DEBUG_SKIP) && (MRH_DEBUG_SKIP & 2)
     if (tid < n_elem) slot[tid] = E.u[0] + E.xv[0][0];   // timing experiment: no element work
 #elif defined(MRH_JIT_METRIC)
-#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
+#if MRH_SRC_REUSE
     if (tid < n_elem) thermal_element_metric<DIM>(P, E, slot + tid, src_cache, s > s0 ? chain_inv : 0);
 #else
     if (tid < n_elem) thermal_element_metric<DIM>(P, E, slot + tid);
 #endif
 #else
-#if defined(MRH_SRC_CACHE_N) && MRH_SRC_CACHE_N > 0
+#if MRH_SRC_REUSE
+#if MRH_SRC_SHARED_N > 0
+    if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid, src_cache, (s > s0 ? chain_inv : 0) | (shared_ready ? (MRH_SRC_SHARED_AXES << 4) : 0), src_shared);
+#else
     if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid, src_cache, s > s0 ? chain_inv : 0);
+#endif
 #else
     if (tid < n_elem) thermal_element<DIM>(P, E, cap, slot + tid);
 #endif
@@ -1222,6 +1261,21 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
     }
 #endif
     if (more) elem_stage2<DIM>(P, E);
+#endif
+#if defined(MRH_SRC_SHARED_N) && MRH_SRC_SHARED_N > 0 && !defined(MRH_JIT_METRIC)
+    {
+      // the last warp's first element of step s + 1 stands for all of them (the plan checked the coordinates bitwise)
+      const bool shared_next = chain_shares && (s + 1 < s1) && ((MRH_THREADS / 32 - 1) * 32 < sr_next.y);
+      if (shared_next && tid == (MRH_THREADS / 32 - 1) * 32) {
+        double xa[3][1 << DIM], vals[MRH_SRC_SHARED_N];
+        box_axis_points<DIM>(E, xa);
+        mrh_fn_source_box_shared(xa[0], xa[1], xa[2], P.td.time, vals);
+        double* dst = const_cast<double*>(src_shared);
+#pragma unroll
+        for (int i = 0; i < MRH_SRC_SHARED_N; ++i) dst[i] = vals[i];
+      }
+      shared_ready = shared_next;
+    }
 #endif
 #ifdef MRH_JIT_PREFETCH_META
     // the record streams of step s + 2 (connectivity, row and batch records: each byte is read once, so every load of them is a DRAM

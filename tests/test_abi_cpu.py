@@ -380,8 +380,10 @@ def test_column_cache_flags(product_lib):
     from mrhyde_b200.problems import ThermalBrick
     brick = ThermalBrick(3, [12, 10, 9], device=-1, options={"column elements": 16, "min segment levels": 2})
     assert brick.plan.stat("column_cache_axes") == 3 and brick.plan.stat("n_invariant_chains") > 0
+    assert brick.plan.stat("step_shared_axes") == 4   # all elements of a sweep level share their z interval: one warp evaluates sin(2 pi z) for the CTA
+    assert ThermalBrick(3, [12, 10, 9], device=-1, options={"column elements": 16, "min segment levels": 2, "column cache": "registers"}).plan.stat("step_shared_axes") == 0
     assert ThermalBrick(3, [12, 10, 9], device=-1, options={"column elements": 16, "min segment levels": 2, "column cache": False}).plan.stat("column_cache_axes") == 0
     bent = ThermalBrick(3, [12, 10, 9], device=-1, perturb=0.1, options={"column elements": 16, "min segment levels": 2})
     assert bent.plan.stat("column_cache_axes") == 0 and bent.plan.stat("n_invariant_chains") == 0
     x_sweep = ThermalBrick(3, [12, 10, 9], device=-1, options={"column elements": 16, "min segment levels": 2, "sweep axis": 0})
-    assert x_sweep.plan.stat("column_cache_axes") == 6
+    assert x_sweep.plan.stat("column_cache_axes") == 6 and x_sweep.plan.stat("step_shared_axes") == 1

@@ -240,16 +240,18 @@ def test_metric_ring_variants(oracle_lib, product_lib, kernel_build, mesh):
 
 
 @pytest.mark.parametrize("options", [{"flush": "flat"}, {"stage1": "early"}, {"pull group": 28}, {"flush": "flat", "ring": "metric"},
-                                     {"stage1": "early", "prefetch": "lean", "prefetch records": True}, {"stage1": "late", "prefetch": True, "prefetch records": True}, {"column cache": False}, {"column cache": True, "sweep axis": 0}],
-                         ids=["flush-flat", "stage1-early", "group-28", "metric-flat", "early-lean-records", "late-records", "no-column-cache", "x-sweep-cache"])
+                                     {"stage1": "early", "prefetch": "lean", "prefetch records": True}, {"stage1": "late", "prefetch": True, "prefetch records": True}, {"column cache": False}, {"column cache": True, "sweep axis": 0}, {"column cache": "registers"}, {"threads": 32}, {"threads": 64, "column elements": 40}],
+                         ids=["flush-flat", "stage1-early", "group-28", "metric-flat", "early-lean-records", "late-records", "no-column-cache", "x-sweep-cache", "column-cache-registers", "shared-values-1-warp", "shared-values-2-warps"])
 def test_measured_build_alternatives_match_oracle(oracle_lib, product_lib, kernel_build, options):
     """Alternatives of the specialised build that were measured on the B200 and kept as options stay correct."""
     if kernel_build == "false":
         pytest.skip("options of the plan-specialised build")
     cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 13, "Mesh/NY": 11, "Mesh/NZ": 9})
     op = oracle_lib.OracleProblem(cfg)
-    plan = helpers.plan_from_oracle(op, cfg, options=dict(options, **{"column elements": 6, "min segment levels": 2}))
+    plan = helpers.plan_from_oracle(op, cfg, options=dict({"column elements": 6, "min segment levels": 2}, **options))
     _check(op, plan, helpers.manufactured_state(op))
+    if "threads" in options:   # the last warp holds elements: it evaluates the z-only sub-expressions of the source for the whole CTA
+        assert plan.stat("step_shared_axes") == 4 and plan.stat("threads_per_block") == options["threads"]
 
 
 @pytest.mark.parametrize("shear", [0.0, 0.3], ids=["box", "sheared"])

@@ -1,17 +1,25 @@
 #!/bin/bash
 # The GPU job of the moment: `gpurun --gpus N --timeout T -- 'bash tools/gpu_job.sh N'`.  Overwritten between calls; results that matter are copied to profiles/.
-# Final single-GPU pass on the v17 kernel: whole GPU suite, smoke, default bench line, launch list (general-path lines, reference arm and the full ncu capture: r02_final_* and r02_v17_*).
+# CTA-shared sub-expression values: the last warp evaluates the sweep-axis sub-expressions of the next step during the pull.
 mkdir -p gpurun_out
 O=gpurun_out
-L=$O/r02_final2.log
+L=$O/r02_s19.log
 : > $L
-echo "== pytest -m gpu" >> $L
-timeout -k 5 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -8 >> $L
-echo "== smoke" >> $L
-timeout -k 5 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 >> $L
-echo "== bench (default)" >> $L
-timeout -k 5 400 python bench.py > $O/r02_final2_bench_thermal.json 2>> $O/r02_final2.err; cat $O/r02_final2_bench_thermal.json >> $L
-echo "== ncu launch list" >> $L
-timeout -k 5 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_final2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-traffic > /dev/null 2>> $O/r02_final2.err
-grep -c . $O/r02_final2_launches.csv >> $L
-tail -c 3000 $L
+b() {
+  python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: continue
+    r=d['roofline']; print('$1', 'ms', round(d['ms_per_step'],4), 'median', round(d.get('ms_per_step_median',0),4), 'kernel_ms', round(r['kernel_ms'],4), 'frac', round(r['frac'],4), 'G elem/s', round(d['value']/1e9,4))
+"
+}
+echo "== GPU tests: thermal, full size" >> $L
+timeout -k 5 600 python -m pytest tests/test_gpu_thermal.py tests/test_gpu_fullsize.py -q -x 2>&1 | tail -3 >> $L
+run() { timeout -k 5 200 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-traffic "${@:2}" 2>> $O/r02_s19.err | b "$1" >> $L; }
+run "[shared z values + column cache (default)]"
+run "[column cache in registers only (v17)]" --opt "column cache=registers"
+run "[default again]"
+echo "== bench (default, full line)" >> $L
+timeout -k 5 400 python bench.py > $O/r02_v18_bench_thermal.json 2>> $O/r02_s19.err; cat $O/r02_v18_bench_thermal.json >> $L
+cat $L
