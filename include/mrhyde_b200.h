@@ -225,6 +225,12 @@ int mrhyde_b200_halo_sum(mrhyde_b200_plan* plan, double* res, double* jac_values
  * Ghost rows [n_owned_rows, n_rows) hold this rank's partial sums only and are not part of the owned matrix. */
 int mrhyde_b200_plan_owned_extent(mrhyde_b200_plan* plan, int64_t* n_owned_rows, int64_t* nnz_owned);
 
+/* Point constraints (disc->point_dofs, discretizationInterface_dof.hpp:365-628): dofConstraints replaces the whole Jacobian row of every
+ * such dof by the identity row after the assembly, whatever the output mode; the residual entry is left as assembled
+ * (setJacobianConstraints(J, dofs, block, ...), assemblyManager_constraints.hpp:97-116, 261-266).  lids: local row ids (owned or ghost;
+ * like the reference, every rank that holds the row sets it before the export).  n = 0 clears the list.  Call after plan_finalize. */
+int mrhyde_b200_plan_set_point_dofs(mrhyde_b200_plan* plan, int64_t n, const int32_t* lids /*host [n]*/);
+
 /* ---- introspection (tests, bench) ----------------------------------------------------------- */
 /* keys: "n_chains" "n_columns" "n_segments" "n_levels" "n_steps" "n_patterns" "n_pattern_slots" "n_batches" "max_batches_per_step" "ring_capacity"
  *       "max_rows_per_step" "kernel_launches_per_assemble" "halo_launches_per_sum" "smem_bytes" "threads_per_block"

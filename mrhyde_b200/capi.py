@@ -27,7 +27,7 @@ SYMBOLS = [
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
     "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_class_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_plan_debug_chain_rows", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
-    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_debug_set_emulator", "mrhyde_b200_plan_warmup", "mrhyde_b200_assemble_jacres_adjoint", "mrhyde_b200_plan_owned_extent", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
+    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_debug_set_emulator", "mrhyde_b200_plan_warmup", "mrhyde_b200_assemble_jacres_adjoint", "mrhyde_b200_plan_owned_extent", "mrhyde_b200_plan_set_point_dofs", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
     "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
 
@@ -374,6 +374,11 @@ class AssemblyPlan:
         """col_gids: global ids of the local column ids (rows first, then column-only ghosts)."""
         g = np.ascontiguousarray(col_gids, dtype=np.int64)
         self._chk(self.L.mrhyde_b200_plan_set_halo(self.h, len(g), _ptr(g)))
+
+    def set_point_dofs(self, lids):
+        """Point constraints: after every assembly the Jacobian rows of these local dofs are identity rows (the residual is left as assembled)."""
+        d = np.ascontiguousarray(lids, dtype=np.int32)
+        self._chk(self.L.mrhyde_b200_plan_set_point_dofs(self.h, len(d), _ptr(d)))
 
     def owned_extent(self):
         """(owned rows, non-zeros of the owned rows): the owned matrix after halo_sum is the prefix of the caller's CSR arrays."""

@@ -111,6 +111,9 @@ struct mrhyde_b200_plan {
   DevBuf<double> d_vx, d_vy, d_vz;
   DevBuf<int32_t> d_conn, d_lids, d_colind, d_chain_step_ptr, d_step_elems, d_step_conn, d_step_lids, d_orphans;
   DevBuf<int64_t> d_rowptr, d_fixed_diag;
+  DevBuf<int64_t> d_point_rows;       // point constraints: (first entry, end, diagonal entry) per constrained row
+  std::vector<int32_t> point_dofs;
+  bool point_on_ghost = false;        // a ghost row is point-constrained: its identity row must be what the halo sum sends (no in-kernel push)
   DevBuf<uint8_t> d_fixed, d_eclass, d_step_eclass, d_chain_invariant;
   DevBuf<StepRec> d_steps;
   DevBuf<BatchRec> d_batches;
@@ -904,6 +907,22 @@ __global__ void fixed_diag_kernel(const int64_t* __restrict__ diag, int n, doubl
   if (i < n && diag[i] >= 0) jac[diag[i]] = 1.0;
 }
 
+// dofConstraints, point constraints: the whole row becomes the identity row (one warp per row)
+__global__ void point_rows_kernel(const int64_t* __restrict__ rows, int n, double* __restrict__ jac) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const int64_t b = rows[3 * w], e = rows[3 * w + 1], d = rows[3 * w + 2];
+  for (int64_t p = b + lane; p < e; p += 32) jac[p] = (p == d) ? 1.0 : 0.0;
+}
+
+static int point_constraints(mrhyde_b200_plan* P, double* jac, cudaStream_t st) {
+  const int n = (int)(P->d_point_rows.n / 3);
+  if (n == 0 || !jac) return 0;
+  point_rows_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(P->d_point_rows.p, n, jac);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
 void fill_time(const mrhyde_b200_time* t, TimeDev& td, bool device_ptrs_ok) {
   std::memset(&td, 0, sizeof(td));
   td.alpha_u = 1.0;
@@ -1041,6 +1060,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
       ++launched;
       CUDA_OK(cudaGetLastError());
     }
+    if (want_jac) launched += point_constraints(P, jac, st);
     P->launches_per_assemble = launched;
     return;
   }
@@ -1054,7 +1074,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     // in-kernel halo push: the assembly kernel stores ghost rows into the owner's slab as it completes them
     PushDev push;
     std::memset(&push, 0, sizeof(push));
-    if (P->push_ok && P->use_jit && P->halo && !P->suppress_overlap && want_jac && want_res && !adjoint && P->boundary.groups.empty() && P->cp.orphan_rows.empty() &&
+    if (P->push_ok && !P->point_on_ghost && P->use_jit && P->halo && !P->suppress_overlap && want_jac && want_res && !adjoint && P->boundary.groups.empty() && P->cp.orphan_rows.empty() &&
         !opt_bool(P, "overlap halo", false)) {
       if (P->halo->push_params(res, jac, P->mesh.nowned, P->mesh.rowptr[(size_t)P->mesh.nowned], P->cp.n_early_chains, push)) ++P->pushed_assembles;
     }
@@ -1118,6 +1138,7 @@ void do_assemble(mrhyde_b200_plan* P, const double* sol, const TimeDev& td, bool
     ++launched;
     CUDA_OK(cudaGetLastError());
   }
+  if (want_jac) launched += point_constraints(P, jac, st);
   P->launches_per_assemble = launched;
 }
 
@@ -2009,6 +2030,33 @@ int mrhyde_b200_halo_sum(mrhyde_b200_plan* P, double* res, double* jac_values, v
   ABI_END
 }
 
+int mrhyde_b200_plan_set_point_dofs(mrhyde_b200_plan* P, int64_t n, const int32_t* lids) {
+  ABI_BEGIN
+  if (!P || n < 0 || (n > 0 && !lids)) fail(MRHYDE_B200_ERR_INVALID, "plan_set_point_dofs: null argument");
+  if (!P->finalized) fail(MRHYDE_B200_ERR_STATE, "plan_set_point_dofs called before mrhyde_b200_plan_finalize");
+  const MeshGraph& M = P->mesh;
+  std::vector<int64_t> rows;
+  bool ghost = false;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t r = lids[i];
+    if (r < 0 || r >= M.nrows) fail(MRHYDE_B200_ERR_INVALID, "plan_set_point_dofs: row id out of range");
+    int64_t d = -1;
+    for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) if (M.colind[(size_t)p] == r) d = p;
+    rows.push_back(M.rowptr[(size_t)r]); rows.push_back(M.rowptr[(size_t)r + 1]); rows.push_back(d);
+    if (M.nowned > 0 && r >= M.nowned) ghost = true;
+  }
+  P->point_dofs.assign(lids, lids + n);
+  P->point_on_ghost = ghost;
+  if (P->device >= 0) {
+    CUDA_OK(cudaSetDevice(P->device));
+    CUDA_OK(cudaDeviceSynchronize());   // an assembly in flight may still read the old list
+    size_t dummy = 0;
+    P->d_point_rows.upload(rows, &dummy);
+    if (rows.empty()) P->d_point_rows.n = 0;
+  }
+  ABI_END
+}
+
 int mrhyde_b200_plan_owned_extent(mrhyde_b200_plan* P, int64_t* n_owned_rows, int64_t* nnz_owned) {
   ABI_BEGIN
   if (!P || !n_owned_rows || !nnz_owned) fail(MRHYDE_B200_ERR_INVALID, "plan_owned_extent: null argument");
@@ -2210,6 +2258,9 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
     for (int64_t r = 0; r < M.nowned; ++r)
       if (M.fixed[(size_t)r])
         for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) if (M.colind[(size_t)p] == r) jac[p] = 1.0;
+  if (compute_jacobian && jac)
+    for (int32_t r : P->point_dofs)
+      for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) jac[p] = (M.colind[(size_t)p] == r) ? 1.0 : 0.0;
   ABI_END
 }
 

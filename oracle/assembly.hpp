@@ -80,6 +80,7 @@ class AssemblyManager {
   int type_AD = 0, maxdof = 0;
   bool assemble_volume_terms = true, assemble_boundary_terms = true, use_strong_DBCs = true;
   bool lump_mass = false;    // Solver: lump mass (assemblyManager_construct.hpp:36): the fused scatter sends every entry of a row to its diagonal
+  std::vector<int> point_dofs;   // disc->point_dofs (local ids): dofConstraints replaces their whole Jacobian row by the identity row
   bool useadjoint = false;   // assembleJacRes(..., useadjoint, ...): transposed local Jacobians (updateJac, assemblyManager_jacres.hpp:1459-1475)
   TimeData td;
   std::unique_ptr<EngineBase> eng_scalar, eng_ad;
@@ -359,6 +360,12 @@ struct Engine : EngineBase {
         for (int64_t p = am.graph.rowptr[d]; p < am.graph.rowptr[d + 1]; ++p)
           if (am.graph.colind[p] == d) Jvals[p] = 1.0;
       }
+    }
+    // point constraints: setJacobianConstraints(J, fixedDOFs, block, ...) sets ALL entries of the row to 0 and the diagonal to 1
+    // (assemblyManager_constraints.hpp:97-116, 261-266); the residual entry stays what the assembly made it
+    if (compute_jacobian && Jvals) {
+      for (int d : am.point_dofs)
+        for (int64_t p = am.graph.rowptr[d]; p < am.graph.rowptr[d + 1]; ++p) Jvals[p] = (am.graph.colind[p] == d) ? 1.0 : 0.0;
     }
   }
 

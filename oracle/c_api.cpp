@@ -170,6 +170,11 @@ int oracle_set_time(void* hv, int isTransient, double time, double deltat, int s
   return 0;
 }
 
+int oracle_set_point_dofs(void* hv, int n, const int* dofs) {
+  ((OracleHandle*)hv)->am->point_dofs.assign(dofs, dofs + n);
+  return 0;
+}
+
 int oracle_set_adjoint(void* hv, int useadjoint) {
   ((OracleHandle*)hv)->am->useadjoint = useadjoint != 0;
   return 0;

@@ -172,6 +172,11 @@ class OracleProblem:
         self.L.oracle_set_time(self.h, int(transient), C.c_double(time), C.c_double(dt), int(stage), len(b),
                                _p(A, C.c_double), _p(b, C.c_double), _p(c, C.c_double), len(bdf), _p(bdf, C.c_double))
 
+    def set_point_dofs(self, dofs):
+        """disc->point_dofs: dofConstraints turns their Jacobian rows into identity rows (assemblyManager_constraints.hpp:97-116, 261-266)."""
+        d = np.ascontiguousarray(dofs, dtype=np.int32)
+        self.L.oracle_set_point_dofs(self.h, len(d), d.ctypes.data_as(C.POINTER(C.c_int)))
+
     def set_adjoint(self, useadjoint):
         """assembleJacRes(..., useadjoint = true): the Jacobian is filled transposed (and thermal's weak-Dirichlet sides use sf = 1)."""
         self.L.oracle_set_adjoint(self.h, int(bool(useadjoint)))

@@ -219,3 +219,31 @@ def test_initial_projection_reproduces_reference_gold(oracle_lib, product_lib):
     for f in ("E", "B"):
         got = op.l2_error([f + "[x]", f + "[y]", f + "[z]"], u)
         assert abs(got - gold[f]) <= 0.5e-5 * gold[f], (f, got, gold[f])
+
+
+def test_point_constraints_replace_rows(oracle_lib, product_lib):
+    """disc->point_dofs: dofConstraints turns the whole Jacobian row into the identity row and leaves the residual alone
+    (assemblyManager_constraints.hpp:97-116, 261-266)."""
+    from mrhyde_b200.capi import MrhydeB200Error
+    cfg = configs.NS_2D
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options={"kernel": "general"})
+    pts = np.array([5, 17, op.num_dofs - 3], dtype=np.int32)
+    op.set_point_dofs(pts)
+    plan.set_point_dofs(pts)
+    u = helpers.manufactured_state(op)
+    res_ref, jac_ref = op.assemble_jacres(u)
+    res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+    plan.debug_emulate(u, res, jac)
+    assert helpers.rel_err_vec(res, res_ref) < TOL and helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL
+    for d in pts:
+        row = jac[op.rowptr[d]:op.rowptr[d + 1]]
+        assert row.sum() == 1.0 and np.count_nonzero(row) == 1 and row[np.where(op.colind[op.rowptr[d]:op.rowptr[d + 1]] == d)[0][0]] == 1.0
+    with pytest.raises(MrhydeB200Error):
+        plan.set_point_dofs(np.array([op.num_dofs], dtype=np.int32))
+    plan.set_point_dofs(np.zeros(0, dtype=np.int32))   # clears the list
+    op.set_point_dofs(np.zeros(0, dtype=np.int32))
+    res_ref, jac_ref = op.assemble_jacres(u)
+    res[:], jac[:] = 0.0, 0.0   # the plan accumulates
+    plan.debug_emulate(u, res, jac)
+    assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL

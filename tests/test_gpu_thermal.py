@@ -357,3 +357,22 @@ def test_overwrite_mode_without_strong_dbcs_leaves_fixed_rows_zero(oracle_lib, p
         assert np.all(jac[fixed[rows]] == 0.0) and np.all(res[fixed] == 0.0), key
         assert np.array_equal(res, outs[("sweep", "true")][0]) or helpers.rel_err_vec(res, outs[("sweep", "true")][0]) < TOL
         assert helpers.rel_err_rows(jac, outs[("sweep", "true")][1], op.rowptr) < TOL
+
+
+@pytest.mark.parametrize("kernel", ["sweep", "general"])
+def test_point_constraints(oracle_lib, product_lib, kernel):
+    """disc->point_dofs: identity Jacobian rows after the assembly, residual untouched (assemblyManager_constraints.hpp:97-116, 261-266),
+    in overwrite and in accumulate mode, both kernels."""
+    import torch
+    cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 7, "Mesh/NY": 6, "Mesh/NZ": 5})
+    op = oracle_lib.OracleProblem(cfg)
+    pts = np.array([3, 40, op.num_dofs - 1], dtype=np.int32)
+    op.set_point_dofs(pts)
+    for accumulate in (False, True):
+        plan = helpers.plan_from_oracle(op, cfg, options={"kernel": kernel, "accumulate": "true" if accumulate else "false"})
+        plan.set_point_dofs(pts)
+        _check(op, plan, helpers.manufactured_state(op))
+        assert plan.stat("kernel_launches_per_assemble") >= 2
+        plan.set_point_dofs(np.zeros(0, dtype=np.int32))
+    op.set_point_dofs(np.zeros(0, dtype=np.int32))
+    _check(op, plan, helpers.manufactured_state(op))
