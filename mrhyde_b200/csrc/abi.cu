@@ -785,10 +785,25 @@ std::string pull_codegen_metric(const ChainPlan& cp, int max_patterns, int nv, i
 // navierstokes.cpp:64-76, maxwell.cpp:63-78 (there the YAML keys permeability / permittivity / conductivity feed the
 // functions mu / epsilon / sigma).
 struct ModuleFn { const char* key; const char* def; };
-std::string canonical_physics(const std::string& name) {
+static std::string canonical_module(std::string name) {
+  while (!name.empty() && name.front() == ' ') name.erase(name.begin());
+  while (!name.empty() && name.back() == ' ') name.pop_back();
   if (name == "linear elasticity") return "linearelasticity";
   if (name == "Navier Stokes" || name == "navierstokes") return "navier stokes";
   return name;
+}
+// "modules: a, b" (the reference's comma separated list, physicsInterface) -> "a+b": the name of a two-module block kernel
+std::string canonical_physics(const std::string& name) {
+  std::string out;
+  size_t b = 0;
+  while (b <= name.size()) {
+    size_t e = name.find(',', b);
+    if (e == std::string::npos) e = name.size();
+    const std::string m = canonical_module(name.substr(b, e - b));
+    if (!m.empty()) out += (out.empty() ? "" : "+") + m;
+    b = e + 1;
+  }
+  return out;
 }
 const ModuleFn* module_functions(const std::string& phys) {
   static const ModuleFn thermal[] = {{"thermal source", "0.0"}, {"thermal diffusion", "1.0"}, {"specific heat", "1.0"}, {"density", "1.0"},
@@ -797,10 +812,20 @@ const ModuleFn* module_functions(const std::string& phys) {
   static const ModuleFn ns[] = {{"source ux", "0.0"}, {"source pr", "0.0"}, {"source uy", "0.0"}, {"source uz", "0.0"}, {"density", "1.0"}, {"viscosity", "1.0"}, {nullptr, nullptr}};
   static const ModuleFn mx[] = {{"current x", "0.0"}, {"current y", "0.0"}, {"current z", "0.0"}, {"permeability", "1.0"}, {"refractive index", "1.0"},
                                 {"permittivity", "1.0"}, {"conductivity", "0.0"}, {nullptr, nullptr}};
+  // two-module blocks: the functions of the first module, then those of the second (general_physics.cuh); "density" of thermal and of
+  // navier stokes is one and the same `Functions:` entry, as in the reference's per-block function manager
+  static const ModuleFn th_le[] = {{"thermal source", "0.0"}, {"thermal diffusion", "1.0"}, {"specific heat", "1.0"}, {"density", "1.0"},
+                                   {"advection x", "0.0"}, {"advection y", "0.0"}, {"advection z", "0.0"}, {"robin alpha", "0.0"},
+                                   {"lambda", "1.0"}, {"mu", "0.5"}, {"source dx", "0.0"}, {"source dy", "0.0"}, {"source dz", "0.0"}, {nullptr, nullptr}};
+  static const ModuleFn ns_th[] = {{"source ux", "0.0"}, {"source pr", "0.0"}, {"source uy", "0.0"}, {"source uz", "0.0"}, {"density", "1.0"}, {"viscosity", "1.0"},
+                                   {"thermal source", "0.0"}, {"thermal diffusion", "1.0"}, {"specific heat", "1.0"}, {"density", "1.0"},
+                                   {"advection x", "0.0"}, {"advection y", "0.0"}, {"advection z", "0.0"}, {"robin alpha", "0.0"}, {nullptr, nullptr}};
   if (phys == "thermal") return thermal;
   if (phys == "linearelasticity") return le;
   if (phys == "navier stokes") return ns;
   if (phys == "maxwell") return mx;
+  if (phys == "thermal+linearelasticity") return th_le;
+  if (phys == "navier stokes+thermal") return ns_th;
   return nullptr;
 }
 std::vector<std::string> module_variables(const std::string& phys, int dim) {
@@ -808,6 +833,12 @@ std::vector<std::string> module_variables(const std::string& phys, int dim) {
   if (phys == "linearelasticity") return dim == 2 ? std::vector<std::string>{"dx", "dy"} : std::vector<std::string>{"dx", "dy", "dz"};
   if (phys == "navier stokes") return dim == 2 ? std::vector<std::string>{"ux", "pr", "uy"} : std::vector<std::string>{"ux", "pr", "uy", "uz"};
   if (phys == "maxwell") return {"E", "B"};
+  const size_t plus = phys.find('+');
+  if (plus != std::string::npos) {   // two-module block: variables module by module
+    std::vector<std::string> a = module_variables(phys.substr(0, plus), dim), b = module_variables(phys.substr(plus + 1), dim);
+    a.insert(a.end(), b.begin(), b.end());
+    return a;
+  }
   return {};
 }
 
@@ -826,15 +857,7 @@ std::vector<std::string> initial_function_names(const mrhyde_b200_plan* P, int v
 FunctionSet make_function_set(const mrhyde_b200_plan* P, bool side, bool state_slots = false) {
   FunctionSet fs;
   // module defaults (thermal::defineFunctions, thermal.cpp:47-65), then user overrides
-  if (P->physics == "thermal") {
-    fs.set("thermal source", "0.0");
-    fs.set("thermal diffusion", "1.0");
-    fs.set("specific heat", "1.0");
-    fs.set("density", "1.0");
-    fs.set("advection x", "0.0"); fs.set("advection y", "0.0"); fs.set("advection z", "0.0");
-    fs.set("robin alpha", "0.0");
-  }
-  for (const ModuleFn* f = module_functions(canonical_physics(P->physics)); f && f->key; ++f) if (P->physics != "thermal") fs.set(f->key, f->def);
+  for (const ModuleFn* f = module_functions(canonical_physics(P->physics)); f && f->key; ++f) fs.set(f->key, f->def);
   // "initial <var>" (HGRAD / HVOL) or "initial <var>[x|y|z]" (HCURL / HDIV): variables the Initial conditions sublist does not
   // name start from 0.0 (physicsInterface_functions.hpp:154-226)
   for (size_t v = 0; v < P->var_names.size(); ++v)

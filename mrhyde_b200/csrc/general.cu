@@ -375,6 +375,7 @@ const char* gen_run(GeneralPlanDev* D, const GeneralPlanHost& H, const GenDevice
   auto mark_state = [&]() { P.fn_state = 0; if (!pull_mass_mode) for (int f = 0; f < GEN_MAXFN; ++f) if ((P.fn[f].pad & 1) && !P.fn[f].is_const) P.fn_state = 1; };
   mark_state();
   P.fn_op = D->fn_op.p; P.fn_c = D->fn_c.p; P.opt = H.opt;
+  if (adjoint && std::string(I.physics).find('+') != std::string::npos) return "adjoint assembly of a two-module block is not built (thermal's sf = 1 and the other module's form_param share one option slot)";
   if (adjoint && std::string(I.physics) == "thermal") P.opt.form_param = 1.0;   // thermal.cpp:197-201, 292-296: sf = 1 when wkset->isAdjoint
   for (int v = 0; v < GEN_MAXVARS; ++v) { P.bc_type[v] = 0; P.bc_fn[v] = -1; }
   P.elem_jac = (pull_mass_mode == 3) ? nullptr : ((O.jac || pull_mass_mode) ? D->elem_jac.p : nullptr);

@@ -14,6 +14,9 @@ typedef ElasticityPhys<2, 2> GenLe22;
 typedef ElasticityPhys<3, 2> GenLe32;
 typedef NavierStokesPhys<2, 1> GenNs21;
 typedef NavierStokesPhys<3, 1> GenNs31;
+typedef ThermalElasticityPhys<2, 1> GenThLe21;
+typedef ThermalElasticityPhys<3, 1> GenThLe31;
+typedef NavierStokesThermalPhys<2, 1> GenNsTh21;
 }  // namespace mrhyde_b200
 
 // X(physics name, dim, order, NQ, NQS, K, Phys, MAXT, MINB, MAXT_L, MINB_L): launch bounds (threads per CTA at most, CTAs per SM at
@@ -31,6 +34,9 @@ typedef NavierStokesPhys<3, 1> GenNs31;
   X("linearelasticity", 3, 2, 27, 9, 1, GenLe32, 576, 1, 96, 2)             \
   X("navier stokes", 2, 1, 4, 2, 1, GenNs21, 256, 3, 256, 2)                \
   X("navier stokes", 3, 1, 8, 4, 1, GenNs31, 256, 2, 128, 3)                \
+  X("thermal+linearelasticity", 2, 1, 4, 2, 1, GenThLe21, 256, 3, 256, 3)     \
+  X("thermal+linearelasticity", 3, 1, 8, 4, 1, GenThLe31, 256, 2, 256, 2)     \
+  X("navier stokes+thermal", 2, 1, 4, 2, 1, GenNsTh21, 256, 2, 256, 2)        \
   X("maxwell", 3, 1, 8, 4, 1, MaxwellPhys, 128, 3, 128, 3)
 
 namespace mrhyde_b200 {

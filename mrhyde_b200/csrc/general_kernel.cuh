@@ -98,7 +98,7 @@ MRH_HD void mrh_ldn(const double* __restrict__ p, double* __restrict__ o) {
 
 // ---- launch parameters --------------------------------------------------------------------------------------
 constexpr int GEN_MAXVARS = 4;
-constexpr int GEN_MAXFN = 16;
+constexpr int GEN_MAXFN = 20;   // two-module blocks: 14 module functions + 4 boundary data
 constexpr int GEN_MAXDOF = 96;
 enum GenBasisType : int32_t { BT_HGRAD = 0, BT_HCURL = 1, BT_HDIV = 2, BT_HVOL = 3 };
 enum GenBcType : int32_t { BC_NONE = 0, BC_DIRICHLET = 1, BC_WEAK_DIRICHLET = 2, BC_NEUMANN = 3 };

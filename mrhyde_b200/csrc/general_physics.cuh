@@ -47,24 +47,24 @@ struct HGradSystem {
 template <int DIM_, int P_>
 struct ThermalPhys : HGradSystem<DIM_, P_, 1> {
   static constexpr int NFN = 8;
-  template <class T, bool STATE = false>
+  template <class T, bool STATE = false, int FN0 = 0, int BD0 = NFN, int V0 = 0>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[1][4], const T (&Ft)[1][4], T (&Cf)[1][4]) {
-    const auto source = MRH_FN(0), diff = MRH_FN(1), cp = MRH_FN(2), rho = MRH_FN(3);
+    const auto source = MRH_FN(FN0 + 0), diff = MRH_FN(FN0 + 1), cp = MRH_FN(FN0 + 2), rho = MRH_FN(FN0 + 3);
     Cf[0][0] = (rho * cp * Ft[0][0] - source) * c.w;
     for (int d = 0; d < DIM_; ++d) Cf[0][1 + d] = diff * F[0][1 + d] * c.w;
     if (o.have_advection) {
-      T adv = MRH_FN(4) * F[0][1];
-      if (DIM_ > 1) adv = adv + MRH_FN(5) * F[0][2];
-      if (DIM_ > 2) adv = adv + MRH_FN(6) * F[0][3];
+      T adv = MRH_FN(FN0 + 4) * F[0][1];
+      if (DIM_ > 1) adv = adv + MRH_FN(FN0 + 5) * F[0][2];
+      if (DIM_ > 2) adv = adv + MRH_FN(FN0 + 6) * F[0][3];
       Cf[0][0] = Cf[0][0] + adv * c.w;
     }
   }
-  template <class T, bool STATE = false>
+  template <class T, bool STATE = false, int FN0 = 0, int BD0 = NFN, int V0 = 0>
   MRH_HD static void boundary(const QpCtx& c, const GenOpts& o, const T (&F)[1][4], const T (&)[1][4], T (&Cf)[1][4]) {
-    const auto diff = MRH_FN(1), bdata = MRH_FN(NFN + 0);
-    if (c.bc_type[0] == BC_NEUMANN) {
+    const auto diff = MRH_FN(FN0 + 1), bdata = MRH_FN(BD0 + 0);
+    if (c.bc_type[V0] == BC_NEUMANN) {
       Cf[0][0] = T(0.0) - bdata * c.w;
-    } else if (c.bc_type[0] == BC_WEAK_DIRICHLET) {
+    } else if (c.bc_type[V0] == BC_WEAK_DIRICHLET) {
       const double epen = 10.0;
       T flux = F[0][1] * c.n[0] + F[0][2] * c.n[1];
       if (DIM_ > 2) flux = flux + F[0][3] * c.n[2];
@@ -82,9 +82,9 @@ template <int DIM_, int P_>
 struct ElasticityPhys : HGradSystem<DIM_, P_, DIM_> {
   static constexpr int NFN = 5;
   static constexpr int NVAR = DIM_;
-  template <class T, bool STATE = false>
+  template <class T, bool STATE = false, int FN0 = 0, int BD0 = NFN, int V0 = 0>
   MRH_HD static void stress(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], T (&s)[3][3]) {
-    const auto lambda = MRH_FN(0), mu = MRH_FN(1);
+    const auto lambda = MRH_FN(FN0 + 0), mu = MRH_FN(FN0 + 1);
     // computeStress (linearelasticity.cpp:1158-1240)
     if (DIM_ == 2) {
       if (o.incplanestress) {
@@ -109,31 +109,31 @@ struct ElasticityPhys : HGradSystem<DIM_, P_, DIM_> {
       s[2][2] = (2.0 * mu + lambda) * F[Z][3] + lambda * (F[X][1] + F[Y][2]);
     }
   }
-  template <class T, bool STATE = false>
+  template <class T, bool STATE = false, int FN0 = 0, int BD0 = NFN, int V0 = 0>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&)[NVAR][4], T (&Cf)[NVAR][4]) {
     T s[3][3];
-    stress<T, STATE>(c, o, F, s);
+    stress<T, STATE, FN0, BD0, V0>(c, o, F, s);
     for (int d = 0; d < DIM_; ++d) {
-      Cf[d][0] = T(0.0) - MRH_FN(2 + d) * c.w;
+      Cf[d][0] = T(0.0) - MRH_FN(FN0 + 2 + d) * c.w;
       for (int e = 0; e < DIM_; ++e) Cf[d][1 + e] = s[d][e] * c.w;
     }
   }
-  template <class T, bool STATE = false>
+  template <class T, bool STATE = false, int FN0 = 0, int BD0 = NFN, int V0 = 0>
   MRH_HD static void boundary(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&)[NVAR][4], T (&Cf)[NVAR][4]) {
-    const auto lam = MRH_FN(0), mu = MRH_FN(1);
+    const auto lam = MRH_FN(FN0 + 0), mu = MRH_FN(FN0 + 1);
     bool any = false;
-    for (int d = 0; d < DIM_; ++d) any = any || c.bc_type[d] == BC_WEAK_DIRICHLET;
+    for (int d = 0; d < DIM_; ++d) any = any || c.bc_type[V0 + d] == BC_WEAK_DIRICHLET;
     T s[3][3], delta[3];
     if (any) {
-      stress<T, STATE>(c, o, F, s);
+      stress<T, STATE, FN0, BD0, V0>(c, o, F, s);
       // data of a variable that is neither Neumann nor weak Dirichlet on this side is an unset Vista in the reference
       // (linearelasticity.cpp:264-283); it reads as 0 here
-      for (int d = 0; d < DIM_; ++d) delta[d] = F[d][0] - MRH_FN(NFN + d);
+      for (int d = 0; d < DIM_; ++d) delta[d] = F[d][0] - MRH_FN(BD0 + d);
     }
     for (int d = 0; d < DIM_; ++d) {
-      if (c.bc_type[d] == BC_NEUMANN) {
-        Cf[d][0] = T(0.0) - MRH_FN(NFN + d) * c.w;
-      } else if (c.bc_type[d] == BC_WEAK_DIRICHLET) {
+      if (c.bc_type[V0 + d] == BC_NEUMANN) {
+        Cf[d][0] = T(0.0) - MRH_FN(BD0 + d) * c.w;
+      } else if (c.bc_type[V0 + d] == BC_WEAK_DIRICHLET) {
         const auto penalty = o.penalty * (lam + 2.0 * mu) * c.ih;
         T trac = s[d][0] * c.n[0] + s[d][1] * c.n[1];
         if (DIM_ > 2) trac = trac + s[d][2] * c.n[2];
@@ -177,9 +177,9 @@ struct NavierStokesPhys : HGradSystem<DIM_, P_, DIM_ + 1> {
     const T nv = (C2 * ih) * nvel;
     return mrh_rsqrt(nv * nv + (t1 * t1 + t3 * t3));
   }
-  template <class T, bool STATE = false>
+  template <class T, bool STATE = false, int FN0 = 0, int BD0 = NFN, int V0 = 0>
   MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&Ft)[NVAR][4], T (&Cf)[NVAR][4]) {
-    const auto dens = MRH_FN(4), visc = MRH_FN(5);
+    const auto dens = MRH_FN(FN0 + 4), visc = MRH_FN(FN0 + 5);
     T u[3];
     for (int d = 0; d < 3; ++d) u[d] = d < DIM_ ? F[vel(d < DIM_ ? d : 0)][0] : T(0.0);
     const T pr = F[1][0];
@@ -195,14 +195,14 @@ struct NavierStokesPhys : HGradSystem<DIM_, P_, DIM_ + 1> {
       T conv = u[0] * F[v][1] + u[1] * F[v][2];
       if (DIM_ > 2) conv = conv + u[2] * F[v][3];
       T co[4];
-      co[0] = (Ft[v][0] + conv - MRH_FN(src(d))) * wdens;
+      co[0] = (Ft[v][0] + conv - MRH_FN(FN0 + src(d))) * wdens;
       for (int e = 0; e < DIM_; ++e) {
         T Fe = visc * F[v][1 + e];
         if (e == d) Fe = Fe - pr;
         co[1 + e] = Fe * c.w;
       }
       T stabres = T(0.0);
-      if (o.useSUPG || o.usePSPG) stabres = dens * Ft[v][0] + dens * conv + F[1][1 + d] - dens * MRH_FN(src(d));
+      if (o.useSUPG || o.usePSPG) stabres = dens * Ft[v][0] + dens * conv + F[1][1 + d] - dens * MRH_FN(FN0 + src(d));
       if (o.useSUPG) for (int e = 0; e < DIM_; ++e) co[1 + e] = co[1 + e] + tau * stabres * u[e] * c.w;
       // [g1] navierstokes.cpp:688: the 3-D z-momentum block writes through the uy offsets
       if (DIM_ == 3 && d == 2 && o.uz_reference) {
@@ -215,10 +215,63 @@ struct NavierStokesPhys : HGradSystem<DIM_, P_, DIM_ + 1> {
     }
     Cf[1][0] = divu * c.w;
   }
-  template <class T, bool STATE = false>
+  template <class T, bool STATE = false, int FN0 = 0, int BD0 = NFN, int V0 = 0>
   MRH_HD static void boundary(const QpCtx& c, const GenOpts&, const T (&)[NVAR][4], const T (&)[NVAR][4], T (&Cf)[NVAR][4]) {
     for (int d = 0; d < DIM_; ++d)
-      if (c.bc_type[vel(d)] == BC_NEUMANN) Cf[vel(d)][0] = T(0.0) - MRH_FN(NFN + vel(d)) * c.w;
+      if (c.bc_type[V0 + vel(d)] == BC_NEUMANN) Cf[vel(d)][0] = T(0.0) - MRH_FN(BD0 + vel(d)) * c.w;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Blocks with two modules ("modules: thermal, linearelasticity", "modules: navier stokes, thermal"): the reference runs the modules one
+// after the other on the block's workset (volumeResidual / boundaryResidual of every module, assemblyManager_jacres.hpp:362-368,
+// 470-480), each writing the residual rows of its own variables; variables and coefficient functions are listed module by module,
+// boundary data after all functions (index NFN + variable).  Couplings a module switches on when it finds another module's variable:
+//   thermal: have_nsvel (thermal.cpp:117-149, 379) -- the temperature is advected by the Navier-Stokes velocity.
+// (linearelasticity's thermo-elastic terms and navierstokes' energy term key on a variable named "e"; the thermal module's variable is
+//  "T", so neither is active in these blocks -- linearelasticity.cpp:905, navierstokes.cpp:1031-1045.)
+// ---------------------------------------------------------------------------------------------------------
+template <int NA, int NB, class T, int NV>
+MRH_HD const T (&sub_fields(const T (&F)[NV][4]))[NB][4] { return *reinterpret_cast<const T (*)[NB][4]>(&F[NA]); }
+template <int NA, int NB, class T, int NV>
+MRH_HD T (&sub_coefs(T (&F)[NV][4]))[NB][4] { return *reinterpret_cast<T (*)[NB][4]>(&F[NA]); }
+
+template <int DIM_, int P_>
+struct ThermalElasticityPhys : HGradSystem<DIM_, P_, 1 + DIM_> {   // variables T, dx, dy(, dz)
+  typedef ThermalPhys<DIM_, P_> A;
+  typedef ElasticityPhys<DIM_, P_> B;
+  static constexpr int NVAR = 1 + DIM_, NFN = A::NFN + B::NFN;
+  template <class T, bool STATE = false>
+  MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&Ft)[NVAR][4], T (&Cf)[NVAR][4]) {
+    A::template volume<T, STATE, 0, NFN, 0>(c, o, sub_fields<0, 1>(F), sub_fields<0, 1>(Ft), sub_coefs<0, 1>(Cf));
+    B::template volume<T, STATE, A::NFN, NFN + 1, 1>(c, o, sub_fields<1, DIM_>(F), sub_fields<1, DIM_>(Ft), sub_coefs<1, DIM_>(Cf));
+  }
+  template <class T, bool STATE = false>
+  MRH_HD static void boundary(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&Ft)[NVAR][4], T (&Cf)[NVAR][4]) {
+    A::template boundary<T, STATE, 0, NFN, 0>(c, o, sub_fields<0, 1>(F), sub_fields<0, 1>(Ft), sub_coefs<0, 1>(Cf));
+    B::template boundary<T, STATE, A::NFN, NFN + 1, 1>(c, o, sub_fields<1, DIM_>(F), sub_fields<1, DIM_>(Ft), sub_coefs<1, DIM_>(Cf));
+  }
+};
+
+template <int DIM_, int P_>
+struct NavierStokesThermalPhys : HGradSystem<DIM_, P_, DIM_ + 2> {   // variables ux, pr, uy(, uz), T
+  typedef NavierStokesPhys<DIM_, P_> A;
+  typedef ThermalPhys<DIM_, P_> B;
+  static constexpr int NA = DIM_ + 1, NVAR = DIM_ + 2, NFN = A::NFN + B::NFN;
+  template <class T, bool STATE = false>
+  MRH_HD static void volume(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&Ft)[NVAR][4], T (&Cf)[NVAR][4]) {
+    A::template volume<T, STATE, 0, NFN, 0>(c, o, sub_fields<0, NA>(F), sub_fields<0, NA>(Ft), sub_coefs<0, NA>(Cf));
+    B::template volume<T, STATE, A::NFN, NFN + NA, NA>(c, o, sub_fields<NA, 1>(F), sub_fields<NA, 1>(Ft), sub_coefs<NA, 1>(Cf));
+    // have_nsvel (thermal.cpp:139-149): + (u . grad T) v
+    T adv = F[A::vel(0)][0] * F[NA][1];
+    if (DIM_ > 1) adv = adv + F[A::vel(DIM_ > 1 ? 1 : 0)][0] * F[NA][2];
+    if (DIM_ > 2) adv = adv + F[A::vel(DIM_ > 2 ? 2 : 0)][0] * F[NA][3];
+    Cf[NA][0] = Cf[NA][0] + adv * c.w;
+  }
+  template <class T, bool STATE = false>
+  MRH_HD static void boundary(const QpCtx& c, const GenOpts& o, const T (&F)[NVAR][4], const T (&Ft)[NVAR][4], T (&Cf)[NVAR][4]) {
+    A::template boundary<T, STATE, 0, NFN, 0>(c, o, sub_fields<0, NA>(F), sub_fields<0, NA>(Ft), sub_coefs<0, NA>(Cf));
+    B::template boundary<T, STATE, A::NFN, NFN + NA, NA>(c, o, sub_fields<NA, 1>(F), sub_fields<NA, 1>(Ft), sub_coefs<NA, 1>(Cf));
   }
 };
 

@@ -16,6 +16,7 @@ class thermal : public PhysicsBase<EvalT> {
   using PhysicsBase<EvalT>::wkset;
   using PhysicsBase<EvalT>::functionManager;
   int T_num = -1, T_basis_num = -1;
+  bool have_nsvel = false;
   double formparam = 1.0;
   bool have_advection = false;
 
@@ -44,6 +45,7 @@ class thermal : public PhysicsBase<EvalT> {
     wkset = w;
     T_num = this->findVar("T");
     T_basis_num = wkset->usebasis[T_num];
+    have_nsvel = this->findVar("ux") >= 0;   // thermal.cpp:362-379: a Navier-Stokes velocity in the block advects the temperature
   }
 
   void volumeResidual() override {
@@ -74,6 +76,12 @@ class thermal : public PhysicsBase<EvalT> {
           res(elem, off[dof]) += diff(elem, pt) * dTdx(elem, pt) * w * basis_grad(elem, dof, pt, 0);
           if (spaceDim > 1) res(elem, off[dof]) += diff(elem, pt) * dTdy(elem, pt) * w * basis_grad(elem, dof, pt, 1);
           if (spaceDim > 2) res(elem, off[dof]) += diff(elem, pt) * dTdz(elem, pt) * w * basis_grad(elem, dof, pt, 2);
+          if (have_nsvel) {   // thermal.cpp:139-149
+            auto& Ux = wkset->getSolutionField("ux");
+            if (spaceDim == 1) res(elem, off[dof]) += Ux(elem, pt) * dTdx(elem, pt) * w * basis(elem, dof, pt, 0);
+            else if (spaceDim == 2) res(elem, off[dof]) += (Ux(elem, pt) * dTdx(elem, pt) + wkset->getSolutionField("uy")(elem, pt) * dTdy(elem, pt)) * w * basis(elem, dof, pt, 0);
+            else res(elem, off[dof]) += (Ux(elem, pt) * dTdx(elem, pt) + wkset->getSolutionField("uy")(elem, pt) * dTdy(elem, pt) + wkset->getSolutionField("uz")(elem, pt) * dTdz(elem, pt)) * w * basis(elem, dof, pt, 0);
+          }
           if (have_advection) {
             if (spaceDim == 1) res(elem, off[dof]) += bx(elem, pt) * dTdx(elem, pt) * w * basis(elem, dof, pt, 0);
             else if (spaceDim == 2) res(elem, off[dof]) += (bx(elem, pt) * dTdx(elem, pt) + by(elem, pt) * dTdy(elem, pt)) * w * basis(elem, dof, pt, 0);

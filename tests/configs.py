@@ -92,6 +92,40 @@ MAXWELL_3D = {
     "Solver": {"solver": "transient"},
 }
 MAXWELL_ABC = {"Physics/Dirichlet conditions": {"E": {"left": "0.0"}}, "Physics/Neumann conditions": {"B": {"right": "0.0", "top": "0.0", "front": "0.0"}}}
+# two-module blocks (the reference's regression/thermoelastic/2D_transient couples "thermal, linearelasticity"; "navier stokes, thermal"
+# switches thermal's have_nsvel advection on, thermal.cpp:117-149)
+THERMOELASTIC_2D = {
+    "Mesh": {"dimension": 2, "NX": 6, "NY": 5, "perturb": 0.03},
+    "Physics": {"modules": "thermal, linearelasticity",
+                "Dirichlet conditions": {"T": {"all boundaries": "0.0"}, "dx": {"all boundaries": "0.0"}, "dy": {"all boundaries": "0.0"}}},
+    "Functions": {"thermal source": "2*pi*pi*sin(pi*x)*sin(pi*y)", "thermal diffusion": "1.0+0.5*x", "density": "1.2", "lambda": "2.0", "mu": "0.7",
+                  "source dx": "x*y", "source dy": "1.0"},
+    "Discretization": {"order": {"T": 1, "dx": 1, "dy": 1}, "quadrature": 2},
+    "Solver": {"solver": "transient"},
+}
+THERMOELASTIC_2D_WEAK = {"Solver/use strong DBCs": False,
+                         "Physics/Dirichlet conditions": {"T": {"left": "1.0+y", "top": "x*x"}, "dx": {"left": "0.1*y", "top": "0.0"}, "dy": {"left": "0.0", "top": "x"}},
+                         "Physics/Neumann conditions": {"T": {"right": "2.0*y-0.3"}, "dx": {"right": "1.0"}, "dy": {"right": "y"}}}
+THERMOELASTIC_3D = {
+    "Mesh": {"dimension": 3, "NX": 4, "NY": 3, "NZ": 3, "perturb": 0.03},
+    "Physics": {"modules": "thermal, linearelasticity",
+                "Dirichlet conditions": {"T": {"all boundaries": "0.0"}, "dx": {"all boundaries": "0.0"}, "dy": {"all boundaries": "0.0"}, "dz": {"all boundaries": "0.0"}}},
+    "Functions": {"thermal source": "sin(pi*x)*y+z", "lambda": "1.0+0.3*x", "mu": "1.0", "source dx": "sin(pi*x)*y", "source dy": "lambda*z", "source dz": "1.0-x*y"},
+    "Discretization": {"order": {"T": 1, "dx": 1, "dy": 1, "dz": 1}, "quadrature": 2},
+    "Solver": {"solver": "steady-state"},
+}
+NS_THERMAL_2D = {
+    "Mesh": {"dimension": 2, "NX": 6, "NY": 5, "perturb": 0.02},
+    "Physics": {"modules": "navier stokes, thermal", "useSUPG": True, "usePSPG": True,
+                "Dirichlet conditions": {"ux": {"left": "1.0", "top": "0.0", "bottom": "0.0"}, "uy": {"left": "0.0", "top": "0.0", "bottom": "0.0"},
+                                         "pr": {"right": "0.0"}, "T": {"left": "1.0", "bottom": "0.0"}}},
+    "Functions": {"source ux": "1.0", "viscosity": "0.5", "density": "1.3", "thermal source": "x+y", "thermal diffusion": "0.2", "specific heat": "1.1"},
+    "Discretization": {"order": {"ux": 1, "pr": 1, "uy": 1, "T": 1}, "quadrature": 2},
+    "Solver": {"solver": "steady-state"},
+}
+NS_THERMAL_2D_WEAK = {"Solver/use strong DBCs": False,
+                      "Physics/Dirichlet conditions": {"ux": {"left": "1.0"}, "uy": {"left": "0.0"}, "T": {"left": "1.0+y", "top": "x*x"}},
+                      "Physics/Neumann conditions": {"ux": {"right": "0.3"}, "uy": {"right": "y"}, "T": {"right": "2.0*y-0.3"}}}
 THERMAL_WEAK = {"Solver/use strong DBCs": False, "Physics/assemble boundary terms": True, "Mesh/NX": 6, "Mesh/NY": 5, "Mesh/perturb": 0.01,
                 "Physics/Dirichlet conditions/T": {"left": "1.0+y", "top": "x*x"}, "Physics/Neumann conditions/T": {"right": "2.0*y-0.3"}}
 BWE = ([[1.0]], [1.0], [1.0], 0)
@@ -142,5 +176,14 @@ def general_cases():
         # Solver: lump mass -- the fused scatter adds every entry of a row to its diagonal (assemblyManager_scatter.hpp:263-268)
         ("thermal3d-lump-dirk", variant(t3, **{"Solver/lump mass": True, "Functions/density": "2.0"}), {}, DIRK12, False),
         ("thermal2d-lump-dirk", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Solver/lump mass": True})), {}, DIRK12, False),
+        # two-module blocks
+        ("thermoelastic2d", THERMOELASTIC_2D, {}, None, False),
+        ("thermoelastic2d-bwe", THERMOELASTIC_2D, {}, BWE, False),
+        ("thermoelastic2d-weak", variant(THERMOELASTIC_2D, **THERMOELASTIC_2D_WEAK), {}, None, False),
+        ("thermoelastic3d-dirk", THERMOELASTIC_3D, {}, DIRK12, False),
+        ("ns-thermal2d", NS_THERMAL_2D, {}, None, False),
+        ("ns-thermal2d-bwe", NS_THERMAL_2D, {}, BWE, False),
+        ("ns-thermal2d-weak", variant(NS_THERMAL_2D, **NS_THERMAL_2D_WEAK), {}, None, False),
+        ("ns-thermal2d-state", variant(NS_THERMAL_2D, **{"Functions/thermal diffusion": "0.2+0.1*T*T", "Functions/viscosity": "0.5+0.1*T"}), {}, None, False),
         ("thermal2d-weak-state", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Functions/thermal diffusion": "1.0+0.5*T*T"})), {}, None, False),
     ]

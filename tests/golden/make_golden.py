@@ -20,7 +20,8 @@ REF = "/root/reference/regression"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 CASES = ["thermal/2D_verification", "thermal/2D_verification_mpi", "thermal/3D_verification", "thermal/2D_verification_transient",
-         "thermal/2D_mixed_bcs", "le/3D_manufactured", "le/2D_manufactured", "navierstokes/channel", "maxwell/PlaneWave", "maxwell/NonzeroIC"]
+         "thermal/2D_mixed_bcs", "le/3D_manufactured", "le/2D_manufactured", "navierstokes/channel", "maxwell/PlaneWave", "maxwell/NonzeroIC",
+         "thermoelastic/2D_transient"]   # a two-module block: "modules: thermal, linearelasticity"
 # (thermal/2D_verification_nonzeroDBC is not usable as a pin: its Dirichlet data come from the solver's boundary
 #  L2 projection, solverManager_util.hpp:24-48, which is outside the path)
 

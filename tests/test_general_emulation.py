@@ -247,3 +247,26 @@ def test_point_constraints_replace_rows(oracle_lib, product_lib):
     res[:], jac[:] = 0.0, 0.0   # the plan accumulates
     plan.debug_emulate(u, res, jac)
     assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL
+
+
+def test_thermoelastic_gold_through_kernel_stages(oracle_lib, product_lib):
+    """regression/thermoelastic/2D_transient (block "thermal, linearelasticity"): ten BWE steps assembled by the host replay of the two-module
+    kernel's stages reproduce the reference's printed L2 norms of T (0.331419 at t = 0.1 ... 0.498946 at 0.9)."""
+    from test_oracle_golden import _thermoelastic_steps
+    deck, errs = helpers.gold_errors("thermoelastic/2D_transient")
+    cfg = helpers.deck_to_cfg(deck)
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1)
+    assert plan.stat("general") == 1
+    state = {}
+
+    def set_time(t, dt):
+        state["t"], state["dt"] = t, dt
+
+    def assemble(us, u):
+        ts = helpers.TimeSpec(time=state["t"], deltat=state["dt"], stage=0, A=((1.0,),), b=(1.0,), c=(1.0,), bdf=(1.0, -1.0), sol_prev=[u], sol_stage=[us])
+        res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+        plan.debug_emulate(us, res, jac, time=ts)
+        return res, jac
+
+    _thermoelastic_steps(cfg, errs, op.num_dofs, assemble, op.l2_error, set_time, op.csr)

@@ -218,6 +218,26 @@ def test_set_initial_reproduces_reference_gold(oracle_lib, product_lib):
         assert abs(got - gold[f]) <= 0.5e-5 * gold[f], (f, got, gold[f])
 
 
+def test_thermoelastic_gold_through_cuda_path(oracle_lib, product_lib):
+    """regression/thermoelastic/2D_transient (block "thermal, linearelasticity") assembled on the GPU: the reference's printed L2 norms of T."""
+    from test_oracle_golden import _thermoelastic_steps
+    deck, errs = helpers.gold_errors("thermoelastic/2D_transient")
+    cfg = helpers.deck_to_cfg(deck)
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg)
+    assert plan.stat("general") == 1
+    state = {}
+
+    def set_time(t, dt):
+        state["t"], state["dt"] = t, dt
+
+    def assemble(us, u):
+        ts = helpers.TimeSpec(time=state["t"], deltat=state["dt"], stage=0, A=((1.0,),), b=(1.0,), c=(1.0,), bdf=(1.0, -1.0), sol_prev=[_dev(u)], sol_stage=[_dev(us)])
+        return _assemble(plan, op, us, ts)
+
+    _thermoelastic_steps(cfg, errs, op.num_dofs, assemble, op.l2_error, set_time, op.csr)
+
+
 def _spmv(rowptr, colind, vals, x):
     import torch
     J = torch.sparse_csr_tensor(torch.from_numpy(rowptr).to(x.device), torch.from_numpy(colind.astype(np.int64)).to(x.device), vals, size=(len(rowptr) - 1, len(rowptr) - 1))

@@ -59,6 +59,38 @@ def test_transient_thermal_gold(oracle_lib):
         assert abs(got - want) <= _tol(want), (n, got, want)
 
 
+def _thermoelastic_steps(cfg, errs, num_dofs, assemble, l2_error, set_time, csr):
+    """regression/thermoelastic/2D_transient: block "thermal, linearelasticity" (T, dx, dy), BWE, 10 steps; the true solutions are 0, so the
+    printed errors are the L2 norms of the fields: T is the pin, dx / dy stay at the linear solver's noise (gold 4.8e-8, here ~0)."""
+    import scipy.sparse.linalg as spla
+    nsteps = int(cfg["Solver"]["number of steps"])
+    dt = float(cfg["Solver"]["final time"]) / nsteps
+    u = np.zeros(num_dofs)
+    gold = {(e["field"], round(e["time"], 6)): e["value"] for e in errs}
+    for n in range(nsteps):
+        t = n * dt
+        set_time(t, dt)
+        us = u.copy()
+        for _ in range(2):
+            res, jac = assemble(us, u)
+            us = us + spla.spsolve(csr(jac).tocsc(), res)
+        u = us
+        want = gold[("T", round(t + dt, 6))]
+        got = l2_error(["T"], u)
+        assert abs(got - want) <= _tol(want), (n, got, want)
+        assert l2_error(["dx"], u) < 1e-6 and l2_error(["dy"], u) < 1e-6
+    return u
+
+
+def test_thermoelastic_two_module_gold(oracle_lib):
+    cfg, errs = _errs("thermoelastic/2D_transient")
+    op = oracle_lib.OracleProblem(cfg)
+    assert op.modules().replace(" ", "") == "thermal,linearelasticity" and op.var_names() == ["T", "dx", "dy"]
+    _thermoelastic_steps(cfg, errs, op.num_dofs,
+                         lambda us, u: op.assemble_jacres(us, sol_prev=[u], sol_stage=[us]), op.l2_error,
+                         lambda t, dt: op.set_time(True, time=t, dt=dt, stage=0, A=((1.0,),), b=(1.0,), c=(1.0,), bdf=(1.0, -1.0)), op.csr)
+
+
 def test_function_forest_matches_functions_valid_gold(oracle_lib):
     """regression/functions/Valid prints the decomposition forest; the oracle's Interpreter::split restatement
     must produce the same branches in the same order (pins the parse / evaluation order)."""
