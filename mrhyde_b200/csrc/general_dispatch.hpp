@@ -23,21 +23,26 @@ typedef NavierStokesThermalPhys<2, 1> GenNsTh21;
 // least) of the tensor-core build (S4d / S4m: CTAs hold as many elements as the shared memory of MINB resident CTAs allows and MAXT
 // threads whatever the element size, one warp per (element, variable pair) block) and of the derivative-lane build (S4b: one thread
 // per element dof).  The two-basis Maxwell layout has the lane build only.
-#define MRH_GEN_LIST(X)                                                     \
+// four parts of roughly equal compile time, one translation unit each (general_inst0.cu .. general_inst3.cu)
+#define MRH_GEN_LIST_0(X)                                                   \
   X("thermal", 2, 1, 4, 2, 1, GenTh21, 256, 3, 256, 3)                      \
   X("thermal", 3, 1, 8, 4, 1, GenTh31, 256, 3, 256, 3)                      \
   X("thermal", 2, 2, 9, 3, 1, GenTh22, 256, 3, 256, 2)                      \
   X("thermal", 3, 2, 27, 9, 1, GenTh32, 128, 4, 128, 3)                     \
+  X("maxwell", 3, 1, 8, 4, 1, MaxwellPhys, 128, 3, 128, 3)
+#define MRH_GEN_LIST_1(X)                                                   \
   X("linearelasticity", 2, 1, 4, 2, 1, GenLe21, 256, 3, 256, 3)             \
   X("linearelasticity", 3, 1, 8, 4, 1, GenLe31, 256, 3, 256, 3)             \
   X("linearelasticity", 2, 2, 9, 3, 1, GenLe22, 256, 3, 128, 4)             \
+  X("navier stokes", 2, 1, 4, 2, 1, GenNs21, 256, 3, 256, 2)
+#define MRH_GEN_LIST_2(X)                                                   \
   X("linearelasticity", 3, 2, 27, 9, 1, GenLe32, 576, 1, 96, 2)             \
-  X("navier stokes", 2, 1, 4, 2, 1, GenNs21, 256, 3, 256, 2)                \
-  X("navier stokes", 3, 1, 8, 4, 1, GenNs31, 256, 2, 128, 3)                \
-  X("thermal+linearelasticity", 2, 1, 4, 2, 1, GenThLe21, 256, 3, 256, 3)     \
-  X("thermal+linearelasticity", 3, 1, 8, 4, 1, GenThLe31, 256, 2, 256, 2)     \
-  X("navier stokes+thermal", 2, 1, 4, 2, 1, GenNsTh21, 256, 2, 256, 2)        \
-  X("maxwell", 3, 1, 8, 4, 1, MaxwellPhys, 128, 3, 128, 3)
+  X("navier stokes", 3, 1, 8, 4, 1, GenNs31, 256, 2, 128, 3)
+#define MRH_GEN_LIST_3(X)                                                   \
+  X("thermal+linearelasticity", 2, 1, 4, 2, 1, GenThLe21, 256, 3, 256, 3)   \
+  X("thermal+linearelasticity", 3, 1, 8, 4, 1, GenThLe31, 256, 2, 256, 2)   \
+  X("navier stokes+thermal", 2, 1, 4, 2, 1, GenNsTh21, 256, 2, 256, 2)
+#define MRH_GEN_LIST(X) MRH_GEN_LIST_0(X) MRH_GEN_LIST_1(X) MRH_GEN_LIST_2(X) MRH_GEN_LIST_3(X)
 
 namespace mrhyde_b200 {
 template <class Phys, int NQ, int NQS, int K>

@@ -1,0 +1,6 @@
+// Part 2 of the general element kernel's instantiation list (general_dispatch.hpp: MRH_GEN_LIST_2).
+#include "general_launch.cuh"
+
+namespace mrhyde_b200 {
+MRH_GEN_PART(gen_device_part2, MRH_GEN_LIST_2)
+}  // namespace mrhyde_b200
