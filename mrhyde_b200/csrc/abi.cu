@@ -178,7 +178,7 @@ struct NvtxRange {
 };
 
 const char* kKnownOptions[] = {"accumulate", "use strong DBCs", "assemble boundary terms", "assemble volume terms", "form_param", "include advection",
-                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "lump mass", "prefetch records", "column cache", "scratch GB", "debug transient", "debug mode", nullptr};
+                               "ns3d_uz_rows", "useSUPG", "usePSPG", "penalty", "incplanestress", "kernel", "batch elems", "elements per cta", "column elements", "min chains", "min segment levels", "cta slots", "sweep axis", "threads", "jit", "use leap frog", "ring", "pull patterns", "min blocks", "max registers", "pull group", "debug skip", "max blocks", "stage1", "stagger ns", "flush", "flush unroll", "stage2", "tables", "overlap halo", "halo transport", "pipeline", "store hint", "prefetch", "jacobian", "halo push", "lump mass", "prefetch records", "column cache", "fix zero rows", "scratch GB", "debug transient", "debug mode", nullptr};
 
 std::string opt(const mrhyde_b200_plan* P, const std::string& key, const std::string& def) {
   auto it = P->options.find(key);
@@ -938,7 +938,34 @@ __global__ void point_rows_kernel(const int64_t* __restrict__ rows, int n, doubl
   for (int64_t p = b + lane; p < e; p += 32) jac[p] = (p == d) ? 1.0 : 0.0;
 }
 
+static int point_rows(mrhyde_b200_plan* P, double* jac, cudaStream_t st);
+// Solver: fix zero rows (assemblyManager_jacres.hpp:609-626): rows with sum |J(row, :)| < 1e-14 get J(row,row) = 1; one warp per row
+__global__ void fix_zero_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind, int64_t nrows, double* __restrict__ jac) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const int64_t b = rowptr[row], e = rowptr[row + 1];
+  double s = 0.0;
+  for (int64_t p = b + lane; p < e; p += 32) s += fabs(jac[p]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (s < 1.0e-14)
+    for (int64_t p = b + lane; p < e; p += 32) if (colind[p] == row) jac[p] = 1.0;
+}
+
 static int point_constraints(mrhyde_b200_plan* P, double* jac, cudaStream_t st) {
+  int launched = point_rows(P, jac, st);   // second loop of dofConstraints
+  if (jac && opt_bool(P, "fix zero rows", false) && P->mesh.nrows > 0) {
+    // after dofConstraints, as in the reference; the row sums of an entry order other than the reference's differ in the last bits, which
+    // only matters for rows within rounding of the 1e-14 threshold
+    const int64_t n = P->mesh.nrows;
+    fix_zero_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(P->d_rowptr.p, P->d_colind.p, n, jac);
+    CUDA_OK(cudaGetLastError());
+    ++launched;
+  }
+  return launched;
+}
+
+static int point_rows(mrhyde_b200_plan* P, double* jac, cudaStream_t st) {
   const int n = (int)(P->d_point_rows.n / 3);
   if (n == 0 || !jac) return 0;
   point_rows_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(P->d_point_rows.p, n, jac);
@@ -2284,6 +2311,12 @@ int mrhyde_b200_plan_debug_emulate(mrhyde_b200_plan* P, const double* sol, const
   if (compute_jacobian && jac)
     for (int32_t r : P->point_dofs)
       for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) jac[p] = (M.colind[(size_t)p] == r) ? 1.0 : 0.0;
+  if (compute_jacobian && jac && opt_bool(P, "fix zero rows", false))
+    for (int64_t r = 0; r < M.nrows; ++r) {
+      double s = 0.0;
+      for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) s += std::fabs(jac[p]);
+      if (s < 1.0e-14) for (int64_t p = M.rowptr[(size_t)r]; p < M.rowptr[(size_t)r + 1]; ++p) if (M.colind[(size_t)p] == r) jac[p] = 1.0;
+    }
   ABI_END
 }
 

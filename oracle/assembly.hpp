@@ -81,6 +81,7 @@ class AssemblyManager {
   bool assemble_volume_terms = true, assemble_boundary_terms = true, use_strong_DBCs = true;
   bool lump_mass = false;    // Solver: lump mass (assemblyManager_construct.hpp:36): the fused scatter sends every entry of a row to its diagonal
   std::vector<int> point_dofs;   // disc->point_dofs (local ids): dofConstraints replaces their whole Jacobian row by the identity row
+  bool fix_zero_rows = false;   // Solver: fix zero rows (assemblyManager_construct.hpp:33)
   bool useadjoint = false;   // assembleJacRes(..., useadjoint, ...): transposed local Jacobians (updateJac, assemblyManager_jacres.hpp:1459-1475)
   TimeData td;
   std::unique_ptr<EngineBase> eng_scalar, eng_ad;
@@ -367,6 +368,15 @@ struct Engine : EngineBase {
       for (int d : am.point_dofs)
         for (int64_t p = am.graph.rowptr[d]; p < am.graph.rowptr[d + 1]; ++p) Jvals[p] = (am.graph.colind[p] == d) ? 1.0 : 0.0;
     }
+    // fix_zero_rows (assemblyManager_jacres.hpp:609-626): a row whose entries sum to less than 1e-14 in absolute value gets a unit diagonal
+    if (am.fix_zero_rows && Jvals) {
+      for (int64_t row = 0; row < am.dofs.num_dofs; ++row) {
+        double abssum = 0.0;
+        for (int64_t p = am.graph.rowptr[row]; p < am.graph.rowptr[row + 1]; ++p) abssum += std::abs(Jvals[p]);
+        if (abssum < 1.0e-14)
+          for (int64_t p = am.graph.rowptr[row]; p < am.graph.rowptr[row + 1]; ++p) if (am.graph.colind[p] == row) Jvals[p] = 1.0;
+      }
+    }
   }
 
   std::string printTree(const std::string& name, const std::string& loc) override { return fm.printTree(name, loc); }
@@ -591,6 +601,7 @@ inline AssemblyManager::AssemblyManager(const Settings& s) : settings(s) {
   workset_size = s.geti("Solver/workset size", 100);
   use_strong_DBCs = s.getb("Solver/use strong DBCs", true);
   lump_mass = s.getb("Solver/lump mass", false);
+  fix_zero_rows = s.getb("Solver/fix zero rows", false);
   assemble_volume_terms = s.getb("Physics/assemble volume terms", true);
   assemble_boundary_terms = s.getb("Physics/assemble boundary terms", true);
 

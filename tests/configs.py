@@ -176,6 +176,9 @@ def general_cases():
         # Solver: lump mass -- the fused scatter adds every entry of a row to its diagonal (assemblyManager_scatter.hpp:263-268)
         ("thermal3d-lump-dirk", variant(t3, **{"Solver/lump mass": True, "Functions/density": "2.0"}), {}, DIRK12, False),
         ("thermal2d-lump-dirk", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Solver/lump mass": True})), {}, DIRK12, False),
+        # Solver: fix zero rows (assemblyManager_jacres.hpp:609-626): rows whose entries sum to < 1e-14 in absolute value get a unit diagonal
+        ("thermal3d-fix-zero-rows", variant(t3, **{"Solver/fix zero rows": True, "Functions/thermal diffusion": "0.0"}), {}, None, False),   # every row is empty
+        ("maxwell-fix-zero-rows", variant(MAXWELL_3D, **{"Solver/fix zero rows": True}), {}, DIRK12, True),
         # two-module blocks
         ("thermoelastic2d", THERMOELASTIC_2D, {}, None, False),
         ("thermoelastic2d-bwe", THERMOELASTIC_2D, {}, BWE, False),

@@ -35,6 +35,8 @@ def plan_from_oracle(op, cfg, device=0, options=None, indexed=False):
         plan.set_option("use strong DBCs", solver["use strong DBCs"])
     if "lump mass" in solver:
         plan.set_option("lump mass", solver["lump mass"])
+    if "fix zero rows" in solver:
+        plan.set_option("fix zero rows", solver["fix zero rows"])
     for k, v in list(DEFAULT_OPTIONS.items()) + list((options or {}).items()):
         plan.set_option(k, v)
     if indexed:

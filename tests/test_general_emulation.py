@@ -270,3 +270,19 @@ def test_thermoelastic_gold_through_kernel_stages(oracle_lib, product_lib):
         return res, jac
 
     _thermoelastic_steps(cfg, errs, op.num_dofs, assemble, op.l2_error, set_time, op.csr)
+
+
+def test_fix_zero_rows_gives_unit_diagonal(oracle_lib, product_lib):
+    """Solver: fix zero rows with a vanishing diffusion coefficient: every Jacobian row is empty, so every diagonal entry becomes 1
+    (assemblyManager_jacres.hpp:609-626) -- in the oracle and in the product's replay."""
+    name, cfg, opts, tableau, zero = [c for c in configs.general_cases() if c[0] == "thermal3d-fix-zero-rows"][0]
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options={"kernel": "general"})
+    u = helpers.manufactured_state(op)
+    _, jac_ref = op.assemble_jacres(u)
+    res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+    plan.debug_emulate(u, res, jac)
+    import scipy.sparse as sp
+    for J in (jac_ref, jac):
+        A = op.csr(J)
+        assert abs(A - sp.identity(op.num_dofs)).max() == 0.0

@@ -376,3 +376,16 @@ def test_point_constraints(oracle_lib, product_lib, kernel):
         plan.set_point_dofs(np.zeros(0, dtype=np.int32))
     op.set_point_dofs(np.zeros(0, dtype=np.int32))
     _check(op, plan, helpers.manufactured_state(op))
+
+
+def test_fix_zero_rows_after_the_sweep_kernel(oracle_lib, product_lib):
+    """Solver: fix zero rows (assemblyManager_jacres.hpp:609-626) as a post-pass of the sweep kernel: with a vanishing diffusion coefficient
+    every Jacobian row is empty and gets a unit diagonal; with the regular deck nothing changes."""
+    for diff in ("0.0", "1.0"):
+        cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 7, "Mesh/NY": 6, "Mesh/NZ": 5, "Solver/fix zero rows": True, "Functions/thermal diffusion": diff})
+        op = oracle_lib.OracleProblem(cfg)
+        plan = helpers.plan_from_oracle(op, cfg)
+        assert plan.stat("general") == 0
+        _, jac, _, _ = _check(op, plan, helpers.manufactured_state(op))
+        if diff == "0.0":
+            assert abs(op.csr(jac) - __import__("scipy.sparse").sparse.identity(op.num_dofs)).max() == 0.0
