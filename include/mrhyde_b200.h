@@ -85,6 +85,12 @@ typedef struct {
   const double* bdf_wts;        /* host [nbdf]                                                   */
   const double* const* sol_prev;  /* host array of [nbdf-1] device vectors u_{n}, u_{n-1}, ...    */
   const double* const* sol_stage; /* host array of [nstages] device vectors (stages < stage read) */
+  /* What the Jacobian is the derivative with respect to (seedwhat / seedindex of updateWorkset, assemblyManager_jacres.hpp:176-190;
+   * computeSolnTransientSeeded, workset.cpp:622-785): 0 or 1 = the stage solution `sol` (assembleJacRes' default), 2 = previous step
+   * seed_index (compute_previous_jac: sol_prev[seed_index]), 3 = previous stage seed_index (sol_stage[seed_index]).  The residual and
+   * the evaluation point are the same in all modes. */
+  int32_t seed_what;
+  int32_t seed_index;
 } mrhyde_b200_time;
 
 /* Side data of one boundary group family (BoundaryGroup, assemblyManager_groups.hpp; reference

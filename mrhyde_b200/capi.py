@@ -55,7 +55,7 @@ class TimeData(C.Structure):
     _fields_ = [("time", C.c_double), ("deltat", C.c_double), ("stage", C.c_int32), ("nstages", C.c_int32),
                 ("butcher_A", C.POINTER(C.c_double)), ("butcher_b", C.POINTER(C.c_double)), ("butcher_c", C.POINTER(C.c_double)),
                 ("nbdf", C.c_int32), ("bdf_wts", C.POINTER(C.c_double)),
-                ("sol_prev", C.POINTER(C.c_void_p)), ("sol_stage", C.POINTER(C.c_void_p))]
+                ("sol_prev", C.POINTER(C.c_void_p)), ("sol_stage", C.POINTER(C.c_void_p)), ("seed_what", C.c_int32), ("seed_index", C.c_int32)]
 
 
 class BoundaryGroup(C.Structure):
@@ -183,8 +183,9 @@ def _make_basis(b, keep):
 class TimeSpec:
     """Python-side holder of mrhyde_b200_time (keeps the arrays alive)."""
 
-    def __init__(self, time=0.0, deltat=1.0, stage=0, A=None, b=None, c=None, bdf=None, sol_prev=(), sol_stage=()):
+    def __init__(self, time=0.0, deltat=1.0, stage=0, A=None, b=None, c=None, bdf=None, sol_prev=(), sol_stage=(), seed_what=1, seed_index=0):
         self.s = TimeData()
+        self.s.seed_what, self.s.seed_index = seed_what, seed_index
         self.s.time = time
         self.s.deltat = deltat
         self.s.stage = stage

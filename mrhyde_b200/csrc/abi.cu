@@ -976,10 +976,14 @@ static int point_rows(mrhyde_b200_plan* P, double* jac, cudaStream_t st) {
 void fill_time(const mrhyde_b200_time* t, TimeDev& td, bool device_ptrs_ok) {
   std::memset(&td, 0, sizeof(td));
   td.alpha_u = 1.0;
+  td.seed_u = 1.0;
   td.deltat = 1.0;
   if (!t) return;
   td.time = t->time;
-  if (t->nstages <= 0) return;  // steady evaluation at a given time
+  if (t->nstages <= 0) {        // steady evaluation at a given time
+    if (t->seed_what > 1) fail(MRHYDE_B200_ERR_INVALID, "time: seed_what 2 / 3 (previous step / stage) needs a transient evaluation");
+    return;
+  }
   if (t->stage < 0 || t->stage >= t->nstages || t->nstages > MAX_STAGE) fail(MRHYDE_B200_ERR_INVALID, "time: stage index / stage count out of range");
   if (t->nbdf < 2 || t->nbdf - 1 > MAX_PREV) fail(MRHYDE_B200_ERR_INVALID, "time: unsupported number of BDF weights");
   if (!t->butcher_A || !t->butcher_b || !t->butcher_c || !t->bdf_wts || !t->sol_prev) fail(MRHYDE_B200_ERR_INVALID, "time: missing tables");
@@ -995,6 +999,21 @@ void fill_time(const mrhyde_b200_time* t, TimeDev& td, bool device_ptrs_ok) {
   td.nstage_lo = s;
   for (int k = 0; k < s; ++k) td.stage_w[k] = t->butcher_A[s * ns + k] / t->butcher_b[k];
   td.time = t->time + t->butcher_c[s] * t->deltat;
+  // derivative seeds (computeSolnTransientSeeded, workset.cpp:622-785): the chain-rule factors of the seeded vector in u and u_t, accumulated
+  // in the order Sacado accumulates them
+  td.seed_u = td.alpha_u; td.seed_t = td.alpha_t;
+  if (t->seed_what == 2) {        // previous step seed_index
+    if (t->seed_index < 0 || t->seed_index >= td.nprev) fail(MRHYDE_B200_ERR_INVALID, "time: seed_index is not a previous step of this BDF formula");
+    td.seed_u = 0.0;
+    if (t->seed_index == 0) { td.seed_u = td.one_minus_alpha_u; for (int k = 0; k < s; ++k) td.seed_u += td.stage_w[k] * -1.0; }
+    td.seed_t = td.bdf[t->seed_index + 1] * td.timewt;
+  } else if (t->seed_what == 3) { // previous stage seed_index
+    if (t->seed_index < 0 || t->seed_index >= s) fail(MRHYDE_B200_ERR_INVALID, "time: seed_index is not a stage below the current one");
+    td.seed_u = td.stage_w[t->seed_index];
+    td.seed_t = 0.0;
+  } else if (t->seed_what != 0 && t->seed_what != 1) {
+    fail(MRHYDE_B200_ERR_INVALID, "time: seed_what must be 0 / 1 (stage solution), 2 (previous step) or 3 (previous stage)");
+  }
   if (device_ptrs_ok) {
     for (int k = 0; k < td.nprev; ++k) { td.prev[k] = t->sol_prev[k]; if (!td.prev[k]) fail(MRHYDE_B200_ERR_INVALID, "time: null sol_prev vector"); }
     if (s > 0 && !t->sol_stage) fail(MRHYDE_B200_ERR_INVALID, "time: missing sol_stage");
@@ -2390,7 +2409,7 @@ int mrhyde_b200_plan_debug_emulate_initial(mrhyde_b200_plan* P, double time, dou
   Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
   Q.orient = M.orient.empty() ? nullptr : M.orient.data();
   Q.sol = zero.data();
-  Q.td.alpha_u = 1.0; Q.td.deltat = 1.0; Q.td.time = time;
+  Q.td.alpha_u = 1.0; Q.td.seed_u = 1.0; Q.td.deltat = 1.0; Q.td.time = time;
   std::memcpy(Q.off, H.off, sizeof(Q.off));
   std::memcpy(Q.fn, H.init_fn, sizeof(Q.fn));
   Q.fn_op = H.fn_op.data(); Q.fn_c = H.fn_c.data(); Q.opt = H.opt;
@@ -2420,7 +2439,7 @@ int mrhyde_b200_plan_debug_emulate_mass(mrhyde_b200_plan* P, const double* mass_
   Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
   Q.orient = M.orient.empty() ? nullptr : M.orient.data();
   Q.sol = zero.data();
-  Q.td.alpha_u = 1.0; Q.td.deltat = 1.0;
+  Q.td.alpha_u = 1.0; Q.td.seed_u = 1.0; Q.td.deltat = 1.0;
   std::memcpy(Q.off, H.off, sizeof(Q.off));
   std::memcpy(Q.fn, H.fn, sizeof(Q.fn));
   Q.fn_op = H.fn_op.data(); Q.fn_c = H.fn_c.data(); Q.opt = H.opt;
@@ -2451,7 +2470,7 @@ int mrhyde_b200_plan_debug_emulate_apply_mass(mrhyde_b200_plan* P, const double*
   Q.vx = M.vcoord[0].data(); Q.vy = M.vcoord[1].data(); Q.vz = M.vcoord[2].data(); Q.conn = M.conn.data(); Q.lids = M.lids.data();
   Q.orient = M.orient.empty() ? nullptr : M.orient.data();
   Q.sol = x;
-  Q.td.alpha_u = 1.0; Q.td.deltat = 1.0;
+  Q.td.alpha_u = 1.0; Q.td.seed_u = 1.0; Q.td.deltat = 1.0;
   std::memcpy(Q.off, H.off, sizeof(Q.off));
   std::memcpy(Q.fn, H.fn, sizeof(Q.fn));
   Q.fn_op = H.fn_op.data(); Q.fn_c = H.fn_c.data(); Q.opt = H.opt;
@@ -2476,8 +2495,8 @@ int mrhyde_b200_plan_debug_metric_host(mrhyde_b200_plan* P, const double* sol, c
   fill_time(t, td, true);   // host pointers: the replay reads them on the host
   std::vector<double> met;
   const int ng = P->dim * (P->dim + 1) / 2;
-  if (P->dim == 3) { metric_host_elements<3>(P, P->th3, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th3.tab.Stab[0][0], &P->th3.tab.Mtab[0], td.alpha_u, td.transient ? td.alpha_t : 0.0, accumulate != 0, res, jac); }
-  else { metric_host_elements<2>(P, P->th2, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th2.tab.Stab[0][0], &P->th2.tab.Mtab[0], td.alpha_u, td.transient ? td.alpha_t : 0.0, accumulate != 0, res, jac); }
+  if (P->dim == 3) { metric_host_elements<3>(P, P->th3, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th3.tab.Stab[0][0], &P->th3.tab.Mtab[0], td.seed_u, td.transient ? td.seed_t : 0.0, accumulate != 0, res, jac); }
+  else { metric_host_elements<2>(P, P->th2, sol, td, met); host_apply_metric_plan(P->mesh, P->cp, met.data(), ng, &P->th2.tab.Stab[0][0], &P->th2.tab.Mtab[0], td.seed_u, td.transient ? td.seed_t : 0.0, accumulate != 0, res, jac); }
   ABI_END
 }
 
@@ -2523,7 +2542,7 @@ int mrhyde_b200_plan_debug_class_host(mrhyde_b200_plan* P, const double* sol, co
       double k = 0.0;
       for (int g = 0; g < dim; ++g) k += m[g] * St[(size_t)g * NT + rep];   // boxes: the diagonal metric entries only
       kc[(size_t)c] = k;
-      if (td.transient) { mc[(size_t)c] = m[NG] * Mt[rep]; k = td.alpha_u * k + td.alpha_t * mc[(size_t)c]; }
+      if (td.transient) { mc[(size_t)c] = m[NG] * Mt[rep]; k = td.seed_u * k + td.seed_t * mc[(size_t)c]; }
       o[c] = k;
     }
     for (int i = 0; i < NV; ++i) {

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(64) thermal_boundary_kernel(const __grid_const
       r[i] += -kap * dTn * w * ph;
       r[i] += -sf * kap * (T - data) * w * gn[i];
       for (int j = 0; j < NV; ++j)
-        K[i][j] += P.td.alpha_u * (epen / h * kap * g.phi[q][j] * w * ph - kap * gn[j] * w * ph - sf * kap * g.phi[q][j] * w * gn[i]);
+        K[i][j] += P.td.seed_u * (epen / h * kap * g.phi[q][j] * w * ph - kap * gn[j] * w * ph - sf * kap * g.phi[q][j] * w * gn[i]);
     }
   }
   // ---- scatter (items of one launch never share a row)

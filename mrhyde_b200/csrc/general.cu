@@ -289,7 +289,7 @@ const char* gen_assemble_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const
   // the mass matrix does not depend on the state: any valid vector serves as `sol` (the element residual scratch is one)
   TimeDev td;
   std::memset(&td, 0, sizeof(td));
-  td.alpha_u = 1.0; td.deltat = 1.0;
+  td.alpha_u = 1.0; td.seed_u = 1.0; td.deltat = 1.0;
   OutDev O;
   O.jac = mass; O.res = diag; O.accumulate = accumulate ? 1 : 0; O.diag_one = 1;
   if (!D->zero.p) {
@@ -305,7 +305,7 @@ const char* gen_apply_mass(GeneralPlanDev* D, const GeneralPlanHost& H, const Ge
                            void* stream, GenLaunchStats* stats) {
   TimeDev td;
   std::memset(&td, 0, sizeof(td));
-  td.alpha_u = 1.0; td.deltat = 1.0;
+  td.alpha_u = 1.0; td.seed_u = 1.0; td.deltat = 1.0;
   OutDev O;
   O.jac = nullptr; O.res = y; O.accumulate = accumulate ? 1 : 0; O.diag_one = 1;
   return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, x, td, true, false, stream, stats, 3, mass_wts);
@@ -316,7 +316,7 @@ const char* gen_project_initial(GeneralPlanDev* D, const GeneralPlanHost& H, con
                                 GenLaunchStats* stats) {
   TimeDev td;
   std::memset(&td, 0, sizeof(td));
-  td.alpha_u = 1.0; td.deltat = 1.0; td.time = time;
+  td.alpha_u = 1.0; td.seed_u = 1.0; td.deltat = 1.0; td.time = time;
   OutDev O;
   O.jac = nullptr; O.res = rhs; O.accumulate = accumulate ? 1 : 0; O.diag_one = 1;
   const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0};

@@ -644,7 +644,7 @@ struct GenBlock {
     QpCtx c;
     make_ctx(P, sme, q, c);
     const bool transient = P.td.transient != 0;
-    const double au = transient ? P.td.alpha_u : 1.0, at = transient ? P.td.alpha_t : 0.0;
+    const double au = transient ? P.td.seed_u : 1.0, at = transient ? P.td.seed_t : 0.0;   // derivative seeds (TimeDev)
     Dual<KK> F[NVAR][NC], Ft[NVAR][NC];
     for (int v = 0; v < NVAR; ++v)
       for (int k = 0; k < NC; ++k) {
@@ -756,7 +756,7 @@ struct GenBlock {
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) acc[r][kk] = 0.0;
     const bool transient = P.td.transient != 0;
-    const double au = transient ? P.td.alpha_u : 1.0, at = transient ? P.td.alpha_t : 0.0;
+    const double au = transient ? P.td.seed_u : 1.0, at = transient ? P.td.seed_t : 0.0;   // derivative seeds (TimeDev)
     for (int q = 0; q < NQ; ++q) {
       QpCtx c;
       make_ctx(P, sme, q, c);
@@ -824,7 +824,7 @@ struct GenBlock {
     QpCtx c;
     make_ctx(P, sme, q, c);
     const bool transient = P.td.transient != 0;
-    const double au = transient ? P.td.alpha_u : 1.0, at = transient ? P.td.alpha_t : 0.0;
+    const double au = transient ? P.td.seed_u : 1.0, at = transient ? P.td.seed_t : 0.0;   // derivative seeds (TimeDev)
     Dual<1> F[NVAR][NC], Ft[NVAR][NC], Cf[NVAR][NC];
 #pragma unroll
     for (int v = 0; v < NVAR; ++v)

@@ -146,7 +146,9 @@ constexpr int MAX_STAGE = 4;  // Butcher stages
 struct TimeDev {
   int transient;
   int nprev, nstage_lo;          // previous steps used, stages below the current one
-  double alpha_u, alpha_t;       // du/d(dof), du_t/d(dof)
+  double alpha_u, alpha_t;       // weights of the stage solution in the evaluation point: u = alpha_u s + ..., u_t = alpha_t s + ...
+  double seed_u, seed_t;         // du/d(seeded dof), du_t/d(seeded dof): (alpha_u, alpha_t) when the stage solution is seeded, the chain-rule
+                                 // factors of a previous step / stage otherwise (mrhyde_b200_time::seed_what)
   double one_minus_alpha_u;
   double timewt;                 // 1 / (dt b_s)
   double bdf[MAX_PREV + 1];      // BDF weights 1..nprev (index 0 unused)

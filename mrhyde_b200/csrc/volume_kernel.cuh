@@ -332,7 +332,7 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
 #pragma unroll
       for (int g = 0; g < NGU; ++g) k += G[g] * MRH_LTAB(Stab)[g][jit_tab::rep[c]];
       kc[c] = k; mc[c] = 0.0;
-      if (MRH_TRANSIENT(td)) { mc[c] = md * MRH_LTAB(Mtab)[jit_tab::rep[c]]; k = td.alpha_u * k + td.alpha_t * mc[c]; }
+      if (MRH_TRANSIENT(td)) { mc[c] = md * MRH_LTAB(Mtab)[jit_tab::rep[c]]; k = td.seed_u * k + td.seed_t * mc[c]; }
 #ifdef MRH_JIT_PIPE
       kreg[c] = k;
 #else
@@ -363,7 +363,7 @@ __device__ __forceinline__ void thermal_affine(const ThermalParams<DIM>& P, cons
         const double mm = md * MRH_CTAB(Mtab)[t];
         r[i] += mm * ut[j];
         if (j != i) r[j] += mm * ut[i];
-        k = td.alpha_u * k + td.alpha_t * mm;
+        k = td.seed_u * k + td.seed_t * mm;
       }
       st[t * cap] = k;
     }
@@ -576,9 +576,9 @@ __device__ __forceinline__ void thermal_element(const ThermalParams<DIM>& P, con
 #pragma unroll
         for (int j = 0; j < NV; ++j) Tt += ut[j] * MRH_CTAB(phi)[q][j];
         lin += rc * Tt * wd;
-        mw = td.alpha_t * rc * wd;
+        mw = td.seed_t * rc * wd;
       }
-      const double kw = td.alpha_u * kap * wd;
+      const double kw = td.seed_u * kap * wd;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         double s = lin * MRH_CTAB(phi)[q][i];
@@ -1060,7 +1060,7 @@ __device__ __forceinline__ void thermal_chain(const ThermalParams<DIM>& P) {
   const int slot_doubles = cap * (MRH_STAGE_K(S::NT) + S::NV);
   double* wbuf = ring + ((2 * slot_doubles + 1) & ~1) + warp * PULL_WARP_DOUBLES;   // 16-byte aligned (bulk copies read it)
 #endif
-  const double au = P.td.alpha_u, at = P.td.alpha_t;
+  const double au = P.td.seed_u, at = P.td.seed_t;   // derivative seeds: J = au dR/du + at dR/du_t
 #ifdef MRH_JIT_MODE
   constexpr int mode = MRH_JIT_MODE;   // output mode of this build: 1 res | 2 jac | 4 accumulate (the host picks the build)
 #else

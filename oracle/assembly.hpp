@@ -81,6 +81,7 @@ class AssemblyManager {
   bool assemble_volume_terms = true, assemble_boundary_terms = true, use_strong_DBCs = true;
   bool lump_mass = false;    // Solver: lump mass (assemblyManager_construct.hpp:36): the fused scatter sends every entry of a row to its diagonal
   std::vector<int> point_dofs;   // disc->point_dofs (local ids): dofConstraints replaces their whole Jacobian row by the identity row
+  int seedwhat = 1, seedindex = 0;   // compute_previous_jac: seedwhat = 2, seedindex = stepindex (assemblyManager_jacres.hpp:176-190); 3: a previous stage
   bool fix_zero_rows = false;   // Solver: fix zero rows (assemblyManager_construct.hpp:33)
   bool useadjoint = false;   // assembleJacRes(..., useadjoint, ...): transposed local Jacobians (updateJac, assemblyManager_jacres.hpp:1459-1475)
   TimeData td;
@@ -261,7 +262,7 @@ struct Engine : EngineBase {
   void seed(AssemblyManager& am, bool doseed) {
     if (wkset.isTransient)
       wkset.computeSolnTransientSeeded(gsol, gsol_prev, gsol_stage, am.maxdof, std::max(1, (int)am.td.BDF_wts.size() - 1),
-                                       std::max(1, am.td.nstages()), doseed ? 1 : 0);
+                                       std::max(1, am.td.nstages()), doseed ? am.seedwhat : 0, am.seedindex);
     else
       wkset.computeSolnSteadySeeded(gsol, am.maxdof, doseed ? 1 : 0);
   }

@@ -170,6 +170,12 @@ int oracle_set_time(void* hv, int isTransient, double time, double deltat, int s
   return 0;
 }
 
+int oracle_set_seeding(void* hv, int seedwhat, int seedindex) {
+  ((OracleHandle*)hv)->am->seedwhat = seedwhat;
+  ((OracleHandle*)hv)->am->seedindex = seedindex;
+  return 0;
+}
+
 int oracle_set_point_dofs(void* hv, int n, const int* dofs) {
   ((OracleHandle*)hv)->am->point_dofs.assign(dofs, dofs + n);
   return 0;

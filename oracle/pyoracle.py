@@ -172,6 +172,11 @@ class OracleProblem:
         self.L.oracle_set_time(self.h, int(transient), C.c_double(time), C.c_double(dt), int(stage), len(b),
                                _p(A, C.c_double), _p(b, C.c_double), _p(c, C.c_double), len(bdf), _p(bdf, C.c_double))
 
+    def set_seeding(self, seedwhat=1, seedindex=0):
+        """What the Jacobian differentiates with respect to: 1 the stage solution (default), 2 previous step `seedindex`
+        (compute_previous_jac, assemblyManager_jacres.hpp:176-190), 3 previous stage `seedindex` (workset.cpp:727-785)."""
+        self.L.oracle_set_seeding(self.h, int(seedwhat), int(seedindex))
+
     def set_point_dofs(self, dofs):
         """disc->point_dofs: dofConstraints turns their Jacobian rows into identity rows (assemblyManager_constraints.hpp:97-116, 261-266)."""
         d = np.ascontiguousarray(dofs, dtype=np.int32)

@@ -6,7 +6,7 @@
 //   SolutionField label parsing                      src/tools/fields.hpp:44-128
 //   resetResidual                                    src/tools/workset.cpp:497-528
 //   computeSolnSteadySeeded                          src/tools/workset.cpp:864-901
-//   computeSolnTransientSeeded (seedwhat 0/1)        src/tools/workset.cpp:600-834
+//   computeSolnTransientSeeded (seedwhat 0/1/2/3)    src/tools/workset.cpp:600-834
 //   evaluateSolutionField (dof-ascending sum, dof 0 assigned first)   src/tools/workset.cpp:978-1111
 //   getSolutionField / lazily allocated zero fields  src/tools/workset.cpp:1537-1650
 //   getElementSize / getSideElementSize              src/tools/workset.cpp:2699-2733
@@ -181,7 +181,8 @@ class Workset {
   }
   // u_prev (E,nvar,maxdof,nsteps), u_stage (E,nvar,maxdof,nstages)
   void computeSolnTransientSeeded(const std::vector<double>& u, const std::vector<double>& u_prev, const std::vector<double>& u_stage,
-                                  int maxdof, int nsteps, int nstages, int seedwhat) {  // workset.cpp:600-834 (seedwhat 0/1)
+                                  int maxdof, int nsteps, int nstages, int seedwhat, int index = 0) {  // workset.cpp:600-834
+    // seedwhat 1: the stage solution; 2: previous step `index` (compute_previous_jac, :669-726); 3: previous stage `index` (:727-785)
     const double dt = deltat;
     const int stage = current_stage;
     const int ns = td.nstages();
@@ -197,6 +198,27 @@ class Workset {
           const size_t base = ((size_t)elem * vars.size() + var) * maxdof + dof;
           auto cu_prev = [&](int s) { return u_prev[base * nsteps + s]; };
           auto cu_stage = [&](int s) { return u_stage[base * nstages + s]; };
+          if (seedwhat == 2 || seedwhat == 3) {
+            const double stageval = u[base];
+            EvalT u_prev_val = EvalT(cu_prev(0));
+            if (seedwhat == 2 && index == 0) u_prev_val = ADTraits<EvalT>::seed(offsets[var][dof], cu_prev(0));
+            EvalT beta_u = (1.0 - alpha_u) * u_prev_val;
+            for (int s = 0; s < stage; s++) {
+              EvalT u_stage_val = EvalT(cu_stage(s));
+              if (seedwhat == 3 && index == s) u_stage_val = ADTraits<EvalT>::seed(offsets[var][dof], cu_stage(s));
+              beta_u += b_A(stage, s) / td.butcher_b[s] * (u_stage_val - u_prev_val);
+            }
+            u_AD(elem, dof) = alpha_u * stageval + beta_u;
+            EvalT beta_t = EvalT(0.0);
+            for (size_t s = 1; s < td.BDF_wts.size(); s++) {
+              EvalT pv = EvalT(cu_prev((int)s - 1));
+              if (seedwhat == 2 && index == (int)s - 1) pv = ADTraits<EvalT>::seed(offsets[var][dof], cu_prev((int)s - 1));
+              beta_t += td.BDF_wts[s] * pv;
+            }
+            beta_t *= timewt;
+            u_dot_AD(elem, dof) = alpha_t * stageval + beta_t;
+            continue;
+          }
           EvalT stageval = (seedwhat == 1) ? ADTraits<EvalT>::seed(offsets[var][dof], u[base]) : EvalT(u[base]);
           double beta_u = (1.0 - alpha_u) * cu_prev(0);
           for (int s = 0; s < stage; s++) beta_u += b_A(stage, s) / td.butcher_b[s] * (cu_stage(s) - cu_prev(0));

@@ -286,3 +286,31 @@ def test_fix_zero_rows_gives_unit_diagonal(oracle_lib, product_lib):
     for J in (jac_ref, jac):
         A = op.csr(J)
         assert abs(A - sp.identity(op.num_dofs)).max() == 0.0
+
+
+@pytest.mark.parametrize("seed_what,seed_index", [(2, 0), (2, 1), (3, 0)], ids=["prev-step-0", "prev-step-1", "prev-stage-0"])
+@pytest.mark.parametrize("name", ["thermal3d-advection", "ns2d-bwe", "maxwell-abc-bwe", "thermoelastic2d"])
+def test_previous_step_and_stage_jacobians(oracle_lib, product_lib, name, seed_what, seed_index):
+    """compute_previous_jac (seedwhat = 2, seedindex = stepindex: assemblyManager_jacres.hpp:176-190) and the previous-stage seeding
+    (workset.cpp:727-785): the Jacobian with respect to sol_prev[index] / sol_stage[index], same residual, same evaluation point.
+    Second stage of a two-stage DIRK tableau with BDF-2 weights so that every branch of the seeding has something to differentiate."""
+    cfg = [c for c in configs.general_cases() if c[0] == name][0][1]
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1, options={"kernel": "general"})
+    rng = np.random.default_rng(11)
+    u = helpers.manufactured_state(op)
+    prev = [0.1 * rng.standard_normal(op.num_dofs) for _ in range(2)]
+    stg = [0.1 * rng.standard_normal(op.num_dofs) for _ in range(2)]
+    A, b, c, bdf = ((0.25, 0.0), (0.5, 0.25)), (0.5, 0.5), (0.25, 0.75), (1.5, -2.0, 0.5)
+    op.set_time(True, time=0.3, dt=0.01, stage=1, A=A, b=b, c=c, bdf=bdf)
+    op.set_seeding(seed_what, seed_index)
+    res_ref, jac_ref = op.assemble_jacres(u, sol_prev=prev, sol_stage=stg)
+    op.set_seeding(1, 0)
+    res_1, jac_1 = op.assemble_jacres(u, sol_prev=prev, sol_stage=stg)
+    op.set_time(False)
+    assert helpers.rel_err_vec(res_ref, res_1) < 1e-14 and not np.allclose(jac_ref, jac_1)   # same residual, another derivative
+    ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=1, A=A, b=b, c=c, bdf=bdf, sol_prev=prev, sol_stage=stg, seed_what=seed_what, seed_index=seed_index)
+    res, jac = np.zeros(op.num_dofs), np.zeros(op.nnz)
+    plan.debug_emulate(u, res, jac, time=ts)
+    assert helpers.rel_err_vec(res, res_ref) < TOL
+    assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL

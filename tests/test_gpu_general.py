@@ -218,6 +218,34 @@ def test_set_initial_reproduces_reference_gold(oracle_lib, product_lib):
         assert abs(got - gold[f]) <= 0.5e-5 * gold[f], (f, got, gold[f])
 
 
+@pytest.mark.parametrize("seed_what,seed_index", [(2, 0), (2, 1), (3, 0)], ids=["prev-step-0", "prev-step-1", "prev-stage-0"])
+@pytest.mark.parametrize("name,kernel", [("thermal3d-sweep", "sweep"), ("thermal3d-sweep", "general"), ("ns2d-bwe", "general"), ("maxwell-abc-bwe", "general")])
+def test_previous_step_and_stage_jacobians(oracle_lib, product_lib, name, kernel, seed_what, seed_index):
+    """compute_previous_jac (seedwhat = 2, seedindex = stepindex: assemblyManager_jacres.hpp:176-190) and the previous-stage seeding
+    (workset.cpp:727-785) on the GPU, sweep kernel and general path: Jacobian with respect to sol_prev[index] / sol_stage[index]."""
+    if name == "thermal3d-sweep":
+        cfg = configs.variant(configs.THERMAL_3D, **{"Mesh/NX": 7, "Mesh/NY": 6, "Mesh/NZ": 5, "Functions/density": "2.0", "Functions/specific heat": "1.5"})
+    else:
+        cfg = [c for c in configs.general_cases() if c[0] == name][0][1]
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, options={"kernel": kernel})
+    rng = np.random.default_rng(11)
+    u = helpers.manufactured_state(op)
+    prev = [0.1 * rng.standard_normal(op.num_dofs) for _ in range(2)]
+    stg = [0.1 * rng.standard_normal(op.num_dofs) for _ in range(2)]
+    A, b, c, bdf = ((0.25, 0.0), (0.5, 0.25)), (0.5, 0.5), (0.25, 0.75), (1.5, -2.0, 0.5)
+    op.set_time(True, time=0.3, dt=0.01, stage=1, A=A, b=b, c=c, bdf=bdf)
+    op.set_seeding(seed_what, seed_index)
+    res_ref, jac_ref = op.assemble_jacres(u, sol_prev=prev, sol_stage=stg)
+    op.set_seeding(1, 0)
+    op.set_time(False)
+    ts = helpers.TimeSpec(time=0.3, deltat=0.01, stage=1, A=A, b=b, c=c, bdf=bdf, sol_prev=[_dev(v) for v in prev], sol_stage=[_dev(v) for v in stg],
+                          seed_what=seed_what, seed_index=seed_index)
+    res, jac = _assemble(plan, op, u, ts)
+    assert helpers.rel_err_vec(res, res_ref) < TOL
+    assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL
+
+
 def test_thermoelastic_gold_through_cuda_path(oracle_lib, product_lib):
     """regression/thermoelastic/2D_transient (block "thermal, linearelasticity") assembled on the GPU: the reference's printed L2 norms of T."""
     from test_oracle_golden import _thermoelastic_steps
