@@ -222,6 +222,11 @@ int mrhyde_b200_plan_comm_init(mrhyde_b200_plan* plan, const uint8_t* id128, int
  * need so that the summed row is complete (the column map of the owned Tpetra matrix J that
  * exportMatrixFromOverlapped fills).  n_cols >= n_rows.  Collective over the communicator. */
 int mrhyde_b200_plan_set_halo(mrhyde_b200_plan* plan, int64_t n_cols, const int64_t* col_gids /*host [n_cols]*/);
+/* Deviation on strong-Dirichlet rows that sit on a partition interface: the library writes J(d,d) = 1 on the OWNED copy only, ghost
+ * copies of fixed rows stay zero, so after halo_sum the diagonal is 1.  The reference calls replaceLocalValues on every overlapped
+ * dbc dof (assemblyManager_constraints.hpp:125-138), and its Export(ADD) therefore leaves the sharing multiplicity (2, 4, ...) on such
+ * diagonals.  Residual entries of fixed rows are 0 in both, so the Newton update of those dofs is 0 either way.  Point-constrained
+ * rows (plan_set_point_dofs) DO follow the reference: every rank that holds the row sets the identity row before the sum. */
 int mrhyde_b200_halo_sum(mrhyde_b200_plan* plan, double* res, double* jac_values, void* stream);
 /* The OWNED matrix after halo_sum, i.e. what the reference obtains with fillComplete(J_over) -> Export(ADD) -> fillComplete(J)
  * (solverManager_solvers.hpp:463-466, linearAlgebraInterface_matrix.hpp:233-237), needs no compaction pass here: owned rows come
