@@ -2379,7 +2379,7 @@ int mrhyde_b200_apply_mass(mrhyde_b200_plan* P, const double* mass_wts, const do
 
 int mrhyde_b200_project_initial(mrhyde_b200_plan* P, double time, double* rhs, void* stream) {
   ABI_BEGIN
-  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0};
+  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0, 1.0};
   check_mass_plan(P, ones);
   if (P->device == -1) fail(MRHYDE_B200_ERR_STATE, "host-only analysis plan (device = -1) cannot assemble: there is no CPU path");
   if (!rhs) fail(MRHYDE_B200_ERR_INVALID, "project_initial: null vector");
@@ -2395,7 +2395,7 @@ int mrhyde_b200_project_initial(mrhyde_b200_plan* P, double time, double* rhs, v
 
 int mrhyde_b200_plan_debug_emulate_initial(mrhyde_b200_plan* P, double time, double* rhs) {
   ABI_BEGIN
-  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0};
+  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0, 1.0};
   check_mass_plan(P, ones);
   if (P->device != -1) fail(MRHYDE_B200_ERR_STATE, "debug_emulate_initial: only host-only analysis plans (device = -1) replay the kernel stages on the host");
   if (!rhs) fail(MRHYDE_B200_ERR_INVALID, "debug_emulate_initial: null vector");

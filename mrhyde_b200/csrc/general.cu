@@ -319,7 +319,7 @@ const char* gen_project_initial(GeneralPlanDev* D, const GeneralPlanHost& H, con
   td.alpha_u = 1.0; td.seed_u = 1.0; td.deltat = 1.0; td.time = time;
   OutDev O;
   O.jac = nullptr; O.res = rhs; O.accumulate = accumulate ? 1 : 0; O.diag_one = 1;
-  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0};
+  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0, 1.0};
   return gen_run(D, H, kd, vx, vy, vz, conn, lids, G, O, rhs /* state is not read in this mode: any valid vector */, td, true, false, stream, stats, 4, ones);
 }
 

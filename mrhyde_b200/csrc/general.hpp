@@ -56,8 +56,8 @@ struct GenSideFamily {      // one boundary group: (sideset, local side) with it
   int64_t inst_base = 0;               // scratch instance of items[0]
   std::vector<double> geo_N, geo_dN, ref_tab, qwts;
   double tan_u[3] = {0, 0, 0}, tan_v[3] = {0, 0, 0};
-  int32_t bc_type[GEN_MAXVARS] = {0, 0, 0, 0};
-  int32_t bc_fn[GEN_MAXVARS] = {-1, -1, -1, -1};
+  int32_t bc_type[GEN_MAXVARS] = {0, 0, 0, 0, 0};
+  int32_t bc_fn[GEN_MAXVARS] = {-1, -1, -1, -1, -1};
   GenFnRec fn[GEN_MAXFN];              // module functions at side ip, then the boundary data of each variable
   bool active = false;                 // some variable has a Neumann / weak Dirichlet condition here
 };

@@ -17,6 +17,7 @@ typedef NavierStokesPhys<3, 1> GenNs31;
 typedef ThermalElasticityPhys<2, 1> GenThLe21;
 typedef ThermalElasticityPhys<3, 1> GenThLe31;
 typedef NavierStokesThermalPhys<2, 1> GenNsTh21;
+typedef NavierStokesThermalPhys<3, 1> GenNsTh31;
 }  // namespace mrhyde_b200
 
 // X(physics name, dim, order, NQ, NQS, K, Phys, MAXT, MINB, MAXT_L, MINB_L): launch bounds (threads per CTA at most, CTAs per SM at
@@ -41,7 +42,8 @@ typedef NavierStokesThermalPhys<2, 1> GenNsTh21;
 #define MRH_GEN_LIST_3(X)                                                   \
   X("thermal+linearelasticity", 2, 1, 4, 2, 1, GenThLe21, 256, 3, 256, 3)   \
   X("thermal+linearelasticity", 3, 1, 8, 4, 1, GenThLe31, 256, 2, 256, 2)   \
-  X("navier stokes+thermal", 2, 1, 4, 2, 1, GenNsTh21, 256, 2, 256, 2)
+  X("navier stokes+thermal", 2, 1, 4, 2, 1, GenNsTh21, 256, 2, 256, 2)      \
+  X("navier stokes+thermal", 3, 1, 8, 4, 1, GenNsTh31, 256, 2, 128, 3)
 #define MRH_GEN_LIST(X) MRH_GEN_LIST_0(X) MRH_GEN_LIST_1(X) MRH_GEN_LIST_2(X) MRH_GEN_LIST_3(X)
 
 namespace mrhyde_b200 {

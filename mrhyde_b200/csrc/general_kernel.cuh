@@ -97,7 +97,7 @@ MRH_HD void mrh_ldn(const double* __restrict__ p, double* __restrict__ o) {
 }
 
 // ---- launch parameters --------------------------------------------------------------------------------------
-constexpr int GEN_MAXVARS = 4;
+constexpr int GEN_MAXVARS = 5;   // navier stokes + thermal in 3-D: ux, pr, uy, uz, T
 constexpr int GEN_MAXFN = 20;   // two-module blocks: 14 module functions + 4 boundary data
 constexpr int GEN_MAXDOF = 96;
 enum GenBasisType : int32_t { BT_HGRAD = 0, BT_HCURL = 1, BT_HDIV = 2, BT_HVOL = 3 };
@@ -361,7 +361,7 @@ MRH_HD void gen_initial_point(const QpCtx& c, T (&Cf)[Phys::NVAR][Phys::NC]) {
 // ---- shared-memory layout of one element (offsets in doubles; every block is a multiple of 2 doubles) ---------
 template <class Phys, int NQ, bool WITH_D = false>   // WITH_D: the tensor-core build's D region (requested for single-basis layouts only)
 struct GenLayout {
-  static constexpr int DIM = Phys::DIM, NV = 1 << DIM, NVAR = Phys::NVAR, NC = Phys::NC, NFN = Phys::NFN + GEN_MAXVARS;
+  static constexpr int DIM = Phys::DIM, NV = 1 << DIM, NVAR = Phys::NVAR, NC = Phys::NC, NFN = Phys::NFN + (Phys::NVAR > 4 ? Phys::NVAR : 4);   // function slots per point: the module's functions + boundary data per variable
   static constexpr int N = Phys::N;
   static constexpr int GEO = 28;   // w, x y z, Jinv[9], J[9], det, pad, n[3], pad
   static MRH_CE int even(int x) { return (x + 1) & ~1; }
@@ -568,8 +568,10 @@ struct GenBlock {
       case 0: s3_var<0>(P, sme, q); break;
       case 1: s3_var<(NVAR > 1 ? 1 : 0)>(P, sme, q); break;
       case 2: s3_var<(NVAR > 2 ? 2 : 0)>(P, sme, q); break;
-      default: s3_var<(NVAR > 3 ? 3 : 0)>(P, sme, q); break;
+      case 3: s3_var<(NVAR > 3 ? 3 : 0)>(P, sme, q); break;
+      default: s3_var<(NVAR > 4 ? 4 : 0)>(P, sme, q); break;
     }
+    static_assert(NVAR <= 5, "per-variable dispatch is written out for up to five variables");
   }
   // variables of the expression evaluator at a point: x y z t n[x] n[y] n[z], then (plans with state-dependent coefficients) the
   // solution fields F[v][k] and their time derivatives Ft[v][k] (slots of FunctionSet::set_solution_slots, abi.cu)
@@ -713,6 +715,7 @@ struct GenBlock {
     if (NVAR > 1) store_var<(NVAR > 1 ? 1 : 0)>(P, out, col, acc, kk);
     if (NVAR > 2) store_var<(NVAR > 2 ? 2 : 0)>(P, out, col, acc, kk);
     if (NVAR > 3) store_var<(NVAR > 3 ? 3 : 0)>(P, out, col, acc, kk);
+    if (NVAR > 4) store_var<(NVAR > 4 ? 4 : 0)>(P, out, col, acc, kk);
   }
   template <int V>
   MRH_HD static void rows_var(const double* __restrict__ pbase, int q, const Dual<K> (&Cf)[NVAR][NC], double (&acc)[N][K]) {
@@ -734,6 +737,7 @@ struct GenBlock {
     if (NVAR > 1) rows_var<(NVAR > 1 ? 1 : 0)>(pbase, q, Cf, acc);
     if (NVAR > 2) rows_var<(NVAR > 2 ? 2 : 0)>(pbase, q, Cf, acc);
     if (NVAR > 3) rows_var<(NVAR > 3 ? 3 : 0)>(pbase, q, Cf, acc);
+    if (NVAR > 4) rows_var<(NVAR > 4 ? 4 : 0)>(pbase, q, Cf, acc);
   }
   MRH_HD static void s4b(const GenParams& P, double* sm, int blk, int idx) {
     if (idx >= P.epb * TPE) return;

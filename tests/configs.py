@@ -123,6 +123,14 @@ NS_THERMAL_2D = {
     "Discretization": {"order": {"ux": 1, "pr": 1, "uy": 1, "T": 1}, "quadrature": 2},
     "Solver": {"solver": "steady-state"},
 }
+NS_THERMAL_3D = {
+    "Mesh": {"dimension": 3, "NX": 4, "NY": 3, "NZ": 3, "perturb": 0.02},
+    "Physics": {"modules": "navier stokes, thermal", "useSUPG": True, "usePSPG": True,
+                "Dirichlet conditions": {"ux": {"all boundaries": "0.0"}, "uy": {"all boundaries": "0.0"}, "uz": {"all boundaries": "0.0"}, "T": {"left": "1.0", "right": "0.0"}}},
+    "Functions": {"source ux": "1.0", "source uz": "x", "thermal source": "x+y*z", "thermal diffusion": "0.2", "specific heat": "1.1", "density": "1.3"},
+    "Discretization": {"order": {"ux": 1, "pr": 1, "uy": 1, "uz": 1, "T": 1}, "quadrature": 2},
+    "Solver": {"solver": "steady-state"},
+}
 NS_THERMAL_2D_WEAK = {"Solver/use strong DBCs": False,
                       "Physics/Dirichlet conditions": {"ux": {"left": "1.0"}, "uy": {"left": "0.0"}, "T": {"left": "1.0+y", "top": "x*x"}},
                       "Physics/Neumann conditions": {"ux": {"right": "0.3"}, "uy": {"right": "y"}, "T": {"right": "2.0*y-0.3"}}}
@@ -187,6 +195,9 @@ def general_cases():
         ("ns-thermal2d", NS_THERMAL_2D, {}, None, False),
         ("ns-thermal2d-bwe", NS_THERMAL_2D, {}, BWE, False),
         ("ns-thermal2d-weak", variant(NS_THERMAL_2D, **NS_THERMAL_2D_WEAK), {}, None, False),
+        ("ns-thermal3d", NS_THERMAL_3D, {}, None, False),
+        ("ns-thermal3d-dirk", NS_THERMAL_3D, {}, DIRK12, False),
+        ("ns-thermal3d-neumann", variant(NS_THERMAL_3D, **dict(NS_3D_NEUMANN, **{"Physics/Neumann conditions": {"ux": {"right": "0.3"}, "uy": {"right": "y"}, "uz": {"top": "1.0"}, "T": {"top": "0.5*x"}}})), {}, None, False),
         ("ns-thermal2d-state", variant(NS_THERMAL_2D, **{"Functions/thermal diffusion": "0.2+0.1*T*T", "Functions/viscosity": "0.5+0.1*T"}), {}, None, False),
         ("thermal2d-weak-state", variant(THERMAL_2D, **dict(THERMAL_WEAK, **{"Functions/thermal diffusion": "1.0+0.5*T*T"})), {}, None, False),
     ]
