@@ -135,7 +135,16 @@ int mrhyde_b200_plan_set_function(mrhyde_b200_plan* plan, const char* name, cons
  *   "column elements", "min chains", "min segment levels", "sweep axis", "threads", "cta slots", "max blocks", "min blocks",
  *   "max registers", "pull patterns", "pull group", "flush", "flush unroll", "stage1", "stage2", "stagger ns"
  *                    sweep-plan / specialised-build tuning (defaults are the measured best)
- *   "debug skip"     timing experiments only (parts of the specialised kernel compiled out; results are then wrong)
+ *   "lump mass"      = Solver: lump mass -- the fused scatter adds every entry of a row to its diagonal (assemblyManager_scatter.hpp:263-268;
+ *                      general path; a thermal plan that asks for it leaves the sweep kernel)
+ *   "fix zero rows"  = Solver: fix zero rows -- after the constraints, rows with sum |J(row,:)| < 1e-14 get a unit diagonal (assemblyManager_jacres.hpp:609-626)
+ *   "jacobian"       = "auto" | "lanes" | "tensor": derivative-lane or FP64 tensor-core (mma.m8n8k4.f64) build of the general path's Jacobian stage
+ *   "scratch GB"     = budget of the general path's element scratch ring (default: a quarter of the free device memory)
+ *   "halo transport" = "auto" | "p2p" | "nccl";  "halo push" = in-kernel push of ghost rows into the owner's slab (default true);  "overlap halo"
+ *   "prefetch" = true | false | lean, "prefetch records", "column cache" = true | false | registers, "pipeline", "store hint"
+ *                    further sweep-kernel build options (each was measured; defaults are the measured best)
+ *   "debug skip", "debug transient", "debug mode"   kernel-debugging keys, accepted only with MRHYDE_B200_DEBUG_OPTIONS=1 in the environment
+ *                    ("debug skip" compiles parts of the specialised kernel out: results are then wrong)
  * Unknown keys are an error, never silently ignored. */
 int mrhyde_b200_plan_set_option(mrhyde_b200_plan* plan, const char* key, const char* value);
 
