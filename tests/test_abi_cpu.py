@@ -387,3 +387,38 @@ def test_column_cache_flags(product_lib):
     assert bent.plan.stat("column_cache_axes") == 0 and bent.plan.stat("n_invariant_chains") == 0
     x_sweep = ThermalBrick(3, [12, 10, 9], device=-1, options={"column elements": 16, "min segment levels": 2, "sweep axis": 0})
     assert x_sweep.plan.stat("column_cache_axes") == 6 and x_sweep.plan.stat("step_shared_axes") == 1
+
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _build_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "host_assemble")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "host_assemble.cpp"),
+                           "-L", os.path.join(root, "mrhyde_b200"), "-lmrhyde_b200", "-Wl,-rpath," + os.path.join(root, "mrhyde_b200"), "-o", exe])
+    return exe
+
+
+def test_header_is_valid_c_and_cpp(tmp_path, product_lib):
+    """include/mrhyde_b200.h is the boundary a C++ (or C) host binds to: it must compile on its own in both languages."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    src = tmp_path / "inc.c"
+    src.write_text('#include "mrhyde_b200.h"\nint main(void) { return mrhyde_b200_version() == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", os.path.join(root, "include"), str(src)])
+
+
+def test_cpp_host_example_runs_against_the_library(tmp_path, product_lib):
+    """examples/host_assemble.cpp drives the C ABI from C++ with no Python in between; without a GPU it builds the host-only plan and a
+    device plan fails loudly (no CPU path)."""
+    import subprocess
+    exe = _build_example(tmp_path)
+    out = subprocess.run([exe, "8", "-1"], capture_output=True, text=True)
+    assert out.returncode == 0 and "64 elements, 81 rows, 625 non-zeros" in out.stdout and "host-only plan" in out.stdout
+    import torch
+    if not torch.cuda.is_available():
+        bad = subprocess.run([exe, "8", "0"], capture_output=True, text=True)
+        assert bad.returncode != 0 and "no CPU path" in bad.stderr
