@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrhyde_b200.so")
+# MRHYDE_B200_LIB: an alternative build of the same library (tools/asan_check.sh points it at an AddressSanitizer build)
+LIB_PATH = os.environ.get("MRHYDE_B200_LIB") or os.path.join(_HERE, "libmrhyde_b200.so")
 _LIB = None
 _EMU = None
 

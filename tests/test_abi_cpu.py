@@ -86,8 +86,9 @@ def test_argument_validation(oracle_lib, product_lib):
     with pytest.raises(product_lib.MrhydeB200Error):
         q.finalize()
     with pytest.raises(product_lib.MrhydeB200Error) as ei:
-        product_lib.AssemblyPlan("maxwell", 3, ["E"], [0], [dict(type="HGRAD", order=1, card=4, val=rb["val"], grad=rb["grad"])], 4,
-                                 op.offsets, op.qpts, op.qwts, device=-1).finalize()
+        # (arrays sized for the 3-D descriptor they are passed with: the library reads nqp * dim coordinates)
+        product_lib.AssemblyPlan("maxwell", 3, ["E"], [0], [dict(type="HGRAD", order=1, card=4, val=rb["val"], grad=np.zeros((4, len(op.qwts), 3)))], 4,
+                                 op.offsets, np.zeros((len(op.qwts), 3)), op.qwts, device=-1).finalize()
     assert ei.value.code in (product_lib.ERR_STATE, product_lib.ERR_UNSUPPORTED)
 
 
