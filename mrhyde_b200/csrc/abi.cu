@@ -2160,6 +2160,16 @@ int mrhyde_b200_plan_stat(mrhyde_b200_plan* P, const char* key, int64_t* value) 
   else if (k == "n_early_chains") *value = P->cp.n_early_chains;
   else if (k == "column_cache_axes") *value = column_cache_axes(P) & 7;
   else if (k == "step_shared_axes") *value = (column_cache_axes(P) >> 4) & 7;   // axes whose sub-expressions one warp evaluates for the whole CTA   // axes whose one-coordinate source sub-expressions a thread keeps along its chain
+  else if (k == "plan_hash") {   // FNV-1a over every array of the sweep plan: two builds that agree here launch the same schedule
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+    const ChainPlan& c = P->cp;
+    auto vec = [&](const auto& v) { if (!v.empty()) mix(v.data(), v.size() * sizeof(v[0])); };
+    vec(c.chain_step_ptr); vec(c.steps); vec(c.step_elems); vec(c.step_conn); vec(c.step_lids); vec(c.step_eclass); vec(c.batches); vec(c.rows);
+    vec(c.desc[0]); vec(c.desc[1]); vec(c.mdesc[0]); vec(c.mdesc[1]); vec(c.orphan_rows); vec(c.ghost_patterns); vec(c.chain_invariant);
+    mix(&c.cap, sizeof(c.cap)); mix(&c.n_early_chains, sizeof(c.n_early_chains));
+    *value = (int64_t)(h >> 1);
+  }
   else if (k == "n_invariant_chains") { int64_t n = 0; for (uint8_t f : P->cp.chain_invariant) n += f != 0; *value = n; }
   else if (k == "class_ring") *value = P->class_nc;
   else if (k == "stage_len") *value = P->stage_len;

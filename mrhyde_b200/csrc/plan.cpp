@@ -4,6 +4,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -134,6 +137,18 @@ struct ChainWork {  // per-chain scratch produced in parallel, concatenated afte
 
 }  // namespace
 
+// MRHYDE_B200_PLAN_TIMING=1: wall time of the plan builder's phases on stderr
+struct PhaseTimer {
+  bool on = std::getenv("MRHYDE_B200_PLAN_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[mrhyde_b200 plan] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, const std::vector<uint16_t>& rmap,
                       int stage_len, const ChainOptions& opt, ChainPlan& out) {
   const int64_t ne = m.nelem, nr = m.nrows;
@@ -141,6 +156,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
   if (ne <= 0 || nr <= 0) throw std::runtime_error("plan: empty mesh or graph");
   const int axis = (opt.sweep_axis >= 0 && opt.sweep_axis < dim) ? opt.sweep_axis : dim - 1;
 
+  PhaseTimer phase;
   // ---- row -> (element, local dof) adjacency, elements ascending
   std::vector<int64_t> r2e_ptr((size_t)nr + 1, 0);
   for (int64_t k = 0; k < ne * nd; ++k) {
@@ -162,6 +178,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       }
   }
 
+  phase.lap("row adjacency");
   // ---- element centroids and lowest coordinate along the sweep axis
   std::vector<double> cen[3], elo((size_t)ne);
   for (int d = 0; d < 3; ++d) cen[d].assign((size_t)ne, 0.0);
@@ -180,6 +197,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
   }
   const double atol = 1e-9 * std::max(amax - amin, 1e-300);
 
+  phase.lap("centroids");
   // ---- levels: breadth-first sweep over "shares a dof" adjacency, seeded at the low face of the sweep axis
   std::vector<int32_t> level((size_t)ne, -1);
   {
@@ -218,6 +236,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
   int32_t nlevels = 0;
   for (int64_t e = 0; e < ne; ++e) nlevels = std::max(nlevels, level[(size_t)e] + 1);
 
+  phase.lap("levels");
   // axis along which consecutive element ids are displaced most often (x on the reference's inline meshes)
   int fast_axis = 0;
   {
@@ -246,6 +265,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       for (int64_t e = 0; e < ne; ++e) idx[(size_t)e] = (int32_t)e;
       struct Range { int64_t b, e; };
       std::vector<Range> stack{{0, ne}};
+      std::vector<double> keys;
       const int64_t target = (int64_t)column_elems * nlevels;
       while (!stack.empty()) {
         const Range rg = stack.back();
@@ -269,19 +289,25 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
           for (int a = 0; a < na && !split; ++a) {
             const int d = axes[a];
             if (!(spread[a] > 0.0)) continue;
-            std::sort(idx.begin() + rg.b, idx.begin() + rg.e, [&](int32_t x, int32_t y) {
-              const double cx = cen[d][(size_t)x], cy = cen[d][(size_t)y];
-              return cx < cy || (cx == cy && x < y);
-            });
+            // the cut sits between two distinct coordinate values, so the two halves are {c < v} and {c >= v} for the value v right of
+            // the cut: sorting the coordinate VALUES finds v, a stable partition of the ids applies it (the ids of a range stay
+            // ascending; an indirect sort of the ids gave the same halves at several times the cost)
+            keys.resize((size_t)n);
+            for (int64_t k = 0; k < n; ++k) keys[(size_t)k] = cen[d][(size_t)idx[(size_t)(rg.b + k)]];
+            std::sort(keys.begin(), keys.end());
             const double tol = 1e-9 * spread[a];
-            const int64_t mid = rg.b + n / 2;
+            const int64_t mid = n / 2;
             int64_t cut = -1;
             for (int64_t off = 0; off < n; ++off) {  // nearest position to the median where the coordinate changes
               const int64_t c1 = mid + off, c2 = mid - off;
-              if (c1 > rg.b && c1 < rg.e && cen[d][(size_t)idx[(size_t)c1]] - cen[d][(size_t)idx[(size_t)c1 - 1]] > tol) { cut = c1; break; }
-              if (c2 > rg.b && c2 < rg.e && cen[d][(size_t)idx[(size_t)c2]] - cen[d][(size_t)idx[(size_t)c2 - 1]] > tol) { cut = c2; break; }
+              if (c1 > 0 && c1 < n && keys[(size_t)c1] - keys[(size_t)c1 - 1] > tol) { cut = c1; break; }
+              if (c2 > 0 && c2 < n && keys[(size_t)c2] - keys[(size_t)c2 - 1] > tol) { cut = c2; break; }
             }
-            if (cut > rg.b && cut < rg.e) { stack.push_back({cut, rg.e}); stack.push_back({rg.b, cut}); split = true; }
+            if (cut > 0 && cut < n) {
+              const double v = keys[(size_t)cut];
+              std::stable_partition(idx.begin() + rg.b, idx.begin() + rg.e, [&](int32_t x) { return cen[d][(size_t)x] < v; });
+              stack.push_back({rg.b + cut, rg.e}); stack.push_back({rg.b, rg.b + cut}); split = true;
+            }
           }
         }
         if (!split) {
@@ -323,6 +349,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
     const int32_t nchains = ncol * nseg;
     out.n_chains = nchains;
 
+    phase.lap("columns + segments");
     // ---- row owner: the chain of the adjacent element with the largest (level, column); row completes at that level
     std::vector<int32_t> row_chain((size_t)nr, -1), row_level((size_t)nr, -1);
     std::vector<int32_t> chain_row_ptr((size_t)nchains + 1, 0);
@@ -360,6 +387,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       for (int64_t r = 0; r < nr; ++r) if (row_chain[(size_t)r] >= 0) chain_rows[(size_t)fill[(size_t)row_chain[(size_t)r]]++] = (int32_t)r;
     }
 
+    phase.lap("row owners");
     // ---- pass 1: per-chain element lists by level (own column + halo ring), ring capacity
     const int nthreads = host_threads();
     std::vector<ChainWork> work((size_t)nchains);
@@ -403,6 +431,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
     const uint32_t slot_bytes = (uint32_t)out.slot_bytes();
     const bool metric_ok = nd <= 8 && cap <= 256;   // field widths of the metric source word
 
+    phase.lap("pass 1 (element lists)");
     // ---- pass 2: rows of every step and their gather patterns
     std::unordered_map<std::string, int32_t> pattern_ids;
     std::mutex mu;
@@ -575,6 +604,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
     out.max_rows_step = max_rows_step.load();
     out.max_batches_step = max_batches_step.load();
 
+    phase.lap("pass 2 (rows, patterns)");
     // ---- concatenate
     out.chain_step_ptr.assign((size_t)nchains + 1, 0);
     for (int32_t c = 0; c < nchains; ++c) {
@@ -613,6 +643,7 @@ void build_chain_plan(const MeshGraph& m, const std::vector<uint16_t>& kmap, con
       std::memcpy(&out.step_lids[(size_t)k * nd], &m.lids[(size_t)e * nd], sizeof(int32_t) * (size_t)nd);
       out.step_eclass[(size_t)k] = m.eclass.empty() ? 0 : m.eclass[(size_t)e];
     }
+    phase.lap("concatenate + step inputs");
     // step-invariant axes per chain (extruded columns: the sweep changes one coordinate only)
     out.chain_invariant.assign((size_t)out.n_chains, 0);
     if (nv == (1 << m.dim)) {
