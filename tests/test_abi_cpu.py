@@ -423,3 +423,12 @@ def test_cpp_host_example_runs_against_the_library(tmp_path, product_lib):
     if not torch.cuda.is_available():
         bad = subprocess.run([exe, "8", "0"], capture_output=True, text=True)
         assert bad.returncode != 0 and "no CPU path" in bad.stderr
+
+
+def test_plan_construction_is_deterministic(product_lib):
+    """The sweep plan is built by several host threads (patterns are de-duplicated under a lock); the schedule must not depend on their
+    timing: every array of the plan hashes the same over repeated builds, on a mesh with many gather patterns too."""
+    from mrhyde_b200.problems import ThermalBrick
+    for n, perturb in (([33, 17, 29], 0.05), ([20, 20, 20], 0.0)):
+        seen = {ThermalBrick(3, n, device=-1, perturb=perturb).plan.stat("plan_hash") for _ in range(3)}
+        assert len(seen) == 1
