@@ -220,6 +220,10 @@ int mrhyde_b200_apply_mass(mrhyde_b200_plan* plan, const double* mass_wts, const
  * unnamed variables start from 0.0.  The mass matrix of the projection is mrhyde_b200_assemble_mass with unit weights.  No
  * isFixedDOF check (the reference has none here); rhs: device [n_rows], follows the accumulate option; time = initial time. */
 int mrhyde_b200_project_initial(mrhyde_b200_plan* plan, double time, double* rhs, void* stream);
+/* setInitial as a whole (assemblyManager_initial.hpp:36-133): rhs as project_initial, mass_values = getMass (unit weights) summed into the
+ * graph's entries, then the routine's own fix_zero_rows loop (always on there: rows with sum |M(row,:)| < 1e-14 get a unit diagonal).
+ * Both outputs follow the accumulate option.  The lumped insertion (Solver: lump mass) is not built: ERR_UNSUPPORTED. */
+int mrhyde_b200_set_initial(mrhyde_b200_plan* plan, double time, double* rhs, double* mass_values, void* stream);
 
 /* ---- multi-GPU: the Tpetra Export(overlapped -> owned, ADD) replacement ---------------------------
  * (linearAlgebraInterface_matrix.hpp:233-237, _vector.hpp:56-66).  Ghost rows of this rank are summed

@@ -28,7 +28,7 @@ SYMBOLS = [
     "mrhyde_b200_comm_unique_id", "mrhyde_b200_plan_comm_init", "mrhyde_b200_plan_set_halo", "mrhyde_b200_halo_sum",
     "mrhyde_b200_plan_stat", "mrhyde_b200_plan_kernel_time", "mrhyde_b200_plan_eval_function",
     "mrhyde_b200_expr_disassemble", "mrhyde_b200_expr_eval_host", "mrhyde_b200_plan_debug_scatter_host", "mrhyde_b200_plan_debug_jit", "mrhyde_b200_plan_debug_metric_host", "mrhyde_b200_plan_debug_class_host", "mrhyde_b200_plan_debug_stage_map", "mrhyde_b200_plan_debug_chain_rows", "mrhyde_b200_project_initial", "mrhyde_b200_plan_debug_emulate_initial",
-    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_debug_set_emulator", "mrhyde_b200_plan_warmup", "mrhyde_b200_assemble_jacres_adjoint", "mrhyde_b200_plan_owned_extent", "mrhyde_b200_plan_set_point_dofs", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
+    "mrhyde_b200_plan_debug_emulate", "mrhyde_b200_debug_set_emulator", "mrhyde_b200_plan_warmup", "mrhyde_b200_assemble_jacres_adjoint", "mrhyde_b200_plan_owned_extent", "mrhyde_b200_plan_set_point_dofs", "mrhyde_b200_set_initial", "mrhyde_b200_assemble_mass", "mrhyde_b200_plan_debug_emulate_mass",
     "mrhyde_b200_apply_mass", "mrhyde_b200_plan_debug_emulate_apply_mass",
 ]
 
@@ -111,6 +111,7 @@ def lib():
         L.mrhyde_b200_plan_debug_scatter_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_jit.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.mrhyde_b200_project_initial.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        L.mrhyde_b200_set_initial.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrhyde_b200_plan_debug_emulate_initial.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.mrhyde_b200_plan_debug_chain_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.mrhyde_b200_plan_debug_stage_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -416,6 +417,10 @@ class AssemblyPlan:
     def project_initial(self, rhs, time=0.0, stream=0):
         """setInitial: rhs (+)= sum_q initial(x_q) phi_i w (device vector); functions "initial <var>[...]" come from set_function."""
         self._chk(self.L.mrhyde_b200_project_initial(self.h, float(time), _ptr(rhs), C.c_void_p(stream)))
+
+    def set_initial(self, rhs, mass_values, time=0.0, stream=0):
+        """setInitial as a whole: projection right-hand side, unit-weight mass matrix, the routine's own fix_zero_rows pass (device buffers)."""
+        self._chk(self.L.mrhyde_b200_set_initial(self.h, float(time), _ptr(rhs), _ptr(mass_values), C.c_void_p(stream)))
 
     def debug_emulate_initial(self, rhs, time=0.0):
         """Host replay of project_initial on a host-only plan (debugging aid, never an assembly path)."""

@@ -2403,6 +2403,29 @@ int mrhyde_b200_project_initial(mrhyde_b200_plan* P, double time, double* rhs, v
   ABI_END
 }
 
+int mrhyde_b200_set_initial(mrhyde_b200_plan* P, double time, double* rhs, double* mass_values, void* stream) {
+  ABI_BEGIN
+  if (!P || !rhs || !mass_values) fail(MRHYDE_B200_ERR_INVALID, "set_initial: null argument");
+  if (P->finalized && opt_bool(P, "lump mass", false))
+    fail(MRHYDE_B200_ERR_UNSUPPORTED, "set_initial: the lumped insertion of setInitial (assemblyManager_initial.hpp:100-105) is not built");
+  const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0, 1.0};   // getMass: unit weights
+  int rc = mrhyde_b200_project_initial(P, time, rhs, stream);
+  if (rc != MRHYDE_B200_OK) return rc;
+  int launches = P->launches_per_assemble;
+  rc = mrhyde_b200_assemble_mass(P, ones, 0, mass_values, nullptr, stream);
+  if (rc != MRHYDE_B200_OK) return rc;
+  launches += P->launches_per_assemble;
+  // setInitial fixes empty rows of the mass matrix unconditionally (`bool fix_zero_rows = true`, assemblyManager_initial.hpp:48, 114-131)
+  const int64_t n = P->mesh.nrows;
+  if (n > 0) {
+    fix_zero_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P->d_rowptr.p, P->d_colind.p, n, mass_values);
+    CUDA_OK(cudaGetLastError());
+    ++launches;
+  }
+  P->launches_per_assemble = launches;
+  ABI_END
+}
+
 int mrhyde_b200_plan_debug_emulate_initial(mrhyde_b200_plan* P, double time, double* rhs) {
   ABI_BEGIN
   const double ones[GEN_MAXVARS] = {1.0, 1.0, 1.0, 1.0, 1.0};

@@ -236,6 +236,17 @@ class OracleProblem:
         self._chk(self.L.oracle_weighted_mass(self.h, _p(w, C.c_double), int(lump), _p(M, C.c_double), _p(d, C.c_double)))
         return M, d
 
+    def set_initial(self):
+        """setInitial as a whole (assemblyManager_initial.hpp:36-133): the projection's right-hand side, getMass (unit weights) and the
+        routine's own fix_zero_rows loop (`bool fix_zero_rows = true`, :48, :114-131): rows with sum |M(row,:)| < 1e-14 get M(row,row) = 1."""
+        rhs = self.project_initial()
+        M, _ = self.weighted_mass(np.ones(len(self.var_names())))
+        for row in range(self.num_dofs):
+            a, b = self.rowptr[row], self.rowptr[row + 1]
+            if np.abs(M[a:b]).sum() < 1.0e-14:
+                M[a:b][self.colind[a:b] == row] = 1.0
+        return rhs, M
+
     # ---- evaluation helpers (postprocess-style L2 errors, expression trees) -------------
     def group_info(self, grp, boundary=False):
         n = C.c_int64(0)

@@ -314,3 +314,19 @@ def test_previous_step_and_stage_jacobians(oracle_lib, product_lib, name, seed_w
     plan.debug_emulate(u, res, jac, time=ts)
     assert helpers.rel_err_vec(res, res_ref) < TOL
     assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL
+
+
+def test_set_initial_entry_point_and_oracle_composition(oracle_lib, product_lib):
+    """setInitial as a whole: the oracle's composition (projection, unit-weight mass, fix_zero_rows) against the stage replays of the two
+    kernels it is made of; the device entry point refuses host-only plans like every assemble call (no CPU path)."""
+    from mrhyde_b200.capi import MrhydeB200Error
+    cfg = configs.variant(configs.LE_3D, **{"Physics/Initial conditions": {"dx": "sin(pi*x)*y", "dy": "1.0+z"}})
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, device=-1)
+    rhs_ref, M_ref = op.set_initial()
+    rhs, M, d = np.zeros(op.num_dofs), np.zeros(op.nnz), np.zeros(op.num_dofs)
+    plan.debug_emulate_initial(rhs)
+    plan.debug_emulate_mass(np.ones(3), M, d)
+    assert helpers.rel_err_vec(rhs, rhs_ref) < TOL and helpers.rel_err_rows(M, M_ref, op.rowptr) < TOL   # a mass matrix has no empty row
+    with pytest.raises(MrhydeB200Error):
+        plan.set_initial(rhs, M)

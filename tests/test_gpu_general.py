@@ -246,6 +246,27 @@ def test_previous_step_and_stage_jacobians(oracle_lib, product_lib, name, kernel
     assert helpers.rel_err_rows(jac, jac_ref, op.rowptr) < TOL
 
 
+@pytest.mark.parametrize("name,cfg", [
+    ("le3d", configs.variant(configs.LE_3D, **{"Physics/Initial conditions": {"dx": "sin(pi*x)*y", "dy": "1.0+z"}})),
+    ("maxwell", configs.variant(configs.MAXWELL_3D, **{"Physics/Initial conditions": {"E[x]": "sin(pi*z)", "E[y]": "x*y", "B[z]": "cos(pi*x)+y"}})),
+    ("thermoelastic2d", configs.variant(configs.THERMOELASTIC_2D, **{"Physics/Initial conditions": {"T": "1.0+x*y", "dy": "sin(pi*x)"}}))],
+    ids=["le3d", "maxwell", "thermoelastic2d"])
+def test_set_initial_as_a_whole(oracle_lib, product_lib, name, cfg):
+    """mrhyde_b200_set_initial = setInitial (assemblyManager_initial.hpp:36-133): projection right-hand side, unit-weight mass matrix and
+    the routine's own fix_zero_rows pass, against the oracle's."""
+    import torch
+    op = oracle_lib.OracleProblem(cfg)
+    plan = helpers.plan_from_oracle(op, cfg, options={"kernel": "general"})
+    rhs_ref, M_ref = op.set_initial()
+    dev = torch.device("cuda:0")
+    d_rhs = torch.zeros(op.num_dofs, dtype=torch.float64, device=dev)
+    d_M = torch.zeros(op.nnz, dtype=torch.float64, device=dev)
+    plan.set_initial(d_rhs, d_M)
+    torch.cuda.synchronize()
+    assert np.abs(rhs_ref).max() > 0 and helpers.rel_err_vec(d_rhs.cpu().numpy(), rhs_ref) < TOL
+    assert helpers.rel_err_rows(d_M.cpu().numpy(), M_ref, op.rowptr) < TOL
+
+
 def test_thermoelastic_gold_through_cuda_path(oracle_lib, product_lib):
     """regression/thermoelastic/2D_transient (block "thermal, linearelasticity") assembled on the GPU: the reference's printed L2 norms of T."""
     from test_oracle_golden import _thermoelastic_steps
